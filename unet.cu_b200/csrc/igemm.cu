@@ -1,0 +1,566 @@
+// tcgen05 implicit-GEMM kernels for sm_100a: convolution fprop/dgrad and wgrad on NHWC bf16 operands.
+//
+// Both kernels are warp-specialised:
+//   warp 0   : TMA producer (one elected lane) - stages halo-shifted activation boxes + weight boxes in smem
+//   warp 1   : tcgen05.mma issuer (one elected lane) + TMEM allocator
+//   warps 2-5: epilogue - tcgen05.ld accumulators out of TMEM, fuse bias/emb/residual, store
+// smem stages are handed over with mbarriers (full: TMA complete_tx, empty: tcgen05.commit).
+//
+// Reference behaviour being replaced (not its structure): /root/reference/dev/conv2d_k3.cu:679-740 (forward3),
+// :1132-1174 (dx_backward), :2468-2547 (dweight_dbias_backward1), :1365-1393 (dweight_reduce_kernel).
+#include "igemm.cuh"
+#include "ptx.cuh"
+
+#include <cstdio>
+#include <cstring>
+
+namespace ub {
+
+static constexpr int kMaxStages = 8;
+static constexpr int kConvThreads = 192;
+
+// =====================================================================================================
+// fprop / dgrad / 1x1 / linear
+// =====================================================================================================
+__global__ void __launch_bounds__(kConvThreads) igemm_conv_kernel(const __grid_constant__ IgemmConvParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + size_t(p.stages) * p.stage_bytes);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tmem_full_bar = empty_bar + kMaxStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // tile coordinates
+    int t = blockIdx.x;
+    const int tw = t % p.tiles_w;
+    t /= p.tiles_w;
+    const int th = t % p.tiles_h;
+    const int tb = t / p.tiles_h;
+    const int w0 = tw * p.TW, h0 = th * p.TH, b0 = tb * p.TB;
+    const int n0 = blockIdx.y * p.BN;
+
+    int nk = 0;
+    for (int s = 0; s < p.nseg; ++s) nk += p.seg[s].ntaps * p.seg[s].cblocks;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.nseg; ++s) {
+            tma_prefetch_desc(&p.seg[s].tmA);
+            tma_prefetch_desc(&p.seg[s].tmW);
+        }
+        for (int i = 0; i < p.stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, p.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int s = 0; s < p.nseg; ++s) {
+                const IgemmSeg& sg = p.seg[s];
+                for (int tap = 0; tap < sg.ntaps; ++tap) {
+                    const int dy = sg.ntaps == 9 ? tap / 3 - 1 : 0;
+                    const int dx = sg.ntaps == 9 ? tap % 3 - 1 : 0;
+                    for (int cb = 0; cb < sg.cblocks; ++cb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sA = smem + size_t(stage) * p.stage_bytes;
+                        uint8_t* sB = sA + 16384;
+                        mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
+                        tma_load_4d(sA, &sg.tmA, &full_bar[stage], cb * 64, w0 + dx, h0 + dy, b0);
+                        tma_load_2d(sB, &sg.tmW, &full_bar[stage], cb * 64, tap * p.Cout + n0);
+                        if (++stage == p.stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < nk; ++it) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sA = smem_u32(smem + size_t(stage) * p.stage_bytes);
+                const uint32_t sB = sA + 16384;
+                const uint64_t dA = make_smem_desc_sw128(sA, 16, 1024);
+                const uint64_t dB = make_smem_desc_sw128(sB, 16, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    // advance 16 bf16 (32 B) along K inside the 128-byte swizzle row: +2 in the >>4 address field
+                    umma_bf16(tmem_base, dA + uint64_t(k * 2), dB + uint64_t(k * 2), idesc, (it | k) != 0);
+                }
+                umma_commit(&empty_bar[stage]);
+                if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (warps 2..5)
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        const int row = q * 32 + lane;
+        const int lw = row % p.TW;
+        const int lh = (row / p.TW) % p.TH;
+        const int lb = row / (p.TW * p.TH);
+        const int w = w0 + lw, h = h0 + lh, b = b0 + lb;
+        const bool valid = (lb < p.TB) && (w < p.W) && (h < p.H) && (b < p.B);
+
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+
+        const size_t pix = (size_t(b) * p.H + h) * p.W + w;
+        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c0), v);
+            tmem_ld_wait();
+            if (!valid) continue;
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+            const int n = n0 + c0;
+            if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 bv = *reinterpret_cast<const float4*>(p.bias + n + j);
+                    f[j] += bv.x, f[j + 1] += bv.y, f[j + 2] += bv.z, f[j + 3] += bv.w;
+                }
+            }
+            if (p.rowvec) {
+                const float* rv = p.rowvec + size_t(b) * p.Cout + n;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 bv = *reinterpret_cast<const float4*>(rv + j);
+                    f[j] += bv.x, f[j + 1] += bv.y, f[j + 2] += bv.z, f[j + 3] += bv.w;
+                }
+            }
+            if (p.residual) {
+                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.ldr + n);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint4 r = rp[j];
+                    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
+                        f[j * 8 + i * 2] += __bfloat162float(h2.x);
+                        f[j * 8 + i * 2 + 1] += __bfloat162float(h2.y);
+                    }
+                }
+            }
+            if (p.out_mode == OUT_NHWC_BF16) {
+                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + n;
+                uint32_t pk[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                    pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
+                }
+                reinterpret_cast<uint4*>(op)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                reinterpret_cast<uint4*>(op)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            } else if (p.out_mode == OUT_NHWC_F32) {
+                float* op = reinterpret_cast<float*>(p.out) + pix * p.ldo + n;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {  // OUT_NCHW_F32: a warp writes 32 consecutive pixels of one channel -> coalesced
+                float* op = reinterpret_cast<float*>(p.out) + ((size_t(b) * p.Cout + n) * p.H + h) * p.W + w;
+                const size_t cs = size_t(p.H) * p.W;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) op[j * cs] = f[j];
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// =====================================================================================================
+// wgrad: both operands MN-major (the contraction index is the pixel index, channels are contiguous)
+// =====================================================================================================
+__global__ void __launch_bounds__(kConvThreads) igemm_wgrad_kernel(const __grid_constant__ IgemmWgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + size_t(p.stages) * p.stage_bytes);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tmem_full_bar = empty_bar + kMaxStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int n_ctiles = p.Cin / p.NC;
+    const int o0 = (blockIdx.x / n_ctiles) * p.MO;
+    const int c0 = (blockIdx.x % n_ctiles) * p.NC;
+    const int tap0 = blockIdx.y * p.TC;
+    const int split = blockIdx.z;
+
+    const int ktiles = p.tiles_w * p.tiles_h * p.tiles_b;
+    const int k_begin = int((long long)ktiles * split / p.nsplit);
+    const int k_end = int((long long)ktiles * (split + 1) / p.nsplit);
+    const int a_atoms = p.MO / 64, b_atoms = p.NC / 64;
+    const uint32_t b_off = uint32_t(a_atoms) * 8192u;  // B region offset inside a stage
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmDY);
+        tma_prefetch_desc(&p.tmX);
+        for (int i = 0; i < p.stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, p.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kt = k_begin; kt < k_end; ++kt) {
+                int t = kt;
+                const int w0 = (t % p.tiles_w) * p.TW;
+                t /= p.tiles_w;
+                const int h0 = (t % p.tiles_h) * p.TH;
+                const int b0 = (t / p.tiles_h) * p.TB;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sA = smem + size_t(stage) * p.stage_bytes;
+                uint8_t* sB = sA + b_off;
+                mbar_expect_tx(&full_bar[stage], p.tx_bytes);
+                for (int a = 0; a < a_atoms; ++a)
+                    tma_load_4d(sA + a * 8192, &p.tmDY, &full_bar[stage], o0 + a * 64, w0, h0, b0);
+                for (int ti = 0; ti < p.TC; ++ti) {
+                    const int tap = tap0 + ti;
+                    const int dy = p.ntaps == 9 ? tap / 3 - 1 : 0;
+                    const int dx = p.ntaps == 9 ? tap % 3 - 1 : 0;
+                    for (int nb = 0; nb < b_atoms; ++nb)
+                        tma_load_4d(sB + (ti * b_atoms + nb) * 8192, &p.tmX, &full_bar[stage], c0 + nb * 64, w0 + dx,
+                                    h0 + dy, b0);
+                }
+                if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(p.MO, p.NC, 1, 1);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kt = k_begin; kt < k_end; ++kt) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sA = smem_u32(smem + size_t(stage) * p.stage_bytes);
+                const uint32_t sB = sA + b_off;
+                for (int ti = 0; ti < p.TC; ++ti) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        // 16 pixels (K) per MMA = 16 rows of 128 B = 2048 B; atoms (64 channels) are 8192 B apart
+                        const uint64_t dA = make_smem_desc_sw128(sA + k * 2048, 8192, 1024);
+                        const uint64_t dB = make_smem_desc_sw128(sB + ti * b_atoms * 8192 + k * 2048, 8192, 1024);
+                        umma_bf16(tmem_base + uint32_t(ti * p.NC), dA, dB, idesc, (kt != k_begin) || (k != 0));
+                    }
+                }
+                umma_commit(&empty_bar[stage]);
+                if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {
+        const int q = warp & 3;
+        // M=128: accumulator row m lives in TMEM lane m.  M=64: row m lives in lane (m%16) + 32*(m/16).
+        int row;
+        bool valid;
+        if (p.MO == 128) {
+            row = q * 32 + lane;
+            valid = true;
+        } else {
+            row = q * 16 + lane;
+            valid = lane < 16;
+        }
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        if (k_end > k_begin) {
+            for (int ti = 0; ti < p.TC; ++ti) {
+                const int tap = tap0 + ti;
+                float* dst = p.partial + ((size_t(split) * p.ntaps + tap) * p.Cout + (o0 + row)) * p.Cin + c0;
+                for (int cc = 0; cc < p.NC; cc += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(ti * p.NC + cc), v);
+                    tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4)
+                            *reinterpret_cast<float4*>(dst + cc + j) =
+                                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                            __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// dweight[o][c][tap] = sum_split partial[split][tap][o][c]   (deterministic order)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dweight, int nsplit,
+                                    int ntaps, int Cout, int Cin) {
+    const size_t n = size_t(Cout) * Cin;
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;  // (o, c) index
+    if (i >= n) return;
+    for (int tap = 0; tap < ntaps; ++tap) {
+        float s = 0.f;
+        for (int sp = 0; sp < nsplit; ++sp) s += partial[(size_t(sp) * ntaps + tap) * n + i];
+        dweight[i * ntaps + tap] = s;
+    }
+}
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) {
+            fprintf(stderr, "[unet_b200] cuTensorMapEncodeTiled unavailable (%d)\n", int(e));
+            return nullptr;
+        }
+        fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// NHWC bf16 activation map: dims (C, W, H, B), channel pitch ld, box (64, TW, TH, TB), 128B swizzle, zero OOB fill.
+static int make_act_map(CUtensorMap* m, const __nv_bfloat16* x, int C, int ld, int W, int H, int B, int TW, int TH,
+                        int TB) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return -10;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (ld % 8) != 0) return -11;
+    cuuint64_t dims[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(B)};
+    cuuint64_t strides[3] = {cuuint64_t(ld) * 2, cuuint64_t(W) * ld * 2, cuuint64_t(H) * W * ld * 2};
+    cuuint32_t box[4] = {64, cuuint32_t(TW), cuuint32_t(TH), cuuint32_t(TB)};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(x), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "[unet_b200] cuTensorMapEncodeTiled(act C=%d ld=%d W=%d H=%d B=%d box=%d,%d,%d) -> %d\n", C, ld,
+                W, H, B, TW, TH, TB, int(r));
+        return -12;
+    }
+    return 0;
+}
+
+static int make_weight_map(CUtensorMap* m, const __nv_bfloat16* wp, int Cin, int rows, int BN) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return -10;
+    if ((reinterpret_cast<uintptr_t>(wp) & 15) || (Cin % 8) != 0) return -13;
+    cuuint64_t dims[2] = {cuuint64_t(Cin), cuuint64_t(rows)};
+    cuuint64_t strides[1] = {cuuint64_t(Cin) * 2};
+    cuuint32_t box[2] = {64, cuuint32_t(BN)};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(wp), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "[unet_b200] cuTensorMapEncodeTiled(weight Cin=%d rows=%d BN=%d) -> %d\n", Cin, rows, BN,
+                int(r));
+        return -14;
+    }
+    return 0;
+}
+
+static int next_pow2(int v) {
+    int r = 1;
+    while (r < v) r <<= 1;
+    return r;
+}
+static int ceil_div_i(int a, int b) { return (a + b - 1) / b; }
+
+static constexpr int kBarrierBytes = 256;
+
+int igemm_conv_plan(IgemmConvParams* p, const ConvSegDesc* segs, int nseg, int B, int H, int W, int Cout,
+                    const ConvEpilogue& ep) {
+    memset(p, 0, sizeof(*p));
+    if (nseg < 1 || nseg > 2) return -1;
+    if (Cout % 16 != 0) return -2;
+    // output-channel tile: the largest divisor of Cout that is a multiple of 16 and <= 256
+    int BN = 0;
+    for (int cand = 256; cand >= 16; cand -= 16)
+        if (Cout % cand == 0) {
+            BN = cand;
+            break;
+        }
+    if (!BN) return -2;
+    p->nseg = nseg;
+    p->B = B, p->H = H, p->W = W, p->Cout = Cout, p->BN = BN;
+    p->TW = W < 128 ? W : 128;
+    p->TH = H < 128 / p->TW ? H : 128 / p->TW;
+    if (p->TH < 1) p->TH = 1;
+    p->TB = B < 128 / (p->TW * p->TH) ? B : 128 / (p->TW * p->TH);
+    if (p->TB < 1) p->TB = 1;
+    p->tiles_w = ceil_div_i(W, p->TW);
+    p->tiles_h = ceil_div_i(H, p->TH);
+    p->tiles_b = ceil_div_i(B, p->TB);
+    p->tmem_cols = next_pow2(BN < 32 ? 32 : BN);
+    p->a_bytes = uint32_t(64 * p->TW * p->TH * p->TB * 2);
+    p->b_bytes = uint32_t(64 * BN * 2);
+    p->stage_bytes = 16384u + ((p->b_bytes + 1023u) & ~1023u);
+    // Two CTAs per SM when possible (one CTA's epilogue overlaps the other's main loop): <= ~110 KiB each.
+    int stages = int((110u * 1024u) / p->stage_bytes);
+    if (stages < 3) stages = int((220u * 1024u) / p->stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) return -3;
+    p->stages = stages;
+    for (int s = 0; s < nseg; ++s) {
+        const ConvSegDesc& d = segs[s];
+        if (d.ntaps != 9 && d.ntaps != 1) return -4;
+        if (d.Cin % 8 != 0) return -5;
+        int r = make_act_map(&p->seg[s].tmA, d.x, d.Cin, d.ldx, W, H, B, p->TW, p->TH, p->TB);
+        if (r) return r;
+        r = make_weight_map(&p->seg[s].tmW, d.wp, d.Cin, d.ntaps * Cout, BN);
+        if (r) return r;
+        p->seg[s].cblocks = ceil_div_i(d.Cin, 64);
+        p->seg[s].ntaps = d.ntaps;
+    }
+    p->bias = ep.bias;
+    p->rowvec = ep.rowvec;
+    p->residual = ep.residual;
+    p->ldr = ep.ldr ? ep.ldr : Cout;
+    p->out = ep.out;
+    p->ldo = ep.ldo ? ep.ldo : Cout;
+    p->out_mode = ep.out_mode;
+    if (p->out_mode != OUT_NCHW_F32) {
+        const int esz = p->out_mode == OUT_NHWC_BF16 ? 2 : 4;
+        if ((p->ldo * esz) % 16 != 0 || (reinterpret_cast<uintptr_t>(p->out) & 15)) return -6;
+    }
+    if (p->residual && ((p->ldr % 8) != 0 || (reinterpret_cast<uintptr_t>(p->residual) & 15))) return -7;
+    if (p->bias && (reinterpret_cast<uintptr_t>(p->bias) & 15)) return -8;
+    if (p->rowvec && ((reinterpret_cast<uintptr_t>(p->rowvec) & 15) || (Cout % 4) != 0)) return -8;
+    return 0;
+}
+
+int igemm_conv_launch(const IgemmConvParams& p, cudaStream_t st) {
+    const size_t smem = size_t(p.stages) * p.stage_bytes + 1024 + kBarrierBytes;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e =
+            cudaFuncSetAttribute(igemm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(227 * 1024));
+        if (e != cudaSuccess) return int(e);
+        configured = 227 * 1024;
+    }
+    dim3 grid(p.tiles_w * p.tiles_h * p.tiles_b, p.Cout / p.BN);
+    igemm_conv_kernel<<<grid, kConvThreads, smem, st>>>(p);
+    return int(cudaGetLastError());
+}
+
+size_t igemm_wgrad_partial_floats(int Cin, int Cout, int ntaps, int nsplit) {
+    return size_t(nsplit) * ntaps * Cout * Cin;
+}
+
+int igemm_wgrad_plan(IgemmWgradParams* p, const __nv_bfloat16* dy, int ldy, const __nv_bfloat16* x, int ldx, int B,
+                     int H, int W, int Cin, int Cout, int ntaps, float* partial, size_t partial_cap_floats,
+                     int sm_count) {
+    memset(p, 0, sizeof(*p));
+    if (ntaps != 9 && ntaps != 1) return -4;
+    if (Cin % 64 != 0 || Cout % 64 != 0) return -5;
+    p->B = B, p->H = H, p->W = W, p->Cin = Cin, p->Cout = Cout, p->ntaps = ntaps;
+    // K tile = 64 pixels; boxes may overhang the image (TMA zero-fills), they must hold exactly 64 pixels
+    p->TW = next_pow2(W) < 64 ? next_pow2(W) : 64;
+    p->TH = next_pow2(H) < 64 / p->TW ? next_pow2(H) : 64 / p->TW;
+    p->TB = 64 / (p->TW * p->TH);
+    p->tiles_w = ceil_div_i(W, p->TW);
+    p->tiles_h = ceil_div_i(H, p->TH);
+    p->tiles_b = ceil_div_i(B, p->TB);
+    p->MO = (Cout % 128 == 0) ? 128 : 64;
+    p->TC = ntaps == 9 ? 3 : 1;
+    // TMEM: TC * NC columns <= 512
+    p->NC = (Cin % 128 == 0) ? 128 : 64;
+    p->tmem_cols = next_pow2(p->TC * p->NC < 32 ? 32 : p->TC * p->NC);
+    const int a_atoms = p->MO / 64, b_atoms = p->NC / 64;
+    p->stage_bytes = uint32_t(a_atoms + p->TC * b_atoms) * 8192u;
+    p->tx_bytes = p->stage_bytes;
+    int stages = int((200u * 1024u) / p->stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) return -3;
+    p->stages = stages;
+    const int ktiles = p->tiles_w * p->tiles_h * p->tiles_b;
+    const int base_ctas = (Cout / p->MO) * (Cin / p->NC) * (ntaps / p->TC);
+    int nsplit = ceil_div_i(2 * sm_count, base_ctas);  // aim at ~2 waves of CTAs
+    if (nsplit > ktiles / 4) nsplit = ktiles / 4;      // at least 4 K tiles per CTA
+    if (nsplit < 1) nsplit = 1;
+    while (nsplit > 1 && igemm_wgrad_partial_floats(Cin, Cout, ntaps, nsplit) > partial_cap_floats) --nsplit;
+    if (igemm_wgrad_partial_floats(Cin, Cout, ntaps, nsplit) > partial_cap_floats) return -9;
+    p->nsplit = nsplit;
+    p->partial = partial;
+    int r = make_act_map(&p->tmDY, dy, Cout, ldy, W, H, B, p->TW, p->TH, p->TB);
+    if (r) return r;
+    r = make_act_map(&p->tmX, x, Cin, ldx, W, H, B, p->TW, p->TH, p->TB);
+    return r;
+}
+
+int igemm_wgrad_launch(const IgemmWgradParams& p, cudaStream_t st) {
+    const size_t smem = size_t(p.stages) * p.stage_bytes + 1024 + kBarrierBytes;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e =
+            cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(227 * 1024));
+        if (e != cudaSuccess) return int(e);
+        configured = true;
+    }
+    dim3 grid((p.Cout / p.MO) * (p.Cin / p.NC), p.ntaps / p.TC, p.nsplit);
+    igemm_wgrad_kernel<<<grid, kConvThreads, smem, st>>>(p);
+    return int(cudaGetLastError());
+}
+
+int igemm_wgrad_reduce(const IgemmWgradParams& p, float* dweight, cudaStream_t st) {
+    const size_t n = size_t(p.Cout) * p.Cin;
+    wgrad_reduce_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(p.partial, dweight, p.nsplit, p.ntaps, p.Cout,
+                                                                    p.Cin);
+    return int(cudaGetLastError());
+}
+
+}  // namespace ub

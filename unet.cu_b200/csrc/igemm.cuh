@@ -1,0 +1,97 @@
+// Parameter blocks + host launch API of the tcgen05 implicit-GEMM kernels (NHWC bf16 operands).
+//
+//   igemm_conv : fprop AND dgrad of 3x3 (pad 1, stride 1) / 1x1 convolutions and Linear layers
+//                D[pix, n] = sum_seg sum_tap sum_c  A_seg[pix + shift(tap), c] * Wp_seg[tap][n][c]
+//                replaces conv2d_k3_forward3 / dx_backward (/root/reference/dev/conv2d_k3.cu:679,1132),
+//                conv2d_k1_forward2 (dev/conv2d_k1.cu:215) and matmul_forward2 (dev/linear.cu).
+//   igemm_wgrad: weight gradient  dW[tap][o][c] = sum_pix dY[pix, o] * X[pix + shift(tap), c]
+//                replaces dweight_dbias_backward1 + dweight_reduce_kernel (dev/conv2d_k3.cu:2468,1365).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace ub {
+
+enum OutMode : int {
+    OUT_NHWC_BF16 = 0,  // out[((b*H+h)*W+w)*ldo + n]  bf16   (internal layout)
+    OUT_NCHW_F32 = 1,   // out[((b*Cout+n)*H+h)*W+w]   fp32   (reference API layout)
+    OUT_NHWC_F32 = 2,   // out[((b*H+h)*W+w)*ldo + n]  fp32
+};
+
+struct IgemmSeg {
+    CUtensorMap tmA;  // activations NHWC bf16, dims (C, W, H, B), box (64, TW, TH, TB), SWIZZLE_128B
+    CUtensorMap tmW;  // packed weights [ntaps*Cout][Cin] bf16, dims (Cin, ntaps*Cout), box (64, BN), SWIZZLE_128B
+    int cblocks;      // ceil(Cin / 64)
+    int ntaps;        // 9 or 1
+};
+
+struct IgemmConvParams {
+    IgemmSeg seg[2];
+    int nseg;
+    int B, H, W, Cout;
+    int TW, TH, TB;  // pixel tile (TW*TH*TB <= 128)
+    int tiles_w, tiles_h, tiles_b;
+    int BN;          // output-channel tile: multiple of 16, <= 256
+    int stages;
+    int tmem_cols;   // power of two >= max(32, BN)
+    uint32_t a_bytes, b_bytes;  // TMA transaction bytes per stage
+    uint32_t stage_bytes;       // smem bytes per stage (A tile 16 KiB + B tile, 1024-aligned)
+    // epilogue
+    const float* bias;             // [Cout] or nullptr
+    const float* rowvec;           // [B][Cout] per-image additive vector (time-embedding) or nullptr
+    const __nv_bfloat16* residual; // NHWC bf16 [B,H,W,ldr] added to the output, or nullptr
+    int ldr;
+    void* out;
+    int ldo;  // channel pitch of an NHWC output (>= Cout; lets a producer write into a concat buffer)
+    int out_mode;
+};
+
+struct IgemmWgradParams {
+    CUtensorMap tmDY;  // dY NHWC bf16 dims (Cout, W, H, B), box (64, TW, TH, TB), TW*TH*TB == 64
+    CUtensorMap tmX;   // X  NHWC bf16 dims (Cin,  W, H, B), same box
+    int B, H, W, Cin, Cout, ntaps;
+    int TW, TH, TB;
+    int tiles_w, tiles_h, tiles_b;
+    int MO;      // Cout tile: 64 or 128
+    int NC;      // Cin tile: multiple of 64, <= 256
+    int TC;      // taps per CTA: 3 (one filter row) or 1
+    int nsplit;  // split of the pixel (K) dimension across CTAs
+    int stages;
+    int tmem_cols;
+    uint32_t stage_bytes, tx_bytes;
+    float* partial;  // [nsplit][ntaps][Cout][Cin] fp32
+};
+
+// ---- host API (implemented in igemm.cu); all return cudaError_t-like int (0 == ok) -------------------------
+struct ConvSegDesc {
+    const __nv_bfloat16* x;  // NHWC bf16 [B,H,W,ldx]; channels [0,Cin) are used
+    int Cin;
+    int ldx;                   // channel pitch of x
+    const __nv_bfloat16* wp;   // packed [ntaps][Cout][Cin] bf16
+    int ntaps;
+};
+struct ConvEpilogue {
+    const float* bias = nullptr;
+    const float* rowvec = nullptr;
+    const __nv_bfloat16* residual = nullptr;
+    int ldr = 0;
+    void* out = nullptr;
+    int ldo = 0;
+    int out_mode = OUT_NHWC_BF16;
+};
+// Fills `p` (tensor maps + tiling). Returns 0 or a negative error code (unsupported shape).
+int igemm_conv_plan(IgemmConvParams* p, const ConvSegDesc* segs, int nseg, int B, int H, int W, int Cout,
+                    const ConvEpilogue& ep);
+int igemm_conv_launch(const IgemmConvParams& p, cudaStream_t st);
+
+int igemm_wgrad_plan(IgemmWgradParams* p, const __nv_bfloat16* dy, int ldy, const __nv_bfloat16* x, int ldx, int B,
+                     int H, int W, int Cin, int Cout, int ntaps, float* partial, size_t partial_cap_floats,
+                     int sm_count);
+int igemm_wgrad_launch(const IgemmWgradParams& p, cudaStream_t st);
+// dW (reference layout [Cout][Cin][ntaps], fp32) = sum over splits of partial[split][tap][o][c]; overwrite.
+int igemm_wgrad_reduce(const IgemmWgradParams& p, float* dweight, cudaStream_t st);
+size_t igemm_wgrad_partial_floats(int Cin, int Cout, int ntaps, int nsplit);
+
+}  // namespace ub
