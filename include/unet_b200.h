@@ -1,0 +1,207 @@
+/* unet_b200.h -- C ABI of the B200-native U-Net diffusion training path.
+ *
+ * Two groups of entry points:
+ *
+ *  (1) Layer operators: drop-in replacements of the launchers declared in the reference's dev/\*.cuh
+ *      (same argument order and meaning, device pointers to fp32 NCHW / (N,C) buffers, int shapes).  The C symbols
+ *      carry a `ub_` prefix so that they can be linked next to the reference objects; include/unet_b200_legacy.hpp
+ *      re-exposes the exact reference C++ signatures (including the ignored cublasHandle_t / block_size / t1..t6
+ *      arguments) as inline wrappers.  Every function returns 0 on success or a non-zero error code instead of
+ *      calling exit() (reference convention: utils.cuh:24-41 cudaCheck -> exit(EXIT_FAILURE)).
+ *      All layer calls run on the stream set by ub_set_stream() (default: the legacy default stream, like the
+ *      reference which never names a stream).
+ *
+ *  (2) Trainer: the model graph + optimizer + checkpoint path of train_unet.cu (unet_forward / unet_backward /
+ *      unet_update / save_unet_states / load_unet_and_diffusion_states, train_unet.cu:4335-4911) behind an opaque
+ *      handle, with batch data parallelism over NCCL.
+ *
+ * Each declaration cites the reference interface it replaces (paths under /root/reference).
+ */
+#ifndef UNET_B200_H
+#define UNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UB_OK 0
+#define UB_ERR_SHAPE (-1)   /* unsupported shape / violated precondition (reference: device/host assert) */
+#define UB_ERR_CUDA (-2)    /* a CUDA runtime call failed; see ub_last_error() */
+#define UB_ERR_IO (-3)      /* file error */
+#define UB_ERR_STATE (-4)   /* call sequence error (e.g. update before backward) */
+#define UB_ERR_NCCL (-5)
+
+const char* ub_last_error(void);
+const char* ub_version(void);
+/* stream used by the layer operators; `stream` is a cudaStream_t */
+int ub_set_stream(void* stream);
+/* number of kernels launched by this library since process start (bench.py's gpu_launches) */
+unsigned long long ub_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (1) Layer operators
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* dev/conv2d_k3.cuh:17-21  conv2d_k3_forward3(x, weight, bias, out, B, C_in, C_out, H, W)
+ * 3x3, pad 1, stride 1.  x (B,C_in,H,W), weight (C_out,C_in,3,3), bias (C_out), out (B,C_out,H,W).
+ * BF16 tensor-core path (fp32 accumulate) when C_in % 8 == 0 and C_out % 16 == 0, exact fp32 SIMT otherwise
+ * (C_in = 3 or C_out = 3). */
+int ub_conv2d_k3_forward3(const float* x, const float* weight, const float* bias, float* out, int B, int C_in,
+                          int C_out, int H, int W);
+/* dev/conv2d_k3.cuh:8-15  conv2d_k3_forward2 -- superseded generation, same maths; alias of forward3 */
+int ub_conv2d_k3_forward2(const float* x, const float* weight, const float* bias, float* out, int B, int C_in,
+                          int C_out, int H, int W);
+/* dev/conv2d_k3.cuh:33-38  conv2d_k3_backward2(dout, x, weight, dweight_buf, dbias_buf, dx, dweight, dbias, ...)
+ * dx, dweight, dbias are overwritten.  dweight_buf / dbias_buf (the reference's split-K scratch) are accepted and
+ * ignored: the library keeps its own workspace.  dx may be NULL (first layer). */
+int ub_conv2d_k3_backward2(const float* dout, const float* x, const float* weight, float* dweight_buf,
+                           float* dbias_buf, float* dx, float* dweight, float* dbias, int B, int C_in, int C_out,
+                           int H, int W);
+/* dev/conv2d_k3.cuh:23-31  conv2d_k3_backward1 -- superseded generation; alias of backward2 */
+int ub_conv2d_k3_backward1(const float* dout, const float* x, const float* weight, float* dx, float* dweight,
+                           float* dbias, int B, int C_in, int C_out, int H, int W);
+
+/* dev/conv2d_k1.cuh:15-19  conv2d_k1_forward2(x, weight, bias, out, B, C_in, H, W, C_out) */
+int ub_conv2d_k1_forward2(const float* x, const float* weight, const float* bias, float* out, int B, int C_in, int H,
+                          int W, int C_out);
+/* dev/conv2d_k1.cuh:6-13 conv2d_k1_forward1(cublas, out, x, weight, bias, B, C_in, H, W, C_out, ...) alias */
+int ub_conv2d_k1_forward1(float* out, const float* x, const float* weight, const float* bias, int B, int C_in, int H,
+                          int W, int C_out);
+/* dev/conv2d_k1.cuh:21-27  conv2d_k1_backward1(cublas, dout, x, weight, dx, dweight, dbias, B, C_in, C_out, H, W) */
+int ub_conv2d_k1_backward1(const float* dout, const float* x, const float* weight, float* dx, float* dweight,
+                           float* dbias, int B, int C_in, int C_out, int H, int W);
+
+/* dev/linear.cuh:5-11  matmul_forward2(cublas, out, inp, weight, bias, N, C, OC, block_size)
+ * out (N,OC) = inp (N,C) . weight (OC,C)^T + bias */
+int ub_matmul_forward2(float* out, const float* inp, const float* weight, const float* bias, int N, int C, int OC);
+/* dev/linear.cuh:13-18  matmul_backward1(cublas, dinp, dweight, dbias, dout, inp, weight, N, C, OC); overwrite */
+int ub_matmul_backward1(float* dinp, float* dweight, float* dbias, const float* dout, const float* inp,
+                        const float* weight, int N, int C, int OC);
+
+/* dev/groupnorm.cuh:3-7   groupnorm_forward(x, weight, bias, out, mean, rstd, B, C, H, W, n_groups); eps 1e-5 */
+int ub_groupnorm_forward(const float* x, const float* weight, const float* bias, float* out, float* mean,
+                         float* rstd, int B, int C, int H, int W, int n_groups);
+/* dev/groupnorm.cuh:9-13  groupnorm_backward(...): dx overwritten; dweight/dbias ACCUMULATED (reference uses
+ * atomicAdd into them, train_unet.cu:1926-1991) */
+int ub_groupnorm_backward(const float* dout, const float* x, const float* mean, const float* rstd,
+                          const float* weight, float* dx, float* dweight, float* dbias, int B, int C, int H, int W,
+                          int n_groups);
+
+/* dev/silu.cuh:3-13 */
+int ub_silu_forward(const float* x, float* out, int N);
+int ub_silu_backward(const float* dout, const float* x, float* dx, int N);
+
+/* dev/add.cuh:3-13 */
+int ub_add_forward(const float* a, const float* b, float* out, int N);
+int ub_add_inplace_forward(const float* a, float* b, int N); /* b += a */
+
+/* dev/upsample.cuh:3-15 (x is (B,C,H,W), out (B,C,2H,2W)) ; dev/avgpool.cuh:4-16 (x (B,C,H,W), out (B,C,H/2,W/2)) */
+int ub_upsample_forward1(float* out, const float* x, int B, int C, int H, int W);
+int ub_upsample_backward1(float* dx, const float* dout, int B, int C, int H, int W);
+int ub_avgpool_2d_forward1(float* out, const float* x, int B, int C, int H, int W);
+int ub_avgpool_2d_backward1(const float* dout, float* dx, int B, int C, int H, int W);
+
+/* dev/concat_channel.cuh:4-15 */
+int ub_concat_channel_forward(const float* x1, const float* x2, float* out, int B, int C1, int C2, int H, int W);
+int ub_concat_channel_backward(const float* dout, float* dx1, float* dx2, int B, int C1, int C2, int H, int W);
+
+/* dev/broadcast.cuh:4-14: x (N) -> out (N,H,W); backward sums over the last two dims */
+int ub_broadcast_last_dims_forward(const float* x, float* out, int N, int H, int W);
+int ub_broadcast_last_dims_backward(const float* dout, float* dx, int N, int H, int W);
+
+/* dev/mse.cuh:1-3: loss is a device pointer to one float (overwritten) */
+int ub_mse_forward(const float* inp, const float* y, float* loss, int N);
+int ub_mse_backward(const float* inp, const float* y, float* dinp, int N);
+
+/* dev/timestep_embedding.cuh:8-14 (freqs table is recomputed on the fly; no init/free needed) */
+int ub_get_timestep_embeddings(const float* timesteps, float* out, int B, int dim, int max_period);
+
+/* dev/attention.cuh:6-13  attention_forward1(cublas, out, qkvr, preatt, att, inp, B, T, C, NH, block_size)
+ * inp (B,T,3C) in (B,T,3,NH,HS) order; out (B,T,C).  qkvr (3,B,NH,T,HS), preatt and att (B,NH,T,T) are filled as
+ * the reference does (att = softmax probabilities, needed by attention_backward). fp32. */
+int ub_attention_forward1(float* out, float* qkvr, float* preatt, float* att, const float* inp, int B, int T, int C,
+                          int NH);
+/* dev/attention.cuh:15-22  attention_backward(cublas, dinp, dqkvr, dpreatt, datt, scratch, dout, qkvr, att, ...) */
+int ub_attention_backward(float* dinp, float* dqkvr, float* dpreatt, float* datt, float* scratch, const float* dout,
+                          const float* qkvr, const float* att, int B, int T, int C, int NH);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (2) Trainer
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct UbTrainer UbTrainer;
+
+/* UnetConfig of train_unet.cu:3318-3336 (+ the literals hard-coded at :4842-4864), generalised. */
+typedef struct {
+    int B;               /* per-GPU batch */
+    int C_in, C_model, C_out;
+    int H, W;
+    int max_period;      /* 1000 */
+    int n_levels;        /* 4 */
+    int channel_mult[8]; /* {1,2,3,4} */
+    int n_res_blocks;    /* 2 */
+    int att_start_level; /* 2 : attention at levels >= this */
+    int head_size;       /* 32 */
+    int gn_n_groups;     /* 32 */
+    int n_timesteps;     /* 1000, linear beta schedule 1e-4 .. 0.02 (train_unet.cu:3131-3147) */
+    unsigned long long seed;
+    int use_cuda_graph;  /* capture the whole step in one CUDA graph */
+} UbConfig;
+
+void ub_default_config(UbConfig* cfg);
+/* number of parameters for a config (326 tensors / 20 494 211 floats for the default) */
+size_t ub_num_params(const UbConfig* cfg);
+
+int ub_trainer_create(UbTrainer** out, const UbConfig* cfg, int device);
+void ub_trainer_destroy(UbTrainer* t);
+
+/* checkpoint, train_unet.cu:4762-4911 / train_unet.py:768-795: int32[256] header {12345678, B, C_in, C_model, C_out,
+ * H, W, max_period, has_adamw, has_rng} + fp32 params [+ m + v].  The rng flag is always written 0 (the reference's
+ * blob is a raw curandState dump); header[10] additionally stores the AdamW step count (the reference forgets it). */
+int ub_trainer_load(UbTrainer* t, const char* path);
+int ub_trainer_save(UbTrainer* t, const char* path, int with_adamw);
+/* read the {B, C_in, C_model, C_out, H, W, max_period} header of a checkpoint into cfg (other fields untouched) */
+int ub_read_checkpoint_header(const char* path, UbConfig* cfg);
+
+/* host <-> device parameter access, reference parameter order (forward layer order) */
+int ub_trainer_set_params(UbTrainer* t, const float* host, size_t n);
+int ub_trainer_get_params(UbTrainer* t, float* host, size_t n);
+int ub_trainer_get_grads(UbTrainer* t, float* host, size_t n);
+int ub_trainer_get_output(UbTrainer* t, float* host, size_t n); /* last forward's eps prediction (B,C_out,H,W) */
+int ub_trainer_get_dinput(UbTrainer* t, float* host, size_t n); /* not computed: returns UB_ERR_STATE */
+
+/* One forward + backward (unet_forward + unet_backward, train_unet.cu:4335-4701) on a HOST batch x0 (B,C_in,H,W).
+ * t_host (B) and noise_host (B,C_in,H,W) may be NULL: then timesteps / noise are drawn on the device (Philox).
+ * Gradients are left in the gradient arena (all-reduced over the data-parallel group if one is attached).
+ * loss_out receives the mean-squared error (device->host copy of 4 bytes). */
+int ub_trainer_forward_backward(UbTrainer* t, const float* x0_host, const float* t_host, const float* noise_host,
+                                float* loss_out);
+/* unet_update (train_unet.cu:4738-4757): AdamW with bias correction; zeroes the gradients. */
+int ub_trainer_update(UbTrainer* t, float lr, float beta1, float beta2, float eps, float weight_decay);
+/* The whole loop body of train_unet.cu:5019-5037 in one call (one CUDA-graph launch when enabled):
+ * H2D batch copy, timesteps/noise, q-sample, forward, loss, backward, gradient all-reduce, AdamW.  loss_out may be
+ * NULL (then no device->host copy / sync happens; use ub_trainer_sync + ub_trainer_last_loss). */
+int ub_trainer_train_step(UbTrainer* t, const float* x0_host, const float* t_host, const float* noise_host, float lr,
+                          float beta1, float beta2, float eps, float weight_decay, float* loss_out);
+/* Same step with the batch already resident on the device (bench.py's device-resident `value`). */
+int ub_trainer_train_step_device(UbTrainer* t, const float* x0_dev, float lr, float beta1, float beta2, float eps,
+                                 float weight_decay);
+int ub_trainer_sync(UbTrainer* t);
+int ub_trainer_last_loss(UbTrainer* t, float* loss_out);
+void* ub_trainer_stream(UbTrainer* t); /* cudaStream_t the trainer launches on */
+/* kernels launched per train step (counted while building the step) */
+int ub_trainer_launches_per_step(UbTrainer* t);
+/* forward only on a device batch that is ALREADY x_t (for sampling, generate.py:29-52): out_dev (B,C_out,H,W) */
+int ub_trainer_predict(UbTrainer* t, const float* xt_host, const float* t_host, float* out_host);
+
+/* ---- data parallel: one process per GPU; rank 0 creates the id, everyone attaches ---- */
+#define UB_NCCL_ID_BYTES 128
+int ub_nccl_get_unique_id(void* id_out /* UB_NCCL_ID_BYTES */);
+int ub_trainer_attach_dp(UbTrainer* t, int rank, int world, const void* nccl_id, int n_buckets);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNET_B200_H */

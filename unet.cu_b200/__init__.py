@@ -1,0 +1,230 @@
+"""unet.cu_b200 -- Python host-side mirror of the C ABI in include/unet_b200.h (ctypes, no torch types in any
+signature).  The shared library is built in-tree by `__graft_entry__.build()` / `make -C unet.cu_b200`.
+
+The package fails loudly when the CUDA extension is missing: there is no CPU fallback.
+
+Because the directory name contains a dot it is loaded with importlib (see __graft_entry__.load_package()).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libunet_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "unet_b200.h")
+
+UB_NCCL_ID_BYTES = 128
+
+
+class UbConfig(C.Structure):
+    """UbConfig of include/unet_b200.h (UnetConfig of train_unet.cu:3318-3336, generalised)."""
+    _fields_ = [("B", C.c_int), ("C_in", C.c_int), ("C_model", C.c_int), ("C_out", C.c_int), ("H", C.c_int),
+                ("W", C.c_int), ("max_period", C.c_int), ("n_levels", C.c_int), ("channel_mult", C.c_int * 8),
+                ("n_res_blocks", C.c_int), ("att_start_level", C.c_int), ("head_size", C.c_int),
+                ("gn_n_groups", C.c_int), ("n_timesteps", C.c_int), ("seed", C.c_ulonglong),
+                ("use_cuda_graph", C.c_int)]
+
+
+class UbError(RuntimeError):
+    pass
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    """Load libunet_b200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise UbError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(the CUDA extension is mandatory, there is no CPU path)")
+        _lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        _declare(_lib)
+    return _lib
+
+
+def _declare(L: C.CDLL) -> None:
+    fp, vp, i = C.c_void_p, C.c_void_p, C.c_int
+    L.ub_last_error.restype = C.c_char_p
+    L.ub_version.restype = C.c_char_p
+    L.ub_launch_count.restype = C.c_ulonglong
+    L.ub_set_stream.argtypes = [vp]
+    L.ub_default_config.argtypes = [C.POINTER(UbConfig)]
+    L.ub_default_config.restype = None
+    L.ub_num_params.argtypes = [C.POINTER(UbConfig)]
+    L.ub_num_params.restype = C.c_size_t
+    L.ub_trainer_create.argtypes = [C.POINTER(vp), C.POINTER(UbConfig), i]
+    L.ub_trainer_destroy.argtypes = [vp]
+    L.ub_trainer_destroy.restype = None
+    L.ub_trainer_load.argtypes = [vp, C.c_char_p]
+    L.ub_trainer_save.argtypes = [vp, C.c_char_p, i]
+    L.ub_read_checkpoint_header.argtypes = [C.c_char_p, C.POINTER(UbConfig)]
+    for n in ("set_params", "get_params", "get_grads", "get_output", "get_dinput"):
+        getattr(L, "ub_trainer_" + n).argtypes = [vp, fp, C.c_size_t]
+    L.ub_trainer_forward_backward.argtypes = [vp, fp, fp, fp, C.POINTER(C.c_float)]
+    L.ub_trainer_update.argtypes = [vp] + [C.c_float] * 5
+    L.ub_trainer_train_step.argtypes = [vp, fp, fp, fp] + [C.c_float] * 5 + [C.POINTER(C.c_float)]
+    L.ub_trainer_train_step_device.argtypes = [vp, fp] + [C.c_float] * 5
+    L.ub_trainer_sync.argtypes = [vp]
+    L.ub_trainer_last_loss.argtypes = [vp, C.POINTER(C.c_float)]
+    L.ub_trainer_stream.argtypes = [vp]
+    L.ub_trainer_stream.restype = vp
+    L.ub_trainer_launches_per_step.argtypes = [vp]
+    L.ub_trainer_predict.argtypes = [vp, fp, fp, fp]
+    L.ub_nccl_get_unique_id.argtypes = [vp]
+    L.ub_trainer_attach_dp.argtypes = [vp, i, i, vp, i]
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise UbError(f"{what} failed with code {rc}: {lib().ub_last_error().decode()}")
+
+
+def default_config(**over) -> UbConfig:
+    cfg = UbConfig()
+    lib().ub_default_config(C.byref(cfg))
+    for k, v in over.items():
+        if k == "channel_mult":
+            for j, m in enumerate(v):
+                cfg.channel_mult[j] = int(m)
+            cfg.n_levels = len(v)
+        else:
+            setattr(cfg, k, v)
+    return cfg
+
+
+def num_params(cfg: UbConfig) -> int:
+    return int(lib().ub_num_params(C.byref(cfg)))
+
+
+def _ptr(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Trainer:
+    """Mirror of the train_unet.cu loop body (train_unet.cu:5019-5037) over host (numpy) buffers."""
+
+    def __init__(self, cfg: Optional[UbConfig] = None, device: int = 0, **over):
+        self.cfg = cfg if cfg is not None else default_config(**over)
+        self._h = C.c_void_p()
+        check(lib().ub_trainer_create(C.byref(self._h), C.byref(self.cfg), device), "ub_trainer_create")
+        self.nparams = num_params(self.cfg)
+
+    def close(self):
+        if self._h:
+            lib().ub_trainer_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- parameters / checkpoints
+    def set_params(self, flat: np.ndarray):
+        flat = np.ascontiguousarray(flat, dtype=np.float32)
+        check(lib().ub_trainer_set_params(self._h, _ptr(flat), flat.size), "set_params")
+
+    def _get(self, fn, n):
+        out = np.empty(n, dtype=np.float32)
+        check(fn(self._h, _ptr(out), out.size), fn.__name__)
+        return out
+
+    def get_params(self):
+        return self._get(lib().ub_trainer_get_params, self.nparams)
+
+    def get_grads(self):
+        return self._get(lib().ub_trainer_get_grads, self.nparams)
+
+    def get_output(self):
+        c = self.cfg
+        return self._get(lib().ub_trainer_get_output, c.B * c.C_out * c.H * c.W).reshape(c.B, c.C_out, c.H, c.W)
+
+    def load(self, path: str):
+        check(lib().ub_trainer_load(self._h, path.encode()), "ub_trainer_load")
+
+    def save(self, path: str, with_adamw: bool = False):
+        check(lib().ub_trainer_save(self._h, path.encode(), int(with_adamw)), "ub_trainer_save")
+
+    # -- steps
+    def forward_backward(self, x0, t=None, noise=None) -> float:
+        loss = C.c_float()
+        x0 = np.ascontiguousarray(x0, dtype=np.float32)
+        t = None if t is None else np.ascontiguousarray(t, dtype=np.float32).reshape(-1)
+        noise = None if noise is None else np.ascontiguousarray(noise, dtype=np.float32)
+        check(lib().ub_trainer_forward_backward(self._h, _ptr(x0), _ptr(t), _ptr(noise), C.byref(loss)),
+              "forward_backward")
+        return float(loss.value)
+
+    def update(self, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0):
+        check(lib().ub_trainer_update(self._h, lr, beta1, beta2, eps, weight_decay), "update")
+
+    def train_step(self, x0, t=None, noise=None, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
+                   want_loss=True) -> Optional[float]:
+        loss = C.c_float()
+        x0 = np.ascontiguousarray(x0, dtype=np.float32)
+        t = None if t is None else np.ascontiguousarray(t, dtype=np.float32).reshape(-1)
+        noise = None if noise is None else np.ascontiguousarray(noise, dtype=np.float32)
+        check(lib().ub_trainer_train_step(self._h, _ptr(x0), _ptr(t), _ptr(noise), lr, beta1, beta2, eps,
+                                          weight_decay, C.byref(loss) if want_loss else None), "train_step")
+        return float(loss.value) if want_loss else None
+
+    def train_step_ptr(self, x0_host_ptr: int, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
+                       loss_ref=None):
+        """Same as train_step with a raw (e.g. pinned) host pointer; device-side timestep/noise draws."""
+        check(lib().ub_trainer_train_step(self._h, C.c_void_p(x0_host_ptr), None, None, lr, beta1, beta2, eps,
+                                          weight_decay, loss_ref), "train_step")
+
+    def train_step_device(self, x0_dev_ptr: int, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0):
+        check(lib().ub_trainer_train_step_device(self._h, C.c_void_p(x0_dev_ptr), lr, beta1, beta2, eps,
+                                                 weight_decay), "train_step_device")
+
+    def sync(self):
+        check(lib().ub_trainer_sync(self._h), "sync")
+
+    def last_loss(self) -> float:
+        loss = C.c_float()
+        check(lib().ub_trainer_last_loss(self._h, C.byref(loss)), "last_loss")
+        return float(loss.value)
+
+    def stream(self) -> int:
+        return int(lib().ub_trainer_stream(self._h) or 0)
+
+    def launches_per_step(self) -> int:
+        return int(lib().ub_trainer_launches_per_step(self._h))
+
+    def predict(self, xt, t):
+        c = self.cfg
+        xt = np.ascontiguousarray(xt, dtype=np.float32)
+        t = np.ascontiguousarray(t, dtype=np.float32).reshape(-1)
+        out = np.empty((c.B, c.C_out, c.H, c.W), dtype=np.float32)
+        check(lib().ub_trainer_predict(self._h, _ptr(xt), _ptr(t), _ptr(out)), "predict")
+        return out
+
+    # -- data parallel
+    def attach_dp(self, rank: int, world: int, nccl_id: bytes, n_buckets: int = 4):
+        buf = C.create_string_buffer(nccl_id, UB_NCCL_ID_BYTES)
+        check(lib().ub_trainer_attach_dp(self._h, rank, world, buf, n_buckets), "attach_dp")
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(UB_NCCL_ID_BYTES)
+    check(lib().ub_nccl_get_unique_id(buf), "ub_nccl_get_unique_id")
+    return buf.raw
+
+
+def shard_batch(global_batch: int, rank: int, world: int):
+    """Contiguous batch shard of rank `rank`: samples [r*Bg/R, (r+1)*Bg/R)."""
+    if global_batch % world:
+        raise ValueError("global batch must be divisible by the world size")
+    per = global_batch // world
+    return rank * per, (rank + 1) * per

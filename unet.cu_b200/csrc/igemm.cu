@@ -147,6 +147,13 @@ __global__ void __launch_bounds__(kConvThreads) igemm_conv_kernel(const __grid_c
                     f[j] += bv.x, f[j + 1] += bv.y, f[j + 2] += bv.z, f[j + 3] += bv.w;
                 }
             }
+            if (p.bias2) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 bv = *reinterpret_cast<const float4*>(p.bias2 + n + j);
+                    f[j] += bv.x, f[j + 1] += bv.y, f[j + 2] += bv.z, f[j + 3] += bv.w;
+                }
+            }
             if (p.rowvec) {
                 const float* rv = p.rowvec + size_t(b) * p.Cout + n;
 #pragma unroll
@@ -467,6 +474,7 @@ int igemm_conv_plan(IgemmConvParams* p, const ConvSegDesc* segs, int nseg, int B
         p->seg[s].ntaps = d.ntaps;
     }
     p->bias = ep.bias;
+    p->bias2 = ep.bias2;
     p->rowvec = ep.rowvec;
     p->residual = ep.residual;
     p->ldr = ep.ldr ? ep.ldr : Cout;
@@ -479,19 +487,22 @@ int igemm_conv_plan(IgemmConvParams* p, const ConvSegDesc* segs, int nseg, int B
     }
     if (p->residual && ((p->ldr % 8) != 0 || (reinterpret_cast<uintptr_t>(p->residual) & 15))) return -7;
     if (p->bias && (reinterpret_cast<uintptr_t>(p->bias) & 15)) return -8;
+    if (p->bias2 && (reinterpret_cast<uintptr_t>(p->bias2) & 15)) return -8;
     if (p->rowvec && ((reinterpret_cast<uintptr_t>(p->rowvec) & 15) || (Cout % 4) != 0)) return -8;
     return 0;
 }
 
+void igemm_init() {
+    static bool done = false;
+    if (done) return;
+    cudaFuncSetAttribute(igemm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(227 * 1024));
+    cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(227 * 1024));
+    done = true;
+}
+
 int igemm_conv_launch(const IgemmConvParams& p, cudaStream_t st) {
+    igemm_init();
     const size_t smem = size_t(p.stages) * p.stage_bytes + 1024 + kBarrierBytes;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e =
-            cudaFuncSetAttribute(igemm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(227 * 1024));
-        if (e != cudaSuccess) return int(e);
-        configured = 227 * 1024;
-    }
     dim3 grid(p.tiles_w * p.tiles_h * p.tiles_b, p.Cout / p.BN);
     igemm_conv_kernel<<<grid, kConvThreads, smem, st>>>(p);
     return int(cudaGetLastError());
@@ -543,14 +554,8 @@ int igemm_wgrad_plan(IgemmWgradParams* p, const __nv_bfloat16* dy, int ldy, cons
 }
 
 int igemm_wgrad_launch(const IgemmWgradParams& p, cudaStream_t st) {
+    igemm_init();
     const size_t smem = size_t(p.stages) * p.stage_bytes + 1024 + kBarrierBytes;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e =
-            cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(227 * 1024));
-        if (e != cudaSuccess) return int(e);
-        configured = true;
-    }
     dim3 grid((p.Cout / p.MO) * (p.Cin / p.NC), p.ntaps / p.TC, p.nsplit);
     igemm_wgrad_kernel<<<grid, kConvThreads, smem, st>>>(p);
     return int(cudaGetLastError());

@@ -40,6 +40,7 @@ struct IgemmConvParams {
     uint32_t stage_bytes;       // smem bytes per stage (A tile 16 KiB + B tile, 1024-aligned)
     // epilogue
     const float* bias;             // [Cout] or nullptr
+    const float* bias2;            // second [Cout] bias (fused 1x1 skip conv) or nullptr
     const float* rowvec;           // [B][Cout] per-image additive vector (time-embedding) or nullptr
     const __nv_bfloat16* residual; // NHWC bf16 [B,H,W,ldr] added to the output, or nullptr
     int ldr;
@@ -74,6 +75,7 @@ struct ConvSegDesc {
 };
 struct ConvEpilogue {
     const float* bias = nullptr;
+    const float* bias2 = nullptr;
     const float* rowvec = nullptr;
     const __nv_bfloat16* residual = nullptr;
     int ldr = 0;
@@ -81,6 +83,8 @@ struct ConvEpilogue {
     int ldo = 0;
     int out_mode = OUT_NHWC_BF16;
 };
+// One-time kernel attribute setup (opt-in shared memory); safe to call repeatedly, call before graph capture.
+void igemm_init();
 // Fills `p` (tensor maps + tiling). Returns 0 or a negative error code (unsupported shape).
 int igemm_conv_plan(IgemmConvParams* p, const ConvSegDesc* segs, int nseg, int B, int H, int W, int Cout,
                     const ConvEpilogue& ep);

@@ -1,0 +1,540 @@
+// See misc_ops.cuh.
+#include "misc_ops.cuh"
+
+#include <cstdio>
+
+namespace ub {
+
+static constexpr float kLog2e = 1.4426950408889634f;
+static constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ void ld8f(const bf16* p, float* f) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&u[i]);
+        f[2 * i] = __bfloat162float(h.x);
+        f[2 * i + 1] = __bfloat162float(h.y);
+    }
+}
+__device__ __forceinline__ void st8f(bf16* p, const float* f) {
+    uint32_t u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+        u[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(u[0], u[1], u[2], u[3]);
+}
+
+// =====================================================================================================
+// attention core, head size 32, one thread per query (forward, dq) or per key (dk, dv)
+// =====================================================================================================
+static constexpr int HS = 32;
+static constexpr int KT = 256;  // keys (or queries) staged in smem per chunk
+
+// stage `n` rows of a 32-channel slice (row r at src + r*ld) into smem as fp32 [n][32]
+__device__ __forceinline__ void stage_rows(const bf16* src, int ld, int n, float* dst, float scale) {
+    for (int i = threadIdx.x; i < n * 4; i += blockDim.x) {
+        const int r = i >> 2, part = i & 3;
+        float f[8];
+        ld8f(src + size_t(r) * ld + part * 8, f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dst[r * HS + part * 8 + k] = f[k] * scale;
+    }
+}
+
+__global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ qkv, int ld, int T, int NH,
+                                                       bf16* __restrict__ out, int ldo, float* __restrict__ lse) {
+    extern __shared__ float smf[];  // K [KT][32], V [KT][32]
+    float* sK = smf;
+    float* sV = smf + KT * HS;
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int C = NH * HS;
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = qi < T;
+    const bf16* base = qkv + size_t(b) * T * ld;
+    float q[HS], acc[HS];
+    const float qscale = rsqrtf(float(HS)) * kLog2e;
+    if (active) {
+#pragma unroll
+        for (int part = 0; part < 4; ++part) ld8f(base + size_t(qi) * ld + h * HS + part * 8, q + part * 8);
+    }
+#pragma unroll
+    for (int d = 0; d < HS; ++d) q[d] = active ? q[d] * qscale : 0.f, acc[d] = 0.f;
+    float m = -1e30f, l = 0.f;
+    for (int k0 = 0; k0 < T; k0 += KT) {
+        const int nk = min(KT, T - k0);
+        __syncthreads();
+        stage_rows(base + size_t(k0) * ld + C + h * HS, ld, nk, sK, 1.f);
+        stage_rows(base + size_t(k0) * ld + 2 * C + h * HS, ld, nk, sV, 1.f);
+        __syncthreads();
+        for (int j0 = 0; j0 < nk; j0 += 8) {
+            float s[8];
+            float cmax = -1e30f;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const float4* kr = reinterpret_cast<const float4*>(sK + (j0 + jj) * HS);
+                float a = 0.f;
+#pragma unroll
+                for (int d4 = 0; d4 < 8; ++d4) {
+                    const float4 kv = kr[d4];
+                    a += q[d4 * 4] * kv.x + q[d4 * 4 + 1] * kv.y + q[d4 * 4 + 2] * kv.z + q[d4 * 4 + 3] * kv.w;
+                }
+                s[jj] = (j0 + jj < nk) ? a : -1e30f;
+                cmax = fmaxf(cmax, s[jj]);
+            }
+            if (cmax > m) {
+                const float corr = exp2f(m - cmax);
+                l *= corr;
+#pragma unroll
+                for (int d = 0; d < HS; ++d) acc[d] *= corr;
+                m = cmax;
+            }
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                if (j0 + jj >= nk) continue;  // never touch unstaged smem rows
+                const float p = exp2f(s[jj] - m);
+                l += p;
+                const float4* vr = reinterpret_cast<const float4*>(sV + (j0 + jj) * HS);
+#pragma unroll
+                for (int d4 = 0; d4 < 8; ++d4) {
+                    const float4 vv = vr[d4];
+                    acc[d4 * 4] += p * vv.x, acc[d4 * 4 + 1] += p * vv.y, acc[d4 * 4 + 2] += p * vv.z,
+                        acc[d4 * 4 + 3] += p * vv.w;
+                }
+            }
+        }
+    }
+    if (active) {
+        const float inv = 1.f / l;
+#pragma unroll
+        for (int d = 0; d < HS; ++d) acc[d] *= inv;
+        bf16* op = out + (size_t(b) * T + qi) * ldo + h * HS;
+#pragma unroll
+        for (int part = 0; part < 4; ++part) st8f(op + part * 8, acc + part * 8);
+        lse[(size_t(b) * NH + h) * T + qi] = m + log2f(l);
+    }
+}
+
+// dq: thread per query
+__global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const bf16* __restrict__ qkv, int ld,
+                                                          const bf16* __restrict__ out, int ldo,
+                                                          const bf16* __restrict__ dout, int lddo,
+                                                          const float* __restrict__ lse, int T, int NH,
+                                                          bf16* __restrict__ dqkv, int ldd,
+                                                          float* __restrict__ dsum) {
+    extern __shared__ float smf[];
+    float* sK = smf;
+    float* sV = smf + KT * HS;
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int C = NH * HS;
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = qi < T;
+    const bf16* base = qkv + size_t(b) * T * ld;
+    float q[HS], dO[HS], dq[HS];
+    const float scale = rsqrtf(float(HS));
+    float Dv = 0.f, L = 0.f;
+    if (active) {
+        float o[HS];
+#pragma unroll
+        for (int part = 0; part < 4; ++part) {
+            ld8f(base + size_t(qi) * ld + h * HS + part * 8, q + part * 8);
+            ld8f(dout + (size_t(b) * T + qi) * lddo + h * HS + part * 8, dO + part * 8);
+            ld8f(out + (size_t(b) * T + qi) * ldo + h * HS + part * 8, o + part * 8);
+        }
+#pragma unroll
+        for (int d = 0; d < HS; ++d) Dv += dO[d] * o[d];
+        L = lse[(size_t(b) * NH + h) * T + qi];
+        dsum[(size_t(b) * NH + h) * T + qi] = Dv;
+    }
+#pragma unroll
+    for (int d = 0; d < HS; ++d) {
+        q[d] = active ? q[d] * scale * kLog2e : 0.f;
+        if (!active) dO[d] = 0.f;
+        dq[d] = 0.f;
+    }
+    for (int k0 = 0; k0 < T; k0 += KT) {
+        const int nk = min(KT, T - k0);
+        __syncthreads();
+        stage_rows(base + size_t(k0) * ld + C + h * HS, ld, nk, sK, 1.f);
+        stage_rows(base + size_t(k0) * ld + 2 * C + h * HS, ld, nk, sV, 1.f);
+        __syncthreads();
+        for (int j = 0; j < nk; ++j) {
+            const float4* kr = reinterpret_cast<const float4*>(sK + j * HS);
+            const float4* vr = reinterpret_cast<const float4*>(sV + j * HS);
+            float s = 0.f, dp = 0.f;
+#pragma unroll
+            for (int d4 = 0; d4 < 8; ++d4) {
+                const float4 kv = kr[d4];
+                const float4 vv = vr[d4];
+                s += q[d4 * 4] * kv.x + q[d4 * 4 + 1] * kv.y + q[d4 * 4 + 2] * kv.z + q[d4 * 4 + 3] * kv.w;
+                dp += dO[d4 * 4] * vv.x + dO[d4 * 4 + 1] * vv.y + dO[d4 * 4 + 2] * vv.z + dO[d4 * 4 + 3] * vv.w;
+            }
+            const float ds = exp2f(s - L) * (dp - Dv);
+#pragma unroll
+            for (int d4 = 0; d4 < 8; ++d4) {
+                const float4 kv = kr[d4];
+                dq[d4 * 4] += ds * kv.x, dq[d4 * 4 + 1] += ds * kv.y, dq[d4 * 4 + 2] += ds * kv.z,
+                    dq[d4 * 4 + 3] += ds * kv.w;
+            }
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int d = 0; d < HS; ++d) dq[d] *= scale;
+        bf16* op = dqkv + (size_t(b) * T + qi) * ldd + h * HS;
+#pragma unroll
+        for (int part = 0; part < 4; ++part) st8f(op + part * 8, dq + part * 8);
+    }
+}
+
+// dk, dv: thread per key
+__global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, int ld,
+                                                           const bf16* __restrict__ dout, int lddo,
+                                                           const float* __restrict__ lse,
+                                                           const float* __restrict__ dsum, int T, int NH,
+                                                           bf16* __restrict__ dqkv, int ldd) {
+    extern __shared__ float smf[];  // Q(scaled) [KT][32], dO [KT][32], lse [KT], D [KT]
+    float* sQ = smf;
+    float* sdO = smf + KT * HS;
+    float* sL = smf + 2 * KT * HS;
+    float* sD = sL + KT;
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int C = NH * HS;
+    const int kj = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = kj < T;
+    const bf16* base = qkv + size_t(b) * T * ld;
+    float k[HS], v[HS], dk[HS], dv[HS];
+    if (active) {
+#pragma unroll
+        for (int part = 0; part < 4; ++part) {
+            ld8f(base + size_t(kj) * ld + C + h * HS + part * 8, k + part * 8);
+            ld8f(base + size_t(kj) * ld + 2 * C + h * HS + part * 8, v + part * 8);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < HS; ++d) {
+        if (!active) k[d] = 0.f, v[d] = 0.f;
+        dk[d] = 0.f, dv[d] = 0.f;
+    }
+    const float qscale = rsqrtf(float(HS)) * kLog2e;
+    for (int q0 = 0; q0 < T; q0 += KT) {
+        const int nq = min(KT, T - q0);
+        __syncthreads();
+        stage_rows(base + size_t(q0) * ld + h * HS, ld, nq, sQ, qscale);
+        stage_rows(dout + (size_t(b) * T + q0) * lddo + h * HS, lddo, nq, sdO, 1.f);
+        for (int i = threadIdx.x; i < nq; i += blockDim.x) {
+            sL[i] = lse[(size_t(b) * NH + h) * T + q0 + i];
+            sD[i] = dsum[(size_t(b) * NH + h) * T + q0 + i];
+        }
+        __syncthreads();
+        for (int i = 0; i < nq; ++i) {
+            const float4* qr = reinterpret_cast<const float4*>(sQ + i * HS);
+            const float4* gr = reinterpret_cast<const float4*>(sdO + i * HS);
+            float s = 0.f, dp = 0.f;
+#pragma unroll
+            for (int d4 = 0; d4 < 8; ++d4) {
+                const float4 qv = qr[d4];
+                const float4 gv = gr[d4];
+                s += k[d4 * 4] * qv.x + k[d4 * 4 + 1] * qv.y + k[d4 * 4 + 2] * qv.z + k[d4 * 4 + 3] * qv.w;
+                dp += v[d4 * 4] * gv.x + v[d4 * 4 + 1] * gv.y + v[d4 * 4 + 2] * gv.z + v[d4 * 4 + 3] * gv.w;
+            }
+            const float p = exp2f(s - sL[i]);
+            const float ds = p * (dp - sD[i]);
+#pragma unroll
+            for (int d4 = 0; d4 < 8; ++d4) {
+                const float4 qv = qr[d4];
+                const float4 gv = gr[d4];
+                dk[d4 * 4] += ds * qv.x, dk[d4 * 4 + 1] += ds * qv.y, dk[d4 * 4 + 2] += ds * qv.z,
+                    dk[d4 * 4 + 3] += ds * qv.w;
+                dv[d4 * 4] += p * gv.x, dv[d4 * 4 + 1] += p * gv.y, dv[d4 * 4 + 2] += p * gv.z,
+                    dv[d4 * 4 + 3] += p * gv.w;
+            }
+        }
+    }
+    if (active) {
+        // sQ holds q * scale * log2e, so sum(ds * sQ) = log2e * (scale * sum ds q): multiply by ln2
+#pragma unroll
+        for (int d = 0; d < HS; ++d) dk[d] *= kLn2;
+        bf16* okp = dqkv + (size_t(b) * T + kj) * ldd + C + h * HS;
+        bf16* ovp = dqkv + (size_t(b) * T + kj) * ldd + 2 * C + h * HS;
+#pragma unroll
+        for (int part = 0; part < 4; ++part) {
+            st8f(okp + part * 8, dk + part * 8);
+            st8f(ovp + part * 8, dv + part * 8);
+        }
+    }
+}
+
+static int attn_block_threads(int T) { return T >= 128 ? 128 : (T >= 64 ? 64 : 32); }
+
+void attn_init() {
+    static bool cfg = false;
+    if (cfg) return;
+    cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * KT * HS * 4);
+    cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * KT * HS * 4);
+    cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * KT * HS + 2 * KT) * 4);
+    cfg = true;
+}
+
+int attn_fwd(const bf16* qkv, int ld, int B, int T, int NH, int HSz, bf16* out, int ldo, float* lse,
+             cudaStream_t st) {
+    if (HSz != HS) return -20;
+    attn_init();
+    const int bt = attn_block_threads(T);
+    attn_fwd_kernel<<<dim3((T + bt - 1) / bt, NH, B), bt, 2 * KT * HS * 4, st>>>(qkv, ld, T, NH, out, ldo, lse);
+    return int(cudaGetLastError());
+}
+
+int attn_bwd(const bf16* qkv, int ld, const bf16* out, int ldo, const bf16* dout, int lddo, const float* lse, int B,
+             int T, int NH, int HSz, bf16* dqkv, int ldd, float* dsum, cudaStream_t st) {
+    if (HSz != HS) return -20;
+    const int bt = attn_block_threads(T);
+    dim3 grid((T + bt - 1) / bt, NH, B);
+    attn_bwd_dq_kernel<<<grid, bt, 2 * KT * HS * 4, st>>>(qkv, ld, out, ldo, dout, lddo, lse, T, NH, dqkv, ldd, dsum);
+    attn_bwd_dkv_kernel<<<grid, bt, (2 * KT * HS + 2 * KT) * 4, st>>>(qkv, ld, dout, lddo, lse, dsum, T, NH, dqkv,
+                                                                        ldd);
+    return int(cudaGetLastError());
+}
+
+// =====================================================================================================
+// small fp32 linears (N = batch rows): one warp per output element, lanes split the reduction
+// =====================================================================================================
+__device__ __forceinline__ float silu_f(float z) { return z / (1.f + __expf(-z)); }
+__device__ __forceinline__ float dsilu_f(float z) {
+    const float s = 1.f / (1.f + __expf(-z));
+    return s * (1.f + z * (1.f - s));
+}
+
+__global__ void small_linear_fwd_kernel(const SmallLinear* __restrict__ table, int N) {
+    const SmallLinear e = table[blockIdx.y];
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= N * e.OC) return;
+    const int n = warp / e.OC, o = warp % e.OC;
+    const float* wr = e.w + size_t(o) * e.C;
+    const float* ir = e.inp + size_t(n) * e.C;
+    float s = 0.f;
+    for (int k = lane; k < e.C; k += 32) {
+        float x = ir[k];
+        if (e.silu_in) x = silu_f(x);
+        s += x * wr[k];
+    }
+    for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) e.out[size_t(n) * e.OC + o] = s + e.b[o];
+}
+void small_linear_fwd(const SmallLinear* table_dev, int n_entries, int N, int max_oc, cudaStream_t st) {
+    const int warps = N * max_oc;
+    small_linear_fwd_kernel<<<dim3((warps * 32 + 255) / 256, n_entries), 256, 0, st>>>(table_dev, N);
+}
+
+// dW[o][k] = sum_n dout[n][o] * act(inp[n][k]) ; db[o] = sum_n dout[n][o]
+__global__ void small_linear_bwd_w_kernel(const SmallLinear* __restrict__ table, int N) {
+    const SmallLinear e = table[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= e.OC * e.C) return;
+    const int o = i / e.C, k = i % e.C;
+    float s = 0.f, sb = 0.f;
+    for (int n = 0; n < N; ++n) {
+        float x = e.inp[size_t(n) * e.C + k];
+        if (e.silu_in) x = silu_f(x);
+        const float d = e.dout[size_t(n) * e.OC + o];
+        s += d * x;
+        sb += d;
+    }
+    e.dw[i] = s;
+    if (k == 0) {
+        e.db[o] = sb;
+        if (e.db2) e.db2[o] = sb;
+    }
+}
+// dinp[n][k] += sum_o dout[n][o] * W[o][k]
+__global__ void small_linear_bwd_x_kernel(const SmallLinear* __restrict__ table, int N) {
+    const SmallLinear e = table[blockIdx.y];
+    if (!e.dinp) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * e.C) return;
+    const int n = i / e.C, k = i % e.C;
+    float s = 0.f;
+    for (int o = 0; o < e.OC; ++o) s += e.dout[size_t(n) * e.OC + o] * e.w[size_t(o) * e.C + k];
+    atomicAdd(&e.dinp[i], s);
+}
+void small_linear_bwd(const SmallLinear* table_dev, int n_entries, int N, int max_oc, int max_c, cudaStream_t st) {
+    small_linear_bwd_w_kernel<<<dim3((max_oc * max_c + 255) / 256, n_entries), 256, 0, st>>>(table_dev, N);
+    small_linear_bwd_x_kernel<<<dim3((N * max_c + 255) / 256, n_entries), 256, 0, st>>>(table_dev, N);
+}
+
+__global__ void dsilu_mul_kernel(const float* __restrict__ dact, const float* __restrict__ pre, float* __restrict__ g,
+                                 size_t n) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) g[i] = dact[i] * dsilu_f(pre[i]);
+}
+void dsilu_mul(const float* dact, const float* pre, float* g, size_t n, cudaStream_t st) {
+    dsilu_mul_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(dact, pre, g, n);
+}
+
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, int half, float log_mp,
+                                          float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * half) return;
+    const int b = i / half, j = i % half;
+    const float f = expf(-log_mp * float(j) / float(half));
+    const float a = t[b] * f;
+    out[size_t(b) * 2 * half + j] = cosf(a);
+    out[size_t(b) * 2 * half + half + j] = sinf(a);
+}
+void timestep_embedding(const float* t, int B, int dim, int max_period, float* out, cudaStream_t st) {
+    const int half = dim / 2;
+    timestep_embedding_kernel<<<(B * half + 127) / 128, 128, 0, st>>>(t, B, half, logf(float(max_period)), out);
+}
+
+// =====================================================================================================
+// diffusion: Philox4x32-10 counter RNG (own implementation; stateless => nothing to checkpoint but seed+step)
+// =====================================================================================================
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (float(x >> 8) + 0.5f) * (1.f / 16777216.f); }
+
+__global__ void diffusion_t_kernel(int B, int n_timesteps, uint64_t seed, const int* __restrict__ step_dev,
+                                   float* __restrict__ t) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint4 r = philox4x32_10(make_uint4(uint32_t(b), 0u, 0x7u, uint32_t(*step_dev)),
+                                  make_uint2(uint32_t(seed), uint32_t(seed >> 32)));
+    t[b] = float(r.x % uint32_t(n_timesteps));
+}
+__global__ void diffusion_prepare_kernel(const float* __restrict__ x0, const float* __restrict__ sqrt_ac,
+                                         const float* __restrict__ sqrt_1mac, size_t total4, size_t per_image,
+                                         uint64_t seed, const int* __restrict__ step_dev, int gen_noise,
+                                         const float* __restrict__ t, float* __restrict__ noise,
+                                         float* __restrict__ x_t) {
+    const size_t i4 = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i4 >= total4) return;
+    const size_t i = i4 * 4;
+    float4 e;
+    if (gen_noise) {
+        const uint4 r = philox4x32_10(make_uint4(uint32_t(i4), uint32_t(i4 >> 32), 0x1u, uint32_t(*step_dev)),
+                                      make_uint2(uint32_t(seed), uint32_t(seed >> 32)));
+        const float r0 = sqrtf(-2.f * logf(u01(r.x))), r1 = sqrtf(-2.f * logf(u01(r.z)));
+        float s0, c0, s1, c1;
+        sincospif(2.f * u01(r.y), &s0, &c0);
+        sincospif(2.f * u01(r.w), &s1, &c1);
+        e = make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+        *reinterpret_cast<float4*>(noise + i) = e;
+    } else {
+        e = *reinterpret_cast<const float4*>(noise + i);
+    }
+    const int b = int(i / per_image);  // per_image % 4 == 0, so the 4 elements share one image
+    const int ti = int(t[b]);
+    const float a = sqrt_ac[ti], s = sqrt_1mac[ti];
+    const float4 x = *reinterpret_cast<const float4*>(x0 + i);
+    *reinterpret_cast<float4*>(x_t + i) = make_float4(a * x.x + s * e.x, a * x.y + s * e.y, a * x.z + s * e.z,
+                                                      a * x.w + s * e.w);
+}
+void diffusion_prepare(const float* x0, const float* sqrt_ac, const float* sqrt_1mac, int B, size_t per_image,
+                       int n_timesteps, uint64_t seed, const int* step_dev, int gen_t, int gen_noise, float* t,
+                       float* noise, float* x_t, cudaStream_t st) {
+    if (gen_t) diffusion_t_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, n_timesteps, seed, step_dev, t);
+    const size_t total4 = size_t(B) * per_image / 4;
+    diffusion_prepare_kernel<<<unsigned((total4 + 255) / 256), 256, 0, st>>>(x0, sqrt_ac, sqrt_1mac, total4, per_image,
+                                                                             seed, step_dev, gen_noise, t, noise, x_t);
+}
+
+// =====================================================================================================
+// weight packing: 32x32 (o, c) tiles through smem so both packed layouts are written coalesced
+// =====================================================================================================
+__global__ void pack_weights_kernel(const PackEntry* __restrict__ table) {
+    const PackEntry e = table[blockIdx.y];
+    const int tiles_c = (e.Cin + 31) / 32, tiles_o = (e.Cout + 31) / 32;
+    if (int(blockIdx.x) >= tiles_c * tiles_o) return;
+    const int o0 = (blockIdx.x / tiles_c) * 32, c0 = (blockIdx.x % tiles_c) * 32;
+    __shared__ float tile[9][32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 256 threads: ty in 0..7
+    const int nt = e.ntaps;
+    // load: rows o, the (c, tap) run is contiguous in memory: nt*32 floats per o row
+    for (int oo = ty; oo < 32; oo += 8) {
+        const int o = o0 + oo;
+        for (int i = tx; i < 32 * nt; i += 32) {
+            const int cc = i / nt, tap = i % nt;
+            float v = 0.f;
+            if (o < e.Cout && c0 + cc < e.Cin) v = e.w[(size_t(o) * e.Cin + c0 + cc) * nt + tap];
+            tile[tap][oo][cc] = v;
+        }
+    }
+    __syncthreads();
+    for (int tap = 0; tap < nt; ++tap) {
+        if (e.wf) {
+            for (int oo = ty; oo < 32; oo += 8)
+                if (o0 + oo < e.Cout && c0 + tx < e.Cin)
+                    e.wf[(size_t(tap) * e.Cout + o0 + oo) * e.Cin + c0 + tx] = __float2bfloat16(tile[tap][oo][tx]);
+        }
+        if (e.wd) {
+            for (int cc = ty; cc < 32; cc += 8)
+                if (c0 + cc < e.Cin && o0 + tx < e.Cout)
+                    e.wd[(size_t(nt - 1 - tap) * e.Cin + c0 + cc) * e.Cout + o0 + tx] =
+                        __float2bfloat16(tile[tap][tx][cc]);
+        }
+    }
+}
+void pack_weights(const PackEntry* table_dev, int n_entries, int max_tiles, cudaStream_t st) {
+    pack_weights_kernel<<<dim3(max_tiles, n_entries), 256, 0, st>>>(table_dev);
+}
+
+// =====================================================================================================
+// AdamW
+// =====================================================================================================
+__global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, size_t n4, size_t n, float lr, float b1, float b2, float eps,
+                             float wd, float gscale, const int* __restrict__ step_dev) {
+    const int t = *step_dev + 1;
+    const float c1 = 1.f - powf(b1, float(t)), c2 = 1.f - powf(b2, float(t));
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n4) {
+        const float4 pv = reinterpret_cast<float4*>(p)[i], gv = reinterpret_cast<float4*>(g)[i],
+                     mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+        float pp[4] = {pv.x, pv.y, pv.z, pv.w}, gp[4] = {gv.x, gv.y, gv.z, gv.w}, mp[4] = {mv.x, mv.y, mv.z, mv.w},
+              vp[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gr = gp[k] * gscale;
+            mp[k] = b1 * mp[k] + (1.f - b1) * gr;
+            vp[k] = b2 * vp[k] + (1.f - b2) * gr * gr;
+            const float mh = mp[k] / c1, vh = vp[k] / c2;
+            pp[k] -= lr * (mh / (sqrtf(vh) + eps) + wd * pp[k]);
+        }
+        reinterpret_cast<float4*>(p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+        reinterpret_cast<float4*>(m)[i] = make_float4(mp[0], mp[1], mp[2], mp[3]);
+        reinterpret_cast<float4*>(v)[i] = make_float4(vp[0], vp[1], vp[2], vp[3]);
+        reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else if (i == n4) {  // tail (n % 4 elements)
+        for (size_t k = n4 * 4; k < n; ++k) {
+            const float gr = g[k] * gscale;
+            m[k] = b1 * m[k] + (1.f - b1) * gr;
+            v[k] = b2 * v[k] + (1.f - b2) * gr * gr;
+            p[k] -= lr * ((m[k] / c1) / (sqrtf(v[k] / c2) + eps) + wd * p[k]);
+            g[k] = 0.f;
+        }
+    }
+}
+void adamw_step(float* p, float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, float wd,
+                float grad_scale, const int* step_dev, cudaStream_t st) {
+    const size_t n4 = n / 4;
+    adamw_kernel<<<unsigned((n4 + 1 + 255) / 256), 256, 0, st>>>(p, g, m, v, n4, n, lr, b1, b2, eps, wd, grad_scale,
+                                                                step_dev);
+}
+__global__ void increment_step_kernel(int* s) { *s += 1; }
+void increment_step(int* step_dev, cudaStream_t st) { increment_step_kernel<<<1, 1, 0, st>>>(step_dev); }
+
+}  // namespace ub

@@ -1,0 +1,689 @@
+// Memory-bound kernels of the internal NHWC bf16 training path (see nhwc_ops.cuh).
+// Every kernel moves 16-byte vectors (8 bf16 channels) per thread, is coalesced along the channel axis and
+// sizes its grid to a few waves of the 148 SMs.
+#include "nhwc_ops.cuh"
+
+#include <cstdio>
+
+namespace ub {
+
+static constexpr int kSMs = 148;
+
+__device__ __forceinline__ void ld8(const bf16* p, float (&f)[8]) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&u[i]);
+        f[2 * i] = __bfloat162float(h.x);
+        f[2 * i + 1] = __bfloat162float(h.y);
+    }
+}
+__device__ __forceinline__ void st8(bf16* p, const float (&f)[8]) {
+    uint32_t u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+        u[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(u[0], u[1], u[2], u[3]);
+}
+__device__ __forceinline__ float silu_f(float z) { return z / (1.f + __expf(-z)); }
+// d silu(z) / dz
+__device__ __forceinline__ float dsilu_f(float z) {
+    const float s = 1.f / (1.f + __expf(-z));
+    return s * (1.f + z * (1.f - s));
+}
+
+// Thread layout shared by the per-image kernels: blockDim = C8 * rows, thread -> (octet j, row r);
+// block (chunk, b) walks pixels [chunk*ppb, (chunk+1)*ppb) of image b with stride rows.
+struct RowMap {
+    int C8, rows, threads, nchunks, ppb;
+};
+static RowMap make_rowmap(int B, int HW, int C) {
+    RowMap m;
+    m.C8 = C / 8;
+    m.rows = 256 / m.C8;
+    if (m.rows < 1) m.rows = 1;
+    if (m.rows > HW) m.rows = HW;
+    m.threads = m.C8 * m.rows;
+    int want = (4 * kSMs + B - 1) / B;  // chunks per image for ~4 waves
+    int maxc = (HW + m.rows - 1) / m.rows;
+    m.nchunks = want < maxc ? want : maxc;
+    if (m.nchunks < 1) m.nchunks = 1;
+    m.ppb = (HW + m.nchunks - 1) / m.nchunks;
+    m.nchunks = (HW + m.ppb - 1) / m.ppb;
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------------ GN stats
+__global__ void gn_stats_kernel(const bf16* __restrict__ x, int ldx, int HW, int C, int C8, int rows, int ppb,
+                                float* __restrict__ chsum) {
+    extern __shared__ float sm[];  // [2][C]
+    const int b = blockIdx.y;
+    const int j = threadIdx.x % C8, r = threadIdx.x / C8;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    float s[8], ss[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
+    const int p0 = blockIdx.x * ppb;
+    const int p1 = min(p0 + ppb, HW);
+    const bf16* xb = x + (size_t(b) * HW) * ldx + j * 8;
+    for (int p = p0 + r; p < p1; p += rows) {
+        float f[8];
+        ld8(xb + size_t(p) * ldx, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] += f[i], ss[i] += f[i] * f[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        atomicAdd(&sm[j * 8 + i], s[i]);
+        atomicAdd(&sm[C + j * 8 + i], ss[i]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        atomicAdd(&chsum[(size_t(b) * C + c) * 2], sm[c]);
+        atomicAdd(&chsum[(size_t(b) * C + c) * 2 + 1], sm[C + c]);
+    }
+}
+
+void gn_stats(const bf16* x, int ldx, int B, int HW, int C, float* chsum, cudaStream_t st) {
+    RowMap m = make_rowmap(B, HW, C);
+    gn_stats_kernel<<<dim3(m.nchunks, B), m.threads, 2 * C * sizeof(float), st>>>(x, ldx, HW, C, m.C8, m.rows, m.ppb,
+                                                                                   chsum);
+}
+
+// per-channel affine of the normalisation, from per-channel sums:  xhat = x*sr - smr ;  z = x*sa + sb
+__device__ __forceinline__ void gn_channel_consts(const float* __restrict__ chsum_b, const float* __restrict__ gamma,
+                                                  const float* __restrict__ beta, int C, int cpg, int HW, int c,
+                                                  float& r, float& mr, float& a, float& bb) {
+    const int g0 = (c / cpg) * cpg;
+    float s = 0.f, ss = 0.f;
+    for (int k = 0; k < cpg; ++k) {
+        s += chsum_b[(g0 + k) * 2];
+        ss += chsum_b[(g0 + k) * 2 + 1];
+    }
+    const float n = float(cpg) * float(HW);
+    const float mean = s / n;
+    const float var = fmaxf(ss / n - mean * mean, 0.f);
+    r = rsqrtf(var + 1e-5f);
+    mr = mean * r;
+    a = r * gamma[c];
+    bb = beta[c] - mean * a;
+}
+
+// ------------------------------------------------------------------------------------------------ GN apply
+__global__ void gn_apply_kernel(const bf16* __restrict__ x, int ldx, const float* __restrict__ chsum,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C, int G,
+                                int silu, int C8, int rows, int ppb, bf16* __restrict__ y, int ldy,
+                                float* __restrict__ meanrstd) {
+    extern __shared__ float sm[];  // sa[C], sb[C]
+    float* sa = sm;
+    float* sb = sm + C;
+    const int b = blockIdx.y;
+    const int cpg = C / G;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float r, mr, a, bb;
+        gn_channel_consts(chsum + size_t(b) * C * 2, gamma, beta, C, cpg, HW, c, r, mr, a, bb);
+        sa[c] = a, sb[c] = bb;
+        if (meanrstd && blockIdx.x == 0 && (c % cpg) == 0) {
+            meanrstd[(size_t(b) * G + c / cpg) * 2] = mr / r;
+            meanrstd[(size_t(b) * G + c / cpg) * 2 + 1] = r;
+        }
+    }
+    __syncthreads();
+    const int j = threadIdx.x % C8, r = threadIdx.x / C8;
+    float a[8], bb[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = sa[j * 8 + i], bb[i] = sb[j * 8 + i];
+    const int p0 = blockIdx.x * ppb;
+    const int p1 = min(p0 + ppb, HW);
+    const bf16* xb = x + (size_t(b) * HW) * ldx + j * 8;
+    bf16* yb = y + (size_t(b) * HW) * ldy + j * 8;
+    for (int p = p0 + r; p < p1; p += rows) {
+        float f[8];
+        ld8(xb + size_t(p) * ldx, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float z = f[i] * a[i] + bb[i];
+            f[i] = silu ? silu_f(z) : z;
+        }
+        st8(yb + size_t(p) * ldy, f);
+    }
+}
+
+void gn_apply(const bf16* x, int ldx, const float* chsum, const float* gamma, const float* beta, int B, int HW, int C,
+              int G, int silu, bf16* y, int ldy, float* meanrstd, cudaStream_t st) {
+    RowMap m = make_rowmap(B, HW, C);
+    gn_apply_kernel<<<dim3(m.nchunks, B), m.threads, 2 * C * sizeof(float), st>>>(
+        x, ldx, chsum, gamma, beta, HW, C, G, silu, m.C8, m.rows, m.ppb, y, ldy, meanrstd);
+}
+
+// ------------------------------------------------------------------------------------------------ GN backward
+__global__ void gn_bwd_stats_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ dy, int lddy,
+                                    const float* __restrict__ chsum, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, int HW, int C, int G, int silu, int C8, int rows,
+                                    int ppb, float* __restrict__ S) {
+    extern __shared__ float sm[];  // sa, sb, sr, smr, acc1, acc2  : 6*C
+    float *sa = sm, *sb = sm + C, *sr = sm + 2 * C, *smr = sm + 3 * C, *acc1 = sm + 4 * C, *acc2 = sm + 5 * C;
+    const int b = blockIdx.y;
+    const int cpg = C / G;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float r, mr, a, bb;
+        gn_channel_consts(chsum + size_t(b) * C * 2, gamma, beta, C, cpg, HW, c, r, mr, a, bb);
+        sa[c] = a, sb[c] = bb, sr[c] = r, smr[c] = mr, acc1[c] = 0.f, acc2[c] = 0.f;
+    }
+    __syncthreads();
+    const int j = threadIdx.x % C8, r = threadIdx.x / C8;
+    float s1[8], s2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+    const int p0 = blockIdx.x * ppb;
+    const int p1 = min(p0 + ppb, HW);
+    const bf16* xb = x + (size_t(b) * HW) * ldx + j * 8;
+    const bf16* db = dy + (size_t(b) * HW) * lddy + j * 8;
+    for (int p = p0 + r; p < p1; p += rows) {
+        float f[8], d[8];
+        ld8(xb + size_t(p) * ldx, f);
+        ld8(db + size_t(p) * lddy, d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = j * 8 + i;
+            float dz = d[i];
+            if (silu) dz *= dsilu_f(f[i] * sa[c] + sb[c]);
+            const float xh = f[i] * sr[c] - smr[c];
+            s1[i] += dz;
+            s2[i] += dz * xh;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        atomicAdd(&acc1[j * 8 + i], s1[i]);
+        atomicAdd(&acc2[j * 8 + i], s2[i]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        atomicAdd(&S[(size_t(b) * C + c) * 2], acc1[c]);
+        atomicAdd(&S[(size_t(b) * C + c) * 2 + 1], acc2[c]);
+    }
+}
+
+void gn_bwd_stats(const bf16* x, int ldx, const bf16* dy, int lddy, const float* chsum, const float* gamma,
+                  const float* beta, int B, int HW, int C, int G, int silu, float* S, cudaStream_t st) {
+    RowMap m = make_rowmap(B, HW, C);
+    gn_bwd_stats_kernel<<<dim3(m.nchunks, B), m.threads, 6 * C * sizeof(float), st>>>(
+        x, ldx, dy, lddy, chsum, gamma, beta, HW, C, G, silu, m.C8, m.rows, m.ppb, S);
+}
+
+__global__ void gn_bwd_apply_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ dy, int lddy,
+                                    const float* __restrict__ chsum, const float* __restrict__ S,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C,
+                                    int G, int silu, int C8, int rows, int ppb, const bf16* __restrict__ add_in,
+                                    int ldadd, bf16* __restrict__ dx, int lddx, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, float* __restrict__ colsum_out) {
+    extern __shared__ float sm[];  // sa, sb, sr, smr, sgr, sm1, sm2, acc : 8*C
+    float *sa = sm, *sb = sm + C, *sr = sm + 2 * C, *smr = sm + 3 * C, *sgr = sm + 4 * C, *sm1 = sm + 5 * C,
+          *sm2 = sm + 6 * C, *acc = sm + 7 * C;
+    const int b = blockIdx.y;
+    const int cpg = C / G;
+    const float* Sb = S + size_t(b) * C * 2;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float r, mr, a, bb;
+        gn_channel_consts(chsum + size_t(b) * C * 2, gamma, beta, C, cpg, HW, c, r, mr, a, bb);
+        const int g0 = (c / cpg) * cpg;
+        float m1 = 0.f, m2 = 0.f;
+        for (int k = 0; k < cpg; ++k) {
+            m1 += gamma[g0 + k] * Sb[(g0 + k) * 2];
+            m2 += gamma[g0 + k] * Sb[(g0 + k) * 2 + 1];
+        }
+        const float n = float(cpg) * float(HW);
+        sa[c] = a, sb[c] = bb, sr[c] = r, smr[c] = mr, sgr[c] = a;  // a == gamma * rstd
+        sm1[c] = r * m1 / n, sm2[c] = r * m2 / n;
+        acc[c] = 0.f;
+        if (blockIdx.x == 0) {
+            atomicAdd(&dgamma[c], Sb[c * 2 + 1]);
+            atomicAdd(&dbeta[c], Sb[c * 2]);
+        }
+    }
+    __syncthreads();
+    const int j = threadIdx.x % C8, r = threadIdx.x / C8;
+    float cs[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cs[i] = 0.f;
+    const int p0 = blockIdx.x * ppb;
+    const int p1 = min(p0 + ppb, HW);
+    const size_t img = size_t(b) * HW;
+    for (int p = p0 + r; p < p1; p += rows) {
+        float f[8], d[8], o[8];
+        ld8(x + (img + p) * ldx + j * 8, f);
+        ld8(dy + (img + p) * lddy + j * 8, d);
+        if (add_in) {
+            ld8(add_in + (img + p) * ldadd + j * 8, o);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = j * 8 + i;
+            float dz = d[i];
+            if (silu) dz *= dsilu_f(f[i] * sa[c] + sb[c]);
+            const float xh = f[i] * sr[c] - smr[c];
+            const float g = sgr[c] * dz - sm1[c] - xh * sm2[c];
+            cs[i] += g;
+            o[i] += g;
+        }
+        st8(dx + (img + p) * lddx + j * 8, o);
+    }
+    if (colsum_out) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(&acc[j * 8 + i], cs[i]);
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&colsum_out[size_t(b) * C + c], acc[c]);
+    }
+}
+
+void gn_bwd_apply(const bf16* x, int ldx, const bf16* dy, int lddy, const float* chsum, const float* S,
+                  const float* gamma, const float* beta, int B, int HW, int C, int G, int silu, const bf16* add_in,
+                  int ldadd, bf16* dx, int lddx, float* dgamma, float* dbeta, float* colsum_out, cudaStream_t st) {
+    RowMap m = make_rowmap(B, HW, C);
+    gn_bwd_apply_kernel<<<dim3(m.nchunks, B), m.threads, 8 * C * sizeof(float), st>>>(
+        x, ldx, dy, lddy, chsum, S, gamma, beta, HW, C, G, silu, m.C8, m.rows, m.ppb, add_in, ldadd, dx, lddx, dgamma,
+        dbeta, colsum_out);
+}
+
+// ------------------------------------------------------------------------------------------------ pooling etc.
+__global__ void avgpool2_fwd_kernel(const bf16* __restrict__ x, int ldx, int H, int W, int C8, size_t total,
+                                    bf16* __restrict__ y, int ldy) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int j = int(i % C8);
+    size_t p = i / C8;
+    const int Wo = W / 2, Ho = H / 2;
+    const int wo = int(p % Wo), ho = int((p / Wo) % Ho);
+    const size_t b = p / (size_t(Wo) * Ho);
+    const bf16* xp = x + ((b * H + 2 * ho) * W + 2 * wo) * ldx + j * 8;
+    float a[8], t[8];
+    ld8(xp, a);
+    ld8(xp + ldx, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += t[k];
+    ld8(xp + size_t(W) * ldx, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += t[k];
+    ld8(xp + size_t(W + 1) * ldx, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = (a[k] + t[k]) * 0.25f;
+    st8(y + p * ldy + j * 8, a);
+}
+void avgpool2_fwd(const bf16* x, int ldx, int B, int H, int W, int C, bf16* y, int ldy, cudaStream_t st) {
+    const size_t total = size_t(B) * (H / 2) * (W / 2) * (C / 8);
+    avgpool2_fwd_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(x, ldx, H, W, C / 8, total, y, ldy);
+}
+
+__global__ void avgpool2_bwd_kernel(const bf16* __restrict__ dy, int lddy, int H, int W, int C8, size_t total,
+                                    const bf16* __restrict__ add_in, int ldadd, bf16* __restrict__ dx, int lddx) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int j = int(i % C8);
+    const size_t p = i / C8;
+    const int w = int(p % W), h = int((p / W) % H);
+    const size_t b = p / (size_t(W) * H);
+    float a[8];
+    ld8(dy + ((b * (H / 2) + h / 2) * (W / 2) + w / 2) * lddy + j * 8, a);
+    if (add_in) {
+        float t[8];
+        ld8(add_in + p * ldadd + j * 8, t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = a[k] * 0.25f + t[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] *= 0.25f;
+    }
+    st8(dx + p * lddx + j * 8, a);
+}
+void avgpool2_bwd(const bf16* dy, int lddy, int B, int H, int W, int C, const bf16* add_in, int ldadd, bf16* dx,
+                  int lddx, cudaStream_t st) {
+    const size_t total = size_t(B) * H * W * (C / 8);
+    avgpool2_bwd_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(dy, lddy, H, W, C / 8, total, add_in, ldadd,
+                                                                      dx, lddx);
+}
+
+__global__ void concat2_kernel(const bf16* __restrict__ a, int lda, int C1_8, int up, const bf16* __restrict__ b,
+                               int ldb, int C2_8, int H, int W, size_t total, bf16* __restrict__ out, int ldo) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int CT = C1_8 + C2_8;
+    const int j = int(i % CT);
+    const size_t p = i / CT;
+    uint4 v;
+    if (j < C1_8) {
+        size_t ps = p;
+        if (up) {
+            const int w = int(p % W), h = int((p / W) % H);
+            const size_t bi = p / (size_t(W) * H);
+            ps = (bi * (H / 2) + h / 2) * (W / 2) + w / 2;
+        }
+        v = *reinterpret_cast<const uint4*>(a + ps * lda + j * 8);
+    } else {
+        v = *reinterpret_cast<const uint4*>(b + p * ldb + (j - C1_8) * 8);
+    }
+    *reinterpret_cast<uint4*>(out + p * ldo + j * 8) = v;
+}
+void concat2(const bf16* a, int lda, int C1, int up, const bf16* b, int ldb, int C2, int B, int H, int W, bf16* out,
+             int ldo, cudaStream_t st) {
+    const size_t total = size_t(B) * H * W * ((C1 + C2) / 8);
+    concat2_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(a, lda, C1 / 8, up, b, ldb, C2 / 8, H, W, total, out,
+                                                                 ldo);
+}
+
+__global__ void upsample2_bwd_kernel(const bf16* __restrict__ dy, int lddy, int H, int W, int C8, size_t total,
+                                     bf16* __restrict__ dx, int lddx) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int j = int(i % C8);
+    const size_t p = i / C8;
+    const int Wo = W / 2, Ho = H / 2;
+    const int wo = int(p % Wo), ho = int((p / Wo) % Ho);
+    const size_t b = p / (size_t(Wo) * Ho);
+    const bf16* yp = dy + ((b * H + 2 * ho) * W + 2 * wo) * lddy + j * 8;
+    float a[8], t[8];
+    ld8(yp, a);
+    ld8(yp + lddy, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += t[k];
+    ld8(yp + size_t(W) * lddy, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += t[k];
+    ld8(yp + size_t(W + 1) * lddy, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += t[k];
+    st8(dx + p * lddx + j * 8, a);
+}
+void upsample2_bwd(const bf16* dy, int lddy, int B, int H, int W, int C, bf16* dx, int lddx, cudaStream_t st) {
+    const size_t total = size_t(B) * (H / 2) * (W / 2) * (C / 8);
+    upsample2_bwd_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(dy, lddy, H, W, C / 8, total, dx, lddx);
+}
+
+__global__ void add2_kernel(const bf16* __restrict__ a, int lda, const bf16* __restrict__ b, int ldb, int C8,
+                            size_t total, bf16* __restrict__ out, int ldo) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int j = int(i % C8);
+    const size_t p = i / C8;
+    float x[8], y[8];
+    ld8(a + p * lda + j * 8, x);
+    ld8(b + p * ldb + j * 8, y);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] += y[k];
+    st8(out + p * ldo + j * 8, x);
+}
+void add2(const bf16* a, int lda, const bf16* b, int ldb, size_t npix, int C, bf16* out, int ldo, cudaStream_t st) {
+    const size_t total = npix * (C / 8);
+    add2_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(a, lda, b, ldb, C / 8, total, out, ldo);
+}
+
+__global__ void colsum_kernel(const bf16* __restrict__ x, int ldx, size_t npix, int C, int C8, int rows, size_t ppb,
+                              float* __restrict__ out, float* __restrict__ out2) {
+    extern __shared__ float sm[];  // [C]
+    for (int c = threadIdx.x; c < C; c += blockDim.x) sm[c] = 0.f;
+    __syncthreads();
+    const int j = threadIdx.x % C8, r = threadIdx.x / C8;
+    float s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 0.f;
+    const size_t p0 = size_t(blockIdx.x) * ppb;
+    const size_t p1 = p0 + ppb < npix ? p0 + ppb : npix;
+    for (size_t p = p0 + r; p < p1; p += rows) {
+        float f[8];
+        ld8(x + p * ldx + j * 8, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] += f[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&sm[j * 8 + i], s[i]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        atomicAdd(&out[c], sm[c]);
+        if (out2) atomicAdd(&out2[c], sm[c]);
+    }
+}
+void colsum(const bf16* x, int ldx, size_t npix, int C, float* out, float* out2, cudaStream_t st) {
+    const int C8 = C / 8;
+    int rows = 256 / C8;
+    if (rows < 1) rows = 1;
+    size_t nblk = (npix + rows - 1) / rows;
+    if (nblk > size_t(2 * kSMs)) nblk = 2 * kSMs;
+    const size_t ppb = (npix + nblk - 1) / nblk;
+    nblk = (npix + ppb - 1) / ppb;
+    colsum_kernel<<<unsigned(nblk), C8 * rows, C * sizeof(float), st>>>(x, ldx, npix, C, C8, rows, ppb, out, out2);
+}
+
+// ------------------------------------------------------------------------------------------------ 3-channel convs
+// y[p][cb] (NHWC bf16, Cb "big" channels) = bias[cb] + sum_tap sum_{s<Cs} xs[b][s][p + shift(tap)] * Wsm[cb][s][tap]
+// flip == 0: Wsm = w[cb][s][tap]                  (conv_in forward,  w is (Cb, Cs, 3, 3))
+// flip == 1: Wsm = w[s][cb][8 - tap]              (conv_out dgrad,   w is (Cs, Cb, 3, 3))
+__global__ void smallc_conv_kernel(const float* __restrict__ xs, const float* __restrict__ w,
+                                   const float* __restrict__ bias, int Cs, int Cb, int H, int W, int flip,
+                                   size_t total, bf16* __restrict__ y, int ldy) {
+    extern __shared__ float sw[];  // [Cs*9][Cb]
+    for (int i = threadIdx.x; i < Cb * Cs * 9; i += blockDim.x) {
+        const int cb = i % Cb, st = i / Cb;  // st = s*9 + tap
+        const int s = st / 9, tap = st % 9;
+        sw[i] = flip ? w[(size_t(s) * Cb + cb) * 9 + (8 - tap)] : w[(size_t(cb) * Cs + s) * 9 + tap];
+    }
+    __syncthreads();
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int C8 = Cb / 8;
+    const int j = int(i % C8);
+    const size_t p = i / C8;
+    const int wq = int(p % W), h = int((p / W) % H);
+    const size_t b = p / (size_t(W) * H);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = bias ? bias[j * 8 + k] : 0.f;
+    for (int s = 0; s < Cs; ++s) {
+        const float* xp = xs + (b * Cs + s) * size_t(H) * W;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int hh = h + tap / 3 - 1, ww = wq + tap % 3 - 1;
+            if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+            const float v = __ldg(xp + size_t(hh) * W + ww);
+            const float* wr = sw + (s * 9 + tap) * Cb + j * 8;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += v * wr[k];
+        }
+    }
+    st8(y + p * ldy + j * 8, acc);
+}
+
+void conv_in_fwd(const float* x, const float* w, const float* b, int B, int Cin, int Cout, int H, int W, bf16* y,
+                 int ldy, cudaStream_t st) {
+    const size_t total = size_t(B) * H * W * (Cout / 8);
+    smallc_conv_kernel<<<unsigned((total + 255) / 256), 256, size_t(Cout) * Cin * 9 * sizeof(float), st>>>(
+        x, w, b, Cin, Cout, H, W, 0, total, y, ldy);
+}
+void conv_out_dgrad(const float* dout, const float* w, int B, int Cin, int Cout, int H, int W, bf16* da, int ldda,
+                    cudaStream_t st) {
+    const size_t total = size_t(B) * H * W * (Cin / 8);
+    smallc_conv_kernel<<<unsigned((total + 255) / 256), 256, size_t(Cout) * Cin * 9 * sizeof(float), st>>>(
+        dout, w, nullptr, Cout, Cin, H, W, 1, total, da, ldda);
+}
+
+// partial[blk][cb][s*9+tap] = sum_{p in block} yb[p][cb] * xs[b][s][p + shift(tap)] ; partial_b[blk][cb] = sum yb
+// blockDim = Cb * 4 (4 pixel lanes per channel), each block walks ppb pixels.
+__global__ void smallc_wgrad_kernel(const float* __restrict__ xs, const bf16* __restrict__ yb, int ldy, int Cs, int Cb,
+                                    int H, int W, size_t npix, size_t ppb, float* __restrict__ partial) {
+    extern __shared__ float sred[];  // [4][Cb][Cs*9+1]
+    const int cb = threadIdx.x % Cb, q = threadIdx.x / Cb;
+    const int NT = Cs * 9;
+    float acc[37];  // Cs <= 4
+#pragma unroll
+    for (int k = 0; k < 37; ++k) acc[k] = 0.f;
+    const size_t p0 = size_t(blockIdx.x) * ppb;
+    const size_t p1 = p0 + ppb < npix ? p0 + ppb : npix;
+    for (size_t p = p0 + q; p < p1; p += 4) {
+        const float v = __bfloat162float(yb[p * ldy + cb]);
+        const int wq = int(p % W), h = int((p / W) % H);
+        const size_t b = p / (size_t(W) * H);
+        acc[36] += v;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {  // fully unrolled so acc[] stays in registers
+            if (s < Cs) {
+                const float* xp = xs + (b * Cs + s) * size_t(H) * W;
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int hh = h + tap / 3 - 1, ww = wq + tap % 3 - 1;
+                    if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+                        acc[s * 9 + tap] += v * __ldg(xp + size_t(hh) * W + ww);
+                }
+            }
+        }
+    }
+    float* mine = sred + (size_t(q) * Cb + cb) * (NT + 1);
+#pragma unroll
+    for (int k = 0; k < 36; ++k)
+        if (k < NT) mine[k] = acc[k];
+    mine[NT] = acc[36];
+    __syncthreads();
+    for (int i = threadIdx.x; i < Cb * (NT + 1); i += blockDim.x) {
+        float s = 0.f;
+        for (int qq = 0; qq < 4; ++qq) s += sred[size_t(qq) * Cb * (NT + 1) + i];
+        partial[size_t(blockIdx.x) * Cb * (NT + 1) + i] = s;
+    }
+}
+// mode 0 (conv_in):  dw[cb][s][tap] = sum_blk partial[..][cb][s*9+tap] ; db[cb] = sum partial[..][cb][NT]
+// mode 1 (conv_out): dw[s][cb][8-tap] = ...                            ; db untouched (computed elsewhere)
+__global__ void smallc_wgrad_reduce_kernel(const float* __restrict__ partial, int nblk, int Cs, int Cb, int mode,
+                                           float* __restrict__ dw, float* __restrict__ db) {
+    const int NT = Cs * 9;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Cb * (NT + 1)) return;
+    float s = 0.f;
+    for (int k = 0; k < nblk; ++k) s += partial[size_t(k) * Cb * (NT + 1) + i];
+    const int cb = i / (NT + 1), r = i % (NT + 1);
+    if (r == NT) {
+        if (mode == 0 && db) db[cb] = s;
+        return;
+    }
+    const int sidx = r / 9, tap = r % 9;
+    if (mode == 0)
+        dw[(size_t(cb) * Cs + sidx) * 9 + tap] = s;
+    else
+        dw[(size_t(sidx) * Cb + cb) * 9 + (8 - tap)] = s;
+}
+static void smallc_wgrad(const float* xs, const bf16* yb, int ldy, int B, int Cs, int Cb, int H, int W, int mode,
+                         float* dw, float* db, float* scratch, size_t scratch_floats, cudaStream_t st) {
+    const size_t npix = size_t(B) * H * W;
+    const int NT = Cs * 9;
+    size_t nblk = 2 * kSMs;
+    const size_t per = size_t(Cb) * (NT + 1);
+    if (nblk * per > scratch_floats) nblk = scratch_floats / per;
+    if (nblk < 1) {
+        fprintf(stderr, "[unet_b200] smallc_wgrad: scratch too small\n");
+        return;
+    }
+    const size_t ppb = (npix + nblk - 1) / nblk;
+    nblk = (npix + ppb - 1) / ppb;
+    smallc_wgrad_kernel<<<unsigned(nblk), Cb * 4, 4 * per * sizeof(float), st>>>(xs, yb, ldy, Cs, Cb, H, W, npix, ppb,
+                                                                                  scratch);
+    smallc_wgrad_reduce_kernel<<<unsigned((per + 127) / 128), 128, 0, st>>>(scratch, int(nblk), Cs, Cb, mode, dw, db);
+}
+void conv_in_wgrad(const float* x, const bf16* dy, int lddy, int B, int Cin, int Cout, int H, int W, float* dw,
+                   float* db, float* scratch, size_t scratch_floats, cudaStream_t st) {
+    smallc_wgrad(x, dy, lddy, B, Cin, Cout, H, W, 0, dw, db, scratch, scratch_floats, st);
+}
+
+// out[b][o][p] (NCHW fp32) = bias[o] + sum_tap sum_c a[p+shift][c] * w[o][c][tap] ; Cout <= 4
+__global__ void conv_out_fwd_kernel(const bf16* __restrict__ a, int lda, const float* __restrict__ w,
+                                    const float* __restrict__ bias, int Cin, int Cout, int H, int W, size_t npix,
+                                    float* __restrict__ out) {
+    extern __shared__ float sw[];  // [9][Cin][4]
+    for (int i = threadIdx.x; i < 9 * Cin * 4; i += blockDim.x) {
+        const int o = i % 4, c = (i / 4) % Cin, tap = i / (4 * Cin);
+        sw[i] = o < Cout ? w[(size_t(o) * Cin + c) * 9 + tap] : 0.f;
+    }
+    __syncthreads();
+    const size_t p = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    const int wq = int(p % W), h = int((p / W) % H);
+    const size_t b = p / (size_t(W) * H);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int tap = 0; tap < 9; ++tap) {
+        const int hh = h + tap / 3 - 1, ww = wq + tap % 3 - 1;
+        if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+        const bf16* ap = a + ((b * H + hh) * W + ww) * lda;
+        const float* wt = sw + size_t(tap) * Cin * 4;
+        for (int c = 0; c < Cin; c += 8) {
+            float f[8];
+            ld8(ap + c, f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float4 wv = *reinterpret_cast<const float4*>(wt + (c + k) * 4);
+                acc[0] += f[k] * wv.x, acc[1] += f[k] * wv.y, acc[2] += f[k] * wv.z, acc[3] += f[k] * wv.w;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+        if (o < Cout) out[((b * Cout + o) * H + h) * W + wq] = acc[o] + bias[o];
+}
+void conv_out_fwd(const bf16* a, int lda, const float* w, const float* b, int B, int Cin, int Cout, int H, int W,
+                  float* out, cudaStream_t st) {
+    const size_t npix = size_t(B) * H * W;
+    conv_out_fwd_kernel<<<unsigned((npix + 127) / 128), 128, size_t(9) * Cin * 4 * sizeof(float), st>>>(
+        a, lda, w, b, Cin, Cout, H, W, npix, out);
+}
+
+// db[o] = sum_{b,p} dout[b][o][p]   (tiny: B*Cout*H*W fp32)
+__global__ void nchw_chansum_kernel(const float* __restrict__ x, int B, int C, size_t HW, float* __restrict__ out) {
+    const int o = blockIdx.x;
+    float s = 0.f;
+    for (int b = 0; b < B; ++b)
+        for (size_t i = threadIdx.x; i < HW; i += blockDim.x) s += x[(size_t(b) * C + o) * HW + i];
+    __shared__ float red[32];
+    for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (threadIdx.x == 0) out[o] = s;
+    }
+}
+void conv_out_wgrad(const bf16* a, int lda, const float* dout, int B, int Cin, int Cout, int H, int W, float* dw,
+                    float* db, float* scratch, size_t scratch_floats, cudaStream_t st) {
+    // D'[c][o][t'] = sum_p a[p][c] * dout[o][p + shift(t')]  ->  dw[o][c][8 - t']
+    smallc_wgrad(dout, a, lda, B, Cout, Cin, H, W, 1, dw, nullptr, scratch, scratch_floats, st);
+    nchw_chansum_kernel<<<Cout, 1024, 0, st>>>(dout, B, Cout, size_t(H) * W, db);
+}
+
+// ------------------------------------------------------------------------------------------------ loss
+__global__ void mse_kernel(const float* __restrict__ out, const float* __restrict__ y, size_t N,
+                           float* __restrict__ loss, float* __restrict__ dout, float inv_n, float gscale) {
+    float s = 0.f;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < N; i += size_t(gridDim.x) * blockDim.x) {
+        const float d = out[i] - y[i];
+        s += d * d;
+        if (dout) dout[i] = 2.f * d * inv_n * gscale;
+    }
+    __shared__ float red[32];
+    for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (threadIdx.x == 0) atomicAdd(loss, s * inv_n);
+    }
+}
+void mse_fwd_bwd(const float* out, const float* y, size_t N, float* loss, float* dout, float grad_scale,
+                 cudaStream_t st) {
+    size_t nblk = (N + 255) / 256;
+    if (nblk > size_t(kSMs) * 4) nblk = size_t(kSMs) * 4;
+    mse_kernel<<<unsigned(nblk), 256, 0, st>>>(out, y, N, loss, dout, 1.f / float(N), grad_scale);
+}
+
+}  // namespace ub

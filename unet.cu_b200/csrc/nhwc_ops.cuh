@@ -1,0 +1,62 @@
+// Memory-bound kernels of the internal (NHWC bf16) training path. All tensors are (ptr, ld) pairs:
+// element (pixel p, channel c) lives at ptr[p * ld + c]; ld lets a kernel read/write a channel slice of a
+// wider buffer (concat buffers, gradient-of-concat buffers) without a copy.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace ub {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- GroupNorm (+ optional SiLU), replaces groupnorm_forward/backward + silu_forward/backward
+//      (/root/reference/train_unet.cu:1768-1991, :305-351).
+// chsum: [B][C][2] fp32 per-(image, channel) sum and sum of squares (must be zero on entry to gn_stats).
+void gn_stats(const bf16* x, int ldx, int B, int HW, int C, float* chsum, cudaStream_t st);
+// y = act(gn(x)); also writes meanrstd[B][G][2] if non-null.
+void gn_apply(const bf16* x, int ldx, const float* chsum, const float* gamma, const float* beta, int B, int HW, int C,
+              int G, int silu, bf16* y, int ldy, float* meanrstd, cudaStream_t st);
+// Backward pass 1: S[B][C][2] = per-(image,channel) sums of dz and dz*xhat (must be zero on entry).
+void gn_bwd_stats(const bf16* x, int ldx, const bf16* dy, int lddy, const float* chsum, const float* gamma,
+                  const float* beta, int B, int HW, int C, int G, int silu, float* S, cudaStream_t st);
+// Backward pass 2: dx = gn_bwd(dy) [+ add_in]; dgamma/dbeta += (atomic); colsum_out[B][C] += sum_pix dx (optional).
+void gn_bwd_apply(const bf16* x, int ldx, const bf16* dy, int lddy, const float* chsum, const float* S,
+                  const float* gamma, const float* beta, int B, int HW, int C, int G, int silu, const bf16* add_in,
+                  int ldadd, bf16* dx, int lddx, float* dgamma, float* dbeta, float* colsum_out, cudaStream_t st);
+
+// ---- data movement (replace avgpool/upsample/concat/add of train_unet.cu:187-627)
+void avgpool2_fwd(const bf16* x, int ldx, int B, int H, int W, int C, bf16* y, int ldy, cudaStream_t st);
+// dx (H x W) = dy (H/2 x W/2) / 4 [+ add_in]
+void avgpool2_bwd(const bf16* dy, int lddy, int B, int H, int W, int C, const bf16* add_in, int ldadd, bf16* dx,
+                  int lddx, cudaStream_t st);
+// out[:, :C1] = up ? nearest_up2(a) : a ; out[:, C1:] = b.   (H, W) is the OUTPUT resolution.
+void concat2(const bf16* a, int lda, int C1, int up, const bf16* b, int ldb, int C2, int B, int H, int W, bf16* out,
+             int ldo, cudaStream_t st);
+// dx (H/2 x W/2) = sum of the 4 children of dy (H x W)
+void upsample2_bwd(const bf16* dy, int lddy, int B, int H, int W, int C, bf16* dx, int lddx, cudaStream_t st);
+void add2(const bf16* a, int lda, const bf16* b, int ldb, size_t npix, int C, bf16* out, int ldo, cudaStream_t st);
+// out[c] += sum_p x[p][c] (and out2[c] if non-null)   (fp32 atomics; outputs must be initialised)
+void colsum(const bf16* x, int ldx, size_t npix, int C, float* out, float* out2, cudaStream_t st);
+
+// ---- 3-channel convolutions (first / last layer of the U-Net) -- SIMT, negligible FLOPs
+// conv_in: x NCHW fp32 (B,Cin<=4,H,W), w (Cout,Cin,3,3) fp32 -> y NHWC bf16
+void conv_in_fwd(const float* x, const float* w, const float* b, int B, int Cin, int Cout, int H, int W, bf16* y,
+                 int ldy, cudaStream_t st);
+// dW, db of conv_in from dy NHWC bf16 (overwrite); scratch >= blocks*(Cout*Cin*9 + Cout) floats
+void conv_in_wgrad(const float* x, const bf16* dy, int lddy, int B, int Cin, int Cout, int H, int W, float* dw,
+                   float* db, float* scratch, size_t scratch_floats, cudaStream_t st);
+// conv_out: a NHWC bf16 (Cin = 64..), w (Cout<=4,Cin,3,3) -> out NCHW fp32
+void conv_out_fwd(const bf16* a, int lda, const float* w, const float* b, int B, int Cin, int Cout, int H, int W,
+                  float* out, cudaStream_t st);
+// da NHWC bf16 = conv_transpose(dout NCHW fp32, w)
+void conv_out_dgrad(const float* dout, const float* w, int B, int Cin, int Cout, int H, int W, bf16* da, int ldda,
+                    cudaStream_t st);
+void conv_out_wgrad(const bf16* a, int lda, const float* dout, int B, int Cin, int Cout, int H, int W, float* dw,
+                    float* db, float* scratch, size_t scratch_floats, cudaStream_t st);
+
+// ---- loss (replaces mse_forward/backward, train_unet.cu:2981-3030): loss += mean((out-y)^2); dout = 2(out-y)/N
+void mse_fwd_bwd(const float* out, const float* y, size_t N, float* loss, float* dout, float grad_scale,
+                 cudaStream_t st);
+
+}  // namespace ub

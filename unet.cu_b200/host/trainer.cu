@@ -1,0 +1,1180 @@
+// Host side of the training path: model graph, arena planner, step builder (eager or one CUDA graph),
+// checkpoint I/O, NCCL data parallelism.  Mirrors the responsibilities of train_unet.cu:3318-4911
+// (Unet/UnetConfig, unet_make_ptrs_and_count_memory, unet_forward/backward, unet_update, save/load) without
+// following its structure: the graph is built once as a tape of launch closures over bump-allocated NHWC bf16
+// tensors, every tcgen05 launch carries pre-encoded TMA descriptors, and the whole step replays as one graph.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "../../include/unet_b200.h"
+#include "../csrc/igemm.cuh"
+#include "../csrc/misc_ops.cuh"
+#include "../csrc/nhwc_ops.cuh"
+#include "host_common.h"
+
+namespace ub {
+void igemm_init();
+void attn_init();
+}
+extern "C" void ub_count_launches(unsigned long long n);
+
+using namespace ub;
+
+// ======================================================================================================
+// NCCL through dlopen (no link-time dependency; inside torchrun the already loaded libnccl.so.2 is reused)
+// ======================================================================================================
+namespace {
+typedef struct ncclComm* ncclComm_t;
+typedef struct {
+    char internal[128];
+} ncclUniqueId;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi& nccl() {
+    static NcclApi api;
+    if (api.lib) return api;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) return api;
+    api.GetUniqueId = (int (*)(ncclUniqueId*))dlsym(api.lib, "ncclGetUniqueId");
+    api.CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(api.lib, "ncclCommInitRank");
+    api.AllReduce =
+        (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(api.lib, "ncclAllReduce");
+    api.CommDestroy = (int (*)(ncclComm_t))dlsym(api.lib, "ncclCommDestroy");
+    api.GetErrorString = (const char* (*)(int))dlsym(api.lib, "ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy;
+    return api;
+}
+constexpr int kNcclFloat = 7;  // ncclFloat32
+constexpr int kNcclSum = 0;    // ncclSum
+}  // namespace
+
+// ======================================================================================================
+// small utilities
+// ======================================================================================================
+struct View {  // NHWC bf16 tensor view
+    bf16* p = nullptr;
+    int ld = 0;
+    int C = 0, H = 0, W = 0;
+};
+
+struct DeviceArena {
+    uint8_t* base = nullptr;
+    size_t cap = 0, off = 0;
+    bool counting = true;  // first pass: only count
+    void* alloc(size_t bytes) {
+        off = (off + 255) & ~size_t(255);
+        void* r = counting ? nullptr : base + off;
+        off += bytes;
+        return r;
+    }
+};
+
+struct ParamRef {
+    size_t off;
+    size_t n;
+};
+
+struct UbTrainer {
+    UbConfig cfg;
+    int device = 0;
+    cudaStream_t stream = nullptr, comm_stream = nullptr;
+    // flat fp32 arenas in reference order
+    size_t nparams = 0;
+    float *params = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr;
+    std::vector<ParamRef> tensors;  // every parameter tensor in order
+    // everything else lives in one bump arena
+    DeviceArena arena;
+    // zero-on-every-step region (atomically accumulated small buffers)
+    uint8_t* zero_base = nullptr;
+    size_t zero_bytes = 0;
+    DeviceArena zarena;
+    // io buffers
+    float *x0 = nullptr, *xt = nullptr, *noise = nullptr, *tsteps = nullptr, *out = nullptr, *dout = nullptr;
+    float *loss = nullptr, *sqrt_ac = nullptr, *sqrt_1mac = nullptr;
+    int* step_dev = nullptr;
+    float *h_x0 = nullptr, *h_noise = nullptr, *h_t = nullptr, *h_loss = nullptr;  // pinned staging
+    // wgrad workspace
+    float* wg_partial = nullptr;
+    size_t wg_cap = size_t(24) << 20;  // floats
+    float* small_scratch = nullptr;
+    size_t small_scratch_floats = size_t(1) << 20;
+    // tables (device)
+    PackEntry* pack_table = nullptr;
+    int n_pack = 0, pack_max_tiles = 0;
+    std::vector<PackEntry> h_pack;
+    SmallLinear *emb_table = nullptr, *temb_table = nullptr;
+    std::vector<SmallLinear> h_emb, h_temb;
+    int emb_max_oc = 0;
+    // tapes
+    typedef std::function<void(cudaStream_t)> Op;
+    std::vector<Op> fwd_ops, bwd_ops /* executed in reverse order of push */;
+    int launches_fwd = 0, launches_bwd = 0, launches_misc = 0;
+    // hyper-parameters baked into the captured graph
+    float lr = 1e-4f, b1 = 0.9f, b2 = 0.999f, eps = 1e-8f, wd = 0.f;
+    bool gen_t = true, gen_noise = true;
+    cudaGraphExec_t graph_exec = nullptr;
+    bool graph_valid = false;
+    bool graph_gen_t = false, graph_gen_noise = false, graph_h2d = false;
+    float g_lr = 0, g_b1 = 0, g_b2 = 0, g_eps = 0, g_wd = 0;
+    bool have_grads = false;
+    int host_step = 0;
+    // data parallel
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1, n_buckets = 4;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    std::vector<cudaEvent_t> bucket_events;
+    std::vector<size_t> bucket_bounds;  // param offsets, descending
+    // emb bookkeeping
+    float *sin_emb = nullptr, *h0 = nullptr, *emb = nullptr, *d_embact = nullptr, *demb = nullptr,
+          *d_h0act = nullptr, *dh0 = nullptr;
+    std::string err;
+};
+
+static thread_local std::string g_err;
+static void set_err(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+const char* ub_host_last_error() { return g_err.c_str(); }
+void ub_host_set_error(const char* s) { g_err = s; }
+
+#define CUDA_TRY(x)                                                                    \
+    do {                                                                               \
+        cudaError_t e_ = (x);                                                          \
+        if (e_ != cudaSuccess) {                                                       \
+            set_err("%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return UB_ERR_CUDA;                                                        \
+        }                                                                              \
+    } while (0)
+
+// ======================================================================================================
+// graph construction: forward tape + per-node backward builders, walked in reverse
+// ======================================================================================================
+namespace {
+
+constexpr int kMaxEmbEntries = 96;
+
+struct Builder {
+    UbTrainer* T;
+    const UbConfig& c;
+    size_t poff = 0;  // running parameter offset (reference order)
+    int B;
+    int plan_errors = 0;
+
+    struct Node {
+        std::function<View(View)> bwd;  // emits backward ops, returns gradient w.r.t. the node's main input
+        bool pushed = false;            // output was pushed on the skip stack
+        View out;                       // output view (shape used for the skip-gradient add)
+        size_t param_begin = 0;         // parameters of nodes >= this one start here
+    };
+    std::vector<Node> nodes;
+    std::vector<View> skipgrad;  // per node: gradient arriving from the up path
+
+    explicit Builder(UbTrainer* t) : T(t), c(t->cfg), B(t->cfg.B) {}
+
+    size_t take(size_t n) {
+        size_t o = poff;
+        poff += n;
+        if (real()) T->tensors.push_back({o, n});
+        return o;
+    }
+    float* P(size_t off) const { return T->params + off; }
+    float* G(size_t off) const { return T->grads + off; }
+
+    View act(int C, int H, int W) {
+        View v;
+        v.p = (bf16*)T->arena.alloc(size_t(B) * H * W * C * sizeof(bf16));
+        v.ld = C, v.C = C, v.H = H, v.W = W;
+        return v;
+    }
+    float* f32(size_t n) { return (float*)T->arena.alloc(n * sizeof(float)); }
+    float* zf32(size_t n) { return (float*)T->zarena.alloc(n * sizeof(float)); }
+    bf16* packbuf(size_t n) { return (bf16*)T->arena.alloc(n * sizeof(bf16)); }
+
+    bool real() const { return !T->arena.counting; }
+    void F(UbTrainer::Op op, int launches = 1) {
+        if (real()) T->fwd_ops.push_back(std::move(op)), T->launches_fwd += launches;
+    }
+    void Bk(UbTrainer::Op op, int launches = 1) {
+        if (real()) T->bwd_ops.push_back(std::move(op)), T->launches_bwd += launches;
+    }
+
+    struct Packed {
+        bf16 *wf = nullptr, *wd = nullptr;
+    };
+    Packed pack(size_t woff, int Cout, int Cin, int ntaps) {
+        Packed pk;
+        pk.wf = packbuf(size_t(ntaps) * Cout * Cin);
+        pk.wd = packbuf(size_t(ntaps) * Cout * Cin);
+        if (real()) {
+            T->h_pack.push_back({P(woff), pk.wf, pk.wd, Cout, Cin, ntaps});
+            int tiles = ((Cout + 31) / 32) * ((Cin + 31) / 32);
+            if (tiles > T->pack_max_tiles) T->pack_max_tiles = tiles;
+        }
+        return pk;
+    }
+
+    void conv_op(bool fwd, std::vector<ConvSegDesc> segs, int H, int W, int Cout, ConvEpilogue ep) {
+        if (!real()) return;
+        IgemmConvParams p;
+        int r = igemm_conv_plan(&p, segs.data(), int(segs.size()), B, H, W, Cout, ep);
+        if (r) {
+            set_err("igemm_conv_plan failed (%d) for %dx%d Cout=%d Cin0=%d", r, H, W, Cout, segs[0].Cin);
+            plan_errors++;
+            return;
+        }
+        auto op = [p](cudaStream_t st) { igemm_conv_launch(p, st); };
+        if (fwd)
+            F(op);
+        else
+            Bk(op);
+    }
+    void wgrad_op(View dy, View x, int Cin, int Cout, int ntaps, float* dw) {
+        if (!real()) return;
+        IgemmWgradParams p;
+        int r = igemm_wgrad_plan(&p, dy.p, dy.ld, x.p, x.ld, B, x.H, x.W, Cin, Cout, ntaps, T->wg_partial, T->wg_cap,
+                                 148);
+        if (r) {
+            set_err("igemm_wgrad_plan failed (%d) for %dx%d %d->%d", r, x.H, x.W, Cin, Cout);
+            plan_errors++;
+            return;
+        }
+        Bk([p, dw](cudaStream_t st) {
+            igemm_wgrad_launch(p, st);
+            igemm_wgrad_reduce(p, dw, st);
+        }, 2);
+    }
+
+    struct GN {
+        size_t w, b;
+        float *chsum, *S;
+    };
+    GN gn_fwd(View x, View y, int silu) {
+        GN g;
+        g.w = take(x.C), g.b = take(x.C);
+        g.chsum = zf32(size_t(B) * x.C * 2);
+        g.S = zf32(size_t(B) * x.C * 2);
+        const int HW = x.H * x.W, Gn = c.gn_n_groups, Bn = B;
+        float *gw = P(g.w), *gb = P(g.b), *cs = g.chsum;
+        F([=](cudaStream_t st) {
+            gn_stats(x.p, x.ld, Bn, HW, x.C, cs, st);
+            gn_apply(x.p, x.ld, cs, gw, gb, Bn, HW, x.C, Gn, silu, y.p, y.ld, nullptr, st);
+        }, 2);
+        return g;
+    }
+    void gn_bwd(const GN& g, View x, View dy, int silu, View add_in, View dx, float* colsum_out) {
+        const int HW = x.H * x.W, Gn = c.gn_n_groups, Bn = B;
+        float *gw = P(g.w), *gb = P(g.b), *cs = g.chsum, *S = g.S, *dgw = G(g.w), *dgb = G(g.b);
+        Bk([=](cudaStream_t st) {
+            gn_bwd_stats(x.p, x.ld, dy.p, dy.ld, cs, gw, gb, Bn, HW, x.C, Gn, silu, S, st);
+            gn_bwd_apply(x.p, x.ld, dy.p, dy.ld, cs, S, gw, gb, Bn, HW, x.C, Gn, silu, add_in.p, add_in.ld, dx.p,
+                         dx.ld, dgw, dgb, colsum_out, st);
+        }, 2);
+    }
+
+    int res_index = 0;
+
+    // ResBlock (dev/resblock.py:107-160, train_unet.cu:2213-2384)
+    View resblock(View x, int Cout) {
+        Node nd;
+        nd.param_begin = poff;
+        const int C = x.C, H = x.H, W = x.W, Cemb = 4 * c.C_model;
+        const int blk = res_index++;
+        View a1 = act(C, H, W);
+        GN g1 = gn_fwd(x, a1, 1);
+        const size_t w1 = take(size_t(Cout) * C * 9), b1 = take(Cout);
+        const size_t wl = take(size_t(Cout) * Cemb), bl = take(Cout);
+        View h1 = act(Cout, H, W);
+        float* embproj = f32(size_t(B) * Cout);
+        float* d_embproj = zf32(size_t(B) * Cout);
+        Packed p1 = pack(w1, Cout, C, 9);
+        {
+            ConvEpilogue ep;
+            ep.bias = P(b1), ep.rowvec = embproj, ep.out = h1.p, ep.ldo = h1.ld;
+            conv_op(true, {{a1.p, C, a1.ld, p1.wf, 9}}, H, W, Cout, ep);
+        }
+        View a2 = act(Cout, H, W);
+        GN g2 = gn_fwd(h1, a2, 1);
+        const size_t w2 = take(size_t(Cout) * Cout * 9), b2 = take(Cout);
+        Packed p2 = pack(w2, Cout, Cout, 9);
+        const bool proj = C != Cout;
+        size_t ws = 0, bs = 0;
+        Packed ps;
+        if (proj) {
+            ws = take(size_t(Cout) * C), bs = take(Cout);
+            ps = pack(ws, Cout, C, 1);
+        }
+        View out = act(Cout, H, W);
+        {
+            ConvEpilogue ep;
+            ep.bias = P(b2), ep.out = out.p, ep.ldo = out.ld;
+            std::vector<ConvSegDesc> segs = {{a2.p, Cout, a2.ld, p2.wf, 9}};
+            if (proj) {
+                segs.push_back({x.p, C, x.ld, ps.wf, 1});
+                ep.bias2 = P(bs);
+            } else {
+                ep.residual = x.p, ep.ldr = x.ld;
+            }
+            conv_op(true, segs, H, W, Cout, ep);
+        }
+        if (real()) {
+            SmallLinear e{};
+            e.w = P(wl), e.b = P(bl), e.inp = T->emb, e.out = embproj, e.C = Cemb, e.OC = Cout, e.silu_in = 1;
+            e.dout = d_embproj, e.dw = G(wl), e.db = G(bl), e.db2 = G(b1), e.dinp = T->d_embact;
+            T->h_emb.push_back(e);
+            if (Cout > T->emb_max_oc) T->emb_max_oc = Cout;
+        }
+        nd.out = out;
+        nd.bwd = [=](View dout) -> View {
+            View da2 = act(Cout, H, W), dh1 = act(Cout, H, W), da1 = act(C, H, W), dxg = act(C, H, W);
+            View dxo = proj ? act(C, H, W) : dxg;
+            const size_t npix = size_t(B) * H * W;
+            float *gb2 = G(b2), *gbs = proj ? G(bs) : nullptr;
+            UbTrainer* Tt = T;
+            const int Bn = B;
+            // bias / weight gradients of conv2 (and of the fused 1x1 skip conv)
+            Bk([=](cudaStream_t st) { colsum(dout.p, dout.ld, npix, Cout, gb2, gbs, st); });
+            wgrad_op(dout, a2, Cout, Cout, 9, G(w2));
+            if (proj) wgrad_op(dout, x, C, Cout, 1, G(ws));
+            {
+                ConvEpilogue ep;
+                ep.out = da2.p, ep.ldo = da2.ld;
+                conv_op(false, {{dout.p, Cout, dout.ld, p2.wd, 9}}, H, W, Cout, ep);
+            }
+            // GN2 + SiLU backward; per-image column sums of dh1 feed the embedding-projection backward
+            gn_bwd(g2, h1, da2, 1, View{}, dh1, d_embproj);
+            Bk([=](cudaStream_t st) { small_linear_bwd(Tt->emb_table + blk, 1, Bn, Cout, Cemb, st); }, 2);
+            wgrad_op(dh1, a1, C, Cout, 9, G(w1));
+            {
+                ConvEpilogue ep;
+                ep.out = da1.p, ep.ldo = da1.ld;
+                conv_op(false, {{dh1.p, Cout, dh1.ld, p1.wd, 9}}, H, W, C, ep);
+            }
+            gn_bwd(g1, x, da1, 1, proj ? View{} : dout, dxg, nullptr);
+            if (proj) {
+                ConvEpilogue ep;
+                ep.out = dxo.p, ep.ldo = dxo.ld, ep.residual = dxg.p, ep.ldr = dxg.ld;
+                conv_op(false, {{dout.p, Cout, dout.ld, ps.wd, 1}}, H, W, C, ep);
+            }
+            return dxo;
+        };
+        nodes.push_back(nd);
+        return out;
+    }
+
+    // AttentionBlock (dev/unet.py:44-58, train_unet.cu:2933-2976)
+    View attnblock(View x) {
+        Node nd;
+        nd.param_begin = poff;
+        const int C = x.C, H = x.H, W = x.W, Tn = H * W, NH = C / c.head_size, HSz = c.head_size;
+        View g = act(C, H, W);
+        GN gn = gn_fwd(x, g, 0);
+        const size_t wq = take(size_t(3) * C * C), bq = take(size_t(3) * C);
+        const size_t wp = take(size_t(C) * C), bp = take(C);
+        Packed pq = pack(wq, 3 * C, C, 1), pp = pack(wp, C, C, 1);
+        View qkv = act(3 * C, H, W), ao = act(C, H, W), out = act(C, H, W);
+        float* lse = f32(size_t(B) * NH * Tn);
+        float* dsum = f32(size_t(B) * NH * Tn);
+        {
+            ConvEpilogue ep;
+            ep.bias = P(bq), ep.out = qkv.p, ep.ldo = qkv.ld;
+            conv_op(true, {{g.p, C, g.ld, pq.wf, 1}}, H, W, 3 * C, ep);
+        }
+        const int Bn = B;
+        F([=](cudaStream_t st) { attn_fwd(qkv.p, qkv.ld, Bn, Tn, NH, HSz, ao.p, ao.ld, lse, st); });
+        {
+            ConvEpilogue ep;
+            ep.bias = P(bp), ep.out = out.p, ep.ldo = out.ld, ep.residual = x.p, ep.ldr = x.ld;
+            conv_op(true, {{ao.p, C, ao.ld, pp.wf, 1}}, H, W, C, ep);
+        }
+        nd.out = out;
+        nd.bwd = [=](View dout) -> View {
+            View dao = act(C, H, W), dqkv = act(3 * C, H, W), dg = act(C, H, W), dx = act(C, H, W);
+            const size_t npix = size_t(B) * H * W;
+            float *gbp = G(bp), *gbq = G(bq);
+            Bk([=](cudaStream_t st) { colsum(dout.p, dout.ld, npix, C, gbp, nullptr, st); });
+            wgrad_op(dout, ao, C, C, 1, G(wp));
+            {
+                ConvEpilogue ep;
+                ep.out = dao.p, ep.ldo = dao.ld;
+                conv_op(false, {{dout.p, C, dout.ld, pp.wd, 1}}, H, W, C, ep);
+            }
+            Bk([=](cudaStream_t st) {
+                attn_bwd(qkv.p, qkv.ld, ao.p, ao.ld, dao.p, dao.ld, lse, Bn, Tn, NH, HSz, dqkv.p, dqkv.ld, dsum, st);
+            }, 2);
+            Bk([=](cudaStream_t st) { colsum(dqkv.p, dqkv.ld, npix, 3 * C, gbq, nullptr, st); });
+            wgrad_op(dqkv, g, C, 3 * C, 1, G(wq));
+            {
+                ConvEpilogue ep;
+                ep.out = dg.p, ep.ldo = dg.ld;
+                conv_op(false, {{dqkv.p, 3 * C, dqkv.ld, pq.wd, 1}}, H, W, C, ep);
+            }
+            gn_bwd(gn, x, dg, 0, dout, dx, nullptr);
+            return dx;
+        };
+        nodes.push_back(nd);
+        return out;
+    }
+
+    int build();
+};
+
+int Builder::build() {
+    const int Cm = c.C_model, Cemb = 4 * Cm, H0 = c.H, W0 = c.W;
+    const size_t img = size_t(c.C_in) * H0 * W0;
+    UbTrainer* Tt = T;
+    const int Bn = B;
+    // io + small fp32 state
+    T->x0 = f32(size_t(B) * img), T->xt = f32(size_t(B) * img), T->noise = f32(size_t(B) * img);
+    T->tsteps = f32(B);
+    T->out = f32(size_t(B) * c.C_out * H0 * W0), T->dout = f32(size_t(B) * c.C_out * H0 * W0);
+    T->sqrt_ac = f32(c.n_timesteps), T->sqrt_1mac = f32(c.n_timesteps);
+    T->step_dev = (int*)T->arena.alloc(256);
+    T->loss = zf32(64);
+    T->sin_emb = f32(size_t(B) * Cm), T->h0 = f32(size_t(B) * Cemb), T->emb = f32(size_t(B) * Cemb);
+    T->d_embact = zf32(size_t(B) * Cemb), T->demb = f32(size_t(B) * Cemb);
+    T->d_h0act = zf32(size_t(B) * Cemb), T->dh0 = f32(size_t(B) * Cemb);
+    T->wg_partial = f32(T->wg_cap);
+    T->small_scratch = f32(T->small_scratch_floats);
+    T->emb_table = (SmallLinear*)T->arena.alloc(kMaxEmbEntries * sizeof(SmallLinear));
+    T->temb_table = (SmallLinear*)T->arena.alloc(2 * sizeof(SmallLinear));
+    T->pack_table = (PackEntry*)T->arena.alloc(256 * sizeof(PackEntry));
+
+    // ---- time-embedding MLP (dev/unet.py:176-180); its forward and all 22 embedding projections run first
+    const size_t tw0 = take(size_t(Cemb) * Cm), tb0 = take(Cemb), tw1 = take(size_t(Cemb) * Cemb), tb1 = take(Cemb);
+    if (real()) {
+        SmallLinear e0{}, e1{};
+        e0.w = P(tw0), e0.b = P(tb0), e0.inp = T->sin_emb, e0.out = T->h0, e0.C = Cm, e0.OC = Cemb, e0.silu_in = 0;
+        e0.dout = T->dh0, e0.dw = G(tw0), e0.db = G(tb0);
+        e1.w = P(tw1), e1.b = P(tb1), e1.inp = T->h0, e1.out = T->emb, e1.C = Cemb, e1.OC = Cemb, e1.silu_in = 1;
+        e1.dout = T->demb, e1.dw = G(tw1), e1.db = G(tb1), e1.dinp = T->d_h0act;
+        T->h_temb = {e0, e1};
+    }
+    {
+        const int mp = c.max_period;
+        F([=](cudaStream_t st) {
+            timestep_embedding(Tt->tsteps, Bn, Cm, mp, Tt->sin_emb, st);
+            small_linear_fwd(Tt->temb_table, 1, Bn, Cemb, st);
+            small_linear_fwd(Tt->temb_table + 1, 1, Bn, Cemb, st);
+            small_linear_fwd(Tt->emb_table, int(Tt->h_emb.size()), Bn, Tt->emb_max_oc, st);
+        }, 4);
+    }
+    const size_t time_mlp_end = poff;
+
+    // ---- input conv (dev/unet.py:183-185)
+    int ch = c.channel_mult[0] * Cm;
+    View h = act(ch, H0, W0);
+    {
+        Node nd;
+        nd.param_begin = poff;
+        const size_t wi = take(size_t(ch) * c.C_in * 9), bi = take(ch);
+        float *w = P(wi), *b = P(bi), *gw = G(wi), *gb = G(bi);
+        const int Cin = c.C_in;
+        View hv = h;
+        F([=](cudaStream_t st) { conv_in_fwd(Tt->xt, w, b, Bn, Cin, hv.C, hv.H, hv.W, hv.p, hv.ld, st); });
+        nd.out = h, nd.pushed = true;
+        nd.bwd = [=](View dout) -> View {
+            Bk([=](cudaStream_t st) {
+                conv_in_wgrad(Tt->xt, dout.p, dout.ld, Bn, Cin, hv.C, hv.H, hv.W, gw, gb, Tt->small_scratch,
+                              Tt->small_scratch_floats, st);
+            }, 2);
+            return View{};
+        };
+        nodes.push_back(nd);
+    }
+    std::vector<int> skip_stack = {0};  // node ids whose outputs are on the skip stack
+    std::vector<View> skip_views = {h};
+
+    const int nlev = c.n_levels;
+    for (int level = 0; level < nlev; ++level) {
+        const int cout = c.channel_mult[level] * Cm;
+        for (int i = 0; i < c.n_res_blocks; ++i) {
+            h = resblock(h, cout);
+            if (level >= c.att_start_level) h = attnblock(h);
+            nodes.back().pushed = true;
+            skip_stack.push_back(int(nodes.size()) - 1);
+            skip_views.push_back(h);
+        }
+        if (level != nlev - 1) {  // Downsample (dev/resblock.py:34-43)
+            Node nd;
+            nd.param_begin = poff;
+            View x = h, y = act(h.C, h.H / 2, h.W / 2);
+            F([=](cudaStream_t st) { avgpool2_fwd(x.p, x.ld, Bn, x.H, x.W, x.C, y.p, y.ld, st); });
+            nd.out = y, nd.pushed = true;
+            nd.bwd = [=](View dout) -> View {
+                View dx = act(x.C, x.H, x.W);
+                Bk([=](cudaStream_t st) {
+                    avgpool2_bwd(dout.p, dout.ld, Bn, x.H, x.W, x.C, nullptr, 0, dx.p, dx.ld, st);
+                });
+                return dx;
+            };
+            nodes.push_back(nd);
+            h = y;
+            skip_stack.push_back(int(nodes.size()) - 1);
+            skip_views.push_back(h);
+        }
+    }
+    // ---- middle (dev/unet.py:224-243)
+    h = resblock(h, h.C);
+    h = attnblock(h);
+    h = resblock(h, h.C);
+    // ---- up path (dev/unet.py:246-284)
+    bool pending_up = false;
+    for (int level = nlev - 1; level >= 0; --level) {
+        const int cout = c.channel_mult[level] * Cm;
+        for (int i = 0; i <= c.n_res_blocks; ++i) {
+            const int src = skip_stack.back();
+            View sk = skip_views.back();
+            skip_stack.pop_back(), skip_views.pop_back();
+            // concat (+ fused nearest x2 upsample of the main path, dev/resblock.py:25-32)
+            Node nd;
+            nd.param_begin = poff;
+            const int C1 = h.C, C2 = sk.C, Hc = sk.H, Wc = sk.W, up = pending_up ? 1 : 0;
+            View cat = act(C1 + C2, Hc, Wc), a = h;
+            F([=](cudaStream_t st) { concat2(a.p, a.ld, C1, up, sk.p, sk.ld, C2, Bn, Hc, Wc, cat.p, cat.ld, st); });
+            nd.out = cat;
+            std::vector<View>* sg = &skipgrad;
+            nd.bwd = [=](View d) -> View {
+                View skv = d;  // gradient of the skip half is a channel-slice view of d(cat): no copy
+                skv.p = d.p ? d.p + C1 : nullptr, skv.C = C2;
+                (*sg)[src] = skv;
+                if (up) {
+                    View dlow = act(C1, Hc / 2, Wc / 2);
+                    Bk([=](cudaStream_t st) { upsample2_bwd(d.p, d.ld, Bn, Hc, Wc, C1, dlow.p, dlow.ld, st); });
+                    return dlow;
+                }
+                View mv = d;
+                mv.C = C1;
+                return mv;
+            };
+            nodes.push_back(nd);
+            pending_up = false;
+            h = resblock(cat, cout);
+            if (level >= c.att_start_level) h = attnblock(h);
+            if (level && i == c.n_res_blocks) pending_up = true;
+        }
+    }
+    // ---- output head: GN + SiLU + conv3x3 (-> C_out) + MSE (dev/unet.py:286-290, train_unet.cu:4408-4418)
+    {
+        Node nd;
+        nd.param_begin = poff;
+        View ao = act(h.C, h.H, h.W), hx = h;
+        GN g = gn_fwd(h, ao, 1);
+        const size_t wo = take(size_t(c.C_out) * h.C * 9), bo = take(c.C_out);
+        float *w = P(wo), *b = P(bo), *gw = G(wo), *gb = G(bo);
+        const int Cin = h.C, Co = c.C_out, Hh = h.H, Ww = h.W;
+        const size_t N = size_t(B) * c.C_out * h.H * h.W;
+        F([=](cudaStream_t st) {
+            conv_out_fwd(ao.p, ao.ld, w, b, Bn, Cin, Co, Hh, Ww, Tt->out, st);
+            mse_fwd_bwd(Tt->out, Tt->noise, N, Tt->loss, Tt->dout, 1.f, st);
+        }, 2);
+        nd.out = View{};
+        nd.bwd = [=](View) -> View {
+            View dao = act(Cin, Hh, Ww), dh = act(Cin, Hh, Ww);
+            Bk([=](cudaStream_t st) {
+                conv_out_wgrad(ao.p, ao.ld, Tt->dout, Bn, Cin, Co, Hh, Ww, gw, gb, Tt->small_scratch,
+                               Tt->small_scratch_floats, st);
+                conv_out_dgrad(Tt->dout, w, Bn, Cin, Co, Hh, Ww, dao.p, dao.ld, st);
+            }, 4);
+            gn_bwd(g, hx, dao, 1, View{}, dh, nullptr);
+            return dh;
+        };
+        nodes.push_back(nd);
+    }
+    if (real() && poff != T->nparams) {
+        set_err("parameter count mismatch: built %zu, expected %zu", poff, T->nparams);
+        return UB_ERR_SHAPE;
+    }
+    // ---- backward: walk the nodes in reverse.  Gradient buckets (data parallel): parameters live in forward
+    //      order, so once node i's backward has been emitted every parameter at offset >= node[i].param_begin is
+    //      final (the time MLP at the head of the arena finishes last).
+    skipgrad.assign(nodes.size(), View{});
+    std::vector<size_t> cuts;  // descending offsets at which a bucket is flushed
+    {
+        const int nb = T->n_buckets < 1 ? 1 : T->n_buckets;
+        for (int k = nb - 1; k >= 1; --k) cuts.push_back(T->nparams * size_t(k) / nb);
+    }
+    size_t flushed_hi = T->nparams;
+    size_t cut_i = 0;
+    int bucket_no = 0;
+    auto flush_bucket = [&](size_t lo, size_t hi) {
+        if (hi <= lo) return;
+        const int k = bucket_no++;
+        Bk([=](cudaStream_t st) {
+            if (Tt->world <= 1) return;
+            cudaEvent_t ev = Tt->bucket_events[k % Tt->bucket_events.size()];
+            cudaEventRecord(ev, st);
+            cudaStreamWaitEvent(Tt->comm_stream, ev, 0);
+            nccl().AllReduce(Tt->grads + lo, Tt->grads + lo, hi - lo, kNcclFloat, kNcclSum, Tt->comm, Tt->comm_stream);
+        }, 0);
+    };
+    View g{};
+    for (int i = int(nodes.size()) - 1; i >= 0; --i) {
+        Node& nd = nodes[i];
+        if (nd.pushed) {  // gradient of a tensor that also fed a skip connection: sum both contributions
+            View s = skipgrad[i];
+            View sum = act(nd.out.C, nd.out.H, nd.out.W);
+            View a = g;
+            const size_t npix = size_t(B) * nd.out.H * nd.out.W;
+            const int C = nd.out.C;
+            Bk([=](cudaStream_t st) { add2(a.p, a.ld, s.p, s.ld, npix, C, sum.p, sum.ld, st); });
+            g = sum;
+        }
+        g = nd.bwd(g);
+        while (cut_i < cuts.size() && nd.param_begin <= cuts[cut_i] && nd.param_begin > time_mlp_end) {
+            flush_bucket(nd.param_begin, flushed_hi);
+            flushed_hi = nd.param_begin;
+            while (cut_i < cuts.size() && cuts[cut_i] >= nd.param_begin) ++cut_i;
+        }
+    }
+    // time MLP backward (needs the complete d_embact), then the last bucket
+    Bk([=](cudaStream_t st) {
+        dsilu_mul(Tt->d_embact, Tt->emb, Tt->demb, size_t(Bn) * Cemb, st);
+        small_linear_bwd(Tt->temb_table + 1, 1, Bn, Cemb, Cemb, st);
+        dsilu_mul(Tt->d_h0act, Tt->h0, Tt->dh0, size_t(Bn) * Cemb, st);
+        small_linear_bwd(Tt->temb_table, 1, Bn, Cemb, Cm, st);
+    }, 6);
+    flush_bucket(0, flushed_hi);
+    Bk([=](cudaStream_t st) {  // join the communication stream
+        if (Tt->world <= 1) return;
+        cudaEventRecord(Tt->ev_join, Tt->comm_stream);
+        cudaStreamWaitEvent(st, Tt->ev_join, 0);
+    }, 0);
+    return plan_errors ? UB_ERR_SHAPE : UB_OK;
+}
+
+}  // namespace
+
+// ======================================================================================================
+// trainer lifetime
+// ======================================================================================================
+extern "C" void ub_default_config(UbConfig* cfg) {
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->B = 32, cfg->C_in = 3, cfg->C_model = 64, cfg->C_out = 3, cfg->H = 64, cfg->W = 64;
+    cfg->max_period = 1000, cfg->n_levels = 4;
+    cfg->channel_mult[0] = 1, cfg->channel_mult[1] = 2, cfg->channel_mult[2] = 3, cfg->channel_mult[3] = 4;
+    cfg->n_res_blocks = 2, cfg->att_start_level = 2, cfg->head_size = 32, cfg->gn_n_groups = 32;
+    cfg->n_timesteps = 1000, cfg->seed = 0x5eedULL, cfg->use_cuda_graph = 1;
+}
+
+static int validate_config(const UbConfig& c) {
+    if (c.B < 1 || c.C_in < 1 || c.C_in > 4 || c.C_out < 1 || c.C_out > 4 || c.n_levels < 1 || c.n_levels > 8) {
+        set_err("bad config: B/C_in/C_out/n_levels out of range");
+        return UB_ERR_SHAPE;
+    }
+    if (c.C_model % 64 != 0) {
+        set_err("C_model must be a multiple of 64 (tcgen05 K blocks of 64 channels)");
+        return UB_ERR_SHAPE;
+    }
+    if (c.head_size != 32) {
+        set_err("head_size must be 32");
+        return UB_ERR_SHAPE;
+    }
+    if ((c.H >> (c.n_levels - 1)) < 1 || c.H % (1 << (c.n_levels - 1)) || c.W % (1 << (c.n_levels - 1))) {
+        set_err("H, W must be divisible by 2^(n_levels-1)");
+        return UB_ERR_SHAPE;
+    }
+    if ((size_t(c.C_in) * c.H * c.W) % 4) {
+        set_err("C_in*H*W must be a multiple of 4");
+        return UB_ERR_SHAPE;
+    }
+    for (int l = 0; l < c.n_levels; ++l)
+        if ((c.channel_mult[l] * c.C_model) % c.gn_n_groups) {
+            set_err("channels not divisible by gn groups");
+            return UB_ERR_SHAPE;
+        }
+    return UB_OK;
+}
+
+extern "C" size_t ub_num_params(const UbConfig* cfg) {
+    UbTrainer tmp;
+    tmp.cfg = *cfg;
+    if (validate_config(tmp.cfg)) return 0;
+    tmp.arena.counting = tmp.zarena.counting = true;
+    Builder b(&tmp);
+    b.build();
+    return b.poff;
+}
+
+static int upload_tables(UbTrainer* t) {
+    if (t->h_emb.size() > size_t(kMaxEmbEntries) || t->h_pack.size() > 256) {
+        set_err("table overflow");
+        return UB_ERR_SHAPE;
+    }
+    CUDA_TRY(cudaMemcpy(t->emb_table, t->h_emb.data(), t->h_emb.size() * sizeof(SmallLinear), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(t->temb_table, t->h_temb.data(), 2 * sizeof(SmallLinear), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(t->pack_table, t->h_pack.data(), t->h_pack.size() * sizeof(PackEntry), cudaMemcpyHostToDevice));
+    t->n_pack = int(t->h_pack.size());
+    return UB_OK;
+}
+
+static void run_pack(UbTrainer* t, cudaStream_t st) { pack_weights(t->pack_table, t->n_pack, t->pack_max_tiles, st); }
+
+extern "C" int ub_trainer_create(UbTrainer** out, const UbConfig* cfg, int device) {
+    *out = nullptr;
+    int r = validate_config(*cfg);
+    if (r) return r;
+    CUDA_TRY(cudaSetDevice(device));
+    igemm_init();
+    attn_init();
+    UbTrainer* t = new UbTrainer();
+    t->cfg = *cfg;
+    t->device = device;
+    // pass 1: count
+    t->arena.counting = t->zarena.counting = true;
+    {
+        Builder b(t);
+        b.build();
+        t->nparams = b.poff;
+    }
+    const size_t arena_bytes = t->arena.off + 4096, zero_bytes = t->zarena.off + 4096;
+    const size_t pbytes = (t->nparams * sizeof(float) + 255) & ~size_t(255);
+    uint8_t* blob = nullptr;
+    cudaError_t e = cudaMalloc(&blob, 4 * pbytes + arena_bytes + zero_bytes);
+    if (e != cudaSuccess) {
+        set_err("cudaMalloc of %zu MiB failed: %s", (4 * pbytes + arena_bytes + zero_bytes) >> 20,
+                cudaGetErrorString(e));
+        delete t;
+        return UB_ERR_CUDA;
+    }
+    cudaMemset(blob, 0, 4 * pbytes + arena_bytes + zero_bytes);
+    t->params = (float*)blob, t->grads = (float*)(blob + pbytes), t->m = (float*)(blob + 2 * pbytes),
+    t->v = (float*)(blob + 3 * pbytes);
+    t->arena.base = blob + 4 * pbytes, t->arena.cap = arena_bytes, t->arena.off = 0, t->arena.counting = false;
+    t->zarena.base = blob + 4 * pbytes + arena_bytes, t->zarena.cap = zero_bytes, t->zarena.off = 0,
+    t->zarena.counting = false;
+    t->zero_base = t->zarena.base, t->zero_bytes = zero_bytes;
+    cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&t->comm_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming);
+    t->bucket_events.resize(16);
+    for (auto& ev : t->bucket_events) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    // pass 2: build
+    {
+        Builder b(t);
+        r = b.build();
+        if (r) {
+            ub_trainer_destroy(t);
+            return r;
+        }
+    }
+    r = upload_tables(t);
+    if (r) {
+        ub_trainer_destroy(t);
+        return r;
+    }
+    // diffusion tables: float32 cumprod of (1 - beta), beta = float32(linspace_f64(1e-4, 0.02)) scaled
+    // (train_unet.py:811-826, 875-892; train_unet.cu:3131-3147)
+    {
+        const int n = cfg->n_timesteps;
+        std::vector<float> sa(n), sb(n);
+        const double scale = 1000.0 / n, b0 = scale * 0.0001, b1 = scale * 0.02;
+        float ac = 1.f;
+        for (int i = 0; i < n; ++i) {
+            const float beta = float(n > 1 ? b0 + (b1 - b0) * double(i) / double(n - 1) : b0);
+            ac = ac * (1.f - beta);
+            sa[i] = sqrtf(ac), sb[i] = sqrtf(1.f - ac);
+        }
+        cudaMemcpy(t->sqrt_ac, sa.data(), n * sizeof(float), cudaMemcpyHostToDevice);
+        cudaMemcpy(t->sqrt_1mac, sb.data(), n * sizeof(float), cudaMemcpyHostToDevice);
+    }
+    const size_t img = size_t(cfg->B) * cfg->C_in * cfg->H * cfg->W;
+    cudaMallocHost(&t->h_x0, img * sizeof(float));
+    cudaMallocHost(&t->h_noise, img * sizeof(float));
+    cudaMallocHost(&t->h_t, cfg->B * sizeof(float));
+    cudaMallocHost(&t->h_loss, 64);
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        set_err("trainer init failed: %s", cudaGetErrorString(e));
+        ub_trainer_destroy(t);
+        return UB_ERR_CUDA;
+    }
+    *out = t;
+    return UB_OK;
+}
+
+extern "C" void ub_trainer_destroy(UbTrainer* t) {
+    if (!t) return;
+    cudaSetDevice(t->device);
+    cudaDeviceSynchronize();
+    if (t->graph_exec) cudaGraphExecDestroy(t->graph_exec);
+    if (t->comm && nccl().ok) nccl().CommDestroy(t->comm);
+    if (t->params) cudaFree(t->params);
+    if (t->h_x0) cudaFreeHost(t->h_x0);
+    if (t->h_noise) cudaFreeHost(t->h_noise);
+    if (t->h_t) cudaFreeHost(t->h_t);
+    if (t->h_loss) cudaFreeHost(t->h_loss);
+    for (auto ev : t->bucket_events) cudaEventDestroy(ev);
+    if (t->ev_join) cudaEventDestroy(t->ev_join);
+    if (t->stream) cudaStreamDestroy(t->stream);
+    if (t->comm_stream) cudaStreamDestroy(t->comm_stream);
+    delete t;
+}
+
+// ======================================================================================================
+// running the tapes
+// ======================================================================================================
+struct StepOpts {
+    bool gen_t, gen_noise, update;
+    float lr, b1, b2, eps, wd;
+};
+
+// everything of one step that lives on the device, in stream order (this is what gets captured into the graph)
+static void enqueue_step(UbTrainer* t, const StepOpts& o, cudaStream_t st) {
+    const UbConfig& c = t->cfg;
+    cudaMemsetAsync(t->zero_base, 0, t->zero_bytes, st);
+    diffusion_prepare(t->x0, t->sqrt_ac, t->sqrt_1mac, c.B, size_t(c.C_in) * c.H * c.W, c.n_timesteps, c.seed,
+                      t->step_dev, o.gen_t ? 1 : 0, o.gen_noise ? 1 : 0, t->tsteps, t->noise, t->xt, st);
+    for (auto& op : t->fwd_ops) op(st);
+    for (auto& op : t->bwd_ops) op(st);
+    if (o.update) {
+        adamw_step(t->params, t->grads, t->m, t->v, t->nparams, o.lr, o.b1, o.b2, o.eps, o.wd, 1.f / float(t->world),
+                   t->step_dev, st);
+        run_pack(t, st);
+        increment_step(t->step_dev, st);
+    }
+}
+
+static int ensure_packed(UbTrainer* t) {
+    run_pack(t, t->stream);
+    return UB_OK;
+}
+
+static int stage_inputs(UbTrainer* t, const float* x0_host, const float* t_host, const float* noise_host) {
+    const UbConfig& c = t->cfg;
+    const size_t img = size_t(c.B) * c.C_in * c.H * c.W;
+    CUDA_TRY(cudaMemcpyAsync(t->x0, x0_host, img * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+    if (t_host) CUDA_TRY(cudaMemcpyAsync(t->tsteps, t_host, c.B * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+    if (noise_host)
+        CUDA_TRY(cudaMemcpyAsync(t->noise, noise_host, img * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+    return UB_OK;
+}
+
+static int fetch_loss(UbTrainer* t, float* loss_out) {
+    CUDA_TRY(cudaMemcpyAsync(t->h_loss, t->loss, sizeof(float), cudaMemcpyDeviceToHost, t->stream));
+    CUDA_TRY(cudaStreamSynchronize(t->stream));
+    *loss_out = *t->h_loss;
+    return UB_OK;
+}
+
+extern "C" int ub_trainer_forward_backward(UbTrainer* t, const float* x0_host, const float* t_host,
+                                           const float* noise_host, float* loss_out) {
+    CUDA_TRY(cudaSetDevice(t->device));
+    int r = stage_inputs(t, x0_host, t_host, noise_host);
+    if (r) return r;
+    // gradients accumulate in parts of the arena (GroupNorm affine, biases): start from zero like unet_zero_grad
+    CUDA_TRY(cudaMemsetAsync(t->grads, 0, t->nparams * sizeof(float), t->stream));
+    StepOpts o{t_host == nullptr, noise_host == nullptr, false, 0, 0, 0, 0, 0};
+    enqueue_step(t, o, t->stream);
+    t->have_grads = true;
+    CUDA_TRY(cudaGetLastError());
+    if (loss_out) return fetch_loss(t, loss_out);
+    return UB_OK;
+}
+
+extern "C" int ub_trainer_update(UbTrainer* t, float lr, float beta1, float beta2, float eps, float weight_decay) {
+    CUDA_TRY(cudaSetDevice(t->device));
+    if (!t->have_grads) {
+        set_err("ub_trainer_update called without gradients");
+        return UB_ERR_STATE;
+    }
+    adamw_step(t->params, t->grads, t->m, t->v, t->nparams, lr, beta1, beta2, eps, weight_decay,
+               1.f / float(t->world), t->step_dev, t->stream);
+    run_pack(t, t->stream);
+    increment_step(t->step_dev, t->stream);
+    t->have_grads = false;
+    t->host_step++;
+    CUDA_TRY(cudaGetLastError());
+    return UB_OK;
+}
+
+static int launch_step(UbTrainer* t, const StepOpts& o) {
+    if (!t->cfg.use_cuda_graph) {
+        enqueue_step(t, o, t->stream);
+        ub_count_launches((unsigned long long)ub_trainer_launches_per_step(t));
+        CUDA_TRY(cudaGetLastError());
+        return UB_OK;
+    }
+    const bool same = t->graph_valid && t->graph_gen_t == o.gen_t && t->graph_gen_noise == o.gen_noise &&
+                      t->g_lr == o.lr && t->g_b1 == o.b1 && t->g_b2 == o.b2 && t->g_eps == o.eps && t->g_wd == o.wd;
+    if (!same) {
+        if (t->graph_exec) cudaGraphExecDestroy(t->graph_exec), t->graph_exec = nullptr;
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(cudaStreamBeginCapture(t->stream, cudaStreamCaptureModeThreadLocal));
+        enqueue_step(t, o, t->stream);
+        cudaError_t e = cudaStreamEndCapture(t->stream, &graph);
+        if (e != cudaSuccess || !graph) {
+            set_err("graph capture failed: %s", cudaGetErrorString(e));
+            return UB_ERR_CUDA;
+        }
+        e = cudaGraphInstantiate(&t->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            set_err("graph instantiate failed: %s", cudaGetErrorString(e));
+            return UB_ERR_CUDA;
+        }
+        t->graph_valid = true, t->graph_gen_t = o.gen_t, t->graph_gen_noise = o.gen_noise;
+        t->g_lr = o.lr, t->g_b1 = o.b1, t->g_b2 = o.b2, t->g_eps = o.eps, t->g_wd = o.wd;
+    }
+    CUDA_TRY(cudaGraphLaunch(t->graph_exec, t->stream));
+    ub_count_launches((unsigned long long)ub_trainer_launches_per_step(t));
+    return UB_OK;
+}
+
+extern "C" int ub_trainer_train_step(UbTrainer* t, const float* x0_host, const float* t_host, const float* noise_host,
+                                     float lr, float beta1, float beta2, float eps, float weight_decay,
+                                     float* loss_out) {
+    CUDA_TRY(cudaSetDevice(t->device));
+    int r = stage_inputs(t, x0_host, t_host, noise_host);
+    if (r) return r;
+    StepOpts o{t_host == nullptr, noise_host == nullptr, true, lr, beta1, beta2, eps, weight_decay};
+    r = launch_step(t, o);
+    if (r) return r;
+    t->host_step++;
+    t->have_grads = false;
+    if (loss_out) return fetch_loss(t, loss_out);
+    return UB_OK;
+}
+
+extern "C" int ub_trainer_train_step_device(UbTrainer* t, const float* x0_dev, float lr, float beta1, float beta2,
+                                            float eps, float weight_decay) {
+    CUDA_TRY(cudaSetDevice(t->device));
+    const UbConfig& c = t->cfg;
+    const size_t img = size_t(c.B) * c.C_in * c.H * c.W;
+    if (x0_dev != t->x0)
+        CUDA_TRY(cudaMemcpyAsync(t->x0, x0_dev, img * sizeof(float), cudaMemcpyDeviceToDevice, t->stream));
+    StepOpts o{true, true, true, lr, beta1, beta2, eps, weight_decay};
+    int r = launch_step(t, o);
+    if (r) return r;
+    t->host_step++;
+    return UB_OK;
+}
+
+extern "C" int ub_trainer_sync(UbTrainer* t) {
+    CUDA_TRY(cudaSetDevice(t->device));
+    CUDA_TRY(cudaStreamSynchronize(t->stream));
+    return UB_OK;
+}
+extern "C" int ub_trainer_last_loss(UbTrainer* t, float* loss_out) {
+    CUDA_TRY(cudaSetDevice(t->device));
+    return fetch_loss(t, loss_out);
+}
+extern "C" void* ub_trainer_stream(UbTrainer* t) { return (void*)t->stream; }
+extern "C" int ub_trainer_launches_per_step(UbTrainer* t) {
+    // tapes + memset-free extras: diffusion (2), adamw, pack, step increment
+    return t->launches_fwd + t->launches_bwd + 5;
+}
+
+extern "C" int ub_trainer_predict(UbTrainer* t, const float* xt_host, const float* t_host, float* out_host) {
+    CUDA_TRY(cudaSetDevice(t->device));
+    const UbConfig& c = t->cfg;
+    const size_t img = size_t(c.B) * c.C_in * c.H * c.W, oimg = size_t(c.B) * c.C_out * c.H * c.W;
+    CUDA_TRY(cudaMemcpyAsync(t->xt, xt_host, img * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+    CUDA_TRY(cudaMemcpyAsync(t->tsteps, t_host, c.B * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+    CUDA_TRY(cudaMemsetAsync(t->zero_base, 0, t->zero_bytes, t->stream));
+    CUDA_TRY(cudaMemsetAsync(t->noise, 0, img * sizeof(float), t->stream));
+    for (auto& op : t->fwd_ops) op(t->stream);
+    CUDA_TRY(cudaMemcpyAsync(out_host, t->out, oimg * sizeof(float), cudaMemcpyDeviceToHost, t->stream));
+    CUDA_TRY(cudaStreamSynchronize(t->stream));
+    return UB_OK;
+}
+
+// ======================================================================================================
+// parameter / gradient access and checkpoints
+// ======================================================================================================
+static int copy_out(UbTrainer* t, const float* dev, float* host, size_t n, size_t expect) {
+    if (n != expect) {
+        set_err("size mismatch: got %zu expected %zu", n, expect);
+        return UB_ERR_SHAPE;
+    }
+    CUDA_TRY(cudaSetDevice(t->device));
+    CUDA_TRY(cudaStreamSynchronize(t->stream));
+    CUDA_TRY(cudaMemcpy(host, dev, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return UB_OK;
+}
+extern "C" int ub_trainer_set_params(UbTrainer* t, const float* host, size_t n) {
+    if (n != t->nparams) {
+        set_err("size mismatch: got %zu expected %zu", n, t->nparams);
+        return UB_ERR_SHAPE;
+    }
+    CUDA_TRY(cudaSetDevice(t->device));
+    CUDA_TRY(cudaStreamSynchronize(t->stream));
+    CUDA_TRY(cudaMemcpy(t->params, host, n * sizeof(float), cudaMemcpyHostToDevice));
+    ensure_packed(t);
+    CUDA_TRY(cudaStreamSynchronize(t->stream));
+    return UB_OK;
+}
+extern "C" int ub_trainer_get_params(UbTrainer* t, float* host, size_t n) {
+    return copy_out(t, t->params, host, n, t->nparams);
+}
+extern "C" int ub_trainer_get_grads(UbTrainer* t, float* host, size_t n) {
+    return copy_out(t, t->grads, host, n, t->nparams);
+}
+extern "C" int ub_trainer_get_output(UbTrainer* t, float* host, size_t n) {
+    const UbConfig& c = t->cfg;
+    return copy_out(t, t->out, host, n, size_t(c.B) * c.C_out * c.H * c.W);
+}
+extern "C" int ub_trainer_get_dinput(UbTrainer*, float*, size_t) {
+    set_err("dL/dinput is not computed by the training path (the reference trainer never uses it)");
+    return UB_ERR_STATE;
+}
+
+static const int kModelMagic = 12345678;  // train_unet.py:781
+
+extern "C" int ub_read_checkpoint_header(const char* path, UbConfig* cfg) {
+    FILE* f = fopen(path, "rb");
+    if (!f) {
+        set_err("cannot open %s", path);
+        return UB_ERR_IO;
+    }
+    int header[256];
+    const size_t got = fread(header, sizeof(int), 256, f);
+    fclose(f);
+    if (got != 256 || header[0] != kModelMagic) {
+        set_err("%s: bad header / magic", path);
+        return UB_ERR_IO;
+    }
+    cfg->B = header[1], cfg->C_in = header[2], cfg->C_model = header[3], cfg->C_out = header[4];
+    cfg->H = header[5], cfg->W = header[6], cfg->max_period = header[7];
+    return UB_OK;
+}
+
+extern "C" int ub_trainer_load(UbTrainer* t, const char* path) {
+    FILE* f = fopen(path, "rb");
+    if (!f) {
+        set_err("cannot open %s", path);
+        return UB_ERR_IO;
+    }
+    int header[256];
+    if (fread(header, sizeof(int), 256, f) != 256 || header[0] != kModelMagic) {
+        fclose(f);
+        set_err("%s: bad header / magic", path);
+        return UB_ERR_IO;
+    }
+    const UbConfig& c = t->cfg;
+    if (header[2] != c.C_in || header[3] != c.C_model || header[4] != c.C_out || header[5] != c.H ||
+        header[6] != c.W) {
+        fclose(f);
+        set_err("%s: checkpoint shape (C_in %d, C_model %d, C_out %d, %dx%d) does not match the trainer", path,
+                header[2], header[3], header[4], header[5], header[6]);
+        return UB_ERR_SHAPE;
+    }
+    std::vector<float> buf(t->nparams);
+    auto read_arena = [&](float* dev) -> int {
+        if (fread(buf.data(), sizeof(float), t->nparams, f) != t->nparams) return UB_ERR_IO;
+        return cudaMemcpy(dev, buf.data(), t->nparams * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess
+                   ? UB_OK
+                   : UB_ERR_CUDA;
+    };
+    CUDA_TRY(cudaSetDevice(t->device));
+    CUDA_TRY(cudaStreamSynchronize(t->stream));
+    int r = read_arena(t->params);
+    if (!r && header[8] == 1) {  // AdamW moments (train_unet.cu:4874-4886)
+        r = read_arena(t->m);
+        if (!r) r = read_arena(t->v);
+        const int step = header[10];
+        cudaMemcpy(t->step_dev, &step, sizeof(int), cudaMemcpyHostToDevice);
+        t->host_step = step;
+    }
+    fclose(f);
+    if (r) {
+        set_err("%s: truncated checkpoint", path);
+        return r;
+    }
+    ensure_packed(t);
+    CUDA_TRY(cudaStreamSynchronize(t->stream));
+    return UB_OK;
+}
+
+extern "C" int ub_trainer_save(UbTrainer* t, const char* path, int with_adamw) {
+    CUDA_TRY(cudaSetDevice(t->device));
+    CUDA_TRY(cudaStreamSynchronize(t->stream));
+    FILE* f = fopen(path, "wb");
+    if (!f) {
+        set_err("cannot open %s for writing", path);
+        return UB_ERR_IO;
+    }
+    const UbConfig& c = t->cfg;
+    int header[256];
+    memset(header, 0, sizeof header);
+    header[0] = kModelMagic, header[1] = c.B, header[2] = c.C_in, header[3] = c.C_model, header[4] = c.C_out;
+    header[5] = c.H, header[6] = c.W, header[7] = c.max_period, header[8] = with_adamw ? 1 : 0, header[9] = 0;
+    int step = 0;
+    cudaMemcpy(&step, t->step_dev, sizeof(int), cudaMemcpyDeviceToHost);
+    header[10] = step;
+    std::vector<float> buf(t->nparams);
+    bool ok = fwrite(header, sizeof(int), 256, f) == 256;
+    auto write_arena = [&](const float* dev) {
+        ok = ok && cudaMemcpy(buf.data(), dev, t->nparams * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess;
+        ok = ok && fwrite(buf.data(), sizeof(float), t->nparams, f) == t->nparams;
+    };
+    write_arena(t->params);
+    if (with_adamw) write_arena(t->m), write_arena(t->v);
+    fclose(f);
+    if (!ok) {
+        set_err("write to %s failed", path);
+        return UB_ERR_IO;
+    }
+    return UB_OK;
+}
+
+// ======================================================================================================
+// data parallel
+// ======================================================================================================
+extern "C" int ub_nccl_get_unique_id(void* id_out) {
+    if (!nccl().ok) {
+        set_err("libnccl.so.2 could not be loaded");
+        return UB_ERR_NCCL;
+    }
+    ncclUniqueId id;
+    int r = nccl().GetUniqueId(&id);
+    if (r) {
+        set_err("ncclGetUniqueId failed (%d)", r);
+        return UB_ERR_NCCL;
+    }
+    memcpy(id_out, &id, sizeof id);
+    return UB_OK;
+}
+
+extern "C" int ub_trainer_attach_dp(UbTrainer* t, int rank, int world, const void* nccl_id, int n_buckets) {
+    if (!nccl().ok) {
+        set_err("libnccl.so.2 could not be loaded");
+        return UB_ERR_NCCL;
+    }
+    if (n_buckets != t->n_buckets && n_buckets > 0)
+        fprintf(stderr, "[unet_b200] note: bucket count is fixed at build time (%d)\n", t->n_buckets);
+    CUDA_TRY(cudaSetDevice(t->device));
+    ncclUniqueId id;
+    memcpy(&id, nccl_id, sizeof id);
+    int r = nccl().CommInitRank(&t->comm, world, id, rank);
+    if (r) {
+        set_err("ncclCommInitRank failed (%d: %s)", r, nccl().GetErrorString ? nccl().GetErrorString(r) : "?");
+        return UB_ERR_NCCL;
+    }
+    t->rank = rank, t->world = world;
+    t->graph_valid = false;  // the step must be re-captured with the all-reduce nodes
+    return UB_OK;
+}
