@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- UNet-64 diffusion training step throughput (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...          # the reference's CPU (PyTorch) path, oracle port
+
+One "step" = the loop body of train_unet.cu:5019-5037 on one synthetic batch: H2D batch copy (e2e only),
+timestep + noise draw, q-sample, U-Net forward, MSE, backward, (gradient all-reduce), AdamW.
+Workload at N=1: BASELINE.json configs[2] -- default 64x64 unconditional U-Net (20 494 211 params), batch 32.
+N>1: weak scaling, batch 32 per GPU (N=8 is configs[3]: global batch 256), gradients all-reduced over NCCL.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "UNet-64 train images/sec"
+UNIT = "images/s"
+FLOP_PER_IMG_FWD_BWD = 38.76e9  # BASELINE.md section 3 (tensor FLOPs, fwd + bwd)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])), mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ---------------------------------------------------------------------------------------------------- CPU arm
+def cpu_step_timer(B: int, steps: int, warmup: int):
+    """Time the oracle port (the reference's PyTorch-CPU path restated, oracle/unet_oracle.py) on all host cores."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import unet_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.UNetConfig()
+    flat = O.flatten_params(cfg, O.init_params(cfg, seed=0))
+    m, v = torch.zeros_like(flat), torch.zeros_like(flat)
+    times = []
+    for i in range(warmup + steps):
+        x0, t, noise = O.synthetic_batch(cfg, B, seed=1234 + i)
+        t0 = time.perf_counter()
+        _, _, g = O.train_step_grads(cfg, flat, x0, t, noise)
+        flat, m, v = O.adamw_step(flat, g, m, v, i + 1, lr=1e-4)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sum(times) / len(times), cores, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    B = 4  # bounded sample of the batch-32 workload (configs[0] size): ~1-3 s of CPU work per step
+    sec, cores, threads = cpu_step_timer(B, args.steps, min(args.warmup, 2))
+    val = B / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 2), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "train_unet default 64x64 unconditional U-Net (20494211 params), full train step",
+                   "batch_per_step": B, "note": "CPU arm: each step is a batch-4 sample of the batch-32 workload"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} full train steps (fwd+bwd+AdamW) at batch {B}, torch CPU fp32, "
+                                   f"{threads} threads of {cores} cores"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------- CUDA arm
+def run_cuda(args):
+    import numpy as np
+    import torch
+    import __graft_entry__ as ge
+    rank, local_rank, world = dist_env()
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ub = ge.load_package()
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    B = args.batch
+    tr = ub.Trainer(B=B, device=local_rank, seed=1234 + rank)
+
+    # random-init weights of the reference architecture: PyTorch default init, seed 0 (identical on every rank)
+    import unet_oracle as O
+    cfg = O.UNetConfig()
+    flat = O.flatten_params(cfg, O.init_params(cfg, seed=0)).numpy()
+    tr.set_params(flat)
+
+    if use_dist:
+        idt = torch.zeros(ub.UB_NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(ub.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        tr.attach_dp(rank, world, bytes(idt.cpu().numpy().tobytes()))
+
+    g = torch.Generator().manual_seed(99 + rank)
+    n_host = 4
+    host_batches = [(torch.rand(B, 3, 64, 64, generator=g) * 2 - 1).pin_memory() for _ in range(n_host)]
+    dev_batch = host_batches[0].cuda()
+    stream = torch.cuda.ExternalStream(tr.stream())
+    hp = dict(lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for i in range(steps):
+            fn(i)
+        e1.record(stream)
+        tr.sync()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if use_dist:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident throughput (`value`)
+    for i in range(max(args.warmup, 3)):
+        tr.train_step_device(dev_batch.data_ptr(), **hp)
+    tr.sync()
+    launches0 = int(ub.lib().ub_launch_count())
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_total = timed(lambda i: tr.train_step_device(dev_batch.data_ptr(), **hp), args.steps)
+    clocks = sampler.stop() if sampler else None
+    launches = int(ub.lib().ub_launch_count()) - launches0
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step * 1e-3)
+    loss_now = tr.last_loss()
+
+    # ---- end to end through the public API with HOST buffers: H2D of the batch + D2H of the loss every step
+    import ctypes
+    loss_c = ctypes.c_float()
+
+    def e2e_step(i):
+        tr.train_step_ptr(host_batches[i % n_host].data_ptr(), loss_ref=ctypes.byref(loss_c), **hp)
+
+    for i in range(3):
+        e2e_step(i)
+    t_e2e = []
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    e2e_ms = torch.tensor([wall * 1e3 / args.steps], device="cuda")
+    if use_dist:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * B / (float(e2e_ms.item()) * 1e-3)
+
+    # ---- live per-kernel-class timing (CUDA events around every launch, same process, same stream)
+    prof = tr.profile(reps=3) if rank == 0 else None
+
+    if rank == 0:
+        pk = peaks()
+        conv = prof["conv_igemm"]
+        conv_tf = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
+        roofline = {
+            "bound": "tensor", "kernel": "igemm_conv_kernel (3x3/1x1 conv fprop+dgrad, qkv/proj GEMMs; tcgen05)",
+            "achieved": conv_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+            "frac": conv_tf / pk["tf_sustained"], "traffic": None, "peak_source": pk["source"] + ", sustained bf16",
+            "flops_per_launch": conv["flops"] / max(conv["launches"], 1),
+            "avg_launch_ms": conv["ms"] / max(conv["launches"], 1), "launches_per_step": conv["launches"],
+            "share_of_step": conv["ms"] / prof["total_ms"],
+        }
+        classes = {}
+        for k in ub.UB_KINDS:
+            c = prof[k]
+            ent = {"ms": round(c["ms"], 4), "launches": c["launches"]}
+            if c["flops"] > 0 and c["ms"] > 0:
+                ent["tflops"] = round(c["flops"] / (c["ms"] * 1e-3) / 1e12, 1)
+            if c["bytes"] > 0 and c["ms"] > 0:
+                ent["alg_gbs"] = round(c["bytes"] / (c["ms"] * 1e-3) / 1e9, 1)
+            classes[k] = ent
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "train_unet default 64x64 unconditional U-Net (20494211 params, channel_mult 1-2-3-4, "
+                                   "attention at 16x16 and 8x8), full train step (q-sample, fwd, MSE, bwd, AdamW)",
+                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "weights": "random init (PyTorch default, seed 0)", "cuda_graph": True,
+                       "l2": "per-step working set (~2 GB of bf16 activations + 330 MB optimizer state) exceeds the "
+                             "126 MB L2; no extra flush"},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 3 * 64 * 64 * 4,
+                    "d2h_bytes_per_step": 4, "ms_per_step": float(e2e_ms.item())},
+            "roofline": roofline, "kernel_classes": classes, "profile_total_ms": prof["total_ms"],
+            "model_tflops": value * FLOP_PER_IMG_FWD_BWD / 1e12 / world,
+            "loss_after": loss_now,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            sec, cores, threads = cpu_step_timer(4, 5, 1)
+            line["cpu_baseline"] = {"value": 4 / sec, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"5 full train steps at batch 4 (a batch-4 sample of the batch-32 "
+                                              f"workload), torch CPU fp32 oracle, {threads} threads"}
+            ref = reference_cuda_baseline(args)
+            if ref:
+                line["reference_cuda"] = ref
+        print(json.dumps(line), flush=True)
+    tr.close()
+    if use_dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def reference_cuda_baseline(args):
+    """The reference's own CUDA trainer (train_unet.cu built unmodified for sm_100 into oracle/_ref/train_unet by
+    oracle/Makefile) timed for a bounded ~20 s on the same GPU: parsed from its own log lines
+    (train_unet.cu:5045-5051: 'step N/... | cur time X s')."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "train_unet")
+    if not os.path.exists(exe) or args.no_reference_cuda:
+        return None
+    try:
+        import numpy as np
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import unet_oracle as O
+        with tempfile.TemporaryDirectory() as d:
+            cfg = O.UNetConfig()
+            flat = O.flatten_params(cfg, O.init_params(cfg, seed=0)).numpy()
+            O.write_model_bin(os.path.join(d, "unet_init.bin"), cfg, flat, B=32)
+            rng = np.random.default_rng(0)
+            O.write_data_bin(os.path.join(d, "data.bin"), rng.uniform(-1, 1, (256, 3, 64, 64)).astype(np.float32))
+            log = os.path.join(d, "log.txt")
+            p = subprocess.Popen([exe, "--model_weights", "unet_init.bin", "--data_file", "data.bin", "--log_file",
+                                  "log.txt"], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            t0 = time.time()
+            pts = []
+            while time.time() - t0 < 45:
+                time.sleep(1.0)
+                if os.path.exists(log):
+                    pts = []
+                    for ln in open(log).read().splitlines():
+                        if ln.startswith("step") and "cur time" in ln:
+                            it = int(ln.split("/")[0].split()[1])
+                            sec = float(ln.split("cur time")[1].split()[0])
+                            pts.append((it, sec))
+                    if len(pts) >= 3 or p.poll() is not None:
+                        break
+            p.kill()
+            p.wait()
+            if len(pts) >= 2:
+                (i0, s0), (i1, s1) = pts[0], pts[-1]
+                ms = (s1 - s0) / (i1 - i0) * 1e3
+                return {"ms_per_step": ms, "value": 32 / (ms * 1e-3), "unit": UNIT, "batch": 32,
+                        "what": "reference train_unet.cu (fp32 SIMT + cuBLAS), unmodified, nvcc -O3 --use_fast_math "
+                                "-arch=sm_100, same GPU", "iters_measured": i1 - i0}
+    except Exception as e:  # the comparison line is best effort
+        return {"error": str(e)[:200]}
+    return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-cuda", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

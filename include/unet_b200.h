@@ -196,6 +196,25 @@ int ub_trainer_launches_per_step(UbTrainer* t);
 /* forward only on a device batch that is ALREADY x_t (for sampling, generate.py:29-52): out_dev (B,C_out,H,W) */
 int ub_trainer_predict(UbTrainer* t, const float* xt_host, const float* t_host, float* out_host);
 
+/* ---- per-kernel-class timing of one training step (CUDA events around every launch, eager replay of the tape).
+ * Used by bench.py for the live roofline numbers. */
+#define UB_KIND_CONV 0    /* igemm_conv_kernel: 3x3 / 1x1 conv fprop + dgrad, attention qkv/proj GEMMs (tensor) */
+#define UB_KIND_WGRAD 1   /* igemm_wgrad_kernel + split-K reduce (tensor) */
+#define UB_KIND_NORM 2    /* GroupNorm(+SiLU) forward / backward (HBM) */
+#define UB_KIND_ATTN 3    /* attention core forward / backward */
+#define UB_KIND_ELTWISE 4 /* concat / pool / add / column sums (HBM) */
+#define UB_KIND_SMALL 5   /* embedding MLPs, 3-channel convs, loss */
+#define UB_KIND_OPTIM 6   /* diffusion noise + q-sample, AdamW, weight packing (HBM) */
+#define UB_NUM_KINDS 7
+typedef struct {
+    double ms[UB_NUM_KINDS];       /* device time per class, average per step */
+    double flops[UB_NUM_KINDS];    /* algorithmic FLOPs per step */
+    double bytes[UB_NUM_KINDS];    /* algorithmic bytes per step */
+    int launches[UB_NUM_KINDS];    /* kernel launches per step */
+    double total_ms;               /* sum over classes */
+} UbProfile;
+int ub_trainer_profile(UbTrainer* t, int reps, UbProfile* out);
+
 /* ---- data parallel: one process per GPU; rank 0 creates the id, everyone attaches ---- */
 #define UB_NCCL_ID_BYTES 128
 int ub_nccl_get_unique_id(void* id_out /* UB_NCCL_ID_BYTES */);

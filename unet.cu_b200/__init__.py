@@ -29,6 +29,14 @@ class UbConfig(C.Structure):
                 ("use_cuda_graph", C.c_int)]
 
 
+UB_KINDS = ("conv_igemm", "wgrad_igemm", "groupnorm", "attention", "eltwise", "small", "optimizer")
+
+
+class UbProfile(C.Structure):
+    _fields_ = [("ms", C.c_double * 7), ("flops", C.c_double * 7), ("bytes", C.c_double * 7),
+                ("launches", C.c_int * 7), ("total_ms", C.c_double)]
+
+
 class UbError(RuntimeError):
     pass
 
@@ -76,6 +84,7 @@ def _declare(L: C.CDLL) -> None:
     L.ub_trainer_stream.restype = vp
     L.ub_trainer_launches_per_step.argtypes = [vp]
     L.ub_trainer_predict.argtypes = [vp, fp, fp, fp]
+    L.ub_trainer_profile.argtypes = [vp, i, C.POINTER(UbProfile)]
     L.ub_nccl_get_unique_id.argtypes = [vp]
     L.ub_trainer_attach_dp.argtypes = [vp, i, i, vp, i]
 
@@ -201,6 +210,13 @@ class Trainer:
 
     def launches_per_step(self) -> int:
         return int(lib().ub_trainer_launches_per_step(self._h))
+
+    def profile(self, reps: int = 3) -> dict:
+        """Per-kernel-class device time of one step (CUDA events around every launch)."""
+        p = UbProfile()
+        check(lib().ub_trainer_profile(self._h, reps, C.byref(p)), "profile")
+        return {k: {"ms": p.ms[j], "flops": p.flops[j], "bytes": p.bytes[j], "launches": p.launches[j]}
+                for j, k in enumerate(UB_KINDS)} | {"total_ms": p.total_ms}
 
     def predict(self, xt, t):
         c = self.cfg

@@ -126,7 +126,14 @@ struct UbTrainer {
     int emb_max_oc = 0;
     // tapes
     typedef std::function<void(cudaStream_t)> Op;
-    std::vector<Op> fwd_ops, bwd_ops /* executed in reverse order of push */;
+    std::vector<Op> fwd_ops, bwd_ops;  // executed in push order
+    struct OpInfo {
+        int kind;       // UB_KIND_*
+        int launches;
+        double flops;   // algorithmic FLOPs (tensor kernels) ...
+        double bytes;   // ... or algorithmic bytes (memory-bound kernels)
+    };
+    std::vector<OpInfo> fwd_info, bwd_info;
     int launches_fwd = 0, launches_bwd = 0, launches_misc = 0;
     // hyper-parameters baked into the captured graph
     float lr = 1e-4f, b1 = 0.9f, b2 = 0.999f, eps = 1e-8f, wd = 0.f;
@@ -215,12 +222,17 @@ struct Builder {
     bf16* packbuf(size_t n) { return (bf16*)T->arena.alloc(n * sizeof(bf16)); }
 
     bool real() const { return !T->arena.counting; }
-    void F(UbTrainer::Op op, int launches = 1) {
-        if (real()) T->fwd_ops.push_back(std::move(op)), T->launches_fwd += launches;
+    void F(UbTrainer::Op op, int launches = 1, int kind = UB_KIND_SMALL, double flops = 0, double bytes = 0) {
+        if (!real()) return;
+        T->fwd_ops.push_back(std::move(op)), T->launches_fwd += launches;
+        T->fwd_info.push_back({kind, launches, flops, bytes});
     }
-    void Bk(UbTrainer::Op op, int launches = 1) {
-        if (real()) T->bwd_ops.push_back(std::move(op)), T->launches_bwd += launches;
+    void Bk(UbTrainer::Op op, int launches = 1, int kind = UB_KIND_SMALL, double flops = 0, double bytes = 0) {
+        if (!real()) return;
+        T->bwd_ops.push_back(std::move(op)), T->launches_bwd += launches;
+        T->bwd_info.push_back({kind, launches, flops, bytes});
     }
+    double act_bytes(int C, int H, int W) const { return 2.0 * B * H * W * C; }
 
     struct Packed {
         bf16 *wf = nullptr, *wd = nullptr;
@@ -247,10 +259,13 @@ struct Builder {
             return;
         }
         auto op = [p](cudaStream_t st) { igemm_conv_launch(p, st); };
+        double k = 0, bytes = act_bytes(Cout, H, W);
+        for (auto& sg : segs) k += double(sg.ntaps) * sg.Cin, bytes += act_bytes(sg.Cin, H, W) + 2.0 * sg.ntaps * sg.Cin * Cout;
+        const double flops = 2.0 * B * H * W * Cout * k;
         if (fwd)
-            F(op);
+            F(op, 1, UB_KIND_CONV, flops, bytes);
         else
-            Bk(op);
+            Bk(op, 1, UB_KIND_CONV, flops, bytes);
     }
     void wgrad_op(View dy, View x, int Cin, int Cout, int ntaps, float* dw) {
         if (!real()) return;
@@ -265,7 +280,8 @@ struct Builder {
         Bk([p, dw](cudaStream_t st) {
             igemm_wgrad_launch(p, st);
             igemm_wgrad_reduce(p, dw, st);
-        }, 2);
+        }, 2, UB_KIND_WGRAD, 2.0 * B * x.H * x.W * double(Cout) * Cin * ntaps,
+           act_bytes(Cin, x.H, x.W) + act_bytes(Cout, x.H, x.W) + 4.0 * ntaps * Cin * Cout);
     }
 
     struct GN {
@@ -282,7 +298,7 @@ struct Builder {
         F([=](cudaStream_t st) {
             gn_stats(x.p, x.ld, Bn, HW, x.C, cs, st);
             gn_apply(x.p, x.ld, cs, gw, gb, Bn, HW, x.C, Gn, silu, y.p, y.ld, nullptr, st);
-        }, 2);
+        }, 2, UB_KIND_NORM, 0, 3 * act_bytes(x.C, x.H, x.W));
         return g;
     }
     void gn_bwd(const GN& g, View x, View dy, int silu, View add_in, View dx, float* colsum_out) {
@@ -292,7 +308,7 @@ struct Builder {
             gn_bwd_stats(x.p, x.ld, dy.p, dy.ld, cs, gw, gb, Bn, HW, x.C, Gn, silu, S, st);
             gn_bwd_apply(x.p, x.ld, dy.p, dy.ld, cs, S, gw, gb, Bn, HW, x.C, Gn, silu, add_in.p, add_in.ld, dx.p,
                          dx.ld, dgw, dgb, colsum_out, st);
-        }, 2);
+        }, 2, UB_KIND_NORM, 0, (5 + (add_in.p ? 1 : 0)) * act_bytes(x.C, x.H, x.W));
     }
 
     int res_index = 0;
@@ -356,7 +372,8 @@ struct Builder {
             UbTrainer* Tt = T;
             const int Bn = B;
             // bias / weight gradients of conv2 (and of the fused 1x1 skip conv)
-            Bk([=](cudaStream_t st) { colsum(dout.p, dout.ld, npix, Cout, gb2, gbs, st); });
+            Bk([=](cudaStream_t st) { colsum(dout.p, dout.ld, npix, Cout, gb2, gbs, st); }, 1, UB_KIND_ELTWISE, 0,
+               act_bytes(Cout, H, W));
             wgrad_op(dout, a2, Cout, Cout, 9, G(w2));
             if (proj) wgrad_op(dout, x, C, Cout, 1, G(ws));
             {
@@ -404,7 +421,8 @@ struct Builder {
             conv_op(true, {{g.p, C, g.ld, pq.wf, 1}}, H, W, 3 * C, ep);
         }
         const int Bn = B;
-        F([=](cudaStream_t st) { attn_fwd(qkv.p, qkv.ld, Bn, Tn, NH, HSz, ao.p, ao.ld, lse, st); });
+        F([=](cudaStream_t st) { attn_fwd(qkv.p, qkv.ld, Bn, Tn, NH, HSz, ao.p, ao.ld, lse, st); }, 1, UB_KIND_ATTN,
+          4.0 * B * NH * double(Tn) * Tn * HSz, act_bytes(4 * C, H, W));
         {
             ConvEpilogue ep;
             ep.bias = P(bp), ep.out = out.p, ep.ldo = out.ld, ep.residual = x.p, ep.ldr = x.ld;
@@ -415,7 +433,8 @@ struct Builder {
             View dao = act(C, H, W), dqkv = act(3 * C, H, W), dg = act(C, H, W), dx = act(C, H, W);
             const size_t npix = size_t(B) * H * W;
             float *gbp = G(bp), *gbq = G(bq);
-            Bk([=](cudaStream_t st) { colsum(dout.p, dout.ld, npix, C, gbp, nullptr, st); });
+            Bk([=](cudaStream_t st) { colsum(dout.p, dout.ld, npix, C, gbp, nullptr, st); }, 1, UB_KIND_ELTWISE, 0,
+               act_bytes(C, H, W));
             wgrad_op(dout, ao, C, C, 1, G(wp));
             {
                 ConvEpilogue ep;
@@ -424,8 +443,9 @@ struct Builder {
             }
             Bk([=](cudaStream_t st) {
                 attn_bwd(qkv.p, qkv.ld, ao.p, ao.ld, dao.p, dao.ld, lse, Bn, Tn, NH, HSz, dqkv.p, dqkv.ld, dsum, st);
-            }, 2);
-            Bk([=](cudaStream_t st) { colsum(dqkv.p, dqkv.ld, npix, 3 * C, gbq, nullptr, st); });
+            }, 2, UB_KIND_ATTN, 10.0 * B * NH * double(Tn) * Tn * HSz, act_bytes(8 * C, H, W));
+            Bk([=](cudaStream_t st) { colsum(dqkv.p, dqkv.ld, npix, 3 * C, gbq, nullptr, st); }, 1, UB_KIND_ELTWISE, 0,
+               act_bytes(3 * C, H, W));
             wgrad_op(dqkv, g, C, 3 * C, 1, G(wq));
             {
                 ConvEpilogue ep;
@@ -522,13 +542,14 @@ int Builder::build() {
             Node nd;
             nd.param_begin = poff;
             View x = h, y = act(h.C, h.H / 2, h.W / 2);
-            F([=](cudaStream_t st) { avgpool2_fwd(x.p, x.ld, Bn, x.H, x.W, x.C, y.p, y.ld, st); });
+            F([=](cudaStream_t st) { avgpool2_fwd(x.p, x.ld, Bn, x.H, x.W, x.C, y.p, y.ld, st); }, 1, UB_KIND_ELTWISE, 0,
+              1.25 * act_bytes(x.C, x.H, x.W));
             nd.out = y, nd.pushed = true;
             nd.bwd = [=](View dout) -> View {
                 View dx = act(x.C, x.H, x.W);
                 Bk([=](cudaStream_t st) {
                     avgpool2_bwd(dout.p, dout.ld, Bn, x.H, x.W, x.C, nullptr, 0, dx.p, dx.ld, st);
-                });
+                }, 1, UB_KIND_ELTWISE, 0, 1.25 * act_bytes(x.C, x.H, x.W));
                 return dx;
             };
             nodes.push_back(nd);
@@ -554,7 +575,8 @@ int Builder::build() {
             nd.param_begin = poff;
             const int C1 = h.C, C2 = sk.C, Hc = sk.H, Wc = sk.W, up = pending_up ? 1 : 0;
             View cat = act(C1 + C2, Hc, Wc), a = h;
-            F([=](cudaStream_t st) { concat2(a.p, a.ld, C1, up, sk.p, sk.ld, C2, Bn, Hc, Wc, cat.p, cat.ld, st); });
+            F([=](cudaStream_t st) { concat2(a.p, a.ld, C1, up, sk.p, sk.ld, C2, Bn, Hc, Wc, cat.p, cat.ld, st); }, 1,
+              UB_KIND_ELTWISE, 0, 2 * act_bytes(C1 + C2, Hc, Wc));
             nd.out = cat;
             std::vector<View>* sg = &skipgrad;
             nd.bwd = [=](View d) -> View {
@@ -563,7 +585,8 @@ int Builder::build() {
                 (*sg)[src] = skv;
                 if (up) {
                     View dlow = act(C1, Hc / 2, Wc / 2);
-                    Bk([=](cudaStream_t st) { upsample2_bwd(d.p, d.ld, Bn, Hc, Wc, C1, dlow.p, dlow.ld, st); });
+                    Bk([=](cudaStream_t st) { upsample2_bwd(d.p, d.ld, Bn, Hc, Wc, C1, dlow.p, dlow.ld, st); }, 1,
+                       UB_KIND_ELTWISE, 0, 1.25 * act_bytes(C1, Hc, Wc));
                     return dlow;
                 }
                 View mv = d;
@@ -640,7 +663,8 @@ int Builder::build() {
             View a = g;
             const size_t npix = size_t(B) * nd.out.H * nd.out.W;
             const int C = nd.out.C;
-            Bk([=](cudaStream_t st) { add2(a.p, a.ld, s.p, s.ld, npix, C, sum.p, sum.ld, st); });
+            Bk([=](cudaStream_t st) { add2(a.p, a.ld, s.p, s.ld, npix, C, sum.p, sum.ld, st); }, 1, UB_KIND_ELTWISE, 0,
+               3 * act_bytes(C, nd.out.H, nd.out.W));
             g = sum;
         }
         g = nd.bwd(g);
@@ -970,6 +994,59 @@ extern "C" int ub_trainer_train_step_device(UbTrainer* t, const float* x0_dev, f
     int r = launch_step(t, o);
     if (r) return r;
     t->host_step++;
+    return UB_OK;
+}
+
+// Eager replay of one step with a CUDA event pair around every tape op (device time per kernel class).
+extern "C" int ub_trainer_profile(UbTrainer* t, int reps, UbProfile* out) {
+    CUDA_TRY(cudaSetDevice(t->device));
+    memset(out, 0, sizeof(*out));
+    if (reps < 1) reps = 1;
+    const UbConfig& c = t->cfg;
+    const size_t nops = t->fwd_ops.size() + t->bwd_ops.size() + 2;
+    std::vector<cudaEvent_t> ev(nops + 1);
+    for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+    cudaStream_t st = t->stream;
+    for (int rep = 0; rep < reps; ++rep) {
+        size_t k = 0;
+        cudaEventRecord(ev[k++], st);
+        cudaMemsetAsync(t->zero_base, 0, t->zero_bytes, st);
+        diffusion_prepare(t->x0, t->sqrt_ac, t->sqrt_1mac, c.B, size_t(c.C_in) * c.H * c.W, c.n_timesteps, c.seed,
+                          t->step_dev, 1, 1, t->tsteps, t->noise, t->xt, st);
+        cudaEventRecord(ev[k++], st);
+        for (auto& op : t->fwd_ops) op(st), cudaEventRecord(ev[k++], st);
+        for (auto& op : t->bwd_ops) op(st), cudaEventRecord(ev[k++], st);
+        adamw_step(t->params, t->grads, t->m, t->v, t->nparams, t->g_lr > 0 ? t->g_lr : 1e-4f, 0.9f, 0.999f, 1e-8f, 0.f,
+                   1.f / float(t->world), t->step_dev, st);
+        run_pack(t, st);
+        increment_step(t->step_dev, st);
+        cudaEventRecord(ev[k++], st);
+        CUDA_TRY(cudaStreamSynchronize(st));
+        float ms = 0;
+        size_t j = 1;
+        cudaEventElapsedTime(&ms, ev[0], ev[1]);
+        out->ms[UB_KIND_OPTIM] += ms;
+        for (size_t i = 0; i < t->fwd_ops.size(); ++i, ++j) {
+            cudaEventElapsedTime(&ms, ev[j], ev[j + 1]);
+            out->ms[t->fwd_info[i].kind] += ms;
+        }
+        for (size_t i = 0; i < t->bwd_ops.size(); ++i, ++j) {
+            cudaEventElapsedTime(&ms, ev[j], ev[j + 1]);
+            out->ms[t->bwd_info[i].kind] += ms;
+        }
+        cudaEventElapsedTime(&ms, ev[j], ev[j + 1]);
+        out->ms[UB_KIND_OPTIM] += ms;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    for (int k = 0; k < UB_NUM_KINDS; ++k) out->ms[k] /= reps, out->total_ms += out->ms[k];
+    auto acc = [&](const std::vector<UbTrainer::OpInfo>& v) {
+        for (auto& i : v) out->flops[i.kind] += i.flops, out->bytes[i.kind] += i.bytes, out->launches[i.kind] += i.launches;
+    };
+    acc(t->fwd_info), acc(t->bwd_info);
+    out->launches[UB_KIND_OPTIM] += 5;
+    const double img = double(c.B) * c.C_in * c.H * c.W * 4;
+    out->bytes[UB_KIND_OPTIM] += 3 * img + 7.0 * 4 * t->nparams + 4.0 * t->nparams + 2.0 * 2 * t->nparams;
+    t->host_step += reps;
     return UB_OK;
 }
 
