@@ -1,0 +1,65 @@
+"""Host-side logic that needs no GPU: parameter planner of the C++ graph builder vs the oracle's layer list,
+checkpoint byte layout, batch sharding."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+
+@pytest.mark.parametrize("kw,okw", [
+    (dict(), dict()),
+    (dict(H=128, W=128, channel_mult=(1, 1, 2, 3, 4), att_start_level=3),
+     dict(H=128, W=128, channel_mult=(1, 1, 2, 3, 4), attn_start_level=3)),
+    (dict(H=32, W=32, channel_mult=(1, 2), att_start_level=1), dict(H=32, W=32, channel_mult=(1, 2), attn_start_level=1)),
+    (dict(C_model=128, channel_mult=(1, 2, 2), att_start_level=2, n_res_blocks=1),
+     dict(model_channels=128, channel_mult=(1, 2, 2), attn_start_level=2, num_res_blocks=1)),
+])
+def test_builder_param_count_matches_oracle(ub, oracle, kw, okw):
+    """ub_num_params runs the C++ graph builder in counting mode (no CUDA call)."""
+    cfg = ub.default_config(**kw)
+    assert ub.num_params(cfg) == oracle.num_params(oracle.UNetConfig(**okw))
+
+
+def test_default_config_is_the_reference_model(ub):
+    cfg = ub.default_config()
+    assert (cfg.B, cfg.C_in, cfg.C_model, cfg.C_out, cfg.H, cfg.W, cfg.max_period) == (32, 3, 64, 3, 64, 64, 1000)
+    assert list(cfg.channel_mult)[:4] == [1, 2, 3, 4] and cfg.n_levels == 4 and cfg.att_start_level == 2
+    assert ub.num_params(cfg) == 20494211
+
+
+def test_bad_configs_are_rejected_without_gpu(ub):
+    assert ub.num_params(ub.default_config(head_size=16)) == 0
+    assert ub.num_params(ub.default_config(C_model=48)) == 0
+    assert ub.num_params(ub.default_config(H=60)) == 0
+
+
+def test_checkpoint_header_reader(ub, oracle, tmp_path):
+    O = oracle
+    cfg = O.UNetConfig(channel_mult=(1, 2), attn_start_level=1, H=32, W=32)
+    flat = np.arange(O.num_params(cfg), dtype=np.float32)
+    path = str(tmp_path / "m.bin")
+    O.write_model_bin(path, cfg, flat, B=8)
+    c = ub.default_config()
+    rc = ub.lib().ub_read_checkpoint_header(path.encode(), ctypes.byref(c))
+    assert rc == 0 and (c.B, c.C_in, c.C_model, c.C_out, c.H, c.W, c.max_period) == (8, 3, 64, 3, 32, 32, 1000)
+    with open(path, "r+b") as f:
+        f.write(b"\0\0\0\0")
+    assert ub.lib().ub_read_checkpoint_header(path.encode(), ctypes.byref(c)) != 0
+    assert b"magic" in ub.lib().ub_last_error()
+
+
+def test_data_bin_format(oracle, tmp_path):
+    """prepare_data.py:20-38 layout."""
+    imgs = np.random.default_rng(0).uniform(-1, 1, (5, 3, 8, 8)).astype(np.float32)
+    p = str(tmp_path / "d.bin")
+    oracle.write_data_bin(p, imgs)
+    hdr = np.fromfile(p, dtype=np.int32, count=256)
+    assert list(hdr[:5]) == [20240620, 5, 3, 8, 8]
+    np.testing.assert_array_equal(np.fromfile(p, dtype=np.float32, offset=1024).reshape(imgs.shape), imgs)
+
+
+def test_shard_batch(ub):
+    assert [ub.shard_batch(256, r, 8) for r in (0, 3, 7)] == [(0, 32), (96, 128), (224, 256)]
+    with pytest.raises(ValueError):
+        ub.shard_batch(10, 0, 4)

@@ -1,0 +1,59 @@
+"""Direct check of the oracle against the reference's own Python modules -- only where /root/reference exists
+(the build container).  On the GPU box the committed golden vectors (test_oracle_golden.py) carry the pin."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "dev")), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def ref_unet():
+    sys.path.insert(0, os.path.join(REF, "dev"))
+    import unet as ref_unet_mod  # dev/unet.py (imports dev/resblock.py, dev/utils.py)
+    return ref_unet_mod
+
+
+@pytest.mark.parametrize("B", [1, 2])
+def test_forward_backward_equal(oracle, ref_unet, B):
+    O = oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.UNetConfig()
+    torch.manual_seed(0)
+    model = ref_unet.UNetModel(3, 64, 3, 2, (4, 8), num_head_channels=32)
+    P = O.init_params(cfg, seed=0)
+    for n, p in model.named_parameters():
+        assert torch.equal(P[n], p.detach()), n
+    x0, t, noise = O.synthetic_batch(cfg, B)
+    xt = O.q_sample(x0, t, noise)
+    flat = O.flatten_params(cfg, P)
+    loss, out, g = O.train_step_grads(cfg, flat, x0, t, noise)
+    out_ref = model(xt, t)
+    loss_ref = ((out_ref - noise) ** 2).mean()
+    loss_ref.backward()
+    g_ref = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    assert abs(float(loss) - float(loss_ref)) < 1e-6
+    assert float((out - out_ref.detach()).abs().max()) < 1e-5
+    assert float((g - g_ref).abs().max()) < 1e-6 + 1e-4 * float(g_ref.abs().max())
+
+
+def test_five_level_config_matches_reference(oracle, ref_unet):
+    """BASELINE config 5 shape (128x128, channel_mult 1-1-2-3-4, attention at 16x16 and 8x8), tiny batch."""
+    O = oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.UNetConfig(channel_mult=(1, 1, 2, 3, 4), attn_start_level=3, H=128, W=128)
+    torch.manual_seed(0)
+    model = ref_unet.UNetModel(3, 64, 3, 2, cfg.attention_resolutions(), channel_mult=cfg.channel_mult,
+                               num_head_channels=32)
+    names = [(n, tuple(p.shape)) for n, p in model.named_parameters()]
+    assert names == O.param_spec(cfg)
+    assert O.num_params(cfg) == 21082755
+    P = O.init_params(cfg, seed=0)
+    x = torch.randn(1, 3, 128, 128)
+    t = torch.tensor([[17.0]])
+    with torch.no_grad():
+        assert float((O.unet_forward(cfg, P, x, t) - model(x, t)).abs().max()) < 1e-5

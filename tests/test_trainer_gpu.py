@@ -1,0 +1,199 @@
+"""Full training step through the C ABI vs the oracle (BASELINE config 1: dev/unet_test.py semantics at B=4)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup(oracle):
+    O = oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.UNetConfig()
+    flat = O.flatten_params(cfg, O.init_params(cfg, seed=0))
+    return O, cfg, flat
+
+
+def _per_tensor_rel(O, cfg, g, g_ref):
+    off, out = 0, []
+    for name, shape in O.param_spec(cfg):
+        n = int(np.prod(shape))
+        a, b = g[off:off + n], g_ref[off:off + n]
+        out.append((float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30)), name))
+        off += n
+    return out
+
+
+def test_forward_backward_matches_oracle_B4(ub, setup):
+    """out, loss and all 326 gradient tensors (dev/unet_test.cu:2082-2107 checks the same set)."""
+    O, cfg, flat = setup
+    B = 4
+    x0, t, noise = O.synthetic_batch(cfg, B)
+    tr = ub.Trainer(B=B)
+    tr.set_params(flat.numpy())
+    loss = tr.forward_backward(x0.numpy(), t.numpy(), noise.numpy())
+    out, g = tr.get_output(), tr.get_grads()
+    loss_ref, out_ref, g_ref = O.train_step_grads(cfg, flat, x0, t, noise)
+    g_ref = g_ref.numpy()
+    assert not np.isnan(g).any()
+    assert abs(loss - float(loss_ref)) <= 2e-3 * float(loss_ref)          # loss: 2e-3 relative
+    assert np.abs(out - out_ref.numpy()).max() <= 3e-2 * np.abs(out_ref.numpy()).max()   # bf16 activations
+    cos = float(g @ g_ref / (np.linalg.norm(g) * np.linalg.norm(g_ref)))
+    assert cos > 0.9995, cos
+    assert np.linalg.norm(g - g_ref) <= 2e-2 * np.linalg.norm(g_ref)      # global rel-L2 of all gradients
+    worst = max(_per_tensor_rel(O, cfg, g, g_ref))
+    assert worst[0] <= 0.15, worst                                        # every tensor: max-norm relative
+    tr.close()
+
+
+def test_golden_fixture_B2(ub, setup, golden_dir):
+    """Same comparison against the committed vectors that came from the reference's own UNetModel."""
+    O, cfg, flat = setup
+    g = np.load(os.path.join(golden_dir, "unet_step_B2.npz"))
+    x0, t, noise = O.synthetic_batch(cfg, 2)
+    tr = ub.Trainer(B=2)
+    tr.set_params(flat.numpy())
+    loss = tr.forward_backward(x0.numpy(), t.numpy(), noise.numpy())
+    assert abs(loss - g["loss_trace"][0]) <= 2e-3 * g["loss_trace"][0]
+    out = tr.get_output().reshape(-1)[::37]
+    assert np.abs(out - g["out_slice"]).max() <= 3e-2 * np.abs(g["out_slice"]).max()
+    grads = tr.get_grads()
+    off, norms = 0, []
+    for _, s in O.param_spec(cfg):
+        n = int(np.prod(s))
+        norms.append(float(np.linalg.norm(grads[off:off + n].astype(np.float64))))
+        off += n
+    np.testing.assert_allclose(np.array(norms), g["grad_norms"], rtol=0.1)
+    tr.close()
+
+
+def test_ten_step_loss_trace_and_params(ub, setup):
+    """10 AdamW steps (trainer hyper-parameters of train_unet.cu:5037): loss trace within 1e-2, as the reference's
+    own eyeballed cpu-vs-gpu loss print (dev/unet_test.cu:2117-2132)."""
+    O, cfg, flat = setup
+    B = 4
+    batches = [O.synthetic_batch(cfg, B, seed=1234 + i) for i in range(10)]
+    losses_ref, flat_ref = O.train_steps(cfg, flat, batches, lr=1e-4)
+    tr = ub.Trainer(B=B)
+    tr.set_params(flat.numpy())
+    losses = [tr.train_step(b[0].numpy(), b[1].numpy(), b[2].numpy(), lr=1e-4) for b in batches]
+    assert np.abs(np.array(losses) - np.array(losses_ref)).max() <= 1e-2
+    p = tr.get_params()
+    assert np.abs(p - flat_ref.numpy()).max() <= 2.5e-3   # 10 steps x lr 1e-4 bounds any weight's travel by 1e-3
+    tr.close()
+
+
+def test_eager_and_graph_steps_agree(ub, setup):
+    O, cfg, flat = setup
+    B = 2
+    x0, t, noise = O.synthetic_batch(cfg, B)
+    res = []
+    for graph in (0, 1):
+        tr = ub.Trainer(B=B, use_cuda_graph=graph)
+        tr.set_params(flat.numpy())
+        l1 = tr.train_step(x0.numpy(), t.numpy(), noise.numpy())
+        l2 = tr.train_step(x0.numpy(), t.numpy(), noise.numpy())
+        res.append((l1, l2, tr.get_params()))
+        tr.close()
+    assert abs(res[0][0] - res[1][0]) < 1e-4 and abs(res[0][1] - res[1][1]) < 1e-3
+    # two AdamW steps move a weight by at most 2*lr; a near-zero gradient whose sign differs between the runs
+    # (atomic summation order) can therefore differ by 4*lr
+    assert np.abs(res[0][2] - res[1][2]).max() <= 4.5e-4
+    assert np.abs(res[0][2] - res[1][2]).mean() < 2e-6
+
+
+def test_update_matches_oracle_adamw(ub, setup):
+    """unet_update / adamw_kernel2 (train_unet.cu:4720-4757) on the gradients the CUDA path produced: fp32-exact."""
+    O, cfg, flat = setup
+    B = 2
+    x0, t, noise = O.synthetic_batch(cfg, B)
+    tr = ub.Trainer(B=B)
+    tr.set_params(flat.numpy())
+    tr.forward_backward(x0.numpy(), t.numpy(), noise.numpy())
+    g = torch.from_numpy(tr.get_grads())
+    tr.update(lr=1e-3, weight_decay=0.01)  # dev/unet_test.cu:2108 hyper-parameters
+    p = tr.get_params()
+    p_ref, _, _ = O.adamw_step(flat, g, torch.zeros_like(flat), torch.zeros_like(flat), 1, lr=1e-3, wd=0.01)
+    np.testing.assert_allclose(p, p_ref.numpy(), rtol=0, atol=2e-6)
+    assert np.abs(tr.get_grads()).max() == 0.0   # update zeroes the gradient arena (unet_zero_grad)
+    tr.close()
+
+
+def test_device_noise_statistics(ub, setup):
+    """Device-side timestep / noise draws (Philox) replace cuRAND (train_unet.cu:3115-3254): sanity of the moments
+    through the loss of an untrained net, and different steps draw different noise."""
+    O, cfg, flat = setup
+    tr = ub.Trainer(B=8)
+    tr.set_params(flat.numpy())
+    x0 = (torch.rand(8, 3, 64, 64) * 2 - 1).numpy()
+    l1 = tr.forward_backward(x0)
+    l2 = tr.forward_backward(x0)
+    assert 0.8 < l1 < 1.5 and 0.8 < l2 < 1.5    # E[(out - eps)^2] ~ 1 for eps ~ N(0,1) and a near-zero initial output
+    tr.close()
+
+
+def test_checkpoint_roundtrip_and_reference_layout(ub, setup, tmp_path):
+    O, cfg, flat = setup
+    tr = ub.Trainer(B=2)
+    ref_file = str(tmp_path / "unet_init.bin")
+    O.write_model_bin(ref_file, cfg, flat.numpy(), B=32)     # the layout train_unet.py:768-795 writes
+    tr.load(ref_file)
+    np.testing.assert_array_equal(tr.get_params(), flat.numpy())
+    x0, t, noise = O.synthetic_batch(cfg, 2)
+    tr.train_step(x0.numpy(), t.numpy(), noise.numpy())
+    out_file = str(tmp_path / "model_1.bin")
+    tr.save(out_file, with_adamw=True)
+    header, rest = O.read_model_bin(out_file)                 # generate.py:17-27 reads header + params
+    n = tr.nparams
+    assert list(header[:10]) == [12345678, 2, 3, 64, 3, 64, 64, 1000, 1, 0] and header[10] == 1
+    assert rest.size == 3 * n and os.path.getsize(out_file) == 1024 + 12 * n
+    np.testing.assert_array_equal(rest[:n], tr.get_params())
+    tr2 = ub.Trainer(B=2)
+    tr2.load(out_file)                                        # resume: params + m + v + step counter
+    b = O.synthetic_batch(cfg, 2, seed=7)
+    la = tr.train_step(b[0].numpy(), b[1].numpy(), b[2].numpy())
+    lb = tr2.train_step(b[0].numpy(), b[1].numpy(), b[2].numpy())
+    assert abs(la - lb) < 1e-3
+    assert np.abs(tr.get_params() - tr2.get_params()).max() <= 2.5e-4   # one step: 2*lr + rounding
+    tr.close(), tr2.close()
+
+
+def test_predict_matches_oracle_forward(ub, setup):
+    """Forward only (what generate.py:29-52 needs from the checkpoint consumer side)."""
+    O, cfg, flat = setup
+    P = O.unflatten_params(cfg, flat)
+    xt = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(5))
+    t = torch.tensor([[10.0], [900.0]])
+    tr = ub.Trainer(B=2)
+    tr.set_params(flat.numpy())
+    out = tr.predict(xt.numpy(), t.numpy())
+    with torch.no_grad():
+        ref = O.unet_forward(cfg, P, xt, t).numpy()
+    assert np.abs(out - ref).max() <= 3e-2 * np.abs(ref).max()
+    tr.close()
+
+
+def test_full_size_properties_B32(ub, setup):
+    """BASELINE config 3 size (B=32): size-independent properties instead of an oracle run --
+    (1) the loss of a batch made of 8 copies of a B=4 batch equals the B=4 loss, and its gradient equals the B=4
+    gradient (mean reduction), (2) training on a fixed batch decreases the loss."""
+    O, cfg, flat = setup
+    x0, t, noise = O.synthetic_batch(cfg, 4)
+    tr4 = ub.Trainer(B=4)
+    tr4.set_params(flat.numpy())
+    l4 = tr4.forward_backward(x0.numpy(), t.numpy(), noise.numpy())
+    g4 = tr4.get_grads()
+    tr4.close()
+    rep = lambda a: np.concatenate([a.numpy()] * 8, axis=0)
+    tr = ub.Trainer(B=32)
+    tr.set_params(flat.numpy())
+    l32 = tr.forward_backward(rep(x0), rep(t), rep(noise))
+    g32 = tr.get_grads()
+    assert abs(l32 - l4) < 1e-4
+    assert np.linalg.norm(g32 - g4) <= 5e-3 * np.linalg.norm(g4)
+    losses = [tr.train_step(rep(x0), rep(t), rep(noise), lr=1e-4) for _ in range(6)]
+    assert losses[-1] < losses[0]
+    tr.close()

@@ -345,16 +345,32 @@ __global__ void __launch_bounds__(kConvThreads) igemm_wgrad_kernel(const __grid_
     if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
-// dweight[o][c][tap] = sum_split partial[split][tap][o][c]   (deterministic order)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dweight, int nsplit,
-                                    int ntaps, int Cout, int Cin) {
-    const size_t n = size_t(Cout) * Cin;
-    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;  // (o, c) index
-    if (i >= n) return;
-    for (int tap = 0; tap < ntaps; ++tap) {
-        float s = 0.f;
-        for (int sp = 0; sp < nsplit; ++sp) s += partial[(size_t(sp) * ntaps + tap) * n + i];
-        dweight[i * ntaps + tap] = s;
+// dweight[o][c][tap] = sum_split partial[split][tap][o][c], deterministic (fixed summation tree).
+// grid (ceil(n/32), ntaps), block 256 = 32 consecutive (o,c) elements x 8 split lanes: every warp reads whole
+// 128-byte rows of one split, 8 splits are in flight per block.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial,
+                                                           float* __restrict__ dweight, int nsplit, int ntaps,
+                                                           size_t n) {
+    __shared__ float red[8][33];
+    const int el = threadIdx.x & 31, lane8 = threadIdx.x >> 5;
+    const size_t e = size_t(blockIdx.x) * 32 + el;
+    const int tap = blockIdx.y;
+    float s0 = 0.f, s1 = 0.f;
+    if (e < n) {
+        int sp = lane8;
+        for (; sp + 8 < nsplit; sp += 16) {
+            s0 += partial[(size_t(sp) * ntaps + tap) * n + e];
+            s1 += partial[(size_t(sp + 8) * ntaps + tap) * n + e];
+        }
+        if (sp < nsplit) s0 += partial[(size_t(sp) * ntaps + tap) * n + e];
+    }
+    red[lane8][el] = s0 + s1;
+    __syncthreads();
+    if (lane8 == 0 && e < n) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][el];
+        dweight[e * ntaps + tap] = t;
     }
 }
 
@@ -540,7 +556,7 @@ int igemm_wgrad_plan(IgemmWgradParams* p, const __nv_bfloat16* dy, int ldy, cons
     p->stages = stages;
     const int ktiles = p->tiles_w * p->tiles_h * p->tiles_b;
     const int base_ctas = (Cout / p->MO) * (Cin / p->NC) * (ntaps / p->TC);
-    int nsplit = ceil_div_i(2 * sm_count, base_ctas);  // aim at ~2 waves of CTAs
+    int nsplit = ceil_div_i(sm_count, base_ctas);  // one CTA per SM (a CTA owns the SM's smem and TMEM)
     if (nsplit > ktiles / 4) nsplit = ktiles / 4;      // at least 4 K tiles per CTA
     if (nsplit < 1) nsplit = 1;
     while (nsplit > 1 && igemm_wgrad_partial_floats(Cin, Cout, ntaps, nsplit) > partial_cap_floats) --nsplit;
@@ -563,8 +579,8 @@ int igemm_wgrad_launch(const IgemmWgradParams& p, cudaStream_t st) {
 
 int igemm_wgrad_reduce(const IgemmWgradParams& p, float* dweight, cudaStream_t st) {
     const size_t n = size_t(p.Cout) * p.Cin;
-    wgrad_reduce_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(p.partial, dweight, p.nsplit, p.ntaps, p.Cout,
-                                                                    p.Cin);
+    wgrad_reduce_kernel<<<dim3(unsigned((n + 31) / 32), p.ntaps), 256, 0, st>>>(p.partial, dweight, p.nsplit, p.ntaps,
+                                                                               n);
     return int(cudaGetLastError());
 }
 

@@ -350,20 +350,33 @@ __global__ void small_linear_bwd_w_kernel(const SmallLinear* __restrict__ table,
         if (e.db2) e.db2[o] = sb;
     }
 }
-// dinp[n][k] += sum_o dout[n][o] * W[o][k]
+// dinp[n][k] += sum_o dout[n][o] * W[o][k]; blockIdx.z walks chunks of 32 output channels
 __global__ void small_linear_bwd_x_kernel(const SmallLinear* __restrict__ table, int N) {
     const SmallLinear e = table[blockIdx.y];
     if (!e.dinp) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N * e.C) return;
+    const int o0 = blockIdx.z * 32;
+    if (i >= N * e.C || o0 >= e.OC) return;
     const int n = i / e.C, k = i % e.C;
+    const int o1 = min(o0 + 32, e.OC);
     float s = 0.f;
-    for (int o = 0; o < e.OC; ++o) s += e.dout[size_t(n) * e.OC + o] * e.w[size_t(o) * e.C + k];
+#pragma unroll 8
+    for (int o = o0; o < o1; ++o) s += e.dout[size_t(n) * e.OC + o] * e.w[size_t(o) * e.C + k];
     atomicAdd(&e.dinp[i], s);
 }
 void small_linear_bwd(const SmallLinear* table_dev, int n_entries, int N, int max_oc, int max_c, cudaStream_t st) {
     small_linear_bwd_w_kernel<<<dim3((max_oc * max_c + 255) / 256, n_entries), 256, 0, st>>>(table_dev, N);
-    small_linear_bwd_x_kernel<<<dim3((N * max_c + 255) / 256, n_entries), 256, 0, st>>>(table_dev, N);
+    small_linear_bwd_x_kernel<<<dim3((N * max_c + 255) / 256, n_entries, (max_oc + 31) / 32), 256, 0, st>>>(table_dev,
+                                                                                                          N);
+}
+
+// out[i] = silu(x[i])
+__global__ void silu_f32_kernel(const float* __restrict__ x, float* __restrict__ out, size_t n) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = silu_f(x[i]);
+}
+void silu_f32(const float* x, float* out, size_t n, cudaStream_t st) {
+    silu_f32_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(x, out, n);
 }
 
 __global__ void dsilu_mul_kernel(const float* __restrict__ dact, const float* __restrict__ pre, float* __restrict__ g,

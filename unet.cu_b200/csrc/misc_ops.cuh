@@ -35,6 +35,7 @@ struct SmallLinear {
 };
 void small_linear_fwd(const SmallLinear* table_dev, int n_entries, int N, int max_oc, cudaStream_t st);
 void small_linear_bwd(const SmallLinear* table_dev, int n_entries, int N, int max_oc, int max_c, cudaStream_t st);
+void silu_f32(const float* x, float* out, size_t n, cudaStream_t st);
 // g[i] = dact[i] * silu'(pre[i])
 void dsilu_mul(const float* dact, const float* pre, float* g, size_t n, cudaStream_t st);
 // timestep embedding (replaces get_timestep_embeddings, train_unet.cu:3258-3313): out[b][j]=cos(t f_j), [half+j]=sin

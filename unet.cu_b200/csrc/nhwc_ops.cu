@@ -19,6 +19,15 @@ __device__ __forceinline__ void ld8(const bf16* p, float (&f)[8]) {
         f[2 * i + 1] = __bfloat162float(h.y);
     }
 }
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&u[i]);
+        f[2 * i] = __bfloat162float(h.x);
+        f[2 * i + 1] = __bfloat162float(h.y);
+    }
+}
 __device__ __forceinline__ void st8(bf16* p, const float (&f)[8]) {
     uint32_t u[4];
 #pragma unroll
@@ -70,11 +79,20 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, int ldx, int HW, int
     const int p0 = blockIdx.x * ppb;
     const int p1 = min(p0 + ppb, HW);
     const bf16* xb = x + (size_t(b) * HW) * ldx + j * 8;
-    for (int p = p0 + r; p < p1; p += rows) {
-        float f[8];
-        ld8(xb + size_t(p) * ldx, f);
+    for (int p = p0 + r; p < p1; p += 4 * rows) {  // 4 independent 16-byte loads in flight per thread
+        uint4 v[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s[i] += f[i], ss[i] += f[i] * f[i];
+        for (int u = 0; u < 4; ++u) {
+            const int pp = p + u * rows;
+            v[u] = pp < p1 ? *reinterpret_cast<const uint4*>(xb + size_t(pp) * ldx) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float f[8];
+            unpack8(v[u], f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s[i] += f[i], ss[i] += f[i] * f[i];
+        }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -141,15 +159,26 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int ldx, const float
     const int p1 = min(p0 + ppb, HW);
     const bf16* xb = x + (size_t(b) * HW) * ldx + j * 8;
     bf16* yb = y + (size_t(b) * HW) * ldy + j * 8;
-    for (int p = p0 + r; p < p1; p += rows) {
-        float f[8];
-        ld8(xb + size_t(p) * ldx, f);
+    for (int p = p0 + r; p < p1; p += 4 * rows) {
+        uint4 v[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float z = f[i] * a[i] + bb[i];
-            f[i] = silu ? silu_f(z) : z;
+        for (int u = 0; u < 4; ++u) {
+            const int pp = p + u * rows;
+            v[u] = pp < p1 ? *reinterpret_cast<const uint4*>(xb + size_t(pp) * ldx) : make_uint4(0, 0, 0, 0);
         }
-        st8(yb + size_t(p) * ldy, f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int pp = p + u * rows;
+            if (pp >= p1) break;
+            float f[8];
+            unpack8(v[u], f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float z = f[i] * a[i] + bb[i];
+                f[i] = silu ? silu_f(z) : z;
+            }
+            st8(yb + size_t(pp) * ldy, f);
+        }
     }
 }
 
@@ -176,25 +205,38 @@ __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ x, int ldx, const b
     }
     __syncthreads();
     const int j = threadIdx.x % C8, r = threadIdx.x / C8;
-    float s1[8], s2[8];
+    float s1[8], s2[8], ca[8], cb[8], cr[8], cm[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+    for (int i = 0; i < 8; ++i) {
+        s1[i] = s2[i] = 0.f;
+        ca[i] = sa[j * 8 + i], cb[i] = sb[j * 8 + i], cr[i] = sr[j * 8 + i], cm[i] = smr[j * 8 + i];
+    }
     const int p0 = blockIdx.x * ppb;
     const int p1 = min(p0 + ppb, HW);
     const bf16* xb = x + (size_t(b) * HW) * ldx + j * 8;
     const bf16* db = dy + (size_t(b) * HW) * lddy + j * 8;
-    for (int p = p0 + r; p < p1; p += rows) {
-        float f[8], d[8];
-        ld8(xb + size_t(p) * ldx, f);
-        ld8(db + size_t(p) * lddy, d);
+    for (int p = p0 + r; p < p1; p += 2 * rows) {
+        uint4 vx[2], vd[2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = j * 8 + i;
-            float dz = d[i];
-            if (silu) dz *= dsilu_f(f[i] * sa[c] + sb[c]);
-            const float xh = f[i] * sr[c] - smr[c];
-            s1[i] += dz;
-            s2[i] += dz * xh;
+        for (int u = 0; u < 2; ++u) {
+            const int pp = p + u * rows;
+            const bool ok = pp < p1;
+            vx[u] = ok ? *reinterpret_cast<const uint4*>(xb + size_t(pp) * ldx) : make_uint4(0, 0, 0, 0);
+            vd[u] = ok ? *reinterpret_cast<const uint4*>(db + size_t(pp) * lddy) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            float f[8], d[8];
+            unpack8(vx[u], f);
+            unpack8(vd[u], d);  // zero-filled when out of range: contributes nothing
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float dz = d[i];
+                if (silu) dz *= dsilu_f(f[i] * ca[i] + cb[i]);
+                const float xh = f[i] * cr[i] - cm[i];
+                s1[i] += dz;
+                s2[i] += dz * xh;
+            }
         }
     }
 #pragma unroll
@@ -248,33 +290,46 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ x, int ldx, const b
     }
     __syncthreads();
     const int j = threadIdx.x % C8, r = threadIdx.x / C8;
-    float cs[8];
+    float cs[8], ca[8], cb[8], cr[8], cm[8], c1[8], c2[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) cs[i] = 0.f;
+    for (int i = 0; i < 8; ++i) {
+        cs[i] = 0.f;
+        ca[i] = sa[j * 8 + i], cb[i] = sb[j * 8 + i], cr[i] = sr[j * 8 + i], cm[i] = smr[j * 8 + i];
+        c1[i] = sm1[j * 8 + i], c2[i] = sm2[j * 8 + i];
+    }
     const int p0 = blockIdx.x * ppb;
     const int p1 = min(p0 + ppb, HW);
     const size_t img = size_t(b) * HW;
-    for (int p = p0 + r; p < p1; p += rows) {
-        float f[8], d[8], o[8];
-        ld8(x + (img + p) * ldx + j * 8, f);
-        ld8(dy + (img + p) * lddy + j * 8, d);
-        if (add_in) {
-            ld8(add_in + (img + p) * ldadd + j * 8, o);
-        } else {
+    for (int p = p0 + r; p < p1; p += 2 * rows) {
+        uint4 vx[2], vd[2], va[2];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = 0.f;
+        for (int u = 0; u < 2; ++u) {
+            const int pp = p + u * rows;
+            const bool ok = pp < p1;
+            vx[u] = ok ? *reinterpret_cast<const uint4*>(x + (img + pp) * ldx + j * 8) : make_uint4(0, 0, 0, 0);
+            vd[u] = ok ? *reinterpret_cast<const uint4*>(dy + (img + pp) * lddy + j * 8) : make_uint4(0, 0, 0, 0);
+            va[u] = (ok && add_in) ? *reinterpret_cast<const uint4*>(add_in + (img + pp) * ldadd + j * 8)
+                                   : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = j * 8 + i;
-            float dz = d[i];
-            if (silu) dz *= dsilu_f(f[i] * sa[c] + sb[c]);
-            const float xh = f[i] * sr[c] - smr[c];
-            const float g = sgr[c] * dz - sm1[c] - xh * sm2[c];
-            cs[i] += g;
-            o[i] += g;
+        for (int u = 0; u < 2; ++u) {
+            const int pp = p + u * rows;
+            if (pp >= p1) break;
+            float f[8], d[8], o[8];
+            unpack8(vx[u], f);
+            unpack8(vd[u], d);
+            unpack8(va[u], o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float dz = d[i];
+                if (silu) dz *= dsilu_f(f[i] * ca[i] + cb[i]);
+                const float xh = f[i] * cr[i] - cm[i];
+                const float g = ca[i] * dz - c1[i] - xh * c2[i];  // ca == gamma * rstd
+                cs[i] += g;
+                o[i] += g;
+            }
+            st8(dx + (img + pp) * lddx + j * 8, o);
         }
-        st8(dx + (img + p) * lddx + j * 8, o);
     }
     if (colsum_out) {
 #pragma unroll
@@ -512,36 +567,44 @@ void conv_out_dgrad(const float* dout, const float* w, int B, int Cin, int Cout,
         dout, w, nullptr, Cout, Cin, H, W, 1, total, da, ldda);
 }
 
-// partial[blk][cb][s*9+tap] = sum_{p in block} yb[p][cb] * xs[b][s][p + shift(tap)] ; partial_b[blk][cb] = sum yb
-// blockDim = Cb * 4 (4 pixel lanes per channel), each block walks ppb pixels.
+// partial[blk][cb][s*9+tap] = sum_{p in block} yb[p][cb] * xs[b][s][p + shift(tap)] ; partial[blk][cb][NT] = sum yb
+// blockDim = Cb * 4 (4 pixel lanes per channel).  A block walks whole image rows; the 3 x (W+2) zero-padded window
+// of the small-channel tensor is staged in smem once per row, so the inner loop is 27 smem-broadcast FMAs per pixel
+// with no index arithmetic.
 __global__ void smallc_wgrad_kernel(const float* __restrict__ xs, const bf16* __restrict__ yb, int ldy, int Cs, int Cb,
-                                    int H, int W, size_t npix, size_t ppb, float* __restrict__ partial) {
-    extern __shared__ float sred[];  // [4][Cb][Cs*9+1]
+                                    int B, int H, int W, float* __restrict__ partial) {
+    extern __shared__ float sdyn[];  // window [Cs][3][W+2], then reduction scratch [4][Cb][NT+1]
     const int cb = threadIdx.x % Cb, q = threadIdx.x / Cb;
-    const int NT = Cs * 9;
+    const int NT = Cs * 9, Wp = W + 2;
+    float* win = sdyn;
+    float* sred = sdyn + Cs * 3 * Wp;
     float acc[37];  // Cs <= 4
 #pragma unroll
     for (int k = 0; k < 37; ++k) acc[k] = 0.f;
-    const size_t p0 = size_t(blockIdx.x) * ppb;
-    const size_t p1 = p0 + ppb < npix ? p0 + ppb : npix;
-    for (size_t p = p0 + q; p < p1; p += 4) {
-        const float v = __bfloat162float(yb[p * ldy + cb]);
-        const int wq = int(p % W), h = int((p / W) % H);
-        const size_t b = p / (size_t(W) * H);
-        acc[36] += v;
+    for (int row = blockIdx.x; row < B * H; row += gridDim.x) {
+        const int b = row / H, h = row % H;
+        __syncthreads();
+        for (int i = threadIdx.x; i < Cs * 3 * Wp; i += blockDim.x) {
+            const int wq = i % Wp - 1, rr = (i / Wp) % 3, s = i / (3 * Wp);
+            const int hh = h + rr - 1;
+            win[i] = (hh >= 0 && hh < H && wq >= 0 && wq < W) ? xs[((size_t(b) * Cs + s) * H + hh) * W + wq] : 0.f;
+        }
+        __syncthreads();
+        const bf16* yr = yb + (size_t(row) * W) * ldy + cb;
+        for (int w = q; w < W; w += 4) {
+            const float v = __bfloat162float(yr[size_t(w) * ldy]);
+            acc[36] += v;
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {  // fully unrolled so acc[] stays in registers
-            if (s < Cs) {
-                const float* xp = xs + (b * Cs + s) * size_t(H) * W;
+            for (int s = 0; s < 4; ++s) {
+                if (s < Cs) {
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
-                    const int hh = h + tap / 3 - 1, ww = wq + tap % 3 - 1;
-                    if (hh >= 0 && hh < H && ww >= 0 && ww < W)
-                        acc[s * 9 + tap] += v * __ldg(xp + size_t(hh) * W + ww);
+                    for (int tap = 0; tap < 9; ++tap)
+                        acc[s * 9 + tap] += v * win[(s * 3 + tap / 3) * Wp + w + tap % 3];
                 }
             }
         }
     }
+    __syncthreads();
     float* mine = sred + (size_t(q) * Cb + cb) * (NT + 1);
 #pragma unroll
     for (int k = 0; k < 36; ++k)
@@ -576,19 +639,17 @@ __global__ void smallc_wgrad_reduce_kernel(const float* __restrict__ partial, in
 }
 static void smallc_wgrad(const float* xs, const bf16* yb, int ldy, int B, int Cs, int Cb, int H, int W, int mode,
                          float* dw, float* db, float* scratch, size_t scratch_floats, cudaStream_t st) {
-    const size_t npix = size_t(B) * H * W;
     const int NT = Cs * 9;
     size_t nblk = 2 * kSMs;
     const size_t per = size_t(Cb) * (NT + 1);
     if (nblk * per > scratch_floats) nblk = scratch_floats / per;
+    if (nblk > size_t(B) * H) nblk = size_t(B) * H;
     if (nblk < 1) {
         fprintf(stderr, "[unet_b200] smallc_wgrad: scratch too small\n");
         return;
     }
-    const size_t ppb = (npix + nblk - 1) / nblk;
-    nblk = (npix + ppb - 1) / ppb;
-    smallc_wgrad_kernel<<<unsigned(nblk), Cb * 4, 4 * per * sizeof(float), st>>>(xs, yb, ldy, Cs, Cb, H, W, npix, ppb,
-                                                                                  scratch);
+    const size_t smem = (size_t(Cs) * 3 * (W + 2) + 4 * per) * sizeof(float);
+    smallc_wgrad_kernel<<<unsigned(nblk), Cb * 4, smem, st>>>(xs, yb, ldy, Cs, Cb, B, H, W, scratch);
     smallc_wgrad_reduce_kernel<<<unsigned((per + 127) / 128), 128, 0, st>>>(scratch, int(nblk), Cs, Cb, mode, dw, db);
 }
 void conv_in_wgrad(const float* x, const bf16* dy, int lddy, int B, int Cin, int Cout, int H, int W, float* dw,

@@ -1,0 +1,389 @@
+// Drop-in layer operators of include/unet_b200.h, section (1): the launchers of the reference's dev/*.cuh.
+// Contractions (3x3 / 1x1 convolution, linear) run on the tcgen05 implicit-GEMM kernels: the fp32 NCHW operands
+// are converted to NHWC bf16 in a library-owned, grow-only workspace (the reference API has no workspace argument
+// apart from the split-K scratch it passes to conv2d_k3_backward2, which is ignored), the result is written back
+// in the reference layout straight from the GEMM epilogue.  Memory-bound operators are exact fp32 kernels in the
+// reference layout.  Shapes that violate the tensor path's divisibility rules (3-channel layers) use an exact
+// fp32 direct convolution -- still a CUDA kernel of this library, never a CPU path.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+
+#include "../../include/unet_b200.h"
+#include "../csrc/igemm.cuh"
+#include "../csrc/layers_f32.cuh"
+#include "../csrc/misc_ops.cuh"
+#include "../csrc/nhwc_ops.cuh"
+#include "host_common.h"
+
+using namespace ub;
+extern "C" void ub_count_launches(unsigned long long n);
+
+namespace {
+
+struct Workspace {
+    void* p[8] = {nullptr};
+    size_t cap[8] = {0};
+    std::mutex mu;
+    void* get(int slot, size_t bytes) {
+        if (bytes > cap[slot]) {
+            if (p[slot]) cudaFree(p[slot]);
+            size_t want = bytes + bytes / 4;
+            if (cudaMalloc(&p[slot], want) != cudaSuccess) {
+                p[slot] = nullptr, cap[slot] = 0;
+                return nullptr;
+            }
+            cap[slot] = want;
+        }
+        return p[slot];
+    }
+};
+Workspace g_ws;
+
+void fail(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    ub_host_set_error(buf);
+}
+int finish(int launches) {
+    ub_count_launches((unsigned long long)launches);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        fail("CUDA error: %s", cudaGetErrorString(e));
+        return UB_ERR_CUDA;
+    }
+    return UB_OK;
+}
+
+// single-entry weight pack through a 1-element device table kept in workspace slot 7
+int pack_one(const float* w, bf16* wf, bf16* wd, int Cout, int Cin, int ntaps, cudaStream_t st) {
+    PackEntry e{w, wf, wd, Cout, Cin, ntaps};
+    PackEntry* tab = (PackEntry*)g_ws.get(7, 4096);
+    if (!tab) return UB_ERR_CUDA;
+    // stream-ordered upload of 40 bytes (pageable source is copied synchronously into the driver's staging buffer)
+    if (cudaMemcpyAsync(tab, &e, sizeof e, cudaMemcpyHostToDevice, st) != cudaSuccess) return UB_ERR_CUDA;
+    pack_weights(tab, 1, ((Cout + 31) / 32) * ((Cin + 31) / 32), st);
+    return UB_OK;
+}
+
+bool tensor_fprop_ok(int Cin, int Cout) { return Cin % 8 == 0 && Cout % 16 == 0; }
+bool tensor_wgrad_ok(int Cin, int Cout) { return Cin % 64 == 0 && Cout % 64 == 0; }
+
+// generic convolution forward, KS = 1 or 3
+int conv_forward(const float* x, const float* weight, const float* bias, float* out, int B, int Cin, int Cout, int H,
+                 int W, int KS) {
+    cudaStream_t st = ub_layer_stream();
+    const int ntaps = KS * KS;
+    if (B < 1 || Cin < 1 || Cout < 1 || H < 1 || W < 1) {
+        fail("conv forward: bad shape");
+        return UB_ERR_SHAPE;
+    }
+    if (!tensor_fprop_ok(Cin, Cout)) {
+        f32::conv_direct_fwd(x, weight, bias, out, B, Cin, Cout, H, W, KS, st);
+        return finish(1);
+    }
+    std::lock_guard<std::mutex> lk(g_ws.mu);
+    const size_t npix = size_t(B) * H * W;
+    bf16* xb = (bf16*)g_ws.get(0, npix * Cin * 2);
+    bf16* wp = (bf16*)g_ws.get(1, size_t(ntaps) * Cout * Cin * 2);
+    if (!xb || !wp) {
+        fail("workspace allocation failed");
+        return UB_ERR_CUDA;
+    }
+    f32::nchw_to_nhwc_bf16(x, B, Cin, H * W, xb, st);
+    if (pack_one(weight, wp, nullptr, Cout, Cin, ntaps, st)) return UB_ERR_CUDA;
+    ConvSegDesc seg{xb, Cin, Cin, wp, ntaps};
+    ConvEpilogue ep;
+    ep.bias = bias, ep.out = out, ep.out_mode = OUT_NCHW_F32;
+    IgemmConvParams p;
+    int r = igemm_conv_plan(&p, &seg, 1, B, H, W, Cout, ep);
+    if (r) {
+        fail("conv forward: igemm plan failed (%d)", r);
+        return UB_ERR_SHAPE;
+    }
+    igemm_conv_launch(p, st);
+    return finish(3);
+}
+
+int conv_backward(const float* dout, const float* x, const float* weight, float* dx, float* dweight, float* dbias,
+                  int B, int Cin, int Cout, int H, int W, int KS) {
+    cudaStream_t st = ub_layer_stream();
+    const int ntaps = KS * KS;
+    const size_t npix = size_t(B) * H * W;
+    std::lock_guard<std::mutex> lk(g_ws.mu);
+    int launches = 0;
+    const bool dgrad_tc = dx && tensor_fprop_ok(Cout, Cin);   // GEMM N = Cin, K = Cout
+    const bool wgrad_tc = dweight && tensor_wgrad_ok(Cin, Cout);
+    bf16 *dyb = nullptr, *xb = nullptr;
+    if (dgrad_tc || wgrad_tc) {
+        dyb = (bf16*)g_ws.get(2, npix * Cout * 2);
+        if (!dyb) return UB_ERR_CUDA;
+        f32::nchw_to_nhwc_bf16(dout, B, Cout, H * W, dyb, st);
+        launches++;
+    }
+    if (dx) {
+        if (dgrad_tc) {
+            bf16* wd = (bf16*)g_ws.get(1, size_t(ntaps) * Cout * Cin * 2);
+            if (!wd || pack_one(weight, nullptr, wd, Cout, Cin, ntaps, st)) return UB_ERR_CUDA;
+            ConvSegDesc seg{dyb, Cout, Cout, wd, ntaps};
+            ConvEpilogue ep;
+            ep.out = dx, ep.out_mode = OUT_NCHW_F32;
+            IgemmConvParams p;
+            int r = igemm_conv_plan(&p, &seg, 1, B, H, W, Cin, ep);
+            if (r) {
+                fail("conv backward: dgrad plan failed (%d)", r);
+                return UB_ERR_SHAPE;
+            }
+            igemm_conv_launch(p, st);
+            launches += 2;
+        } else {
+            f32::conv_direct_dgrad(dout, weight, dx, B, Cin, Cout, H, W, KS, st);
+            launches++;
+        }
+    }
+    if (dweight) {
+        if (wgrad_tc) {
+            xb = (bf16*)g_ws.get(0, npix * Cin * 2);
+            const size_t cap = size_t(16) << 20;  // floats
+            float* partial = (float*)g_ws.get(3, cap * sizeof(float));
+            if (!xb || !partial) return UB_ERR_CUDA;
+            f32::nchw_to_nhwc_bf16(x, B, Cin, H * W, xb, st);
+            IgemmWgradParams p;
+            int r = igemm_wgrad_plan(&p, dyb, Cout, xb, Cin, B, H, W, Cin, Cout, ntaps, partial, cap, 148);
+            if (r) {
+                fail("conv backward: wgrad plan failed (%d)", r);
+                return UB_ERR_SHAPE;
+            }
+            igemm_wgrad_launch(p, st);
+            igemm_wgrad_reduce(p, dweight, st);
+            launches += 3;
+            if (dbias) f32::nchw_chansum(dout, B, Cout, size_t(H) * W, dbias, st), launches++;
+        } else {
+            f32::conv_direct_wgrad(dout, x, dweight, dbias, B, Cin, Cout, H, W, KS, st);
+            launches += 2;
+        }
+    } else if (dbias) {
+        f32::nchw_chansum(dout, B, Cout, size_t(H) * W, dbias, st), launches++;
+    }
+    return finish(launches);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ub_conv2d_k3_forward3(const float* x, const float* weight, const float* bias, float* out, int B, int C_in,
+                          int C_out, int H, int W) {
+    return conv_forward(x, weight, bias, out, B, C_in, C_out, H, W, 3);
+}
+int ub_conv2d_k3_forward2(const float* x, const float* weight, const float* bias, float* out, int B, int C_in,
+                          int C_out, int H, int W) {
+    return conv_forward(x, weight, bias, out, B, C_in, C_out, H, W, 3);
+}
+int ub_conv2d_k3_backward2(const float* dout, const float* x, const float* weight, float* /*dweight_buf*/,
+                           float* /*dbias_buf*/, float* dx, float* dweight, float* dbias, int B, int C_in, int C_out,
+                           int H, int W) {
+    return conv_backward(dout, x, weight, dx, dweight, dbias, B, C_in, C_out, H, W, 3);
+}
+int ub_conv2d_k3_backward1(const float* dout, const float* x, const float* weight, float* dx, float* dweight,
+                           float* dbias, int B, int C_in, int C_out, int H, int W) {
+    return conv_backward(dout, x, weight, dx, dweight, dbias, B, C_in, C_out, H, W, 3);
+}
+int ub_conv2d_k1_forward2(const float* x, const float* weight, const float* bias, float* out, int B, int C_in, int H,
+                          int W, int C_out) {
+    return conv_forward(x, weight, bias, out, B, C_in, C_out, H, W, 1);
+}
+int ub_conv2d_k1_forward1(float* out, const float* x, const float* weight, const float* bias, int B, int C_in, int H,
+                          int W, int C_out) {
+    return conv_forward(x, weight, bias, out, B, C_in, C_out, H, W, 1);
+}
+int ub_conv2d_k1_backward1(const float* dout, const float* x, const float* weight, float* dx, float* dweight,
+                           float* dbias, int B, int C_in, int C_out, int H, int W) {
+    return conv_backward(dout, x, weight, dx, dweight, dbias, B, C_in, C_out, H, W, 1);
+}
+
+// ---- linear: out (N,OC) = inp (N,C) . W(OC,C)^T + b.  A (N,C) row-major matrix is an NHWC image with W = N.
+int ub_matmul_forward2(float* out, const float* inp, const float* weight, const float* bias, int N, int C, int OC) {
+    cudaStream_t st = ub_layer_stream();
+    if (N < 128 || !tensor_fprop_ok(C, OC)) {  // tiny / odd problems: exact fp32, latency bound anyway
+        f32::linear_fwd(out, inp, weight, bias, N, C, OC, st);
+        return finish(1);
+    }
+    std::lock_guard<std::mutex> lk(g_ws.mu);
+    bf16* xb = (bf16*)g_ws.get(0, size_t(N) * C * 2);
+    bf16* wp = (bf16*)g_ws.get(1, size_t(OC) * C * 2);
+    if (!xb || !wp) return UB_ERR_CUDA;
+    f32::cast_bf16(inp, size_t(N) * C, xb, st);
+    f32::cast_bf16(weight, size_t(OC) * C, wp, st);  // (OC, C) is already the K-major fprop pack of a 1-tap conv
+    ConvSegDesc seg{xb, C, C, wp, 1};
+    ConvEpilogue ep;
+    ep.bias = bias, ep.out = out, ep.out_mode = OUT_NHWC_F32;
+    IgemmConvParams p;
+    int r = igemm_conv_plan(&p, &seg, 1, 1, 1, N, OC, ep);
+    if (r) {
+        fail("matmul_forward2: igemm plan failed (%d)", r);
+        return UB_ERR_SHAPE;
+    }
+    igemm_conv_launch(p, st);
+    return finish(3);
+}
+int ub_matmul_backward1(float* dinp, float* dweight, float* dbias, const float* dout, const float* inp,
+                        const float* weight, int N, int C, int OC) {
+    cudaStream_t st = ub_layer_stream();
+    if (N < 128 || !tensor_fprop_ok(OC, C) || !tensor_wgrad_ok(C, OC)) {
+        f32::linear_bwd(dinp, dweight, dbias, dout, inp, weight, N, C, OC, st);
+        return finish(2);
+    }
+    std::lock_guard<std::mutex> lk(g_ws.mu);
+    bf16* dyb = (bf16*)g_ws.get(2, size_t(N) * OC * 2);
+    bf16* xb = (bf16*)g_ws.get(0, size_t(N) * C * 2);
+    bf16* wd = (bf16*)g_ws.get(1, size_t(OC) * C * 2);
+    const size_t cap = size_t(16) << 20;
+    float* partial = (float*)g_ws.get(3, cap * sizeof(float));
+    if (!dyb || !xb || !wd || !partial) return UB_ERR_CUDA;
+    f32::cast_bf16(dout, size_t(N) * OC, dyb, st);
+    f32::cast_bf16(inp, size_t(N) * C, xb, st);
+    int launches = 2;
+    if (dinp) {
+        if (pack_one(weight, nullptr, wd, OC, C, 1, st)) return UB_ERR_CUDA;
+        ConvSegDesc seg{dyb, OC, OC, wd, 1};
+        ConvEpilogue ep;
+        ep.out = dinp, ep.out_mode = OUT_NHWC_F32;
+        IgemmConvParams p;
+        int r = igemm_conv_plan(&p, &seg, 1, 1, 1, N, C, ep);
+        if (r) {
+            fail("matmul_backward1: dgrad plan failed (%d)", r);
+            return UB_ERR_SHAPE;
+        }
+        igemm_conv_launch(p, st);
+        launches += 2;
+    }
+    IgemmWgradParams p;
+    int r = igemm_wgrad_plan(&p, dyb, OC, xb, C, 1, 1, N, C, OC, 1, partial, cap, 148);
+    if (r) {
+        fail("matmul_backward1: wgrad plan failed (%d)", r);
+        return UB_ERR_SHAPE;
+    }
+    igemm_wgrad_launch(p, st);
+    igemm_wgrad_reduce(p, dweight, st);
+    if (dbias) f32::rows_colsum(dout, N, OC, dbias, st);
+    return finish(launches + 3);
+}
+
+// ---- memory-bound operators (exact fp32, reference layouts)
+int ub_groupnorm_forward(const float* x, const float* weight, const float* bias, float* out, float* mean,
+                         float* rstd, int B, int C, int H, int W, int n_groups) {
+    if (n_groups < 1 || C % n_groups) {
+        fail("groupnorm: C %% n_groups != 0");
+        return UB_ERR_SHAPE;
+    }
+    f32::groupnorm_fwd(x, weight, bias, out, mean, rstd, B, C, H * W, n_groups, ub_layer_stream());
+    return finish(1);
+}
+int ub_groupnorm_backward(const float* dout, const float* x, const float* mean, const float* rstd,
+                          const float* weight, float* dx, float* dweight, float* dbias, int B, int C, int H, int W,
+                          int n_groups) {
+    if (n_groups < 1 || C % n_groups) {
+        fail("groupnorm: C %% n_groups != 0");
+        return UB_ERR_SHAPE;
+    }
+    f32::groupnorm_bwd(dout, x, mean, rstd, weight, dx, dweight, dbias, B, C, H * W, n_groups, ub_layer_stream());
+    return finish(1);
+}
+int ub_silu_forward(const float* x, float* out, int N) {
+    f32::silu_fwd(x, out, size_t(N), ub_layer_stream());
+    return finish(1);
+}
+int ub_silu_backward(const float* dout, const float* x, float* dx, int N) {
+    f32::silu_bwd(dout, x, dx, size_t(N), ub_layer_stream());
+    return finish(1);
+}
+int ub_add_forward(const float* a, const float* b, float* out, int N) {
+    f32::add(a, b, out, size_t(N), ub_layer_stream());
+    return finish(1);
+}
+int ub_add_inplace_forward(const float* a, float* b, int N) {
+    f32::add(a, b, b, size_t(N), ub_layer_stream());
+    return finish(1);
+}
+int ub_upsample_forward1(float* out, const float* x, int B, int C, int H, int W) {
+    f32::upsample_fwd(out, x, size_t(B) * C, H, W, ub_layer_stream());
+    return finish(1);
+}
+int ub_upsample_backward1(float* dx, const float* dout, int B, int C, int H, int W) {
+    f32::upsample_bwd(dx, dout, size_t(B) * C, H, W, ub_layer_stream());
+    return finish(1);
+}
+int ub_avgpool_2d_forward1(float* out, const float* x, int B, int C, int H, int W) {
+    if ((H | W) & 1) {
+        fail("avgpool: H and W must be even");
+        return UB_ERR_SHAPE;
+    }
+    f32::avgpool_fwd(out, x, size_t(B) * C, H, W, ub_layer_stream());
+    return finish(1);
+}
+int ub_avgpool_2d_backward1(const float* dout, float* dx, int B, int C, int H, int W) {
+    if ((H | W) & 1) {
+        fail("avgpool: H and W must be even");
+        return UB_ERR_SHAPE;
+    }
+    f32::avgpool_bwd(dout, dx, size_t(B) * C, H, W, ub_layer_stream());
+    return finish(1);
+}
+int ub_concat_channel_forward(const float* x1, const float* x2, float* out, int B, int C1, int C2, int H, int W) {
+    f32::concat_fwd(x1, x2, out, B, C1, C2, H * W, ub_layer_stream());
+    return finish(1);
+}
+int ub_concat_channel_backward(const float* dout, float* dx1, float* dx2, int B, int C1, int C2, int H, int W) {
+    f32::concat_bwd(dout, dx1, dx2, B, C1, C2, H * W, ub_layer_stream());
+    return finish(1);
+}
+int ub_broadcast_last_dims_forward(const float* x, float* out, int N, int H, int W) {
+    f32::broadcast_fwd(x, out, size_t(N), H * W, ub_layer_stream());
+    return finish(1);
+}
+int ub_broadcast_last_dims_backward(const float* dout, float* dx, int N, int H, int W) {
+    f32::broadcast_bwd(dout, dx, size_t(N), H * W, ub_layer_stream());
+    return finish(1);
+}
+int ub_mse_forward(const float* inp, const float* y, float* loss, int N) {
+    f32::mse_fwd(inp, y, loss, size_t(N), ub_layer_stream());
+    return finish(1);
+}
+int ub_mse_backward(const float* inp, const float* y, float* dinp, int N) {
+    f32::mse_bwd(inp, y, dinp, size_t(N), ub_layer_stream());
+    return finish(1);
+}
+int ub_get_timestep_embeddings(const float* timesteps, float* out, int B, int dim, int max_period) {
+    if (dim & 1) {
+        fail("timestep embedding: dim must be even");
+        return UB_ERR_SHAPE;
+    }
+    timestep_embedding(timesteps, B, dim, max_period, out, ub_layer_stream());
+    return finish(1);
+}
+int ub_attention_forward1(float* out, float* qkvr, float* preatt, float* att, const float* inp, int B, int T, int C,
+                          int NH) {
+    if (NH < 1 || C % NH) {
+        fail("attention: C %% NH != 0");
+        return UB_ERR_SHAPE;
+    }
+    f32::attention_fwd(out, qkvr, preatt, att, inp, B, T, C, NH, ub_layer_stream());
+    return finish(3);
+}
+int ub_attention_backward(float* dinp, float* dqkvr, float* dpreatt, float* datt, float* /*scratch*/,
+                          const float* dout, const float* qkvr, const float* att, int B, int T, int C, int NH) {
+    if (NH < 1 || C % NH) {
+        fail("attention: C %% NH != 0");
+        return UB_ERR_SHAPE;
+    }
+    f32::attention_bwd(dinp, dqkvr, dpreatt, datt, dout, qkvr, att, B, T, C, NH, ub_layer_stream());
+    return finish(3);
+}
+
+}  // extern "C"

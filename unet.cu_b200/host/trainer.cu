@@ -151,7 +151,7 @@ struct UbTrainer {
     std::vector<cudaEvent_t> bucket_events;
     std::vector<size_t> bucket_bounds;  // param offsets, descending
     // emb bookkeeping
-    float *sin_emb = nullptr, *h0 = nullptr, *emb = nullptr, *d_embact = nullptr, *demb = nullptr,
+    float *sin_emb = nullptr, *h0 = nullptr, *emb = nullptr, *semb = nullptr, *d_embact = nullptr, *demb = nullptr,
           *d_h0act = nullptr, *dh0 = nullptr;
     std::string err;
 };
@@ -358,7 +358,7 @@ struct Builder {
         }
         if (real()) {
             SmallLinear e{};
-            e.w = P(wl), e.b = P(bl), e.inp = T->emb, e.out = embproj, e.C = Cemb, e.OC = Cout, e.silu_in = 1;
+            e.w = P(wl), e.b = P(bl), e.inp = T->semb, e.out = embproj, e.C = Cemb, e.OC = Cout, e.silu_in = 0;
             e.dout = d_embproj, e.dw = G(wl), e.db = G(bl), e.db2 = G(b1), e.dinp = T->d_embact;
             T->h_emb.push_back(e);
             if (Cout > T->emb_max_oc) T->emb_max_oc = Cout;
@@ -475,6 +475,7 @@ int Builder::build() {
     T->step_dev = (int*)T->arena.alloc(256);
     T->loss = zf32(64);
     T->sin_emb = f32(size_t(B) * Cm), T->h0 = f32(size_t(B) * Cemb), T->emb = f32(size_t(B) * Cemb);
+    T->semb = f32(size_t(B) * Cemb);
     T->d_embact = zf32(size_t(B) * Cemb), T->demb = f32(size_t(B) * Cemb);
     T->d_h0act = zf32(size_t(B) * Cemb), T->dh0 = f32(size_t(B) * Cemb);
     T->wg_partial = f32(T->wg_cap);
@@ -499,8 +500,9 @@ int Builder::build() {
             timestep_embedding(Tt->tsteps, Bn, Cm, mp, Tt->sin_emb, st);
             small_linear_fwd(Tt->temb_table, 1, Bn, Cemb, st);
             small_linear_fwd(Tt->temb_table + 1, 1, Bn, Cemb, st);
+            silu_f32(Tt->emb, Tt->semb, size_t(Bn) * Cemb, st);  // shared input of all embedding projections
             small_linear_fwd(Tt->emb_table, int(Tt->h_emb.size()), Bn, Tt->emb_max_oc, st);
-        }, 4);
+        }, 5);
     }
     const size_t time_mlp_end = poff;
 
