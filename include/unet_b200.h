@@ -128,6 +128,21 @@ int ub_attention_forward1(float* out, float* qkvr, float* preatt, float* att, co
 int ub_attention_backward(float* dinp, float* dqkvr, float* dpreatt, float* datt, float* scratch, const float* dout,
                           const float* qkvr, const float* att, int B, int T, int C, int NH);
 
+/* ---- native operand layout of the tensor-core path: NHWC bf16 activations, packed bf16 weights.  The reference has
+ * no equivalent; a caller that keeps its activations in this layout skips the NCHW fp32 <-> NHWC bf16 conversion the
+ * drop-in operators above have to do (this is what the trainer does internally).  ksize = 1 or 3.
+ *   wf : bf16 [ksize*ksize][C_out][C_in]  (fprop pack)      wd : bf16 [ksize*ksize][C_in][C_out] (dgrad pack, flipped)
+ * Needs C_in % 8 == 0 and C_out % 16 == 0 (wgrad: both % 64 == 0). */
+int ub_nchw_to_nhwc_bf16(const float* x, void* y_bf16, int B, int C, int H, int W);
+int ub_pack_conv_weight(const float* weight, void* wf_bf16, void* wd_bf16, int C_in, int C_out, int ksize);
+int ub_conv2d_nhwc_forward(const void* x_bf16, const void* wf_bf16, const float* bias, void* out_bf16, int B, int H,
+                           int W, int C_in, int C_out, int ksize);
+int ub_conv2d_nhwc_dgrad(const void* dout_bf16, const void* wd_bf16, void* dx_bf16, int B, int H, int W, int C_in,
+                         int C_out, int ksize);
+/* dweight (C_out,C_in,k,k) fp32 and dbias (C_out) fp32 are overwritten */
+int ub_conv2d_nhwc_wgrad(const void* dout_bf16, const void* x_bf16, float* dweight, float* dbias, int B, int H, int W,
+                         int C_in, int C_out, int ksize);
+
 /* ------------------------------------------------------------------------------------------------------------
  * (2) Trainer
  * ---------------------------------------------------------------------------------------------------------- */

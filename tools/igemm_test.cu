@@ -34,6 +34,9 @@ struct Rng {
 };
 
 static int g_fail = 0;
+#ifdef UB_HALO_TRACE
+namespace ub { void igemm_halo_set_trace(long long* dev_buf); }
+#endif
 
 // ------------------------------------------------------------------------------------------ conv test
 // x NHWC [B,H,W,Cin], w reference layout [Cout][Cin][ntaps]
@@ -52,7 +55,7 @@ static void cpu_conv_point(const std::vector<float>& x, const std::vector<float>
 }
 
 static bool test_conv(int B, int H, int W, int Cin, int Cout, int ntaps, int Cin2, int out_mode, bool use_bias,
-                      bool use_rowvec, bool use_res, int nsample, int reps) {
+                      bool use_rowvec, bool use_res, int nsample, int reps, bool halo = false) {
     Rng rng(1234 + Cin + Cout + H);
     size_t npix = size_t(B) * H * W;
     std::vector<float> x(npix * Cin), w(size_t(Cout) * Cin * ntaps), x2, w2, bias(Cout), rowvec(size_t(B) * Cout),
@@ -112,13 +115,16 @@ static bool test_conv(int B, int H, int W, int Cin, int Cout, int ntaps, int Cin
     ep.out = dout;
     ep.out_mode = out_mode;
     IgemmConvParams p;
-    int r = igemm_conv_plan(&p, segs, Cin2 ? 2 : 1, B, H, W, Cout, ep);
+    IgemmHaloParams ph;
+    int r = halo ? igemm_halo_plan(&ph, segs, Cin2 ? 2 : 1, B, H, W, Cout, ep, 148)
+                 : igemm_conv_plan(&p, segs, Cin2 ? 2 : 1, B, H, W, Cout, ep);
     if (r) {
         printf("conv plan failed %d\n", r);
         g_fail++;
         return false;
     }
-    r = igemm_conv_launch(p, 0);
+    auto launch = [&]() { return halo ? igemm_halo_launch(ph, 0) : igemm_conv_launch(p, 0); };
+    r = launch();
     cudaError_t e = cudaDeviceSynchronize();
     if (r || e != cudaSuccess) {
         printf("conv launch failed r=%d e=%s\n", r, cudaGetErrorString(e));
@@ -167,18 +173,19 @@ static bool test_conv(int B, int H, int W, int Cin, int Cout, int ntaps, int Cin
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
-        for (int i = 0; i < 3; ++i) igemm_conv_launch(p, 0);
+        for (int i = 0; i < 3; ++i) launch();
         cudaEventRecord(e0);
-        for (int i = 0; i < reps; ++i) igemm_conv_launch(p, 0);
+        for (int i = 0; i < reps; ++i) launch();
         cudaEventRecord(e1);
         CK(cudaEventSynchronize(e1));
         cudaEventElapsedTime(&ms, e0, e1);
         ms /= reps;
     }
     double flops = 2.0 * npix * Cout * (double(ntaps) * Cin + Cin2);
-    printf("conv B%d %dx%d %d->%d taps%d seg2=%d mode%d b%d r%d s%d | BN=%d stages=%d | checked %zu bad %d max_err %.3g "
+    printf("%s B%d %dx%d %d->%d taps%d seg2=%d mode%d b%d r%d s%d | BN=%d stages=%d | checked %zu bad %d max_err %.3g "
            "(max_ref %.3g) | %.4f ms %.1f TFLOP/s  %s\n",
-           B, H, W, Cin, Cout, ntaps, Cin2, out_mode, use_bias, use_rowvec, use_res, p.BN, p.stages, ncheck, bad,
+           halo ? "HALO" : "conv", B, H, W, Cin, Cout, ntaps, Cin2, out_mode, use_bias, use_rowvec, use_res,
+           halo ? ph.BN : p.BN, halo ? ph.w_stages : p.stages, ncheck, bad,
            max_err, max_ref, ms, ms > 0 ? flops / ms * 1e-9 : 0.0, bad ? "FAIL" : "ok");
     if (bad) g_fail++;
     cudaFree(dx), cudaFree(dw), cudaFree(dres), cudaFree(dbias), cudaFree(drow), cudaFree(dout);
@@ -430,6 +437,39 @@ static void run_probe() {
 
 int main(int argc, char** argv) {
     bool quick = argc > 1 && !strcmp(argv[1], "quick");
+    if (argc > 8 && !strcmp(argv[1], "shape")) {  // shape B H W Cin Cout halo reps  (single case, for ncu)
+        int B = atoi(argv[2]), H = atoi(argv[3]), W = atoi(argv[4]), Cin = atoi(argv[5]), Cout = atoi(argv[6]);
+        test_conv(B, H, W, Cin, Cout, 9, 0, OUT_NHWC_BF16, true, true, false, 2000, atoi(argv[8]), atoi(argv[7]) != 0);
+        return g_fail ? 1 : 0;
+    }
+#ifdef UB_HALO_TRACE
+    if (argc > 6 && !strcmp(argv[1], "trace")) {  // trace B H W Cin Cout : clock stamps of the halo kernel
+        long long* d;
+        CK(cudaMalloc(&d, 148 * 8 * 8 * 8));
+        CK(cudaMemset(d, 0, 148 * 8 * 8 * 8));
+        test_conv(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), 9, 0, OUT_NHWC_BF16, true,
+                  true, false, 100, 3, true);  // warm
+        igemm_halo_set_trace(d);
+        test_conv(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), 9, 0, OUT_NHWC_BF16, true,
+                  true, false, 100, 0, true);
+        std::vector<long long> h(148 * 64);
+        CK(cudaMemcpy(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost));
+        for (int cta : {0, 77}) {
+            long long t0 = h[size_t(cta) * 64];
+            printf("CTA %d (cycles since its first stamp): tile | A-prod start | mma start (tmem free) | A landed | last commit | epi wait | acc ready | epi done\n", cta);
+            for (int it = 0; it < 5; ++it) {
+                printf("  %d |", it);
+                for (int s = 0; s < 7; ++s) printf(" %8lld", h[(size_t(cta) * 8 + it) * 8 + s] ? h[(size_t(cta) * 8 + it) * 8 + s] - t0 : -1);
+                printf("\n");
+            }
+        }
+        return 0;
+    }
+#endif
+    if (argc > 7 && !strcmp(argv[1], "wgrad")) {  // wgrad B H W Cin Cout reps
+        test_wgrad(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), 9, 200, atoi(argv[7]));
+        return g_fail ? 1 : 0;
+    }
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
     printf("device: %s, %d SMs, cc %d.%d\n", prop.name, prop.multiProcessorCount, prop.major, prop.minor);
@@ -459,6 +499,26 @@ int main(int argc, char** argv) {
         test_conv(32, 16, 16, 192, 576, 1, 0, OUT_NHWC_BF16, true, false, false, 20000, reps);
         test_conv(32, 64, 64, 256, 256, 9, 0, OUT_NHWC_BF16, true, false, false, 20000, reps);
         test_conv(32, 64, 64, 512, 512, 9, 0, OUT_NHWC_BF16, true, false, false, 5000, 5);
+    }
+    printf("== halo-reuse persistent conv ==\n");
+    test_conv(1, 32, 32, 64, 64, 9, 0, OUT_NHWC_F32, false, false, false, 1 << 20, 0, true);
+    test_conv(2, 32, 32, 64, 64, 9, 0, OUT_NHWC_F32, true, false, false, 1 << 20, 0, true);
+    test_conv(2, 64, 64, 128, 64, 9, 0, OUT_NHWC_BF16, true, true, true, 1 << 20, 0, true);
+    test_conv(3, 32, 32, 64, 128, 1, 0, OUT_NCHW_F32, true, false, false, 1 << 20, 0, true);
+    test_conv(2, 32, 32, 64, 192, 9, 128, OUT_NHWC_BF16, true, true, false, 1 << 20, 0, true);
+    test_conv(1, 40, 36, 72, 48, 9, 0, OUT_NHWC_F32, true, false, false, 1 << 20, 0, true);
+    test_conv(1, 128, 128, 64, 64, 9, 0, OUT_NHWC_BF16, true, false, false, 200000, 0, true);
+    if (!quick) {
+        int reps = 20;
+        test_conv(32, 64, 64, 64, 64, 9, 0, OUT_NHWC_BF16, true, true, false, 20000, reps, true);
+        test_conv(32, 64, 64, 128, 64, 9, 0, OUT_NHWC_BF16, true, true, false, 20000, reps, true);
+        test_conv(32, 64, 64, 192, 64, 9, 0, OUT_NHWC_BF16, true, false, false, 20000, reps, true);
+        test_conv(32, 64, 64, 64, 64, 9, 64, OUT_NHWC_BF16, true, true, false, 20000, reps, true);
+        test_conv(32, 32, 32, 128, 128, 9, 0, OUT_NHWC_BF16, true, true, false, 20000, reps, true);
+        test_conv(32, 32, 32, 320, 128, 9, 320, OUT_NHWC_BF16, true, true, false, 20000, reps, true);
+        test_conv(32, 32, 32, 64, 128, 9, 64, OUT_NHWC_BF16, true, true, false, 20000, reps, true);
+        test_conv(32, 64, 64, 256, 256, 9, 0, OUT_NHWC_BF16, true, false, false, 20000, reps, true);
+        test_conv(32, 64, 64, 512, 512, 9, 0, OUT_NHWC_BF16, true, false, false, 5000, 5, true);
     }
     printf("== wgrad ==\n");
     test_wgrad(2, 8, 8, 64, 64, 9, 1 << 20, 0);

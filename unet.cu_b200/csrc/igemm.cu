@@ -8,6 +8,7 @@
 //
 // Reference behaviour being replaced (not its structure): /root/reference/dev/conv2d_k3.cu:679-740 (forward3),
 // :1132-1174 (dx_backward), :2468-2547 (dweight_dbias_backward1), :1365-1393 (dweight_reduce_kernel).
+#include "epilogue.cuh"
 #include "igemm.cuh"
 #include "ptx.cuh"
 
@@ -29,6 +30,8 @@ __global__ void __launch_bounds__(kConvThreads) igemm_conv_kernel(const __grid_c
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tmem_full_bar = empty_bar + kMaxStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    // [ncomb][BN] staged per-channel addend (one row per image of the tile), 16-byte aligned behind the barriers
+    float* comb = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -126,78 +129,20 @@ __global__ void __launch_bounds__(kConvThreads) igemm_conv_kernel(const __grid_c
         const int lb = row / (p.TW * p.TH);
         const int w = w0 + lw, h = h0 + lh, b = b0 + lb;
         const bool valid = (lb < p.TB) && (w < p.W) && (h < p.H) && (b < p.B);
+        // stage bias + bias2 + embedding vector while the main loop runs: one row per image of the tile when the
+        // embedding vector is used (p.ncomb == TB), a single shared row otherwise
+        const int et = threadIdx.x - 64;
+        for (int i = 0; i < p.ncomb; ++i)
+            epi_stage_comb(comb + i * p.BN, p.bias, p.bias2, p.rowvec, min(b0 + i, p.B - 1), p.Cout, n0, p.BN, et, 128);
+        named_bar_sync(1, 128);
 
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
 
         const size_t pix = (size_t(b) * p.H + h) * p.W + w;
-        for (int c0 = 0; c0 < p.BN; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c0), v);
-            tmem_ld_wait();
-            if (!valid) continue;
-            float f[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-            const int n = n0 + c0;
-            if (p.bias) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    const float4 bv = *reinterpret_cast<const float4*>(p.bias + n + j);
-                    f[j] += bv.x, f[j + 1] += bv.y, f[j + 2] += bv.z, f[j + 3] += bv.w;
-                }
-            }
-            if (p.bias2) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    const float4 bv = *reinterpret_cast<const float4*>(p.bias2 + n + j);
-                    f[j] += bv.x, f[j + 1] += bv.y, f[j + 2] += bv.z, f[j + 3] += bv.w;
-                }
-            }
-            if (p.rowvec) {
-                const float* rv = p.rowvec + size_t(b) * p.Cout + n;
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    const float4 bv = *reinterpret_cast<const float4*>(rv + j);
-                    f[j] += bv.x, f[j + 1] += bv.y, f[j + 2] += bv.z, f[j + 3] += bv.w;
-                }
-            }
-            if (p.residual) {
-                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.ldr + n);
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const uint4 r = rp[j];
-                    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
-                        f[j * 8 + i * 2] += __bfloat162float(h2.x);
-                        f[j * 8 + i * 2 + 1] += __bfloat162float(h2.y);
-                    }
-                }
-            }
-            if (p.out_mode == OUT_NHWC_BF16) {
-                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + n;
-                uint32_t pk[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                    pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
-                }
-                reinterpret_cast<uint4*>(op)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                reinterpret_cast<uint4*>(op)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            } else if (p.out_mode == OUT_NHWC_F32) {
-                float* op = reinterpret_cast<float*>(p.out) + pix * p.ldo + n;
-#pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            } else {  // OUT_NCHW_F32: a warp writes 32 consecutive pixels of one channel -> coalesced
-                float* op = reinterpret_cast<float*>(p.out) + ((size_t(b) * p.Cout + n) * p.H + h) * p.W + w;
-                const size_t cs = size_t(p.H) * p.W;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) op[j * cs] = f[j];
-            }
-        }
+        const EpiOut eo{p.residual, p.ldr, p.out, p.ldo, p.out_mode, p.Cout, p.H, p.W};
+        epi_row(eo, tmem_base + (uint32_t(q * 32) << 16), comb + (p.ncomb > 1 ? min(lb, p.ncomb - 1) : 0) * p.BN, p.BN,
+                valid, pix, b, h, w, n0);
     }
 
     tc_fence_before();
@@ -396,6 +341,8 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+EncodeTiledFn igemm_encode_fn() { return get_encode_fn(); }
+
 // NHWC bf16 activation map: dims (C, W, H, B), channel pitch ld, box (64, TW, TH, TB), 128B swizzle, zero OOB fill.
 static int make_act_map(CUtensorMap* m, const __nv_bfloat16* x, int C, int ld, int W, int H, int B, int TW, int TH,
                         int TB) {
@@ -450,12 +397,23 @@ int igemm_conv_plan(IgemmConvParams* p, const ConvSegDesc* segs, int nseg, int B
     memset(p, 0, sizeof(*p));
     if (nseg < 1 || nseg > 2) return -1;
     if (Cout % 16 != 0) return -2;
-    // output-channel tile: the largest divisor of Cout that is a multiple of 16 and <= 256
+    // pixel tile first (needed to count CTAs)
+    const int TW0 = W < 128 ? W : 128;
+    int TH0 = H < 128 / TW0 ? H : 128 / TW0;
+    if (TH0 < 1) TH0 = 1;
+    int TB0 = B < 128 / (TW0 * TH0) ? B : 128 / (TW0 * TH0);
+    if (TB0 < 1) TB0 = 1;
+    const int pix_tiles = ceil_div_i(W, TW0) * ceil_div_i(H, TH0) * ceil_div_i(B, TB0);
+    // output-channel tile: the largest divisor of Cout that is a multiple of 16 and <= 256 -- but small problems
+    // (8x8 / 16x16 layers) would then run on a handful of SMs, each limited by its own L2->SMEM bandwidth, so BN is
+    // lowered (not below 64) until there are ~128 CTAs.
     int BN = 0;
     for (int cand = 256; cand >= 16; cand -= 16)
         if (Cout % cand == 0) {
+            if (!BN) BN = cand;
+            if (cand < 64) break;
             BN = cand;
-            break;
+            if (pix_tiles * (Cout / cand) >= 128) break;
         }
     if (!BN) return -2;
     p->nseg = nseg;
@@ -497,6 +455,8 @@ int igemm_conv_plan(IgemmConvParams* p, const ConvSegDesc* segs, int nseg, int B
     p->out = ep.out;
     p->ldo = ep.ldo ? ep.ldo : Cout;
     p->out_mode = ep.out_mode;
+    p->ncomb = p->rowvec ? p->TB : 1;
+    if (size_t(p->ncomb) * BN * sizeof(float) > 16384) return -9;  // staged addend rows must fit the smem tail
     if (p->out_mode != OUT_NCHW_F32) {
         const int esz = p->out_mode == OUT_NHWC_BF16 ? 2 : 4;
         if ((p->ldo * esz) % 16 != 0 || (reinterpret_cast<uintptr_t>(p->out) & 15)) return -6;
@@ -518,7 +478,7 @@ void igemm_init() {
 
 int igemm_conv_launch(const IgemmConvParams& p, cudaStream_t st) {
     igemm_init();
-    const size_t smem = size_t(p.stages) * p.stage_bytes + 1024 + kBarrierBytes;
+    const size_t smem = size_t(p.stages) * p.stage_bytes + 1024 + kBarrierBytes + size_t(p.ncomb) * p.BN * sizeof(float);
     dim3 grid(p.tiles_w * p.tiles_h * p.tiles_b, p.Cout / p.BN);
     igemm_conv_kernel<<<grid, kConvThreads, smem, st>>>(p);
     return int(cudaGetLastError());

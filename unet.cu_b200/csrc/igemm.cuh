@@ -36,6 +36,7 @@ struct IgemmConvParams {
     int BN;          // output-channel tile: multiple of 16, <= 256
     int stages;
     int tmem_cols;   // power of two >= max(32, BN)
+    int ncomb;       // rows of the staged per-channel addend (TB when a per-image vector is fused, else 1)
     uint32_t a_bytes, b_bytes;  // TMA transaction bytes per stage
     uint32_t stage_bytes;       // smem bytes per stage (A tile 16 KiB + B tile, 1024-aligned)
     // epilogue
@@ -46,6 +47,28 @@ struct IgemmConvParams {
     int ldr;
     void* out;
     int ldo;  // channel pitch of an NHWC output (>= Cout; lets a producer write into a concat buffer)
+    int out_mode;
+};
+
+// persistent halo-reuse variant (igemm_halo.cu); same segments / epilogue as IgemmConvParams
+struct IgemmHaloParams {
+    IgemmSeg seg[2];  // tmA box = (64, Wp, NR, 1), tmW box = (64, BN)
+    int nseg;
+    int B, H, W, Cout;
+    int Wp, NR;         // padded row pitch (W + 2) and rows per halo box
+    int tiles_per_img;  // ceil(H * Wp / 256)
+    int num_tiles;      // B * tiles_per_img * (Cout / BN)
+    int BN;             // <= 128
+    int w_stages;
+    int grid;
+    uint32_t a_bytes, a_stage_bytes, w_bytes, w_stage_bytes;
+    const float* bias;
+    const float* bias2;
+    const float* rowvec;
+    const __nv_bfloat16* residual;
+    int ldr;
+    void* out;
+    int ldo;
     int out_mode;
 };
 
@@ -89,6 +112,12 @@ void igemm_init();
 int igemm_conv_plan(IgemmConvParams* p, const ConvSegDesc* segs, int nseg, int B, int H, int W, int Cout,
                     const ConvEpilogue& ep);
 int igemm_conv_launch(const IgemmConvParams& p, cudaStream_t st);
+
+bool igemm_halo_eligible(int B, int H, int W, int Cout);
+int igemm_halo_plan(IgemmHaloParams* p, const ConvSegDesc* segs, int nseg, int B, int H, int W, int Cout,
+                    const ConvEpilogue& ep, int sm_count);
+int igemm_halo_launch(const IgemmHaloParams& p, cudaStream_t st);
+void igemm_halo_init();
 
 int igemm_wgrad_plan(IgemmWgradParams* p, const __nv_bfloat16* dy, int ldy, const __nv_bfloat16* x, int ldx, int B,
                      int H, int W, int Cin, int Cout, int ntaps, float* partial, size_t partial_cap_floats,

@@ -37,11 +37,32 @@ __device__ __forceinline__ void st8(bf16* p, const float (&f)[8]) {
     }
     *reinterpret_cast<uint4*>(p) = make_uint4(u[0], u[1], u[2], u[3]);
 }
-__device__ __forceinline__ float silu_f(float z) { return z / (1.f + __expf(-z)); }
+// sigmoid through one MUFU op: sigma(z) = 0.5 * (1 + tanh(z / 2))  (tanh.approx.f32, rel. error ~2^-11: far below
+// the bf16 rounding of the stored result; the IEEE divide of z / (1 + exp(-z)) costs ~10 instructions more)
+__device__ __forceinline__ float sigmoid_f(float z) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
+    return fmaf(0.5f, t, 0.5f);
+}
+__device__ __forceinline__ float silu_f(float z) { return z * sigmoid_f(z); }
 // d silu(z) / dz
 __device__ __forceinline__ float dsilu_f(float z) {
-    const float s = 1.f / (1.f + __expf(-z));
-    return s * (1.f + z * (1.f - s));
+    const float s = sigmoid_f(z);
+    return s * fmaf(z, 1.f - s, 1.f);
+}
+
+// Sum per-thread partials over the `rows` threads that own the same channel octet, without shared-memory atomics:
+// every thread stores its 8 values into scratch[r][C], then thread c adds the `rows` entries of column c.
+// (ATOMS on 8 addresses shared by 32 threads serialises for microseconds per block.)
+__device__ __forceinline__ void store_partials(float* scratch, int C, int r, int j, const float (&v)[8]) {
+    float4* d = reinterpret_cast<float4*>(scratch + size_t(r) * C + j * 8);
+    d[0] = make_float4(v[0], v[1], v[2], v[3]);
+    d[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ float column_total(const float* scratch, int C, int rows, int c) {
+    float t = 0.f;
+    for (int r = 0; r < rows; ++r) t += scratch[size_t(r) * C + c];
+    return t;
 }
 
 // Thread layout shared by the per-image kernels: blockDim = C8 * rows, thread -> (octet j, row r);
@@ -56,7 +77,7 @@ static RowMap make_rowmap(int B, int HW, int C) {
     if (m.rows < 1) m.rows = 1;
     if (m.rows > HW) m.rows = HW;
     m.threads = m.C8 * m.rows;
-    int want = (4 * kSMs + B - 1) / B;  // chunks per image for ~4 waves
+    int want = (3 * kSMs + B - 1) / B;  // chunks per image: ~3 blocks per SM, each with a long pixel loop
     int maxc = (HW + m.rows - 1) / m.rows;
     m.nchunks = want < maxc ? want : maxc;
     if (m.nchunks < 1) m.nchunks = 1;
@@ -68,11 +89,9 @@ static RowMap make_rowmap(int B, int HW, int C) {
 // ------------------------------------------------------------------------------------------------ GN stats
 __global__ void gn_stats_kernel(const bf16* __restrict__ x, int ldx, int HW, int C, int C8, int rows, int ppb,
                                 float* __restrict__ chsum) {
-    extern __shared__ float sm[];  // [2][C]
+    extern __shared__ float sm[];  // [2][rows][C]
     const int b = blockIdx.y;
     const int j = threadIdx.x % C8, r = threadIdx.x / C8;
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-    __syncthreads();
     float s[8], ss[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
@@ -94,21 +113,18 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, int ldx, int HW, int
             for (int i = 0; i < 8; ++i) s[i] += f[i], ss[i] += f[i] * f[i];
         }
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        atomicAdd(&sm[j * 8 + i], s[i]);
-        atomicAdd(&sm[C + j * 8 + i], ss[i]);
-    }
+    store_partials(sm, C, r, j, s);
+    store_partials(sm + size_t(rows) * C, C, r, j, ss);
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        atomicAdd(&chsum[(size_t(b) * C + c) * 2], sm[c]);
-        atomicAdd(&chsum[(size_t(b) * C + c) * 2 + 1], sm[C + c]);
+        atomicAdd(&chsum[(size_t(b) * C + c) * 2], column_total(sm, C, rows, c));
+        atomicAdd(&chsum[(size_t(b) * C + c) * 2 + 1], column_total(sm + size_t(rows) * C, C, rows, c));
     }
 }
 
 void gn_stats(const bf16* x, int ldx, int B, int HW, int C, float* chsum, cudaStream_t st) {
     RowMap m = make_rowmap(B, HW, C);
-    gn_stats_kernel<<<dim3(m.nchunks, B), m.threads, 2 * C * sizeof(float), st>>>(x, ldx, HW, C, m.C8, m.rows, m.ppb,
+    gn_stats_kernel<<<dim3(m.nchunks, B), m.threads, 2 * size_t(m.rows) * C * sizeof(float), st>>>(x, ldx, HW, C, m.C8, m.rows, m.ppb,
                                                                                    chsum);
 }
 
@@ -194,14 +210,14 @@ __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ x, int ldx, const b
                                     const float* __restrict__ chsum, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, int HW, int C, int G, int silu, int C8, int rows,
                                     int ppb, float* __restrict__ S) {
-    extern __shared__ float sm[];  // sa, sb, sr, smr, acc1, acc2  : 6*C
-    float *sa = sm, *sb = sm + C, *sr = sm + 2 * C, *smr = sm + 3 * C, *acc1 = sm + 4 * C, *acc2 = sm + 5 * C;
+    extern __shared__ float sm[];  // sa, sb, sr, smr : 4*C ; then scratch [2][rows][C]
+    float *sa = sm, *sb = sm + C, *sr = sm + 2 * C, *smr = sm + 3 * C, *scr = sm + 4 * C;
     const int b = blockIdx.y;
     const int cpg = C / G;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float r, mr, a, bb;
         gn_channel_consts(chsum + size_t(b) * C * 2, gamma, beta, C, cpg, HW, c, r, mr, a, bb);
-        sa[c] = a, sb[c] = bb, sr[c] = r, smr[c] = mr, acc1[c] = 0.f, acc2[c] = 0.f;
+        sa[c] = a, sb[c] = bb, sr[c] = r, smr[c] = mr;
     }
     __syncthreads();
     const int j = threadIdx.x % C8, r = threadIdx.x / C8;
@@ -239,22 +255,19 @@ __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ x, int ldx, const b
             }
         }
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        atomicAdd(&acc1[j * 8 + i], s1[i]);
-        atomicAdd(&acc2[j * 8 + i], s2[i]);
-    }
+    store_partials(scr, C, r, j, s1);
+    store_partials(scr + size_t(rows) * C, C, r, j, s2);
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        atomicAdd(&S[(size_t(b) * C + c) * 2], acc1[c]);
-        atomicAdd(&S[(size_t(b) * C + c) * 2 + 1], acc2[c]);
+        atomicAdd(&S[(size_t(b) * C + c) * 2], column_total(scr, C, rows, c));
+        atomicAdd(&S[(size_t(b) * C + c) * 2 + 1], column_total(scr + size_t(rows) * C, C, rows, c));
     }
 }
 
 void gn_bwd_stats(const bf16* x, int ldx, const bf16* dy, int lddy, const float* chsum, const float* gamma,
                   const float* beta, int B, int HW, int C, int G, int silu, float* S, cudaStream_t st) {
     RowMap m = make_rowmap(B, HW, C);
-    gn_bwd_stats_kernel<<<dim3(m.nchunks, B), m.threads, 6 * C * sizeof(float), st>>>(
+    gn_bwd_stats_kernel<<<dim3(m.nchunks, B), m.threads, (4 + 2 * size_t(m.rows)) * C * sizeof(float), st>>>(
         x, ldx, dy, lddy, chsum, gamma, beta, HW, C, G, silu, m.C8, m.rows, m.ppb, S);
 }
 
@@ -264,9 +277,9 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ x, int ldx, const b
                                     int G, int silu, int C8, int rows, int ppb, const bf16* __restrict__ add_in,
                                     int ldadd, bf16* __restrict__ dx, int lddx, float* __restrict__ dgamma,
                                     float* __restrict__ dbeta, float* __restrict__ colsum_out) {
-    extern __shared__ float sm[];  // sa, sb, sr, smr, sgr, sm1, sm2, acc : 8*C
-    float *sa = sm, *sb = sm + C, *sr = sm + 2 * C, *smr = sm + 3 * C, *sgr = sm + 4 * C, *sm1 = sm + 5 * C,
-          *sm2 = sm + 6 * C, *acc = sm + 7 * C;
+    extern __shared__ float sm[];  // sa, sb, sr, smr, sm1, sm2 : 6*C ; then scratch [rows][C]
+    float *sa = sm, *sb = sm + C, *sr = sm + 2 * C, *smr = sm + 3 * C, *sm1 = sm + 4 * C, *sm2 = sm + 5 * C,
+          *scr = sm + 6 * C;
     const int b = blockIdx.y;
     const int cpg = C / G;
     const float* Sb = S + size_t(b) * C * 2;
@@ -280,9 +293,8 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ x, int ldx, const b
             m2 += gamma[g0 + k] * Sb[(g0 + k) * 2 + 1];
         }
         const float n = float(cpg) * float(HW);
-        sa[c] = a, sb[c] = bb, sr[c] = r, smr[c] = mr, sgr[c] = a;  // a == gamma * rstd
+        sa[c] = a, sb[c] = bb, sr[c] = r, smr[c] = mr;  // a == gamma * rstd
         sm1[c] = r * m1 / n, sm2[c] = r * m2 / n;
-        acc[c] = 0.f;
         if (blockIdx.x == 0) {
             atomicAdd(&dgamma[c], Sb[c * 2 + 1]);
             atomicAdd(&dbeta[c], Sb[c * 2]);
@@ -332,10 +344,10 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ x, int ldx, const b
         }
     }
     if (colsum_out) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) atomicAdd(&acc[j * 8 + i], cs[i]);
+        store_partials(scr, C, r, j, cs);
         __syncthreads();
-        for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&colsum_out[size_t(b) * C + c], acc[c]);
+        for (int c = threadIdx.x; c < C; c += blockDim.x)
+            atomicAdd(&colsum_out[size_t(b) * C + c], column_total(scr, C, rows, c));
     }
 }
 
@@ -343,7 +355,7 @@ void gn_bwd_apply(const bf16* x, int ldx, const bf16* dy, int lddy, const float*
                   const float* gamma, const float* beta, int B, int HW, int C, int G, int silu, const bf16* add_in,
                   int ldadd, bf16* dx, int lddx, float* dgamma, float* dbeta, float* colsum_out, cudaStream_t st) {
     RowMap m = make_rowmap(B, HW, C);
-    gn_bwd_apply_kernel<<<dim3(m.nchunks, B), m.threads, 8 * C * sizeof(float), st>>>(
+    gn_bwd_apply_kernel<<<dim3(m.nchunks, B), m.threads, (6 + size_t(m.rows)) * C * sizeof(float), st>>>(
         x, ldx, dy, lddy, chsum, S, gamma, beta, HW, C, G, silu, m.C8, m.rows, m.ppb, add_in, ldadd, dx, lddx, dgamma,
         dbeta, colsum_out);
 }
@@ -481,27 +493,34 @@ void add2(const bf16* a, int lda, const bf16* b, int ldb, size_t npix, int C, bf
 
 __global__ void colsum_kernel(const bf16* __restrict__ x, int ldx, size_t npix, int C, int C8, int rows, size_t ppb,
                               float* __restrict__ out, float* __restrict__ out2) {
-    extern __shared__ float sm[];  // [C]
-    for (int c = threadIdx.x; c < C; c += blockDim.x) sm[c] = 0.f;
-    __syncthreads();
+    extern __shared__ float sm[];  // [rows][C]
     const int j = threadIdx.x % C8, r = threadIdx.x / C8;
     float s[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = 0.f;
     const size_t p0 = size_t(blockIdx.x) * ppb;
     const size_t p1 = p0 + ppb < npix ? p0 + ppb : npix;
-    for (size_t p = p0 + r; p < p1; p += rows) {
-        float f[8];
-        ld8(x + p * ldx + j * 8, f);
+    for (size_t p = p0 + r; p < p1; p += size_t(4) * rows) {
+        uint4 v[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s[i] += f[i];
+        for (int u = 0; u < 4; ++u) {
+            const size_t pp = p + size_t(u) * rows;
+            v[u] = pp < p1 ? *reinterpret_cast<const uint4*>(x + pp * ldx + j * 8) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float f[8];
+            unpack8(v[u], f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s[i] += f[i];
+        }
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(&sm[j * 8 + i], s[i]);
+    store_partials(sm, C, r, j, s);
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        atomicAdd(&out[c], sm[c]);
-        if (out2) atomicAdd(&out2[c], sm[c]);
+        const float t = column_total(sm, C, rows, c);
+        atomicAdd(&out[c], t);
+        if (out2) atomicAdd(&out2[c], t);
     }
 }
 void colsum(const bf16* x, int ldx, size_t npix, int C, float* out, float* out2, cudaStream_t st) {
@@ -512,7 +531,7 @@ void colsum(const bf16* x, int ldx, size_t npix, int C, float* out, float* out2,
     if (nblk > size_t(2 * kSMs)) nblk = 2 * kSMs;
     const size_t ppb = (npix + nblk - 1) / nblk;
     nblk = (npix + ppb - 1) / ppb;
-    colsum_kernel<<<unsigned(nblk), C8 * rows, C * sizeof(float), st>>>(x, ldx, npix, C, C8, rows, ppb, out, out2);
+    colsum_kernel<<<unsigned(nblk), C8 * rows, size_t(rows) * C * sizeof(float), st>>>(x, ldx, npix, C, C8, rows, ppb, out, out2);
 }
 
 // ------------------------------------------------------------------------------------------------ 3-channel convs

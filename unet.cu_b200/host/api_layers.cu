@@ -386,4 +386,79 @@ int ub_attention_backward(float* dinp, float* dqkvr, float* dpreatt, float* datt
     return finish(3);
 }
 
+// ---- native-layout entry points (NHWC bf16)
+int ub_nchw_to_nhwc_bf16(const float* x, void* y, int B, int C, int H, int W) {
+    f32::nchw_to_nhwc_bf16(x, B, C, H * W, (bf16*)y, ub_layer_stream());
+    return finish(1);
+}
+int ub_pack_conv_weight(const float* weight, void* wf, void* wd, int C_in, int C_out, int ksize) {
+    std::lock_guard<std::mutex> lk(g_ws.mu);
+    if (pack_one(weight, (bf16*)wf, (bf16*)wd, C_out, C_in, ksize * ksize, ub_layer_stream())) return UB_ERR_CUDA;
+    return finish(1);
+}
+int ub_conv2d_nhwc_forward(const void* x, const void* wf, const float* bias, void* out, int B, int H, int W, int C_in,
+                           int C_out, int ksize) {
+    if (!tensor_fprop_ok(C_in, C_out)) {
+        fail("conv2d_nhwc_forward needs C_in %% 8 == 0 and C_out %% 16 == 0");
+        return UB_ERR_SHAPE;
+    }
+    ConvSegDesc seg{(const bf16*)x, C_in, C_in, (const bf16*)wf, ksize * ksize};
+    ConvEpilogue ep;
+    ep.bias = bias, ep.out = out, ep.out_mode = OUT_NHWC_BF16;
+    IgemmConvParams p;
+    int r = igemm_conv_plan(&p, &seg, 1, B, H, W, C_out, ep);
+    if (r) {
+        fail("conv2d_nhwc_forward: plan failed (%d)", r);
+        return UB_ERR_SHAPE;
+    }
+    igemm_conv_launch(p, ub_layer_stream());
+    return finish(1);
+}
+int ub_conv2d_nhwc_dgrad(const void* dout, const void* wd, void* dx, int B, int H, int W, int C_in, int C_out,
+                         int ksize) {
+    if (!tensor_fprop_ok(C_out, C_in)) {
+        fail("conv2d_nhwc_dgrad needs C_out %% 8 == 0 and C_in %% 16 == 0");
+        return UB_ERR_SHAPE;
+    }
+    ConvSegDesc seg{(const bf16*)dout, C_out, C_out, (const bf16*)wd, ksize * ksize};
+    ConvEpilogue ep;
+    ep.out = dx, ep.out_mode = OUT_NHWC_BF16;
+    IgemmConvParams p;
+    int r = igemm_conv_plan(&p, &seg, 1, B, H, W, C_in, ep);
+    if (r) {
+        fail("conv2d_nhwc_dgrad: plan failed (%d)", r);
+        return UB_ERR_SHAPE;
+    }
+    igemm_conv_launch(p, ub_layer_stream());
+    return finish(1);
+}
+int ub_conv2d_nhwc_wgrad(const void* dout, const void* x, float* dweight, float* dbias, int B, int H, int W, int C_in,
+                         int C_out, int ksize) {
+    if (!tensor_wgrad_ok(C_in, C_out)) {
+        fail("conv2d_nhwc_wgrad needs C_in %% 64 == 0 and C_out %% 64 == 0");
+        return UB_ERR_SHAPE;
+    }
+    cudaStream_t st = ub_layer_stream();
+    std::lock_guard<std::mutex> lk(g_ws.mu);
+    const size_t cap = size_t(16) << 20;
+    float* partial = (float*)g_ws.get(3, cap * sizeof(float));
+    if (!partial) return UB_ERR_CUDA;
+    IgemmWgradParams p;
+    int r = igemm_wgrad_plan(&p, (const bf16*)dout, C_out, (const bf16*)x, C_in, B, H, W, C_in, C_out, ksize * ksize,
+                             partial, cap, 148);
+    if (r) {
+        fail("conv2d_nhwc_wgrad: plan failed (%d)", r);
+        return UB_ERR_SHAPE;
+    }
+    igemm_wgrad_launch(p, st);
+    igemm_wgrad_reduce(p, dweight, st);
+    int launches = 2;
+    if (dbias) {
+        cudaMemsetAsync(dbias, 0, size_t(C_out) * sizeof(float), st);
+        colsum((const bf16*)dout, C_out, size_t(B) * H * W, C_out, dbias, nullptr, st);
+        launches++;
+    }
+    return finish(launches);
+}
+
 }  // extern "C"
