@@ -147,6 +147,7 @@ struct UbTrainer {
     // data parallel
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1, n_buckets = 4;
+    bool comm_off = false;  // rank-local eager replays (profiling) must not enqueue collectives
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::vector<cudaEvent_t> bucket_events;
     std::vector<size_t> bucket_bounds;  // param offsets, descending
@@ -649,7 +650,7 @@ int Builder::build() {
         if (hi <= lo) return;
         const int k = bucket_no++;
         Bk([=](cudaStream_t st) {
-            if (Tt->world <= 1) return;
+            if (Tt->world <= 1 || Tt->comm_off) return;
             cudaEvent_t ev = Tt->bucket_events[k % Tt->bucket_events.size()];
             cudaEventRecord(ev, st);
             cudaStreamWaitEvent(Tt->comm_stream, ev, 0);
@@ -685,7 +686,7 @@ int Builder::build() {
     }, 6);
     flush_bucket(0, flushed_hi);
     Bk([=](cudaStream_t st) {  // join the communication stream
-        if (Tt->world <= 1) return;
+        if (Tt->world <= 1 || Tt->comm_off) return;
         cudaEventRecord(Tt->ev_join, Tt->comm_stream);
         cudaStreamWaitEvent(st, Tt->ev_join, 0);
     }, 0);
@@ -1009,6 +1010,7 @@ extern "C" int ub_trainer_profile(UbTrainer* t, int reps, UbProfile* out) {
     std::vector<cudaEvent_t> ev(nops + 1);
     for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
     cudaStream_t st = t->stream;
+    t->comm_off = true;  // a profile is rank-local: the peers are not replaying with us
     for (int rep = 0; rep < reps; ++rep) {
         size_t k = 0;
         cudaEventRecord(ev[k++], st);
@@ -1039,6 +1041,7 @@ extern "C" int ub_trainer_profile(UbTrainer* t, int reps, UbProfile* out) {
         cudaEventElapsedTime(&ms, ev[j], ev[j + 1]);
         out->ms[UB_KIND_OPTIM] += ms;
     }
+    t->comm_off = false;
     for (auto& e : ev) cudaEventDestroy(e);
     for (int k = 0; k < UB_NUM_KINDS; ++k) out->ms[k] /= reps, out->total_ms += out->ms[k];
     auto acc = [&](const std::vector<UbTrainer::OpInfo>& v) {
