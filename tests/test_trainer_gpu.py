@@ -102,7 +102,9 @@ def test_eager_and_graph_steps_agree(ub, setup):
     # two AdamW steps move a weight by at most 2*lr; a near-zero gradient whose sign differs between the runs
     # (atomic summation order) can therefore differ by 4*lr
     assert np.abs(res[0][2] - res[1][2]).max() <= 4.5e-4
-    assert np.abs(res[0][2] - res[1][2]).mean() < 2e-6
+    # GroupNorm statistics are accumulated with fp32 atomics in the conv epilogues: the summation order (and with it a
+    # few bf16 roundings downstream) differs from run to run, so the mean drift is bounded, not zero
+    assert np.abs(res[0][2] - res[1][2]).mean() < 1e-5
 
 
 def test_update_matches_oracle_adamw(ub, setup):

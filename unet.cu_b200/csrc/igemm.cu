@@ -23,7 +23,7 @@ static constexpr int kConvThreads = 192;
 // =====================================================================================================
 // fprop / dgrad / 1x1 / linear
 // =====================================================================================================
-__global__ void __launch_bounds__(kConvThreads) igemm_conv_kernel(const __grid_constant__ IgemmConvParams p) {
+__global__ void __launch_bounds__(kConvThreads, 2) igemm_conv_kernel(const __grid_constant__ IgemmConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + size_t(p.stages) * p.stage_bytes);
@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(kConvThreads) igemm_conv_kernel(const __grid_c
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
     // [ncomb][BN] staged per-channel addend (one row per image of the tile), 16-byte aligned behind the barriers
     float* comb = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
+    float* gconst = comb + p.ncomb * p.BN;  // [ngimg][4][BN] GroupNorm constants (gn-bwd epilogue only)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -134,15 +135,23 @@ __global__ void __launch_bounds__(kConvThreads) igemm_conv_kernel(const __grid_c
         const int et = threadIdx.x - 64;
         for (int i = 0; i < p.ncomb; ++i)
             epi_stage_comb(comb + i * p.BN, p.bias, p.bias2, p.rowvec, min(b0 + i, p.B - 1), p.Cout, n0, p.BN, et, 128);
+        for (int i = 0; i < p.ngimg; ++i)
+            epi_stage_gconst(gconst + i * 4 * p.BN, p.gn_chsum, p.gn_gamma, p.gn_beta, min(b0 + i, p.B - 1), p.Cout,
+                             p.gn_cpg, p.H * p.W, n0, p.BN, et, 128);
         named_bar_sync(1, 128);
 
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
 
         const size_t pix = (size_t(b) * p.H + h) * p.W + w;
-        const EpiOut eo{p.residual, p.ldr, p.out, p.ldo, p.out_mode, p.Cout, p.H, p.W};
+        EpiOut eo{p.residual, p.ldr, p.out, p.ldo, p.out_mode, p.Cout, p.H, p.W};
+        eo.stats = p.stats, eo.gx = p.gn_x, eo.ldgx = p.gn_ldx, eo.gS = p.gn_S, eo.gsilu = p.gn_silu;
+        // GroupNorm hooks: the warp's image (uniform by construction), clamped so that fully masked warps of an
+        // overhanging tile still address valid memory (they add zeros)
+        const int lbw = min(lb, p.TB - 1);
+        const int bw = min(b0 + lbw, p.B - 1);
         epi_row(eo, tmem_base + (uint32_t(q * 32) << 16), comb + (p.ncomb > 1 ? min(lb, p.ncomb - 1) : 0) * p.BN, p.BN,
-                valid, pix, b, h, w, n0);
+                valid, pix, (p.stats || p.gn_x) ? bw : b, h, w, n0, gconst + lbw * 4 * p.BN, lane);
     }
 
     tc_fence_before();
@@ -407,9 +416,10 @@ int igemm_conv_plan(IgemmConvParams* p, const ConvSegDesc* segs, int nseg, int B
     // output-channel tile: the largest divisor of Cout that is a multiple of 16 and <= 256 -- but small problems
     // (8x8 / 16x16 layers) would then run on a handful of SMs, each limited by its own L2->SMEM bandwidth, so BN is
     // lowered (not below 64) until there are ~128 CTAs.
+    const bool gn_hook = ep.stats || ep.gn_x;
     int BN = 0;
     for (int cand = 256; cand >= 16; cand -= 16)
-        if (Cout % cand == 0) {
+        if (Cout % cand == 0 && (!gn_hook || cand % 32 == 0)) {
             if (!BN) BN = cand;
             if (cand < 64) break;
             BN = cand;
@@ -456,7 +466,23 @@ int igemm_conv_plan(IgemmConvParams* p, const ConvSegDesc* segs, int nseg, int B
     p->ldo = ep.ldo ? ep.ldo : Cout;
     p->out_mode = ep.out_mode;
     p->ncomb = p->rowvec ? p->TB : 1;
-    if (size_t(p->ncomb) * BN * sizeof(float) > 16384) return -9;  // staged addend rows must fit the smem tail
+    p->stats = ep.stats;
+    p->gn_x = ep.gn_x, p->gn_ldx = ep.gn_ldx, p->gn_chsum = ep.gn_chsum, p->gn_gamma = ep.gn_gamma;
+    p->gn_beta = ep.gn_beta, p->gn_S = ep.gn_S, p->gn_silu = ep.gn_silu;
+    p->ngimg = ep.gn_x ? p->TB : 0;
+    if (gn_hook) {
+        if (ep.stats && ep.gn_x) return -15;
+        if (p->out_mode != OUT_NHWC_BF16 || BN % 32 != 0) return -15;
+        if ((p->TW * p->TH) % 32 != 0 && p->TB > 1) return -15;  // a warp's 32 pixels must share one image
+        if (ep.gn_x) {
+            if (ep.residual) return -15;
+            if (!ep.gn_chsum || !ep.gn_gamma || !ep.gn_beta || !ep.gn_S || ep.gn_groups < 1 || Cout % ep.gn_groups)
+                return -15;
+            if ((ep.gn_ldx % 8) != 0 || (reinterpret_cast<uintptr_t>(ep.gn_x) & 15)) return -15;
+            p->gn_cpg = Cout / ep.gn_groups;
+        }
+    }
+    if (size_t(p->ncomb + 4 * p->ngimg) * BN * sizeof(float) > 16384) return -9;  // staged rows must fit the smem tail
     if (p->out_mode != OUT_NCHW_F32) {
         const int esz = p->out_mode == OUT_NHWC_BF16 ? 2 : 4;
         if ((p->ldo * esz) % 16 != 0 || (reinterpret_cast<uintptr_t>(p->out) & 15)) return -6;
@@ -478,7 +504,8 @@ void igemm_init() {
 
 int igemm_conv_launch(const IgemmConvParams& p, cudaStream_t st) {
     igemm_init();
-    const size_t smem = size_t(p.stages) * p.stage_bytes + 1024 + kBarrierBytes + size_t(p.ncomb) * p.BN * sizeof(float);
+    const size_t smem = size_t(p.stages) * p.stage_bytes + 1024 + kBarrierBytes +
+                        size_t(p.ncomb + 4 * p.ngimg) * p.BN * sizeof(float);
     dim3 grid(p.tiles_w * p.tiles_h * p.tiles_b, p.Cout / p.BN);
     igemm_conv_kernel<<<grid, kConvThreads, smem, st>>>(p);
     return int(cudaGetLastError());
@@ -516,7 +543,9 @@ int igemm_wgrad_plan(IgemmWgradParams* p, const __nv_bfloat16* dy, int ldy, cons
     p->stages = stages;
     const int ktiles = p->tiles_w * p->tiles_h * p->tiles_b;
     const int base_ctas = (Cout / p->MO) * (Cin / p->NC) * (ntaps / p->TC);
-    int nsplit = ceil_div_i(sm_count, base_ctas);  // one CTA per SM (a CTA owns the SM's smem and TMEM)
+    // One CTA per SM (a CTA owns the SM's smem and TMEM), and never more CTAs than SMs: a grid of 150 CTAs on 148
+    // SMs runs as two waves and doubles the kernel time (ncu r01: 64->64@64x64 took 57 us as (1,3,50)).
+    int nsplit = sm_count / base_ctas;
     if (nsplit > ktiles / 4) nsplit = ktiles / 4;      // at least 4 K tiles per CTA
     if (nsplit < 1) nsplit = 1;
     while (nsplit > 1 && igemm_wgrad_partial_floats(Cin, Cout, ntaps, nsplit) > partial_cap_floats) --nsplit;

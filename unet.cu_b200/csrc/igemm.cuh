@@ -48,6 +48,16 @@ struct IgemmConvParams {
     void* out;
     int ldo;  // channel pitch of an NHWC output (>= Cout; lets a producer write into a concat buffer)
     int out_mode;
+    // fused GroupNorm hooks (see epilogue.cuh); NHWC bf16 output, BN % 32 == 0, a warp's 32 pixels in one image
+    float* stats;                   // [B][Cout][2] += (sum, sumsq) of the output, or nullptr
+    const __nv_bfloat16* gn_x;      // gn-bwd: GroupNorm input (Cout channels, pitch gn_ldx), or nullptr
+    int gn_ldx;
+    const float* gn_chsum;          // forward statistics of gn_x [B][Cout][2]
+    const float* gn_gamma;
+    const float* gn_beta;
+    float* gn_S;                    // [B][Cout][2] += (sum dz, sum dz*xhat)
+    int gn_silu, gn_cpg;
+    int ngimg;                      // rows of the staged GroupNorm constants (TB when gn_x is set, else 0)
 };
 
 // persistent halo-reuse variant (igemm_halo.cu); same segments / epilogue as IgemmConvParams
@@ -105,6 +115,15 @@ struct ConvEpilogue {
     void* out = nullptr;
     int ldo = 0;
     int out_mode = OUT_NHWC_BF16;
+    // fused GroupNorm hooks
+    float* stats = nullptr;
+    const __nv_bfloat16* gn_x = nullptr;
+    int gn_ldx = 0;
+    const float* gn_chsum = nullptr;
+    const float* gn_gamma = nullptr;
+    const float* gn_beta = nullptr;
+    float* gn_S = nullptr;
+    int gn_silu = 0, gn_groups = 32;
 };
 // One-time kernel attribute setup (opt-in shared memory); safe to call repeatedly, call before graph capture.
 void igemm_init();

@@ -277,6 +277,7 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ x, int ldx, const b
                                     int G, int silu, int C8, int rows, int ppb, const bf16* __restrict__ add_in,
                                     int ldadd, bf16* __restrict__ dx, int lddx, float* __restrict__ dgamma,
                                     float* __restrict__ dbeta, float* __restrict__ colsum_out) {
+    // silu == 2: `dy` already holds dz = dL/d(gn(x)) (the producing dgrad conv applied silu' in its epilogue)
     extern __shared__ float sm[];  // sa, sb, sr, smr, sm1, sm2 : 6*C ; then scratch [rows][C]
     float *sa = sm, *sb = sm + C, *sr = sm + 2 * C, *smr = sm + 3 * C, *sm1 = sm + 4 * C, *sm2 = sm + 5 * C,
           *scr = sm + 6 * C;
@@ -334,7 +335,7 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ x, int ldx, const b
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 float dz = d[i];
-                if (silu) dz *= dsilu_f(f[i] * ca[i] + cb[i]);
+                if (silu == 1) dz *= dsilu_f(f[i] * ca[i] + cb[i]);
                 const float xh = f[i] * cr[i] - cm[i];
                 const float g = ca[i] * dz - c1[i] - xh * c2[i];  // ca == gamma * rstd
                 cs[i] += g;
@@ -418,8 +419,19 @@ void avgpool2_bwd(const bf16* dy, int lddy, int B, int H, int W, int C, const bf
 }
 
 __global__ void concat2_kernel(const bf16* __restrict__ a, int lda, int C1_8, int up, const bf16* __restrict__ b,
-                               int ldb, int C2_8, int H, int W, size_t total, bf16* __restrict__ out, int ldo) {
+                               int ldb, int C2_8, int H, int W, size_t total, bf16* __restrict__ out, int ldo,
+                               const float* __restrict__ cs_a, const float* __restrict__ cs_b,
+                               float* __restrict__ cs_out, size_t cs_total) {
     const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (cs_out && i < cs_total) {
+        // GroupNorm statistics of the concatenation = the parts' per-(image, channel) sums side by side; a nearest
+        // x2 upsample repeats every pixel 4 times
+        const int C1 = C1_8 * 8, C2 = C2_8 * 8, Ct = C1 + C2;
+        const int k = int(i & 1);
+        const int c = int((i >> 1) % Ct);
+        const size_t bi = (i >> 1) / Ct;
+        cs_out[i] = c < C1 ? cs_a[(bi * C1 + c) * 2 + k] * (up ? 4.f : 1.f) : cs_b[(bi * C2 + (c - C1)) * 2 + k];
+    }
     if (i >= total) return;
     const int CT = C1_8 + C2_8;
     const int j = int(i % CT);
@@ -439,10 +451,13 @@ __global__ void concat2_kernel(const bf16* __restrict__ a, int lda, int C1_8, in
     *reinterpret_cast<uint4*>(out + p * ldo + j * 8) = v;
 }
 void concat2(const bf16* a, int lda, int C1, int up, const bf16* b, int ldb, int C2, int B, int H, int W, bf16* out,
-             int ldo, cudaStream_t st) {
+             int ldo, const float* cs_a, const float* cs_b, float* cs_out, cudaStream_t st) {
     const size_t total = size_t(B) * H * W * ((C1 + C2) / 8);
-    concat2_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(a, lda, C1 / 8, up, b, ldb, C2 / 8, H, W, total, out,
-                                                                 ldo);
+    const size_t cs_total = size_t(B) * (C1 + C2) * 2;
+    const size_t nthr = total > cs_total ? total : cs_total;
+    concat2_kernel<<<unsigned((nthr + 255) / 256), 256, 0, st>>>(a, lda, C1 / 8, up, b, ldb, C2 / 8, H, W, total, out,
+                                                                ldo, cs_a, cs_b, (cs_a && cs_b) ? cs_out : nullptr,
+                                                                cs_total);
 }
 
 __global__ void upsample2_bwd_kernel(const bf16* __restrict__ dy, int lddy, int H, int W, int C8, size_t total,

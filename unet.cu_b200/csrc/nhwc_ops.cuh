@@ -21,6 +21,8 @@ void gn_apply(const bf16* x, int ldx, const float* chsum, const float* gamma, co
 void gn_bwd_stats(const bf16* x, int ldx, const bf16* dy, int lddy, const float* chsum, const float* gamma,
                   const float* beta, int B, int HW, int C, int G, int silu, float* S, cudaStream_t st);
 // Backward pass 2: dx = gn_bwd(dy) [+ add_in]; dgamma/dbeta += (atomic); colsum_out[B][C] += sum_pix dx (optional).
+// silu: 0 = no activation, 1 = SiLU follows the norm (dy is dL/d silu(gn(x))), 2 = SiLU follows the norm and dy is
+// already dL/d gn(x) (the dgrad conv that produced it applied silu' in its epilogue, see epilogue.cuh).
 void gn_bwd_apply(const bf16* x, int ldx, const bf16* dy, int lddy, const float* chsum, const float* S,
                   const float* gamma, const float* beta, int B, int HW, int C, int G, int silu, const bf16* add_in,
                   int ldadd, bf16* dx, int lddx, float* dgamma, float* dbeta, float* colsum_out, cudaStream_t st);
@@ -31,8 +33,10 @@ void avgpool2_fwd(const bf16* x, int ldx, int B, int H, int W, int C, bf16* y, i
 void avgpool2_bwd(const bf16* dy, int lddy, int B, int H, int W, int C, const bf16* add_in, int ldadd, bf16* dx,
                   int lddx, cudaStream_t st);
 // out[:, :C1] = up ? nearest_up2(a) : a ; out[:, C1:] = b.   (H, W) is the OUTPUT resolution.
+// If cs_a and cs_b (GroupNorm statistics [B][C][2] of the two inputs) are given, cs_out receives the statistics of
+// the concatenation.
 void concat2(const bf16* a, int lda, int C1, int up, const bf16* b, int ldb, int C2, int B, int H, int W, bf16* out,
-             int ldo, cudaStream_t st);
+             int ldo, const float* cs_a, const float* cs_b, float* cs_out, cudaStream_t st);
 // dx (H/2 x W/2) = sum of the 4 children of dy (H x W)
 void upsample2_bwd(const bf16* dy, int lddy, int B, int H, int W, int C, bf16* dx, int lddx, cudaStream_t st);
 void add2(const bf16* a, int lda, const bf16* b, int ldb, size_t npix, int C, bf16* out, int ldo, cudaStream_t st);

@@ -74,6 +74,7 @@ struct View {  // NHWC bf16 tensor view
     bf16* p = nullptr;
     int ld = 0;
     int C = 0, H = 0, W = 0;
+    float* cs = nullptr;  // per-(image, channel) sum / sumsq [B][C][2], filled by the tensor's producer (or null)
 };
 
 struct DeviceArena {
@@ -289,30 +290,50 @@ struct Builder {
         size_t w, b;
         float *chsum, *S;
     };
+    // statistics buffer of a tensor whose producer (a conv epilogue) accumulates them
+    float* stats_buf(int C) { return zf32(size_t(B) * C * 2); }
     GN gn_fwd(View x, View y, int silu) {
         GN g;
         g.w = take(x.C), g.b = take(x.C);
-        g.chsum = zf32(size_t(B) * x.C * 2);
+        const bool have = x.cs != nullptr;  // the producer's epilogue already accumulated the statistics
+        g.chsum = have ? x.cs : zf32(size_t(B) * x.C * 2);
         g.S = zf32(size_t(B) * x.C * 2);
         const int HW = x.H * x.W, Gn = c.gn_n_groups, Bn = B;
         float *gw = P(g.w), *gb = P(g.b), *cs = g.chsum;
         F([=](cudaStream_t st) {
-            gn_stats(x.p, x.ld, Bn, HW, x.C, cs, st);
+            if (!have) gn_stats(x.p, x.ld, Bn, HW, x.C, cs, st);
             gn_apply(x.p, x.ld, cs, gw, gb, Bn, HW, x.C, Gn, silu, y.p, y.ld, nullptr, st);
-        }, 2, UB_KIND_NORM, 0, 3 * act_bytes(x.C, x.H, x.W));
+        }, have ? 1 : 2, UB_KIND_NORM, 0, (have ? 2 : 3) * act_bytes(x.C, x.H, x.W));
         return g;
     }
-    void gn_bwd(const GN& g, View x, View dy, int silu, View add_in, View dx, float* colsum_out) {
+    // Fuse the first half of GroupNorm(+SiLU) backward into the epilogue of the dgrad conv that produces dL/dy:
+    // that conv then writes dz = dL/d gn(x) and accumulates S (see epilogue.cuh); call gn_bwd(..., fused = true) after.
+    void gn_hook(ConvEpilogue& ep, const GN& g, View x, int silu) {
+        ep.gn_x = x.p, ep.gn_ldx = x.ld, ep.gn_chsum = g.chsum, ep.gn_gamma = P(g.w), ep.gn_beta = P(g.b);
+        ep.gn_S = g.S, ep.gn_silu = silu, ep.gn_groups = c.gn_n_groups;
+    }
+    void gn_bwd(const GN& g, View x, View dy, int silu, View add_in, View dx, float* colsum_out, bool fused = false) {
         const int HW = x.H * x.W, Gn = c.gn_n_groups, Bn = B;
         float *gw = P(g.w), *gb = P(g.b), *cs = g.chsum, *S = g.S, *dgw = G(g.w), *dgb = G(g.b);
+        const int mode = fused ? (silu ? 2 : 0) : silu;
         Bk([=](cudaStream_t st) {
-            gn_bwd_stats(x.p, x.ld, dy.p, dy.ld, cs, gw, gb, Bn, HW, x.C, Gn, silu, S, st);
-            gn_bwd_apply(x.p, x.ld, dy.p, dy.ld, cs, S, gw, gb, Bn, HW, x.C, Gn, silu, add_in.p, add_in.ld, dx.p,
+            if (!fused) gn_bwd_stats(x.p, x.ld, dy.p, dy.ld, cs, gw, gb, Bn, HW, x.C, Gn, silu, S, st);
+            gn_bwd_apply(x.p, x.ld, dy.p, dy.ld, cs, S, gw, gb, Bn, HW, x.C, Gn, mode, add_in.p, add_in.ld, dx.p,
                          dx.ld, dgw, dgb, colsum_out, st);
-        }, 2, UB_KIND_NORM, 0, (5 + (add_in.p ? 1 : 0)) * act_bytes(x.C, x.H, x.W));
+        }, fused ? 1 : 2, UB_KIND_NORM, 0, ((fused ? 3 : 5) + (add_in.p ? 1 : 0)) * act_bytes(x.C, x.H, x.W));
     }
 
     int res_index = 0;
+    // The 22 embedding-projection backward GEMMs (N = B rows each) are latency-bound: they are launched in batches,
+    // one batch per gradient bucket (their weight gradients must be final before the bucket is all-reduced).
+    int emb_lo = 1 << 30, emb_hi = -1;
+    void emb_flush() {
+        if (emb_hi <= emb_lo) return;
+        UbTrainer* Tt = T;
+        const int lo = emb_lo, n = emb_hi - emb_lo, Bn = B, Cemb = 4 * c.C_model;
+        Bk([=](cudaStream_t st) { small_linear_bwd(Tt->emb_table + lo, n, Bn, Tt->emb_max_oc, Cemb, st); }, 2);
+        emb_lo = 1 << 30, emb_hi = -1;
+    }
 
     // ResBlock (dev/resblock.py:107-160, train_unet.cu:2213-2384)
     View resblock(View x, int Cout) {
@@ -325,12 +346,13 @@ struct Builder {
         const size_t w1 = take(size_t(Cout) * C * 9), b1 = take(Cout);
         const size_t wl = take(size_t(Cout) * Cemb), bl = take(Cout);
         View h1 = act(Cout, H, W);
+        h1.cs = stats_buf(Cout);
         float* embproj = f32(size_t(B) * Cout);
         float* d_embproj = zf32(size_t(B) * Cout);
         Packed p1 = pack(w1, Cout, C, 9);
         {
             ConvEpilogue ep;
-            ep.bias = P(b1), ep.rowvec = embproj, ep.out = h1.p, ep.ldo = h1.ld;
+            ep.bias = P(b1), ep.rowvec = embproj, ep.out = h1.p, ep.ldo = h1.ld, ep.stats = h1.cs;
             conv_op(true, {{a1.p, C, a1.ld, p1.wf, 9}}, H, W, Cout, ep);
         }
         View a2 = act(Cout, H, W);
@@ -345,9 +367,10 @@ struct Builder {
             ps = pack(ws, Cout, C, 1);
         }
         View out = act(Cout, H, W);
+        out.cs = stats_buf(Cout);
         {
             ConvEpilogue ep;
-            ep.bias = P(b2), ep.out = out.p, ep.ldo = out.ld;
+            ep.bias = P(b2), ep.out = out.p, ep.ldo = out.ld, ep.stats = out.cs;
             std::vector<ConvSegDesc> segs = {{a2.p, Cout, a2.ld, p2.wf, 9}};
             if (proj) {
                 segs.push_back({x.p, C, x.ld, ps.wf, 1});
@@ -380,18 +403,20 @@ struct Builder {
             {
                 ConvEpilogue ep;
                 ep.out = da2.p, ep.ldo = da2.ld;
+                gn_hook(ep, g2, h1, 1);  // da2 receives dz = dL/d gn2(h1)
                 conv_op(false, {{dout.p, Cout, dout.ld, p2.wd, 9}}, H, W, Cout, ep);
             }
             // GN2 + SiLU backward; per-image column sums of dh1 feed the embedding-projection backward
-            gn_bwd(g2, h1, da2, 1, View{}, dh1, d_embproj);
-            Bk([=](cudaStream_t st) { small_linear_bwd(Tt->emb_table + blk, 1, Bn, Cout, Cemb, st); }, 2);
+            gn_bwd(g2, h1, da2, 1, View{}, dh1, d_embproj, true);
+            emb_lo = blk < emb_lo ? blk : emb_lo, emb_hi = blk + 1 > emb_hi ? blk + 1 : emb_hi;  // batched, see emb_flush
             wgrad_op(dh1, a1, C, Cout, 9, G(w1));
             {
                 ConvEpilogue ep;
                 ep.out = da1.p, ep.ldo = da1.ld;
+                gn_hook(ep, g1, x, 1);
                 conv_op(false, {{dh1.p, Cout, dh1.ld, p1.wd, 9}}, H, W, C, ep);
             }
-            gn_bwd(g1, x, da1, 1, proj ? View{} : dout, dxg, nullptr);
+            gn_bwd(g1, x, da1, 1, proj ? View{} : dout, dxg, nullptr, true);
             if (proj) {
                 ConvEpilogue ep;
                 ep.out = dxo.p, ep.ldo = dxo.ld, ep.residual = dxg.p, ep.ldr = dxg.ld;
@@ -414,6 +439,7 @@ struct Builder {
         const size_t wp = take(size_t(C) * C), bp = take(C);
         Packed pq = pack(wq, 3 * C, C, 1), pp = pack(wp, C, C, 1);
         View qkv = act(3 * C, H, W), ao = act(C, H, W), out = act(C, H, W);
+        out.cs = stats_buf(C);
         float* lse = f32(size_t(B) * NH * Tn);
         float* dsum = f32(size_t(B) * NH * Tn);
         {
@@ -426,7 +452,7 @@ struct Builder {
           4.0 * B * NH * double(Tn) * Tn * HSz, act_bytes(4 * C, H, W));
         {
             ConvEpilogue ep;
-            ep.bias = P(bp), ep.out = out.p, ep.ldo = out.ld, ep.residual = x.p, ep.ldr = x.ld;
+            ep.bias = P(bp), ep.out = out.p, ep.ldo = out.ld, ep.residual = x.p, ep.ldr = x.ld, ep.stats = out.cs;
             conv_op(true, {{ao.p, C, ao.ld, pp.wf, 1}}, H, W, C, ep);
         }
         nd.out = out;
@@ -451,9 +477,10 @@ struct Builder {
             {
                 ConvEpilogue ep;
                 ep.out = dg.p, ep.ldo = dg.ld;
+                gn_hook(ep, gn, x, 0);
                 conv_op(false, {{dqkv.p, 3 * C, dqkv.ld, pq.wd, 1}}, H, W, C, ep);
             }
-            gn_bwd(gn, x, dg, 0, dout, dx, nullptr);
+            gn_bwd(gn, x, dg, 0, dout, dx, nullptr, true);
             return dx;
         };
         nodes.push_back(nd);
@@ -578,8 +605,10 @@ int Builder::build() {
             nd.param_begin = poff;
             const int C1 = h.C, C2 = sk.C, Hc = sk.H, Wc = sk.W, up = pending_up ? 1 : 0;
             View cat = act(C1 + C2, Hc, Wc), a = h;
-            F([=](cudaStream_t st) { concat2(a.p, a.ld, C1, up, sk.p, sk.ld, C2, Bn, Hc, Wc, cat.p, cat.ld, st); }, 1,
-              UB_KIND_ELTWISE, 0, 2 * act_bytes(C1 + C2, Hc, Wc));
+            if (a.cs && sk.cs) cat.cs = stats_buf(C1 + C2);  // GroupNorm statistics of the parts, side by side
+            F([=](cudaStream_t st) {
+                concat2(a.p, a.ld, C1, up, sk.p, sk.ld, C2, Bn, Hc, Wc, cat.p, cat.ld, a.cs, sk.cs, cat.cs, st);
+            }, 1, UB_KIND_ELTWISE, 0, 2 * act_bytes(C1 + C2, Hc, Wc));
             nd.out = cat;
             std::vector<View>* sg = &skipgrad;
             nd.bwd = [=](View d) -> View {
@@ -672,11 +701,13 @@ int Builder::build() {
         }
         g = nd.bwd(g);
         while (cut_i < cuts.size() && nd.param_begin <= cuts[cut_i] && nd.param_begin > time_mlp_end) {
+            emb_flush();
             flush_bucket(nd.param_begin, flushed_hi);
             flushed_hi = nd.param_begin;
             while (cut_i < cuts.size() && cuts[cut_i] >= nd.param_begin) ++cut_i;
         }
     }
+    emb_flush();
     // time MLP backward (needs the complete d_embact), then the last bucket
     Bk([=](cudaStream_t st) {
         dsilu_mul(Tt->d_embact, Tt->emb, Tt->demb, size_t(Bn) * Cemb, st);
