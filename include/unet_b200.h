@@ -143,6 +143,15 @@ int ub_conv2d_nhwc_dgrad(const void* dout_bf16, const void* wd_bf16, void* dx_bf
 int ub_conv2d_nhwc_wgrad(const void* dout_bf16, const void* x_bf16, float* dweight, float* dbias, int B, int H, int W,
                          int C_in, int C_out, int ksize);
 
+/* Attention core in the native layout (what the trainer runs; replaces attention_forward1 / attention_backward,
+ * dev/attention.cuh:6-22, without their permutes and (B,NH,T,T) matrices): qkv is NHWC bf16 [B*T][3C], channel order
+ * [Q | K | V], each [NH][32]; out [B*T][C] bf16; lse [B][NH][T] fp32 (log2-domain logsumexp, saved for backward).
+ * backward: dqkv [B*T][3C] bf16 from dout [B*T][C]; dsum [B][NH][T] is scratch.  Head size must be 32.
+ * impl: 0 = tcgen05 kernels (needs T in {16,32,64,128,256} and an even NH), 1 = SIMT fp32 fallback (any T). */
+int ub_attention_nhwc_forward(const void* qkv_bf16, void* out_bf16, float* lse, int B, int T, int C, int NH, int impl);
+int ub_attention_nhwc_backward(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse,
+                               void* dqkv_bf16, float* dsum, int B, int T, int C, int NH, int impl);
+
 /* ------------------------------------------------------------------------------------------------------------
  * (2) Trainer
  * ---------------------------------------------------------------------------------------------------------- */

@@ -11,7 +11,7 @@
 //               spot, writes dz = dL/d(gn(x)) instead, and accumulates the per-(image, channel) sums of dz and
 //               dz * xhat (replaces gn_bwd_stats; gn_bwd_apply then needs no sigmoid at all).
 // Both reduce over the 32 pixels of a warp with a shuffle butterfly (31 SHFL per quantity per 32 columns) and add the
-// warp totals with one fp32 RED per (warp, channel, quantity).
+// warp totals of the CTA's 4 epilogue warps in shared memory; one red.global.add.v2.f32 per (tile, channel) follows.
 #pragma once
 #include "igemm.cuh"
 #include "ptx.cuh"
@@ -126,10 +126,10 @@ __device__ __forceinline__ void epi_chunk(const EpiOut& e, uint32_t taddr, const
 
 // 32-column chunk with one of the GroupNorm hooks (NHWC bf16 output).  Every lane of the warp takes part in the
 // reduction; lanes whose pixel is outside the tensor contribute zeros and store nothing.  All pixels of a warp belong
-// to image b (the plan guarantees it).  gconst = staged [4][BN] per-channel constants of image b (a = gamma*rstd,
+// to one image (the plan guarantees it).  gconst = staged [4][BN] per-channel constants of image b (a = gamma*rstd,
 // bb = beta - mean*a, rstd, mean*rstd), offset to this chunk's first column (gn-bwd only); cstride = BN.
 __device__ __forceinline__ void epi_chunk_gn(const EpiOut& e, uint32_t taddr, const float* comb, const float* gconst,
-                                             int cstride, bool valid, size_t pix, int b, int n, int lane) {
+                                             int cstride, bool valid, size_t pix, int n, int lane, float* red) {
     uint32_t v[32];
     tmem_ld32(taddr, v);
     uint4 xr[4];  // the residual row (stats mode) or the GroupNorm input row (gn-bwd mode): never both (plan)
@@ -200,18 +200,42 @@ __device__ __forceinline__ void epi_chunk_gn(const EpiOut& e, uint32_t taddr, co
         for (int j = 0; j < 32; ++j) f[j] = 0.f, q[j] = 0.f;
     }
     warp_colsum2(f, q, lane);
-    float* dst = (e.gx ? e.gS : e.stats) + (size_t(b) * e.Cout + n + lane) * 2;
-    atomicAdd(dst, f[0]);
-    atomicAdd(dst + 1, q[0]);
+    // lane j now holds the warp's totals of column j: park them; epi_flush_stats adds the 4 warps up and issues
+    // one vector RED per (tile, channel) instead of 8 scalar ones (the L2 atomic unit serialises per address)
+    *reinterpret_cast<float2*>(red + 2 * lane) = make_float2(f[0], q[0]);
+}
+
+// red[4 warps][BN][2] -> global [B][Cout][2].  Called by the 128 epilogue threads after a barrier; img_of_warp(q) is
+// the tile-local image index of warp q's 32 pixels.
+__device__ __forceinline__ void epi_flush_stats(const float* red, float* dst, int Cout, int n0, int BN, int b0,
+                                                int B, int rows_per_img, int TB, int tid) {
+    for (int c = tid; c < BN; c += 128) {
+        for (int img = 0; img < TB; ++img) {
+            float s = 0.f, ss = 0.f;
+            bool any = false;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int iq = min((q * 32) / rows_per_img, TB - 1);
+                if (iq == img) {
+                    const float2 v = *reinterpret_cast<const float2*>(red + (size_t(q) * BN + c) * 2);
+                    s += v.x, ss += v.y, any = true;
+                }
+            }
+            if (any && b0 + img < B) {
+                float* d = dst + (size_t(b0 + img) * Cout + n0 + c) * 2;
+                asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(d), "f"(s), "f"(ss) : "memory");
+            }
+        }
+    }
 }
 
 // all columns [0, BN) of one accumulator row
 __device__ __forceinline__ void epi_row(const EpiOut& e, uint32_t trow, const float* comb, int BN, bool valid,
                                         size_t pix, int b, int h, int w, int n0, const float* gconst = nullptr,
-                                        int lane = 0) {
-    if (e.stats || e.gx) {  // BN % 32 == 0 (plan)
+                                        int lane = 0, float* red = nullptr) {
+    if (e.stats || e.gx) {  // BN % 32 == 0 (plan); red = this warp's [BN][2] row of the reduction scratch
         for (int c0 = 0; c0 < BN; c0 += 32)
-            epi_chunk_gn(e, trow + uint32_t(c0), comb + c0, gconst + c0, BN, valid, pix, b, n0 + c0, lane);
+            epi_chunk_gn(e, trow + uint32_t(c0), comb + c0, gconst + c0, BN, valid, pix, n0 + c0, lane, red + 2 * c0);
         return;
     }
     int c0 = 0;

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) igemm_conv_kernel(const __gri
     // [ncomb][BN] staged per-channel addend (one row per image of the tile), 16-byte aligned behind the barriers
     float* comb = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
     float* gconst = comb + p.ncomb * p.BN;  // [ngimg][4][BN] GroupNorm constants (gn-bwd epilogue only)
+    float* red = gconst + p.ngimg * 4 * p.BN;  // [4 warps][BN][2] column sums of the GroupNorm hooks
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -146,12 +147,14 @@ __global__ void __launch_bounds__(kConvThreads, 2) igemm_conv_kernel(const __gri
         const size_t pix = (size_t(b) * p.H + h) * p.W + w;
         EpiOut eo{p.residual, p.ldr, p.out, p.ldo, p.out_mode, p.Cout, p.H, p.W};
         eo.stats = p.stats, eo.gx = p.gn_x, eo.ldgx = p.gn_ldx, eo.gS = p.gn_S, eo.gsilu = p.gn_silu;
-        // GroupNorm hooks: the warp's image (uniform by construction), clamped so that fully masked warps of an
-        // overhanging tile still address valid memory (they add zeros)
+        // GroupNorm hooks: all 32 pixels of a warp lie in one image of the tile (plan)
         const int lbw = min(lb, p.TB - 1);
-        const int bw = min(b0 + lbw, p.B - 1);
         epi_row(eo, tmem_base + (uint32_t(q * 32) << 16), comb + (p.ncomb > 1 ? min(lb, p.ncomb - 1) : 0) * p.BN, p.BN,
-                valid, pix, (p.stats || p.gn_x) ? bw : b, h, w, n0, gconst + lbw * 4 * p.BN, lane);
+                valid, pix, b, h, w, n0, gconst + lbw * 4 * p.BN, lane, red + size_t(q) * p.BN * 2);
+        if (p.stats || p.gn_x) {
+            named_bar_sync(1, 128);
+            epi_flush_stats(red, p.gn_x ? p.gn_S : p.stats, p.Cout, n0, p.BN, b0, p.B, p.TW * p.TH, p.TB, et);
+        }
     }
 
     tc_fence_before();
@@ -441,8 +444,13 @@ int igemm_conv_plan(IgemmConvParams* p, const ConvSegDesc* segs, int nseg, int B
     p->b_bytes = uint32_t(64 * BN * 2);
     p->stage_bytes = 16384u + ((p->b_bytes + 1023u) & ~1023u);
     // Two CTAs per SM when possible (one CTA's epilogue overlaps the other's main loop): <= ~110 KiB each.
-    int stages = int((110u * 1024u) / p->stage_bytes);
-    if (stages < 3) stages = int((220u * 1024u) / p->stage_bytes);
+    // (the smem tail -- barriers, staged addends, GroupNorm constants and reduction scratch -- comes off the budget)
+    const int tb_guess = (128 / (p->TW * p->TH)) < 1 ? 1 : 128 / (p->TW * p->TH);
+    const uint32_t tail = 1024u + uint32_t(kBarrierBytes) +
+                          uint32_t((ep.rowvec ? tb_guess : 1) + (ep.gn_x ? 4 * tb_guess : 0) + (gn_hook ? 8 : 0)) *
+                              uint32_t(BN) * 4u;
+    int stages = int((113u * 1024u - tail) / p->stage_bytes);
+    if (stages < 3) stages = int((227u * 1024u - tail) / p->stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) return -3;
     p->stages = stages;
@@ -482,7 +490,11 @@ int igemm_conv_plan(IgemmConvParams* p, const ConvSegDesc* segs, int nseg, int B
             p->gn_cpg = Cout / ep.gn_groups;
         }
     }
-    if (size_t(p->ncomb + 4 * p->ngimg) * BN * sizeof(float) > 16384) return -9;  // staged rows must fit the smem tail
+    p->nred = gn_hook ? 8 : 0;
+    if (size_t(p->ncomb + 4 * p->ngimg + p->nred) * BN * sizeof(float) > 16384) return -9;  // smem tail budget
+    if (size_t(p->stages) * p->stage_bytes + 1024 + kBarrierBytes +
+            size_t(p->ncomb + 4 * p->ngimg + p->nred) * BN * sizeof(float) > size_t(227) * 1024)
+        return -3;
     if (p->out_mode != OUT_NCHW_F32) {
         const int esz = p->out_mode == OUT_NHWC_BF16 ? 2 : 4;
         if ((p->ldo * esz) % 16 != 0 || (reinterpret_cast<uintptr_t>(p->out) & 15)) return -6;
@@ -505,10 +517,14 @@ void igemm_init() {
 int igemm_conv_launch(const IgemmConvParams& p, cudaStream_t st) {
     igemm_init();
     const size_t smem = size_t(p.stages) * p.stage_bytes + 1024 + kBarrierBytes +
-                        size_t(p.ncomb + 4 * p.ngimg) * p.BN * sizeof(float);
+                        size_t(p.ncomb + 4 * p.ngimg + p.nred) * p.BN * sizeof(float);
     dim3 grid(p.tiles_w * p.tiles_h * p.tiles_b, p.Cout / p.BN);
     igemm_conv_kernel<<<grid, kConvThreads, smem, st>>>(p);
-    return int(cudaGetLastError());
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)  // a failed launch must never pass silently (the output would simply be stale)
+        fprintf(stderr, "[unet_b200] igemm_conv launch failed: %s (grid %u x %u, smem %zu, BN %d, stages %d)\n",
+                cudaGetErrorString(e), grid.x, grid.y, smem, p.BN, p.stages);
+    return int(e);
 }
 
 size_t igemm_wgrad_partial_floats(int Cin, int Cout, int ntaps, int nsplit) {

@@ -58,6 +58,7 @@ struct IgemmConvParams {
     float* gn_S;                    // [B][Cout][2] += (sum dz, sum dz*xhat)
     int gn_silu, gn_cpg;
     int ngimg;                      // rows of the staged GroupNorm constants (TB when gn_x is set, else 0)
+    int nred;                       // BN-float rows of the cross-warp reduction scratch (8 with a hook, else 0)
 };
 
 // persistent halo-reuse variant (igemm_halo.cu); same segments / epilogue as IgemmConvParams

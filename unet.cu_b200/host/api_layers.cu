@@ -12,6 +12,7 @@
 #include <mutex>
 
 #include "../../include/unet_b200.h"
+#include "../csrc/attn_tc.cuh"
 #include "../csrc/igemm.cuh"
 #include "../csrc/layers_f32.cuh"
 #include "../csrc/misc_ops.cuh"
@@ -461,4 +462,56 @@ int ub_conv2d_nhwc_wgrad(const void* dout, const void* x, float* dweight, float*
     return finish(launches);
 }
 
+}  // extern "C"
+
+extern "C" {
+// ---- attention core, native layout
+int ub_attention_nhwc_forward(const void* qkv, void* out, float* lse, int B, int T, int C, int NH, int impl) {
+    if (NH < 1 || C != NH * 32) {
+        fail("attention_nhwc: head size must be 32 (C == NH * 32)");
+        return UB_ERR_SHAPE;
+    }
+    if (impl == 0) {
+        if (!attn_tc_supported(T, NH, 32)) {
+            fail("attention_nhwc: the tcgen05 kernels need T in {16,32,64,128,256} and an even NH");
+            return UB_ERR_SHAPE;
+        }
+        AttnTcParams p;
+        int r = attn_tc_plan(&p, (const bf16*)qkv, 3 * C, B, T, NH, 32, (bf16*)out, C, lse, nullptr, 0, nullptr, 0,
+                             nullptr);
+        if (r) {
+            fail("attn_tc_plan failed (%d)", r);
+            return UB_ERR_SHAPE;
+        }
+        attn_tc_fwd(p, ub_layer_stream());
+    } else {
+        attn_fwd((const bf16*)qkv, 3 * C, B, T, NH, 32, (bf16*)out, C, lse, ub_layer_stream());
+    }
+    return finish(1);
+}
+int ub_attention_nhwc_backward(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                               float* dsum, int B, int T, int C, int NH, int impl) {
+    if (NH < 1 || C != NH * 32) {
+        fail("attention_nhwc: head size must be 32 (C == NH * 32)");
+        return UB_ERR_SHAPE;
+    }
+    if (impl == 0) {
+        if (!attn_tc_supported(T, NH, 32)) {
+            fail("attention_nhwc: the tcgen05 kernels need T in {16,32,64,128,256} and an even NH");
+            return UB_ERR_SHAPE;
+        }
+        AttnTcParams p;
+        int r = attn_tc_plan(&p, (const bf16*)qkv, 3 * C, B, T, NH, 32, (bf16*)const_cast<void*>(out), C,
+                             const_cast<float*>(lse), (const bf16*)dout, C, (bf16*)dqkv, 3 * C, dsum);
+        if (r) {
+            fail("attn_tc_plan failed (%d)", r);
+            return UB_ERR_SHAPE;
+        }
+        attn_tc_bwd(p, ub_layer_stream());
+    } else {
+        attn_bwd((const bf16*)qkv, 3 * C, (const bf16*)out, C, (const bf16*)dout, C, lse, B, T, NH, 32, (bf16*)dqkv,
+                 3 * C, dsum, ub_layer_stream());
+    }
+    return finish(2);
+}
 }  // extern "C"

@@ -9,12 +9,14 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <string>
 #include <vector>
 
 #include "../../include/unet_b200.h"
+#include "../csrc/attn_tc.cuh"
 #include "../csrc/igemm.cuh"
 #include "../csrc/misc_ops.cuh"
 #include "../csrc/nhwc_ops.cuh"
@@ -448,8 +450,19 @@ struct Builder {
             conv_op(true, {{g.p, C, g.ld, pq.wf, 1}}, H, W, 3 * C, ep);
         }
         const int Bn = B;
-        F([=](cudaStream_t st) { attn_fwd(qkv.p, qkv.ld, Bn, Tn, NH, HSz, ao.p, ao.ld, lse, st); }, 1, UB_KIND_ATTN,
-          4.0 * B * NH * double(Tn) * Tn * HSz, act_bytes(4 * C, H, W));
+        // tcgen05 attention core when the shape allows (T <= 256, even head count), SIMT fallback otherwise
+        const bool tc = attn_tc_supported(Tn, NH, HSz);
+        AttnTcParams apf;
+        if (tc && real()) {
+            int r = attn_tc_plan(&apf, qkv.p, qkv.ld, B, Tn, NH, HSz, ao.p, ao.ld, lse, nullptr, 0, nullptr, 0, nullptr);
+            if (r) set_err("attn_tc_plan failed (%d)", r), plan_errors++;
+        }
+        F([=](cudaStream_t st) {
+            if (tc)
+                attn_tc_fwd(apf, st);
+            else
+                attn_fwd(qkv.p, qkv.ld, Bn, Tn, NH, HSz, ao.p, ao.ld, lse, st);
+        }, 1, UB_KIND_ATTN, 4.0 * B * NH * double(Tn) * Tn * HSz, act_bytes(4 * C, H, W));
         {
             ConvEpilogue ep;
             ep.bias = P(bp), ep.out = out.p, ep.ldo = out.ld, ep.residual = x.p, ep.ldr = x.ld, ep.stats = out.cs;
@@ -468,8 +481,18 @@ struct Builder {
                 ep.out = dao.p, ep.ldo = dao.ld;
                 conv_op(false, {{dout.p, C, dout.ld, pp.wd, 1}}, H, W, C, ep);
             }
+            AttnTcParams apb;
+            if (tc && real()) {
+                int r = attn_tc_plan(&apb, qkv.p, qkv.ld, B, Tn, NH, HSz, ao.p, ao.ld, lse, dao.p, dao.ld, dqkv.p,
+                                     dqkv.ld, dsum);
+                if (r) set_err("attn_tc_plan (bwd) failed (%d)", r), plan_errors++;
+            }
             Bk([=](cudaStream_t st) {
-                attn_bwd(qkv.p, qkv.ld, ao.p, ao.ld, dao.p, dao.ld, lse, Bn, Tn, NH, HSz, dqkv.p, dqkv.ld, dsum, st);
+                if (tc)
+                    attn_tc_bwd(apb, st);
+                else
+                    attn_bwd(qkv.p, qkv.ld, ao.p, ao.ld, dao.p, dao.ld, lse, Bn, Tn, NH, HSz, dqkv.p, dqkv.ld, dsum,
+                             st);
             }, 2, UB_KIND_ATTN, 10.0 * B * NH * double(Tn) * Tn * HSz, act_bytes(8 * C, H, W));
             Bk([=](cudaStream_t st) { colsum(dqkv.p, dqkv.ld, npix, 3 * C, gbq, nullptr, st); }, 1, UB_KIND_ELTWISE, 0,
                act_bytes(3 * C, H, W));
@@ -798,6 +821,7 @@ extern "C" int ub_trainer_create(UbTrainer** out, const UbConfig* cfg, int devic
     CUDA_TRY(cudaSetDevice(device));
     igemm_init();
     attn_init();
+    attn_tc_init();
     UbTrainer* t = new UbTrainer();
     t->cfg = *cfg;
     t->device = device;
@@ -906,8 +930,25 @@ static void enqueue_step(UbTrainer* t, const StepOpts& o, cudaStream_t st) {
     cudaMemsetAsync(t->zero_base, 0, t->zero_bytes, st);
     diffusion_prepare(t->x0, t->sqrt_ac, t->sqrt_1mac, c.B, size_t(c.C_in) * c.H * c.W, c.n_timesteps, c.seed,
                       t->step_dev, o.gen_t ? 1 : 0, o.gen_noise ? 1 : 0, t->tsteps, t->noise, t->xt, st);
-    for (auto& op : t->fwd_ops) op(st);
-    for (auto& op : t->bwd_ops) op(st);
+    static const bool debug_sync = getenv("UB_DEBUG_SYNC") != nullptr;  // eager runs only: find the faulting op
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (debug_sync) cudaStreamIsCapturing(st, &cap);
+    auto run = [&](std::vector<UbTrainer::Op>& ops, std::vector<UbTrainer::OpInfo>& info, const char* what) {
+        for (size_t i = 0; i < ops.size(); ++i) {
+            ops[i](st);
+            if (debug_sync && cap == cudaStreamCaptureStatusNone) {
+                cudaError_t e = cudaStreamSynchronize(st);
+                if (e == cudaSuccess) e = cudaGetLastError();
+                if (e != cudaSuccess) {
+                    fprintf(stderr, "[unet_b200] %s op %zu (kind %d): %s\n", what, i, info[i].kind,
+                            cudaGetErrorString(e));
+                    break;
+                }
+            }
+        }
+    };
+    run(t->fwd_ops, t->fwd_info, "forward");
+    run(t->bwd_ops, t->bwd_info, "backward");
     if (o.update) {
         adamw_step(t->params, t->grads, t->m, t->v, t->nparams, o.lr, o.b1, o.b2, o.eps, o.wd, 1.f / float(t->world),
                    t->step_dev, st);
