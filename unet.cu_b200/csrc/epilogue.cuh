@@ -10,8 +10,8 @@
 //   * gn-bwd  : the epilogue of the dgrad conv that produces dL/d(silu(gn(x))) multiplies by silu'(gn(x)) on the
 //               spot, writes dz = dL/d(gn(x)) instead, and accumulates the per-(image, channel) sums of dz and
 //               dz * xhat (replaces gn_bwd_stats; gn_bwd_apply then needs no sigmoid at all).
-// Both reduce over the 32 pixels of a warp with a shuffle butterfly (31 SHFL per quantity per 32 columns) and add the
-// warp totals of the CTA's 4 epilogue warps in shared memory; one red.global.add.v2.f32 per (tile, channel) follows.
+// Both reduce over the 32 pixels of a warp through a small smem transpose and add the warp totals of the CTA's
+// epilogue warps in shared memory; one red.global.add.v2.f32 per (tile, channel) follows.
 #pragma once
 #include "igemm.cuh"
 #include "ptx.cuh"
@@ -37,21 +37,6 @@ __device__ __forceinline__ float epi_sigmoid(float z) {
     float t;
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
     return fmaf(0.5f, t, 0.5f);
-}
-
-// Column sums over the 32 lanes of a warp: on return lane j holds sum_lanes a[j] in a[0] (and likewise b[0]).
-__device__ __forceinline__ void warp_colsum2(float (&a)[32], float (&b)[32], int lane) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        const bool up = (lane & off) != 0;
-#pragma unroll
-        for (int i = 0; i < off; ++i) {
-            const float sa = up ? a[i] : a[i + off], ka = up ? a[i + off] : a[i];
-            const float sb = up ? b[i] : b[i + off], kb = up ? b[i + off] : b[i];
-            a[i] = ka + __shfl_xor_sync(0xffffffffu, sa, off);
-            b[i] = kb + __shfl_xor_sync(0xffffffffu, sb, off);
-        }
-    }
 }
 
 __device__ __forceinline__ void unpack_bf16x8(const uint4& v, float* f) {
@@ -124,43 +109,37 @@ __device__ __forceinline__ void epi_chunk(const EpiOut& e, uint32_t taddr, const
     }
 }
 
-// 32-column chunk with one of the GroupNorm hooks (NHWC bf16 output).  Every lane of the warp takes part in the
+// 16-column chunk with one of the GroupNorm hooks (NHWC bf16 output).  Every lane of the warp takes part in the
 // reduction; lanes whose pixel is outside the tensor contribute zeros and store nothing.  All pixels of a warp belong
-// to one image (the plan guarantees it).  gconst = staged [4][BN] per-channel constants of image b (a = gamma*rstd,
+// to one image (the plan guarantees it).  gconst = staged [4][BN] per-channel constants of that image (a = gamma*rstd,
 // bb = beta - mean*a, rstd, mean*rstd), offset to this chunk's first column (gn-bwd only); cstride = BN.
+// Column sums over the warp's 32 pixels go through a per-warp smem transpose tr[32][36] (f in columns 0..15, q in
+// 16..31; 144-byte rows keep both the 16-byte row stores and the column reads bank-conflict free): 8 STS.128 + 32
+// independent LDS per lane instead of a 5-stage shuffle butterfly -- the epilogue is latency-bound, not issue-bound.
 __device__ __forceinline__ void epi_chunk_gn(const EpiOut& e, uint32_t taddr, const float* comb, const float* gconst,
-                                             int cstride, bool valid, size_t pix, int n, int lane, float* red) {
-    uint32_t v[32];
-    tmem_ld32(taddr, v);
-    uint4 xr[4];  // the residual row (stats mode) or the GroupNorm input row (gn-bwd mode): never both (plan)
+                                             int cstride, bool valid, size_t pix, int n, int lane, float* red,
+                                             float* tr) {
+    uint32_t v[16];
+    tmem_ld16(taddr, v);
+    uint4 xr[2];  // the residual row (stats mode) or the GroupNorm input row (gn-bwd mode): never both (plan)
     if ((e.residual || e.gx) && valid) {
         const uint4* xp = e.gx ? reinterpret_cast<const uint4*>(e.gx + pix * e.ldgx + n)
                                : reinterpret_cast<const uint4*>(e.residual + pix * e.ldr + n);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) xr[j] = xp[j];
+        xr[0] = xp[0], xr[1] = xp[1];
     }
     tmem_ld_wait();
-    float f[32], q[32];
+    float f[16], q[16];
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
+    for (int j = 0; j < 16; j += 4) {
         const float4 c = *reinterpret_cast<const float4*>(comb + j);
         f[j] = __uint_as_float(v[j]) + c.x, f[j + 1] = __uint_as_float(v[j + 1]) + c.y;
         f[j + 2] = __uint_as_float(v[j + 2]) + c.z, f[j + 3] = __uint_as_float(v[j + 3]) + c.w;
     }
-    if (e.residual && !e.gx && valid) {
+    if (valid) {
+        if (e.gx) {
+            // f = dL/d(act(gn(x)))  ->  dz = f * act'(z);  q = dz * xhat
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float t[8];
-            unpack_bf16x8(xr[j], t);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[j * 8 + i] += t[i];
-        }
-    }
-    if (e.gx) {
-        // f = dL/d(act(gn(x)))  ->  dz = f * act'(z);  q = dz * xhat
-        if (valid) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 2; ++j) {
                 float x[8];
                 unpack_bf16x8(xr[j], x);
 #pragma unroll
@@ -169,47 +148,69 @@ __device__ __forceinline__ void epi_chunk_gn(const EpiOut& e, uint32_t taddr, co
                     float dz = f[c];
                     if (e.gsilu) {
                         const float z = fmaf(x[i], gconst[c], gconst[cstride + c]);
-                        const float s = epi_sigmoid(z);
-                        dz *= s * fmaf(z, 1.f - s, 1.f);
+                        const float sg = epi_sigmoid(z);
+                        dz *= sg * fmaf(z, 1.f - sg, 1.f);
                     }
-                    const float xh = fmaf(x[i], gconst[2 * cstride + c], -gconst[3 * cstride + c]);
+                    // the stored (bf16) dz is what gn_bwd_apply will read: sum exactly that
+                    dz = __bfloat162float(__float2bfloat16(dz));
                     f[c] = dz;
-                    q[c] = dz * xh;
+                    q[c] = dz * fmaf(x[i], gconst[2 * cstride + c], -gconst[3 * cstride + c]);
                 }
             }
-        }
-    }
-    // round to the stored precision first: the statistics then describe exactly the tensor the consumer reads
-    uint32_t pk[16];
+        } else {
+            if (e.residual) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-        pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
-        if (!e.gx) {
-            f[2 * i] = __bfloat162float(h2.x), f[2 * i + 1] = __bfloat162float(h2.y);
-            q[2 * i] = f[2 * i] * f[2 * i], q[2 * i + 1] = f[2 * i + 1] * f[2 * i + 1];
+                for (int j = 0; j < 2; ++j) {
+                    float t[8];
+                    unpack_bf16x8(xr[j], t);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) f[j * 8 + i] += t[i];
+                }
+            }
+            // round to the stored precision first: the statistics then describe exactly the tensor the consumer reads
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                f[c] = __bfloat162float(__float2bfloat16(f[c]));
+                q[c] = f[c] * f[c];
+            }
         }
-    }
-    if (valid) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+            pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+        }
         __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(e.out) + pix * e.ldo + n;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            reinterpret_cast<uint4*>(op)[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        reinterpret_cast<uint4*>(op)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        reinterpret_cast<uint4*>(op)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = 0.f, q[j] = 0.f;
+        for (int j = 0; j < 16; ++j) f[j] = 0.f, q[j] = 0.f;
     }
-    warp_colsum2(f, q, lane);
-    // lane j now holds the warp's totals of column j: park them; epi_flush_stats adds the 4 warps up and issues
-    // one vector RED per (tile, channel) instead of 8 scalar ones (the L2 atomic unit serialises per address)
-    *reinterpret_cast<float2*>(red + 2 * lane) = make_float2(f[0], q[0]);
+    float4* row = reinterpret_cast<float4*>(tr + lane * 36);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        row[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        row[4 + j] = make_float4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
+    }
+    __syncwarp();
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; r += 4) {
+        s0 += tr[r * 36 + lane], s1 += tr[(r + 1) * 36 + lane];
+        s2 += tr[(r + 2) * 36 + lane], s3 += tr[(r + 3) * 36 + lane];
+    }
+    __syncwarp();
+    // lane j < 16 holds the warp's total of f column j, lane 16 + j that of q column j: park them; epi_flush_stats
+    // adds the warps up and issues one vector RED per (tile, channel) (the L2 atomic unit serialises per address)
+    red[2 * (lane & 15) + (lane >> 4)] = (s0 + s1) + (s2 + s3);
 }
 
-// red[4 warps][BN][2] -> global [B][Cout][2].  Called by the 128 epilogue threads after a barrier; img_of_warp(q) is
-// the tile-local image index of warp q's 32 pixels.
+// red[4 quadrants][BN][2] -> global [B][Cout][2].  Called by the nthreads epilogue threads after a barrier; quadrant
+// q's 32 pixels belong to tile-local image min(32 q / rows_per_img, TB - 1).
 __device__ __forceinline__ void epi_flush_stats(const float* red, float* dst, int Cout, int n0, int BN, int b0,
-                                                int B, int rows_per_img, int TB, int tid) {
-    for (int c = tid; c < BN; c += 128) {
+                                                int B, int rows_per_img, int TB, int tid, int nthreads) {
+    for (int c = tid; c < BN; c += nthreads) {
         for (int img = 0; img < TB; ++img) {
             float s = 0.f, ss = 0.f;
             bool any = false;
@@ -229,18 +230,23 @@ __device__ __forceinline__ void epi_flush_stats(const float* red, float* dst, in
     }
 }
 
-// all columns [0, BN) of one accumulator row
+// Columns [0, BN) of one accumulator row.  The row is shared by `nhalf` warps of the same TMEM lane quadrant: chunk i
+// goes to warp i % nhalf.
 __device__ __forceinline__ void epi_row(const EpiOut& e, uint32_t trow, const float* comb, int BN, bool valid,
                                         size_t pix, int b, int h, int w, int n0, const float* gconst = nullptr,
-                                        int lane = 0, float* red = nullptr) {
-    if (e.stats || e.gx) {  // BN % 32 == 0 (plan); red = this warp's [BN][2] row of the reduction scratch
-        for (int c0 = 0; c0 < BN; c0 += 32)
-            epi_chunk_gn(e, trow + uint32_t(c0), comb + c0, gconst + c0, BN, valid, pix, n0 + c0, lane, red + 2 * c0);
+                                        int lane = 0, float* red = nullptr, float* tr = nullptr, int half = 0,
+                                        int nhalf = 1) {
+    if (e.stats || e.gx) {  // BN % 32 == 0 (plan); red = this quadrant's [BN][2] row of the reduction scratch
+        for (int c0 = 16 * half; c0 < BN; c0 += 16 * nhalf)
+            epi_chunk_gn(e, trow + uint32_t(c0), comb + c0, gconst + c0, BN, valid, pix, n0 + c0, lane, red + 2 * c0,
+                         tr);
         return;
     }
-    int c0 = 0;
-    for (; c0 + 32 <= BN; c0 += 32) epi_chunk<32>(e, trow + uint32_t(c0), comb + c0, valid, pix, b, h, w, n0 + c0);
-    for (; c0 < BN; c0 += 16) epi_chunk<16>(e, trow + uint32_t(c0), comb + c0, valid, pix, b, h, w, n0 + c0);
+    int i = 0, c0 = 0;
+    for (; c0 + 32 <= BN; c0 += 32, ++i)
+        if (i % nhalf == half) epi_chunk<32>(e, trow + uint32_t(c0), comb + c0, valid, pix, b, h, w, n0 + c0);
+    for (; c0 < BN; c0 += 16, ++i)
+        if (i % nhalf == half) epi_chunk<16>(e, trow + uint32_t(c0), comb + c0, valid, pix, b, h, w, n0 + c0);
 }
 
 // comb[c] = bias[n0+c] + bias2[n0+c] + rowvec[b][n0+c] for c in [0, BN), computed by the calling threads (tid in

@@ -18,7 +18,9 @@
 namespace ub {
 
 static constexpr int kMaxStages = 8;
-static constexpr int kConvThreads = 192;
+static constexpr int kConvThreads = 320;   // conv: TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quadrant)
+static constexpr int kWgradThreads = 192;  // wgrad: TMA warp, MMA warp, 4 epilogue warps
+static constexpr int kEpiThreads = kConvThreads - 64;
 
 // =====================================================================================================
 // fprop / dgrad / 1x1 / linear
@@ -123,8 +125,9 @@ __global__ void __launch_bounds__(kConvThreads, 2) igemm_conv_kernel(const __gri
             umma_commit(tmem_full_bar);
         }
     } else {
-        // ------------------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------------------ epilogue (warps 2..9)
         const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        const int half = (warp - 2) >> 2;  // the two warps of a quadrant split the columns
         const int row = q * 32 + lane;
         const int lw = row % p.TW;
         const int lh = (row / p.TW) % p.TH;
@@ -135,11 +138,12 @@ __global__ void __launch_bounds__(kConvThreads, 2) igemm_conv_kernel(const __gri
         // embedding vector is used (p.ncomb == TB), a single shared row otherwise
         const int et = threadIdx.x - 64;
         for (int i = 0; i < p.ncomb; ++i)
-            epi_stage_comb(comb + i * p.BN, p.bias, p.bias2, p.rowvec, min(b0 + i, p.B - 1), p.Cout, n0, p.BN, et, 128);
+            epi_stage_comb(comb + i * p.BN, p.bias, p.bias2, p.rowvec, min(b0 + i, p.B - 1), p.Cout, n0, p.BN, et,
+                           kEpiThreads);
         for (int i = 0; i < p.ngimg; ++i)
             epi_stage_gconst(gconst + i * 4 * p.BN, p.gn_chsum, p.gn_gamma, p.gn_beta, min(b0 + i, p.B - 1), p.Cout,
-                             p.gn_cpg, p.H * p.W, n0, p.BN, et, 128);
-        named_bar_sync(1, 128);
+                             p.gn_cpg, p.H * p.W, n0, p.BN, et, kEpiThreads);
+        named_bar_sync(1, kEpiThreads);
 
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
@@ -150,10 +154,13 @@ __global__ void __launch_bounds__(kConvThreads, 2) igemm_conv_kernel(const __gri
         // GroupNorm hooks: all 32 pixels of a warp lie in one image of the tile (plan)
         const int lbw = min(lb, p.TB - 1);
         epi_row(eo, tmem_base + (uint32_t(q * 32) << 16), comb + (p.ncomb > 1 ? min(lb, p.ncomb - 1) : 0) * p.BN, p.BN,
-                valid, pix, b, h, w, n0, gconst + lbw * 4 * p.BN, lane, red + size_t(q) * p.BN * 2);
+                valid, pix, b, h, w, n0, gconst + lbw * 4 * p.BN, lane, red + size_t(q) * p.BN * 2,
+                // per-warp transpose scratch: the pipeline stages are free once the accumulator is complete
+                reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 36), half, 2);
         if (p.stats || p.gn_x) {
-            named_bar_sync(1, 128);
-            epi_flush_stats(red, p.gn_x ? p.gn_S : p.stats, p.Cout, n0, p.BN, b0, p.B, p.TW * p.TH, p.TB, et);
+            named_bar_sync(1, kEpiThreads);
+            epi_flush_stats(red, p.gn_x ? p.gn_S : p.stats, p.Cout, n0, p.BN, b0, p.B, p.TW * p.TH, p.TB, et,
+                            kEpiThreads);
         }
     }
 
@@ -165,7 +172,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) igemm_conv_kernel(const __gri
 // =====================================================================================================
 // wgrad: both operands MN-major (the contraction index is the pixel index, channels are contiguous)
 // =====================================================================================================
-__global__ void __launch_bounds__(kConvThreads) igemm_wgrad_kernel(const __grid_constant__ IgemmWgradParams p) {
+__global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid_constant__ IgemmWgradParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + size_t(p.stages) * p.stage_bytes);
@@ -578,7 +585,7 @@ int igemm_wgrad_launch(const IgemmWgradParams& p, cudaStream_t st) {
     igemm_init();
     const size_t smem = size_t(p.stages) * p.stage_bytes + 1024 + kBarrierBytes;
     dim3 grid((p.Cout / p.MO) * (p.Cin / p.NC), p.ntaps / p.TC, p.nsplit);
-    igemm_wgrad_kernel<<<grid, kConvThreads, smem, st>>>(p);
+    igemm_wgrad_kernel<<<grid, kWgradThreads, smem, st>>>(p);
     return int(cudaGetLastError());
 }
 
