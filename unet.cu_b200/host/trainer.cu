@@ -100,6 +100,13 @@ struct UbTrainer {
     UbConfig cfg;
     int device = 0;
     cudaStream_t stream = nullptr, comm_stream = nullptr;
+    // Weight gradients (wgrad GEMMs, bias column sums, embedding-projection backward) feed nothing but the optimizer:
+    // they run on a side stream, concurrently with the dgrad -> GroupNorm -> dgrad critical path of backward (in the
+    // captured graph this is a parallel branch).  Both kinds of kernel are latency-bound on their own.
+    cudaStream_t side_stream = nullptr;
+    std::vector<cudaEvent_t> side_events;
+    size_t side_ev_next = 0;
+    bool use_side = true;
     // flat fp32 arenas in reference order
     size_t nparams = 0;
     float *params = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr;
@@ -135,6 +142,7 @@ struct UbTrainer {
         int launches;
         double flops;   // algorithmic FLOPs (tensor kernels) ...
         double bytes;   // ... or algorithmic bytes (memory-bound kernels)
+        int side;       // 0 = main stream, 1 = weight-gradient branch (side stream), 2 = join marker
     };
     std::vector<OpInfo> fwd_info, bwd_info;
     int launches_fwd = 0, launches_bwd = 0, launches_misc = 0;
@@ -229,13 +237,16 @@ struct Builder {
     void F(UbTrainer::Op op, int launches = 1, int kind = UB_KIND_SMALL, double flops = 0, double bytes = 0) {
         if (!real()) return;
         T->fwd_ops.push_back(std::move(op)), T->launches_fwd += launches;
-        T->fwd_info.push_back({kind, launches, flops, bytes});
+        T->fwd_info.push_back({kind, launches, flops, bytes, 0});
     }
-    void Bk(UbTrainer::Op op, int launches = 1, int kind = UB_KIND_SMALL, double flops = 0, double bytes = 0) {
+    void Bk(UbTrainer::Op op, int launches = 1, int kind = UB_KIND_SMALL, double flops = 0, double bytes = 0,
+            int side = 0) {
         if (!real()) return;
         T->bwd_ops.push_back(std::move(op)), T->launches_bwd += launches;
-        T->bwd_info.push_back({kind, launches, flops, bytes});
+        T->bwd_info.push_back({kind, launches, flops, bytes, side});
     }
+    // the main stream waits for everything the weight-gradient branch has been given so far
+    void join_side() { Bk([](cudaStream_t) {}, 0, UB_KIND_SMALL, 0, 0, 2); }
     double act_bytes(int C, int H, int W) const { return 2.0 * B * H * W * C; }
 
     struct Packed {
@@ -285,7 +296,7 @@ struct Builder {
             igemm_wgrad_launch(p, st);
             igemm_wgrad_reduce(p, dw, st);
         }, 2, UB_KIND_WGRAD, 2.0 * B * x.H * x.W * double(Cout) * Cin * ntaps,
-           act_bytes(Cin, x.H, x.W) + act_bytes(Cout, x.H, x.W) + 4.0 * ntaps * Cin * Cout);
+           act_bytes(Cin, x.H, x.W) + act_bytes(Cout, x.H, x.W) + 4.0 * ntaps * Cin * Cout, 1);
     }
 
     struct GN {
@@ -333,7 +344,8 @@ struct Builder {
         if (emb_hi <= emb_lo) return;
         UbTrainer* Tt = T;
         const int lo = emb_lo, n = emb_hi - emb_lo, Bn = B, Cemb = 4 * c.C_model;
-        Bk([=](cudaStream_t st) { small_linear_bwd(Tt->emb_table + lo, n, Bn, Tt->emb_max_oc, Cemb, st); }, 2);
+        Bk([=](cudaStream_t st) { small_linear_bwd(Tt->emb_table + lo, n, Bn, Tt->emb_max_oc, Cemb, st); }, 2,
+           UB_KIND_SMALL, 0, 0, 1);
         emb_lo = 1 << 30, emb_hi = -1;
     }
 
@@ -399,7 +411,7 @@ struct Builder {
             const int Bn = B;
             // bias / weight gradients of conv2 (and of the fused 1x1 skip conv)
             Bk([=](cudaStream_t st) { colsum(dout.p, dout.ld, npix, Cout, gb2, gbs, st); }, 1, UB_KIND_ELTWISE, 0,
-               act_bytes(Cout, H, W));
+               act_bytes(Cout, H, W), 1);
             wgrad_op(dout, a2, Cout, Cout, 9, G(w2));
             if (proj) wgrad_op(dout, x, C, Cout, 1, G(ws));
             {
@@ -474,7 +486,7 @@ struct Builder {
             const size_t npix = size_t(B) * H * W;
             float *gbp = G(bp), *gbq = G(bq);
             Bk([=](cudaStream_t st) { colsum(dout.p, dout.ld, npix, C, gbp, nullptr, st); }, 1, UB_KIND_ELTWISE, 0,
-               act_bytes(C, H, W));
+               act_bytes(C, H, W), 1);
             wgrad_op(dout, ao, C, C, 1, G(wp));
             {
                 ConvEpilogue ep;
@@ -495,7 +507,7 @@ struct Builder {
                              st);
             }, 2, UB_KIND_ATTN, 10.0 * B * NH * double(Tn) * Tn * HSz, act_bytes(8 * C, H, W));
             Bk([=](cudaStream_t st) { colsum(dqkv.p, dqkv.ld, npix, 3 * C, gbq, nullptr, st); }, 1, UB_KIND_ELTWISE, 0,
-               act_bytes(3 * C, H, W));
+               act_bytes(3 * C, H, W), 1);
             wgrad_op(dqkv, g, C, 3 * C, 1, G(wq));
             {
                 ConvEpilogue ep;
@@ -675,8 +687,8 @@ int Builder::build() {
             Bk([=](cudaStream_t st) {
                 conv_out_wgrad(ao.p, ao.ld, Tt->dout, Bn, Cin, Co, Hh, Ww, gw, gb, Tt->small_scratch,
                                Tt->small_scratch_floats, st);
-                conv_out_dgrad(Tt->dout, w, Bn, Cin, Co, Hh, Ww, dao.p, dao.ld, st);
-            }, 4);
+            }, 3, UB_KIND_SMALL, 0, 0, 1);
+            Bk([=](cudaStream_t st) { conv_out_dgrad(Tt->dout, w, Bn, Cin, Co, Hh, Ww, dao.p, dao.ld, st); }, 1);
             gn_bwd(g, hx, dao, 1, View{}, dh, nullptr);
             return dh;
         };
@@ -725,12 +737,14 @@ int Builder::build() {
         g = nd.bwd(g);
         while (cut_i < cuts.size() && nd.param_begin <= cuts[cut_i] && nd.param_begin > time_mlp_end) {
             emb_flush();
+            join_side();
             flush_bucket(nd.param_begin, flushed_hi);
             flushed_hi = nd.param_begin;
             while (cut_i < cuts.size() && cuts[cut_i] >= nd.param_begin) ++cut_i;
         }
     }
     emb_flush();
+    join_side();
     // time MLP backward (needs the complete d_embact), then the last bucket
     Bk([=](cudaStream_t st) {
         dsilu_mul(Tt->d_embact, Tt->emb, Tt->demb, size_t(Bn) * Cemb, st);
@@ -851,6 +865,10 @@ extern "C" int ub_trainer_create(UbTrainer** out, const UbConfig* cfg, int devic
     t->zero_base = t->zarena.base, t->zero_bytes = zero_bytes;
     cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&t->comm_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&t->side_stream, cudaStreamNonBlocking);
+    t->side_events.resize(512);
+    for (auto& ev : t->side_events) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (const char* e = getenv("UB_NO_SIDE_STREAM")) t->use_side = atoi(e) == 0;
     cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming);
     t->bucket_events.resize(16);
     for (auto& ev : t->bucket_events) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
@@ -913,6 +931,8 @@ extern "C" void ub_trainer_destroy(UbTrainer* t) {
     if (t->ev_join) cudaEventDestroy(t->ev_join);
     if (t->stream) cudaStreamDestroy(t->stream);
     if (t->comm_stream) cudaStreamDestroy(t->comm_stream);
+    if (t->side_stream) cudaStreamDestroy(t->side_stream);
+    for (auto ev : t->side_events) cudaEventDestroy(ev);
     delete t;
 }
 
@@ -933,9 +953,26 @@ static void enqueue_step(UbTrainer* t, const StepOpts& o, cudaStream_t st) {
     static const bool debug_sync = getenv("UB_DEBUG_SYNC") != nullptr;  // eager runs only: find the faulting op
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (debug_sync) cudaStreamIsCapturing(st, &cap);
+    bool side_dirty = false;
+    auto next_event = [&]() { return t->side_events[t->side_ev_next++ % t->side_events.size()]; };
     auto run = [&](std::vector<UbTrainer::Op>& ops, std::vector<UbTrainer::OpInfo>& info, const char* what) {
         for (size_t i = 0; i < ops.size(); ++i) {
-            ops[i](st);
+            if (info[i].side == 1 && t->use_side) {  // fork: the branch sees everything enqueued on main so far
+                cudaEvent_t ev = next_event();
+                cudaEventRecord(ev, st);
+                cudaStreamWaitEvent(t->side_stream, ev, 0);
+                ops[i](t->side_stream);
+                side_dirty = true;
+            } else if (info[i].side == 2) {
+                if (side_dirty) {
+                    cudaEvent_t ev = next_event();
+                    cudaEventRecord(ev, t->side_stream);
+                    cudaStreamWaitEvent(st, ev, 0);
+                    side_dirty = false;
+                }
+            } else {
+                ops[i](st);
+            }
             if (debug_sync && cap == cudaStreamCaptureStatusNone) {
                 cudaError_t e = cudaStreamSynchronize(st);
                 if (e == cudaSuccess) e = cudaGetLastError();
@@ -949,6 +986,11 @@ static void enqueue_step(UbTrainer* t, const StepOpts& o, cudaStream_t st) {
     };
     run(t->fwd_ops, t->fwd_info, "forward");
     run(t->bwd_ops, t->bwd_info, "backward");
+    if (side_dirty) {  // (the tape ends with a join; this only guards against a tape that forgot it)
+        cudaEvent_t ev = next_event();
+        cudaEventRecord(ev, t->side_stream);
+        cudaStreamWaitEvent(st, ev, 0);
+    }
     if (o.update) {
         adamw_step(t->params, t->grads, t->m, t->v, t->nparams, o.lr, o.b1, o.b2, o.eps, o.wd, 1.f / float(t->world),
                    t->step_dev, st);
