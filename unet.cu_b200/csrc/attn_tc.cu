@@ -17,8 +17,8 @@
 // The PV-type MMAs use N = 64 (both heads' channels of the MN-major operand) and keep the 32 columns of the current
 // head: the wasted half costs 16 tensor cycles per MMA and saves a second descriptor mode.
 //
-// Warp roles: warp 0 = TMA + MMA issue (one elected lane) + TMEM allocator; warps 1-4 = row threads (TMEM lane =
-// row).  mbarriers: load -> s (accumulators ready) -> p (operand written to smem) -> o (second MMA done).
+// Warp roles: warp 0 = TMA + MMA issue (one elected lane) + TMEM allocator; warps 1-8 = row threads (TMEM lane =
+// row; the two warps of a lane quadrant split the columns of every chunk).  mbarriers: load -> s (accumulators ready) -> p (operand written to smem) -> o (second MMA done).
 #include "attn_tc.cuh"
 #include "ptx.cuh"
 
@@ -34,10 +34,16 @@ EncodeTiledFn igemm_encode_fn();
 
 namespace {
 
-constexpr int kThreads = 160;
+constexpr int kThreads = 288;     // warp 0: TMA + MMA issue; warps 1-8: row threads, two warps per TMEM lane quadrant
+constexpr int kRowThreads = 256;  // (the two warps of a quadrant split the columns of every chunk)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr int HS = 32;
 
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // byte offset of the 16-byte chunk `c16` (0..7) of row r inside a [rows][128 B] SWIZZLE_128B tile
@@ -92,16 +98,19 @@ __device__ __forceinline__ Tile make_tile(const AttnTcParams& p) {
     }
     return t;
 }
-// column c (tile-local) is visible to row r (tile-local) iff both lie in the same image (T is a power of two)
-__device__ __forceinline__ bool same_image(const AttnTcParams& p, const Tile& t, int r, int c) {
-    return p.T >= 128 ? true : (r >> p.tshift) == (c >> p.tshift);
+// column c (tile-local) is visible to row r (tile-local) iff both lie in the same image (T is a power of two);
+// MASK is false when a tile lies inside one image (T >= 128)
+template <bool MASK>
+__device__ __forceinline__ bool same_image(const AttnTcParams& p, int r, int c) {
+    if constexpr (MASK) return (r >> p.tshift) == (c >> p.tshift);
+    return true;
 }
 
 __device__ __forceinline__ void prologue(Smem* sm, uint32_t ncols_tmem, int warp, int lane) {
     if (warp == 0 && lane == 0) {
         mbar_init(&sm->bar_load, 1);
         mbar_init(&sm->bar_s, 1);
-        mbar_init(&sm->bar_p, 128);
+        mbar_init(&sm->bar_p, kRowThreads);
         mbar_init(&sm->bar_o, 1);
         fence_mbar_init();
     }
@@ -117,6 +126,7 @@ __device__ __forceinline__ void prologue(Smem* sm, uint32_t ncols_tmem, int warp
 // =====================================================================================================
 // forward
 // =====================================================================================================
+template <bool MASK>
 __global__ void __launch_bounds__(kThreads) attn_tc_fwd_kernel(const __grid_constant__ AttnTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -125,7 +135,9 @@ __global__ void __launch_bounds__(kThreads) attn_tc_fwd_kernel(const __grid_cons
     uint8_t* sK = sQ + 16384;                 // [ncols][128 B]
     uint8_t* sV = sK + size_t(t.ncols) * 128; // [ncols][128 B]
     uint8_t* sP = sV + size_t(t.ncols) * 128; // [ncols/64][128][128 B]
-    Smem* sm = reinterpret_cast<Smem*>(sP + size_t(t.ncols) * 256);
+    float* sx = reinterpret_cast<float*>(sP + size_t(t.ncols) * 256);  // [2 heads][2 halves][128] partial row max
+    float* sl = sx + 512;                                              // [2 heads][2 halves][128] partial row sum
+    Smem* sm = reinterpret_cast<Smem*>(sl + 512);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int C = p.NH * HS;
     const uint32_t tm_cols = t.ncols > 128 ? 512 : 256;
@@ -164,7 +176,7 @@ __global__ void __launch_bounds__(kThreads) attn_tc_fwd_kernel(const __grid_cons
             }
         }
     } else {
-        const int q = warp & 3;
+        const int q = warp & 3, half = (warp - 1) >> 2;
         const int r = q * 32 + lane;
         const int gr = t.row0 + r;
         const bool rvalid = gr < p.B * p.T;
@@ -174,24 +186,27 @@ __global__ void __launch_bounds__(kThreads) attn_tc_fwd_kernel(const __grid_cons
             mbar_wait(&sm->bar_s, h);
             tc_fence_after();
             float m = -1e30f;
-            for (int c0 = 0; c0 < t.ncols; c0 += 32) {
+            for (int c0 = 32 * half; c0 < t.ncols; c0 += 64) {
                 uint32_t v[32];
                 tmem_ld32(trow + c0, v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                    if (same_image(p, t, r, c0 + j)) m = fmaxf(m, __uint_as_float(v[j]));
+                    if (same_image<MASK>(p, r, c0 + j)) m = fmaxf(m, __uint_as_float(v[j]));
             }
+            sx[(h * 2 + half) * 128 + r] = m;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            m = fmaxf(m, sx[(h * 2 + (half ^ 1)) * 128 + r]);
             const float mc = m * c;
             float l = 0.f;
-            for (int c0 = 0; c0 < t.ncols; c0 += 32) {
+            for (int c0 = 32 * half; c0 < t.ncols; c0 += 64) {
                 uint32_t v[32];
                 tmem_ld32(trow + c0, v);
                 tmem_ld_wait();
                 float pv[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    float e = same_image(p, t, r, c0 + j) ? exp2f(fmaf(__uint_as_float(v[j]), c, -mc)) : 0.f;
+                    float e = same_image<MASK>(p, r, c0 + j) ? ex2(fmaf(__uint_as_float(v[j]), c, -mc)) : 0.f;
                     // accumulate the sum of what the tensor core will actually multiply (bf16-rounded)
                     e = __bfloat162float(__float2bfloat16(e));
                     pv[j] = e;
@@ -199,28 +214,32 @@ __global__ void __launch_bounds__(kThreads) attn_tc_fwd_kernel(const __grid_cons
                 }
                 store_row32(sP, r, c0, pv);
             }
+            sl[(h * 2 + half) * 128 + r] = l;
             fence_async_smem();
             tc_fence_before();
             mbar_arrive(&sm->bar_p);
             mbar_wait(&sm->bar_o, h);
             tc_fence_after();
-            uint32_t o[32];
-            tmem_ld32(trow + o_col + h * 32, o);
+            l += sl[(h * 2 + (half ^ 1)) * 128 + r];  // (ordered by the bar_p arrive / bar_o wait pair)
+            uint32_t o[16];
+            tmem_ld16(trow + o_col + h * 32 + half * 16, o);
             tmem_ld_wait();
             tc_fence_before();
             if (rvalid) {
                 const float inv = 1.f / l;
                 const int head = t.hp * 2 + h;
-                __nv_bfloat16* op = p.out + size_t(gr) * p.ldo + head * HS;
+                __nv_bfloat16* op = p.out + size_t(gr) * p.ldo + head * HS + half * 16;
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < 2; ++j)
                     reinterpret_cast<uint4*>(op)[j] = make_uint4(
                         pack2(__uint_as_float(o[8 * j]) * inv, __uint_as_float(o[8 * j + 1]) * inv),
                         pack2(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv),
                         pack2(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv),
                         pack2(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv));
-                const int b = gr / p.T, tt = gr % p.T;
-                p.lse[(size_t(b) * p.NH + head) * p.T + tt] = mc + log2f(l);
+                if (half == 0) {
+                    const int b = gr / p.T, tt = gr % p.T;
+                    p.lse[(size_t(b) * p.NH + head) * p.T + tt] = mc + log2f(l);
+                }
             }
         }
     }
@@ -232,6 +251,7 @@ __global__ void __launch_bounds__(kThreads) attn_tc_fwd_kernel(const __grid_cons
 // =====================================================================================================
 // backward, dQ (rows = queries)
 // =====================================================================================================
+template <bool MASK>
 __global__ void __launch_bounds__(kThreads) attn_tc_dq_kernel(const __grid_constant__ AttnTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -288,7 +308,7 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dq_kernel(const __grid_const
             }
         }
     } else {
-        const int q = warp & 3;
+        const int q = warp & 3, half = (warp - 1) >> 2;
         const int r = q * 32 + lane;
         const int gr = t.row0 + r;
         const bool rvalid = gr < p.B * p.T;
@@ -315,7 +335,7 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dq_kernel(const __grid_const
                 }
                 Dv[h] = d;
                 Lv[h] = p.lse[(size_t(b) * p.NH + head) * p.T + tt];
-                p.dsum[(size_t(b) * p.NH + head) * p.T + tt] = d;
+                if (half == 0) p.dsum[(size_t(b) * p.NH + head) * p.T + tt] = d;
             }
         }
         int it = 0;
@@ -324,7 +344,7 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dq_kernel(const __grid_const
                 mbar_wait(&sm->bar_s, it & 1);
                 tc_fence_after();
                 if (it > 0) mbar_wait(&sm->bar_o, (it - 1) & 1);  // sdS is free again
-                for (int c0 = 0; c0 < 128; c0 += 32) {
+                for (int c0 = 32 * half; c0 < 128; c0 += 64) {
                     uint32_t s[32], d[32];
                     tmem_ld32(trow + c0, s);
                     tmem_ld32(trow + 128 + c0, d);
@@ -332,8 +352,8 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dq_kernel(const __grid_const
                     float ds[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const bool vis = rvalid && same_image(p, t, r, cc * 128 + c0 + j);
-                        const float pr = exp2f(fmaf(__uint_as_float(s[j]), c, -Lv[h]));
+                        const bool vis = rvalid && same_image<MASK>(p, r, cc * 128 + c0 + j);
+                        const float pr = ex2(fmaf(__uint_as_float(s[j]), c, -Lv[h]));
                         ds[j] = vis ? pr * (__uint_as_float(d[j]) - Dv[h]) : 0.f;
                     }
                     store_row32(sdS, r, c0, ds);
@@ -345,14 +365,14 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dq_kernel(const __grid_const
             // dQ of this head is complete when the last chunk's MMAs are
             mbar_wait(&sm->bar_o, (it - 1) & 1);
             tc_fence_after();
-            uint32_t o[32];
-            tmem_ld32(trow + 256 + h * 64 + h * 32, o);
+            uint32_t o[16];
+            tmem_ld16(trow + 256 + h * 64 + h * 32 + half * 16, o);
             tmem_ld_wait();
             tc_fence_before();
             if (rvalid) {
-                __nv_bfloat16* op = p.dqkv + size_t(gr) * p.ldd + (t.hp * 2 + h) * HS;
+                __nv_bfloat16* op = p.dqkv + size_t(gr) * p.ldd + (t.hp * 2 + h) * HS + half * 16;
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < 2; ++j)
                     reinterpret_cast<uint4*>(op)[j] = make_uint4(
                         pack2(__uint_as_float(o[8 * j]) * scale, __uint_as_float(o[8 * j + 1]) * scale),
                         pack2(__uint_as_float(o[8 * j + 2]) * scale, __uint_as_float(o[8 * j + 3]) * scale),
@@ -369,6 +389,7 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dq_kernel(const __grid_const
 // =====================================================================================================
 // backward, dK and dV (rows = keys, columns = queries)
 // =====================================================================================================
+template <bool MASK>
 __global__ void __launch_bounds__(kThreads) attn_tc_dkv_kernel(const __grid_constant__ AttnTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -432,7 +453,7 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dkv_kernel(const __grid_cons
             }
         }
     } else {
-        const int q = warp & 3;
+        const int q = warp & 3, half = (warp - 1) >> 2;
         const int r = q * 32 + lane;
         const int gr = t.row0 + r;
         const bool rvalid = gr < p.B * p.T;
@@ -440,7 +461,7 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dkv_kernel(const __grid_cons
         const float scale = rsqrtf(float(HS));
         const float c = scale * kLog2e;
         // logsumexp and D of every query column, both heads
-        for (int i = threadIdx.x - 32; i < 2 * t.ncols; i += 128) {
+        for (int i = threadIdx.x - 32; i < 2 * t.ncols; i += kRowThreads) {
             const int h = i / t.ncols, col = i % t.ncols;
             const int gq = t.col0 + col;
             float L = 0.f, D = 0.f;
@@ -450,14 +471,14 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dkv_kernel(const __grid_cons
             }
             sL[h * 256 + col] = L, sD[h * 256 + col] = D;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         int it = 0;
         for (int h = 0; h < 2; ++h) {
             for (int cc = 0; cc < nchunk; ++cc, ++it) {
                 mbar_wait(&sm->bar_s, it & 1);
                 tc_fence_after();
                 if (it > 0) mbar_wait(&sm->bar_o, (it - 1) & 1);  // sPt / sdSt are free again
-                for (int c0 = 0; c0 < 128; c0 += 32) {
+                for (int c0 = 32 * half; c0 < 128; c0 += 64) {
                     uint32_t s[32], d[32];
                     tmem_ld32(trow + c0, s);
                     tmem_ld32(trow + 128 + c0, d);
@@ -468,8 +489,8 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dkv_kernel(const __grid_cons
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int col = cc * 128 + c0 + j;
-                        const bool vis = rvalid && same_image(p, t, r, col) && (t.col0 + col < p.B * p.T);
-                        const float pr = vis ? exp2f(fmaf(__uint_as_float(s[j]), c, -Lp[j])) : 0.f;
+                        const bool vis = rvalid && same_image<MASK>(p, r, col) && (t.col0 + col < p.B * p.T);
+                        const float pr = vis ? ex2(fmaf(__uint_as_float(s[j]), c, -Lp[j])) : 0.f;
                         pt[j] = pr;
                         ds[j] = pr * (__uint_as_float(d[j]) - Dp[j]);
                     }
@@ -482,16 +503,16 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dkv_kernel(const __grid_cons
             }
             mbar_wait(&sm->bar_o, (it - 1) & 1);
             tc_fence_after();
-            uint32_t dk[32], dv[32];
-            tmem_ld32(trow + 256 + h * 64 + h * 32, dk);
-            tmem_ld32(trow + 384 + h * 64 + h * 32, dv);
+            uint32_t dk[16], dv[16];
+            tmem_ld16(trow + 256 + h * 64 + h * 32 + half * 16, dk);
+            tmem_ld16(trow + 384 + h * 64 + h * 32 + half * 16, dv);
             tmem_ld_wait();
             tc_fence_before();
             if (rvalid) {
-                __nv_bfloat16* kp = p.dqkv + size_t(gr) * p.ldd + C + (t.hp * 2 + h) * HS;
-                __nv_bfloat16* vp = p.dqkv + size_t(gr) * p.ldd + 2 * C + (t.hp * 2 + h) * HS;
+                __nv_bfloat16* kp = p.dqkv + size_t(gr) * p.ldd + C + (t.hp * 2 + h) * HS + half * 16;
+                __nv_bfloat16* vp = p.dqkv + size_t(gr) * p.ldd + 2 * C + (t.hp * 2 + h) * HS + half * 16;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < 2; ++j) {
                     reinterpret_cast<uint4*>(kp)[j] = make_uint4(
                         pack2(__uint_as_float(dk[8 * j]) * scale, __uint_as_float(dk[8 * j + 1]) * scale),
                         pack2(__uint_as_float(dk[8 * j + 2]) * scale, __uint_as_float(dk[8 * j + 3]) * scale),
@@ -525,7 +546,7 @@ int make_map_2d(CUtensorMap* m, const __nv_bfloat16* base, int cols, int rows, i
     return r == CUDA_SUCCESS ? 0 : -12;
 }
 
-size_t smem_fwd(int ncols) { return 1024 + 16384 + size_t(ncols) * 512 + 256; }
+size_t smem_fwd(int ncols) { return 1024 + 16384 + size_t(ncols) * 512 + 4096 + 256; }
 size_t smem_dq(int ncols) { return 1024 + 32768 + size_t(ncols) * 256 + 32768 + 256; }
 size_t smem_dkv(int ncols) { return 1024 + 32768 + size_t(ncols) * 256 + 65536 + 4096 + 256; }
 
@@ -539,9 +560,12 @@ bool attn_tc_supported(int T, int NH, int HSz) {
 void attn_tc_init() {
     static bool done = false;
     if (done) return;
-    cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_fwd(256)));
-    cudaFuncSetAttribute(attn_tc_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_dq(256)));
-    cudaFuncSetAttribute(attn_tc_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_dkv(256)));
+    cudaFuncSetAttribute(attn_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_fwd(256)));
+    cudaFuncSetAttribute(attn_tc_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_dq(256)));
+    cudaFuncSetAttribute(attn_tc_dkv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_dkv(256)));
+    cudaFuncSetAttribute(attn_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_fwd(128)));
+    cudaFuncSetAttribute(attn_tc_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_dq(128)));
+    cudaFuncSetAttribute(attn_tc_dkv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_dkv(128)));
     done = true;
 }
 
@@ -568,14 +592,22 @@ static int attn_ncols(const AttnTcParams& p) { return p.T >= 128 ? p.T : 128; }
 
 int attn_tc_fwd(const AttnTcParams& p, cudaStream_t st) {
     attn_tc_init();
-    attn_tc_fwd_kernel<<<attn_grid(p), kThreads, smem_fwd(attn_ncols(p)), st>>>(p);
+    if (p.T >= 128)
+        attn_tc_fwd_kernel<false><<<attn_grid(p), kThreads, smem_fwd(attn_ncols(p)), st>>>(p);
+    else
+        attn_tc_fwd_kernel<true><<<attn_grid(p), kThreads, smem_fwd(attn_ncols(p)), st>>>(p);
     return int(cudaGetLastError());
 }
 
 int attn_tc_bwd(const AttnTcParams& p, cudaStream_t st) {
     attn_tc_init();
-    attn_tc_dq_kernel<<<attn_grid(p), kThreads, smem_dq(attn_ncols(p)), st>>>(p);
-    attn_tc_dkv_kernel<<<attn_grid(p), kThreads, smem_dkv(attn_ncols(p)), st>>>(p);
+    if (p.T >= 128) {
+        attn_tc_dq_kernel<false><<<attn_grid(p), kThreads, smem_dq(attn_ncols(p)), st>>>(p);
+        attn_tc_dkv_kernel<false><<<attn_grid(p), kThreads, smem_dkv(attn_ncols(p)), st>>>(p);
+    } else {
+        attn_tc_dq_kernel<true><<<attn_grid(p), kThreads, smem_dq(attn_ncols(p)), st>>>(p);
+        attn_tc_dkv_kernel<true><<<attn_grid(p), kThreads, smem_dkv(attn_ncols(p)), st>>>(p);
+    }
     return int(cudaGetLastError());
 }
 

@@ -13,6 +13,7 @@
 #include "ptx.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace ub {
@@ -560,9 +561,11 @@ int igemm_wgrad_plan(IgemmWgradParams* p, const __nv_bfloat16* dy, int ldy, cons
     const int a_atoms = p->MO / 64, b_atoms = p->NC / 64;
     p->stage_bytes = uint32_t(a_atoms + p->TC * b_atoms) * 8192u;
     p->tx_bytes = p->stage_bytes;
-    int stages = int((200u * 1024u) / p->stage_bytes);
+    static const unsigned smem_kb = getenv("UB_WGRAD_SMEM_KB") ? unsigned(atoi(getenv("UB_WGRAD_SMEM_KB"))) : 96u;
+    int stages = int((smem_kb * 1024u) / p->stage_bytes);
+    if (stages < 2) stages = 2;
     if (stages > kMaxStages) stages = kMaxStages;
-    if (stages < 2) return -3;
+    if (size_t(stages) * p->stage_bytes > 220u * 1024u) return -3;
     p->stages = stages;
     const int ktiles = p->tiles_w * p->tiles_h * p->tiles_b;
     const int base_ctas = (Cout / p->MO) * (Cin / p->NC) * (ntaps / p->TC);

@@ -285,8 +285,9 @@ struct Builder {
     void wgrad_op(View dy, View x, int Cin, int Cout, int ntaps, float* dw) {
         if (!real()) return;
         IgemmWgradParams p;
+        static const int wg_sms = getenv("UB_WGRAD_SMS") ? atoi(getenv("UB_WGRAD_SMS")) : 148;
         int r = igemm_wgrad_plan(&p, dy.p, dy.ld, x.p, x.ld, B, x.H, x.W, Cin, Cout, ntaps, T->wg_partial, T->wg_cap,
-                                 148);
+                                 wg_sms);
         if (r) {
             set_err("igemm_wgrad_plan failed (%d) for %dx%d %d->%d", r, x.H, x.W, Cin, Cout);
             plan_errors++;
