@@ -20,6 +20,7 @@
 // Warp roles: warp 0 = TMA + MMA issue (one elected lane) + TMEM allocator; warps 1-8 = row threads (TMEM lane =
 // row; the two warps of a lane quadrant split the columns of every chunk).  mbarriers: load -> s (accumulators ready) -> p (operand written to smem) -> o (second MMA done).
 #include "attn_tc.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 #include <cstdio>
@@ -107,6 +108,7 @@ __device__ __forceinline__ bool same_image(const AttnTcParams& p, int r, int c) 
 }
 
 __device__ __forceinline__ void prologue(Smem* sm, uint32_t ncols_tmem, int warp, int lane) {
+    pdl_trigger();
     if (warp == 0 && lane == 0) {
         mbar_init(&sm->bar_load, 1);
         mbar_init(&sm->bar_s, 1);
@@ -121,6 +123,7 @@ __device__ __forceinline__ void prologue(Smem* sm, uint32_t ncols_tmem, int warp
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();  // the prologue touched only shared memory and TMEM
 }
 
 // =====================================================================================================
@@ -593,20 +596,20 @@ static int attn_ncols(const AttnTcParams& p) { return p.T >= 128 ? p.T : 128; }
 int attn_tc_fwd(const AttnTcParams& p, cudaStream_t st) {
     attn_tc_init();
     if (p.T >= 128)
-        attn_tc_fwd_kernel<false><<<attn_grid(p), kThreads, smem_fwd(attn_ncols(p)), st>>>(p);
+        launch_pdl(attn_tc_fwd_kernel<false>, dim3(attn_grid(p)), dim3(kThreads), smem_fwd(attn_ncols(p)), st, p);
     else
-        attn_tc_fwd_kernel<true><<<attn_grid(p), kThreads, smem_fwd(attn_ncols(p)), st>>>(p);
+        launch_pdl(attn_tc_fwd_kernel<true>, dim3(attn_grid(p)), dim3(kThreads), smem_fwd(attn_ncols(p)), st, p);
     return int(cudaGetLastError());
 }
 
 int attn_tc_bwd(const AttnTcParams& p, cudaStream_t st) {
     attn_tc_init();
     if (p.T >= 128) {
-        attn_tc_dq_kernel<false><<<attn_grid(p), kThreads, smem_dq(attn_ncols(p)), st>>>(p);
-        attn_tc_dkv_kernel<false><<<attn_grid(p), kThreads, smem_dkv(attn_ncols(p)), st>>>(p);
+        launch_pdl(attn_tc_dq_kernel<false>, dim3(attn_grid(p)), dim3(kThreads), smem_dq(attn_ncols(p)), st, p);
+        launch_pdl(attn_tc_dkv_kernel<false>, dim3(attn_grid(p)), dim3(kThreads), smem_dkv(attn_ncols(p)), st, p);
     } else {
-        attn_tc_dq_kernel<true><<<attn_grid(p), kThreads, smem_dq(attn_ncols(p)), st>>>(p);
-        attn_tc_dkv_kernel<true><<<attn_grid(p), kThreads, smem_dkv(attn_ncols(p)), st>>>(p);
+        launch_pdl(attn_tc_dq_kernel<true>, dim3(attn_grid(p)), dim3(kThreads), smem_dq(attn_ncols(p)), st, p);
+        launch_pdl(attn_tc_dkv_kernel<true>, dim3(attn_grid(p)), dim3(kThreads), smem_dkv(attn_ncols(p)), st, p);
     }
     return int(cudaGetLastError());
 }

@@ -10,6 +10,7 @@
 // :1132-1174 (dx_backward), :2468-2547 (dweight_dbias_backward1), :1365-1393 (dweight_reduce_kernel).
 #include "epilogue.cuh"
 #include "igemm.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 #include <cstdio>
@@ -27,6 +28,7 @@ static constexpr int kEpiThreads = kConvThreads - 64;
 // fprop / dgrad / 1x1 / linear
 // =====================================================================================================
 __global__ void __launch_bounds__(kConvThreads, 2) igemm_conv_kernel(const __grid_constant__ IgemmConvParams p) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + size_t(p.stages) * p.stage_bytes);
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) igemm_conv_kernel(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // everything above touched only kernel parameters, shared memory and TMEM
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
@@ -174,6 +177,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) igemm_conv_kernel(const __gri
 // wgrad: both operands MN-major (the contraction index is the pixel index, channels are contiguous)
 // =====================================================================================================
 __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid_constant__ IgemmWgradParams p) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + size_t(p.stages) * p.stage_bytes);
@@ -214,6 +218,7 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // everything above touched only kernel parameters, shared memory and TMEM
 
     if (warp == 0) {
         if (lane == 0) {
@@ -316,6 +321,7 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial,
                                                            float* __restrict__ dweight, int nsplit, int ntaps,
                                                            size_t n) {
+    pdl_entry();
     __shared__ float red[8][33];
     const int el = threadIdx.x & 31, lane8 = threadIdx.x >> 5;
     const size_t e = size_t(blockIdx.x) * 32 + el;
@@ -527,7 +533,7 @@ int igemm_conv_launch(const IgemmConvParams& p, cudaStream_t st) {
     const size_t smem = size_t(p.stages) * p.stage_bytes + 1024 + kBarrierBytes +
                         size_t(p.ncomb + 4 * p.ngimg + p.nred) * p.BN * sizeof(float);
     dim3 grid(p.tiles_w * p.tiles_h * p.tiles_b, p.Cout / p.BN);
-    igemm_conv_kernel<<<grid, kConvThreads, smem, st>>>(p);
+    launch_pdl(igemm_conv_kernel, dim3(grid), dim3(kConvThreads), smem, st, p);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)  // a failed launch must never pass silently (the output would simply be stale)
         fprintf(stderr, "[unet_b200] igemm_conv launch failed: %s (grid %u x %u, smem %zu, BN %d, stages %d)\n",
@@ -588,13 +594,13 @@ int igemm_wgrad_launch(const IgemmWgradParams& p, cudaStream_t st) {
     igemm_init();
     const size_t smem = size_t(p.stages) * p.stage_bytes + 1024 + kBarrierBytes;
     dim3 grid((p.Cout / p.MO) * (p.Cin / p.NC), p.ntaps / p.TC, p.nsplit);
-    igemm_wgrad_kernel<<<grid, kWgradThreads, smem, st>>>(p);
+    launch_pdl(igemm_wgrad_kernel, dim3(grid), dim3(kWgradThreads), smem, st, p);
     return int(cudaGetLastError());
 }
 
 int igemm_wgrad_reduce(const IgemmWgradParams& p, float* dweight, cudaStream_t st) {
     const size_t n = size_t(p.Cout) * p.Cin;
-    wgrad_reduce_kernel<<<dim3(unsigned((n + 31) / 32), p.ntaps), 256, 0, st>>>(p.partial, dweight, p.nsplit, p.ntaps,
+    launch_pdl(wgrad_reduce_kernel, dim3(dim3(unsigned((n + 31) / 32), p.ntaps)), dim3(256), 0, st, p.partial, dweight, p.nsplit, p.ntaps,
                                                                                n);
     return int(cudaGetLastError());
 }

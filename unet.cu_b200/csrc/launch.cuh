@@ -1,0 +1,52 @@
+// Programmatic dependent launch (PDL) for the training path.  Every kernel of the step is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's CTAs may become resident and run their
+// prologue (mbarrier init, TMEM allocation, descriptor prefetch, index math) while the previous kernel drains, and
+// block in pdl_wait() until the previous grid has completed and its writes are visible.  In the captured step graph
+// the kernel -> kernel edges become programmatic edges, which removes the ~1-2 us launch gap between the ~500 small
+// kernels of a step.
+//
+// Rules every kernel follows: (1) pdl_trigger() then pdl_wait() are executed by EVERY thread before its first access
+// to global memory that an earlier kernel may have written, and before any early return; (2) nothing before
+// pdl_wait() touches such memory (kernel parameters, including __grid_constant__ tensor maps, are fine).
+// Launched without the attribute (layer API, tools) both instructions are no-ops.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+#include <utility>
+
+namespace ub {
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifndef UB_PDL_EARLY_TRIGGER
+#define UB_PDL_EARLY_TRIGGER 0
+#endif
+__device__ __forceinline__ void pdl_trigger() {
+#if UB_PDL_EARLY_TRIGGER
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+// the usual kernel entry: let the dependent grid start early, then wait for our own prerequisite
+__device__ __forceinline__ void pdl_entry() {
+    pdl_trigger();
+    pdl_wait();
+}
+
+inline bool pdl_enabled() {
+    static const bool on = !(getenv("UB_NO_PDL") && atoi(getenv("UB_NO_PDL")) != 0);
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at, cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+}  // namespace ub

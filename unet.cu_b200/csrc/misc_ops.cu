@@ -1,5 +1,6 @@
 // See misc_ops.cuh.
 #include "misc_ops.cuh"
+#include "launch.cuh"
 
 #include <cstdio>
 
@@ -47,6 +48,7 @@ __device__ __forceinline__ void stage_rows(const bf16* src, int ld, int n, float
 
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ qkv, int ld, int T, int NH,
                                                        bf16* __restrict__ out, int ldo, float* __restrict__ lse) {
+    pdl_entry();
     extern __shared__ float smf[];  // K [KT][32], V [KT][32]
     float* sK = smf;
     float* sV = smf + KT * HS;
@@ -125,6 +127,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const bf16* __restrict
                                                           const float* __restrict__ lse, int T, int NH,
                                                           bf16* __restrict__ dqkv, int ldd,
                                                           float* __restrict__ dsum) {
+    pdl_entry();
     extern __shared__ float smf[];
     float* sK = smf;
     float* sV = smf + KT * HS;
@@ -196,6 +199,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const bf16* __restric
                                                            const float* __restrict__ lse,
                                                            const float* __restrict__ dsum, int T, int NH,
                                                            bf16* __restrict__ dqkv, int ldd) {
+    pdl_entry();
     extern __shared__ float smf[];  // Q(scaled) [KT][32], dO [KT][32], lse [KT], D [KT]
     float* sQ = smf;
     float* sdO = smf + KT * HS;
@@ -284,7 +288,7 @@ int attn_fwd(const bf16* qkv, int ld, int B, int T, int NH, int HSz, bf16* out, 
     if (HSz != HS) return -20;
     attn_init();
     const int bt = attn_block_threads(T);
-    attn_fwd_kernel<<<dim3((T + bt - 1) / bt, NH, B), bt, 2 * KT * HS * 4, st>>>(qkv, ld, T, NH, out, ldo, lse);
+    launch_pdl(attn_fwd_kernel, dim3(dim3((T + bt - 1) / bt, NH, B)), dim3(bt), 2 * KT * HS * 4, st, qkv, ld, T, NH, out, ldo, lse);
     return int(cudaGetLastError());
 }
 
@@ -293,8 +297,8 @@ int attn_bwd(const bf16* qkv, int ld, const bf16* out, int ldo, const bf16* dout
     if (HSz != HS) return -20;
     const int bt = attn_block_threads(T);
     dim3 grid((T + bt - 1) / bt, NH, B);
-    attn_bwd_dq_kernel<<<grid, bt, 2 * KT * HS * 4, st>>>(qkv, ld, out, ldo, dout, lddo, lse, T, NH, dqkv, ldd, dsum);
-    attn_bwd_dkv_kernel<<<grid, bt, (2 * KT * HS + 2 * KT) * 4, st>>>(qkv, ld, dout, lddo, lse, dsum, T, NH, dqkv,
+    launch_pdl(attn_bwd_dq_kernel, dim3(grid), dim3(bt), 2 * KT * HS * 4, st, qkv, ld, out, ldo, dout, lddo, lse, T, NH, dqkv, ldd, dsum);
+    launch_pdl(attn_bwd_dkv_kernel, dim3(grid), dim3(bt), (2 * KT * HS + 2 * KT) * 4, st, qkv, ld, dout, lddo, lse, dsum, T, NH, dqkv,
                                                                         ldd);
     return int(cudaGetLastError());
 }
@@ -309,6 +313,7 @@ __device__ __forceinline__ float dsilu_f(float z) {
 }
 
 __global__ void small_linear_fwd_kernel(const SmallLinear* __restrict__ table, int N) {
+    pdl_entry();
     const SmallLinear e = table[blockIdx.y];
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -327,11 +332,12 @@ __global__ void small_linear_fwd_kernel(const SmallLinear* __restrict__ table, i
 }
 void small_linear_fwd(const SmallLinear* table_dev, int n_entries, int N, int max_oc, cudaStream_t st) {
     const int warps = N * max_oc;
-    small_linear_fwd_kernel<<<dim3((warps * 32 + 255) / 256, n_entries), 256, 0, st>>>(table_dev, N);
+    launch_pdl(small_linear_fwd_kernel, dim3(dim3((warps * 32 + 255) / 256, n_entries)), dim3(256), 0, st, table_dev, N);
 }
 
 // dW[o][k] = sum_n dout[n][o] * act(inp[n][k]) ; db[o] = sum_n dout[n][o]
 __global__ void small_linear_bwd_w_kernel(const SmallLinear* __restrict__ table, int N) {
+    pdl_entry();
     const SmallLinear e = table[blockIdx.y];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= e.OC * e.C) return;
@@ -352,6 +358,7 @@ __global__ void small_linear_bwd_w_kernel(const SmallLinear* __restrict__ table,
 }
 // dinp[n][k] += sum_o dout[n][o] * W[o][k]; blockIdx.z walks chunks of 32 output channels
 __global__ void small_linear_bwd_x_kernel(const SmallLinear* __restrict__ table, int N) {
+    pdl_entry();
     const SmallLinear e = table[blockIdx.y];
     if (!e.dinp) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -365,31 +372,34 @@ __global__ void small_linear_bwd_x_kernel(const SmallLinear* __restrict__ table,
     atomicAdd(&e.dinp[i], s);
 }
 void small_linear_bwd(const SmallLinear* table_dev, int n_entries, int N, int max_oc, int max_c, cudaStream_t st) {
-    small_linear_bwd_w_kernel<<<dim3((max_oc * max_c + 255) / 256, n_entries), 256, 0, st>>>(table_dev, N);
-    small_linear_bwd_x_kernel<<<dim3((N * max_c + 255) / 256, n_entries, (max_oc + 31) / 32), 256, 0, st>>>(table_dev,
+    launch_pdl(small_linear_bwd_w_kernel, dim3(dim3((max_oc * max_c + 255) / 256, n_entries)), dim3(256), 0, st, table_dev, N);
+    launch_pdl(small_linear_bwd_x_kernel, dim3(dim3((N * max_c + 255) / 256, n_entries, (max_oc + 31) / 32)), dim3(256), 0, st, table_dev,
                                                                                                           N);
 }
 
 // out[i] = silu(x[i])
 __global__ void silu_f32_kernel(const float* __restrict__ x, float* __restrict__ out, size_t n) {
+    pdl_entry();
     const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) out[i] = silu_f(x[i]);
 }
 void silu_f32(const float* x, float* out, size_t n, cudaStream_t st) {
-    silu_f32_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(x, out, n);
+    launch_pdl(silu_f32_kernel, dim3(unsigned((n + 255) / 256)), dim3(256), 0, st, x, out, n);
 }
 
 __global__ void dsilu_mul_kernel(const float* __restrict__ dact, const float* __restrict__ pre, float* __restrict__ g,
                                  size_t n) {
+    pdl_entry();
     const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) g[i] = dact[i] * dsilu_f(pre[i]);
 }
 void dsilu_mul(const float* dact, const float* pre, float* g, size_t n, cudaStream_t st) {
-    dsilu_mul_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(dact, pre, g, n);
+    launch_pdl(dsilu_mul_kernel, dim3(unsigned((n + 255) / 256)), dim3(256), 0, st, dact, pre, g, n);
 }
 
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, int half, float log_mp,
                                           float* __restrict__ out) {
+    pdl_entry();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * half) return;
     const int b = i / half, j = i % half;
@@ -400,7 +410,7 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, in
 }
 void timestep_embedding(const float* t, int B, int dim, int max_period, float* out, cudaStream_t st) {
     const int half = dim / 2;
-    timestep_embedding_kernel<<<(B * half + 127) / 128, 128, 0, st>>>(t, B, half, logf(float(max_period)), out);
+    launch_pdl(timestep_embedding_kernel, dim3((B * half + 127) / 128), dim3(128), 0, st, t, B, half, logf(float(max_period)), out);
 }
 
 // =====================================================================================================
@@ -422,6 +432,7 @@ __device__ __forceinline__ float u01(uint32_t x) { return (float(x >> 8) + 0.5f)
 
 __global__ void diffusion_t_kernel(int B, int n_timesteps, uint64_t seed, const int* __restrict__ step_dev,
                                    float* __restrict__ t) {
+    pdl_entry();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const uint4 r = philox4x32_10(make_uint4(uint32_t(b), 0u, 0x7u, uint32_t(*step_dev)),
@@ -433,6 +444,7 @@ __global__ void diffusion_prepare_kernel(const float* __restrict__ x0, const flo
                                          uint64_t seed, const int* __restrict__ step_dev, int gen_noise,
                                          const float* __restrict__ t, float* __restrict__ noise,
                                          float* __restrict__ x_t) {
+    pdl_entry();
     const size_t i4 = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i4 >= total4) return;
     const size_t i = i4 * 4;
@@ -459,9 +471,9 @@ __global__ void diffusion_prepare_kernel(const float* __restrict__ x0, const flo
 void diffusion_prepare(const float* x0, const float* sqrt_ac, const float* sqrt_1mac, int B, size_t per_image,
                        int n_timesteps, uint64_t seed, const int* step_dev, int gen_t, int gen_noise, float* t,
                        float* noise, float* x_t, cudaStream_t st) {
-    if (gen_t) diffusion_t_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, n_timesteps, seed, step_dev, t);
+    if (gen_t) launch_pdl(diffusion_t_kernel, dim3((B + 127) / 128), dim3(128), 0, st, B, n_timesteps, seed, step_dev, t);
     const size_t total4 = size_t(B) * per_image / 4;
-    diffusion_prepare_kernel<<<unsigned((total4 + 255) / 256), 256, 0, st>>>(x0, sqrt_ac, sqrt_1mac, total4, per_image,
+    launch_pdl(diffusion_prepare_kernel, dim3(unsigned((total4 + 255) / 256)), dim3(256), 0, st, x0, sqrt_ac, sqrt_1mac, total4, per_image,
                                                                              seed, step_dev, gen_noise, t, noise, x_t);
 }
 
@@ -469,6 +481,7 @@ void diffusion_prepare(const float* x0, const float* sqrt_ac, const float* sqrt_
 // weight packing: 32x32 (o, c) tiles through smem so both packed layouts are written coalesced
 // =====================================================================================================
 __global__ void pack_weights_kernel(const PackEntry* __restrict__ table) {
+    pdl_entry();
     const PackEntry e = table[blockIdx.y];
     const int tiles_c = (e.Cin + 31) / 32, tiles_o = (e.Cout + 31) / 32;
     if (int(blockIdx.x) >= tiles_c * tiles_o) return;
@@ -502,7 +515,7 @@ __global__ void pack_weights_kernel(const PackEntry* __restrict__ table) {
     }
 }
 void pack_weights(const PackEntry* table_dev, int n_entries, int max_tiles, cudaStream_t st) {
-    pack_weights_kernel<<<dim3(max_tiles, n_entries), 256, 0, st>>>(table_dev);
+    launch_pdl(pack_weights_kernel, dim3(dim3(max_tiles, n_entries)), dim3(256), 0, st, table_dev);
 }
 
 // =====================================================================================================
@@ -511,6 +524,7 @@ void pack_weights(const PackEntry* table_dev, int n_entries, int max_tiles, cuda
 __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, size_t n4, size_t n, float lr, float b1, float b2, float eps,
                              float wd, float gscale, const int* __restrict__ step_dev) {
+    pdl_entry();
     const int t = *step_dev + 1;
     const float c1 = 1.f - powf(b1, float(t)), c2 = 1.f - powf(b2, float(t));
     const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -544,10 +558,11 @@ __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float
 void adamw_step(float* p, float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, float wd,
                 float grad_scale, const int* step_dev, cudaStream_t st) {
     const size_t n4 = n / 4;
-    adamw_kernel<<<unsigned((n4 + 1 + 255) / 256), 256, 0, st>>>(p, g, m, v, n4, n, lr, b1, b2, eps, wd, grad_scale,
+    launch_pdl(adamw_kernel, dim3(unsigned((n4 + 1 + 255) / 256)), dim3(256), 0, st, p, g, m, v, n4, n, lr, b1, b2, eps, wd, grad_scale,
                                                                 step_dev);
 }
-__global__ void increment_step_kernel(int* s) { *s += 1; }
-void increment_step(int* step_dev, cudaStream_t st) { increment_step_kernel<<<1, 1, 0, st>>>(step_dev); }
+__global__ void increment_step_kernel(int* s) {
+    pdl_entry(); *s += 1; }
+void increment_step(int* step_dev, cudaStream_t st) { launch_pdl(increment_step_kernel, dim3(1), dim3(1), 0, st, step_dev); }
 
 }  // namespace ub

@@ -2,6 +2,7 @@
 // Every kernel moves 16-byte vectors (8 bf16 channels) per thread, is coalesced along the channel axis and
 // sizes its grid to a few waves of the 148 SMs.
 #include "nhwc_ops.cuh"
+#include "launch.cuh"
 
 #include <cstdio>
 
@@ -89,6 +90,7 @@ static RowMap make_rowmap(int B, int HW, int C) {
 // ------------------------------------------------------------------------------------------------ GN stats
 __global__ void gn_stats_kernel(const bf16* __restrict__ x, int ldx, int HW, int C, int C8, int rows, int ppb,
                                 float* __restrict__ chsum) {
+    pdl_entry();
     extern __shared__ float sm[];  // [2][rows][C]
     const int b = blockIdx.y;
     const int j = threadIdx.x % C8, r = threadIdx.x / C8;
@@ -124,7 +126,7 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, int ldx, int HW, int
 
 void gn_stats(const bf16* x, int ldx, int B, int HW, int C, float* chsum, cudaStream_t st) {
     RowMap m = make_rowmap(B, HW, C);
-    gn_stats_kernel<<<dim3(m.nchunks, B), m.threads, 2 * size_t(m.rows) * C * sizeof(float), st>>>(x, ldx, HW, C, m.C8, m.rows, m.ppb,
+    launch_pdl(gn_stats_kernel, dim3(dim3(m.nchunks, B)), dim3(m.threads), 2 * size_t(m.rows) * C * sizeof(float), st, x, ldx, HW, C, m.C8, m.rows, m.ppb,
                                                                                    chsum);
 }
 
@@ -152,6 +154,7 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int ldx, const float
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C, int G,
                                 int silu, int C8, int rows, int ppb, bf16* __restrict__ y, int ldy,
                                 float* __restrict__ meanrstd) {
+    pdl_entry();
     extern __shared__ float sm[];  // sa[C], sb[C]
     float* sa = sm;
     float* sb = sm + C;
@@ -201,7 +204,7 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int ldx, const float
 void gn_apply(const bf16* x, int ldx, const float* chsum, const float* gamma, const float* beta, int B, int HW, int C,
               int G, int silu, bf16* y, int ldy, float* meanrstd, cudaStream_t st) {
     RowMap m = make_rowmap(B, HW, C);
-    gn_apply_kernel<<<dim3(m.nchunks, B), m.threads, 2 * C * sizeof(float), st>>>(
+    launch_pdl(gn_apply_kernel, dim3(dim3(m.nchunks, B)), dim3(m.threads), 2 * C * sizeof(float), st, 
         x, ldx, chsum, gamma, beta, HW, C, G, silu, m.C8, m.rows, m.ppb, y, ldy, meanrstd);
 }
 
@@ -210,6 +213,7 @@ __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ x, int ldx, const b
                                     const float* __restrict__ chsum, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, int HW, int C, int G, int silu, int C8, int rows,
                                     int ppb, float* __restrict__ S) {
+    pdl_entry();
     extern __shared__ float sm[];  // sa, sb, sr, smr : 4*C ; then scratch [2][rows][C]
     float *sa = sm, *sb = sm + C, *sr = sm + 2 * C, *smr = sm + 3 * C, *scr = sm + 4 * C;
     const int b = blockIdx.y;
@@ -267,7 +271,7 @@ __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ x, int ldx, const b
 void gn_bwd_stats(const bf16* x, int ldx, const bf16* dy, int lddy, const float* chsum, const float* gamma,
                   const float* beta, int B, int HW, int C, int G, int silu, float* S, cudaStream_t st) {
     RowMap m = make_rowmap(B, HW, C);
-    gn_bwd_stats_kernel<<<dim3(m.nchunks, B), m.threads, (4 + 2 * size_t(m.rows)) * C * sizeof(float), st>>>(
+    launch_pdl(gn_bwd_stats_kernel, dim3(dim3(m.nchunks, B)), dim3(m.threads), (4 + 2 * size_t(m.rows)) * C * sizeof(float), st, 
         x, ldx, dy, lddy, chsum, gamma, beta, HW, C, G, silu, m.C8, m.rows, m.ppb, S);
 }
 
@@ -277,6 +281,7 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ x, int ldx, const b
                                     int G, int silu, int C8, int rows, int ppb, const bf16* __restrict__ add_in,
                                     int ldadd, bf16* __restrict__ dx, int lddx, float* __restrict__ dgamma,
                                     float* __restrict__ dbeta, float* __restrict__ colsum_out) {
+    pdl_entry();
     // silu == 2: `dy` already holds dz = dL/d(gn(x)) (the producing dgrad conv applied silu' in its epilogue)
     extern __shared__ float sm[];  // sa, sb, sr, smr, sm1, sm2 : 6*C ; then scratch [rows][C]
     float *sa = sm, *sb = sm + C, *sr = sm + 2 * C, *smr = sm + 3 * C, *sm1 = sm + 4 * C, *sm2 = sm + 5 * C,
@@ -356,7 +361,7 @@ void gn_bwd_apply(const bf16* x, int ldx, const bf16* dy, int lddy, const float*
                   const float* gamma, const float* beta, int B, int HW, int C, int G, int silu, const bf16* add_in,
                   int ldadd, bf16* dx, int lddx, float* dgamma, float* dbeta, float* colsum_out, cudaStream_t st) {
     RowMap m = make_rowmap(B, HW, C);
-    gn_bwd_apply_kernel<<<dim3(m.nchunks, B), m.threads, (6 + size_t(m.rows)) * C * sizeof(float), st>>>(
+    launch_pdl(gn_bwd_apply_kernel, dim3(dim3(m.nchunks, B)), dim3(m.threads), (6 + size_t(m.rows)) * C * sizeof(float), st, 
         x, ldx, dy, lddy, chsum, S, gamma, beta, HW, C, G, silu, m.C8, m.rows, m.ppb, add_in, ldadd, dx, lddx, dgamma,
         dbeta, colsum_out);
 }
@@ -364,6 +369,7 @@ void gn_bwd_apply(const bf16* x, int ldx, const bf16* dy, int lddy, const float*
 // ------------------------------------------------------------------------------------------------ pooling etc.
 __global__ void avgpool2_fwd_kernel(const bf16* __restrict__ x, int ldx, int H, int W, int C8, size_t total,
                                     bf16* __restrict__ y, int ldy) {
+    pdl_entry();
     const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int j = int(i % C8);
@@ -387,11 +393,12 @@ __global__ void avgpool2_fwd_kernel(const bf16* __restrict__ x, int ldx, int H, 
 }
 void avgpool2_fwd(const bf16* x, int ldx, int B, int H, int W, int C, bf16* y, int ldy, cudaStream_t st) {
     const size_t total = size_t(B) * (H / 2) * (W / 2) * (C / 8);
-    avgpool2_fwd_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(x, ldx, H, W, C / 8, total, y, ldy);
+    launch_pdl(avgpool2_fwd_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), 0, st, x, ldx, H, W, C / 8, total, y, ldy);
 }
 
 __global__ void avgpool2_bwd_kernel(const bf16* __restrict__ dy, int lddy, int H, int W, int C8, size_t total,
                                     const bf16* __restrict__ add_in, int ldadd, bf16* __restrict__ dx, int lddx) {
+    pdl_entry();
     const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int j = int(i % C8);
@@ -414,7 +421,7 @@ __global__ void avgpool2_bwd_kernel(const bf16* __restrict__ dy, int lddy, int H
 void avgpool2_bwd(const bf16* dy, int lddy, int B, int H, int W, int C, const bf16* add_in, int ldadd, bf16* dx,
                   int lddx, cudaStream_t st) {
     const size_t total = size_t(B) * H * W * (C / 8);
-    avgpool2_bwd_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(dy, lddy, H, W, C / 8, total, add_in, ldadd,
+    launch_pdl(avgpool2_bwd_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), 0, st, dy, lddy, H, W, C / 8, total, add_in, ldadd,
                                                                       dx, lddx);
 }
 
@@ -422,6 +429,7 @@ __global__ void concat2_kernel(const bf16* __restrict__ a, int lda, int C1_8, in
                                int ldb, int C2_8, int H, int W, size_t total, bf16* __restrict__ out, int ldo,
                                const float* __restrict__ cs_a, const float* __restrict__ cs_b,
                                float* __restrict__ cs_out, size_t cs_total) {
+    pdl_entry();
     const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (cs_out && i < cs_total) {
         // GroupNorm statistics of the concatenation = the parts' per-(image, channel) sums side by side; a nearest
@@ -455,13 +463,14 @@ void concat2(const bf16* a, int lda, int C1, int up, const bf16* b, int ldb, int
     const size_t total = size_t(B) * H * W * ((C1 + C2) / 8);
     const size_t cs_total = size_t(B) * (C1 + C2) * 2;
     const size_t nthr = total > cs_total ? total : cs_total;
-    concat2_kernel<<<unsigned((nthr + 255) / 256), 256, 0, st>>>(a, lda, C1 / 8, up, b, ldb, C2 / 8, H, W, total, out,
+    launch_pdl(concat2_kernel, dim3(unsigned((nthr + 255) / 256)), dim3(256), 0, st, a, lda, C1 / 8, up, b, ldb, C2 / 8, H, W, total, out,
                                                                 ldo, cs_a, cs_b, (cs_a && cs_b) ? cs_out : nullptr,
                                                                 cs_total);
 }
 
 __global__ void upsample2_bwd_kernel(const bf16* __restrict__ dy, int lddy, int H, int W, int C8, size_t total,
                                      bf16* __restrict__ dx, int lddx) {
+    pdl_entry();
     const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int j = int(i % C8);
@@ -485,11 +494,12 @@ __global__ void upsample2_bwd_kernel(const bf16* __restrict__ dy, int lddy, int 
 }
 void upsample2_bwd(const bf16* dy, int lddy, int B, int H, int W, int C, bf16* dx, int lddx, cudaStream_t st) {
     const size_t total = size_t(B) * (H / 2) * (W / 2) * (C / 8);
-    upsample2_bwd_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(dy, lddy, H, W, C / 8, total, dx, lddx);
+    launch_pdl(upsample2_bwd_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), 0, st, dy, lddy, H, W, C / 8, total, dx, lddx);
 }
 
 __global__ void add2_kernel(const bf16* __restrict__ a, int lda, const bf16* __restrict__ b, int ldb, int C8,
                             size_t total, bf16* __restrict__ out, int ldo) {
+    pdl_entry();
     const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int j = int(i % C8);
@@ -503,11 +513,12 @@ __global__ void add2_kernel(const bf16* __restrict__ a, int lda, const bf16* __r
 }
 void add2(const bf16* a, int lda, const bf16* b, int ldb, size_t npix, int C, bf16* out, int ldo, cudaStream_t st) {
     const size_t total = npix * (C / 8);
-    add2_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(a, lda, b, ldb, C / 8, total, out, ldo);
+    launch_pdl(add2_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), 0, st, a, lda, b, ldb, C / 8, total, out, ldo);
 }
 
 __global__ void colsum_kernel(const bf16* __restrict__ x, int ldx, size_t npix, int C, int C8, int rows, size_t ppb,
                               float* __restrict__ out, float* __restrict__ out2) {
+    pdl_entry();
     extern __shared__ float sm[];  // [rows][C]
     const int j = threadIdx.x % C8, r = threadIdx.x / C8;
     float s[8];
@@ -546,7 +557,7 @@ void colsum(const bf16* x, int ldx, size_t npix, int C, float* out, float* out2,
     if (nblk > size_t(2 * kSMs)) nblk = 2 * kSMs;
     const size_t ppb = (npix + nblk - 1) / nblk;
     nblk = (npix + ppb - 1) / ppb;
-    colsum_kernel<<<unsigned(nblk), C8 * rows, size_t(rows) * C * sizeof(float), st>>>(x, ldx, npix, C, C8, rows, ppb, out, out2);
+    launch_pdl(colsum_kernel, dim3(unsigned(nblk)), dim3(C8 * rows), size_t(rows) * C * sizeof(float), st, x, ldx, npix, C, C8, rows, ppb, out, out2);
 }
 
 // ------------------------------------------------------------------------------------------------ 3-channel convs
@@ -556,6 +567,7 @@ void colsum(const bf16* x, int ldx, size_t npix, int C, float* out, float* out2,
 __global__ void smallc_conv_kernel(const float* __restrict__ xs, const float* __restrict__ w,
                                    const float* __restrict__ bias, int Cs, int Cb, int H, int W, int flip,
                                    size_t total, bf16* __restrict__ y, int ldy) {
+    pdl_entry();
     extern __shared__ float sw[];  // [Cs*9][Cb]
     for (int i = threadIdx.x; i < Cb * Cs * 9; i += blockDim.x) {
         const int cb = i % Cb, st = i / Cb;  // st = s*9 + tap
@@ -591,13 +603,13 @@ __global__ void smallc_conv_kernel(const float* __restrict__ xs, const float* __
 void conv_in_fwd(const float* x, const float* w, const float* b, int B, int Cin, int Cout, int H, int W, bf16* y,
                  int ldy, cudaStream_t st) {
     const size_t total = size_t(B) * H * W * (Cout / 8);
-    smallc_conv_kernel<<<unsigned((total + 255) / 256), 256, size_t(Cout) * Cin * 9 * sizeof(float), st>>>(
+    launch_pdl(smallc_conv_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), size_t(Cout) * Cin * 9 * sizeof(float), st, 
         x, w, b, Cin, Cout, H, W, 0, total, y, ldy);
 }
 void conv_out_dgrad(const float* dout, const float* w, int B, int Cin, int Cout, int H, int W, bf16* da, int ldda,
                     cudaStream_t st) {
     const size_t total = size_t(B) * H * W * (Cin / 8);
-    smallc_conv_kernel<<<unsigned((total + 255) / 256), 256, size_t(Cout) * Cin * 9 * sizeof(float), st>>>(
+    launch_pdl(smallc_conv_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), size_t(Cout) * Cin * 9 * sizeof(float), st, 
         dout, w, nullptr, Cout, Cin, H, W, 1, total, da, ldda);
 }
 
@@ -607,6 +619,7 @@ void conv_out_dgrad(const float* dout, const float* w, int B, int Cin, int Cout,
 // with no index arithmetic.
 __global__ void smallc_wgrad_kernel(const float* __restrict__ xs, const bf16* __restrict__ yb, int ldy, int Cs, int Cb,
                                     int B, int H, int W, float* __restrict__ partial) {
+    pdl_entry();
     extern __shared__ float sdyn[];  // window [Cs][3][W+2], then reduction scratch [4][Cb][NT+1]
     const int cb = threadIdx.x % Cb, q = threadIdx.x / Cb;
     const int NT = Cs * 9, Wp = W + 2;
@@ -655,6 +668,7 @@ __global__ void smallc_wgrad_kernel(const float* __restrict__ xs, const bf16* __
 // mode 1 (conv_out): dw[s][cb][8-tap] = ...                            ; db untouched (computed elsewhere)
 __global__ void smallc_wgrad_reduce_kernel(const float* __restrict__ partial, int nblk, int Cs, int Cb, int mode,
                                            float* __restrict__ dw, float* __restrict__ db) {
+    pdl_entry();
     const int NT = Cs * 9;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Cb * (NT + 1)) return;
@@ -683,8 +697,8 @@ static void smallc_wgrad(const float* xs, const bf16* yb, int ldy, int B, int Cs
         return;
     }
     const size_t smem = (size_t(Cs) * 3 * (W + 2) + 4 * per) * sizeof(float);
-    smallc_wgrad_kernel<<<unsigned(nblk), Cb * 4, smem, st>>>(xs, yb, ldy, Cs, Cb, B, H, W, scratch);
-    smallc_wgrad_reduce_kernel<<<unsigned((per + 127) / 128), 128, 0, st>>>(scratch, int(nblk), Cs, Cb, mode, dw, db);
+    launch_pdl(smallc_wgrad_kernel, dim3(unsigned(nblk)), dim3(Cb * 4), smem, st, xs, yb, ldy, Cs, Cb, B, H, W, scratch);
+    launch_pdl(smallc_wgrad_reduce_kernel, dim3(unsigned((per + 127) / 128)), dim3(128), 0, st, scratch, int(nblk), Cs, Cb, mode, dw, db);
 }
 void conv_in_wgrad(const float* x, const bf16* dy, int lddy, int B, int Cin, int Cout, int H, int W, float* dw,
                    float* db, float* scratch, size_t scratch_floats, cudaStream_t st) {
@@ -695,6 +709,7 @@ void conv_in_wgrad(const float* x, const bf16* dy, int lddy, int B, int Cin, int
 __global__ void conv_out_fwd_kernel(const bf16* __restrict__ a, int lda, const float* __restrict__ w,
                                     const float* __restrict__ bias, int Cin, int Cout, int H, int W, size_t npix,
                                     float* __restrict__ out) {
+    pdl_entry();
     extern __shared__ float sw[];  // [9][Cin][4]
     for (int i = threadIdx.x; i < 9 * Cin * 4; i += blockDim.x) {
         const int o = i % 4, c = (i / 4) % Cin, tap = i / (4 * Cin);
@@ -728,12 +743,13 @@ __global__ void conv_out_fwd_kernel(const bf16* __restrict__ a, int lda, const f
 void conv_out_fwd(const bf16* a, int lda, const float* w, const float* b, int B, int Cin, int Cout, int H, int W,
                   float* out, cudaStream_t st) {
     const size_t npix = size_t(B) * H * W;
-    conv_out_fwd_kernel<<<unsigned((npix + 127) / 128), 128, size_t(9) * Cin * 4 * sizeof(float), st>>>(
+    launch_pdl(conv_out_fwd_kernel, dim3(unsigned((npix + 127) / 128)), dim3(128), size_t(9) * Cin * 4 * sizeof(float), st, 
         a, lda, w, b, Cin, Cout, H, W, npix, out);
 }
 
 // db[o] = sum_{b,p} dout[b][o][p]   (tiny: B*Cout*H*W fp32)
 __global__ void nchw_chansum_kernel(const float* __restrict__ x, int B, int C, size_t HW, float* __restrict__ out) {
+    pdl_entry();
     const int o = blockIdx.x;
     float s = 0.f;
     for (int b = 0; b < B; ++b)
@@ -752,12 +768,13 @@ void conv_out_wgrad(const bf16* a, int lda, const float* dout, int B, int Cin, i
                     float* db, float* scratch, size_t scratch_floats, cudaStream_t st) {
     // D'[c][o][t'] = sum_p a[p][c] * dout[o][p + shift(t')]  ->  dw[o][c][8 - t']
     smallc_wgrad(dout, a, lda, B, Cout, Cin, H, W, 1, dw, nullptr, scratch, scratch_floats, st);
-    nchw_chansum_kernel<<<Cout, 1024, 0, st>>>(dout, B, Cout, size_t(H) * W, db);
+    launch_pdl(nchw_chansum_kernel, dim3(Cout), dim3(1024), 0, st, dout, B, Cout, size_t(H) * W, db);
 }
 
 // ------------------------------------------------------------------------------------------------ loss
 __global__ void mse_kernel(const float* __restrict__ out, const float* __restrict__ y, size_t N,
                            float* __restrict__ loss, float* __restrict__ dout, float inv_n, float gscale) {
+    pdl_entry();
     float s = 0.f;
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < N; i += size_t(gridDim.x) * blockDim.x) {
         const float d = out[i] - y[i];
@@ -778,7 +795,7 @@ void mse_fwd_bwd(const float* out, const float* y, size_t N, float* loss, float*
                  cudaStream_t st) {
     size_t nblk = (N + 255) / 256;
     if (nblk > size_t(kSMs) * 4) nblk = size_t(kSMs) * 4;
-    mse_kernel<<<unsigned(nblk), 256, 0, st>>>(out, y, N, loss, dout, 1.f / float(N), grad_scale);
+    launch_pdl(mse_kernel, dim3(unsigned(nblk)), dim3(256), 0, st, out, y, N, loss, dout, 1.f / float(N), grad_scale);
 }
 
 }  // namespace ub
