@@ -34,9 +34,6 @@ struct Rng {
 };
 
 static int g_fail = 0;
-#ifdef UB_HALO_TRACE
-namespace ub { void igemm_halo_set_trace(long long* dev_buf); }
-#endif
 
 // ------------------------------------------------------------------------------------------ conv test
 // x NHWC [B,H,W,Cin], w reference layout [Cout][Cin][ntaps]
@@ -115,15 +112,15 @@ static bool test_conv(int B, int H, int W, int Cin, int Cout, int ntaps, int Cin
     ep.out = dout;
     ep.out_mode = out_mode;
     IgemmConvParams p;
-    IgemmHaloParams ph;
-    int r = halo ? igemm_halo_plan(&ph, segs, Cin2 ? 2 : 1, B, H, W, Cout, ep, 148)
+    IgemmRowsParams ph;
+    int r = halo ? igemm_rows_plan(&ph, segs, Cin2 ? 2 : 1, B, H, W, Cout, ep, 148)
                  : igemm_conv_plan(&p, segs, Cin2 ? 2 : 1, B, H, W, Cout, ep);
     if (r) {
         printf("conv plan failed %d\n", r);
         g_fail++;
         return false;
     }
-    auto launch = [&]() { return halo ? igemm_halo_launch(ph, 0) : igemm_conv_launch(p, 0); };
+    auto launch = [&]() { return halo ? igemm_rows_launch(ph, 0) : igemm_conv_launch(p, 0); };
     r = launch();
     cudaError_t e = cudaDeviceSynchronize();
     if (r || e != cudaSuccess) {
@@ -184,7 +181,7 @@ static bool test_conv(int B, int H, int W, int Cin, int Cout, int ntaps, int Cin
     double flops = 2.0 * npix * Cout * (double(ntaps) * Cin + Cin2);
     printf("%s B%d %dx%d %d->%d taps%d seg2=%d mode%d b%d r%d s%d | BN=%d stages=%d | checked %zu bad %d max_err %.3g "
            "(max_ref %.3g) | %.4f ms %.1f TFLOP/s  %s\n",
-           halo ? "HALO" : "conv", B, H, W, Cin, Cout, ntaps, Cin2, out_mode, use_bias, use_rowvec, use_res,
+           halo ? "ROWS" : "conv", B, H, W, Cin, Cout, ntaps, Cin2, out_mode, use_bias, use_rowvec, use_res,
            halo ? ph.BN : p.BN, halo ? ph.w_stages : p.stages, ncheck, bad,
            max_err, max_ref, ms, ms > 0 ? flops / ms * 1e-9 : 0.0, bad ? "FAIL" : "ok");
     if (bad) g_fail++;
@@ -442,30 +439,6 @@ int main(int argc, char** argv) {
         test_conv(B, H, W, Cin, Cout, 9, 0, OUT_NHWC_BF16, true, true, false, 2000, atoi(argv[8]), atoi(argv[7]) != 0);
         return g_fail ? 1 : 0;
     }
-#ifdef UB_HALO_TRACE
-    if (argc > 6 && !strcmp(argv[1], "trace")) {  // trace B H W Cin Cout : clock stamps of the halo kernel
-        long long* d;
-        CK(cudaMalloc(&d, 148 * 8 * 8 * 8));
-        CK(cudaMemset(d, 0, 148 * 8 * 8 * 8));
-        test_conv(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), 9, 0, OUT_NHWC_BF16, true,
-                  true, false, 100, 3, true);  // warm
-        igemm_halo_set_trace(d);
-        test_conv(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), 9, 0, OUT_NHWC_BF16, true,
-                  true, false, 100, 0, true);
-        std::vector<long long> h(148 * 64);
-        CK(cudaMemcpy(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost));
-        for (int cta : {0, 77}) {
-            long long t0 = h[size_t(cta) * 64];
-            printf("CTA %d (cycles since its first stamp): tile | A-prod start | mma start (tmem free) | A landed | last commit | epi wait | acc ready | epi done\n", cta);
-            for (int it = 0; it < 5; ++it) {
-                printf("  %d |", it);
-                for (int s = 0; s < 7; ++s) printf(" %8lld", h[(size_t(cta) * 8 + it) * 8 + s] ? h[(size_t(cta) * 8 + it) * 8 + s] - t0 : -1);
-                printf("\n");
-            }
-        }
-        return 0;
-    }
-#endif
     if (argc > 7 && !strcmp(argv[1], "wgrad")) {  // wgrad B H W Cin Cout reps
         test_wgrad(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), 9, 200, atoi(argv[7]));
         return g_fail ? 1 : 0;
@@ -500,13 +473,14 @@ int main(int argc, char** argv) {
         test_conv(32, 64, 64, 256, 256, 9, 0, OUT_NHWC_BF16, true, false, false, 20000, reps);
         test_conv(32, 64, 64, 512, 512, 9, 0, OUT_NHWC_BF16, true, false, false, 5000, 5);
     }
-    printf("== halo-reuse persistent conv ==\n");
+    printf("== persistent row-tile conv (igemm_rows) ==\n");
     test_conv(1, 32, 32, 64, 64, 9, 0, OUT_NHWC_F32, false, false, false, 1 << 20, 0, true);
     test_conv(2, 32, 32, 64, 64, 9, 0, OUT_NHWC_F32, true, false, false, 1 << 20, 0, true);
     test_conv(2, 64, 64, 128, 64, 9, 0, OUT_NHWC_BF16, true, true, true, 1 << 20, 0, true);
     test_conv(3, 32, 32, 64, 128, 1, 0, OUT_NCHW_F32, true, false, false, 1 << 20, 0, true);
     test_conv(2, 32, 32, 64, 192, 9, 128, OUT_NHWC_BF16, true, true, false, 1 << 20, 0, true);
-    test_conv(1, 40, 36, 72, 48, 9, 0, OUT_NHWC_F32, true, false, false, 1 << 20, 0, true);
+    test_conv(1, 24, 16, 72, 48, 9, 0, OUT_NHWC_F32, true, false, false, 1 << 20, 0, true);  // ragged H, Cin
+    test_conv(5, 16, 16, 192, 192, 9, 0, OUT_NHWC_BF16, true, true, false, 1 << 20, 0, true);
     test_conv(1, 128, 128, 64, 64, 9, 0, OUT_NHWC_BF16, true, false, false, 200000, 0, true);
     if (!quick) {
         int reps = 20;
@@ -514,9 +488,12 @@ int main(int argc, char** argv) {
         test_conv(32, 64, 64, 128, 64, 9, 0, OUT_NHWC_BF16, true, true, false, 20000, reps, true);
         test_conv(32, 64, 64, 192, 64, 9, 0, OUT_NHWC_BF16, true, false, false, 20000, reps, true);
         test_conv(32, 64, 64, 64, 64, 9, 64, OUT_NHWC_BF16, true, true, false, 20000, reps, true);
+        test_conv(32, 64, 64, 64, 128, 9, 0, OUT_NHWC_BF16, true, true, false, 20000, reps, true);
         test_conv(32, 32, 32, 128, 128, 9, 0, OUT_NHWC_BF16, true, true, false, 20000, reps, true);
         test_conv(32, 32, 32, 320, 128, 9, 320, OUT_NHWC_BF16, true, true, false, 20000, reps, true);
         test_conv(32, 32, 32, 64, 128, 9, 64, OUT_NHWC_BF16, true, true, false, 20000, reps, true);
+        test_conv(32, 16, 16, 192, 192, 9, 0, OUT_NHWC_BF16, true, true, false, 20000, reps, true);
+        test_conv(32, 16, 16, 192, 576, 1, 0, OUT_NHWC_BF16, true, false, false, 20000, reps, true);
         test_conv(32, 64, 64, 256, 256, 9, 0, OUT_NHWC_BF16, true, false, false, 20000, reps, true);
         test_conv(32, 64, 64, 512, 512, 9, 0, OUT_NHWC_BF16, true, false, false, 5000, 5, true);
     }

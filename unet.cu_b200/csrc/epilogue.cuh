@@ -116,17 +116,23 @@ __device__ __forceinline__ void epi_chunk(const EpiOut& e, uint32_t taddr, const
 // Column sums over the warp's 32 pixels go through a per-warp smem transpose tr[32][36] (f in columns 0..15, q in
 // 16..31; 144-byte rows keep both the 16-byte row stores and the column reads bank-conflict free): 8 STS.128 + 32
 // independent LDS per lane instead of a 5-stage shuffle butterfly -- the epilogue is latency-bound, not issue-bound.
-__device__ __forceinline__ void epi_chunk_gn(const EpiOut& e, uint32_t taddr, const float* comb, const float* gconst,
-                                             int cstride, bool valid, size_t pix, int n, int lane, float* red,
-                                             float* tr) {
-    uint32_t v[16];
-    tmem_ld16(taddr, v);
-    uint4 xr[2];  // the residual row (stats mode) or the GroupNorm input row (gn-bwd mode): never both (plan)
+// xr holds the 16 channels [n, n+16) of the pixel's side input -- the residual row (stats mode) or the GroupNorm input
+// row (gn-bwd mode), never both (plan) -- fetched one chunk AHEAD (epi_side_load): a dependent global load per chunk
+// was the longest stall of the hooked epilogue.  On return xr holds the chunk at channel n_next (if n_next >= 0).
+__device__ __forceinline__ void epi_side_load(const EpiOut& e, bool valid, size_t pix, int n, uint4 (&xr)[2]) {
     if ((e.residual || e.gx) && valid) {
         const uint4* xp = e.gx ? reinterpret_cast<const uint4*>(e.gx + pix * e.ldgx + n)
                                : reinterpret_cast<const uint4*>(e.residual + pix * e.ldr + n);
         xr[0] = xp[0], xr[1] = xp[1];
     }
+}
+__device__ __forceinline__ void epi_chunk_gn(const EpiOut& e, uint32_t taddr, const float* comb, const float* gconst,
+                                             int cstride, bool valid, size_t pix, int n, int lane, float* red,
+                                             float* tr, uint4 (&xr)[2], int n_next) {
+    uint32_t v[16];
+    tmem_ld16(taddr, v);
+    uint4 xn[2];
+    if (n_next >= 0) epi_side_load(e, valid, pix, n_next, xn);
     tmem_ld_wait();
     float f[16], q[16];
 #pragma unroll
@@ -204,6 +210,7 @@ __device__ __forceinline__ void epi_chunk_gn(const EpiOut& e, uint32_t taddr, co
     // lane j < 16 holds the warp's total of f column j, lane 16 + j that of q column j: park them; epi_flush_stats
     // adds the warps up and issues one vector RED per (tile, channel) (the L2 atomic unit serialises per address)
     red[2 * (lane & 15) + (lane >> 4)] = (s0 + s1) + (s2 + s3);
+    xr[0] = xn[0], xr[1] = xn[1];
 }
 
 // red[4 quadrants][BN][2] -> global [B][Cout][2].  Called by the nthreads epilogue threads after a barrier; quadrant
@@ -235,11 +242,16 @@ __device__ __forceinline__ void epi_flush_stats(const float* red, float* dst, in
 __device__ __forceinline__ void epi_row(const EpiOut& e, uint32_t trow, const float* comb, int BN, bool valid,
                                         size_t pix, int b, int h, int w, int n0, const float* gconst = nullptr,
                                         int lane = 0, float* red = nullptr, float* tr = nullptr, int half = 0,
-                                        int nhalf = 1) {
+                                        int nhalf = 1, uint4* side = nullptr) {
     if (e.stats || e.gx) {  // BN % 32 == 0 (plan); red = this quadrant's [BN][2] row of the reduction scratch
-        for (int c0 = 16 * half; c0 < BN; c0 += 16 * nhalf)
+        // side = the first chunk's side input, loaded by the caller (epi_side_load at channel n0 + 16 * half) before
+        // it waited for the accumulator
+        uint4 xr[2] = {side[0], side[1]};
+        for (int c0 = 16 * half; c0 < BN; c0 += 16 * nhalf) {
+            const int cn = c0 + 16 * nhalf;
             epi_chunk_gn(e, trow + uint32_t(c0), comb + c0, gconst + c0, BN, valid, pix, n0 + c0, lane, red + 2 * c0,
-                         tr);
+                         tr, xr, cn < BN ? n0 + cn : -1);
+        }
         return;
     }
     int i = 0, c0 = 0;

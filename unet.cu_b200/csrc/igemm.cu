@@ -149,18 +149,21 @@ __global__ void __launch_bounds__(kConvThreads, 2) igemm_conv_kernel(const __gri
                              p.gn_cpg, p.H * p.W, n0, p.BN, et, kEpiThreads);
         named_bar_sync(1, kEpiThreads);
 
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
-
         const size_t pix = (size_t(b) * p.H + h) * p.W + w;
         EpiOut eo{p.residual, p.ldr, p.out, p.ldo, p.out_mode, p.Cout, p.H, p.W};
         eo.stats = p.stats, eo.gx = p.gn_x, eo.ldgx = p.gn_ldx, eo.gS = p.gn_S, eo.gsilu = p.gn_silu;
+        uint4 side[2];
+        if (p.stats || p.gn_x) epi_side_load(eo, valid, pix, n0 + 16 * half, side);  // hidden behind the main loop
+
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+
         // GroupNorm hooks: all 32 pixels of a warp lie in one image of the tile (plan)
         const int lbw = min(lb, p.TB - 1);
         epi_row(eo, tmem_base + (uint32_t(q * 32) << 16), comb + (p.ncomb > 1 ? min(lb, p.ncomb - 1) : 0) * p.BN, p.BN,
                 valid, pix, b, h, w, n0, gconst + lbw * 4 * p.BN, lane, red + size_t(q) * p.BN * 2,
                 // per-warp transpose scratch: the pipeline stages are free once the accumulator is complete
-                reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 36), half, 2);
+                reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 36), half, 2, side);
         if (p.stats || p.gn_x) {
             named_bar_sync(1, kEpiThreads);
             epi_flush_stats(red, p.gn_x ? p.gn_S : p.stats, p.Cout, n0, p.BN, b0, p.B, p.TW * p.TH, p.TB, et,

@@ -61,16 +61,17 @@ struct IgemmConvParams {
     int nred;                       // BN-float rows of the cross-warp reduction scratch (8 with a hook, else 0)
 };
 
-// persistent halo-reuse variant (igemm_halo.cu); same segments / epilogue as IgemmConvParams
-struct IgemmHaloParams {
-    IgemmSeg seg[2];  // tmA box = (64, Wp, NR, 1), tmW box = (64, BN)
+// persistent row-tile variant (igemm_rows.cu); same segments / epilogue as IgemmConvParams
+struct IgemmRowsParams {
+    IgemmSeg seg[2];  // tmA box = (64, W, box_rows, 1), tmW box = (64, BN)
     int nseg;
     int B, H, W, Cout;
-    int Wp, NR;         // padded row pitch (W + 2) and rows per halo box
-    int tiles_per_img;  // ceil(H * Wp / 256)
+    int TH;             // image rows per tile (256 / W)
+    int box_rows;       // TH + 2 when a segment is 3x3, else TH
+    int tiles_per_img;  // ceil(H / TH)
     int num_tiles;      // B * tiles_per_img * (Cout / BN)
     int BN;             // <= 128
-    int w_stages;
+    int a_stages, w_stages;
     int grid;
     uint32_t a_bytes, a_stage_bytes, w_bytes, w_stage_bytes;
     const float* bias;
@@ -81,6 +82,14 @@ struct IgemmHaloParams {
     void* out;
     int ldo;
     int out_mode;
+    float* stats;
+    const __nv_bfloat16* gn_x;
+    int gn_ldx;
+    const float* gn_chsum;
+    const float* gn_gamma;
+    const float* gn_beta;
+    float* gn_S;
+    int gn_silu, gn_cpg;
 };
 
 struct IgemmWgradParams {
@@ -133,11 +142,11 @@ int igemm_conv_plan(IgemmConvParams* p, const ConvSegDesc* segs, int nseg, int B
                     const ConvEpilogue& ep);
 int igemm_conv_launch(const IgemmConvParams& p, cudaStream_t st);
 
-bool igemm_halo_eligible(int B, int H, int W, int Cout);
-int igemm_halo_plan(IgemmHaloParams* p, const ConvSegDesc* segs, int nseg, int B, int H, int W, int Cout,
+bool igemm_rows_eligible(int B, int H, int W, int Cout);
+int igemm_rows_plan(IgemmRowsParams* p, const ConvSegDesc* segs, int nseg, int B, int H, int W, int Cout,
                     const ConvEpilogue& ep, int sm_count);
-int igemm_halo_launch(const IgemmHaloParams& p, cudaStream_t st);
-void igemm_halo_init();
+int igemm_rows_launch(const IgemmRowsParams& p, cudaStream_t st);
+void igemm_rows_init();
 
 int igemm_wgrad_plan(IgemmWgradParams* p, const __nv_bfloat16* dy, int ldy, const __nv_bfloat16* x, int ldx, int B,
                      int H, int W, int Cin, int Cout, int ntaps, float* partial, size_t partial_cap_floats,

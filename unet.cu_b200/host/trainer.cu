@@ -143,6 +143,7 @@ struct UbTrainer {
         double flops;   // algorithmic FLOPs (tensor kernels) ...
         double bytes;   // ... or algorithmic bytes (memory-bound kernels)
         int side;       // 0 = main stream, 1 = weight-gradient branch (side stream), 2 = join marker
+        std::string label;
     };
     std::vector<OpInfo> fwd_info, bwd_info;
     int launches_fwd = 0, launches_bwd = 0, launches_misc = 0;
@@ -237,13 +238,22 @@ struct Builder {
     void F(UbTrainer::Op op, int launches = 1, int kind = UB_KIND_SMALL, double flops = 0, double bytes = 0) {
         if (!real()) return;
         T->fwd_ops.push_back(std::move(op)), T->launches_fwd += launches;
-        T->fwd_info.push_back({kind, launches, flops, bytes, 0});
+        T->fwd_info.push_back({kind, launches, flops, bytes, 0, next_label}), next_label.clear();
     }
     void Bk(UbTrainer::Op op, int launches = 1, int kind = UB_KIND_SMALL, double flops = 0, double bytes = 0,
             int side = 0) {
         if (!real()) return;
         T->bwd_ops.push_back(std::move(op)), T->launches_bwd += launches;
-        T->bwd_info.push_back({kind, launches, flops, bytes, side});
+        T->bwd_info.push_back({kind, launches, flops, bytes, side, next_label}), next_label.clear();
+    }
+    std::string next_label;  // optional description of the next op pushed (per-op profile dump)
+    void label(const char* fmt, ...) {
+        char buf[160];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        next_label = buf;
     }
     // the main stream waits for everything the weight-gradient branch has been given so far
     void join_side() { Bk([](cudaStream_t) {}, 0, UB_KIND_SMALL, 0, 0, 2); }
@@ -266,17 +276,36 @@ struct Builder {
 
     void conv_op(bool fwd, std::vector<ConvSegDesc> segs, int H, int W, int Cout, ConvEpilogue ep) {
         if (!real()) return;
-        IgemmConvParams p;
-        int r = igemm_conv_plan(&p, segs.data(), int(segs.size()), B, H, W, Cout, ep);
-        if (r) {
-            set_err("igemm_conv_plan failed (%d) for %dx%d Cout=%d Cin0=%d", r, H, W, Cout, segs[0].Cin);
-            plan_errors++;
-            return;
-        }
-        auto op = [p](cudaStream_t st) { igemm_conv_launch(p, st); };
+        // measured (profiles/r01_ops_rows_vs_basic.txt): the persistent kernel wins where the basic one is bound by its
+        // per-128-pixel fixed costs, i.e. the 64-pixel-wide levels with <= 64 output channels; elsewhere the basic
+        // kernel's larger N tile (up to 256) reads less shared memory per MMA.  UB_ROWS=0 / 2 forces never / always.
+        static const int rows_mode = getenv("UB_ROWS") ? atoi(getenv("UB_ROWS")) : 1;
+        const bool no_rows = rows_mode == 0 || (rows_mode == 1 && !(W >= 64 && Cout <= 64));
         double k = 0, bytes = act_bytes(Cout, H, W);
         for (auto& sg : segs) k += double(sg.ntaps) * sg.Cin, bytes += act_bytes(sg.Cin, H, W) + 2.0 * sg.ntaps * sg.Cin * Cout;
         const double flops = 2.0 * B * H * W * Cout * k;
+        UbTrainer::Op op;
+        // persistent row-tile kernel for the 16x16 .. 128x128 levels, one-CTA-per-128-pixels kernel otherwise
+        IgemmRowsParams pr;
+        if (!no_rows && igemm_rows_eligible(B, H, W, Cout) &&
+            igemm_rows_plan(&pr, segs.data(), int(segs.size()), B, H, W, Cout, ep, 148) == 0) {
+            op = [pr](cudaStream_t st) { igemm_rows_launch(pr, st); };
+            label("conv%s %s Cin=%d%s Cout=%d %dx%d rows BN=%d stages=%d/%d%s%s", segs[0].ntaps == 9 ? "3x3" : "1x1",
+                  fwd ? "fwd" : "dgrad", segs[0].Cin, segs.size() > 1 ? "+skip" : "", Cout, H, W, pr.BN, pr.a_stages,
+                  pr.w_stages, ep.stats ? " +stats" : "", ep.gn_x ? " +gnbwd" : "");
+        } else {
+            IgemmConvParams p;
+            int r = igemm_conv_plan(&p, segs.data(), int(segs.size()), B, H, W, Cout, ep);
+            if (r) {
+                set_err("igemm_conv_plan failed (%d) for %dx%d Cout=%d Cin0=%d", r, H, W, Cout, segs[0].Cin);
+                plan_errors++;
+                return;
+            }
+            op = [p](cudaStream_t st) { igemm_conv_launch(p, st); };
+            label("conv%s %s Cin=%d%s Cout=%d %dx%d BN=%d stages=%d%s%s", segs[0].ntaps == 9 ? "3x3" : "1x1",
+                  fwd ? "fwd" : "dgrad", segs[0].Cin, segs.size() > 1 ? "+skip" : "", Cout, H, W, p.BN, p.stages,
+                  ep.stats ? " +stats" : "", ep.gn_x ? " +gnbwd" : "");
+        }
         if (fwd)
             F(op, 1, UB_KIND_CONV, flops, bytes);
         else
@@ -293,6 +322,8 @@ struct Builder {
             plan_errors++;
             return;
         }
+        label("wgrad taps=%d Cin=%d Cout=%d %dx%d MO=%d NC=%d split=%d stages=%d", ntaps, Cin, Cout, x.H, x.W, p.MO, p.NC,
+              p.nsplit, p.stages);
         Bk([p, dw](cudaStream_t st) {
             igemm_wgrad_launch(p, st);
             igemm_wgrad_reduce(p, dw, st);
@@ -314,6 +345,7 @@ struct Builder {
         g.S = zf32(size_t(B) * x.C * 2);
         const int HW = x.H * x.W, Gn = c.gn_n_groups, Bn = B;
         float *gw = P(g.w), *gb = P(g.b), *cs = g.chsum;
+        label("gn_fwd C=%d %dx%d%s", x.C, x.H, x.W, have ? "" : " +stats pass");
         F([=](cudaStream_t st) {
             if (!have) gn_stats(x.p, x.ld, Bn, HW, x.C, cs, st);
             gn_apply(x.p, x.ld, cs, gw, gb, Bn, HW, x.C, Gn, silu, y.p, y.ld, nullptr, st);
@@ -330,6 +362,7 @@ struct Builder {
         const int HW = x.H * x.W, Gn = c.gn_n_groups, Bn = B;
         float *gw = P(g.w), *gb = P(g.b), *cs = g.chsum, *S = g.S, *dgw = G(g.w), *dgb = G(g.b);
         const int mode = fused ? (silu ? 2 : 0) : silu;
+        label("gn_bwd C=%d %dx%d%s%s", x.C, x.H, x.W, fused ? "" : " +stats pass", add_in.p ? " +add" : "");
         Bk([=](cudaStream_t st) {
             if (!fused) gn_bwd_stats(x.p, x.ld, dy.p, dy.ld, cs, gw, gb, Bn, HW, x.C, Gn, silu, S, st);
             gn_bwd_apply(x.p, x.ld, dy.p, dy.ld, cs, S, gw, gb, Bn, HW, x.C, Gn, mode, add_in.p, add_in.ld, dx.p,
@@ -470,6 +503,7 @@ struct Builder {
             int r = attn_tc_plan(&apf, qkv.p, qkv.ld, B, Tn, NH, HSz, ao.p, ao.ld, lse, nullptr, 0, nullptr, 0, nullptr);
             if (r) set_err("attn_tc_plan failed (%d)", r), plan_errors++;
         }
+        label("attn fwd T=%d C=%d", Tn, C);
         F([=](cudaStream_t st) {
             if (tc)
                 attn_tc_fwd(apf, st);
@@ -500,6 +534,7 @@ struct Builder {
                                      dqkv.ld, dsum);
                 if (r) set_err("attn_tc_plan (bwd) failed (%d)", r), plan_errors++;
             }
+            label("attn bwd T=%d C=%d", Tn, C);
             Bk([=](cudaStream_t st) {
                 if (tc)
                     attn_tc_bwd(apb, st);
@@ -835,6 +870,7 @@ extern "C" int ub_trainer_create(UbTrainer** out, const UbConfig* cfg, int devic
     if (r) return r;
     CUDA_TRY(cudaSetDevice(device));
     igemm_init();
+    igemm_rows_init();
     attn_init();
     attn_tc_init();
     UbTrainer* t = new UbTrainer();
@@ -958,6 +994,8 @@ static void enqueue_step(UbTrainer* t, const StepOpts& o, cudaStream_t st) {
     auto next_event = [&]() { return t->side_events[t->side_ev_next++ % t->side_events.size()]; };
     auto run = [&](std::vector<UbTrainer::Op>& ops, std::vector<UbTrainer::OpInfo>& info, const char* what) {
         for (size_t i = 0; i < ops.size(); ++i) {
+            static const bool skip_side = getenv("UB_DEBUG_SKIP_SIDE") != nullptr;  // timing experiments only
+            if (info[i].side == 1 && skip_side) continue;
             if (info[i].side == 1 && t->use_side) {  // fork: the branch sees everything enqueued on main so far
                 cudaEvent_t ev = next_event();
                 cudaEventRecord(ev, st);
@@ -1123,6 +1161,7 @@ extern "C" int ub_trainer_profile(UbTrainer* t, int reps, UbProfile* out) {
     const UbConfig& c = t->cfg;
     const size_t nops = t->fwd_ops.size() + t->bwd_ops.size() + 2;
     std::vector<cudaEvent_t> ev(nops + 1);
+    std::vector<float> op_us(nops, 0.f);
     for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
     cudaStream_t st = t->stream;
     t->comm_off = true;  // a profile is rank-local: the peers are not replaying with us
@@ -1148,16 +1187,30 @@ extern "C" int ub_trainer_profile(UbTrainer* t, int reps, UbProfile* out) {
         for (size_t i = 0; i < t->fwd_ops.size(); ++i, ++j) {
             cudaEventElapsedTime(&ms, ev[j], ev[j + 1]);
             out->ms[t->fwd_info[i].kind] += ms;
+            op_us[i] = ms * 1e3f;
         }
         for (size_t i = 0; i < t->bwd_ops.size(); ++i, ++j) {
             cudaEventElapsedTime(&ms, ev[j], ev[j + 1]);
             out->ms[t->bwd_info[i].kind] += ms;
+            op_us[t->fwd_ops.size() + i] = ms * 1e3f;
         }
         cudaEventElapsedTime(&ms, ev[j], ev[j + 1]);
         out->ms[UB_KIND_OPTIM] += ms;
     }
     t->comm_off = false;
     for (auto& e : ev) cudaEventDestroy(e);
+    if (const char* path = getenv("UB_PROFILE_DUMP")) {  // per-op times of the LAST repetition
+        if (FILE* f = fopen(path, "w")) {
+            for (size_t i = 0; i < t->fwd_ops.size(); ++i)
+                fprintf(f, "fwd\t%zu\t%d\t%.3f\t%.4g\t%.4g\t%s\n", i, t->fwd_info[i].kind, op_us[i],
+                        t->fwd_info[i].flops, t->fwd_info[i].bytes, t->fwd_info[i].label.c_str());
+            for (size_t i = 0; i < t->bwd_ops.size(); ++i)
+                fprintf(f, "bwd\t%zu\t%d\t%.3f\t%.4g\t%.4g\t%s\n", i, t->bwd_info[i].kind,
+                        op_us[t->fwd_ops.size() + i], t->bwd_info[i].flops, t->bwd_info[i].bytes,
+                        t->bwd_info[i].label.c_str());
+            fclose(f);
+        }
+    }
     for (int k = 0; k < UB_NUM_KINDS; ++k) out->ms[k] /= reps, out->total_ms += out->ms[k];
     auto acc = [&](const std::vector<UbTrainer::OpInfo>& v) {
         for (auto& i : v) out->flops[i.kind] += i.flops, out->bytes[i.kind] += i.bytes, out->launches[i.kind] += i.launches;
