@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + size_t(p.stages) * p.stage_bytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + size_t(p.stages) * p.stage_bytes + (p.ones_off ? 8192 : 0));
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tmem_full_bar = empty_bar + kMaxStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
@@ -202,6 +202,14 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
     const int k_end = int((long long)ktiles * (split + 1) / p.nsplit);
     const int a_atoms = p.MO / 64, b_atoms = p.NC / 64;
     const uint32_t b_off = uint32_t(a_atoms) * 8192u;  // B region offset inside a stage
+    // fused bias gradient: only the CTAs that own the centre tap (or the single tap) of the first Cin tile
+    const int bias_ti = (p.ntaps == 9 ? 4 : 0) - tap0;
+    const bool do_bias = p.ones_off != 0 && c0 == 0 && bias_ti >= 0 && bias_ti < p.TC;
+    if (do_bias) {  // 64 pixel rows x 128 B of bf16 1.0 (any swizzle of a constant tile is the same tile)
+        uint4* ones = reinterpret_cast<uint4*>(smem + p.ones_off);
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) ones[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmDY);
@@ -256,6 +264,8 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(p.MO, p.NC, 1, 1);
+            const uint32_t idesc_b = make_idesc_bf16(p.MO, 16, 1, 1);
+            const uint32_t s_ones = smem_u32(smem + p.ones_off);
             int stage = 0;
             uint32_t phase = 0;
             for (int kt = k_begin; kt < k_end; ++kt) {
@@ -263,6 +273,13 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
                 tc_fence_after();
                 const uint32_t sA = smem_u32(smem + size_t(stage) * p.stage_bytes);
                 const uint32_t sB = sA + b_off;
+                if (do_bias) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tmem_base + uint32_t(p.TC * p.NC), make_smem_desc_sw128(sA + k * 2048, 8192, 1024),
+                                  make_smem_desc_sw128(s_ones + k * 2048, 8192, 1024), idesc_b,
+                                  (kt != k_begin) || (k != 0));
+                }
                 for (int ti = 0; ti < p.TC; ++ti) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -297,18 +314,37 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
         if (k_end > k_begin) {
             for (int ti = 0; ti < p.TC; ++ti) {
                 const int tap = tap0 + ti;
-                float* dst = p.partial + ((size_t(split) * p.ntaps + tap) * p.Cout + (o0 + row)) * p.Cin + c0;
+                float* dst = p.acc ? p.acc + (size_t(tap) * p.Cout + (o0 + row)) * p.Cin + c0
+                                   : p.partial + ((size_t(split) * p.ntaps + tap) * p.Cout + (o0 + row)) * p.Cin + c0;
                 for (int cc = 0; cc < p.NC; cc += 16) {
                     uint32_t v[16];
                     tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(ti * p.NC + cc), v);
                     tmem_ld_wait();
                     if (valid) {
+                        if (p.acc) {
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4)
-                            *reinterpret_cast<float4*>(dst + cc + j) =
-                                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                            __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                            for (int j = 0; j < 16; j += 4)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + cc + j),
+                                             "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
+                                             "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                                             : "memory");
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4)
+                                *reinterpret_cast<float4*>(dst + cc + j) =
+                                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        }
                     }
+                }
+            }
+            if (do_bias) {  // every column of the ones-accumulator holds sum_pixels dY[pix][o]
+                uint32_t v[16];
+                tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(p.TC * p.NC), v);
+                tmem_ld_wait();
+                if (valid) {
+                    atomicAdd(p.dbias + o0 + row, __uint_as_float(v[0]));
+                    if (p.dbias2) atomicAdd(p.dbias2 + o0 + row, __uint_as_float(v[0]));
                 }
             }
         }
@@ -346,6 +382,26 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
         for (int k = 0; k < 8; ++k) t += red[k][el];
         dweight[e * ntaps + tap] = t;
     }
+}
+
+// dw[o][c][tap] = acc[tap][o][c]; acc = 0.  grid (ceil(max_elems / 32), n_entries), block 288 = 32 (o,c) pairs x 9 taps:
+// reads are 9 coalesced 128-byte rows, the write is one contiguous 1152-byte run.
+__global__ void __launch_bounds__(288) wgrad_finalize_kernel(const WgradFinalizeEntry* __restrict__ table) {
+    pdl_entry();
+    const WgradFinalizeEntry e = table[blockIdx.y];
+    const size_t n = size_t(e.Cout) * e.Cin;
+    const size_t e0 = size_t(blockIdx.x) * 32;
+    if (e0 >= n) return;
+    __shared__ float t[9][33];
+    const int el = threadIdx.x & 31, tap = threadIdx.x >> 5;  // 9 warps: warp = tap
+    if (e0 + el < n) {
+        float* src = e.acc + size_t(tap) * n + e0 + el;
+        t[tap][el] = *src;
+        *src = 0.f;
+    }
+    __syncthreads();
+    const int i = threadIdx.x;  // output run: (element i / 9, tap i % 9)
+    if (e0 + i / 9 < n) e.dw[e0 * 9 + i] = t[i % 9][i / 9];
 }
 
 // =====================================================================================================
@@ -548,9 +604,9 @@ size_t igemm_wgrad_partial_floats(int Cin, int Cout, int ntaps, int nsplit) {
     return size_t(nsplit) * ntaps * Cout * Cin;
 }
 
-int igemm_wgrad_plan(IgemmWgradParams* p, const __nv_bfloat16* dy, int ldy, const __nv_bfloat16* x, int ldx, int B,
-                     int H, int W, int Cin, int Cout, int ntaps, float* partial, size_t partial_cap_floats,
-                     int sm_count) {
+static int wgrad_plan_common(IgemmWgradParams* p, const __nv_bfloat16* dy, int ldy, const __nv_bfloat16* x, int ldx,
+                             int B, int H, int W, int Cin, int Cout, int ntaps, float* partial,
+                             size_t partial_cap_floats, int sm_count, bool acc_mode, bool bias) {
     memset(p, 0, sizeof(*p));
     if (ntaps != 9 && ntaps != 1) return -4;
     if (Cin % 64 != 0 || Cout % 64 != 0) return -5;
@@ -566,7 +622,8 @@ int igemm_wgrad_plan(IgemmWgradParams* p, const __nv_bfloat16* dy, int ldy, cons
     p->TC = ntaps == 9 ? 3 : 1;
     // TMEM: TC * NC columns <= 512
     p->NC = (Cin % 128 == 0) ? 128 : 64;
-    p->tmem_cols = next_pow2(p->TC * p->NC < 32 ? 32 : p->TC * p->NC);
+    p->tmem_cols = next_pow2(p->TC * p->NC + (bias ? 16 : 0) < 32 ? 32 : p->TC * p->NC + (bias ? 16 : 0));
+    if (p->tmem_cols > 512) return -3;
     const int a_atoms = p->MO / 64, b_atoms = p->NC / 64;
     p->stage_bytes = uint32_t(a_atoms + p->TC * b_atoms) * 8192u;
     p->tx_bytes = p->stage_bytes;
@@ -583,19 +640,47 @@ int igemm_wgrad_plan(IgemmWgradParams* p, const __nv_bfloat16* dy, int ldy, cons
     int nsplit = sm_count / base_ctas;
     if (nsplit > ktiles / 4) nsplit = ktiles / 4;      // at least 4 K tiles per CTA
     if (nsplit < 1) nsplit = 1;
-    while (nsplit > 1 && igemm_wgrad_partial_floats(Cin, Cout, ntaps, nsplit) > partial_cap_floats) --nsplit;
-    if (igemm_wgrad_partial_floats(Cin, Cout, ntaps, nsplit) > partial_cap_floats) return -9;
+    if (!acc_mode) {
+        while (nsplit > 1 && igemm_wgrad_partial_floats(Cin, Cout, ntaps, nsplit) > partial_cap_floats) --nsplit;
+        if (igemm_wgrad_partial_floats(Cin, Cout, ntaps, nsplit) > partial_cap_floats) return -9;
+    }
     p->nsplit = nsplit;
     p->partial = partial;
+    if (bias) p->ones_off = uint32_t(p->stages) * p->stage_bytes;
     int r = make_act_map(&p->tmDY, dy, Cout, ldy, W, H, B, p->TW, p->TH, p->TB);
     if (r) return r;
     r = make_act_map(&p->tmX, x, Cin, ldx, W, H, B, p->TW, p->TH, p->TB);
     return r;
 }
 
+int igemm_wgrad_plan(IgemmWgradParams* p, const __nv_bfloat16* dy, int ldy, const __nv_bfloat16* x, int ldx, int B,
+                     int H, int W, int Cin, int Cout, int ntaps, float* partial, size_t partial_cap_floats,
+                     int sm_count) {
+    return wgrad_plan_common(p, dy, ldy, x, ldx, B, H, W, Cin, Cout, ntaps, partial, partial_cap_floats, sm_count,
+                             false, false);
+}
+
+int igemm_wgrad_plan_acc(IgemmWgradParams* p, const __nv_bfloat16* dy, int ldy, const __nv_bfloat16* x, int ldx, int B,
+                         int H, int W, int Cin, int Cout, int ntaps, float* acc, float* dbias, float* dbias2,
+                         int sm_count) {
+    int r = wgrad_plan_common(p, dy, ldy, x, ldx, B, H, W, Cin, Cout, ntaps, nullptr, 0, sm_count, true,
+                              dbias != nullptr);
+    if (r) return r;
+    if (!acc || (reinterpret_cast<uintptr_t>(acc) & 15)) return -16;
+    p->acc = acc, p->dbias = dbias, p->dbias2 = dbias2;
+    return 0;
+}
+
+int igemm_wgrad_finalize(const WgradFinalizeEntry* table_dev, int n_entries, size_t max_elems, cudaStream_t st) {
+    if (n_entries < 1) return 0;
+    return int(launch_pdl(wgrad_finalize_kernel, dim3(unsigned((max_elems + 31) / 32), unsigned(n_entries)), dim3(288),
+                          0, st, table_dev));
+}
+
 int igemm_wgrad_launch(const IgemmWgradParams& p, cudaStream_t st) {
     igemm_init();
-    const size_t smem = size_t(p.stages) * p.stage_bytes + 1024 + kBarrierBytes;
+    // the optional ones tile (8 KiB) sits where the barriers used to be; the barriers move behind it
+    const size_t smem = size_t(p.stages) * p.stage_bytes + (p.ones_off ? 8192 : 0) + 1024 + kBarrierBytes;
     dim3 grid((p.Cout / p.MO) * (p.Cin / p.NC), p.ntaps / p.TC, p.nsplit);
     launch_pdl(igemm_wgrad_kernel, dim3(grid), dim3(kWgradThreads), smem, st, p);
     return int(cudaGetLastError());

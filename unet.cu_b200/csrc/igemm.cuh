@@ -105,7 +105,21 @@ struct IgemmWgradParams {
     int stages;
     int tmem_cols;
     uint32_t stage_bytes, tx_bytes;
-    float* partial;  // [nsplit][ntaps][Cout][Cin] fp32
+    float* partial;  // [nsplit][ntaps][Cout][Cin] fp32 (two-pass mode: igemm_wgrad_reduce sums the splits)
+    // accumulate mode (trainer): every CTA adds its tile into acc[ntaps][Cout][Cin] with red.global.add.v4.f32 -- no
+    // partial buffer, no per-layer reduce launch; wgrad_finalize turns [tap][o][c] into the reference [o][c][tap]
+    // layout for a whole gradient bucket at once (for 1x1 / linear layers acc IS the final gradient).
+    float* acc;
+    // fused bias gradient: the CTAs of the centre tap / first Cin tile also contract dY with a tile of ones
+    // (one extra N=16 MMA per K step), and add column 0 of that accumulator into dbias (and dbias2) atomically.
+    float* dbias;
+    float* dbias2;
+    uint32_t ones_off;  // byte offset of the 8 KiB ones tile behind the stages (0 = no bias fusion)
+};
+struct WgradFinalizeEntry {
+    float* acc;  // [9][Cout][Cin], zeroed again by the finalize kernel
+    float* dw;   // [Cout][Cin][9]
+    int Cout, Cin;
 };
 
 // ---- host API (implemented in igemm.cu); all return cudaError_t-like int (0 == ok) -------------------------
@@ -151,6 +165,12 @@ void igemm_rows_init();
 int igemm_wgrad_plan(IgemmWgradParams* p, const __nv_bfloat16* dy, int ldy, const __nv_bfloat16* x, int ldx, int B,
                      int H, int W, int Cin, int Cout, int ntaps, float* partial, size_t partial_cap_floats,
                      int sm_count);
+// accumulate mode: acc [ntaps][Cout][Cin] must hold zeros (or the running sum); dbias/dbias2 may be null
+int igemm_wgrad_plan_acc(IgemmWgradParams* p, const __nv_bfloat16* dy, int ldy, const __nv_bfloat16* x, int ldx, int B,
+                         int H, int W, int Cin, int Cout, int ntaps, float* acc, float* dbias, float* dbias2,
+                         int sm_count);
+// dw[o][c][tap] = acc[tap][o][c]; acc = 0, for n entries of a device table (max_elems = max Cout*Cin over them)
+int igemm_wgrad_finalize(const WgradFinalizeEntry* table_dev, int n_entries, size_t max_elems, cudaStream_t st);
 int igemm_wgrad_launch(const IgemmWgradParams& p, cudaStream_t st);
 // dW (reference layout [Cout][Cin][ntaps], fp32) = sum over splits of partial[split][tap][o][c]; overwrite.
 int igemm_wgrad_reduce(const IgemmWgradParams& p, float* dweight, cudaStream_t st);

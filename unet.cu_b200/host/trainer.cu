@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <functional>
 #include <string>
 #include <vector>
@@ -131,6 +132,8 @@ struct UbTrainer {
     PackEntry* pack_table = nullptr;
     int n_pack = 0, pack_max_tiles = 0;
     std::vector<PackEntry> h_pack;
+    WgradFinalizeEntry* fin_table = nullptr;
+    std::vector<WgradFinalizeEntry> h_fin;  // in backward order
     SmallLinear *emb_table = nullptr, *temb_table = nullptr;
     std::vector<SmallLinear> h_emb, h_temb;
     int emb_max_oc = 0;
@@ -311,24 +314,40 @@ struct Builder {
         else
             Bk(op, 1, UB_KIND_CONV, flops, bytes);
     }
-    void wgrad_op(View dy, View x, int Cin, int Cout, int ntaps, float* dw) {
+    // Weight (and bias) gradient of a conv / linear layer on the side stream.  Every CTA adds its tile into an fp32
+    // accumulator with vector REDs; 3x3 layers accumulate in [tap][o][c] and are transposed into the reference
+    // (Cout, Cin, 3, 3) layout by one finalize launch per gradient bucket (fin_flush), 1x1 layers accumulate straight
+    // into the gradient arena.  db (and db2) = sum over pixels of dy, from an extra ones-column MMA in the same kernel.
+    int fin_done = 0;
+    void wgrad_op(View dy, View x, int Cin, int Cout, int ntaps, float* dw, float* db = nullptr, float* db2 = nullptr) {
+        float* acc = ntaps == 9 ? f32(size_t(9) * Cout * Cin) : dw;
         if (!real()) return;
-        IgemmWgradParams p;
         static const int wg_sms = getenv("UB_WGRAD_SMS") ? atoi(getenv("UB_WGRAD_SMS")) : 148;
-        int r = igemm_wgrad_plan(&p, dy.p, dy.ld, x.p, x.ld, B, x.H, x.W, Cin, Cout, ntaps, T->wg_partial, T->wg_cap,
-                                 wg_sms);
+        IgemmWgradParams p;
+        int r = igemm_wgrad_plan_acc(&p, dy.p, dy.ld, x.p, x.ld, B, x.H, x.W, Cin, Cout, ntaps, acc, db, db2, wg_sms);
         if (r) {
             set_err("igemm_wgrad_plan failed (%d) for %dx%d %d->%d", r, x.H, x.W, Cin, Cout);
             plan_errors++;
             return;
         }
-        label("wgrad taps=%d Cin=%d Cout=%d %dx%d MO=%d NC=%d split=%d stages=%d", ntaps, Cin, Cout, x.H, x.W, p.MO, p.NC,
-              p.nsplit, p.stages);
-        Bk([p, dw](cudaStream_t st) {
-            igemm_wgrad_launch(p, st);
-            igemm_wgrad_reduce(p, dw, st);
-        }, 2, UB_KIND_WGRAD, 2.0 * B * x.H * x.W * double(Cout) * Cin * ntaps,
+        if (ntaps == 9) T->h_fin.push_back({acc, dw, Cout, Cin});
+        label("wgrad taps=%d Cin=%d Cout=%d %dx%d MO=%d NC=%d split=%d stages=%d%s", ntaps, Cin, Cout, x.H, x.W, p.MO,
+              p.NC, p.nsplit, p.stages, db ? " +bias" : "");
+        Bk([p](cudaStream_t st) { igemm_wgrad_launch(p, st); }, 1, UB_KIND_WGRAD,
+           2.0 * B * x.H * x.W * double(Cout) * Cin * ntaps,
            act_bytes(Cin, x.H, x.W) + act_bytes(Cout, x.H, x.W) + 4.0 * ntaps * Cin * Cout, 1);
+    }
+    void fin_flush() {
+        if (!real()) return;
+        const int lo = fin_done, n = int(T->h_fin.size()) - fin_done;
+        if (n <= 0) return;
+        size_t mx = 0;
+        for (int i = lo; i < lo + n; ++i) mx = std::max(mx, size_t(T->h_fin[i].Cout) * T->h_fin[i].Cin);
+        UbTrainer* Tt = T;
+        label("wgrad finalize x%d", n);
+        Bk([=](cudaStream_t st) { igemm_wgrad_finalize(Tt->fin_table + lo, n, mx, st); }, 1, UB_KIND_WGRAD, 0,
+           0, 1);
+        fin_done = lo + n;
     }
 
     struct GN {
@@ -444,9 +463,7 @@ struct Builder {
             UbTrainer* Tt = T;
             const int Bn = B;
             // bias / weight gradients of conv2 (and of the fused 1x1 skip conv)
-            Bk([=](cudaStream_t st) { colsum(dout.p, dout.ld, npix, Cout, gb2, gbs, st); }, 1, UB_KIND_ELTWISE, 0,
-               act_bytes(Cout, H, W), 1);
-            wgrad_op(dout, a2, Cout, Cout, 9, G(w2));
+            wgrad_op(dout, a2, Cout, Cout, 9, G(w2), gb2, gbs);  // + bias gradients of conv2 and of the skip conv
             if (proj) wgrad_op(dout, x, C, Cout, 1, G(ws));
             {
                 ConvEpilogue ep;
@@ -520,9 +537,7 @@ struct Builder {
             View dao = act(C, H, W), dqkv = act(3 * C, H, W), dg = act(C, H, W), dx = act(C, H, W);
             const size_t npix = size_t(B) * H * W;
             float *gbp = G(bp), *gbq = G(bq);
-            Bk([=](cudaStream_t st) { colsum(dout.p, dout.ld, npix, C, gbp, nullptr, st); }, 1, UB_KIND_ELTWISE, 0,
-               act_bytes(C, H, W), 1);
-            wgrad_op(dout, ao, C, C, 1, G(wp));
+            wgrad_op(dout, ao, C, C, 1, G(wp), gbp);
             {
                 ConvEpilogue ep;
                 ep.out = dao.p, ep.ldo = dao.ld;
@@ -542,9 +557,7 @@ struct Builder {
                     attn_bwd(qkv.p, qkv.ld, ao.p, ao.ld, dao.p, dao.ld, lse, Bn, Tn, NH, HSz, dqkv.p, dqkv.ld, dsum,
                              st);
             }, 2, UB_KIND_ATTN, 10.0 * B * NH * double(Tn) * Tn * HSz, act_bytes(8 * C, H, W));
-            Bk([=](cudaStream_t st) { colsum(dqkv.p, dqkv.ld, npix, 3 * C, gbq, nullptr, st); }, 1, UB_KIND_ELTWISE, 0,
-               act_bytes(3 * C, H, W), 1);
-            wgrad_op(dqkv, g, C, 3 * C, 1, G(wq));
+            wgrad_op(dqkv, g, C, 3 * C, 1, G(wq), gbq);
             {
                 ConvEpilogue ep;
                 ep.out = dg.p, ep.ldo = dg.ld;
@@ -582,6 +595,7 @@ int Builder::build() {
     T->emb_table = (SmallLinear*)T->arena.alloc(kMaxEmbEntries * sizeof(SmallLinear));
     T->temb_table = (SmallLinear*)T->arena.alloc(2 * sizeof(SmallLinear));
     T->pack_table = (PackEntry*)T->arena.alloc(256 * sizeof(PackEntry));
+    T->fin_table = (WgradFinalizeEntry*)T->arena.alloc(128 * sizeof(WgradFinalizeEntry));
 
     // ---- time-embedding MLP (dev/unet.py:176-180); its forward and all 22 embedding projections run first
     const size_t tw0 = take(size_t(Cemb) * Cm), tb0 = take(Cemb), tw1 = take(size_t(Cemb) * Cemb), tb1 = take(Cemb);
@@ -773,6 +787,7 @@ int Builder::build() {
         g = nd.bwd(g);
         while (cut_i < cuts.size() && nd.param_begin <= cuts[cut_i] && nd.param_begin > time_mlp_end) {
             emb_flush();
+            fin_flush();
             join_side();
             flush_bucket(nd.param_begin, flushed_hi);
             flushed_hi = nd.param_begin;
@@ -780,6 +795,7 @@ int Builder::build() {
         }
     }
     emb_flush();
+    fin_flush();
     join_side();
     // time MLP backward (needs the complete d_embact), then the last bucket
     Bk([=](cudaStream_t st) {
@@ -858,6 +874,12 @@ static int upload_tables(UbTrainer* t) {
     CUDA_TRY(cudaMemcpy(t->emb_table, t->h_emb.data(), t->h_emb.size() * sizeof(SmallLinear), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(t->temb_table, t->h_temb.data(), 2 * sizeof(SmallLinear), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(t->pack_table, t->h_pack.data(), t->h_pack.size() * sizeof(PackEntry), cudaMemcpyHostToDevice));
+    if (t->h_fin.size() > 128) {
+        set_err("finalize table overflow");
+        return UB_ERR_SHAPE;
+    }
+    CUDA_TRY(cudaMemcpy(t->fin_table, t->h_fin.data(), t->h_fin.size() * sizeof(WgradFinalizeEntry),
+                        cudaMemcpyHostToDevice));
     t->n_pack = int(t->h_pack.size());
     return UB_OK;
 }
