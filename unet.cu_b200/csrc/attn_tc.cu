@@ -162,18 +162,18 @@ __global__ void __launch_bounds__(kThreads) attn_tc_fwd_kernel(const __grid_cons
             tc_fence_after();
             const uint32_t id_s = make_idesc_bf16(128, t.ncols, 0, 0);
             const uint32_t id_o = make_idesc_bf16(128, 64, 0, 1);
+            // descriptors = constant high word + start address in 16-byte units (the issue loop runs on one thread)
+            const uint64_t dQ = make_smem_desc_sw128(smem_u32(sQ), 16, 1024), dK = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+            const uint64_t dP = make_smem_desc_sw128(smem_u32(sP), 16, 1024), dV = make_smem_desc_sw128(smem_u32(sV), 8192, 1024);
             for (int h = 0; h < 2; ++h) {
 #pragma unroll
-                for (int k = 0; k < 2; ++k)
-                    umma_bf16(tmem, make_smem_desc_sw128(smem_u32(sQ) + h * 64 + k * 32, 16, 1024),
-                              make_smem_desc_sw128(smem_u32(sK) + h * 64 + k * 32, 16, 1024), id_s, k);
+                for (int k = 0; k < 2; ++k) umma_bf16(tmem, dQ + uint64_t(h * 4 + k * 2), dK + uint64_t(h * 4 + k * 2), id_s, k);
                 umma_commit(&sm->bar_s);
                 mbar_wait(&sm->bar_p, h);
                 tc_fence_after();
+#pragma unroll 4
                 for (int j = 0; j < t.ncols / 16; ++j)
-                    umma_bf16(tmem + o_col,
-                              make_smem_desc_sw128(smem_u32(sP) + (j >> 2) * 16384 + (j & 3) * 32, 16, 1024),
-                              make_smem_desc_sw128(smem_u32(sV) + j * 2048, 8192, 1024), id_o, j);
+                    umma_bf16(tmem + o_col, dP + uint64_t((j >> 2) * 1024 + (j & 3) * 2), dV + uint64_t(j * 128), id_o, j);
                 // (the row threads drain O_0 before they arrive on bar_p for head 1, so PV of head 1 may reuse it)
                 umma_commit(&sm->bar_o);
             }
@@ -287,25 +287,25 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dq_kernel(const __grid_const
             tc_fence_after();
             const uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);
             const uint32_t id_o = make_idesc_bf16(128, 64, 0, 1);
+            const uint64_t dQ = make_smem_desc_sw128(smem_u32(sQ), 16, 1024), dG = make_smem_desc_sw128(smem_u32(sdO), 16, 1024);
+            const uint64_t dK = make_smem_desc_sw128(smem_u32(sK), 16, 1024), dV = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
+            const uint64_t dS = make_smem_desc_sw128(smem_u32(sdS), 16, 1024), dKm = make_smem_desc_sw128(smem_u32(sK), 8192, 1024);
             int it = 0;
             for (int h = 0; h < 2; ++h) {
                 for (int cc = 0; cc < nchunk; ++cc, ++it) {
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
-                        const uint64_t dK = make_smem_desc_sw128(smem_u32(sK) + cc * 16384 + h * 64 + k * 32, 16, 1024);
-                        const uint64_t dV = make_smem_desc_sw128(smem_u32(sV) + cc * 16384 + h * 64 + k * 32, 16, 1024);
-                        umma_bf16(tmem, make_smem_desc_sw128(smem_u32(sQ) + h * 64 + k * 32, 16, 1024), dK, id_s, k);
-                        umma_bf16(tmem + 128, make_smem_desc_sw128(smem_u32(sdO) + h * 64 + k * 32, 16, 1024), dV, id_s,
-                                  k);
+                        const uint64_t o = uint64_t(h * 4 + k * 2);
+                        umma_bf16(tmem, dQ + o, dK + o + uint64_t(cc * 1024), id_s, k);
+                        umma_bf16(tmem + 128, dG + o, dV + o + uint64_t(cc * 1024), id_s, k);
                     }
                     umma_commit(&sm->bar_s);
                     mbar_wait(&sm->bar_p, it & 1);
                     tc_fence_after();
+#pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        umma_bf16(tmem + 256 + h * 64,
-                                  make_smem_desc_sw128(smem_u32(sdS) + (j >> 2) * 16384 + (j & 3) * 32, 16, 1024),
-                                  make_smem_desc_sw128(smem_u32(sK) + cc * 16384 + j * 2048, 8192, 1024), id_o,
-                                  (cc | j) != 0);
+                        umma_bf16(tmem + 256 + h * 64, dS + uint64_t((j >> 2) * 1024 + (j & 3) * 2),
+                                  dKm + uint64_t(cc * 1024 + j * 128), id_o, (cc | j) != 0);
                     umma_commit(&sm->bar_o);
                 }
             }
@@ -428,28 +428,27 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dkv_kernel(const __grid_cons
             tc_fence_after();
             const uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);
             const uint32_t id_o = make_idesc_bf16(128, 64, 0, 1);
+            const uint64_t dK = make_smem_desc_sw128(smem_u32(sK), 16, 1024), dV = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
+            const uint64_t dQ = make_smem_desc_sw128(smem_u32(sQ), 16, 1024), dG = make_smem_desc_sw128(smem_u32(sdO), 16, 1024);
+            const uint64_t dPt = make_smem_desc_sw128(smem_u32(sPt), 16, 1024), dSt = make_smem_desc_sw128(smem_u32(sdSt), 16, 1024);
+            const uint64_t dQm = make_smem_desc_sw128(smem_u32(sQ), 8192, 1024), dGm = make_smem_desc_sw128(smem_u32(sdO), 8192, 1024);
             int it = 0;
             for (int h = 0; h < 2; ++h) {
                 for (int cc = 0; cc < nchunk; ++cc, ++it) {
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
-                        const uint64_t dQ = make_smem_desc_sw128(smem_u32(sQ) + cc * 16384 + h * 64 + k * 32, 16, 1024);
-                        const uint64_t dG = make_smem_desc_sw128(smem_u32(sdO) + cc * 16384 + h * 64 + k * 32, 16, 1024);
-                        umma_bf16(tmem, make_smem_desc_sw128(smem_u32(sK) + h * 64 + k * 32, 16, 1024), dQ, id_s, k);
-                        umma_bf16(tmem + 128, make_smem_desc_sw128(smem_u32(sV) + h * 64 + k * 32, 16, 1024), dG, id_s,
-                                  k);
+                        const uint64_t o = uint64_t(h * 4 + k * 2);
+                        umma_bf16(tmem, dK + o, dQ + o + uint64_t(cc * 1024), id_s, k);
+                        umma_bf16(tmem + 128, dV + o, dG + o + uint64_t(cc * 1024), id_s, k);
                     }
                     umma_commit(&sm->bar_s);
                     mbar_wait(&sm->bar_p, it & 1);
                     tc_fence_after();
+#pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const uint32_t aoff = (j >> 2) * 16384 + (j & 3) * 32;
-                        umma_bf16(tmem + 384 + h * 64, make_smem_desc_sw128(smem_u32(sPt) + aoff, 16, 1024),
-                                  make_smem_desc_sw128(smem_u32(sdO) + cc * 16384 + j * 2048, 8192, 1024), id_o,
-                                  (cc | j) != 0);
-                        umma_bf16(tmem + 256 + h * 64, make_smem_desc_sw128(smem_u32(sdSt) + aoff, 16, 1024),
-                                  make_smem_desc_sw128(smem_u32(sQ) + cc * 16384 + j * 2048, 8192, 1024), id_o,
-                                  (cc | j) != 0);
+                        const uint64_t aoff = uint64_t((j >> 2) * 1024 + (j & 3) * 2);
+                        umma_bf16(tmem + 384 + h * 64, dPt + aoff, dGm + uint64_t(cc * 1024 + j * 128), id_o, (cc | j) != 0);
+                        umma_bf16(tmem + 256 + h * 64, dSt + aoff, dQm + uint64_t(cc * 1024 + j * 128), id_o, (cc | j) != 0);
                     }
                     umma_commit(&sm->bar_o);
                 }

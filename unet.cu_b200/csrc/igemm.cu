@@ -263,31 +263,45 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(p.MO, p.NC, 1, 1);
+            // The issue loop runs on ONE thread: every instruction in it is on the critical path (the first version
+            // rebuilt two 64-bit descriptors per MMA, ~20 dependent instructions, and the tensor pipe sat idle 3/4 of
+            // the time -- ncu r01 wgrad).  Everything that does not change per K tile is hoisted: descriptors are a
+            // constant high word plus the 16-byte-granular start address, MMA groups are precomputed.
+            const uint64_t dbase = make_smem_desc_sw128(0, 8192, 1024);  // LBO = 8192 (64-channel atoms), SBO = 1024
             const uint32_t idesc_b = make_idesc_bf16(p.MO, 16, 1, 1);
-            const uint32_t s_ones = smem_u32(smem + p.ones_off);
+            const uint64_t d_ones = dbase | uint64_t((smem_u32(smem + p.ones_off) >> 4) & 0x3FFF);
+            // taps are merged into MMAs of N <= 256: the B tiles of consecutive taps are consecutive 64-channel atoms
+            // and their accumulators consecutive TMEM columns, so the dY operand is read once per group
+            const int taps_per_mma = 256 / p.NC;
+            int ng = 0;
+            uint32_t g_col[3], g_boff[3], g_idesc[3];
+            for (int ti = 0; ti < p.TC; ti += taps_per_mma, ++ng) {
+                const int nt = min(taps_per_mma, p.TC - ti);
+                g_col[ng] = uint32_t(ti * p.NC);
+                g_boff[ng] = (b_off + uint32_t(ti * b_atoms) * 8192u) >> 4;
+                g_idesc[ng] = make_idesc_bf16(p.MO, nt * p.NC, 1, 1);
+            }
+            const uint32_t s0 = smem_u32(smem);
+            const uint32_t t_bias = tmem_base + uint32_t(p.TC * p.NC);
             int stage = 0;
             uint32_t phase = 0;
             for (int kt = k_begin; kt < k_end; ++kt) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t sA = smem_u32(smem + size_t(stage) * p.stage_bytes);
-                const uint32_t sB = sA + b_off;
+                // 16 pixels (K) per MMA = 16 rows of 128 B = 2048 B = 128 descriptor units
+                const uint64_t dA = dbase | uint64_t(((s0 + uint32_t(stage) * p.stage_bytes) >> 4) & 0x3FFF);
+                const uint32_t acc0 = kt != k_begin;
                 if (do_bias) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_bf16(tmem_base + uint32_t(p.TC * p.NC), make_smem_desc_sw128(sA + k * 2048, 8192, 1024),
-                                  make_smem_desc_sw128(s_ones + k * 2048, 8192, 1024), idesc_b,
-                                  (kt != k_begin) || (k != 0));
+                        umma_bf16(t_bias, dA + uint64_t(k * 128), d_ones + uint64_t(k * 128), idesc_b, acc0 | uint32_t(k));
                 }
-                for (int ti = 0; ti < p.TC; ++ti) {
+#pragma unroll 3
+                for (int g = 0; g < ng; ++g) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        // 16 pixels (K) per MMA = 16 rows of 128 B = 2048 B; atoms (64 channels) are 8192 B apart
-                        const uint64_t dA = make_smem_desc_sw128(sA + k * 2048, 8192, 1024);
-                        const uint64_t dB = make_smem_desc_sw128(sB + ti * b_atoms * 8192 + k * 2048, 8192, 1024);
-                        umma_bf16(tmem_base + uint32_t(ti * p.NC), dA, dB, idesc, (kt != k_begin) || (k != 0));
-                    }
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tmem_base + g_col[g], dA + uint64_t(k * 128), dA + uint64_t(g_boff[g] + k * 128),
+                                  g_idesc[g], acc0 | uint32_t(k));
                 }
                 umma_commit(&empty_bar[stage]);
                 if (++stage == p.stages) {
