@@ -199,3 +199,27 @@ def test_full_size_properties_B32(ub, setup):
     losses = [tr.train_step(rep(x0), rep(t), rep(noise), lr=1e-4) for _ in range(6)]
     assert losses[-1] < losses[0]
     tr.close()
+
+
+def test_config5_128px_five_levels_matches_oracle(ub, oracle):
+    """BASELINE config 5 architecture: 128x128 input, channel_mult (1,1,2,3,4), attention at
+    16x16 and 8x8 -- outside the reference CUDA trainer's hard-coded 4 levels, inside dev/unet.py's envelope.  One
+    forward+backward at B=2 against the oracle; same bounds as the 64x64 test."""
+    O = oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.UNetConfig(channel_mult=(1, 1, 2, 3, 4), attn_start_level=3, H=128, W=128)
+    flat = O.flatten_params(cfg, O.init_params(cfg, seed=0))
+    assert flat.numel() == 21082755                     # SURVEY.md App. A
+    x0, t, noise = O.synthetic_batch(cfg, 2)
+    tr = ub.Trainer(B=2, H=128, W=128, channel_mult=(1, 1, 2, 3, 4), att_start_level=3)
+    assert tr.nparams == flat.numel()
+    tr.set_params(flat.numpy())
+    loss = tr.forward_backward(x0.numpy(), t.numpy(), noise.numpy())
+    g = tr.get_grads()
+    loss_ref, _, g_ref = O.train_step_grads(cfg, flat, x0, t, noise)
+    g_ref = g_ref.numpy()
+    assert abs(loss - float(loss_ref)) <= 2e-3 * float(loss_ref)
+    cos = float(g @ g_ref / (np.linalg.norm(g) * np.linalg.norm(g_ref)))
+    assert cos > 0.9995, cos
+    assert np.linalg.norm(g - g_ref) <= 2e-2 * np.linalg.norm(g_ref)
+    tr.close()

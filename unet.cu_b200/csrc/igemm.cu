@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + size_t(p.stages) * p.stage_bytes + (p.ones_off ? 8192 : 0));
+    const uint32_t atom = uint32_t(p.KP) * 128u;  // one 64-channel operand atom: KP pixel rows of 128 B
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + size_t(p.stages) * p.stage_bytes + (p.ones_off ? atom : 0));
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tmem_full_bar = empty_bar + kMaxStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
@@ -201,13 +202,13 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
     const int k_begin = int((long long)ktiles * split / p.nsplit);
     const int k_end = int((long long)ktiles * (split + 1) / p.nsplit);
     const int a_atoms = p.MO / 64, b_atoms = p.NC / 64;
-    const uint32_t b_off = uint32_t(a_atoms) * 8192u;  // B region offset inside a stage
+    const uint32_t b_off = uint32_t(a_atoms) * atom;  // B region offset inside a stage
     // fused bias gradient: only the CTAs that own the centre tap (or the single tap) of the first Cin tile
     const int bias_ti = (p.ntaps == 9 ? 4 : 0) - tap0;
     const bool do_bias = p.ones_off != 0 && c0 == 0 && bias_ti >= 0 && bias_ti < p.TC;
-    if (do_bias) {  // 64 pixel rows x 128 B of bf16 1.0 (any swizzle of a constant tile is the same tile)
+    if (do_bias) {  // KP pixel rows x 128 B of bf16 1.0 (any swizzle of a constant tile is the same tile)
         uint4* ones = reinterpret_cast<uint4*>(smem + p.ones_off);
-        for (int i = threadIdx.x; i < 512; i += blockDim.x) ones[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+        for (int i = threadIdx.x; i < p.KP * 8; i += blockDim.x) ones[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
 
@@ -246,13 +247,13 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
                 uint8_t* sB = sA + b_off;
                 mbar_expect_tx(&full_bar[stage], p.tx_bytes);
                 for (int a = 0; a < a_atoms; ++a)
-                    tma_load_4d(sA + a * 8192, &p.tmDY, &full_bar[stage], o0 + a * 64, w0, h0, b0);
+                    tma_load_4d(sA + a * atom, &p.tmDY, &full_bar[stage], o0 + a * 64, w0, h0, b0);
                 for (int ti = 0; ti < p.TC; ++ti) {
                     const int tap = tap0 + ti;
                     const int dy = p.ntaps == 9 ? tap / 3 - 1 : 0;
                     const int dx = p.ntaps == 9 ? tap % 3 - 1 : 0;
                     for (int nb = 0; nb < b_atoms; ++nb)
-                        tma_load_4d(sB + (ti * b_atoms + nb) * 8192, &p.tmX, &full_bar[stage], c0 + nb * 64, w0 + dx,
+                        tma_load_4d(sB + (ti * b_atoms + nb) * atom, &p.tmX, &full_bar[stage], c0 + nb * 64, w0 + dx,
                                     h0 + dy, b0);
                 }
                 if (++stage == p.stages) {
@@ -267,7 +268,8 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
             // rebuilt two 64-bit descriptors per MMA, ~20 dependent instructions, and the tensor pipe sat idle 3/4 of
             // the time -- ncu r01 wgrad).  Everything that does not change per K tile is hoisted: descriptors are a
             // constant high word plus the 16-byte-granular start address, MMA groups are precomputed.
-            const uint64_t dbase = make_smem_desc_sw128(0, 8192, 1024);  // LBO = 8192 (64-channel atoms), SBO = 1024
+            const uint64_t dbase = make_smem_desc_sw128(0, atom, 1024);  // LBO = atom (64-channel atoms), SBO = 1024
+            const int ksteps = p.KP / 16;
             const uint32_t idesc_b = make_idesc_bf16(p.MO, 16, 1, 1);
             const uint64_t d_ones = dbase | uint64_t((smem_u32(smem + p.ones_off) >> 4) & 0x3FFF);
             // taps are merged into MMAs of N <= 256: the B tiles of consecutive taps are consecutive 64-channel atoms
@@ -278,7 +280,7 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
             for (int ti = 0; ti < p.TC; ti += taps_per_mma, ++ng) {
                 const int nt = min(taps_per_mma, p.TC - ti);
                 g_col[ng] = uint32_t(ti * p.NC);
-                g_boff[ng] = (b_off + uint32_t(ti * b_atoms) * 8192u) >> 4;
+                g_boff[ng] = (b_off + uint32_t(ti * b_atoms) * atom) >> 4;
                 g_idesc[ng] = make_idesc_bf16(p.MO, nt * p.NC, 1, 1);
             }
             const uint32_t s0 = smem_u32(smem);
@@ -292,14 +294,14 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
                 const uint64_t dA = dbase | uint64_t(((s0 + uint32_t(stage) * p.stage_bytes) >> 4) & 0x3FFF);
                 const uint32_t acc0 = kt != k_begin;
                 if (do_bias) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
+#pragma unroll 4
+                    for (int k = 0; k < ksteps; ++k)
                         umma_bf16(t_bias, dA + uint64_t(k * 128), d_ones + uint64_t(k * 128), idesc_b, acc0 | uint32_t(k));
                 }
 #pragma unroll 3
                 for (int g = 0; g < ng; ++g) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
+#pragma unroll 4
+                    for (int k = 0; k < ksteps; ++k)
                         umma_bf16(tmem_base + g_col[g], dA + uint64_t(k * 128), dA + uint64_t(g_boff[g] + k * 128),
                                   g_idesc[g], acc0 | uint32_t(k));
                 }
@@ -625,10 +627,19 @@ static int wgrad_plan_common(IgemmWgradParams* p, const __nv_bfloat16* dy, int l
     if (ntaps != 9 && ntaps != 1) return -4;
     if (Cin % 64 != 0 || Cout % 64 != 0) return -5;
     p->B = B, p->H = H, p->W = W, p->Cin = Cin, p->Cout = Cout, p->ntaps = ntaps;
-    // K tile = 64 pixels; boxes may overhang the image (TMA zero-fills), they must hold exactly 64 pixels
-    p->TW = next_pow2(W) < 64 ? next_pow2(W) : 64;
-    p->TH = next_pow2(H) < 64 / p->TW ? next_pow2(H) : 64 / p->TW;
-    p->TB = 64 / (p->TW * p->TH);
+    // boxes may overhang the image (TMA zero-fills), they must hold exactly KP pixels
+    // K tile = KP pixels per stage.  128 halves the number of TMA issues and barrier round trips per byte (the single
+    // producer thread was the pacing resource at KP = 64); 64 is kept for operands whose tiles would not fit.
+    static const int kp_env = getenv("UB_WGRAD_KP") ? atoi(getenv("UB_WGRAD_KP")) : 128;
+    int KP = (kp_env == 64 || size_t(B) * H * W < 256) ? 64 : 128;
+    {   // two stages of the chosen tile must fit beside the epilogue's needs
+        const int mo = (Cout % 128 == 0) ? 128 : 64, nc = (Cin % 128 == 0) ? 128 : 64, tc = ntaps == 9 ? 3 : 1;
+        if (size_t(2) * (mo / 64 + tc * (nc / 64)) * 128 * 128 > size_t(160) * 1024) KP = 64;
+    }
+    p->KP = KP;
+    p->TW = next_pow2(W) < KP ? next_pow2(W) : KP;
+    p->TH = next_pow2(H) < KP / p->TW ? next_pow2(H) : KP / p->TW;
+    p->TB = KP / (p->TW * p->TH);
     p->tiles_w = ceil_div_i(W, p->TW);
     p->tiles_h = ceil_div_i(H, p->TH);
     p->tiles_b = ceil_div_i(B, p->TB);
@@ -639,7 +650,7 @@ static int wgrad_plan_common(IgemmWgradParams* p, const __nv_bfloat16* dy, int l
     p->tmem_cols = next_pow2(p->TC * p->NC + (bias ? 16 : 0) < 32 ? 32 : p->TC * p->NC + (bias ? 16 : 0));
     if (p->tmem_cols > 512) return -3;
     const int a_atoms = p->MO / 64, b_atoms = p->NC / 64;
-    p->stage_bytes = uint32_t(a_atoms + p->TC * b_atoms) * 8192u;
+    p->stage_bytes = uint32_t(a_atoms + p->TC * b_atoms) * uint32_t(KP) * 128u;
     p->tx_bytes = p->stage_bytes;
     static const unsigned smem_kb = getenv("UB_WGRAD_SMEM_KB") ? unsigned(atoi(getenv("UB_WGRAD_SMEM_KB"))) : 96u;
     int stages = int((smem_kb * 1024u) / p->stage_bytes);
@@ -652,7 +663,7 @@ static int wgrad_plan_common(IgemmWgradParams* p, const __nv_bfloat16* dy, int l
     // One CTA per SM (a CTA owns the SM's smem and TMEM), and never more CTAs than SMs: a grid of 150 CTAs on 148
     // SMs runs as two waves and doubles the kernel time (ncu r01: 64->64@64x64 took 57 us as (1,3,50)).
     int nsplit = sm_count / base_ctas;
-    if (nsplit > ktiles / 4) nsplit = ktiles / 4;      // at least 4 K tiles per CTA
+    if (nsplit > ktiles * KP / 256) nsplit = ktiles * KP / 256;  // at least 256 pixels of K per CTA
     if (nsplit < 1) nsplit = 1;
     if (!acc_mode) {
         while (nsplit > 1 && igemm_wgrad_partial_floats(Cin, Cout, ntaps, nsplit) > partial_cap_floats) --nsplit;
@@ -694,7 +705,7 @@ int igemm_wgrad_finalize(const WgradFinalizeEntry* table_dev, int n_entries, siz
 int igemm_wgrad_launch(const IgemmWgradParams& p, cudaStream_t st) {
     igemm_init();
     // the optional ones tile (8 KiB) sits where the barriers used to be; the barriers move behind it
-    const size_t smem = size_t(p.stages) * p.stage_bytes + (p.ones_off ? 8192 : 0) + 1024 + kBarrierBytes;
+    const size_t smem = size_t(p.stages) * p.stage_bytes + (p.ones_off ? size_t(p.KP) * 128 : 0) + 1024 + kBarrierBytes;
     dim3 grid((p.Cout / p.MO) * (p.Cin / p.NC), p.ntaps / p.TC, p.nsplit);
     launch_pdl(igemm_wgrad_kernel, dim3(grid), dim3(kWgradThreads), smem, st, p);
     return int(cudaGetLastError());

@@ -102,6 +102,7 @@ struct IgemmWgradParams {
     int NC;      // Cin tile: multiple of 64, <= 256
     int TC;      // taps per CTA: 3 (one filter row) or 1
     int nsplit;  // split of the pixel (K) dimension across CTAs
+    int KP;      // pixels per K tile (= per stage): 64 or 128; an operand atom is KP rows of 128 B
     int stages;
     int tmem_cols;
     uint32_t stage_bytes, tx_bytes;

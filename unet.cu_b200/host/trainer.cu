@@ -922,9 +922,14 @@ extern "C" int ub_trainer_create(UbTrainer** out, const UbConfig* cfg, int devic
     t->zarena.base = blob + 4 * pbytes + arena_bytes, t->zarena.cap = zero_bytes, t->zarena.off = 0,
     t->zarena.counting = false;
     t->zero_base = t->zarena.base, t->zero_bytes = zero_bytes;
-    cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&t->comm_stream, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&t->side_stream, cudaStreamNonBlocking);
+    // the main stream carries the critical path (forward, dgrad chain): highest priority; the weight-gradient branch
+    // and the collectives fill the gaps (stream priorities become kernel-node priorities in the captured graph)
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    static const bool use_prio = !(getenv("UB_NO_PRIO") && atoi(getenv("UB_NO_PRIO")) != 0);
+    cudaStreamCreateWithPriority(&t->stream, cudaStreamNonBlocking, use_prio ? prio_hi : 0);
+    cudaStreamCreateWithPriority(&t->comm_stream, cudaStreamNonBlocking, use_prio ? prio_hi : 0);
+    cudaStreamCreateWithPriority(&t->side_stream, cudaStreamNonBlocking, use_prio ? prio_lo : 0);
     t->side_events.resize(512);
     for (auto& ev : t->side_events) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (const char* e = getenv("UB_NO_SIDE_STREAM")) t->use_side = atoi(e) == 0;
