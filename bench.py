@@ -234,9 +234,14 @@ def run_cuda(args):
         conv = prof["conv_igemm"]
         conv_tf = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
         roofline = {
-            "bound": "tensor", "kernel": "igemm_conv_kernel (3x3/1x1 conv fprop+dgrad, qkv/proj GEMMs; tcgen05)",
+            "bound": "tensor", "kernel": "igemm_conv_kernel + igemm_rows_kernel (3x3/1x1 conv fprop+dgrad, qkv/proj GEMMs; tcgen05)",
             "achieved": conv_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-            "frac": conv_tf / pk["tf_sustained"], "traffic": None, "peak_source": pk["source"] + ", sustained bf16",
+            "frac": conv_tf / pk["tf_sustained"], "traffic": conv_traffic(),
+            "traffic_note": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
+                            "profiles/r01_tc_traffic.json; writes are absorbed by the L2 within the kernel); "
+                            "algorithmic bytes per launch = bytes_per_launch",
+            "bytes_per_launch": conv["bytes"] / max(conv["launches"], 1),
+            "peak_source": pk["source"] + ", sustained bf16",
             "flops_per_launch": conv["flops"] / max(conv["launches"], 1),
             "avg_launch_ms": conv["ms"] / max(conv["launches"], 1), "launches_per_step": conv["launches"],
             "share_of_step": conv["ms"] / prof["total_ms"],
@@ -280,6 +285,21 @@ def run_cuda(args):
     if use_dist:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def conv_traffic():
+    """DRAM bytes per launch of the conv kernel (read + write) from the committed ncu capture of one training step
+    (profiles/r01_tc_traffic.json, produced by tools/measure_all.sh + tools/traffic_summary.py); None if absent."""
+    p = os.path.join(ROOT, "profiles", "r01_tc_traffic.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        ks = [v for k, v in d.items() if k in ("igemm_conv_kernel", "igemm_rows_kernel")]
+        n = sum(v["launches"] for v in ks)
+        byts = sum(v["launches"] * (v["dram_read_bytes_per_launch"] + v["dram_write_bytes_per_launch"]) for v in ks)
+        return byts / n if n else None
+    except Exception:
+        return None
 
 
 def reference_cuda_baseline(args):
