@@ -561,6 +561,14 @@ void adamw_step(float* p, float* g, float* m, float* v, size_t n, float lr, floa
     launch_pdl(adamw_kernel, dim3(unsigned((n4 + 1 + 255) / 256)), dim3(256), 0, st, p, g, m, v, n4, n, lr, b1, b2, eps, wd, grad_scale,
                                                                 step_dev);
 }
+// Keeps the stream busy for ~`us` microseconds: the profile replay enqueues a whole step behind it, so the per-op
+// CUDA-event intervals measure device time, not how fast the host can submit launches.
+__global__ void delay_kernel(unsigned us) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < (long long)us * 1900) __nanosleep(1000);
+}
+void stream_delay(unsigned us, cudaStream_t st) { delay_kernel<<<1, 1, 0, st>>>(us); }
+
 __global__ void increment_step_kernel(int* s) {
     pdl_entry(); *s += 1; }
 void increment_step(int* step_dev, cudaStream_t st) { launch_pdl(increment_step_kernel, dim3(1), dim3(1), 0, st, step_dev); }

@@ -64,5 +64,7 @@ void pack_weights(const PackEntry* table_dev, int n_entries, int max_tiles, cuda
 void adamw_step(float* p, float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, float wd,
                 float grad_scale, const int* step_dev, cudaStream_t st);
 void increment_step(int* step_dev, cudaStream_t st);
+// occupy the stream for ~us microseconds (profiling aid: lets the host queue work ahead of the device)
+void stream_delay(unsigned us, cudaStream_t st);
 
 }  // namespace ub

@@ -1194,6 +1194,9 @@ extern "C" int ub_trainer_profile(UbTrainer* t, int reps, UbProfile* out) {
     t->comm_off = true;  // a profile is rank-local: the peers are not replaying with us
     for (int rep = 0; rep < reps; ++rep) {
         size_t k = 0;
+        // the host needs ~3 us per launch + event, many kernels run for less: park the stream for a few ms so that the
+        // whole tape is queued before the first op starts and the event intervals are pure device time
+        stream_delay(6000, st);
         cudaEventRecord(ev[k++], st);
         cudaMemsetAsync(t->zero_base, 0, t->zero_bytes, st);
         diffusion_prepare(t->x0, t->sqrt_ac, t->sqrt_1mac, c.B, size_t(c.C_in) * c.H * c.W, c.n_timesteps, c.seed,
