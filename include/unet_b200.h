@@ -220,6 +220,28 @@ int ub_trainer_launches_per_step(UbTrainer* t);
 /* forward only on a device batch that is ALREADY x_t (for sampling, generate.py:29-52): out_dev (B,C_out,H,W) */
 int ub_trainer_predict(UbTrainer* t, const float* xt_host, const float* t_host, float* out_host);
 
+/* DDPM ancestral sampling, the loop of generate.py:29-79 on the device: for t = t_start .. t_end (descending)
+ *   eps = model(x_t, t);  mu = (x_t - beta_t / sqrt(1 - acp_t) * eps) / sqrt(1 - beta_t);
+ *   x_{t-1} = mu + sqrt((1 - acp_{t-1}) / (1 - acp_t) * beta_t) * z,     beta_t = betas[t-1], acp_t = acp[t-1]
+ * on all B images of the trainer at once.  generate.py runs t = n_timesteps-1 .. 2 (pass t_start = -1, t_end = -1 for
+ * exactly that).  x_init_host (B,C_in,H,W) may be NULL: x_T ~ N(0,1) from `seed`.  noise_host may be NULL (z from the
+ * device Philox stream of `seed`), else it holds one (B,C_in,H,W) draw per iteration, first iteration first (parity
+ * runs inject the oracle's draws).  out_host (B,C_in,H,W) receives the final x.  One CUDA graph per iteration. */
+int ub_trainer_sample(UbTrainer* t, const float* x_init_host, int t_start, int t_end, const float* noise_host,
+                      unsigned long long seed, float* out_host);
+
+/* ---- dataset reader: prepare_data.py:20-38 format (int32[256] header {20240620, N, C, H, W} + float32 images),
+ * semantics of DataLoader / dataloader_next_batch (train_unet.cu:3035-3099): sequential batches of B images,
+ * wrapping to the start when fewer than B images remain.  Batches are prefetched by a background thread into two
+ * page-locked buffers, so the returned pointer can be handed to ub_trainer_train_step directly (async H2D).
+ * Data parallel: rank r of `world` reads global batches r, r + world, ... (each global step consumes world batches). */
+typedef struct UbDataLoader UbDataLoader;
+int ub_dataloader_open(UbDataLoader** out, const char* path, int B, int rank, int world);
+int ub_dataloader_info(UbDataLoader* d, int* n_imgs, int* C, int* H, int* W, long long* batches_per_epoch);
+const float* ub_dataloader_next(UbDataLoader* d);  /* valid until the next call; NULL on I/O error */
+void ub_dataloader_reset(UbDataLoader* d);
+void ub_dataloader_close(UbDataLoader* d);
+
 /* ---- per-kernel-class timing of one training step (CUDA events around every launch, eager replay of the tape).
  * Used by bench.py for the live roofline numbers. */
 #define UB_KIND_CONV 0    /* igemm_conv_kernel: 3x3 / 1x1 conv fprop + dgrad, attention qkv/proj GEMMs (tensor) */

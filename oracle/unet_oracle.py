@@ -357,6 +357,25 @@ def q_sample(x0: torch.Tensor, t: torch.Tensor, noise: torch.Tensor) -> torch.Te
     return a * x0 + b * noise
 
 
+def ddpm_sample(cfg: UNetConfig, P: Dict[str, torch.Tensor], x: torch.Tensor, t_start: int, t_end: int, noises,
+                T: int = 1000) -> torch.Tensor:
+    """generate.py:29-52 (sample_next_step) looped as generate.py:75-79 does: for t = t_start .. t_end (descending,
+    2 <= t < T) with beta_t = betas[t-1], alpha_t = acp[t-1], alpha_t_1 = acp[t-2];  noises[i] is the N(0,1) draw of
+    iteration i (generate.py draws it with torch.randn_like)."""
+    betas = torch.tensor(linear_betas(T), dtype=torch.float32)
+    acp = torch.tensor(np.cumprod(1.0 - linear_betas(T)), dtype=torch.float32)   # GaussianDiffusion.alphas_cumprod
+    with torch.no_grad():
+        for i, t in enumerate(range(t_start, t_end - 1, -1)):
+            assert 2 <= t < T
+            beta_t, alpha_t, alpha_t_1 = betas[t - 1], acp[t - 1], acp[t - 2]
+            tt = torch.full((x.shape[0], 1), float(t))
+            eps = unet_forward(cfg, P, x, tt)
+            mu = (x - (beta_t / torch.sqrt(1 - alpha_t)) * eps) / torch.sqrt(1 - beta_t)
+            sigma = torch.sqrt((1 - alpha_t_1) / (1 - alpha_t) * beta_t)
+            x = mu + sigma * noises[i]
+    return x
+
+
 def mse_loss(out: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     """train_unet.cu:2981-3030: mean over all elements."""
     return ((out - target) ** 2).mean()

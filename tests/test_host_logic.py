@@ -63,3 +63,31 @@ def test_shard_batch(ub):
     assert [ub.shard_batch(256, r, 8) for r in (0, 3, 7)] == [(0, 32), (96, 128), (224, 256)]
     with pytest.raises(ValueError):
         ub.shard_batch(10, 0, 4)
+
+
+def test_dataloader_batches_wrap_and_rank_striding(ub, oracle, tmp_path):
+    """ub_dataloader_* vs the semantics of DataLoader / dataloader_next_batch (train_unet.cu:3035-3099): sequential
+    batches of B, wrap to the start when fewer than B images remain; rank r of R reads global batches r, r+R, ..."""
+    rng = np.random.default_rng(3)
+    imgs = rng.uniform(-1, 1, (11, 3, 8, 8)).astype(np.float32)       # 11 images, B = 4 -> 2 full batches per epoch
+    path = str(tmp_path / "data.bin")
+    oracle.write_data_bin(path, imgs)
+    dl = ub.DataLoader(path, B=4)
+    assert (dl.n_imgs, dl.shape, dl.batches_per_epoch) == (11, (3, 8, 8), 2)
+    for k in range(5):                                                 # 0, 1, wrap -> 0, 1, 0
+        np.testing.assert_array_equal(dl.next(), imgs[(k % 2) * 4:(k % 2) * 4 + 4])
+    dl.reset()
+    np.testing.assert_array_equal(dl.next(), imgs[0:4])
+    dl.close()
+    imgs = rng.uniform(-1, 1, (24, 1, 4, 4)).astype(np.float32)        # 6 batches of 4, two ranks
+    oracle.write_data_bin(path, imgs)
+    r0, r1 = ub.DataLoader(path, B=4, rank=0, world=2), ub.DataLoader(path, B=4, rank=1, world=2)
+    for k in range(4):                                                 # rank 0: 0,2,4,0   rank 1: 1,3,5,1
+        np.testing.assert_array_equal(r0.next(), imgs[((2 * k) % 6) * 4:((2 * k) % 6) * 4 + 4])
+        np.testing.assert_array_equal(r1.next(), imgs[((2 * k + 1) % 6) * 4:((2 * k + 1) % 6) * 4 + 4])
+    r0.close(), r1.close()
+    with pytest.raises(ub.UbError):
+        ub.DataLoader(str(tmp_path / "missing.bin"), B=4)
+    (tmp_path / "bad.bin").write_bytes(b"\x00" * 2048)
+    with pytest.raises(ub.UbError):
+        ub.DataLoader(str(tmp_path / "bad.bin"), B=4)

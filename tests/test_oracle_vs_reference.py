@@ -57,3 +57,32 @@ def test_five_level_config_matches_reference(oracle, ref_unet):
     t = torch.tensor([[17.0]])
     with torch.no_grad():
         assert float((O.unet_forward(cfg, P, x, t) - model(x, t)).abs().max()) < 1e-5
+
+
+def test_sampler_matches_generate_py(oracle, ref_unet):
+    """oracle.ddpm_sample vs the reference's own generate.sample_next_step (generate.py:29-52), three steps."""
+    sys.path.insert(0, REF)
+    gen = pytest.importorskip("generate")     # imports PIL, tqdm and train_unet (all __main__-guarded)
+    O = oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.UNetConfig()
+    torch.manual_seed(0)
+    model = ref_unet.UNetModel(3, 64, 3, 2, (4, 8), num_head_channels=32).eval()
+    P = O.init_params(cfg, seed=0)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(1, 3, 64, 64, generator=g)
+    noises = [torch.randn(1, 3, 64, 64, generator=g) for _ in range(3)]
+    import train_unet as tu
+    betas = tu.get_named_beta_schedule("linear", 1000)
+    beta_t = torch.tensor(betas, dtype=torch.float32)
+    acp = torch.tensor(tu.GaussianDiffusion(betas=betas).alphas_cumprod)
+    x_ref = x.clone()
+    with torch.no_grad():
+        for i, t in enumerate([700, 699, 698]):
+            torch.manual_seed(1000 + i)
+            z = torch.randn_like(x_ref)        # what sample_next_step will draw
+            noises[i] = z
+            torch.manual_seed(1000 + i)
+            x_ref = gen.sample_next_step(x_ref, torch.tensor([[t]]), model, 1000, beta_t, acp).float()
+    x_or = O.ddpm_sample(cfg, P, x, 700, 698, noises)
+    assert float((x_or - x_ref).abs().max()) < 1e-4

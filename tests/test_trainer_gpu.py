@@ -223,3 +223,48 @@ def test_config5_128px_five_levels_matches_oracle(ub, oracle):
     assert cos > 0.9995, cos
     assert np.linalg.norm(g - g_ref) <= 2e-2 * np.linalg.norm(g_ref)
     tr.close()
+
+
+def test_sampler_matches_oracle(ub, setup):
+    """ub_trainer_sample (generate.py:29-79 on the device) vs oracle.ddpm_sample with the same injected draws: three
+    iterations at small t (where the update weights eps the most), B = 2; then a run with device-side noise."""
+    O, cfg, flat = setup
+    P = O.unflatten_params(cfg, flat)
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(2, 3, 64, 64, generator=g)
+    noises = [torch.randn(2, 3, 64, 64, generator=g) for _ in range(3)]
+    ref = O.ddpm_sample(cfg, P, x, 40, 38, noises).numpy()
+    tr = ub.Trainer(B=2)
+    tr.set_params(flat.numpy())
+    out = tr.sample(x.numpy(), 40, 38, torch.stack(noises).numpy())
+    assert np.abs(out - ref).max() <= 3e-2 * np.abs(ref).max()
+    # device-side draws: finite, roughly unit scale after a few steps from N(0,1); a fixed seed reproduces the run up
+    # to the summation order of the GroupNorm-statistics atomics (bf16 roundings downstream), a new seed does not
+    a = tr.sample(None, 999, 990, None, seed=5)
+    b = tr.sample(None, 999, 990, None, seed=5)
+    c = tr.sample(None, 999, 990, None, seed=6)
+    assert np.isfinite(a).all() and 0.5 < a.std() < 2.0
+    assert np.abs(a - b).max() < 2e-2 and np.abs(a - c).max() > 0.5
+    tr.close()
+
+
+def test_train_from_dataloader(ub, setup, tmp_path):
+    """The reference's loop (train_unet.cu:5019-5037) end to end: prepare_data.py-format file -> prefetching reader ->
+    pinned buffer -> train step; the loss of a step on a loader batch equals the loss on the same images passed in."""
+    O, cfg, flat = setup
+    rng = np.random.default_rng(0)
+    imgs = rng.uniform(-1, 1, (12, 3, 64, 64)).astype(np.float32)
+    path = str(tmp_path / "train.bin")
+    O.write_data_bin(path, imgs)
+    dl = ub.DataLoader(path, B=4)
+    _, t, noise = O.synthetic_batch(cfg, 4)
+    tr = ub.Trainer(B=4)
+    tr.set_params(flat.numpy())
+    l_direct = tr.forward_backward(imgs[0:4], t.numpy(), noise.numpy())
+    import ctypes as C
+    loss = C.c_float()
+    rc = ub.lib().ub_trainer_forward_backward(tr._h, C.cast(dl.next_ptr(), C.POINTER(C.c_float)),
+                                              t.numpy().ctypes.data_as(C.POINTER(C.c_float)),
+                                              noise.numpy().ctypes.data_as(C.POINTER(C.c_float)), C.byref(loss))
+    assert rc == 0 and abs(loss.value - l_direct) < 1e-3
+    tr.close(), dl.close()

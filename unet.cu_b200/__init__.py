@@ -85,6 +85,16 @@ def _declare(L: C.CDLL) -> None:
     L.ub_trainer_launches_per_step.argtypes = [vp]
     L.ub_trainer_predict.argtypes = [vp, fp, fp, fp]
     L.ub_trainer_profile.argtypes = [vp, i, C.POINTER(UbProfile)]
+    L.ub_trainer_sample.argtypes = [vp, fp, i, i, fp, C.c_ulonglong, fp]
+    L.ub_dataloader_open.argtypes = [C.POINTER(vp), C.c_char_p, i, i, i]
+    L.ub_dataloader_info.argtypes = [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i),
+                                     C.POINTER(C.c_longlong)]
+    L.ub_dataloader_next.argtypes = [vp]
+    L.ub_dataloader_next.restype = vp
+    L.ub_dataloader_reset.argtypes = [vp]
+    L.ub_dataloader_reset.restype = None
+    L.ub_dataloader_close.argtypes = [vp]
+    L.ub_dataloader_close.restype = None
     L.ub_nccl_get_unique_id.argtypes = [vp]
     L.ub_trainer_attach_dp.argtypes = [vp, i, i, vp, i]
 
@@ -227,9 +237,55 @@ class Trainer:
         return out
 
     # -- data parallel
+    def sample(self, x_init=None, t_start: int = -1, t_end: int = -1, noises=None, seed: int = 0) -> np.ndarray:
+        """DDPM ancestral sampling (generate.py:29-79) of B images; noises: (iterations, B, C, H, W) or None."""
+        c = self.cfg
+        x_init = None if x_init is None else np.ascontiguousarray(x_init, dtype=np.float32)
+        noises = None if noises is None else np.ascontiguousarray(noises, dtype=np.float32)
+        out = np.empty((c.B, c.C_in, c.H, c.W), dtype=np.float32)
+        check(lib().ub_trainer_sample(self._h, _ptr(x_init), t_start, t_end, _ptr(noises), seed, _ptr(out)), "sample")
+        return out
+
     def attach_dp(self, rank: int, world: int, nccl_id: bytes, n_buckets: int = 4):
         buf = C.create_string_buffer(nccl_id, UB_NCCL_ID_BYTES)
         check(lib().ub_trainer_attach_dp(self._h, rank, world, buf, n_buckets), "attach_dp")
+
+
+class DataLoader:
+    """prepare_data.py-format reader with background prefetch (mirror of DataLoader, train_unet.cu:3035-3099)."""
+
+    def __init__(self, path: str, B: int, rank: int = 0, world: int = 1):
+        self._h = C.c_void_p()
+        check(lib().ub_dataloader_open(C.byref(self._h), path.encode(), B, rank, world), "ub_dataloader_open")
+        n, c, h, w, nb = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_longlong()
+        lib().ub_dataloader_info(self._h, C.byref(n), C.byref(c), C.byref(h), C.byref(w), C.byref(nb))
+        self.B, self.n_imgs, self.shape, self.batches_per_epoch = B, n.value, (c.value, h.value, w.value), nb.value
+
+    def next_ptr(self) -> int:
+        """Address of the (page-locked) buffer holding the next batch; valid until the following call."""
+        p = lib().ub_dataloader_next(self._h)
+        if not p:
+            raise UbError("ub_dataloader_next failed: " + lib().ub_last_error().decode())
+        return p
+
+    def next(self) -> np.ndarray:
+        n = self.B * int(np.prod(self.shape))
+        buf = (C.c_float * n).from_address(self.next_ptr())
+        return np.frombuffer(buf, dtype=np.float32).reshape((self.B,) + self.shape).copy()
+
+    def reset(self):
+        lib().ub_dataloader_reset(self._h)
+
+    def close(self):
+        if self._h:
+            lib().ub_dataloader_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def nccl_unique_id() -> bytes:

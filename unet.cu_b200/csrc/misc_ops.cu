@@ -561,6 +561,63 @@ void adamw_step(float* p, float* g, float* m, float* v, size_t n, float lr, floa
     launch_pdl(adamw_kernel, dim3(unsigned((n4 + 1 + 255) / 256)), dim3(256), 0, st, p, g, m, v, n4, n, lr, b1, b2, eps, wd, grad_scale,
                                                                 step_dev);
 }
+// ---- DDPM sampling
+__global__ void sample_set_t_kernel(const int* __restrict__ t_dev, int B, float* __restrict__ tsteps) {
+    pdl_entry();
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) tsteps[b] = float(*t_dev);
+}
+void sample_set_t(const int* t_dev, int B, float* tsteps, cudaStream_t st) {
+    launch_pdl(sample_set_t_kernel, dim3((B + 127) / 128), dim3(128), 0, st, t_dev, B, tsteps);
+}
+__device__ __forceinline__ float4 philox_normal4(uint64_t i4, uint32_t stream, uint32_t ctr, uint64_t seed) {
+    const uint4 r = philox4x32_10(make_uint4(uint32_t(i4), uint32_t(i4 >> 32), stream, ctr),
+                                  make_uint2(uint32_t(seed), uint32_t(seed >> 32)));
+    const float r0 = sqrtf(-2.f * logf(u01(r.x))), r1 = sqrtf(-2.f * logf(u01(r.z)));
+    float s0, c0, s1, c1;
+    sincospif(2.f * u01(r.y), &s0, &c0);
+    sincospif(2.f * u01(r.w), &s1, &c1);
+    return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+}
+__global__ void ddpm_step_kernel(float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ betas,
+                                 const float* __restrict__ sqrt_ac, const float* __restrict__ sqrt_1mac,
+                                 const float* __restrict__ z, size_t n4, uint64_t seed, const int* __restrict__ t_dev,
+                                 const int* __restrict__ it_dev) {
+    pdl_entry();
+    const size_t i4 = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i4 >= n4) return;
+    const int t = *t_dev;  // generate.py: beta_t = betas[t-1], alpha_t = acp[t-1], alpha_t_1 = acp[t-2]
+    const float beta = betas[t - 1];
+    const float om_t = sqrt_1mac[t - 1] * sqrt_1mac[t - 1], om_t1 = sqrt_1mac[t - 2] * sqrt_1mac[t - 2];
+    const float c_eps = beta / sqrt_1mac[t - 1], inv = rsqrtf(1.f - beta), sigma = sqrtf(om_t1 / om_t * beta);
+    const float4 xv = reinterpret_cast<const float4*>(x)[i4], ev = reinterpret_cast<const float4*>(eps)[i4];
+    const float4 zv = z ? reinterpret_cast<const float4*>(z)[i4] : philox_normal4(i4, 0x3u, uint32_t(*it_dev), seed);
+    reinterpret_cast<float4*>(x)[i4] =
+        make_float4((xv.x - c_eps * ev.x) * inv + sigma * zv.x, (xv.y - c_eps * ev.y) * inv + sigma * zv.y,
+                    (xv.z - c_eps * ev.z) * inv + sigma * zv.z, (xv.w - c_eps * ev.w) * inv + sigma * zv.w);
+}
+__global__ void sample_advance_kernel(int* t_dev, int* it_dev) {
+    pdl_entry();
+    *t_dev -= 1;
+    *it_dev += 1;
+}
+void ddpm_step(float* x, const float* eps, const float* betas, const float* sqrt_ac, const float* sqrt_1mac,
+               const float* z, size_t n, uint64_t seed, int* t_dev, int* it_dev, cudaStream_t st) {
+    const size_t n4 = n / 4;
+    launch_pdl(ddpm_step_kernel, dim3(unsigned((n4 + 255) / 256)), dim3(256), 0, st, x, eps, betas, sqrt_ac, sqrt_1mac,
+               z, n4, seed, static_cast<const int*>(t_dev), static_cast<const int*>(it_dev));
+    launch_pdl(sample_advance_kernel, dim3(1), dim3(1), 0, st, t_dev, it_dev);
+}
+__global__ void fill_normal_kernel(float* __restrict__ x, size_t n4, uint64_t seed) {
+    pdl_entry();
+    const size_t i4 = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i4 < n4) reinterpret_cast<float4*>(x)[i4] = philox_normal4(i4, 0x2u, 0u, seed);
+}
+void fill_normal(float* x, size_t n, uint64_t seed, cudaStream_t st) {
+    const size_t n4 = n / 4;
+    launch_pdl(fill_normal_kernel, dim3(unsigned((n4 + 255) / 256)), dim3(256), 0, st, x, n4, seed);
+}
+
 // Keeps the stream busy for ~`us` microseconds: the profile replay enqueues a whole step behind it, so the per-op
 // CUDA-event intervals measure device time, not how fast the host can submit launches.
 __global__ void delay_kernel(unsigned us) {

@@ -64,6 +64,15 @@ void pack_weights(const PackEntry* table_dev, int n_entries, int max_tiles, cuda
 void adamw_step(float* p, float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, float wd,
                 float grad_scale, const int* step_dev, cudaStream_t st);
 void increment_step(int* step_dev, cudaStream_t st);
+
+// ---- DDPM sampling step (generate.py:29-52).  t_dev holds the current t (2 <= t < T): fill t for the embedding,
+//      then (after the forward) x <- mu(x, eps, t) + sigma_t * z and t_dev <- t - 1.
+void sample_set_t(const int* t_dev, int B, float* tsteps, cudaStream_t st);
+// z: injected noise for this iteration (may be null: Philox(seed, counter = iteration index from it_dev))
+void ddpm_step(float* x, const float* eps, const float* betas, const float* sqrt_ac, const float* sqrt_1mac,
+               const float* z, size_t n, uint64_t seed, int* t_dev, int* it_dev, cudaStream_t st);
+// x ~ N(0,1) (Philox4x32-10, key = seed, stream id 0x2)
+void fill_normal(float* x, size_t n, uint64_t seed, cudaStream_t st);
 // occupy the stream for ~us microseconds (profiling aid: lets the host queue work ahead of the device)
 void stream_delay(unsigned us, cudaStream_t st);
 

@@ -120,7 +120,11 @@ struct UbTrainer {
     DeviceArena zarena;
     // io buffers
     float *x0 = nullptr, *xt = nullptr, *noise = nullptr, *tsteps = nullptr, *out = nullptr, *dout = nullptr;
-    float *loss = nullptr, *sqrt_ac = nullptr, *sqrt_1mac = nullptr;
+    float *loss = nullptr, *sqrt_ac = nullptr, *sqrt_1mac = nullptr, *betas = nullptr;
+    int* samp_state = nullptr;  // {t, iteration} of the sampling loop
+    cudaGraphExec_t samp_graph = nullptr;
+    bool samp_graph_noise = false;
+    float* samp_z = nullptr;  // injected noise of the current iteration (graph reads a fixed address)
     int* step_dev = nullptr;
     float *h_x0 = nullptr, *h_noise = nullptr, *h_t = nullptr, *h_loss = nullptr;  // pinned staging
     // wgrad workspace
@@ -583,7 +587,9 @@ int Builder::build() {
     T->x0 = f32(size_t(B) * img), T->xt = f32(size_t(B) * img), T->noise = f32(size_t(B) * img);
     T->tsteps = f32(B);
     T->out = f32(size_t(B) * c.C_out * H0 * W0), T->dout = f32(size_t(B) * c.C_out * H0 * W0);
-    T->sqrt_ac = f32(c.n_timesteps), T->sqrt_1mac = f32(c.n_timesteps);
+    T->sqrt_ac = f32(c.n_timesteps), T->sqrt_1mac = f32(c.n_timesteps), T->betas = f32(c.n_timesteps);
+    T->samp_state = (int*)T->arena.alloc(256);
+    T->samp_z = f32(size_t(B) * img);
     T->step_dev = (int*)T->arena.alloc(256);
     T->loss = zf32(64);
     T->sin_emb = f32(size_t(B) * Cm), T->h0 = f32(size_t(B) * Cemb), T->emb = f32(size_t(B) * Cemb);
@@ -954,14 +960,15 @@ extern "C" int ub_trainer_create(UbTrainer** out, const UbConfig* cfg, int devic
     // (train_unet.py:811-826, 875-892; train_unet.cu:3131-3147)
     {
         const int n = cfg->n_timesteps;
-        std::vector<float> sa(n), sb(n);
+        std::vector<float> sa(n), sb(n), bt(n);
         const double scale = 1000.0 / n, b0 = scale * 0.0001, b1 = scale * 0.02;
         float ac = 1.f;
         for (int i = 0; i < n; ++i) {
             const float beta = float(n > 1 ? b0 + (b1 - b0) * double(i) / double(n - 1) : b0);
             ac = ac * (1.f - beta);
-            sa[i] = sqrtf(ac), sb[i] = sqrtf(1.f - ac);
+            sa[i] = sqrtf(ac), sb[i] = sqrtf(1.f - ac), bt[i] = beta;
         }
+        cudaMemcpy(t->betas, bt.data(), n * sizeof(float), cudaMemcpyHostToDevice);
         cudaMemcpy(t->sqrt_ac, sa.data(), n * sizeof(float), cudaMemcpyHostToDevice);
         cudaMemcpy(t->sqrt_1mac, sb.data(), n * sizeof(float), cudaMemcpyHostToDevice);
     }
@@ -985,6 +992,7 @@ extern "C" void ub_trainer_destroy(UbTrainer* t) {
     cudaSetDevice(t->device);
     cudaDeviceSynchronize();
     if (t->graph_exec) cudaGraphExecDestroy(t->graph_exec);
+    if (t->samp_graph) cudaGraphExecDestroy(t->samp_graph);
     if (t->comm && nccl().ok) nccl().CommDestroy(t->comm);
     if (t->params) cudaFree(t->params);
     if (t->h_x0) cudaFreeHost(t->h_x0);
@@ -1279,6 +1287,66 @@ extern "C" int ub_trainer_predict(UbTrainer* t, const float* xt_host, const floa
     for (auto& op : t->fwd_ops) op(t->stream);
     CUDA_TRY(cudaMemcpyAsync(out_host, t->out, oimg * sizeof(float), cudaMemcpyDeviceToHost, t->stream));
     CUDA_TRY(cudaStreamSynchronize(t->stream));
+    return UB_OK;
+}
+
+// generate.py:29-79 on the device (see include/unet_b200.h)
+extern "C" int ub_trainer_sample(UbTrainer* t, const float* x_init_host, int t_start, int t_end,
+                                 const float* noise_host, unsigned long long seed, float* out_host) {
+    CUDA_TRY(cudaSetDevice(t->device));
+    const UbConfig& c = t->cfg;
+    if (c.C_in != c.C_out) {
+        set_err("sampling needs C_in == C_out");
+        return UB_ERR_SHAPE;
+    }
+    if (t_start < 0) t_start = c.n_timesteps - 1;
+    if (t_end < 0) t_end = 2;
+    if (t_start >= c.n_timesteps || t_end < 2 || t_end > t_start) {
+        set_err("sampling range must satisfy 2 <= t_end <= t_start < n_timesteps");
+        return UB_ERR_SHAPE;
+    }
+    const size_t img = size_t(c.B) * c.C_in * c.H * c.W;
+    cudaStream_t st = t->stream;
+    if (x_init_host)
+        CUDA_TRY(cudaMemcpyAsync(t->xt, x_init_host, img * sizeof(float), cudaMemcpyHostToDevice, st));
+    else
+        fill_normal(t->xt, img, seed, st);
+    const int state[2] = {t_start, 0};
+    CUDA_TRY(cudaMemcpyAsync(t->samp_state, state, sizeof state, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(t->noise, 0, img * sizeof(float), st));  // (the forward tape ends with the MSE vs noise)
+    const bool inject = noise_host != nullptr;
+    if (!t->samp_graph || t->samp_graph_noise != inject) {
+        if (t->samp_graph) cudaGraphExecDestroy(t->samp_graph), t->samp_graph = nullptr;
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        cudaMemsetAsync(t->zero_base, 0, t->zero_bytes, st);
+        sample_set_t(t->samp_state, c.B, t->tsteps, st);
+        for (auto& op : t->fwd_ops) op(st);
+        ddpm_step(t->xt, t->out, t->betas, t->sqrt_ac, t->sqrt_1mac, inject ? t->samp_z : nullptr, img, seed,
+                  t->samp_state, t->samp_state + 1, st);
+        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        if (e != cudaSuccess || !graph) {
+            set_err("sampling graph capture failed: %s", cudaGetErrorString(e));
+            return UB_ERR_CUDA;
+        }
+        e = cudaGraphInstantiate(&t->samp_graph, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            set_err("sampling graph instantiate failed: %s", cudaGetErrorString(e));
+            return UB_ERR_CUDA;
+        }
+        t->samp_graph_noise = inject;
+    }
+    for (int tt = t_start, it = 0; tt >= t_end; --tt, ++it) {
+        if (inject)
+            CUDA_TRY(cudaMemcpyAsync(t->samp_z, noise_host + size_t(it) * img, img * sizeof(float),
+                                     cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaGraphLaunch(t->samp_graph, st));
+        ub_count_launches((unsigned long long)(t->launches_fwd + 3));
+    }
+    CUDA_TRY(cudaMemcpyAsync(out_host, t->xt, img * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return UB_OK;
 }
 
