@@ -128,6 +128,47 @@ int ub_attention_forward1(float* out, float* qkvr, float* preatt, float* att, co
 int ub_attention_backward(float* dinp, float* dqkvr, float* dpreatt, float* datt, float* scratch, const float* dout,
                           const float* qkvr, const float* att, int B, int T, int C, int NH);
 
+/* ---- composite blocks (dev/resblock.cuh:71-131, dev/attention_block.cuh:78-112).  The structs carry the same
+ * tensors, in the same order and with the same meaning, as ResBlockParameters / ResBlockActivations /
+ * ResBlockBackwardActivations and AttentionParams / AttentionActs / AttentionBackwardActs (the size arrays of the
+ * reference structs are bookkeeping of its arena planner and are not needed here); include/unet_b200_legacy.hpp maps
+ * the reference structs onto them.  All tensors fp32, NCHW / row-major, device memory owned by the caller; every
+ * intermediate the reference materialises is written (its unit tests compare them, dev/resblock.cu:542-630).
+ * Backward clobbers the forward activations the reference clobbers (cv3_2, add2, ud_x, silu1, l_emb) and writes
+ * dx / demb (resblock) or dinp (attention); conv / linear gradients are overwritten, GroupNorm gradients accumulate. */
+typedef struct {
+    float *gn1_w, *gn1_b, *cv3_1_w, *cv3_1_b, *l_emb_w, *l_emb_b, *gn2_w, *gn2_b, *cv3_2_w, *cv3_2_b, *res_cv1_w,
+        *res_cv1_b;
+} UbResBlockParams;
+typedef struct {
+    float *gn1, *gn1_mean, *gn1_rstd, *silu1, *ud_h, *ud_x, *cv3_1, *silu_emb, *l_emb, *broad_emb, *add1, *gn2,
+        *gn2_mean, *gn2_rstd, *silu2, *cv3_2, *res_cv1, *add2;
+    float *input, *emb;
+} UbResBlockActs;
+typedef struct {
+    float *buf_BCemb, *buf_BCHoWo, *buf1_BCHW, *buf2_BCHW, *dout, *dx, *demb;
+} UbResBlockBack;
+int ub_resblock_forward(int C, int C_emb, int C_out, int B, int H, int W, int up, int down, int gn_n_groups,
+                        const UbResBlockParams* params, const UbResBlockActs* acts);
+int ub_resblock_backward(int C, int C_emb, int C_out, int B, int H, int W, int up, int down, int gn_n_groups,
+                         const UbResBlockParams* params, const UbResBlockParams* grads, const UbResBlockActs* acts,
+                         const UbResBlockBack* back);
+typedef struct {
+    float *gn_w, *gn_b, *qkv_w, *qkv_b, *proj_w, *proj_b;
+} UbAttentionParams;
+typedef struct {
+    float *gn, *gn_mean, *gn_rstd, *perm1, *qkv1, *qkv2, *preatt, *att, *att_out, *proj, *perm2, *add;
+    float* input;
+} UbAttentionActs;
+typedef struct {
+    float *buf1_BCHW, *buf2_BCHW, *buf_B3CHW, *dqkvr, *dpreatt, *datt, *dout, *dinp;
+} UbAttentionBack;
+int ub_attention_block_forward(int B, int C, int H, int W, int HS, int gn_n_groups, const UbAttentionParams* params,
+                               const UbAttentionActs* acts);
+int ub_attention_block_backward(int B, int C, int H, int W, int HS, int gn_n_groups, const UbAttentionParams* params,
+                                const UbAttentionActs* acts, const UbAttentionBack* back,
+                                const UbAttentionParams* grads);
+
 /* ---- native operand layout of the tensor-core path: NHWC bf16 activations, packed bf16 weights.  The reference has
  * no equivalent; a caller that keeps its activations in this layout skips the NCHW fp32 <-> NHWC bf16 conversion the
  * drop-in operators above have to do (this is what the trainer does internally).  ksize = 1 or 3.

@@ -153,3 +153,143 @@ inline void attention_backward(cublasHandle_t, float* dinp, float* dqkvr, float*
                                const float* dout, const float* qkvr, const float* att, int B, int T, int C, int NH) {
     UB_LEGACY_CHECK(ub_attention_backward(dinp, dqkvr, dpreatt, datt, scratch, dout, qkvr, att, B, T, C, NH));
 }
+
+// ---- dev/resblock.cuh: struct layouts kept field for field (callers fill them, train_unet.cu:3877-4083)
+#define NUM_RES_PARAM_TENSORS 12
+typedef struct {
+    float *gn1_w, *gn1_b, *cv3_1_w, *cv3_1_b, *l_emb_w, *l_emb_b, *gn2_w, *gn2_b, *cv3_2_w, *cv3_2_b, *res_cv1_w,
+        *res_cv1_b;
+    size_t param_sizes[NUM_RES_PARAM_TENSORS];
+    size_t n_params;
+} ResBlockParameters;
+#define NUM_RES_ACT_TENSORS 18
+typedef struct {
+    float *gn1, *gn1_mean, *gn1_rstd, *silu1, *ud_h, *ud_x, *cv3_1, *silu_emb, *l_emb, *broad_emb, *add1, *gn2,
+        *gn2_mean, *gn2_rstd, *silu2, *cv3_2, *res_cv1, *add2;
+    size_t act_sizes[NUM_RES_ACT_TENSORS];
+    size_t n_acts;
+    float* input;
+    float* emb;
+} ResBlockActivations;
+#define NUM_RES_BACKWARD_TENSORS 7
+typedef struct {
+    float *buf_BCemb, *buf_BCHoWo, *buf1_BCHW, *buf2_BCHW, *dout, *dweight_buf, *dbias_buf, *dx, *demb;
+    size_t back_sizes[NUM_RES_BACKWARD_TENSORS];
+    size_t n_backs;
+} ResBlockBackwardActivations;
+
+inline UbResBlockParams ub_legacy_params(const ResBlockParameters* p) {
+    return UbResBlockParams{p->gn1_w, p->gn1_b, p->cv3_1_w, p->cv3_1_b, p->l_emb_w, p->l_emb_b,
+                            p->gn2_w, p->gn2_b, p->cv3_2_w, p->cv3_2_b, p->res_cv1_w, p->res_cv1_b};
+}
+inline UbResBlockActs ub_legacy_acts(const ResBlockActivations* a) {
+    return UbResBlockActs{a->gn1, a->gn1_mean, a->gn1_rstd, a->silu1, a->ud_h, a->ud_x, a->cv3_1, a->silu_emb, a->l_emb,
+                          a->broad_emb, a->add1, a->gn2, a->gn2_mean, a->gn2_rstd, a->silu2, a->cv3_2, a->res_cv1,
+                          a->add2, a->input, a->emb};
+}
+// tensor sizes / pointer carving of the reference's arena planner (dev/resblock.cu:204-330): same order, same sizes
+inline void resblock_count_params(ResBlockParameters* p, int C, int C_emb, int C_out, int, int, int, int, int, int) {
+    const size_t s[NUM_RES_PARAM_TENSORS] = {size_t(C), size_t(C), size_t(C_out) * C * 9, size_t(C_out),
+                                             size_t(C_out) * C_emb, size_t(C_out), size_t(C_out), size_t(C_out),
+                                             size_t(C_out) * C_out * 9, size_t(C_out),
+                                             C == C_out ? 0 : size_t(C_out) * C, C == C_out ? 0 : size_t(C_out)};
+    p->n_params = 0;
+    for (int i = 0; i < NUM_RES_PARAM_TENSORS; ++i) p->param_sizes[i] = s[i], p->n_params += s[i];
+}
+inline void set_resblock_params_ptrs(int, int, ResBlockParameters* p, float* mem) {
+    float** ptrs[NUM_RES_PARAM_TENSORS] = {&p->gn1_w, &p->gn1_b, &p->cv3_1_w, &p->cv3_1_b, &p->l_emb_w, &p->l_emb_b,
+                                          &p->gn2_w, &p->gn2_b, &p->cv3_2_w, &p->cv3_2_b, &p->res_cv1_w, &p->res_cv1_b};
+    for (int i = 0; i < NUM_RES_PARAM_TENSORS; ++i) *ptrs[i] = mem, mem += p->param_sizes[i];
+}
+inline void resblock_count_acts(ResBlockActivations* a, int C, int C_emb, int C_out, int B, int H, int W, int up,
+                                int down, int gn_n_groups) {
+    const int Ho = up ? 2 * H : (down ? H / 2 : H), Wo = up ? 2 * W : (down ? W / 2 : W);
+    const size_t in = size_t(B) * C * H * W, mid = size_t(B) * C * Ho * Wo, out = size_t(B) * C_out * Ho * Wo;
+    const size_t g = size_t(B) * gn_n_groups;
+    const size_t s[NUM_RES_ACT_TENSORS] = {in, g, g, in, mid, mid, out, size_t(B) * C_emb, size_t(B) * C_out, out, out,
+                                           out, g, g, out, out, C == C_out ? 0 : out, out};
+    a->n_acts = 0;
+    for (int i = 0; i < NUM_RES_ACT_TENSORS; ++i) a->act_sizes[i] = s[i], a->n_acts += s[i];
+}
+inline void set_resblock_acts_ptrs(int, int, ResBlockActivations* a, float* mem) {
+    float** ptrs[NUM_RES_ACT_TENSORS] = {&a->gn1, &a->gn1_mean, &a->gn1_rstd, &a->silu1, &a->ud_h, &a->ud_x,
+                                        &a->cv3_1, &a->silu_emb, &a->l_emb, &a->broad_emb, &a->add1, &a->gn2,
+                                        &a->gn2_mean, &a->gn2_rstd, &a->silu2, &a->cv3_2, &a->res_cv1, &a->add2};
+    for (int i = 0; i < NUM_RES_ACT_TENSORS; ++i) *ptrs[i] = mem, mem += a->act_sizes[i];
+}
+inline void resblock_forward(cublasHandle_t, int C, int C_emb, int C_out, int B, int H, int W, int /*block_size*/, int up,
+                             int down, int gn_n_groups, ResBlockParameters* params, ResBlockActivations* acts) {
+    const UbResBlockParams p = ub_legacy_params(params);
+    const UbResBlockActs a = ub_legacy_acts(acts);
+    UB_LEGACY_CHECK(ub_resblock_forward(C, C_emb, C_out, B, H, W, up, down, gn_n_groups, &p, &a));
+}
+inline void resblock_backward(cublasHandle_t, int C, int C_emb, int C_out, int B, int H, int W, int /*block_size*/, int up,
+                              int down, int gn_n_groups, ResBlockParameters* params, ResBlockParameters* grads,
+                              ResBlockActivations* acts, ResBlockBackwardActivations* back_acts) {
+    const UbResBlockParams p = ub_legacy_params(params), g = ub_legacy_params(grads);
+    const UbResBlockActs a = ub_legacy_acts(acts);
+    const UbResBlockBack k{back_acts->buf_BCemb, back_acts->buf_BCHoWo, back_acts->buf1_BCHW, back_acts->buf2_BCHW,
+                           back_acts->dout, back_acts->dx, back_acts->demb};
+    UB_LEGACY_CHECK(ub_resblock_backward(C, C_emb, C_out, B, H, W, up, down, gn_n_groups, &p, &g, &a, &k));
+}
+
+// ---- dev/attention_block.cuh
+#define NUM_ATT_PARAM_TENSORS 6
+typedef struct {
+    float *gn_w, *gn_b, *qkv_w, *qkv_b, *proj_w, *proj_b;
+    size_t param_sizes[NUM_ATT_PARAM_TENSORS];
+    size_t n_params;
+} AttentionParams;
+#define NUM_ATT_ACT_TENSORS 12
+typedef struct {
+    float *gn, *gn_mean, *gn_rstd, *perm1, *qkv1, *qkv2, *preatt, *att, *att_out, *proj, *perm2, *add;
+    size_t act_sizes[NUM_ATT_ACT_TENSORS];
+    size_t n_acts;
+    float* input;
+} AttentionActs;
+#define NUM_ATT_BACKWARD_ACTS_TENSORS 7
+typedef struct {
+    float *buf1_BCHW, *buf2_BCHW, *buf_B3CHW, *dqkvr, *dpreatt, *datt, *dout, *dinp;
+    size_t back_sizes[NUM_ATT_BACKWARD_ACTS_TENSORS];
+    size_t n_backs;
+} AttentionBackwardActs;
+
+inline void attention_block_count_params(AttentionParams* p, int C) {
+    const size_t s[NUM_ATT_PARAM_TENSORS] = {size_t(C), size_t(C), size_t(3) * C * C, size_t(3) * C, size_t(C) * C,
+                                             size_t(C)};
+    p->n_params = 0;
+    for (int i = 0; i < NUM_ATT_PARAM_TENSORS; ++i) p->param_sizes[i] = s[i], p->n_params += s[i];
+}
+inline void attention_block_count_acts(AttentionActs* a, int B, int C, int H, int W, int gn_n_groups, int HS) {
+    const size_t T = size_t(H) * W, x = size_t(B) * C * T, g = size_t(B) * gn_n_groups, tt = size_t(B) * (C / HS) * T * T;
+    const size_t s[NUM_ATT_ACT_TENSORS] = {x, g, g, x, 3 * x, 3 * x, tt, tt, x, x, x, x};
+    a->n_acts = 0;
+    for (int i = 0; i < NUM_ATT_ACT_TENSORS; ++i) a->act_sizes[i] = s[i], a->n_acts += s[i];
+}
+inline void set_attention_params_pointers(AttentionParams* p, float* mem) {
+    float** ptrs[NUM_ATT_PARAM_TENSORS] = {&p->gn_w, &p->gn_b, &p->qkv_w, &p->qkv_b, &p->proj_w, &p->proj_b};
+    for (int i = 0; i < NUM_ATT_PARAM_TENSORS; ++i) *ptrs[i] = mem, mem += p->param_sizes[i];
+}
+inline void set_attention_acts_pointers(AttentionActs* a, float* mem) {
+    float** ptrs[NUM_ATT_ACT_TENSORS] = {&a->gn, &a->gn_mean, &a->gn_rstd, &a->perm1, &a->qkv1, &a->qkv2,
+                                        &a->preatt, &a->att, &a->att_out, &a->proj, &a->perm2, &a->add};
+    for (int i = 0; i < NUM_ATT_ACT_TENSORS; ++i) *ptrs[i] = mem, mem += a->act_sizes[i];
+}
+inline void attention_block_forward(cublasHandle_t, int B, int C, int H, int W, int HS, int gn_n_groups,
+                                    int /*block_size*/, AttentionParams* params, AttentionActs* acts) {
+    const UbAttentionParams p{params->gn_w, params->gn_b, params->qkv_w, params->qkv_b, params->proj_w, params->proj_b};
+    const UbAttentionActs a{acts->gn, acts->gn_mean, acts->gn_rstd, acts->perm1, acts->qkv1, acts->qkv2, acts->preatt,
+                            acts->att, acts->att_out, acts->proj, acts->perm2, acts->add, acts->input};
+    UB_LEGACY_CHECK(ub_attention_block_forward(B, C, H, W, HS, gn_n_groups, &p, &a));
+}
+inline void attention_block_backward(cublasHandle_t, int B, int C, int H, int W, int HS, int gn_n_groups,
+                                     int /*block_size*/, AttentionParams* params, AttentionActs* acts,
+                                     AttentionBackwardActs* back_acts, AttentionParams* grads) {
+    const UbAttentionParams p{params->gn_w, params->gn_b, params->qkv_w, params->qkv_b, params->proj_w, params->proj_b};
+    const UbAttentionParams g{grads->gn_w, grads->gn_b, grads->qkv_w, grads->qkv_b, grads->proj_w, grads->proj_b};
+    const UbAttentionActs a{acts->gn, acts->gn_mean, acts->gn_rstd, acts->perm1, acts->qkv1, acts->qkv2, acts->preatt,
+                            acts->att, acts->att_out, acts->proj, acts->perm2, acts->add, acts->input};
+    const UbAttentionBack k{back_acts->buf1_BCHW, back_acts->buf2_BCHW, back_acts->buf_B3CHW, back_acts->dqkvr,
+                            back_acts->dpreatt, back_acts->datt, back_acts->dout, back_acts->dinp};
+    UB_LEGACY_CHECK(ub_attention_block_backward(B, C, H, W, HS, gn_n_groups, &p, &a, &k, &g));
+}

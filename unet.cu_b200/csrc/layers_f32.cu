@@ -598,5 +598,31 @@ void linear_bwd(float* dinp, float* dw, float* db, const float* dout, const floa
     if (dinp) linear_bwd_x_kernel<<<unsigned((size_t(N) * C + 255) / 256), 256, 0, st>>>(dinp, dout, w, N, C, OC);
 }
 
+// (B, R, Cc) -> (B, Cc, R) for fp32 matrices, 32x32 tiles through smem: both sides coalesced
+__global__ void transpose_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int R, int Cc) {
+    __shared__ float t[32][33];
+    const size_t base = size_t(blockIdx.z) * R * Cc;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        if (r < R && c < Cc) t[i][threadIdx.x] = x[base + size_t(r) * Cc + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < R && c < Cc) y[base + size_t(c) * R + r] = t[threadIdx.x][i];
+    }
+}
+static void transpose_f32(const float* x, float* y, int B, int R, int Cc, cudaStream_t st) {
+    dim3 grid((Cc + 31) / 32, (R + 31) / 32, B);
+    transpose_f32_kernel<<<grid, dim3(32, 8), 0, st>>>(x, y, R, Cc);
+}
+void permute_bchw_to_bhwc(const float* x, float* y, int B, int C, int HW, cudaStream_t st) {
+    transpose_f32(x, y, B, C, HW, st);
+}
+void permute_bhwc_to_bchw(const float* x, float* y, int B, int C, int HW, cudaStream_t st) {
+    transpose_f32(x, y, B, HW, C, st);
+}
+
 }  // namespace f32
 }  // namespace ub

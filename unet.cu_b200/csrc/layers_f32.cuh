@@ -12,6 +12,9 @@ namespace f32 {
 // layout conversion: x (B, C, HW) fp32 -> y (B, HW, C) bf16 (tiled transpose through smem)
 void nchw_to_nhwc_bf16(const float* x, int B, int C, int HW, __nv_bfloat16* y, cudaStream_t st);
 void cast_bf16(const float* x, size_t n, __nv_bfloat16* y, cudaStream_t st);
+// fp32 layout permutes of the attention block (dev/attention_block.cu:7-62): (B, C, HW) <-> (B, HW, C), tiled
+void permute_bchw_to_bhwc(const float* x, float* y, int B, int C, int HW, cudaStream_t st);
+void permute_bhwc_to_bchw(const float* x, float* y, int B, int C, int HW, cudaStream_t st);
 
 // GroupNorm (train_unet.cu:1768-1991)
 void groupnorm_fwd(const float* x, const float* w, const float* b, float* out, float* mean, float* rstd, int B, int C,

@@ -514,4 +514,140 @@ int ub_attention_nhwc_backward(const void* qkv, const void* out, const void* dou
     }
     return finish(2);
 }
+
+// ---- composite blocks: the op sequence and buffer roles are the reference's contract (dev/resblock.cu:24-200,
+//      dev/attention_block.cu:64-108); each step is one of the operators above.
+#define UB_STEP(call)        \
+    do {                     \
+        int rc_ = (call);    \
+        if (rc_) return rc_; \
+    } while (0)
+
+static int resample(float* out, const float* x, int B, int C, int H, int W, int up, int down) {
+    if (up) return ub_upsample_forward1(out, x, B, C, H, W);
+    if (down) return ub_avgpool_2d_forward1(out, x, B, C, H, W);
+    if (cudaMemcpyAsync(out, x, size_t(B) * C * H * W * sizeof(float), cudaMemcpyDeviceToDevice, ub_layer_stream()) !=
+        cudaSuccess) {
+        fail("resblock: device copy failed");
+        return UB_ERR_CUDA;
+    }
+    return UB_OK;
+}
+static int resample_bwd(const float* dout, float* dx, int B, int C, int H, int W, int up, int down) {
+    if (up) return ub_upsample_backward1(dx, dout, B, C, H, W);
+    if (down) return ub_avgpool_2d_backward1(dout, dx, B, C, H, W);
+    if (cudaMemcpyAsync(dx, dout, size_t(B) * C * H * W * sizeof(float), cudaMemcpyDeviceToDevice, ub_layer_stream()) !=
+        cudaSuccess) {
+        fail("resblock: device copy failed");
+        return UB_ERR_CUDA;
+    }
+    return UB_OK;
+}
+
+int ub_resblock_forward(int C, int C_emb, int C_out, int B, int H, int W, int up, int down, int G,
+                        const UbResBlockParams* p, const UbResBlockActs* a) {
+    if (up && down) {
+        fail("resblock: up and down are exclusive");
+        return UB_ERR_SHAPE;
+    }
+    const int Ho = up ? 2 * H : (down ? H / 2 : H), Wo = up ? 2 * W : (down ? W / 2 : W);
+    const int n_in = B * C * H * W, n_out = B * C_out * Ho * Wo;
+    // GroupNorm -> SiLU -> (resample) -> 3x3 conv
+    UB_STEP(ub_groupnorm_forward(a->input, p->gn1_w, p->gn1_b, a->gn1, a->gn1_mean, a->gn1_rstd, B, C, H, W, G));
+    UB_STEP(ub_silu_forward(a->gn1, a->silu1, n_in));
+    UB_STEP(resample(a->ud_h, a->silu1, B, C, H, W, up, down));
+    UB_STEP(resample(a->ud_x, a->input, B, C, H, W, up, down));
+    UB_STEP(ub_conv2d_k3_forward3(a->ud_h, p->cv3_1_w, p->cv3_1_b, a->cv3_1, B, C, C_out, Ho, Wo));
+    // time embedding: SiLU -> Linear -> broadcast over the pixels -> add
+    UB_STEP(ub_silu_forward(a->emb, a->silu_emb, B * C_emb));
+    UB_STEP(ub_matmul_forward2(a->l_emb, a->silu_emb, p->l_emb_w, p->l_emb_b, B, C_emb, C_out));
+    UB_STEP(ub_broadcast_last_dims_forward(a->l_emb, a->broad_emb, B * C_out, Ho, Wo));
+    UB_STEP(ub_add_forward(a->cv3_1, a->broad_emb, a->add1, n_out));
+    // GroupNorm -> SiLU -> 3x3 conv
+    UB_STEP(ub_groupnorm_forward(a->add1, p->gn2_w, p->gn2_b, a->gn2, a->gn2_mean, a->gn2_rstd, B, C_out, Ho, Wo, G));
+    UB_STEP(ub_silu_forward(a->gn2, a->silu2, n_out));
+    UB_STEP(ub_conv2d_k3_forward3(a->silu2, p->cv3_2_w, p->cv3_2_b, a->cv3_2, B, C_out, C_out, Ho, Wo));
+    // residual, through a 1x1 conv when the channel count changes
+    if (C_out == C) return ub_add_forward(a->cv3_2, a->ud_x, a->add2, n_out);
+    UB_STEP(ub_conv2d_k1_forward2(a->ud_x, p->res_cv1_w, p->res_cv1_b, a->res_cv1, B, C, Ho, Wo, C_out));
+    return ub_add_forward(a->cv3_2, a->res_cv1, a->add2, n_out);
+}
+
+int ub_resblock_backward(int C, int C_emb, int C_out, int B, int H, int W, int up, int down, int G,
+                         const UbResBlockParams* p, const UbResBlockParams* g, const UbResBlockActs* a,
+                         const UbResBlockBack* k) {
+    if (up && down) {
+        fail("resblock: up and down are exclusive");
+        return UB_ERR_SHAPE;
+    }
+    const int Ho = up ? 2 * H : (down ? H / 2 : H), Wo = up ? 2 * W : (down ? W / 2 : W);
+    const int n_in = B * C * H * W, n_out = B * C_out * Ho * Wo;
+    // scratch, as the reference: the two last forward activations (C_out channels) and, once the skip conv has been
+    // differentiated, ud_x (C channels at the output resolution)
+    float *s1 = a->cv3_2, *s2 = a->add2, *sx = a->ud_x;
+    const float* d_skip = k->dout;  // gradient of the residual branch at the output resolution
+    if (C_out != C) {
+        UB_STEP(ub_conv2d_k1_backward1(k->dout, a->ud_x, p->res_cv1_w, k->buf_BCHoWo, g->res_cv1_w, g->res_cv1_b, B, C,
+                                       C_out, Ho, Wo));
+        d_skip = k->buf_BCHoWo;
+    }
+    // conv2 <- SiLU <- GroupNorm2
+    UB_STEP(ub_conv2d_k3_backward2(k->dout, a->silu2, p->cv3_2_w, nullptr, nullptr, s1, g->cv3_2_w, g->cv3_2_b, B, C_out,
+                                   C_out, Ho, Wo));
+    UB_STEP(ub_silu_backward(s1, a->gn2, s2, n_out));
+    UB_STEP(ub_groupnorm_backward(s2, a->add1, a->gn2_mean, a->gn2_rstd, p->gn2_w, s1, g->gn2_w, g->gn2_b, B, C_out, Ho,
+                                  Wo, G));
+    // embedding branch: sum over pixels -> Linear backward -> SiLU backward
+    UB_STEP(ub_broadcast_last_dims_backward(s1, a->l_emb, B * C_out, Ho, Wo));
+    UB_STEP(ub_matmul_backward1(k->buf_BCemb, g->l_emb_w, g->l_emb_b, a->l_emb, a->silu_emb, p->l_emb_w, B, C_emb,
+                                C_out));
+    UB_STEP(ub_silu_backward(k->buf_BCemb, a->emb, k->demb, B * C_emb));
+    // conv1 <- (resample) <- SiLU <- GroupNorm1, plus the residual branch
+    UB_STEP(ub_conv2d_k3_backward2(s1, a->ud_h, p->cv3_1_w, nullptr, nullptr, sx, g->cv3_1_w, g->cv3_1_b, B, C, C_out, Ho,
+                                   Wo));
+    UB_STEP(resample_bwd(sx, k->buf1_BCHW, B, C, H, W, up, down));
+    UB_STEP(resample_bwd(d_skip, k->buf2_BCHW, B, C, H, W, up, down));
+    UB_STEP(ub_silu_backward(k->buf1_BCHW, a->gn1, a->silu1, n_in));
+    UB_STEP(ub_groupnorm_backward(a->silu1, a->input, a->gn1_mean, a->gn1_rstd, p->gn1_w, k->buf1_BCHW, g->gn1_w, g->gn1_b,
+                                  B, C, H, W, G));
+    return ub_add_forward(k->buf1_BCHW, k->buf2_BCHW, k->dx, n_in);
+}
+
+int ub_attention_block_forward(int B, int C, int H, int W, int HS, int G, const UbAttentionParams* p,
+                               const UbAttentionActs* a) {
+    if (HS < 1 || C % HS) {
+        fail("attention_block: C %% HS != 0");
+        return UB_ERR_SHAPE;
+    }
+    const int T = H * W;
+    UB_STEP(ub_groupnorm_forward(a->input, p->gn_w, p->gn_b, a->gn, a->gn_mean, a->gn_rstd, B, C, H, W, G));
+    f32::permute_bchw_to_bhwc(a->gn, a->perm1, B, C, T, ub_layer_stream());
+    UB_STEP(finish(1));
+    UB_STEP(ub_matmul_forward2(a->qkv1, a->perm1, p->qkv_w, p->qkv_b, B * T, C, 3 * C));
+    UB_STEP(ub_attention_forward1(a->att_out, a->qkv2, a->preatt, a->att, a->qkv1, B, T, C, C / HS));
+    UB_STEP(ub_matmul_forward2(a->proj, a->att_out, p->proj_w, p->proj_b, B * T, C, C));
+    f32::permute_bhwc_to_bchw(a->proj, a->perm2, B, C, T, ub_layer_stream());
+    UB_STEP(finish(1));
+    return ub_add_forward(a->input, a->perm2, a->add, B * C * T);
+}
+
+int ub_attention_block_backward(int B, int C, int H, int W, int HS, int G, const UbAttentionParams* p,
+                                const UbAttentionActs* a, const UbAttentionBack* k, const UbAttentionParams* g) {
+    if (HS < 1 || C % HS) {
+        fail("attention_block: C %% HS != 0");
+        return UB_ERR_SHAPE;
+    }
+    const int T = H * W;
+    f32::permute_bchw_to_bhwc(k->dout, k->buf1_BCHW, B, C, T, ub_layer_stream());
+    UB_STEP(finish(1));
+    UB_STEP(ub_matmul_backward1(k->buf2_BCHW, g->proj_w, g->proj_b, k->buf1_BCHW, a->att_out, p->proj_w, B * T, C, C));
+    UB_STEP(ub_attention_backward(k->buf_B3CHW, k->dqkvr, k->dpreatt, k->datt, k->buf1_BCHW, k->buf2_BCHW, a->qkv2, a->att,
+                                  B, T, C, C / HS));
+    UB_STEP(ub_matmul_backward1(k->buf1_BCHW, g->qkv_w, g->qkv_b, k->buf_B3CHW, a->perm1, p->qkv_w, B * T, C, 3 * C));
+    f32::permute_bhwc_to_bchw(k->buf1_BCHW, k->buf2_BCHW, B, C, T, ub_layer_stream());
+    UB_STEP(finish(1));
+    UB_STEP(ub_groupnorm_backward(k->buf2_BCHW, a->input, a->gn_mean, a->gn_rstd, p->gn_w, k->buf1_BCHW, g->gn_w, g->gn_b,
+                                  B, C, H, W, G));
+    return ub_add_forward(k->buf1_BCHW, k->dout, k->dinp, B * C * T);
+}
 }  // extern "C"
