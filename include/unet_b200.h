@@ -213,6 +213,7 @@ typedef struct {
     int n_timesteps;     /* 1000, linear beta schedule 1e-4 .. 0.02 (train_unet.cu:3131-3147) */
     unsigned long long seed;
     int use_cuda_graph;  /* capture the whole step in one CUDA graph */
+    int compute_dinput;  /* also compute dL/d(x_t) (the reference's unet_backward does, dev/unet_test.cu:2103); 0 */
 } UbConfig;
 
 void ub_default_config(UbConfig* cfg);
@@ -235,7 +236,7 @@ int ub_trainer_set_params(UbTrainer* t, const float* host, size_t n);
 int ub_trainer_get_params(UbTrainer* t, float* host, size_t n);
 int ub_trainer_get_grads(UbTrainer* t, float* host, size_t n);
 int ub_trainer_get_output(UbTrainer* t, float* host, size_t n); /* last forward's eps prediction (B,C_out,H,W) */
-int ub_trainer_get_dinput(UbTrainer* t, float* host, size_t n); /* not computed: returns UB_ERR_STATE */
+int ub_trainer_get_dinput(UbTrainer* t, float* host, size_t n); /* dL/d(x_t) (B,C_in,H,W); needs cfg.compute_dinput */
 
 /* One forward + backward (unet_forward + unet_backward, train_unet.cu:4335-4701) on a HOST batch x0 (B,C_in,H,W).
  * t_host (B) and noise_host (B,C_in,H,W) may be NULL: then timesteps / noise are drawn on the device (Philox).

@@ -268,3 +268,24 @@ def test_train_from_dataloader(ub, setup, tmp_path):
                                               noise.numpy().ctypes.data_as(C.POINTER(C.c_float)), C.byref(loss))
     assert rc == 0 and abs(loss.value - l_direct) < 1e-3
     tr.close(), dl.close()
+
+
+def test_dinput_matches_oracle(ub, setup):
+    """dL/d(x_t), the last tensor dev/unet_test.cu:2082-2107 compares (unet_backward writes it into its dinp buffer)."""
+    O, cfg, flat = setup
+    P = O.unflatten_params(cfg, flat)
+    x0, t, noise = O.synthetic_batch(cfg, 2)
+    xt = O.q_sample(x0, t, noise).requires_grad_(True)
+    loss = O.mse_loss(O.unet_forward(cfg, P, xt, t), noise)
+    loss.backward()
+    tr = ub.Trainer(B=2, compute_dinput=1)
+    tr.set_params(flat.numpy())
+    tr.forward_backward(x0.numpy(), t.numpy(), noise.numpy())
+    d = tr.get_dinput()
+    ref = xt.grad.numpy()
+    assert np.abs(d - ref).max() <= 3e-2 * np.abs(ref).max()
+    tr.close()
+    tr = ub.Trainer(B=2)
+    with pytest.raises(ub.UbError):
+        tr.get_dinput()
+    tr.close()

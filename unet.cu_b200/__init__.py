@@ -26,7 +26,7 @@ class UbConfig(C.Structure):
                 ("W", C.c_int), ("max_period", C.c_int), ("n_levels", C.c_int), ("channel_mult", C.c_int * 8),
                 ("n_res_blocks", C.c_int), ("att_start_level", C.c_int), ("head_size", C.c_int),
                 ("gn_n_groups", C.c_int), ("n_timesteps", C.c_int), ("seed", C.c_ulonglong),
-                ("use_cuda_graph", C.c_int)]
+                ("use_cuda_graph", C.c_int), ("compute_dinput", C.c_int)]
 
 
 UB_KINDS = ("conv_igemm", "wgrad_igemm", "groupnorm", "attention", "eltwise", "small", "optimizer")
@@ -163,6 +163,10 @@ class Trainer:
 
     def get_grads(self):
         return self._get(lib().ub_trainer_get_grads, self.nparams)
+
+    def get_dinput(self):
+        c = self.cfg
+        return self._get(lib().ub_trainer_get_dinput, c.B * c.C_in * c.H * c.W).reshape(c.B, c.C_in, c.H, c.W)
 
     def get_output(self):
         c = self.cfg

@@ -706,14 +706,16 @@ void conv_in_wgrad(const float* x, const bf16* dy, int lddy, int B, int Cin, int
 }
 
 // out[b][o][p] (NCHW fp32) = bias[o] + sum_tap sum_c a[p+shift][c] * w[o][c][tap] ; Cout <= 4
+// flip == 1: the same contraction with w given as (Cin, Cout, 3, 3) and taps mirrored: the input gradient of the
+// 3-channel first conv (dx[s] = sum_tap sum_cb dh[p - shift][cb] * w_in[cb][s][tap]); bias may be null.
 __global__ void conv_out_fwd_kernel(const bf16* __restrict__ a, int lda, const float* __restrict__ w,
                                     const float* __restrict__ bias, int Cin, int Cout, int H, int W, size_t npix,
-                                    float* __restrict__ out) {
+                                    float* __restrict__ out, int flip) {
     pdl_entry();
     extern __shared__ float sw[];  // [9][Cin][4]
     for (int i = threadIdx.x; i < 9 * Cin * 4; i += blockDim.x) {
         const int o = i % 4, c = (i / 4) % Cin, tap = i / (4 * Cin);
-        sw[i] = o < Cout ? w[(size_t(o) * Cin + c) * 9 + tap] : 0.f;
+        sw[i] = o < Cout ? (flip ? w[(size_t(c) * Cout + o) * 9 + (8 - tap)] : w[(size_t(o) * Cin + c) * 9 + tap]) : 0.f;
     }
     __syncthreads();
     const size_t p = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -738,13 +740,20 @@ __global__ void conv_out_fwd_kernel(const bf16* __restrict__ a, int lda, const f
     }
 #pragma unroll
     for (int o = 0; o < 4; ++o)
-        if (o < Cout) out[((b * Cout + o) * H + h) * W + wq] = acc[o] + bias[o];
+        if (o < Cout) out[((b * Cout + o) * H + h) * W + wq] = acc[o] + (bias ? bias[o] : 0.f);
 }
 void conv_out_fwd(const bf16* a, int lda, const float* w, const float* b, int B, int Cin, int Cout, int H, int W,
                   float* out, cudaStream_t st) {
     const size_t npix = size_t(B) * H * W;
     launch_pdl(conv_out_fwd_kernel, dim3(unsigned((npix + 127) / 128)), dim3(128), size_t(9) * Cin * 4 * sizeof(float), st, 
-        a, lda, w, b, Cin, Cout, H, W, npix, out);
+        a, lda, w, b, Cin, Cout, H, W, npix, out, 0);
+}
+void conv_in_dgrad(const bf16* dh, int lddh, const float* w, int B, int Cin, int Cout, int H, int W, float* dx,
+                   cudaStream_t st) {
+    // dh NHWC bf16 with Cout (= model width) channels, w (Cout, Cin, 3, 3), dx NCHW fp32 with Cin <= 4 channels
+    const size_t npix = size_t(B) * H * W;
+    launch_pdl(conv_out_fwd_kernel, dim3(unsigned((npix + 127) / 128)), dim3(128), size_t(9) * Cout * 4 * sizeof(float),
+               st, dh, lddh, w, static_cast<const float*>(nullptr), Cout, Cin, H, W, npix, dx, 1);
 }
 
 // db[o] = sum_{b,p} dout[b][o][p]   (tiny: B*Cout*H*W fp32)

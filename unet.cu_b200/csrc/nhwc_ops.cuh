@@ -50,6 +50,9 @@ void conv_in_fwd(const float* x, const float* w, const float* b, int B, int Cin,
 // dW, db of conv_in from dy NHWC bf16 (overwrite); scratch >= blocks*(Cout*Cin*9 + Cout) floats
 void conv_in_wgrad(const float* x, const bf16* dy, int lddy, int B, int Cin, int Cout, int H, int W, float* dw,
                    float* db, float* scratch, size_t scratch_floats, cudaStream_t st);
+// dx NCHW fp32 (B,Cin<=4,H,W) = conv_transpose(dh NHWC bf16 with Cout channels, w (Cout,Cin,3,3)): dL/d(x_t)
+void conv_in_dgrad(const bf16* dh, int lddh, const float* w, int B, int Cin, int Cout, int H, int W, float* dx,
+                   cudaStream_t st);
 // conv_out: a NHWC bf16 (Cin = 64..), w (Cout<=4,Cin,3,3) -> out NCHW fp32
 void conv_out_fwd(const bf16* a, int lda, const float* w, const float* b, int B, int Cin, int Cout, int H, int W,
                   float* out, cudaStream_t st);

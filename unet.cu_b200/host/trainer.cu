@@ -120,6 +120,7 @@ struct UbTrainer {
     DeviceArena zarena;
     // io buffers
     float *x0 = nullptr, *xt = nullptr, *noise = nullptr, *tsteps = nullptr, *out = nullptr, *dout = nullptr;
+    float* dxt = nullptr;  // dL/d(x_t), only with cfg.compute_dinput
     float *loss = nullptr, *sqrt_ac = nullptr, *sqrt_1mac = nullptr, *betas = nullptr;
     int* samp_state = nullptr;  // {t, iteration} of the sampling loop
     cudaGraphExec_t samp_graph = nullptr;
@@ -586,6 +587,7 @@ int Builder::build() {
     // io + small fp32 state
     T->x0 = f32(size_t(B) * img), T->xt = f32(size_t(B) * img), T->noise = f32(size_t(B) * img);
     T->tsteps = f32(B);
+    T->dxt = c.compute_dinput ? f32(size_t(B) * img) : nullptr;
     T->out = f32(size_t(B) * c.C_out * H0 * W0), T->dout = f32(size_t(B) * c.C_out * H0 * W0);
     T->sqrt_ac = f32(c.n_timesteps), T->sqrt_1mac = f32(c.n_timesteps), T->betas = f32(c.n_timesteps);
     T->samp_state = (int*)T->arena.alloc(256);
@@ -641,7 +643,9 @@ int Builder::build() {
             Bk([=](cudaStream_t st) {
                 conv_in_wgrad(Tt->xt, dout.p, dout.ld, Bn, Cin, hv.C, hv.H, hv.W, gw, gb, Tt->small_scratch,
                               Tt->small_scratch_floats, st);
-            }, 2);
+            }, 2, UB_KIND_SMALL, 0, 0, 1);
+            if (Tt->cfg.compute_dinput)
+                Bk([=](cudaStream_t st) { conv_in_dgrad(dout.p, dout.ld, w, Bn, Cin, hv.C, hv.H, hv.W, Tt->dxt, st); }, 1);
             return View{};
         };
         nodes.push_back(nd);
@@ -1385,9 +1389,13 @@ extern "C" int ub_trainer_get_output(UbTrainer* t, float* host, size_t n) {
     const UbConfig& c = t->cfg;
     return copy_out(t, t->out, host, n, size_t(c.B) * c.C_out * c.H * c.W);
 }
-extern "C" int ub_trainer_get_dinput(UbTrainer*, float*, size_t) {
-    set_err("dL/dinput is not computed by the training path (the reference trainer never uses it)");
-    return UB_ERR_STATE;
+extern "C" int ub_trainer_get_dinput(UbTrainer* t, float* host, size_t n) {
+    if (!t->dxt) {
+        set_err("dL/d(x_t) is only computed when the trainer was created with cfg.compute_dinput = 1");
+        return UB_ERR_STATE;
+    }
+    const UbConfig& c = t->cfg;
+    return copy_out(t, t->dxt, host, n, size_t(c.B) * c.C_in * c.H * c.W);
 }
 
 static const int kModelMagic = 12345678;  // train_unet.py:781
