@@ -600,17 +600,80 @@ __global__ void smallc_conv_kernel(const float* __restrict__ xs, const float* __
     st8(y + p * ldy + j * 8, acc);
 }
 
+// Two horizontally adjacent output pixels per thread: the 3 x 4 input window of a small channel serves both pixels'
+// nine taps (12 loads instead of 18) and every 16-byte weight read from shared memory feeds 8 FMAs instead of 4 --
+// the one-pixel version was bound by LDS issue.  W must be even.
+__global__ void smallc_conv_pair_kernel(const float* __restrict__ xs, const float* __restrict__ w,
+                                        const float* __restrict__ bias, int Cs, int Cb, int H, int W, int flip,
+                                        size_t total, bf16* __restrict__ y, int ldy) {
+    pdl_entry();
+    extern __shared__ float sw[];  // [Cs*9][Cb]
+    for (int i = threadIdx.x; i < Cb * Cs * 9; i += blockDim.x) {
+        const int cb = i % Cb, st = i / Cb;
+        const int s = st / 9, tap = st % 9;
+        sw[i] = flip ? w[(size_t(s) * Cb + cb) * 9 + (8 - tap)] : w[(size_t(cb) * Cs + s) * 9 + tap];
+    }
+    __syncthreads();
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int C8 = Cb / 8, W2 = W / 2;
+    const int j = int(i % C8);
+    const size_t pp = i / C8;  // pixel-pair index
+    const int w0 = int(pp % W2) * 2, h = int((pp / W2) % H);
+    const size_t b = pp / (size_t(W2) * H);
+    float a0[8], a1[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a0[k] = a1[k] = bias ? bias[j * 8 + k] : 0.f;
+    for (int s = 0; s < Cs; ++s) {
+        const float* xp = xs + (b * Cs + s) * size_t(H) * W;
+        float v[3][4];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int hh = h + r - 1;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int ww = w0 + c - 1;
+                v[r][c] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xp + size_t(hh) * W + ww) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const float4* wr = reinterpret_cast<const float4*>(sw + (s * 9 + tap) * Cb + j * 8);
+            const float4 wa = wr[0], wb = wr[1];
+            const float x0 = v[tap / 3][tap % 3], x1 = v[tap / 3][tap % 3 + 1];
+            a0[0] = fmaf(x0, wa.x, a0[0]), a0[1] = fmaf(x0, wa.y, a0[1]), a0[2] = fmaf(x0, wa.z, a0[2]);
+            a0[3] = fmaf(x0, wa.w, a0[3]), a0[4] = fmaf(x0, wb.x, a0[4]), a0[5] = fmaf(x0, wb.y, a0[5]);
+            a0[6] = fmaf(x0, wb.z, a0[6]), a0[7] = fmaf(x0, wb.w, a0[7]);
+            a1[0] = fmaf(x1, wa.x, a1[0]), a1[1] = fmaf(x1, wa.y, a1[1]), a1[2] = fmaf(x1, wa.z, a1[2]);
+            a1[3] = fmaf(x1, wa.w, a1[3]), a1[4] = fmaf(x1, wb.x, a1[4]), a1[5] = fmaf(x1, wb.y, a1[5]);
+            a1[6] = fmaf(x1, wb.z, a1[6]), a1[7] = fmaf(x1, wb.w, a1[7]);
+        }
+    }
+    const size_t p0 = (b * H + h) * size_t(W) + w0;
+    st8(y + p0 * ldy + j * 8, a0);
+    st8(y + (p0 + 1) * ldy + j * 8, a1);
+}
+static void smallc_conv(const float* xs, const float* w, const float* bias, int Cs, int Cb, int B, int H, int W,
+                        int flip, bf16* y, int ldy, cudaStream_t st) {
+    const size_t smem = size_t(Cb) * Cs * 9 * sizeof(float);
+    if (W % 2 == 0) {
+        const size_t total = size_t(B) * H * (W / 2) * (Cb / 8);
+        launch_pdl(smallc_conv_pair_kernel, dim3(unsigned((total + 127) / 128)), dim3(128), smem, st, xs, w, bias, Cs, Cb,
+                   H, W, flip, total, y, ldy);
+    } else {
+        const size_t total = size_t(B) * H * W * (Cb / 8);
+        launch_pdl(smallc_conv_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), smem, st, xs, w, bias, Cs, Cb, H,
+                   W, flip, total, y, ldy);
+    }
+}
+
 void conv_in_fwd(const float* x, const float* w, const float* b, int B, int Cin, int Cout, int H, int W, bf16* y,
                  int ldy, cudaStream_t st) {
-    const size_t total = size_t(B) * H * W * (Cout / 8);
-    launch_pdl(smallc_conv_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), size_t(Cout) * Cin * 9 * sizeof(float), st, 
-        x, w, b, Cin, Cout, H, W, 0, total, y, ldy);
+    smallc_conv(x, w, b, Cin, Cout, B, H, W, 0, y, ldy, st);
 }
 void conv_out_dgrad(const float* dout, const float* w, int B, int Cin, int Cout, int H, int W, bf16* da, int ldda,
                     cudaStream_t st) {
-    const size_t total = size_t(B) * H * W * (Cin / 8);
-    launch_pdl(smallc_conv_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), size_t(Cout) * Cin * 9 * sizeof(float), st, 
-        dout, w, nullptr, Cout, Cin, H, W, 1, total, da, ldda);
+    smallc_conv(dout, w, nullptr, Cout, Cin, B, H, W, 1, da, ldda, st);
 }
 
 // partial[blk][cb][s*9+tap] = sum_{p in block} yb[p][cb] * xs[b][s][p + shift(tap)] ; partial[blk][cb][NT] = sum yb
@@ -742,18 +805,83 @@ __global__ void conv_out_fwd_kernel(const bf16* __restrict__ a, int lda, const f
     for (int o = 0; o < 4; ++o)
         if (o < Cout) out[((b * Cout + o) * H + h) * W + wq] = acc[o] + (bias ? bias[o] : 0.f);
 }
+// Two horizontally adjacent output pixels per thread (W even): the 3 x 4 window of input octets serves both pixels
+// (12 instead of 18 16-byte loads per 8 channels) and every weight read feeds 8 FMAs.
+__global__ void conv_out_pair_kernel(const bf16* __restrict__ a, int lda, const float* __restrict__ w,
+                                     const float* __restrict__ bias, int Cin, int Cout, int H, int W, size_t npairs,
+                                     float* __restrict__ out, int flip) {
+    pdl_entry();
+    extern __shared__ float sw[];  // [9][Cin][4]
+    for (int i = threadIdx.x; i < 9 * Cin * 4; i += blockDim.x) {
+        const int o = i % 4, c = (i / 4) % Cin, tap = i / (4 * Cin);
+        sw[i] = o < Cout ? (flip ? w[(size_t(c) * Cout + o) * 9 + (8 - tap)] : w[(size_t(o) * Cin + c) * 9 + tap]) : 0.f;
+    }
+    __syncthreads();
+    const size_t pp = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (pp >= npairs) return;
+    const int W2 = W / 2;
+    const int w0 = int(pp % W2) * 2, h = int((pp / W2) % H);
+    const size_t b = pp / (size_t(W2) * H);
+    float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < Cin; c += 8) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int hh = h + r - 1;
+            if (hh < 0 || hh >= H) continue;
+            float f[4][8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int ww = w0 + q - 1;
+                if (ww >= 0 && ww < W) {
+                    ld8(a + ((b * H + hh) * W + ww) * lda + c, f[q]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) f[q][k] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const float4* wt = reinterpret_cast<const float4*>(sw + (size_t(r * 3 + dx) * Cin + c) * 4);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float4 wv = wt[k];
+                    const float x0 = f[dx][k], x1 = f[dx + 1][k];
+                    a0[0] = fmaf(x0, wv.x, a0[0]), a0[1] = fmaf(x0, wv.y, a0[1]);
+                    a0[2] = fmaf(x0, wv.z, a0[2]), a0[3] = fmaf(x0, wv.w, a0[3]);
+                    a1[0] = fmaf(x1, wv.x, a1[0]), a1[1] = fmaf(x1, wv.y, a1[1]);
+                    a1[2] = fmaf(x1, wv.z, a1[2]), a1[3] = fmaf(x1, wv.w, a1[3]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+        if (o < Cout) {
+            const float bv = bias ? bias[o] : 0.f;
+            *reinterpret_cast<float2*>(out + ((b * Cout + o) * H + h) * W + w0) = make_float2(a0[o] + bv, a1[o] + bv);
+        }
+}
+static void conv_out_launch(const bf16* a, int lda, const float* w, const float* b, int B, int Cin, int Cout, int H,
+                            int W, float* out, int flip, cudaStream_t st) {
+    const size_t smem = size_t(9) * Cin * 4 * sizeof(float);
+    if (W % 2 == 0) {
+        const size_t npairs = size_t(B) * H * (W / 2);
+        launch_pdl(conv_out_pair_kernel, dim3(unsigned((npairs + 63) / 64)), dim3(64), smem, st, a, lda, w, b, Cin, Cout,
+                   H, W, npairs, out, flip);
+    } else {
+        const size_t npix = size_t(B) * H * W;
+        launch_pdl(conv_out_fwd_kernel, dim3(unsigned((npix + 127) / 128)), dim3(128), smem, st, a, lda, w, b, Cin, Cout,
+                   H, W, npix, out, flip);
+    }
+}
 void conv_out_fwd(const bf16* a, int lda, const float* w, const float* b, int B, int Cin, int Cout, int H, int W,
                   float* out, cudaStream_t st) {
-    const size_t npix = size_t(B) * H * W;
-    launch_pdl(conv_out_fwd_kernel, dim3(unsigned((npix + 127) / 128)), dim3(128), size_t(9) * Cin * 4 * sizeof(float), st, 
-        a, lda, w, b, Cin, Cout, H, W, npix, out, 0);
+    conv_out_launch(a, lda, w, b, B, Cin, Cout, H, W, out, 0, st);
 }
 void conv_in_dgrad(const bf16* dh, int lddh, const float* w, int B, int Cin, int Cout, int H, int W, float* dx,
                    cudaStream_t st) {
     // dh NHWC bf16 with Cout (= model width) channels, w (Cout, Cin, 3, 3), dx NCHW fp32 with Cin <= 4 channels
-    const size_t npix = size_t(B) * H * W;
-    launch_pdl(conv_out_fwd_kernel, dim3(unsigned((npix + 127) / 128)), dim3(128), size_t(9) * Cout * 4 * sizeof(float),
-               st, dh, lddh, w, static_cast<const float*>(nullptr), Cout, Cin, H, W, npix, dx, 1);
+    conv_out_launch(dh, lddh, w, nullptr, B, Cout, Cin, H, W, dx, 1, st);
 }
 
 // db[o] = sum_{b,p} dout[b][o][p]   (tiny: B*Cout*H*W fp32)
