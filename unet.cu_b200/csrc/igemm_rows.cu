@@ -41,6 +41,8 @@ struct RowsBars {
     uint32_t pad_[3];
 };
 // smem tail behind the rings (floats): comb[2][BN] | gconst[2][4][BN] | red[8][BN][2] | tr[8][32*36]
+// (16 epilogue warps -- a column split on top of quadrant x half -- measured 20 % slower: the 102-register cap of a
+// 640-thread CTA spills in the hooked chunk; two-pass 20-float transposes measured 2 % slower than this layout)
 static size_t rows_tail_floats(int BN) { return size_t(2 + 8 + 16) * BN + 8 * 32 * 36; }
 
 __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __grid_constant__ IgemmRowsParams p) {
