@@ -357,10 +357,92 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ x, int ldx, const b
     }
 }
 
+// The same pass when dy already holds dz = dL/d gn(x) (modes 0 and 2): no activation derivative, and
+//   dx = a*dz - c1 - xhat*c2 = A*dz - Bc*x + Cc   with  A = gamma*rstd,  Bc = c2*rstd,  Cc = mean*rstd*c2 - c1
+// -- three constants per channel and two FMAs per element, 4 x (x, dz) loads in flight per thread.
+__global__ void gn_bwd_apply_dz_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ dz, int lddz,
+                                       const float* __restrict__ chsum, const float* __restrict__ S,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C,
+                                       int G, int C8, int rows, int ppb, const bf16* __restrict__ add_in, int ldadd,
+                                       bf16* __restrict__ dx, int lddx, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ colsum_out) {
+    pdl_entry();
+    extern __shared__ float sm[];  // A, Bc, Cc : 3*C ; then scratch [rows][C]
+    float *sA = sm, *sB = sm + C, *sC = sm + 2 * C, *scr = sm + 3 * C;
+    const int b = blockIdx.y;
+    const int cpg = C / G;
+    const float* Sb = S + size_t(b) * C * 2;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float r, mr, a, bb;
+        gn_channel_consts(chsum + size_t(b) * C * 2, gamma, beta, C, cpg, HW, c, r, mr, a, bb);
+        const int g0 = (c / cpg) * cpg;
+        float m1 = 0.f, m2 = 0.f;
+        for (int k = 0; k < cpg; ++k) {
+            m1 += gamma[g0 + k] * Sb[(g0 + k) * 2];
+            m2 += gamma[g0 + k] * Sb[(g0 + k) * 2 + 1];
+        }
+        const float n = float(cpg) * float(HW);
+        const float c1 = r * m1 / n, c2 = r * m2 / n;
+        sA[c] = a, sB[c] = c2 * r, sC[c] = mr * c2 - c1;
+        if (blockIdx.x == 0) {
+            atomicAdd(&dgamma[c], Sb[c * 2 + 1]);
+            atomicAdd(&dbeta[c], Sb[c * 2]);
+        }
+    }
+    __syncthreads();
+    const int j = threadIdx.x % C8, r = threadIdx.x / C8;
+    float cs[8], cA[8], cB[8], cC[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cs[i] = 0.f, cA[i] = sA[j * 8 + i], cB[i] = sB[j * 8 + i], cC[i] = sC[j * 8 + i];
+    const int p0 = blockIdx.x * ppb;
+    const int p1 = min(p0 + ppb, HW);
+    const size_t img = size_t(b) * HW;
+    for (int p = p0 + r; p < p1; p += 4 * rows) {
+        uint4 vx[4], vd[4], va[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int pp = p + u * rows;
+            const bool ok = pp < p1;
+            vx[u] = ok ? *reinterpret_cast<const uint4*>(x + (img + pp) * ldx + j * 8) : make_uint4(0, 0, 0, 0);
+            vd[u] = ok ? *reinterpret_cast<const uint4*>(dz + (img + pp) * lddz + j * 8) : make_uint4(0, 0, 0, 0);
+            va[u] = (ok && add_in) ? *reinterpret_cast<const uint4*>(add_in + (img + pp) * ldadd + j * 8)
+                                   : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int pp = p + u * rows;
+            if (pp >= p1) break;
+            float f[8], d[8], o[8];
+            unpack8(vx[u], f);
+            unpack8(vd[u], d);
+            unpack8(va[u], o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float g = fmaf(cA[i], d[i], fmaf(-cB[i], f[i], cC[i]));
+                cs[i] += g;
+                o[i] += g;
+            }
+            st8(dx + (img + pp) * lddx + j * 8, o);
+        }
+    }
+    if (colsum_out) {
+        store_partials(scr, C, r, j, cs);
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x)
+            atomicAdd(&colsum_out[size_t(b) * C + c], column_total(scr, C, rows, c));
+    }
+}
+
 void gn_bwd_apply(const bf16* x, int ldx, const bf16* dy, int lddy, const float* chsum, const float* S,
                   const float* gamma, const float* beta, int B, int HW, int C, int G, int silu, const bf16* add_in,
                   int ldadd, bf16* dx, int lddx, float* dgamma, float* dbeta, float* colsum_out, cudaStream_t st) {
     RowMap m = make_rowmap(B, HW, C);
+    if (silu != 1) {  // dy is dz already
+        launch_pdl(gn_bwd_apply_dz_kernel, dim3(dim3(m.nchunks, B)), dim3(m.threads),
+                   (3 + size_t(m.rows)) * C * sizeof(float), st, x, ldx, dy, lddy, chsum, S, gamma, beta, HW, C, G, m.C8,
+                   m.rows, m.ppb, add_in, ldadd, dx, lddx, dgamma, dbeta, colsum_out);
+        return;
+    }
     launch_pdl(gn_bwd_apply_kernel, dim3(dim3(m.nchunks, B)), dim3(m.threads), (6 + size_t(m.rows)) * C * sizeof(float), st, 
         x, ldx, dy, lddy, chsum, S, gamma, beta, HW, C, G, silu, m.C8, m.rows, m.ppb, add_in, ldadd, dx, lddx, dgamma,
         dbeta, colsum_out);
