@@ -137,6 +137,7 @@ struct UbTrainer {
     PackEntry* pack_table = nullptr;
     int n_pack = 0, pack_max_tiles = 0;
     std::vector<PackEntry> h_pack;
+    std::vector<size_t> pack_off;  // parameter offset of each pack entry (ascending)
     WgradFinalizeEntry* fin_table = nullptr;
     std::vector<WgradFinalizeEntry> h_fin;  // in backward order
     SmallLinear *emb_table = nullptr, *temb_table = nullptr;
@@ -168,6 +169,13 @@ struct UbTrainer {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1, n_buckets = 4;
     bool comm_off = false;  // rank-local eager replays (profiling) must not enqueue collectives
+    // Optimizer per gradient bucket: as soon as a bucket's gradients are final (and all-reduced), AdamW and the weight
+    // re-pack of that parameter range run on the branch that finalised them, under the rest of backward; only the
+    // last bucket is left for the end of the step.  The tape ops read the current step's hyper-parameters from here.
+    bool opt_in_tape = false;  // true while a step WITH an update is being enqueued
+    bool opt_overlap_ok = true;
+    float o_lr = 0, o_b1 = 0, o_b2 = 0, o_eps = 0, o_wd = 0;
+    size_t opt_done_lo = 0;   // parameters >= this offset were updated by the tape
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::vector<cudaEvent_t> bucket_events;
     std::vector<size_t> bucket_bounds;  // param offsets, descending
@@ -276,6 +284,7 @@ struct Builder {
         pk.wd = packbuf(size_t(ntaps) * Cout * Cin);
         if (real()) {
             T->h_pack.push_back({P(woff), pk.wf, pk.wd, Cout, Cin, ntaps});
+            T->pack_off.push_back(woff);
             int tiles = ((Cout + 31) / 32) * ((Cin + 31) / 32);
             if (tiles > T->pack_max_tiles) T->pack_max_tiles = tiles;
         }
@@ -770,16 +779,38 @@ int Builder::build() {
     size_t flushed_hi = T->nparams;
     size_t cut_i = 0;
     int bucket_no = 0;
-    auto flush_bucket = [&](size_t lo, size_t hi) {
+    auto flush_bucket = [&](size_t lo, size_t hi, bool last) {
         if (hi <= lo) return;
         const int k = bucket_no++;
+        // pack entries whose weights lie in [lo, hi)
+        int pk_first = 0, pk_count = 0, pk_tiles = 0;
+        if (real() && (lo % 4) != 0) Tt->opt_overlap_ok = false;  // AdamW works on float4: ranges must be aligned
+        if (real()) {
+            const int n = int(Tt->pack_off.size());
+            while (pk_first < n && Tt->pack_off[pk_first] < lo) ++pk_first;
+            while (pk_first + pk_count < n && Tt->pack_off[pk_first + pk_count] < hi) {
+                const PackEntry& e = Tt->h_pack[pk_first + pk_count];
+                pk_tiles = std::max(pk_tiles, ((e.Cout + 31) / 32) * ((e.Cin + 31) / 32));
+                ++pk_count;
+            }
+        }
         Bk([=](cudaStream_t st) {
-            if (Tt->world <= 1 || Tt->comm_off) return;
-            cudaEvent_t ev = Tt->bucket_events[k % Tt->bucket_events.size()];
-            cudaEventRecord(ev, st);
-            cudaStreamWaitEvent(Tt->comm_stream, ev, 0);
-            nccl().AllReduce(Tt->grads + lo, Tt->grads + lo, hi - lo, kNcclFloat, kNcclSum, Tt->comm, Tt->comm_stream);
-        }, 0);
+            const bool dp = Tt->world > 1 && !Tt->comm_off;
+            if (dp) {
+                cudaEvent_t ev = Tt->bucket_events[k % Tt->bucket_events.size()];
+                cudaEventRecord(ev, st);
+                cudaStreamWaitEvent(Tt->comm_stream, ev, 0);
+                nccl().AllReduce(Tt->grads + lo, Tt->grads + lo, hi - lo, kNcclFloat, kNcclSum, Tt->comm,
+                                 Tt->comm_stream);
+            }
+            if (!Tt->opt_in_tape || last) return;  // the last bucket is updated at the end of the step
+            // optimizer of this bucket on the stream that owns its final gradients
+            cudaStream_t os = dp ? Tt->comm_stream : st;
+            adamw_step(Tt->params + lo, Tt->grads + lo, Tt->m + lo, Tt->v + lo, hi - lo, Tt->o_lr, Tt->o_b1, Tt->o_b2,
+                       Tt->o_eps, Tt->o_wd, 1.f / float(Tt->world), Tt->step_dev, os);
+            if (pk_count) pack_weights(Tt->pack_table + pk_first, pk_count, pk_tiles, os);
+            Tt->opt_done_lo = lo;
+        }, 0, UB_KIND_OPTIM, 0, 0, 1);
     };
     View g{};
     for (int i = int(nodes.size()) - 1; i >= 0; --i) {
@@ -796,10 +827,11 @@ int Builder::build() {
         }
         g = nd.bwd(g);
         while (cut_i < cuts.size() && nd.param_begin <= cuts[cut_i] && nd.param_begin > time_mlp_end) {
+            // (all of this is on the weight-gradient branch, which has seen everything the main stream did so far:
+            //  the main stream does not wait for it here)
             emb_flush();
             fin_flush();
-            join_side();
-            flush_bucket(nd.param_begin, flushed_hi);
+            flush_bucket(nd.param_begin, flushed_hi, false);
             flushed_hi = nd.param_begin;
             while (cut_i < cuts.size() && cuts[cut_i] >= nd.param_begin) ++cut_i;
         }
@@ -814,7 +846,7 @@ int Builder::build() {
         dsilu_mul(Tt->d_h0act, Tt->h0, Tt->dh0, size_t(Bn) * Cemb, st);
         small_linear_bwd(Tt->temb_table, 1, Bn, Cemb, Cm, st);
     }, 6);
-    flush_bucket(0, flushed_hi);
+    flush_bucket(0, flushed_hi, true);
     Bk([=](cudaStream_t st) {  // join the communication stream
         if (Tt->world <= 1 || Tt->comm_off) return;
         cudaEventRecord(Tt->ev_join, Tt->comm_stream);
@@ -1062,6 +1094,10 @@ static void enqueue_step(UbTrainer* t, const StepOpts& o, cudaStream_t st) {
             }
         }
     };
+    static const bool opt_overlap = !(getenv("UB_NO_OPT_OVERLAP") && atoi(getenv("UB_NO_OPT_OVERLAP")) != 0);
+    t->opt_in_tape = o.update && opt_overlap && t->opt_overlap_ok;
+    t->o_lr = o.lr, t->o_b1 = o.b1, t->o_b2 = o.b2, t->o_eps = o.eps, t->o_wd = o.wd;
+    t->opt_done_lo = t->nparams;
     run(t->fwd_ops, t->fwd_info, "forward");
     run(t->bwd_ops, t->bwd_info, "backward");
     if (side_dirty) {  // (the tape ends with a join; this only guards against a tape that forgot it)
@@ -1070,11 +1106,19 @@ static void enqueue_step(UbTrainer* t, const StepOpts& o, cudaStream_t st) {
         cudaStreamWaitEvent(st, ev, 0);
     }
     if (o.update) {
-        adamw_step(t->params, t->grads, t->m, t->v, t->nparams, o.lr, o.b1, o.b2, o.eps, o.wd, 1.f / float(t->world),
+        // the buckets the tape already updated are [opt_done_lo, nparams); the rest (the last bucket) is updated here
+        const size_t n_left = t->opt_done_lo;
+        adamw_step(t->params, t->grads, t->m, t->v, n_left, o.lr, o.b1, o.b2, o.eps, o.wd, 1.f / float(t->world),
                    t->step_dev, st);
-        run_pack(t, st);
+        int cnt = 0, tiles = 0;
+        while (cnt < t->n_pack && t->pack_off[cnt] < n_left) {
+            tiles = std::max(tiles, ((t->h_pack[cnt].Cout + 31) / 32) * ((t->h_pack[cnt].Cin + 31) / 32));
+            ++cnt;
+        }
+        if (cnt) pack_weights(t->pack_table, cnt, tiles, st);
         increment_step(t->step_dev, st);
     }
+    t->opt_in_tape = false;
 }
 
 static int ensure_packed(UbTrainer* t) {
