@@ -18,6 +18,9 @@
 namespace ub {
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Measured (bench.py, B=32): no PDL 6.87 ms/step, implicit trigger 6.62, early trigger in every kernel 7.30, early
+// trigger only in the forward-pass convs 6.01 vs 5.93 without -- early-resident CTAs of the next kernel take SM slots,
+// TMEM and shared memory from the kernel that is still draining and from the weight-gradient branch.
 #ifndef UB_PDL_EARLY_TRIGGER
 #define UB_PDL_EARLY_TRIGGER 0
 #endif
