@@ -280,11 +280,63 @@ def run_cuda(args):
             ref = reference_cuda_baseline(args)
             if ref:
                 line["reference_cuda"] = ref
+        if world == 1:
+            line["conv_microbench"] = conv_microbench(ub, pk)
         print(json.dumps(line), flush=True)
     tr.close()
     if use_dist:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def conv_microbench(ub, pk):
+    """The second half of BASELINE.json's metric ("conv3x3 fwd/bwd TFLOP/s vs peak", configs[1]) on a few shapes, live:
+    tcgen05 conv forward / input-gradient / weight-gradient on NHWC bf16 operands resident in HBM, batch 32, CUDA
+    events, L2 flushed (256 MB memset) between repetitions.  The full sweep is tools/conv_bench.py."""
+    import ctypes as C
+    import math
+    import torch
+    L = ub.lib()
+    p = lambda t: C.c_void_p(t.data_ptr())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    out = []
+    for (ci, co, h) in ((64, 64, 64), (128, 128, 32), (256, 256, 32), (512, 512, 64)):
+        B = 32
+        x = torch.randn(B, ci, h, h, device="cuda")
+        w = torch.randn(co, ci, 3, 3, device="cuda") / math.sqrt(9 * ci)
+        b = torch.randn(co, device="cuda")
+        dout = torch.randn(B, co, h, h, device="cuda")
+        dw, db = torch.empty_like(w), torch.empty_like(b)
+        xb = torch.empty(B * h * h * ci, dtype=torch.bfloat16, device="cuda")
+        dyb = torch.empty(B * h * h * co, dtype=torch.bfloat16, device="cuda")
+        ob, dxb = torch.empty_like(dyb), torch.empty_like(xb)
+        wf = torch.empty(9 * co * ci, dtype=torch.bfloat16, device="cuda")
+        wd = torch.empty_like(wf)
+        L.ub_nchw_to_nhwc_bf16(p(x), p(xb), B, ci, h, h)
+        L.ub_nchw_to_nhwc_bf16(p(dout), p(dyb), B, co, h, h)
+        L.ub_pack_conv_weight(p(w), p(wf), p(wd), ci, co, 3)
+        runs = {"fwd": lambda: L.ub_conv2d_nhwc_forward(p(xb), p(wf), p(b), p(ob), B, h, h, ci, co, 3),
+                "dgrad": lambda: L.ub_conv2d_nhwc_dgrad(p(dyb), p(wd), p(dxb), B, h, h, ci, co, 3),
+                "wgrad": lambda: L.ub_conv2d_nhwc_wgrad(p(dyb), p(xb), p(dw), p(db), B, h, h, ci, co, 3)}
+        flops = 2.0 * 9 * B * h * h * ci * co
+        ent = {"shape": f"B32 {ci}->{co} @{h}x{h}", "gflop": flops / 1e9}
+        for name, fn in runs.items():
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            tot = 0.0
+            for _ in range(10):
+                flush.zero_()
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                tot += e0.elapsed_time(e1)
+            tf = flops / (tot / 10) / 1e9
+            ent[name] = {"tflops": round(tf, 1), "frac_of_burst_peak": round(tf / pk["tf_burst"], 3)}
+        out.append(ent)
+    return out
 
 
 def conv_traffic():
