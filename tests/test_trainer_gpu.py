@@ -289,3 +289,34 @@ def test_dinput_matches_oracle(ub, setup):
     with pytest.raises(ub.UbError):
         tr.get_dinput()
     tr.close()
+
+
+@pytest.mark.parametrize("kw,okw,B", [
+    (dict(H=32, W=32, channel_mult=(1, 2), att_start_level=1), dict(H=32, W=32, channel_mult=(1, 2), attn_start_level=1), 3),
+    (dict(C_model=128, channel_mult=(1, 2, 2), att_start_level=2, n_res_blocks=1, H=32, W=32),
+     dict(model_channels=128, channel_mult=(1, 2, 2), attn_start_level=2, num_res_blocks=1, H=32, W=32), 2),
+    (dict(H=64, W=32, channel_mult=(1, 2, 4), att_start_level=1, n_res_blocks=1),
+     dict(H=64, W=32, channel_mult=(1, 2, 4), attn_start_level=1, num_res_blocks=1), 2),
+])
+def test_other_configs_match_oracle(ub, oracle, kw, okw, B):
+    """Config generality: other depths, widths, block counts, a non-square image, attention
+    at 16x16 (T=256), 8x8 (T=64) and a 16x8 map (T=128), an odd batch -- one forward+backward against the oracle."""
+    O = oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.UNetConfig(**okw)
+    flat = O.flatten_params(cfg, O.init_params(cfg, seed=0))
+    x0, t, noise = O.synthetic_batch(cfg, B)
+    tr = ub.Trainer(B=B, **kw)
+    assert tr.nparams == flat.numel()
+    tr.set_params(flat.numpy())
+    loss = tr.forward_backward(x0.numpy(), t.numpy(), noise.numpy())
+    g = tr.get_grads()
+    loss_ref, _, g_ref = O.train_step_grads(cfg, flat, x0, t, noise)
+    g_ref = g_ref.numpy()
+    assert abs(loss - float(loss_ref)) <= 2e-3 * float(loss_ref)
+    cos = float(g @ g_ref / (np.linalg.norm(g) * np.linalg.norm(g_ref)))
+    assert cos > 0.9995, cos
+    assert np.linalg.norm(g - g_ref) <= 2e-2 * np.linalg.norm(g_ref)
+    l2 = tr.train_step(x0.numpy(), t.numpy(), noise.numpy(), lr=1e-4)   # the captured-graph path runs too
+    assert np.isfinite(l2)
+    tr.close()

@@ -830,6 +830,12 @@ __global__ void smallc_wgrad_reduce_kernel(const float* __restrict__ partial, in
     else
         dw[(size_t(sidx) * Cb + cb) * 9 + (8 - tap)] = s;
 }
+void nhwc_ops_init() {
+    static bool done = false;
+    if (done) return;
+    cudaFuncSetAttribute(smallc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    done = true;
+}
 static void smallc_wgrad(const float* xs, const bf16* yb, int ldy, int B, int Cs, int Cb, int H, int W, int mode,
                          float* dw, float* db, float* scratch, size_t scratch_floats, cudaStream_t st) {
     const int NT = Cs * 9;
@@ -842,6 +848,11 @@ static void smallc_wgrad(const float* xs, const bf16* yb, int ldy, int B, int Cs
         return;
     }
     const size_t smem = (size_t(Cs) * 3 * (W + 2) + 4 * per) * sizeof(float);
+    nhwc_ops_init();  // (model widths >= 128 need more than the default 48 KiB of dynamic smem)
+    if (smem > size_t(227) * 1024) {
+        fprintf(stderr, "[unet_b200] smallc_wgrad: %d channels need %zu bytes of shared memory\n", Cb, smem);
+        return;
+    }
     launch_pdl(smallc_wgrad_kernel, dim3(unsigned(nblk)), dim3(Cb * 4), smem, st, xs, yb, ldy, Cs, Cb, B, H, W, scratch);
     launch_pdl(smallc_wgrad_reduce_kernel, dim3(unsigned((per + 127) / 128)), dim3(128), 0, st, scratch, int(nblk), Cs, Cb, mode, dw, db);
 }

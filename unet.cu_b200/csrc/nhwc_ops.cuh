@@ -10,6 +10,9 @@ namespace ub {
 
 typedef __nv_bfloat16 bf16;
 
+// one-time kernel attribute setup (opt-in shared memory); call before graph capture
+void nhwc_ops_init();
+
 // ---- GroupNorm (+ optional SiLU), replaces groupnorm_forward/backward + silu_forward/backward
 //      (/root/reference/train_unet.cu:1768-1991, :305-351).
 // chsum: [B][C][2] fp32 per-(image, channel) sum and sum of squares (must be zero on entry to gn_stats).

@@ -935,6 +935,7 @@ extern "C" int ub_trainer_create(UbTrainer** out, const UbConfig* cfg, int devic
     CUDA_TRY(cudaSetDevice(device));
     igemm_init();
     igemm_rows_init();
+    nhwc_ops_init();
     attn_init();
     attn_tc_init();
     UbTrainer* t = new UbTrainer();
