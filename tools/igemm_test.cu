@@ -111,6 +111,12 @@ static bool test_conv(int B, int H, int W, int Cin, int Cout, int ntaps, int Cin
     ep.residual = use_res ? dres : nullptr;
     ep.out = dout;
     ep.out_mode = out_mode;
+    float* dstats = nullptr;
+    if (getenv("UB_TEST_STATS") && out_mode == OUT_NHWC_BF16 && Cout % 32 == 0) {  // time the GroupNorm-statistics hook
+        CK(cudaMalloc(&dstats, size_t(B) * Cout * 2 * sizeof(float)));
+        CK(cudaMemset(dstats, 0, size_t(B) * Cout * 2 * sizeof(float)));
+        ep.stats = dstats;
+    }
     IgemmConvParams p;
     IgemmRowsParams ph;
     int r = halo ? igemm_rows_plan(&ph, segs, Cin2 ? 2 : 1, B, H, W, Cout, ep, 148)
@@ -121,6 +127,9 @@ static bool test_conv(int B, int H, int W, int Cin, int Cout, int ntaps, int Cin
         return false;
     }
     auto launch = [&]() { return halo ? igemm_rows_launch(ph, 0) : igemm_conv_launch(p, 0); };
+#ifdef UB_TRACE
+    igemm_trace_set_mode(0);
+#endif
     r = launch();
     cudaError_t e = cudaDeviceSynchronize();
     if (r || e != cudaSuccess) {
@@ -170,6 +179,9 @@ static bool test_conv(int B, int H, int W, int Cin, int Cout, int ntaps, int Cin
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
+#ifdef UB_TRACE
+        if (getenv("UB_TRACE_MODE")) igemm_trace_set_mode(atoi(getenv("UB_TRACE_MODE")));  // (results are garbage)
+#endif
         for (int i = 0; i < 3; ++i) launch();
         cudaEventRecord(e0);
         for (int i = 0; i < reps; ++i) launch();
@@ -178,6 +190,10 @@ static bool test_conv(int B, int H, int W, int Cin, int Cout, int ntaps, int Cin
         cudaEventElapsedTime(&ms, e0, e1);
         ms /= reps;
     }
+#ifdef UB_TRACE
+    if (!halo && reps > 0) igemm_trace_dump(p.tiles_w * p.tiles_h * p.tiles_b * (p.Cout / p.BN), 1.965);
+#endif
+    if (dstats) cudaFree(dstats);
     double flops = 2.0 * npix * Cout * (double(ntaps) * Cin + Cin2);
     printf("%s B%d %dx%d %d->%d taps%d seg2=%d mode%d b%d r%d s%d | BN=%d stages=%d | checked %zu bad %d max_err %.3g "
            "(max_ref %.3g) | %.4f ms %.1f TFLOP/s  %s\n",

@@ -14,7 +14,10 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libunet_b200.so")
+# UB_LIB_VARIANT=<name> loads lib/libunet_b200_<name>.so: a development switch for A/B-measuring compile-time kernel
+# variants in one GPU session (unet.cu_b200/Makefile, VARIANT=).  Unset = the shipped library.
+_VARIANT = os.environ.get("UB_LIB_VARIANT", "")
+LIB_PATH = os.path.join(_HERE, "lib", f"libunet_b200{'_' + _VARIANT if _VARIANT else ''}.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "unet_b200.h")
 
 UB_NCCL_ID_BYTES = 128

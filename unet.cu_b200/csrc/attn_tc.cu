@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(kThreads) attn_tc_fwd_kernel(const __grid_cons
             tc_fence_before();
             mbar_arrive(&sm->bar_p);
             mbar_wait(&sm->bar_o, h);
+            if (h == 1) pdl_trigger_late();  // all MMAs of this CTA are complete
             tc_fence_after();
             l += sl[(h * 2 + (half ^ 1)) * 128 + r];  // (ordered by the bar_p arrive / bar_o wait pair)
             uint32_t o[16];
@@ -367,6 +368,7 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dq_kernel(const __grid_const
             }
             // dQ of this head is complete when the last chunk's MMAs are
             mbar_wait(&sm->bar_o, (it - 1) & 1);
+            if (h == 1) pdl_trigger_late();  // all MMAs of this CTA are complete
             tc_fence_after();
             uint32_t o[16];
             tmem_ld16(trow + 256 + h * 64 + h * 32 + half * 16, o);
@@ -504,6 +506,7 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dkv_kernel(const __grid_cons
                 mbar_arrive(&sm->bar_p);
             }
             mbar_wait(&sm->bar_o, (it - 1) & 1);
+            if (h == 1) pdl_trigger_late();  // all MMAs of this CTA are complete
             tc_fence_after();
             uint32_t dk[16], dv[16];
             tmem_ld16(trow + 256 + h * 64 + h * 32 + half * 16, dk);

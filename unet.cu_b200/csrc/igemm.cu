@@ -16,6 +16,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#ifdef UB_TRACE
+#include <algorithm>
+#include <vector>
+#endif
 
 namespace ub {
 
@@ -24,11 +28,69 @@ static constexpr int kConvThreads = 320;   // conv: TMA warp, MMA warp, 8 epilog
 static constexpr int kWgradThreads = 192;  // wgrad: TMA warp, MMA warp, 4 epilogue warps
 static constexpr int kEpiThreads = kConvThreads - 64;
 
+// Phase timeline of igemm_conv_kernel (development only: -DUB_TRACE, tools/igemm_test.cu `trace` mode).  Per CTA:
+// [0] globaltimer at entry, [1] SM id, then SM clock at [2] entry [3] prologue done [4] griddepcontrol.wait passed
+// [5] last TMA issued [6] first stage landed [7] last MMA issued [8] accumulator complete [9] epilogue done [10] exit
+// [11] globaltimer at exit.
+#ifdef UB_TRACE
+static constexpr int kTraceSlots = 12, kTraceCtas = 2048;
+__device__ unsigned long long g_conv_trace[kTraceSlots * kTraceCtas];
+// 0 = normal, 1 = TMA stream only (no MMAs: stages are released by a plain arrive), 2 = MMA stream only (no TMA, no
+// full-barrier waits: the MMAs read whatever is in shared memory) -- which side paces the main loop?
+__device__ int g_conv_dbg_mode;
+void igemm_trace_set_mode(int m) { cudaMemcpyToSymbol(g_conv_dbg_mode, &m, sizeof(int)); }
+__device__ __forceinline__ unsigned long long trace_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define UB_TR(slot, val)                                                                              \
+    do {                                                                                              \
+        const unsigned cta_ = blockIdx.y * gridDim.x + blockIdx.x;                                    \
+        if (cta_ < unsigned(kTraceCtas)) g_conv_trace[cta_ * kTraceSlots + (slot)] = (val);           \
+    } while (0)
+void igemm_trace_dump(int nctas, double clock_ghz) {
+    std::vector<unsigned long long> h(size_t(kTraceSlots) * kTraceCtas);
+    cudaMemcpyFromSymbol(h.data(), g_conv_trace, h.size() * sizeof(unsigned long long));
+    if (nctas > kTraceCtas) nctas = kTraceCtas;
+    unsigned long long g0 = ~0ull, g1 = 0, gs_max = 0;
+    for (int i = 0; i < nctas; ++i) {
+        g0 = std::min(g0, h[size_t(i) * kTraceSlots]);
+        gs_max = std::max(gs_max, h[size_t(i) * kTraceSlots]);
+        g1 = std::max(g1, h[size_t(i) * kTraceSlots + 11]);
+    }
+    const char* names[] = {"prologue(sync)", "pdl_wait", "last TMA issued", "first stage landed", "last MMA issued",
+                           "accumulator complete", "epilogue done", "exit"};
+    printf("  trace: %d CTAs, first entry -> last exit %.2f us, entry spread %.2f us\n", nctas, (g1 - g0) * 1e-3,
+           (gs_max - g0) * 1e-3);
+    for (int k = 3; k <= 10; ++k) {
+        double sum = 0, mx = 0, mn = 1e30;
+        for (int i = 0; i < nctas; ++i) {
+            const double d = double(h[size_t(i) * kTraceSlots + k] - h[size_t(i) * kTraceSlots + 2]);
+            sum += d, mx = std::max(mx, d), mn = std::min(mn, d);
+        }
+        printf("    %-22s  avg %8.0f clk (%6.2f us)  min %8.0f  max %8.0f\n", names[k - 3], sum / nctas,
+               sum / nctas / (clock_ghz * 1e3), mn, mx);
+    }
+}
+#else
+#define UB_TR(slot, val) do {} while (0)
+#endif
+
 // =====================================================================================================
 // fprop / dgrad / 1x1 / linear
 // =====================================================================================================
 __global__ void __launch_bounds__(kConvThreads, 2) igemm_conv_kernel(const __grid_constant__ IgemmConvParams p) {
     pdl_trigger();
+#ifdef UB_TRACE
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        UB_TR(0, trace_gtime());
+        UB_TR(1, smid);
+        UB_TR(2, (unsigned long long)clock64());
+    }
+#endif
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + size_t(p.stages) * p.stage_bytes);
@@ -75,11 +137,17 @@ __global__ void __launch_bounds__(kConvThreads, 2) igemm_conv_kernel(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) UB_TR(3, (unsigned long long)clock64());
     pdl_wait();  // everything above touched only kernel parameters, shared memory and TMEM
+    if (threadIdx.x == 0) UB_TR(4, (unsigned long long)clock64());
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
+#ifdef UB_TRACE
+        if (lane == 0 && g_conv_dbg_mode < 2) {
+#else
         if (lane == 0) {
+#endif
             int stage = 0;
             uint32_t phase = 0;
             for (int s = 0; s < p.nseg; ++s) {
@@ -101,32 +169,60 @@ __global__ void __launch_bounds__(kConvThreads, 2) igemm_conv_kernel(const __gri
                     }
                 }
             }
+            UB_TR(5, (unsigned long long)clock64());
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
+        // (One thread's tcgen05.mma stream runs at ~145 cycles per M=128 instruction whatever N is, and streams of
+        //  different warps / CTAs overlap -- profiles/r01_mma_issue.txt.  A second issuer warp on alternate K blocks
+        //  with its own accumulator made the main loop of the 8x8 / 16x16 layers 25-35 % shorter in isolation, but the
+        //  11th warp caps the kernel at 80 registers: the spilling epilogue cost more in the step than the loop won.
+        //  Note for a retry: two issuers need an EVEN ring so that a stage always belongs to the same issuer -- with
+        //  an odd ring an issuer skips every other phase of a full barrier and a parity wait one phase early passes
+        //  immediately; that showed up as a rare hang.)
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
+#ifdef UB_TRACE
+            const int dbg = g_conv_dbg_mode;
+#endif
             for (int it = 0; it < nk; ++it) {
+#ifdef UB_TRACE
+                if (dbg < 2)
+#endif
                 mbar_wait(&full_bar[stage], phase);
+                if (it == 0) UB_TR(6, (unsigned long long)clock64());
                 tc_fence_after();
                 const uint32_t sA = smem_u32(smem + size_t(stage) * p.stage_bytes);
                 const uint32_t sB = sA + 16384;
                 const uint64_t dA = make_smem_desc_sw128(sA, 16, 1024);
                 const uint64_t dB = make_smem_desc_sw128(sB, 16, 1024);
+#ifdef UB_TRACE
+                if (dbg == 1) {
+                    mbar_arrive(&empty_bar[stage]);
+                } else
+#endif
+                {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    // advance 16 bf16 (32 B) along K inside the 128-byte swizzle row: +2 in the >>4 address field
-                    umma_bf16(tmem_base, dA + uint64_t(k * 2), dB + uint64_t(k * 2), idesc, (it | k) != 0);
+                    for (int k = 0; k < 4; ++k) {
+                        // advance 16 bf16 (32 B) along K inside the 128-byte swizzle row: +2 in the >>4 address field
+                        umma_bf16(tmem_base, dA + uint64_t(k * 2), dB + uint64_t(k * 2), idesc, (it | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);
                 }
-                umma_commit(&empty_bar[stage]);
                 if (++stage == p.stages) {
                     stage = 0;
                     phase ^= 1;
                 }
             }
+#ifdef UB_TRACE
+            if (dbg == 1) {
+                mbar_arrive(tmem_full_bar);
+            } else
+#endif
             umma_commit(tmem_full_bar);
+            UB_TR(7, (unsigned long long)clock64());
         }
     } else {
         // ------------------------------------------------------------ epilogue (warps 2..9)
@@ -156,6 +252,8 @@ __global__ void __launch_bounds__(kConvThreads, 2) igemm_conv_kernel(const __gri
         if (p.stats || p.gn_x) epi_side_load(eo, valid, pix, n0 + 16 * half, side);  // hidden behind the main loop
 
         mbar_wait(tmem_full_bar, 0);
+        pdl_trigger_late();  // main loop complete: the next kernel's prologue may overlap this epilogue
+        if (threadIdx.x == 64) UB_TR(8, (unsigned long long)clock64());
         tc_fence_after();
 
         // GroupNorm hooks: all 32 pixels of a warp lie in one image of the tile (plan)
@@ -169,11 +267,18 @@ __global__ void __launch_bounds__(kConvThreads, 2) igemm_conv_kernel(const __gri
             epi_flush_stats(red, p.gn_x ? p.gn_S : p.stats, p.Cout, n0, p.BN, b0, p.B, p.TW * p.TH, p.TB, et,
                             kEpiThreads);
         }
+        if (threadIdx.x == 64) UB_TR(9, (unsigned long long)clock64());
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+#ifdef UB_TRACE
+    if (threadIdx.x == 0) {
+        UB_TR(10, (unsigned long long)clock64());
+        UB_TR(11, trace_gtime());
+    }
+#endif
 }
 
 // =====================================================================================================
@@ -326,6 +431,7 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
             valid = lane < 16;
         }
         mbar_wait(tmem_full_bar, 0);
+        pdl_trigger_late();  // main loop complete: the next kernel's prologue may overlap this epilogue
         tc_fence_after();
         if (k_end > k_begin) {
             for (int ti = 0; ti < p.TC; ++ti) {
@@ -518,6 +624,10 @@ int igemm_conv_plan(IgemmConvParams* p, const ConvSegDesc* segs, int nseg, int B
             if (pix_tiles * (Cout / cand) >= 128) break;
         }
     if (!BN) return -2;
+    if (const char* e = getenv("UB_CONV_FORCE_BN")) {  // experiments only
+        const int f = atoi(e);
+        if (f >= 16 && Cout % f == 0 && f <= 256 && (!gn_hook || f % 32 == 0)) BN = f;
+    }
     p->nseg = nseg;
     p->B = B, p->H = H, p->W = W, p->Cout = Cout, p->BN = BN;
     p->TW = W < 128 ? W : 128;

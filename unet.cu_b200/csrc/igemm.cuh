@@ -177,4 +177,9 @@ int igemm_wgrad_launch(const IgemmWgradParams& p, cudaStream_t st);
 int igemm_wgrad_reduce(const IgemmWgradParams& p, float* dweight, cudaStream_t st);
 size_t igemm_wgrad_partial_floats(int Cin, int Cout, int ntaps, int nsplit);
 
+#ifdef UB_TRACE
+void igemm_trace_dump(int nctas, double clock_ghz);  // phase timeline of the last igemm_conv_kernel launch
+void igemm_trace_set_mode(int m);                    // 0 normal, 1 TMA stream only, 2 MMA stream only
+#endif
+
 }  // namespace ub

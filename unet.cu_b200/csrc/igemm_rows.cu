@@ -65,9 +65,10 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
             tma_prefetch_desc(&p.seg[s].tmA);
             tma_prefetch_desc(&p.seg[s].tmW);
         }
-        for (int i = 0; i < p.a_stages; ++i) mbar_init(&bars->a_full[i], 1), mbar_init(&bars->a_empty[i], 1);
-        for (int i = 0; i < p.w_stages; ++i) mbar_init(&bars->w_full[i], 1), mbar_init(&bars->w_empty[i], 1);
-        for (int i = 0; i < 2; ++i) mbar_init(&bars->t_full[i], 1), mbar_init(&bars->t_empty[i], 8);
+        // (two MMA issuers -- one per M half -- release every stage and complete every accumulator set together)
+        for (int i = 0; i < p.a_stages; ++i) mbar_init(&bars->a_full[i], 1), mbar_init(&bars->a_empty[i], 2);
+        for (int i = 0; i < p.w_stages; ++i) mbar_init(&bars->w_full[i], 1), mbar_init(&bars->w_empty[i], 2);
+        for (int i = 0; i < 2; ++i) mbar_init(&bars->t_full[i], 2), mbar_init(&bars->t_empty[i], 8);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -123,9 +124,13 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
                 }
             }
         }
-    } else if (warp == 2) {
-        // ------------------------------------------------------------------ MMA issuer
+    } else if (warp == 2 || warp == 3) {
+        // ------------------------------------------------------------------ MMA issuers: warp 2 -> M half 0, warp 3 -> 1
+        // One thread's tcgen05.mma stream runs at ~145 cycles per instruction whatever N is (measured with the phase
+        // trace of tools/igemm_test.cu, profiles/r01_mma_issue.txt); streams of different warps overlap, so the two
+        // halves of a tile are issued by two warps.
         if (lane == 0) {
+            const int mhalf = warp - 2;
             const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
             const uint32_t row_bytes = uint32_t(p.W) * 128u;  // one image row of a box (multiple of 1024)
             int sa = 0, sw = 0;
@@ -150,14 +155,11 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
                                 const uint32_t a0 = a_base + uint32_t(dyi) * row_bytes;  // box starts at row h0 - 1
                                 const uint64_t dB =
                                     make_smem_desc_sw128(smem_u32(sW + size_t(sw) * p.w_stage_bytes), 16, 1024);
+                                const uint64_t dA = make_smem_desc_sw128(a0 + uint32_t(mhalf) * 16384u, 16, 1024);
 #pragma unroll
-                                for (int half = 0; half < 2; ++half) {
-                                    const uint64_t dA = make_smem_desc_sw128(a0 + uint32_t(half) * 16384u, 16, 1024);
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k)
-                                        umma_bf16(d0 + uint32_t(half * p.BN), dA + uint64_t(k * 2), dB + uint64_t(k * 2),
-                                                  idesc, (!first || k != 0) ? 1u : 0u);
-                                }
+                                for (int k = 0; k < 4; ++k)
+                                    umma_bf16(d0 + uint32_t(mhalf * p.BN), dA + uint64_t(k * 2), dB + uint64_t(k * 2), idesc,
+                                              (!first || k != 0) ? 1u : 0u);
                                 first = false;
                                 umma_commit(&bars->w_empty[sw]);
                                 if (++sw == p.w_stages) sw = 0, pw ^= 1;
@@ -198,6 +200,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
             uint4 side[2];
             if (hook) epi_side_load(eo, valid, pix, n0, side);  // hidden behind the tile's main loop
             mbar_wait(&bars->t_full[buf], (it >> 1) & 1);
+            if (tile + int(gridDim.x) >= p.num_tiles) pdl_trigger_late();  // last tile of this CTA
             tc_fence_after();
             const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * 2 * p.BN + half * p.BN);
             epi_row(eo, trow, cb_, p.BN, valid, pix, b, h, w, n0, gc_, lane, red + size_t(warp - 4) * p.BN * 2,

@@ -29,9 +29,29 @@ __device__ __forceinline__ void pdl_trigger() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
 }
+// Late trigger (GEMM-shaped kernels): issued by a CTA once its main loop is complete, so the next kernel's CTAs become
+// resident and run their prologue (barrier init, TMEM allocation, descriptor prefetch) under this kernel's epilogue
+// and teardown only -- they cannot take resources from a main loop that is still running.
+#ifndef UB_PDL_LATE_TRIGGER
+#define UB_PDL_LATE_TRIGGER 1
+#endif
+__device__ __forceinline__ void pdl_trigger_late() {
+#if UB_PDL_LATE_TRIGGER
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 // the usual kernel entry: let the dependent grid start early, then wait for our own prerequisite
+// (UB_PDL_ELT_EARLY: entry trigger only in the elementwise / normalisation kernels, whose CTAs hold no shared memory
+//  or TMEM that an early-resident dependent could be starved of)
+#ifndef UB_PDL_ELT_EARLY
+#define UB_PDL_ELT_EARLY 0
+#endif
 __device__ __forceinline__ void pdl_entry() {
+#if UB_PDL_ELT_EARLY
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#else
     pdl_trigger();
+#endif
     pdl_wait();
 }
 

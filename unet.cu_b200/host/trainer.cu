@@ -251,10 +251,17 @@ struct Builder {
     bf16* packbuf(size_t n) { return (bf16*)T->arena.alloc(n * sizeof(bf16)); }
 
     bool real() const { return !T->arena.counting; }
-    void F(UbTrainer::Op op, int launches = 1, int kind = UB_KIND_SMALL, double flops = 0, double bytes = 0) {
+    void F(UbTrainer::Op op, int launches = 1, int kind = UB_KIND_SMALL, double flops = 0, double bytes = 0,
+           int side = 0) {
         if (!real()) return;
         T->fwd_ops.push_back(std::move(op)), T->launches_fwd += launches;
-        T->fwd_info.push_back({kind, launches, flops, bytes, 0, next_label}), next_label.clear();
+        T->fwd_info.push_back({kind, launches, flops, bytes, side, next_label}), next_label.clear();
+    }
+    // forward: the time-embedding chain runs on the side stream until its first consumer (conv1 of the first ResBlock)
+    bool fwd_side_pending = false;
+    void join_side_fwd() {
+        if (fwd_side_pending) F([](cudaStream_t) {}, 0, UB_KIND_SMALL, 0, 0, 2);
+        fwd_side_pending = false;
     }
     void Bk(UbTrainer::Op op, int launches = 1, int kind = UB_KIND_SMALL, double flops = 0, double bytes = 0,
             int side = 0) {
@@ -434,6 +441,7 @@ struct Builder {
         {
             ConvEpilogue ep;
             ep.bias = P(b1), ep.rowvec = embproj, ep.out = h1.p, ep.ldo = h1.ld, ep.stats = h1.cs;
+            join_side_fwd();  // embproj comes from the time-embedding chain
             conv_op(true, {{a1.p, C, a1.ld, p1.wf, 9}}, H, W, Cout, ep);
         }
         View a2 = act(Cout, H, W);
@@ -632,7 +640,8 @@ int Builder::build() {
             small_linear_fwd(Tt->temb_table + 1, 1, Bn, Cemb, st);
             silu_f32(Tt->emb, Tt->semb, size_t(Bn) * Cemb, st);  // shared input of all embedding projections
             small_linear_fwd(Tt->emb_table, int(Tt->h_emb.size()), Bn, Tt->emb_max_oc, st);
-        }, 5);
+        }, 5, UB_KIND_SMALL, 0, 0, 1);  // beside the input conv and the first GroupNorm
+        fwd_side_pending = true;
     }
     const size_t time_mlp_end = poff;
 
