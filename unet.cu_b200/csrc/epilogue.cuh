@@ -31,7 +31,22 @@ struct EpiOut {
     int ldgx = 0;
     float* gS = nullptr;                 // gn-bwd: [B][Cout][2] += (sum dz, sum dz*xhat)
     int gsilu = 0;
+    // two MMA streams (igemm_conv2_kernel): the result is the sum of two accumulators acc_stride TMEM columns apart
+    int nacc = 1;
+    uint32_t acc_stride = 0;
 };
+
+// v[0..16) = the 16 accumulator columns at taddr (summed over both accumulators if there are two)
+__device__ __forceinline__ void epi_tmem_load16(const EpiOut& e, uint32_t taddr, uint32_t (&v)[16]) {
+    tmem_ld16(taddr, v);
+    if (e.nacc == 2) {
+        uint32_t u[16];
+        tmem_ld16(taddr + e.acc_stride, u);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+    }
+}
 
 __device__ __forceinline__ float epi_sigmoid(float z) {
     float t;
@@ -56,9 +71,9 @@ __device__ __forceinline__ void epi_chunk(const EpiOut& e, uint32_t taddr, const
                                           int b, int h, int w, int n) {
     uint32_t v[NC];
     if constexpr (NC == 32) {
-        tmem_ld32(taddr, v);
+        tmem_ld32(taddr, v);  // (one accumulator only: epi_row)
     } else {
-        tmem_ld16(taddr, v);
+        epi_tmem_load16(e, taddr, v);
     }
     uint4 r[NC / 8];
     if (e.residual && valid) {
@@ -130,7 +145,7 @@ __device__ __forceinline__ void epi_chunk_gn(const EpiOut& e, uint32_t taddr, co
                                              int cstride, bool valid, size_t pix, int n, int lane, float* red,
                                              float* tr, uint4 (&xr)[2], int n_next) {
     uint32_t v[16];
-    tmem_ld16(taddr, v);
+    epi_tmem_load16(e, taddr, v);
     uint4 xn[2];
     if (n_next >= 0) epi_side_load(e, valid, pix, n_next, xn);
     tmem_ld_wait();
@@ -255,8 +270,9 @@ __device__ __forceinline__ void epi_row(const EpiOut& e, uint32_t trow, const fl
         return;
     }
     int i = 0, c0 = 0;
-    for (; c0 + 32 <= BN; c0 += 32, ++i)
-        if (i % nhalf == half) epi_chunk<32>(e, trow + uint32_t(c0), comb + c0, valid, pix, b, h, w, n0 + c0);
+    if (e.nacc == 1)  // (two accumulators are added per 16-column chunk)
+        for (; c0 + 32 <= BN; c0 += 32, ++i)
+            if (i % nhalf == half) epi_chunk<32>(e, trow + uint32_t(c0), comb + c0, valid, pix, b, h, w, n0 + c0);
     for (; c0 < BN; c0 += 16, ++i)
         if (i % nhalf == half) epi_chunk<16>(e, trow + uint32_t(c0), comb + c0, valid, pix, b, h, w, n0 + c0);
 }

@@ -80,7 +80,64 @@ void igemm_trace_dump(int nctas, double clock_ghz) {
 // =====================================================================================================
 // fprop / dgrad / 1x1 / linear
 // =====================================================================================================
-__global__ void __launch_bounds__(kConvThreads, 2) igemm_conv_kernel(const __grid_constant__ IgemmConvParams p) {
+// One K block (stage) worth of MMAs for issuer `issuer` of NACC: K blocks it = issuer (mod NACC), accumulator `issuer`.
+template <int NACC>
+__device__ __forceinline__ void conv_issue_loop(const IgemmConvParams& p, int issuer, int nk, uint8_t* smem,
+                                                uint64_t* full_bar, uint64_t* empty_bar, uint64_t* tmem_full_bar,
+                                                uint32_t tmem_base) {
+    const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
+    const uint32_t d = tmem_base + uint32_t(issuer * p.BN);
+    // (NACC == 2: the ring is even -- plan -- so stage s always belongs to issuer s % 2 and each issuer waits for
+    //  consecutive phases of its full barriers)
+    int stage = issuer;
+    uint32_t phase = 0;
+#ifdef UB_TRACE
+    const int dbg = g_conv_dbg_mode;
+#endif
+    for (int it = issuer; it < nk; it += NACC) {
+#ifdef UB_TRACE
+        if (dbg < 2)
+#endif
+        mbar_wait(&full_bar[stage], phase);
+        if (it == 0) UB_TR(6, (unsigned long long)clock64());
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + size_t(stage) * p.stage_bytes);
+        const uint32_t sB = sA + 16384;
+        const uint64_t dA = make_smem_desc_sw128(sA, 16, 1024);
+        const uint64_t dB = make_smem_desc_sw128(sB, 16, 1024);
+#ifdef UB_TRACE
+        if (dbg == 1) {
+            mbar_arrive(&empty_bar[stage]);
+        } else
+#endif
+        {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                // advance 16 bf16 (32 B) along K inside the 128-byte swizzle row: +2 in the >>4 address field
+                umma_bf16(d, dA + uint64_t(k * 2), dB + uint64_t(k * 2), idesc, (it >= NACC || k != 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);
+        }
+        stage += NACC;
+        if (stage >= p.stages) stage -= p.stages, phase ^= 1;
+    }
+#ifdef UB_TRACE
+    if (dbg == 1) {
+        mbar_arrive(tmem_full_bar);
+    } else
+#endif
+    umma_commit(tmem_full_bar);
+    if (issuer == 0) UB_TR(7, (unsigned long long)clock64());
+}
+
+// NACC = number of MMA issue streams (and accumulators).  One thread's tcgen05.mma stream runs at ~145 cycles per
+// M=128 instruction whatever N is, and streams of different warps / CTAs overlap (profiles/r01_mma_issue.txt).  Grids
+// that fill the chip run NACC = 1 with two CTAs per SM (two streams per SM already).  Grids of <= one CTA per SM (the
+// 8x8 / 16x16 levels) run NACC = 2: lane 0 of the last epilogue warp -- idle during the main loop -- issues the odd K
+// blocks into a second accumulator and the epilogue adds the two.  (An 11th warp for the second issuer capped the
+// two-CTA kernel at 80 registers; the spilling epilogue cost more in the step than the main loop won.)
+template <int NACC>
+__device__ __forceinline__ void igemm_conv_body(const IgemmConvParams& p) {
     pdl_trigger();
 #ifdef UB_TRACE
     if (threadIdx.x == 0) {
@@ -126,19 +183,30 @@ __global__ void __launch_bounds__(kConvThreads, 2) igemm_conv_kernel(const __gri
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
-        mbar_init(tmem_full_bar, 1);
+        mbar_init(tmem_full_bar, NACC);
         fence_mbar_init();
     }
     if (warp == 1) {
         tmem_alloc(tmem_slot, p.tmem_cols);
         tmem_relinquish();
     }
+    if (warp == 2 && lane == 0) {
+        // Pull this N tile's weights into L2 while the previous kernel is still in its epilogue (late PDL trigger):
+        // the weights are evicted by the ~2 GB of activations every step streams through the 126 MB L2, and the
+        // low-resolution layers are paced by their weight tiles' latency.  The tile's rows of one tap are contiguous;
+        // the pixel tiles of the grid share the taps.  (Packed weights are written by the optimizer's re-pack long
+        // before -- never by the kernel this launch depends on.)
+        for (int s = 0; s < p.nseg; ++s)
+            for (int tap = blockIdx.x; tap < p.seg[s].ntaps; tap += gridDim.x)
+                l2_prefetch_bulk(p.seg[s].wp + (size_t(tap) * p.Cout + n0) * p.seg[s].Cin,
+                                 uint32_t(p.BN) * uint32_t(p.seg[s].Cin) * 2u);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) UB_TR(3, (unsigned long long)clock64());
-    pdl_wait();  // everything above touched only kernel parameters, shared memory and TMEM
+    pdl_wait();  // everything above touched only kernel parameters, shared memory, TMEM (and prefetched weights)
     if (threadIdx.x == 0) UB_TR(4, (unsigned long long)clock64());
 
     if (warp == 0) {
@@ -172,60 +240,16 @@ __global__ void __launch_bounds__(kConvThreads, 2) igemm_conv_kernel(const __gri
             UB_TR(5, (unsigned long long)clock64());
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer
-        // (One thread's tcgen05.mma stream runs at ~145 cycles per M=128 instruction whatever N is, and streams of
-        //  different warps / CTAs overlap -- profiles/r01_mma_issue.txt.  A second issuer warp on alternate K blocks
-        //  with its own accumulator made the main loop of the 8x8 / 16x16 layers 25-35 % shorter in isolation, but the
-        //  11th warp caps the kernel at 80 registers: the spilling epilogue cost more in the step than the loop won.
-        //  Note for a retry: two issuers need an EVEN ring so that a stage always belongs to the same issuer -- with
-        //  an odd ring an issuer skips every other phase of a full barrier and a parity wait one phase early passes
-        //  immediately; that showed up as a rare hang.)
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
-            int stage = 0;
-            uint32_t phase = 0;
-#ifdef UB_TRACE
-            const int dbg = g_conv_dbg_mode;
-#endif
-            for (int it = 0; it < nk; ++it) {
-#ifdef UB_TRACE
-                if (dbg < 2)
-#endif
-                mbar_wait(&full_bar[stage], phase);
-                if (it == 0) UB_TR(6, (unsigned long long)clock64());
-                tc_fence_after();
-                const uint32_t sA = smem_u32(smem + size_t(stage) * p.stage_bytes);
-                const uint32_t sB = sA + 16384;
-                const uint64_t dA = make_smem_desc_sw128(sA, 16, 1024);
-                const uint64_t dB = make_smem_desc_sw128(sB, 16, 1024);
-#ifdef UB_TRACE
-                if (dbg == 1) {
-                    mbar_arrive(&empty_bar[stage]);
-                } else
-#endif
-                {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        // advance 16 bf16 (32 B) along K inside the 128-byte swizzle row: +2 in the >>4 address field
-                        umma_bf16(tmem_base, dA + uint64_t(k * 2), dB + uint64_t(k * 2), idesc, (it | k) != 0);
-                    }
-                    umma_commit(&empty_bar[stage]);
-                }
-                if (++stage == p.stages) {
-                    stage = 0;
-                    phase ^= 1;
-                }
-            }
-#ifdef UB_TRACE
-            if (dbg == 1) {
-                mbar_arrive(tmem_full_bar);
-            } else
-#endif
-            umma_commit(tmem_full_bar);
-            UB_TR(7, (unsigned long long)clock64());
-        }
+        // ------------------------------------------------------------ MMA issuer (stream 0)
+        if (lane == 0) conv_issue_loop<NACC>(p, 0, nk, smem, full_bar, empty_bar, tmem_full_bar, tmem_base);
     } else {
         // ------------------------------------------------------------ epilogue (warps 2..9)
+        if constexpr (NACC == 2) {  // second MMA stream first; the warp reconverges before it touches the epilogue
+            if (warp == 9) {
+                if (lane == 0) conv_issue_loop<NACC>(p, 1, nk, smem, full_bar, empty_bar, tmem_full_bar, tmem_base);
+                __syncwarp();
+            }
+        }
         const int q = warp & 3;  // TMEM lane quadrant this warp may access
         const int half = (warp - 2) >> 2;  // the two warps of a quadrant split the columns
         const int row = q * 32 + lane;
@@ -248,6 +272,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) igemm_conv_kernel(const __gri
         const size_t pix = (size_t(b) * p.H + h) * p.W + w;
         EpiOut eo{p.residual, p.ldr, p.out, p.ldo, p.out_mode, p.Cout, p.H, p.W};
         eo.stats = p.stats, eo.gx = p.gn_x, eo.ldgx = p.gn_ldx, eo.gS = p.gn_S, eo.gsilu = p.gn_silu;
+        eo.nacc = NACC, eo.acc_stride = uint32_t(p.BN);
         uint4 side[2];
         if (p.stats || p.gn_x) epi_side_load(eo, valid, pix, n0 + 16 * half, side);  // hidden behind the main loop
 
@@ -279,6 +304,12 @@ __global__ void __launch_bounds__(kConvThreads, 2) igemm_conv_kernel(const __gri
         UB_TR(11, trace_gtime());
     }
 #endif
+}
+__global__ void __launch_bounds__(kConvThreads, 2) igemm_conv_kernel(const __grid_constant__ IgemmConvParams p) {
+    igemm_conv_body<1>(p);
+}
+__global__ void __launch_bounds__(kConvThreads, 1) igemm_conv2_kernel(const __grid_constant__ IgemmConvParams p) {
+    igemm_conv_body<2>(p);
 }
 
 // =====================================================================================================
@@ -638,7 +669,16 @@ int igemm_conv_plan(IgemmConvParams* p, const ConvSegDesc* segs, int nseg, int B
     p->tiles_w = ceil_div_i(W, p->TW);
     p->tiles_h = ceil_div_i(H, p->TH);
     p->tiles_b = ceil_div_i(B, p->TB);
-    p->tmem_cols = next_pow2(BN < 32 ? 32 : BN);
+    // Two MMA streams for grids of at most one CTA per SM (see igemm_conv_body); both accumulators within 256 TMEM
+    // columns so that a weight-gradient CTA of the side stream still finds room.
+    p->nacc = 1;
+    {
+        static const bool two = !(getenv("UB_CONV_NACC") && atoi(getenv("UB_CONV_NACC")) < 2);
+        int nkb = 0;
+        for (int s = 0; s < nseg; ++s) nkb += segs[s].ntaps * ceil_div_i(segs[s].Cin, 64);
+        if (two && pix_tiles * (Cout / BN) <= 148 && BN % 32 == 0 && BN <= 128 && nkb >= 4) p->nacc = 2;
+    }
+    p->tmem_cols = next_pow2(p->nacc * BN < 32 ? 32 : p->nacc * BN);
     p->a_bytes = uint32_t(64 * p->TW * p->TH * p->TB * 2);
     p->b_bytes = uint32_t(64 * BN * 2);
     p->stage_bytes = 16384u + ((p->b_bytes + 1023u) & ~1023u);
@@ -652,6 +692,15 @@ int igemm_conv_plan(IgemmConvParams* p, const ConvSegDesc* segs, int nseg, int B
     if (stages < 3) stages = int((227u * 1024u - tail) / p->stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) return -3;
+    if (p->nacc == 2 && (stages & 1)) {
+        // Two issuers need an EVEN ring: with an odd one the owner of a stage alternates, an issuer skips every other
+        // phase of a full barrier, and a parity wait that comes one whole phase early passes immediately (this was a
+        // rare hang).  One CTA per SM here, so the ring may grow a stage (kept <= 128 KiB beside a wgrad CTA).
+        if (size_t(stages + 1) * p->stage_bytes + tail <= 128u * 1024u && stages + 1 <= kMaxStages)
+            stages += 1;
+        else
+            stages -= 1;
+    }
     p->stages = stages;
     for (int s = 0; s < nseg; ++s) {
         const ConvSegDesc& d = segs[s];
@@ -663,6 +712,7 @@ int igemm_conv_plan(IgemmConvParams* p, const ConvSegDesc* segs, int nseg, int B
         if (r) return r;
         p->seg[s].cblocks = ceil_div_i(d.Cin, 64);
         p->seg[s].ntaps = d.ntaps;
+        p->seg[s].wp = d.wp, p->seg[s].Cin = d.Cin;
     }
     p->bias = ep.bias;
     p->bias2 = ep.bias2;
@@ -709,6 +759,7 @@ void igemm_init() {
     static bool done = false;
     if (done) return;
     cudaFuncSetAttribute(igemm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(227 * 1024));
+    cudaFuncSetAttribute(igemm_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(227 * 1024));
     cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(227 * 1024));
     done = true;
 }
@@ -718,7 +769,7 @@ int igemm_conv_launch(const IgemmConvParams& p, cudaStream_t st) {
     const size_t smem = size_t(p.stages) * p.stage_bytes + 1024 + kBarrierBytes +
                         size_t(p.ncomb + 4 * p.ngimg + p.nred) * p.BN * sizeof(float);
     dim3 grid(p.tiles_w * p.tiles_h * p.tiles_b, p.Cout / p.BN);
-    launch_pdl(igemm_conv_kernel, dim3(grid), dim3(kConvThreads), smem, st, p);
+    launch_pdl(p.nacc == 2 ? igemm_conv2_kernel : igemm_conv_kernel, dim3(grid), dim3(kConvThreads), smem, st, p);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)  // a failed launch must never pass silently (the output would simply be stale)
         fprintf(stderr, "[unet_b200] igemm_conv launch failed: %s (grid %u x %u, smem %zu, BN %d, stages %d)\n",

@@ -25,6 +25,8 @@ struct IgemmSeg {
     CUtensorMap tmW;  // packed weights [ntaps*Cout][Cin] bf16, dims (Cin, ntaps*Cout), box (64, BN), SWIZZLE_128B
     int cblocks;      // ceil(Cin / 64)
     int ntaps;        // 9 or 1
+    const __nv_bfloat16* wp;  // the packed weights behind tmW (L2 prefetch in the prologue)
+    int Cin;
 };
 
 struct IgemmConvParams {
@@ -35,7 +37,8 @@ struct IgemmConvParams {
     int tiles_w, tiles_h, tiles_b;
     int BN;          // output-channel tile: multiple of 16, <= 256
     int stages;
-    int tmem_cols;   // power of two >= max(32, BN)
+    int tmem_cols;   // power of two >= max(32, nacc * BN)
+    int nacc;        // MMA issue streams = accumulators (1, or 2 for grids of at most one CTA per SM)
     int ncomb;       // rows of the staged per-channel addend (TB when a per-image vector is fused, else 1)
     uint32_t a_bytes, b_bytes;  // TMA transaction bytes per stage
     uint32_t stage_bytes;       // smem bytes per stage (A tile 16 KiB + B tile, 1024-aligned)
