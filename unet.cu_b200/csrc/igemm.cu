@@ -201,6 +201,20 @@ __device__ __forceinline__ void igemm_conv_body(const IgemmConvParams& p) {
                 l2_prefetch_bulk(p.seg[s].wp + (size_t(tap) * p.Cout + n0) * p.seg[s].Cin,
                                  uint32_t(p.BN) * uint32_t(p.seg[s].Cin) * 2u);
     }
+    if (warp == 3 && lane == 0 && p.gn_x) {
+        // gn-bwd hook: the GroupNorm input rows of this pixel tile were written in the forward pass (long evicted);
+        // fetch them into L2 now instead of at the epilogue's dependent per-chunk loads.  A pixel row of the tile is
+        // contiguous over all channels; the N tiles of the grid share the rows.
+        const int nrows = p.TB * p.TH;
+        for (int r = blockIdx.y; r < nrows; r += gridDim.y) {
+            const int b = b0 + r / p.TH, h = h0 + r % p.TH;
+            if (b < p.B && h < p.H) {
+                const int wn = min(p.TW, p.W - w0);
+                l2_prefetch_bulk(p.gn_x + ((size_t(b) * p.H + h) * p.W + w0) * p.gn_ldx,
+                                 (uint32_t(wn - 1) * uint32_t(p.gn_ldx) + uint32_t(p.Cout)) * 2u);
+            }
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();

@@ -75,6 +75,12 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
         tmem_alloc(&bars->tmem_slot, 512);
         tmem_relinquish();
     }
+    if (warp == 4 && lane == 0 && p.gn_x && int(blockIdx.x) < p.num_tiles) {  // first tile's GroupNorm-input rows -> L2
+        const int mt = int(blockIdx.x) % tiles_mb;
+        const int b = mt / p.tiles_per_img, h0 = (mt % p.tiles_per_img) * p.TH;
+        l2_prefetch_bulk(p.gn_x + ((size_t(b) * p.H + h0) * p.W) * p.gn_ldx,
+                         (uint32_t(min(p.TH, p.H - h0) * p.W - 1) * uint32_t(p.gn_ldx) + uint32_t(p.Cout)) * 2u);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -193,6 +199,17 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
                 epi_stage_gconst(gc_, p.gn_chsum, p.gn_gamma, p.gn_beta, b, p.Cout, p.gn_cpg, p.H * p.W, n0, p.BN, et,
                                  kRowsEpiThreads);
             named_bar_sync(1, kRowsEpiThreads);
+            if (p.gn_x && threadIdx.x == 128) {
+                // the NEXT tile's GroupNorm-input rows (written in the forward pass, long evicted) -> L2
+                const int nt = tile + int(gridDim.x);
+                if (nt < p.num_tiles) {
+                    const int nmt = nt % tiles_mb;
+                    const int nb = nmt / p.tiles_per_img, nh0 = (nmt % p.tiles_per_img) * p.TH;
+                    const int nrows = min(p.TH, p.H - nh0);
+                    l2_prefetch_bulk(p.gn_x + ((size_t(nb) * p.H + nh0) * p.W) * p.gn_ldx,
+                                     (uint32_t(nrows * p.W - 1) * uint32_t(p.gn_ldx) + uint32_t(p.Cout)) * 2u);
+                }
+            }
             const int row = half * 128 + q * 32 + lane;
             const int h = h0 + row / p.W, w = row % p.W;
             const bool valid = h < p.H;

@@ -735,8 +735,88 @@ __global__ void smallc_conv_pair_kernel(const float* __restrict__ xs, const floa
     st8(y + p0 * ldy + j * 8, a0);
     st8(y + (p0 + 1) * ldy + j * 8, a1);
 }
+// Row-per-warp version for Cs == 3, Cb % 64 == 0, W % 4 == 0: a warp owns one image row and one group of 64 big
+// channels; lane l keeps the 2 x 27 weights of channels 2l, 2l+1 in registers, the zero-padded 3 x 3 x (W+2) input
+// window of the row sits in shared memory and is read as warp-uniform (broadcast) vectors -- 18 LDS per 216 FMAs, so
+// the kernel is FMA-bound (the pixel-per-thread kernels above were bound by LDS issue: one 16-byte weight read per
+// 8 FMAs, 2-way bank conflicted) -- and every pixel's 64 channels leave the warp as one 128-byte store.
+constexpr int kSmallcWarps = 8;
+__global__ void __launch_bounds__(kSmallcWarps * 32) smallc_conv_rows_kernel(
+    const float* __restrict__ xs, const float* __restrict__ w, const float* __restrict__ bias, int Cb, int B, int H,
+    int W, int flip, bf16* __restrict__ y, int ldy) {
+    pdl_entry();
+    constexpr int CS = 3;
+    extern __shared__ float sm[];
+    float* sw = sm;                      // [27][Cb]
+    const int WP = W + 4;                // padded row: pixel w at index w + 1, zeros at 0 and W + 1 .. W + 3
+    float* swin = sm + 27 * Cb + (threadIdx.x >> 5) * (9 * WP);  // this warp's [3 rows][CS][WP]
+    for (int i = threadIdx.x; i < Cb * 27; i += blockDim.x) {
+        const int cb = i % Cb, st = i / Cb;
+        const int s_ = st / 9, tap = st % 9;
+        sw[i] = flip ? w[(size_t(s_) * Cb + cb) * 9 + (8 - tap)] : w[(size_t(cb) * CS + s_) * 9 + tap];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int ngroups = Cb / 64;
+    const long long item = (long long)blockIdx.x * kSmallcWarps + (threadIdx.x >> 5);
+    if (item >= (long long)B * H * ngroups) return;
+    const int cg = int(item % ngroups);
+    const int h = int((item / ngroups) % H);
+    const int b = int(item / ((long long)ngroups * H));
+    // window rows h-1, h, h+1 of the three small channels, zero padded
+    for (int i = lane; i < 9 * WP; i += 32) {
+        const int col = i % WP, rs = i / WP;  // rs = r * CS + s
+        const int r = rs / CS, s_ = rs % CS;
+        const int hh = h + r - 1, ww = col - 1;
+        swin[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xs + ((size_t(b) * CS + s_) * H + hh) * W + ww) : 0.f;
+    }
+    float wr0[27], wr1[27];
+    const int c0 = cg * 64 + 2 * lane;
+#pragma unroll
+    for (int st = 0; st < 27; ++st) {
+        const float2 v = *reinterpret_cast<const float2*>(sw + st * Cb + c0);
+        wr0[st] = v.x, wr1[st] = v.y;
+    }
+    const float b0 = bias ? bias[c0] : 0.f, b1 = bias ? bias[c0 + 1] : 0.f;
+    __syncwarp();
+    bf16* yrow = y + ((size_t(b) * H + h) * W) * ldy + c0;
+    for (int x0 = 0; x0 < W; x0 += 4) {
+        float a0[4] = {b0, b0, b0, b0}, a1[4] = {b1, b1, b1, b1};
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s_ = 0; s_ < CS; ++s_) {
+                const float* wp_ = swin + (r * CS + s_) * WP + x0;  // window columns x0-1 .. x0+4 at indices x0 .. x0+5
+                const float4 u = *reinterpret_cast<const float4*>(wp_);
+                const float2 t = *reinterpret_cast<const float2*>(wp_ + 4);
+                const float win[6] = {u.x, u.y, u.z, u.w, t.x, t.y};
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float k0 = wr0[s_ * 9 + r * 3 + c], k1 = wr1[s_ * 9 + r * 3 + c];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) a0[j] = fmaf(win[j + c], k0, a0[j]), a1[j] = fmaf(win[j + c], k1, a1[j]);
+                }
+            }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(a0[j], a1[j]);
+            *reinterpret_cast<__nv_bfloat162*>(yrow + size_t(x0 + j) * ldy) = h2;
+        }
+    }
+}
+
 static void smallc_conv(const float* xs, const float* w, const float* bias, int Cs, int Cb, int B, int H, int W,
                         int flip, bf16* y, int ldy, cudaStream_t st) {
+    static const bool use_rows = !(getenv("UB_SMALLC_ROWS") && atoi(getenv("UB_SMALLC_ROWS")) == 0);
+    if (use_rows && Cs == 3 && Cb % 64 == 0 && W % 4 == 0 && (ldy % 2) == 0) {
+        const size_t smem_r = (size_t(27) * Cb + size_t(kSmallcWarps) * 9 * (W + 4)) * sizeof(float);
+        if (smem_r <= 48 * 1024) {
+            const long long items = (long long)B * H * (Cb / 64);
+            launch_pdl(smallc_conv_rows_kernel, dim3(unsigned((items + kSmallcWarps - 1) / kSmallcWarps)),
+                       dim3(kSmallcWarps * 32), smem_r, st, xs, w, bias, Cb, B, H, W, flip, y, ldy);
+            return;
+        }
+    }
     const size_t smem = size_t(Cb) * Cs * 9 * sizeof(float);
     if (W % 2 == 0) {
         const size_t total = size_t(B) * H * (W / 2) * (Cb / 8);
@@ -954,8 +1034,145 @@ __global__ void conv_out_pair_kernel(const bf16* __restrict__ a, int lda, const 
             *reinterpret_cast<float2*>(out + ((b * Cout + o) * H + h) * W + w0) = make_float2(a0[o] + bv, a1[o] + bv);
         }
 }
+// Row-per-warp output head (Cout == 3, Cin % 64 == 0, W % 8 == 0): lane l owns input channels 2l, 2l+1 of a 64-channel
+// group (its 3 x 2 x 9 weights in registers), slides a 3 x 3 window of bf16 pairs along the image row -- every load is
+// one coalesced 128-byte row of a pixel -- and the 3 x 8 partial sums of 8 pixels are added across the 32 lanes with a
+// 31-shuffle transpose-reduce.  The finished row goes through shared memory so that out (NCHW fp32) is written in
+// coalesced rows; with `target` the MSE loss and its gradient (mse_kernel) are computed on the spot.
+__global__ void __launch_bounds__(kSmallcWarps * 32) conv_out_rows_kernel(
+    const bf16* __restrict__ a, int lda, const float* __restrict__ w, const float* __restrict__ bias, int Cin, int B,
+    int H, int W, float* __restrict__ out, const float* __restrict__ target, float* __restrict__ loss,
+    float* __restrict__ dout, float inv_n, float gscale) {
+    pdl_entry();
+    constexpr int CO = 3;
+    extern __shared__ float sm[];
+    float* sw = sm;                                         // [CO][Cin][9] as given
+    float* srow = sm + CO * Cin * 9 + (threadIdx.x >> 5) * (CO * W);  // this warp's [CO][W] output row
+    __shared__ float sloss[kSmallcWarps];
+    for (int i = threadIdx.x; i < CO * Cin * 9; i += blockDim.x) sw[i] = w[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long item = (long long)blockIdx.x * kSmallcWarps + warp;
+    float lsum = 0.f;
+    if (item < (long long)B * H) {
+        const int h = int(item % H), b = int(item / H);
+        for (int i = lane; i < CO * W; i += 32) srow[i] = bias ? bias[i / W] : 0.f;
+        __syncwarp();
+        for (int cg = 0; cg < Cin / 64; ++cg) {
+            const int c0 = cg * 64 + 2 * lane;
+            float wr[CO][2][9];
+#pragma unroll
+            for (int o = 0; o < CO; ++o)
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) wr[o][cc][t] = sw[(o * Cin + c0 + cc) * 9 + t];
+            const bf16* rowp[3];
+            bool rok[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int hh = h + r - 1;
+                rok[r] = hh >= 0 && hh < H;
+                rowp[r] = a + ((size_t(b) * H + (rok[r] ? hh : h)) * W) * lda + c0;
+            }
+            // packed bf16 pairs of window columns x0-1 .. x0+8 per row: the two leading columns are carried over from
+            // the previous batch, the eight new ones are fetched with 24 independent loads (one L2 latency per 8 pixels)
+            uint32_t colw[3][10];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                colw[r][8] = 0u;  // column -1
+                colw[r][9] = rok[r] ? *reinterpret_cast<const uint32_t*>(rowp[r]) : 0u;  // column 0
+            }
+            for (int x0 = 0; x0 < W; x0 += 8) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    colw[r][0] = colw[r][8], colw[r][1] = colw[r][9];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        colw[r][2 + j] = (rok[r] && x0 + 1 + j < W)
+                                             ? *reinterpret_cast<const uint32_t*>(rowp[r] + size_t(x0 + 1 + j) * lda)
+                                             : 0u;
+                }
+                float v[32];
+#pragma unroll
+                for (int i = 24; i < 32; ++i) v[i] = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float a3[CO] = {0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const uint32_t u = colw[r][j + c];
+                            const float fx = __uint_as_float(u << 16), fy = __uint_as_float(u & 0xffff0000u);
+#pragma unroll
+                            for (int o = 0; o < CO; ++o) {
+                                a3[o] = fmaf(fx, wr[o][0][r * 3 + c], a3[o]);
+                                a3[o] = fmaf(fy, wr[o][1][r * 3 + c], a3[o]);
+                            }
+                        }
+#pragma unroll
+                    for (int o = 0; o < CO; ++o) v[o * 8 + j] = a3[o];
+                }
+                // transpose-reduce: after the five steps lane L holds the warp total of v[L]
+#pragma unroll
+                for (int sft = 16; sft >= 1; sft >>= 1) {
+                    const bool up = (lane & sft) != 0;
+#pragma unroll
+                    for (int i = 0; i < sft; ++i) {
+                        const float keep = up ? v[i + sft] : v[i];
+                        const float send = up ? v[i] : v[i + sft];
+                        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+                    }
+                }
+                if (lane < 24) srow[(lane >> 3) * W + x0 + (lane & 7)] += v[0];
+            }
+            __syncwarp();
+        }
+        // the finished row: out, and optionally the loss and its gradient
+        for (int i = lane; i < CO * W; i += 32) {
+            const int o = i / W, x = i % W;
+            const size_t gi = ((size_t(b) * CO + o) * H + h) * W + x;
+            const float val = srow[i];
+            out[gi] = val;
+            if (target) {
+                const float d = val - target[gi];
+                lsum += d * d;
+                if (dout) dout[gi] = 2.f * d * inv_n * gscale;
+            }
+        }
+    }
+    if (target) {  // one atomic per block (the L2 atomic unit serialises same-address updates)
+        for (int off = 16; off; off >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
+        if (lane == 0) sloss[warp] = lsum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int i = 0; i < kSmallcWarps; ++i) t += sloss[i];
+            atomicAdd(loss, t * inv_n);
+        }
+    }
+}
+static bool conv_out_rows_ok(int Cin, int Cout, int W) {
+    static const bool use_rows = !(getenv("UB_SMALLC_ROWS") && atoi(getenv("UB_SMALLC_ROWS")) == 0);
+    return use_rows && Cout == 3 && Cin % 64 == 0 && W % 8 == 0 &&
+           (size_t(3) * Cin * 9 + size_t(kSmallcWarps) * 3 * W) * sizeof(float) <= 48 * 1024;
+}
+static void conv_out_rows_launch(const bf16* a, int lda, const float* w, const float* b, int B, int Cin, int H, int W,
+                                 float* out, const float* target, float* loss, float* dout, float inv_n, float gscale,
+                                 cudaStream_t st) {
+    const size_t smem = (size_t(3) * Cin * 9 + size_t(kSmallcWarps) * 3 * W) * sizeof(float);
+    const long long items = (long long)B * H;
+    launch_pdl(conv_out_rows_kernel, dim3(unsigned((items + kSmallcWarps - 1) / kSmallcWarps)), dim3(kSmallcWarps * 32),
+               smem, st, a, lda, w, b, Cin, B, H, W, out, target, loss, dout, inv_n, gscale);
+}
+
 static void conv_out_launch(const bf16* a, int lda, const float* w, const float* b, int B, int Cin, int Cout, int H,
                             int W, float* out, int flip, cudaStream_t st) {
+    if (!flip && conv_out_rows_ok(Cin, Cout, W) && (lda % 2) == 0) {
+        conv_out_rows_launch(a, lda, w, b, B, Cin, H, W, out, nullptr, nullptr, nullptr, 0.f, 0.f, st);
+        return;
+    }
     const size_t smem = size_t(9) * Cin * 4 * sizeof(float);
     if (W % 2 == 0) {
         const size_t npairs = size_t(B) * H * (W / 2);
@@ -1021,11 +1238,25 @@ __global__ void mse_kernel(const float* __restrict__ out, const float* __restric
         if (threadIdx.x == 0) atomicAdd(loss, s * inv_n);
     }
 }
+// output conv + MSE loss + dL/dout in one launch when the row kernel applies, else the two separate launches
+void conv_out_fwd_mse(const bf16* a, int lda, const float* w, const float* b, int B, int Cin, int Cout, int H, int W,
+                      float* out, const float* target, float* loss, float* dout, float grad_scale, cudaStream_t st);
 void mse_fwd_bwd(const float* out, const float* y, size_t N, float* loss, float* dout, float grad_scale,
                  cudaStream_t st) {
     size_t nblk = (N + 255) / 256;
     if (nblk > size_t(kSMs) * 4) nblk = size_t(kSMs) * 4;
     launch_pdl(mse_kernel, dim3(unsigned(nblk)), dim3(256), 0, st, out, y, N, loss, dout, 1.f / float(N), grad_scale);
+}
+
+void conv_out_fwd_mse(const bf16* a, int lda, const float* w, const float* b, int B, int Cin, int Cout, int H, int W,
+                      float* out, const float* target, float* loss, float* dout, float grad_scale, cudaStream_t st) {
+    const size_t N = size_t(B) * Cout * H * W;
+    if (conv_out_rows_ok(Cin, Cout, W) && (lda % 2) == 0) {
+        conv_out_rows_launch(a, lda, w, b, B, Cin, H, W, out, target, loss, dout, 1.f / float(N), grad_scale, st);
+        return;
+    }
+    conv_out_fwd(a, lda, w, b, B, Cin, Cout, H, W, out, st);
+    mse_fwd_bwd(out, target, N, loss, dout, grad_scale, st);
 }
 
 }  // namespace ub

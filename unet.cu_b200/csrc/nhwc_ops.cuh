@@ -66,6 +66,8 @@ void conv_out_wgrad(const bf16* a, int lda, const float* dout, int B, int Cin, i
                     float* db, float* scratch, size_t scratch_floats, cudaStream_t st);
 
 // ---- loss (replaces mse_forward/backward, train_unet.cu:2981-3030): loss += mean((out-y)^2); dout = 2(out-y)/N
+void conv_out_fwd_mse(const bf16* a, int lda, const float* w, const float* b, int B, int Cin, int Cout, int H, int W,
+                      float* out, const float* target, float* loss, float* dout, float grad_scale, cudaStream_t st);
 void mse_fwd_bwd(const float* out, const float* y, size_t N, float* loss, float* dout, float grad_scale,
                  cudaStream_t st);
 

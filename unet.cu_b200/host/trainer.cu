@@ -756,9 +756,8 @@ int Builder::build() {
         const int Cin = h.C, Co = c.C_out, Hh = h.H, Ww = h.W;
         const size_t N = size_t(B) * c.C_out * h.H * h.W;
         F([=](cudaStream_t st) {
-            conv_out_fwd(ao.p, ao.ld, w, b, Bn, Cin, Co, Hh, Ww, Tt->out, st);
-            mse_fwd_bwd(Tt->out, Tt->noise, N, Tt->loss, Tt->dout, 1.f, st);
-        }, 2);
+            conv_out_fwd_mse(ao.p, ao.ld, w, b, Bn, Cin, Co, Hh, Ww, Tt->out, Tt->noise, Tt->loss, Tt->dout, 1.f, st);
+        }, 1);
         nd.out = View{};
         nd.bwd = [=](View) -> View {
             View dao = act(Cin, Hh, Ww), dh = act(Cin, Hh, Ww);
