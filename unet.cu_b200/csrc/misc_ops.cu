@@ -330,7 +330,42 @@ __global__ void small_linear_fwd_kernel(const SmallLinear* __restrict__ table, i
     for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
     if (lane == 0) e.out[size_t(n) * e.OC + o] = s + e.b[o];
 }
-void small_linear_fwd(const SmallLinear* table_dev, int n_entries, int N, int max_oc, cudaStream_t st) {
+// Lane = batch row, warp = four output features: the four weight rows are warp-uniform (broadcast) 16-byte loads and
+// are read once for 32 batch rows; the activations (N x C fp32, a few KiB) stay in L1.  The warp-per-(row, output)
+// kernel above needs N * OC warps per entry -- 22 528 blocks for the 22 embedding projections of a step, i.e. ~19 waves
+// of launch overhead for 30 MFLOP; this one is a single wave of 22 x 8 blocks.  C % 4 == 0, OC % 4 == 0.
+__global__ void __launch_bounds__(256) small_linear_fwd_rows_kernel(const SmallLinear* __restrict__ table, int N) {
+    pdl_entry();
+    const SmallLinear e = table[blockIdx.y];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int o = (blockIdx.x * 8 + warp) * 4;
+    const int n = blockIdx.z * 32 + lane;
+    if (o >= e.OC) return;
+    const float4* xr = reinterpret_cast<const float4*>(e.inp + size_t(n < N ? n : N - 1) * e.C);
+    const float4* w0 = reinterpret_cast<const float4*>(e.w + size_t(o) * e.C);
+    const int C4 = e.C / 4;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < C4; ++k) {
+        float4 x = __ldg(xr + k);
+        if (e.silu_in) x.x = silu_f(x.x), x.y = silu_f(x.y), x.z = silu_f(x.z), x.w = silu_f(x.w);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float4 wv = __ldg(w0 + size_t(u) * C4 + k);
+            s[u] = fmaf(x.x, wv.x, s[u]), s[u] = fmaf(x.y, wv.y, s[u]);
+            s[u] = fmaf(x.z, wv.z, s[u]), s[u] = fmaf(x.w, wv.w, s[u]);
+        }
+    }
+    if (n < N)
+        *reinterpret_cast<float4*>(e.out + size_t(n) * e.OC + o) =
+            make_float4(s[0] + e.b[o], s[1] + e.b[o + 1], s[2] + e.b[o + 2], s[3] + e.b[o + 3]);
+}
+// rows_ok: every entry has C % 4 == 0 and OC % 4 == 0 (the caller knows its table)
+void small_linear_fwd(const SmallLinear* table_dev, int n_entries, int N, int max_oc, cudaStream_t st, bool rows_ok) {
+    if (rows_ok) {
+        launch_pdl(small_linear_fwd_rows_kernel, dim3((max_oc / 4 + 7) / 8, n_entries, (N + 31) / 32), dim3(256), 0, st,
+                   table_dev, N);
+        return;
+    }
     const int warps = N * max_oc;
     launch_pdl(small_linear_fwd_kernel, dim3(dim3((warps * 32 + 255) / 256, n_entries)), dim3(256), 0, st, table_dev, N);
 }
@@ -408,6 +443,74 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, in
     out[size_t(b) * 2 * half + j] = cosf(a);
     out[size_t(b) * 2 * half + half + j] = sinf(a);
 }
+// The whole time-embedding MLP in one launch (dev/unet.py:176-180, 327-345): sinusoidal embedding -> linear (Cm ->
+// Cemb) -> SiLU -> linear (Cemb -> Cemb) -> SiLU, keeping every intermediate the backward pass reads (sin_emb, h0 =
+// first pre-activation, emb = second pre-activation, semb = silu(emb)).  Block (b, y) recomputes the first layer of
+// batch row b (it is tiny) and produces quarter y of the second layer's outputs.  A warp works on four outputs at a
+// time so that their weight rows -- cold in HBM at the start of a step -- are in flight together (one output at a
+// time, 16 per warp, measured slower than the four separate launches it replaces).  Same arithmetic and summation
+// order per output as timestep_embedding_kernel + small_linear_fwd_kernel + silu_f32_kernel.
+constexpr int kTimeMlpSplit = 4;
+__device__ __forceinline__ void dot4_rows(const float* __restrict__ x, const float* __restrict__ w, int C, int lane,
+                                          float (&s)[4]) {
+    s[0] = s[1] = s[2] = s[3] = 0.f;
+    for (int k = lane; k < C; k += 32) {
+        const float xv = x[k];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) s[u] += xv * w[size_t(u) * C + k];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        for (int off = 16; off; off >>= 1) s[u] += __shfl_xor_sync(0xffffffffu, s[u], off);
+}
+__global__ void __launch_bounds__(512) time_mlp_fwd_kernel(const float* __restrict__ t, int half, float log_mp,
+                                                           const float* __restrict__ w0, const float* __restrict__ b0,
+                                                           const float* __restrict__ w1, const float* __restrict__ b1,
+                                                           float* __restrict__ sin_emb, float* __restrict__ h0,
+                                                           float* __restrict__ emb, float* __restrict__ semb, int Cm,
+                                                           int Cemb) {
+    pdl_entry();
+    extern __shared__ float sm[];
+    float* s_in = sm;        // [Cm]
+    float* s_h = sm + Cm;    // [Cemb] silu(h0)
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const bool writer = blockIdx.y == 0;
+    for (int j = threadIdx.x; j < half; j += blockDim.x) {
+        const float f = expf(-log_mp * float(j) / float(half));
+        const float a = t[b] * f;
+        const float c = cosf(a), sn = sinf(a);
+        s_in[j] = c, s_in[half + j] = sn;
+        if (writer) sin_emb[size_t(b) * Cm + j] = c, sin_emb[size_t(b) * Cm + half + j] = sn;
+    }
+    __syncthreads();
+    for (int o = warp * 4; o < Cemb; o += nwarps * 4) {  // Cemb % 4 == 0
+        float s[4];
+        dot4_rows(s_in, w0 + size_t(o) * Cm, Cm, lane, s);
+        if (lane < 4) {
+            const float v = s[lane] + b0[o + lane];
+            if (writer) h0[size_t(b) * Cemb + o + lane] = v;
+            s_h[o + lane] = silu_f(v);
+        }
+    }
+    __syncthreads();
+    const int per = Cemb / kTimeMlpSplit;  // Cemb % 16 == 0
+    for (int o = blockIdx.y * per + warp * 4; o < (blockIdx.y + 1) * per; o += nwarps * 4) {
+        float s[4];
+        dot4_rows(s_h, w1 + size_t(o) * Cemb, Cemb, lane, s);
+        if (lane < 4) {
+            const float v = s[lane] + b1[o + lane];
+            emb[size_t(b) * Cemb + o + lane] = v;
+            semb[size_t(b) * Cemb + o + lane] = silu_f(v);
+        }
+    }
+}
+void time_mlp_fwd(const float* t, int B, int Cm, int Cemb, int max_period, const float* w0, const float* b0,
+                  const float* w1, const float* b1, float* sin_emb, float* h0, float* emb, float* semb,
+                  cudaStream_t st) {
+    launch_pdl(time_mlp_fwd_kernel, dim3(B, kTimeMlpSplit), dim3(512), size_t(Cm + Cemb) * sizeof(float), st, t, Cm / 2,
+               logf(float(max_period)), w0, b0, w1, b1, sin_emb, h0, emb, semb, Cm, Cemb);
+}
+
 void timestep_embedding(const float* t, int B, int dim, int max_period, float* out, cudaStream_t st) {
     const int half = dim / 2;
     launch_pdl(timestep_embedding_kernel, dim3((B * half + 127) / 128), dim3(128), 0, st, t, B, half, logf(float(max_period)), out);

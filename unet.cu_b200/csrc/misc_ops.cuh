@@ -33,12 +33,16 @@ struct SmallLinear {
     float* db2;        // optional second copy of db (conv1 bias grad == l_emb bias grad), may be null
     float* dinp;       // (N, C)    += gradient w.r.t. the (activated) input, atomically; may be null
 };
-void small_linear_fwd(const SmallLinear* table_dev, int n_entries, int N, int max_oc, cudaStream_t st);
+void small_linear_fwd(const SmallLinear* table_dev, int n_entries, int N, int max_oc, cudaStream_t st,
+                      bool rows_ok = false);
 void small_linear_bwd(const SmallLinear* table_dev, int n_entries, int N, int max_oc, int max_c, cudaStream_t st);
 void silu_f32(const float* x, float* out, size_t n, cudaStream_t st);
 // g[i] = dact[i] * silu'(pre[i])
 void dsilu_mul(const float* dact, const float* pre, float* g, size_t n, cudaStream_t st);
 // timestep embedding (replaces get_timestep_embeddings, train_unet.cu:3258-3313): out[b][j]=cos(t f_j), [half+j]=sin
+void time_mlp_fwd(const float* t, int B, int Cm, int Cemb, int max_period, const float* w0, const float* b0,
+                  const float* w1, const float* b1, float* sin_emb, float* h0, float* emb, float* semb,
+                  cudaStream_t st);
 void timestep_embedding(const float* t, int B, int dim, int max_period, float* out, cudaStream_t st);
 
 // ---- diffusion: t ~ U{0..T-1}, eps ~ N(0,1) (Philox4x32-10, counter = element index, key = (seed, step)),

@@ -910,14 +910,131 @@ __global__ void smallc_wgrad_reduce_kernel(const float* __restrict__ partial, in
     else
         dw[(size_t(sidx) * Cb + cb) * 9 + (8 - tap)] = s;
 }
+// Row-per-warp weight gradient of the 3-channel convs (Cs == 3, Cb % 64 == 0, W % 4 == 0), the mirror image of
+// smallc_conv_rows_kernel: lane l accumulates the 2 x 27 weight gradients (+ 2 bias sums) of big channels 2l, 2l+1 in
+// registers over whole image rows -- per 4 pixels: 4 coalesced 128-byte rows of dy, 18 broadcast LDS of the window,
+// 216 FMAs -- the 8 warps of a block are added in shared memory and every block adds its totals to dw / db with
+// 8-byte vector REDs (dw, db are zero at the start of a step like every accumulated gradient).
+// mode 0 (conv_in):  dw[cb][s][tap] ; db[cb]          mode 1 (conv_out): dw[s][cb][8 - tap] ; no db
+__global__ void __launch_bounds__(kSmallcWarps * 32) smallc_wgrad_rows_kernel(
+    const float* __restrict__ xs, const bf16* __restrict__ yb, int ldy, int Cb, int B, int H, int W, int mode,
+    float* __restrict__ dw, float* __restrict__ db) {
+    pdl_entry();
+    constexpr int CS = 3;
+    extern __shared__ float sm[];
+    const int WP = W + 4;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* swin = sm + warp * (9 * WP);
+    float* sred = sm + kSmallcWarps * 9 * WP;  // [warps][56][32]
+    const int cg = blockIdx.y;
+    float g0[27], g1[27], bs0 = 0.f, bs1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) g0[k] = g1[k] = 0.f;
+    for (int row = blockIdx.x * kSmallcWarps + warp; row < B * H; row += gridDim.x * kSmallcWarps) {
+        const int b = row / H, h = row % H;
+        __syncwarp();
+        for (int i = lane; i < 9 * WP; i += 32) {
+            const int col = i % WP, rs = i / WP;
+            const int r = rs / CS, s_ = rs % CS;
+            const int hh = h + r - 1, ww = col - 1;
+            swin[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xs + ((size_t(b) * CS + s_) * H + hh) * W + ww) : 0.f;
+        }
+        __syncwarp();
+        const bf16* yrow = yb + (size_t(row) * W) * ldy + cg * 64 + 2 * lane;
+        for (int x16 = 0; x16 < W; x16 += 16) {
+            // dy of 16 pixels is fetched at once (16 independent loads in flight per lane: with one block per SM the
+            // loop was paced by one L2 round trip per 4 pixels)
+            uint32_t raw[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                raw[j] = x16 + j < W ? *reinterpret_cast<const uint32_t*>(yrow + size_t(x16 + j) * ldy) : 0u;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int x0 = x16 + 4 * g;
+                if (x0 < W) {  // (W % 4 == 0)
+                    float d0[4], d1[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t u = raw[4 * g + j];
+                        d0[j] = __uint_as_float(u << 16), d1[j] = __uint_as_float(u & 0xffff0000u);
+                        bs0 += d0[j], bs1 += d1[j];
+                    }
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int s_ = 0; s_ < CS; ++s_) {
+                            const float* wp_ = swin + (r * CS + s_) * WP + x0;
+                            const float4 u = *reinterpret_cast<const float4*>(wp_);
+                            const float2 t = *reinterpret_cast<const float2*>(wp_ + 4);
+                            const float win[6] = {u.x, u.y, u.z, u.w, t.x, t.y};
+#pragma unroll
+                            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    g0[s_ * 9 + r * 3 + c] = fmaf(win[j + c], d0[j], g0[s_ * 9 + r * 3 + c]);
+                                    g1[s_ * 9 + r * 3 + c] = fmaf(win[j + c], d1[j], g1[s_ * 9 + r * 3 + c]);
+                                }
+                        }
+                }
+            }
+        }
+    }
+    // park the warp's 56 values so that value index j of lane l is element j of the lane's contiguous output range:
+    // mode 0: [cc][s][tap] (27 per channel); mode 1: per s, [cc][8 - tap] (18 per s); then the two bias sums
+    float* mine = sred + size_t(warp) * 56 * 32 + lane;
+#pragma unroll
+    for (int s_ = 0; s_ < CS; ++s_)
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int j0 = mode == 0 ? s_ * 9 + tap : s_ * 18 + (8 - tap);
+            const int j1 = mode == 0 ? 27 + s_ * 9 + tap : s_ * 18 + 9 + (8 - tap);
+            mine[j0 * 32] = g0[s_ * 9 + tap];
+            mine[j1 * 32] = g1[s_ * 9 + tap];
+        }
+    mine[54 * 32] = bs0, mine[55 * 32] = bs1;
+    __syncthreads();
+    for (int i = warp; i < 28; i += kSmallcWarps) {  // pair i = values 2i, 2i+1 of every lane
+        float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+        for (int w_ = 0; w_ < kSmallcWarps; ++w_) {
+            t0 += sred[(size_t(w_) * 56 + 2 * i) * 32 + lane];
+            t1 += sred[(size_t(w_) * 56 + 2 * i + 1) * 32 + lane];
+        }
+        float* dst;
+        if (i == 27) {
+            if (mode != 0 || !db) continue;
+            dst = db + cg * 64 + 2 * lane;
+        } else if (mode == 0) {
+            dst = dw + (size_t(cg) * 64 + 2 * lane) * 27 + 2 * i;
+        } else {
+            const int s_ = (2 * i) / 18, q = (2 * i) % 18;
+            dst = dw + (size_t(s_) * Cb + cg * 64 + 2 * lane) * 9 + q;
+        }
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(t0), "f"(t1) : "memory");
+    }
+}
+
 void nhwc_ops_init() {
     static bool done = false;
     if (done) return;
     cudaFuncSetAttribute(smallc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(smallc_wgrad_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     done = true;
 }
 static void smallc_wgrad(const float* xs, const bf16* yb, int ldy, int B, int Cs, int Cb, int H, int W, int mode,
                          float* dw, float* db, float* scratch, size_t scratch_floats, cudaStream_t st) {
+    static const bool use_rows = !(getenv("UB_SMALLC_ROWS") && atoi(getenv("UB_SMALLC_ROWS")) == 0);
+    if (use_rows && Cs == 3 && Cb % 64 == 0 && W % 4 == 0 && (ldy % 2) == 0) {
+        const size_t smem_r = (size_t(kSmallcWarps) * 9 * (W + 4) + size_t(kSmallcWarps) * 56 * 32) * sizeof(float);
+        if (smem_r <= 100 * 1024) {
+            nhwc_ops_init();
+            int gx = (B * H + kSmallcWarps - 1) / kSmallcWarps;
+            if (gx > 2 * kSMs) gx = 2 * kSMs;
+            launch_pdl(smallc_wgrad_rows_kernel, dim3(unsigned(gx), unsigned(Cb / 64)), dim3(kSmallcWarps * 32), smem_r, st,
+                       xs, yb, ldy, Cb, B, H, W, mode, dw, db);
+            return;
+        }
+    }
     const int NT = Cs * 9;
     size_t nblk = 2 * kSMs;
     const size_t per = size_t(Cb) * (NT + 1);

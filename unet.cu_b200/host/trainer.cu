@@ -423,6 +423,23 @@ struct Builder {
         emb_lo = 1 << 30, emb_hi = -1;
     }
 
+    // Time-MLP backward (needs the complete d_embact, i.e. every embedding projection's backward).  Emitted on the
+    // weight-gradient branch as soon as the first ResBlock has produced its embedding gradient, so that it runs under
+    // the last dgrad convs instead of after them (it used to be 80 us of the step's serial tail).
+    bool time_mlp_bwd_done = false;
+    void time_mlp_bwd() {
+        if (time_mlp_bwd_done) return;
+        time_mlp_bwd_done = true;
+        UbTrainer* Tt = T;
+        const int Bn = B, Cm = c.C_model, Cemb = 4 * c.C_model;
+        Bk([=](cudaStream_t st) {
+            dsilu_mul(Tt->d_embact, Tt->emb, Tt->demb, size_t(Bn) * Cemb, st);
+            small_linear_bwd(Tt->temb_table + 1, 1, Bn, Cemb, Cemb, st);
+            dsilu_mul(Tt->d_h0act, Tt->h0, Tt->dh0, size_t(Bn) * Cemb, st);
+            small_linear_bwd(Tt->temb_table, 1, Bn, Cemb, Cm, st);
+        }, 6, UB_KIND_SMALL, 0, 0, 1);
+    }
+
     // ResBlock (dev/resblock.py:107-160, train_unet.cu:2213-2384)
     View resblock(View x, int Cout) {
         Node nd;
@@ -496,6 +513,10 @@ struct Builder {
             // GN2 + SiLU backward; per-image column sums of dh1 feed the embedding-projection backward
             gn_bwd(g2, h1, da2, 1, View{}, dh1, d_embproj, true);
             emb_lo = blk < emb_lo ? blk : emb_lo, emb_hi = blk + 1 > emb_hi ? blk + 1 : emb_hi;  // batched, see emb_flush
+            if (blk == 0) {  // the last embedding gradient of the step: finish the embedding path on the branch now
+                emb_flush();
+                time_mlp_bwd();
+            }
             wgrad_op(dh1, a1, C, Cout, 9, G(w1));
             {
                 ConvEpilogue ep;
@@ -635,12 +656,11 @@ int Builder::build() {
     {
         const int mp = c.max_period;
         F([=](cudaStream_t st) {
-            timestep_embedding(Tt->tsteps, Bn, Cm, mp, Tt->sin_emb, st);
-            small_linear_fwd(Tt->temb_table, 1, Bn, Cemb, st);
-            small_linear_fwd(Tt->temb_table + 1, 1, Bn, Cemb, st);
-            silu_f32(Tt->emb, Tt->semb, size_t(Bn) * Cemb, st);  // shared input of all embedding projections
-            small_linear_fwd(Tt->emb_table, int(Tt->h_emb.size()), Bn, Tt->emb_max_oc, st);
-        }, 5, UB_KIND_SMALL, 0, 0, 1);  // beside the input conv and the first GroupNorm
+            const SmallLinear &e0 = Tt->h_temb[0], &e1 = Tt->h_temb[1];
+            time_mlp_fwd(Tt->tsteps, Bn, Cm, Cemb, mp, e0.w, e0.b, e1.w, e1.b, Tt->sin_emb, Tt->h0, Tt->emb, Tt->semb,
+                         st);  // (semb = silu(emb) is the shared input of all embedding projections)
+            small_linear_fwd(Tt->emb_table, int(Tt->h_emb.size()), Bn, Tt->emb_max_oc, st, true);  // (Cout % 16 == 0)
+        }, 2, UB_KIND_SMALL, 0, 0, 1);  // beside the input conv and the first GroupNorm
         fwd_side_pending = true;
     }
     const size_t time_mlp_end = poff;
@@ -833,6 +853,10 @@ int Builder::build() {
                3 * act_bytes(C, nd.out.H, nd.out.W));
             g = sum;
         }
+        if (i == 0) {  // only the 3-channel input conv is left: finalise the tcgen05 weight gradients before it
+            emb_flush();
+            fin_flush();
+        }
         g = nd.bwd(g);
         while (cut_i < cuts.size() && nd.param_begin <= cuts[cut_i] && nd.param_begin > time_mlp_end) {
             // (all of this is on the weight-gradient branch, which has seen everything the main stream did so far:
@@ -847,13 +871,11 @@ int Builder::build() {
     emb_flush();
     fin_flush();
     join_side();
-    // time MLP backward (needs the complete d_embact), then the last bucket
-    Bk([=](cudaStream_t st) {
-        dsilu_mul(Tt->d_embact, Tt->emb, Tt->demb, size_t(Bn) * Cemb, st);
-        small_linear_bwd(Tt->temb_table + 1, 1, Bn, Cemb, Cemb, st);
-        dsilu_mul(Tt->d_h0act, Tt->h0, Tt->dh0, size_t(Bn) * Cemb, st);
-        small_linear_bwd(Tt->temb_table, 1, Bn, Cemb, Cm, st);
-    }, 6);
+    // (a model without ResBlocks: the time-MLP backward has not been emitted yet), then the last bucket
+    if (!time_mlp_bwd_done) {
+        time_mlp_bwd();
+        join_side();
+    }
     flush_bucket(0, flushed_hi, true);
     Bk([=](cudaStream_t st) {  // join the communication stream
         if (Tt->world <= 1 || Tt->comm_off) return;
