@@ -234,7 +234,7 @@ def run_cuda(args):
         conv = prof["conv_igemm"]
         conv_tf = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
         roofline = {
-            "bound": "tensor", "kernel": "igemm_conv_kernel + igemm_rows_kernel (3x3/1x1 conv fprop+dgrad, qkv/proj GEMMs; tcgen05)",
+            "bound": "tensor", "kernel": "igemm_conv_kernel + igemm_conv2_kernel + igemm_rows_kernel (3x3/1x1 conv fprop+dgrad, qkv/proj GEMMs; tcgen05)",
             "achieved": conv_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
             "frac": conv_tf / pk["tf_sustained"], "traffic": conv_traffic(),
             "traffic_note": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
@@ -346,7 +346,7 @@ def conv_traffic():
     try:
         with open(p) as f:
             d = json.load(f)
-        ks = [v for k, v in d.items() if k in ("igemm_conv_kernel", "igemm_rows_kernel")]
+        ks = [v for k, v in d.items() if k in ("igemm_conv_kernel", "igemm_conv2_kernel", "igemm_rows_kernel")]
         n = sum(v["launches"] for v in ks)
         byts = sum(v["launches"] * (v["dram_read_bytes_per_launch"] + v["dram_write_bytes_per_launch"]) for v in ks)
         return byts / n if n else None
