@@ -84,9 +84,10 @@ __device__ __forceinline__ void epi_chunk(const EpiOut& e, uint32_t taddr, const
     tmem_ld_wait();
     if (!valid) return;
     float f[NC];
+    const uint32_t comb_s = smem_u32(comb);
 #pragma unroll
     for (int j = 0; j < NC; j += 4) {
-        const float4 c = *reinterpret_cast<const float4*>(comb + j);
+        const float4 c = lds_v4(comb_s + 4u * j);
         f[j] = __uint_as_float(v[j]) + c.x, f[j + 1] = __uint_as_float(v[j + 1]) + c.y;
         f[j + 2] = __uint_as_float(v[j + 2]) + c.z, f[j + 3] = __uint_as_float(v[j + 3]) + c.w;
     }
@@ -150,32 +151,42 @@ __device__ __forceinline__ void epi_chunk_gn(const EpiOut& e, uint32_t taddr, co
     if (n_next >= 0) epi_side_load(e, valid, pix, n_next, xn);
     tmem_ld_wait();
     float f[16], q[16];
+    const uint32_t comb_s = smem_u32(comb);
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
-        const float4 c = *reinterpret_cast<const float4*>(comb + j);
+        const float4 c = lds_v4(comb_s + 4u * j);
         f[j] = __uint_as_float(v[j]) + c.x, f[j + 1] = __uint_as_float(v[j + 1]) + c.y;
         f[j + 2] = __uint_as_float(v[j + 2]) + c.z, f[j + 3] = __uint_as_float(v[j + 3]) + c.w;
     }
     if (valid) {
         if (e.gx) {
             // f = dL/d(act(gn(x)))  ->  dz = f * act'(z);  q = dz * xhat
+            const uint32_t gc_s = smem_u32(gconst), gstride = 4u * uint32_t(cstride);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 float x[8];
                 unpack_bf16x8(xr[j], x);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int c = j * 8 + i;
-                    float dz = f[c];
-                    if (e.gsilu) {
-                        const float z = fmaf(x[i], gconst[c], gconst[cstride + c]);
-                        const float sg = epi_sigmoid(z);
-                        dz *= sg * fmaf(z, 1.f - sg, 1.f);
+                for (int h4 = 0; h4 < 2; ++h4) {  // four channels at a time: one 16-byte read per constant row
+                    const uint32_t ga = gc_s + 4u * uint32_t(j * 8 + h4 * 4);
+                    const float4 ca = lds_v4(ga), cb = lds_v4(ga + gstride);
+                    const float4 cr = lds_v4(ga + 2u * gstride), cm = lds_v4(ga + 3u * gstride);
+                    const float a4[4] = {ca.x, ca.y, ca.z, ca.w}, b4[4] = {cb.x, cb.y, cb.z, cb.w};
+                    const float r4[4] = {cr.x, cr.y, cr.z, cr.w}, m4[4] = {cm.x, cm.y, cm.z, cm.w};
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; ++i4) {
+                        const int i = h4 * 4 + i4, c = j * 8 + i;
+                        float dz = f[c];
+                        if (e.gsilu) {
+                            const float z = fmaf(x[i], a4[i4], b4[i4]);
+                            const float sg = epi_sigmoid(z);
+                            dz *= sg * fmaf(z, 1.f - sg, 1.f);
+                        }
+                        // the stored (bf16) dz is what gn_bwd_apply will read: sum exactly that
+                        dz = __bfloat162float(__float2bfloat16(dz));
+                        f[c] = dz;
+                        q[c] = dz * fmaf(x[i], r4[i4], -m4[i4]);
                     }
-                    // the stored (bf16) dz is what gn_bwd_apply will read: sum exactly that
-                    dz = __bfloat162float(__float2bfloat16(dz));
-                    f[c] = dz;
-                    q[c] = dz * fmaf(x[i], gconst[2 * cstride + c], -gconst[3 * cstride + c]);
                 }
             }
         } else {
@@ -208,23 +219,25 @@ __device__ __forceinline__ void epi_chunk_gn(const EpiOut& e, uint32_t taddr, co
 #pragma unroll
         for (int j = 0; j < 16; ++j) f[j] = 0.f, q[j] = 0.f;
     }
-    float4* row = reinterpret_cast<float4*>(tr + lane * 36);
+    const uint32_t tr_s = smem_u32(tr);
+    const uint32_t row_s = tr_s + uint32_t(lane) * 144u;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        row[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-        row[4 + j] = make_float4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
+        sts_v4(row_s + 16u * j, f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        sts_v4(row_s + 64u + 16u * j, q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
     }
     __syncwarp();
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    const uint32_t col_s = tr_s + 4u * uint32_t(lane);
 #pragma unroll
     for (int r = 0; r < 32; r += 4) {
-        s0 += tr[r * 36 + lane], s1 += tr[(r + 1) * 36 + lane];
-        s2 += tr[(r + 2) * 36 + lane], s3 += tr[(r + 3) * 36 + lane];
+        s0 += lds_f32(col_s + 144u * r), s1 += lds_f32(col_s + 144u * (r + 1));
+        s2 += lds_f32(col_s + 144u * (r + 2)), s3 += lds_f32(col_s + 144u * (r + 3));
     }
     __syncwarp();
     // lane j < 16 holds the warp's total of f column j, lane 16 + j that of q column j: park them; epi_flush_stats
     // adds the warps up and issues one vector RED per (tile, channel) (the L2 atomic unit serialises per address)
-    red[2 * (lane & 15) + (lane >> 4)] = (s0 + s1) + (s2 + s3);
+    sts_f32(smem_u32(red) + 4u * uint32_t(2 * (lane & 15) + (lane >> 4)), (s0 + s1) + (s2 + s3));
     xr[0] = xn[0], xr[1] = xn[1];
 }
 
