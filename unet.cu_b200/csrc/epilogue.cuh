@@ -13,6 +13,9 @@
 // Both reduce over the 32 pixels of a warp through a small smem transpose and add the warp totals of the CTA's
 // epilogue warps in shared memory; one red.global.add.v2.f32 per (tile, channel) follows.
 #pragma once
+#ifndef UB_EPI_SHUFFLE_REDUCE
+#define UB_EPI_SHUFFLE_REDUCE 1
+#endif
 #include "igemm.cuh"
 #include "ptx.cuh"
 
@@ -219,6 +222,26 @@ __device__ __forceinline__ void epi_chunk_gn(const EpiOut& e, uint32_t taddr, co
 #pragma unroll
         for (int j = 0; j < 16; ++j) f[j] = 0.f, q[j] = 0.f;
     }
+#if UB_EPI_SHUFFLE_REDUCE
+    // Column sums over the warp's 32 pixels by a transpose-reduce butterfly: 31 shuffles move half as many bytes
+    // through the SM's shuffle/shared-memory crossbar as the 8 STS.128 + 32 LDS of the shared-memory transpose
+    // (64 wavefronts per chunk and warp; with 16 epilogue warps per SM that pipe is what bounds the hooked epilogue).
+    float cs[32];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) cs[j] = f[j], cs[16 + j] = q[j];
+#pragma unroll
+    for (int sft = 16; sft >= 1; sft >>= 1) {
+        const bool up = (lane & sft) != 0;
+#pragma unroll
+        for (int i = 0; i < sft; ++i) {
+            const float keep = up ? cs[i + sft] : cs[i];
+            const float send = up ? cs[i] : cs[i + sft];
+            cs[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+        }
+    }
+    // lane L holds the warp's total of cs[L]: f column L for L < 16, q column L - 16 above
+    sts_f32(smem_u32(red) + 4u * uint32_t(2 * (lane & 15) + (lane >> 4)), cs[0]);
+#else
     const uint32_t tr_s = smem_u32(tr);
     const uint32_t row_s = tr_s + uint32_t(lane) * 144u;
 #pragma unroll
@@ -238,6 +261,7 @@ __device__ __forceinline__ void epi_chunk_gn(const EpiOut& e, uint32_t taddr, co
     // lane j < 16 holds the warp's total of f column j, lane 16 + j that of q column j: park them; epi_flush_stats
     // adds the warps up and issues one vector RED per (tile, channel) (the L2 atomic unit serialises per address)
     sts_f32(smem_u32(red) + 4u * uint32_t(2 * (lane & 15) + (lane >> 4)), (s0 + s1) + (s2 + s3));
+#endif
     xr[0] = xn[0], xr[1] = xn[1];
 }
 
