@@ -300,11 +300,15 @@ struct Builder {
 
     void conv_op(bool fwd, std::vector<ConvSegDesc> segs, int H, int W, int Cout, ConvEpilogue ep) {
         if (!real()) return;
-        // measured (profiles/r01_ops_rows_vs_basic.txt): the persistent kernel wins where the basic one is bound by its
-        // per-128-pixel fixed costs, i.e. the 64-pixel-wide levels with <= 64 output channels; elsewhere the basic
-        // kernel's larger N tile (up to 256) reads less shared memory per MMA.  UB_ROWS=0 / 2 forces never / always.
+        // measured per layer (profiles/r01_ops_rows_vs_basic.txt, r01_ops_rows_vs_basic_final.txt): the persistent
+        // kernel wins (a) where the basic one is bound by its per-128-pixel fixed costs -- the 64-pixel-wide levels with
+        // <= 64 output channels -- and (b) at wide levels with >= 192 output channels, where the basic kernel's N tile
+        // is 160-192 columns: one CTA per SM, i.e. a single MMA issue stream, against the row-tile kernel's two.
+        // Elsewhere (N <= 128: two CTAs per SM; 8x8 / 16x16: too few row tiles) the basic kernel is faster.
+        // UB_ROWS=0 / 2 forces never / always.
         static const int rows_mode = getenv("UB_ROWS") ? atoi(getenv("UB_ROWS")) : 1;
-        const bool no_rows = rows_mode == 0 || (rows_mode == 1 && !(W >= 64 && Cout <= 64));
+        const bool rows_pref = (W >= 64 && (Cout <= 64 || Cout >= 192)) || (W >= 32 && Cout >= 192 && segs[0].ntaps == 9);
+        const bool no_rows = rows_mode == 0 || (rows_mode == 1 && !rows_pref);
         double k = 0, bytes = act_bytes(Cout, H, W);
         for (auto& sg : segs) k += double(sg.ntaps) * sg.Cin, bytes += act_bytes(sg.Cin, H, W) + 2.0 * sg.ntaps * sg.Cin * Cout;
         const double flops = 2.0 * B * H * W * Cout * k;
