@@ -167,7 +167,7 @@ struct UbTrainer {
     int host_step = 0;
     // data parallel
     ncclComm_t comm = nullptr;
-    int rank = 0, world = 1, n_buckets = 4;
+    int rank = 0, world = 1, n_buckets = getenv("UB_BUCKETS") ? atoi(getenv("UB_BUCKETS")) : 8;
     bool comm_off = false;  // rank-local eager replays (profiling) must not enqueue collectives
     // Optimizer per gradient bucket: as soon as a bucket's gradients are final (and all-reduced), AdamW and the weight
     // re-pack of that parameter range run on the branch that finalised them, under the rest of backward; only the
@@ -807,6 +807,12 @@ int Builder::build() {
     {
         const int nb = T->n_buckets < 1 ? 1 : T->n_buckets;
         for (int k = nb - 1; k >= 1; --k) cuts.push_back(T->nparams * size_t(k) / nb);
+        // A last cut right above the input conv: the bucket that must wait for the very end of backward (and whose
+        // AdamW + weight re-pack are the serial tail of the step) then holds only the time MLP and the 3-channel conv.
+        static const bool tail_cut = !(getenv("UB_TAIL_CUT") && atoi(getenv("UB_TAIL_CUT")) == 0);
+        if (tail_cut && nodes.size() > 1 && nodes[1].param_begin > time_mlp_end &&
+            (cuts.empty() || nodes[1].param_begin < cuts.back()))
+            cuts.push_back(nodes[1].param_begin);
     }
     size_t flushed_hi = T->nparams;
     size_t cut_i = 0;
