@@ -253,7 +253,7 @@ class Trainer:
         check(lib().ub_trainer_sample(self._h, _ptr(x_init), t_start, t_end, _ptr(noises), seed, _ptr(out)), "sample")
         return out
 
-    def attach_dp(self, rank: int, world: int, nccl_id: bytes, n_buckets: int = 4):
+    def attach_dp(self, rank: int, world: int, nccl_id: bytes, n_buckets: int = 0):
         buf = C.create_string_buffer(nccl_id, UB_NCCL_ID_BYTES)
         check(lib().ub_trainer_attach_dp(self._h, rank, world, buf, n_buckets), "attach_dp")
 
