@@ -87,8 +87,8 @@ __device__ __forceinline__ void conv_issue_loop(const IgemmConvParams& p, int is
                                                 uint32_t tmem_base) {
     const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
     const uint32_t d = tmem_base + uint32_t(issuer * p.BN);
-    // (NACC == 2: the ring is even -- plan -- so stage s always belongs to issuer s % 2 and each issuer waits for
-    //  consecutive phases of its full barriers)
+    // (NACC > 1: the ring is a multiple of NACC -- plan -- so stage s always belongs to issuer s % NACC and each
+    //  issuer waits for consecutive phases of its full barriers)
     int stage = issuer;
     uint32_t phase = 0;
 #ifdef UB_TRACE
@@ -258,9 +258,11 @@ __device__ __forceinline__ void igemm_conv_body(const IgemmConvParams& p) {
         if (lane == 0) conv_issue_loop<NACC>(p, 0, nk, smem, full_bar, empty_bar, tmem_full_bar, tmem_base);
     } else {
         // ------------------------------------------------------------ epilogue (warps 2..9)
-        if constexpr (NACC == 2) {  // second MMA stream first; the warp reconverges before it touches the epilogue
-            if (warp == 9) {
-                if (lane == 0) conv_issue_loop<NACC>(p, 1, nk, smem, full_bar, empty_bar, tmem_full_bar, tmem_base);
+        if constexpr (NACC > 1) {  // extra MMA streams first; the warp reconverges before it touches the epilogue
+            // issuer i = 1 .. NACC-1 is lane 0 of warp 10 - i (the last epilogue warps)
+            if (warp > 10 - NACC) {
+                if (lane == 0)
+                    conv_issue_loop<NACC>(p, 10 - warp, nk, smem, full_bar, empty_bar, tmem_full_bar, tmem_base);
                 __syncwarp();
             }
         }
@@ -324,6 +326,10 @@ __global__ void __launch_bounds__(kConvThreads, 2) igemm_conv_kernel(const __gri
 }
 __global__ void __launch_bounds__(kConvThreads, 1) igemm_conv2_kernel(const __grid_constant__ IgemmConvParams p) {
     igemm_conv_body<2>(p);
+}
+// four streams: an experiment switch (UB_CONV_NACC=4), not the default -- not yet measured inside the step
+__global__ void __launch_bounds__(kConvThreads, 1) igemm_conv4_kernel(const __grid_constant__ IgemmConvParams p) {
+    igemm_conv_body<4>(p);
 }
 
 // =====================================================================================================
@@ -687,10 +693,11 @@ int igemm_conv_plan(IgemmConvParams* p, const ConvSegDesc* segs, int nseg, int B
     // columns so that a weight-gradient CTA of the side stream still finds room.
     p->nacc = 1;
     {
-        static const bool two = !(getenv("UB_CONV_NACC") && atoi(getenv("UB_CONV_NACC")) < 2);
+        static const int want = getenv("UB_CONV_NACC") ? atoi(getenv("UB_CONV_NACC")) : 2;
         int nkb = 0;
         for (int s = 0; s < nseg; ++s) nkb += segs[s].ntaps * ceil_div_i(segs[s].Cin, 64);
-        if (two && pix_tiles * (Cout / BN) <= 148 && BN % 32 == 0 && BN <= 128 && nkb >= 4) p->nacc = 2;
+        if (want >= 2 && pix_tiles * (Cout / BN) <= 148 && BN % 32 == 0 && BN <= 128 && nkb >= 4) p->nacc = 2;
+        if (want >= 4 && p->nacc == 2 && nkb >= 8) p->nacc = 4;  // (experiment: up to 512 TMEM columns)
     }
     p->tmem_cols = next_pow2(p->nacc * BN < 32 ? 32 : p->nacc * BN);
     p->a_bytes = uint32_t(64 * p->TW * p->TH * p->TB * 2);
@@ -714,6 +721,11 @@ int igemm_conv_plan(IgemmConvParams* p, const ConvSegDesc* segs, int nseg, int B
             stages += 1;
         else
             stages -= 1;
+    }
+    if (p->nacc == 4) {  // ring = 4 or 8 stages (a multiple of the issuer count)
+        stages = (size_t(8) * p->stage_bytes + tail <= 200u * 1024u) ? 8 : 4;
+        if (size_t(stages) * p->stage_bytes + tail > 227u * 1024u) p->nacc = 2, stages = 4;
+        p->tmem_cols = next_pow2(p->nacc * BN < 32 ? 32 : p->nacc * BN);
     }
     p->stages = stages;
     for (int s = 0; s < nseg; ++s) {
@@ -774,6 +786,7 @@ void igemm_init() {
     if (done) return;
     cudaFuncSetAttribute(igemm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(227 * 1024));
     cudaFuncSetAttribute(igemm_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(227 * 1024));
+    cudaFuncSetAttribute(igemm_conv4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(227 * 1024));
     cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(227 * 1024));
     done = true;
 }
@@ -783,7 +796,8 @@ int igemm_conv_launch(const IgemmConvParams& p, cudaStream_t st) {
     const size_t smem = size_t(p.stages) * p.stage_bytes + 1024 + kBarrierBytes +
                         size_t(p.ncomb + 4 * p.ngimg + p.nred) * p.BN * sizeof(float);
     dim3 grid(p.tiles_w * p.tiles_h * p.tiles_b, p.Cout / p.BN);
-    launch_pdl(p.nacc == 2 ? igemm_conv2_kernel : igemm_conv_kernel, dim3(grid), dim3(kConvThreads), smem, st, p);
+    launch_pdl(p.nacc == 4 ? igemm_conv4_kernel : p.nacc == 2 ? igemm_conv2_kernel : igemm_conv_kernel, dim3(grid),
+               dim3(kConvThreads), smem, st, p);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)  // a failed launch must never pass silently (the output would simply be stale)
         fprintf(stderr, "[unet_b200] igemm_conv launch failed: %s (grid %u x %u, smem %zu, BN %d, stages %d)\n",
