@@ -820,6 +820,8 @@ int Builder::build() {
     auto flush_bucket = [&](size_t lo, size_t hi, bool last) {
         if (hi <= lo) return;
         const int k = bucket_no++;
+        static const bool dbg_buckets = getenv("UB_DEBUG_BUCKETS") != nullptr;  // (works in the counting pass too)
+        if (dbg_buckets) fprintf(stderr, "[unet_b200] bucket %d: [%zu, %zu)%s\n", k, lo, hi, last ? " last" : "");
         // pack entries whose weights lie in [lo, hi)
         int pk_first = 0, pk_count = 0, pk_tiles = 0;
         if (real() && (lo % 4) != 0) Tt->opt_overlap_ok = false;  // AdamW works on float4: ranges must be aligned
