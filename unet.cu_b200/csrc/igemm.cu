@@ -3,7 +3,10 @@
 // Both kernels are warp-specialised:
 //   warp 0   : TMA producer (one elected lane) - stages halo-shifted activation boxes + weight boxes in smem
 //   warp 1   : tcgen05.mma issuer (one elected lane) + TMEM allocator
-//   warps 2-5: epilogue - tcgen05.ld accumulators out of TMEM, fuse bias/emb/residual, store
+//   conv     : warps 2-9 epilogue (two per TMEM lane quadrant) - tcgen05.ld accumulators out of TMEM, fuse bias / emb /
+//              residual / GroupNorm hooks, store; in igemm_conv2/4_kernel lane 0 of the last epilogue warp(s) first
+//              issues the extra MMA streams
+//   wgrad    : warps 2-5 epilogue - vector REDs of the accumulators into the fp32 weight-gradient buffers
 // smem stages are handed over with mbarriers (full: TMA complete_tx, empty: tcgen05.commit).
 //
 // Reference behaviour being replaced (not its structure): /root/reference/dev/conv2d_k3.cu:679-740 (forward3),

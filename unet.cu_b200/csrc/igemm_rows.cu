@@ -16,7 +16,8 @@
 //   A ring : boxes (64 ch, W, TH+2, 1) of (TH+2)*W*128 B (36-48 KiB), 2-4 stages
 //   W ring : (tap, 64-ch block) weight tiles BN x 64, 2-8 stages, order (block, dx, dy) to match the A boxes
 //   TMEM   : 2 tile buffers x 2 halves x BN fp32 columns (BN <= 128)
-//   warps  : 0 = A producer, 1 = W producer, 2 = MMA issuer + TMEM allocator, 3 = idle, 4-11 = epilogue
+//   warps  : 0 = A producer, 1 = W producer, 2 = MMA issuer of M half 0 + TMEM allocator, 3 = MMA issuer of M half 1,
+//            4-11 = epilogue
 // Same epilogue (bias / embedding vector / residual / GroupNorm hooks) as igemm_conv_kernel: epilogue.cuh.
 #include "epilogue.cuh"
 #include "igemm.cuh"
