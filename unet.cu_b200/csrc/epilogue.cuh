@@ -42,12 +42,20 @@ struct EpiOut {
 // v[0..16) = the 16 accumulator columns at taddr, summed over the kernel's accumulators
 __device__ __forceinline__ void epi_tmem_load16(const EpiOut& e, uint32_t taddr, uint32_t (&v)[16]) {
     tmem_ld16(taddr, v);
-    for (int a = 1; a < e.nacc; ++a) {  // (nacc is a compile-time constant of the calling kernel)
+    if (e.nacc == 2) {
         uint32_t u[16];
-        tmem_ld16(taddr + uint32_t(a) * e.acc_stride, u);
+        tmem_ld16(taddr + e.acc_stride, u);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+    } else if (e.nacc > 2) {  // (the four-stream experiment)
+        for (int a = 1; a < e.nacc; ++a) {
+            uint32_t u[16];
+            tmem_ld16(taddr + uint32_t(a) * e.acc_stride, u);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+        }
     }
 }
 

@@ -261,8 +261,12 @@ __device__ __forceinline__ void igemm_conv_body(const IgemmConvParams& p) {
         if (lane == 0) conv_issue_loop<NACC>(p, 0, nk, smem, full_bar, empty_bar, tmem_full_bar, tmem_base);
     } else {
         // ------------------------------------------------------------ epilogue (warps 2..9)
-        if constexpr (NACC > 1) {  // extra MMA streams first; the warp reconverges before it touches the epilogue
-            // issuer i = 1 .. NACC-1 is lane 0 of warp 10 - i (the last epilogue warps)
+        if constexpr (NACC == 2) {  // second MMA stream first; the warp reconverges before it touches the epilogue
+            if (warp == 9) {
+                if (lane == 0) conv_issue_loop<NACC>(p, 1, nk, smem, full_bar, empty_bar, tmem_full_bar, tmem_base);
+                __syncwarp();
+            }
+        } else if constexpr (NACC > 2) {  // issuer i = 1 .. NACC-1 is lane 0 of warp 10 - i (the last epilogue warps)
             if (warp > 10 - NACC) {
                 if (lane == 0)
                     conv_issue_loop<NACC>(p, 10 - warp, nk, smem, full_bar, empty_bar, tmem_full_bar, tmem_base);
