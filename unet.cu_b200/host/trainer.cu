@@ -685,7 +685,7 @@ int Builder::build() {
             Bk([=](cudaStream_t st) {
                 conv_in_wgrad(Tt->xt, dout.p, dout.ld, Bn, Cin, hv.C, hv.H, hv.W, gw, gb, Tt->small_scratch,
                               Tt->small_scratch_floats, st);
-            }, 2, UB_KIND_SMALL, 0, 0, 1);
+            }, 1, UB_KIND_SMALL, 0, 0, 1);  // (one launch with the row kernel; two on its fallback path)
             if (Tt->cfg.compute_dinput)
                 Bk([=](cudaStream_t st) { conv_in_dgrad(dout.p, dout.ld, w, Bn, Cin, hv.C, hv.H, hv.W, Tt->dxt, st); }, 1);
             return View{};
@@ -788,7 +788,7 @@ int Builder::build() {
             Bk([=](cudaStream_t st) {
                 conv_out_wgrad(ao.p, ao.ld, Tt->dout, Bn, Cin, Co, Hh, Ww, gw, gb, Tt->small_scratch,
                                Tt->small_scratch_floats, st);
-            }, 3, UB_KIND_SMALL, 0, 0, 1);
+            }, 2, UB_KIND_SMALL, 0, 0, 1);  // (row kernel + bias sum; three on the fallback path)
             Bk([=](cudaStream_t st) { conv_out_dgrad(Tt->dout, w, Bn, Cin, Co, Hh, Ww, dao.p, dao.ld, st); }, 1);
             gn_bwd(g, hx, dao, 1, View{}, dh, nullptr);
             return dh;
