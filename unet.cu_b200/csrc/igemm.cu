@@ -139,7 +139,7 @@ __device__ __forceinline__ void conv_issue_loop(const IgemmConvParams& p, int is
 // 8x8 / 16x16 levels) run NACC = 2: lane 0 of the last epilogue warp -- idle during the main loop -- issues the odd K
 // blocks into a second accumulator and the epilogue adds the two.  (An 11th warp for the second issuer capped the
 // two-CTA kernel at 80 registers; the spilling epilogue cost more in the step than the main loop won.)
-template <int NACC>
+template <int NACC, bool MS = false>
 __device__ __forceinline__ void igemm_conv_body(const IgemmConvParams& p) {
     pdl_trigger();
 #ifdef UB_TRACE
@@ -187,6 +187,7 @@ __device__ __forceinline__ void igemm_conv_body(const IgemmConvParams& p) {
             mbar_init(&empty_bar[i], 1);
         }
         mbar_init(tmem_full_bar, NACC);
+        if constexpr (MS) mbar_init(tmem_full_bar + 2, 1);  // statistics MMAs complete (byte 144 of the barrier block)
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -304,6 +305,101 @@ __device__ __forceinline__ void igemm_conv_body(const IgemmConvParams& p) {
         if (threadIdx.x == 64) UB_TR(8, (unsigned long long)clock64());
         tc_fence_after();
 
+        bool done_ms = false;
+        if constexpr (MS) {
+            if (p.ms) {
+                done_ms = true;
+                // ---- EXPERIMENT: statistics on the tensor core (see IgemmConvParams::ms).  The pipeline stages are dead.
+                uint64_t* stat_bar = tmem_full_bar + 2;
+                const int atoms = p.BN / 64;
+                const uint32_t ys = smem_u32(smem), y2s = ys + uint32_t(atoms) * 16384u;
+                const uint32_t ones_s = ys + 2u * uint32_t(atoms) * 16384u;
+                for (int i = et; i < 1024; i += kEpiThreads)  // 128 pixel rows x 128 B of bf16 1.0
+                    sts_v4_b32(ones_s + 16u * i, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+                const float* cmb = comb + (p.ncomb > 1 ? min(lb, p.ncomb - 1) : 0) * p.BN;
+                const uint32_t rowoff = uint32_t(row >> 3) * 1024u + uint32_t(row & 7) * 128u;
+                for (int c0 = 16 * half; c0 < p.BN; c0 += 32) {
+                    uint32_t v[16];
+                    epi_tmem_load16(eo, tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c0), v);
+                    uint4 r[2];
+                    if (p.residual && valid) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.ldr + n0 + c0);
+                        r[0] = rp[0], r[1] = rp[1];
+                    }
+                    tmem_ld_wait();
+                    float f[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] = valid ? __uint_as_float(v[j]) + cmb[c0 + j] : 0.f;
+                    if (p.residual && valid) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            float t[8];
+                            unpack_bf16x8(r[j], t);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) f[j * 8 + i] += t[i];
+                        }
+                    }
+                    uint32_t py[8], pq[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                        const float2 fr = __bfloat1622float2(h2);  // the stored values: square exactly those
+                        const __nv_bfloat162 q2 = __floats2bfloat162_rn(fr.x * fr.x, fr.y * fr.y);
+                        py[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                        pq[i] = *reinterpret_cast<const uint32_t*>(&q2);
+                    }
+                    // MN-major SW128 atom: row = pixel (128 B = 64 channels), 16-byte chunk index XOR (row % 8)
+                    const uint32_t abase = uint32_t(c0 >> 6) * 16384u + rowoff;
+                    const uint32_t ch = uint32_t((c0 & 63) >> 3), sw = uint32_t(row & 7);
+                    sts_v4_b32(ys + abase + ((ch ^ sw) << 4), py[0], py[1], py[2], py[3]);
+                    sts_v4_b32(ys + abase + (((ch + 1) ^ sw) << 4), py[4], py[5], py[6], py[7]);
+                    sts_v4_b32(y2s + abase + ((ch ^ sw) << 4), pq[0], pq[1], pq[2], pq[3]);
+                    sts_v4_b32(y2s + abase + (((ch + 1) ^ sw) << 4), pq[4], pq[5], pq[6], pq[7]);
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                named_bar_sync(1, kEpiThreads);
+                const uint32_t t_stat = tmem_base + uint32_t(NACC * p.BN);  // [image][sum 16 cols | sumsq 16 cols]
+                if (threadIdx.x == 64) {
+                    tc_fence_after();
+                    for (int a = 0; a < atoms; ++a) tma_store_4d(smem + size_t(a) * 16384, &p.tmO, n0 + a * 64, w0, h0, b0);
+                    bulk_commit_group();
+                    const uint32_t idesc = make_idesc_bf16(uint32_t(p.BN), 16, 1, 1);
+                    const uint64_t dbase = make_smem_desc_sw128(0, 16384, 1024);  // LBO = 64-channel atom, SBO = 8 rows
+                    const uint64_t dY = dbase | uint64_t((ys >> 4) & 0x3FFF), dY2 = dbase | uint64_t((y2s >> 4) & 0x3FFF);
+                    const uint64_t dO = dbase | uint64_t((ones_s >> 4) & 0x3FFF);
+                    const int kpi = 8 / p.TB;  // K steps (16 pixels) per image of the tile
+                    for (int img = 0; img < p.TB; ++img)
+                        for (int k = 0; k < kpi; ++k) {
+                            const uint64_t ko = uint64_t((img * kpi + k) * 128);  // 16 rows x 128 B, in 16-byte units
+                            umma_bf16(t_stat + uint32_t(img * 32), dY + ko, dO + ko, idesc, k != 0);
+                            umma_bf16(t_stat + uint32_t(img * 32 + 16), dY2 + ko, dO + ko, idesc, k != 0);
+                        }
+                    umma_commit(stat_bar);
+                }
+                mbar_wait(stat_bar, 0);
+                tc_fence_after();
+                if (half == 0) {
+                    // M = 128: channel m in TMEM lane m.  M = 64: channel m in lane (m % 16) + 32 * (m / 16).
+                    const int chn = p.BN == 128 ? q * 32 + lane : q * 16 + lane;
+                    const bool cv = p.BN == 128 || lane < 16;
+                    for (int img = 0; img < p.TB; ++img) {
+                        uint32_t sv[16], qv[16];
+                        tmem_ld16(t_stat + (uint32_t(q * 32) << 16) + uint32_t(img * 32), sv);
+                        tmem_ld16(t_stat + (uint32_t(q * 32) << 16) + uint32_t(img * 32 + 16), qv);
+                        tmem_ld_wait();
+                        if (cv && b0 + img < p.B) {
+                            float* d = p.stats + (size_t(b0 + img) * p.Cout + n0 + chn) * 2;
+                            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(d), "f"(__uint_as_float(sv[0])),
+                                         "f"(__uint_as_float(qv[0]))
+                                         : "memory");
+                        }
+                    }
+                }
+                if (threadIdx.x == 64) bulk_wait_group0();  // the Y tile has left shared memory
+            }
+        }
+        if (!done_ms) {
         // GroupNorm hooks: all 32 pixels of a warp lie in one image of the tile (plan)
         const int lbw = min(lb, p.TB - 1);
         epi_row(eo, tmem_base + (uint32_t(q * 32) << 16), comb + (p.ncomb > 1 ? min(lb, p.ncomb - 1) : 0) * p.BN, p.BN,
@@ -315,6 +411,7 @@ __device__ __forceinline__ void igemm_conv_body(const IgemmConvParams& p) {
             epi_flush_stats(red, p.gn_x ? p.gn_S : p.stats, p.Cout, n0, p.BN, b0, p.B, p.TW * p.TH, p.TB, et,
                             kEpiThreads);
         }
+        }  // !done_ms
         if (threadIdx.x == 64) UB_TR(9, (unsigned long long)clock64());
     }
 
@@ -333,6 +430,13 @@ __global__ void __launch_bounds__(kConvThreads, 2) igemm_conv_kernel(const __gri
 }
 __global__ void __launch_bounds__(kConvThreads, 1) igemm_conv2_kernel(const __grid_constant__ IgemmConvParams p) {
     igemm_conv_body<2>(p);
+}
+// EXPERIMENT (UB_EPI_MMA=1): tensor-core GroupNorm statistics + TMA output store, see IgemmConvParams::ms
+__global__ void __launch_bounds__(kConvThreads, 2) igemm_conv_ms_kernel(const __grid_constant__ IgemmConvParams p) {
+    igemm_conv_body<1, true>(p);
+}
+__global__ void __launch_bounds__(kConvThreads, 1) igemm_conv2_ms_kernel(const __grid_constant__ IgemmConvParams p) {
+    igemm_conv_body<2, true>(p);
 }
 // four streams: an experiment switch (UB_CONV_NACC=4), not the default -- not yet measured inside the step
 __global__ void __launch_bounds__(kConvThreads, 1) igemm_conv4_kernel(const __grid_constant__ IgemmConvParams p) {
@@ -773,6 +877,21 @@ int igemm_conv_plan(IgemmConvParams* p, const ConvSegDesc* segs, int nseg, int B
         }
     }
     p->nred = gn_hook ? 8 : 0;
+    {
+        // EXPERIMENT (UB_EPI_MMA=1): tensor-core statistics + TMA output store for the plain stats hook on full
+        // 128-pixel tiles of one or two whole images with a 64- or 128-channel N tile, one or two MMA streams
+        static const bool want_ms = getenv("UB_EPI_MMA") && atoi(getenv("UB_EPI_MMA")) != 0;
+        const bool full_tiles = W % p->TW == 0 && H % p->TH == 0 && p->TW * p->TH * p->TB == 128;
+        const size_t need = size_t(2 * (BN / 64) + 1) * 16384;  // Y atoms, Y*Y atoms, ones tile in the dead stages
+        if (want_ms && ep.stats && !ep.gn_x && p->out_mode == OUT_NHWC_BF16 && (BN == 64 || BN == 128) &&
+            p->nacc <= 2 && (p->TB == 1 || (p->TB == 2 && (p->TW * p->TH) == 64)) && full_tiles &&
+            need <= size_t(p->stages) * p->stage_bytes && p->nacc * BN + 64 <= (p->nacc == 1 ? 256 : 512) &&
+            make_act_map(&p->tmO, reinterpret_cast<const __nv_bfloat16*>(ep.out), Cout, p->ldo, W, H, B, p->TW, p->TH,
+                         p->TB) == 0) {
+            p->ms = 1;
+            p->tmem_cols = next_pow2(p->nacc * BN + 64);
+        }
+    }
     if (size_t(p->ncomb + 4 * p->ngimg + p->nred) * BN * sizeof(float) > 16384) return -9;  // smem tail budget
     if (size_t(p->stages) * p->stage_bytes + 1024 + kBarrierBytes +
             size_t(p->ncomb + 4 * p->ngimg + p->nred) * BN * sizeof(float) > size_t(227) * 1024)
@@ -794,6 +913,8 @@ void igemm_init() {
     cudaFuncSetAttribute(igemm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(227 * 1024));
     cudaFuncSetAttribute(igemm_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(227 * 1024));
     cudaFuncSetAttribute(igemm_conv4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(227 * 1024));
+    cudaFuncSetAttribute(igemm_conv_ms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(227 * 1024));
+    cudaFuncSetAttribute(igemm_conv2_ms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(227 * 1024));
     cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(227 * 1024));
     done = true;
 }
@@ -803,8 +924,9 @@ int igemm_conv_launch(const IgemmConvParams& p, cudaStream_t st) {
     const size_t smem = size_t(p.stages) * p.stage_bytes + 1024 + kBarrierBytes +
                         size_t(p.ncomb + 4 * p.ngimg + p.nred) * p.BN * sizeof(float);
     dim3 grid(p.tiles_w * p.tiles_h * p.tiles_b, p.Cout / p.BN);
-    launch_pdl(p.nacc == 4 ? igemm_conv4_kernel : p.nacc == 2 ? igemm_conv2_kernel : igemm_conv_kernel, dim3(grid),
-               dim3(kConvThreads), smem, st, p);
+    auto kern = p.nacc == 4 ? igemm_conv4_kernel : p.nacc == 2 ? igemm_conv2_kernel : igemm_conv_kernel;
+    if (p.ms) kern = p.nacc == 2 ? igemm_conv2_ms_kernel : igemm_conv_ms_kernel;
+    launch_pdl(kern, dim3(grid), dim3(kConvThreads), smem, st, p);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)  // a failed launch must never pass silently (the output would simply be stale)
         fprintf(stderr, "[unet_b200] igemm_conv launch failed: %s (grid %u x %u, smem %zu, BN %d, stages %d)\n",

@@ -62,6 +62,12 @@ struct IgemmConvParams {
     int gn_silu, gn_cpg;
     int ngimg;                      // rows of the staged GroupNorm constants (TB when gn_x is set, else 0)
     int nred;                       // BN-float rows of the cross-warp reduction scratch (8 with a hook, else 0)
+    // EXPERIMENT (UB_EPI_MMA=1, not the default, not yet run on a GPU): GroupNorm statistics on the tensor core --
+    // the epilogue stages the bf16 output tile Y and Y*Y in shared memory as MN-major SW128 operands (the layout TMA
+    // gives the wgrad kernel), a ones-tile MMA (the wgrad kernel's bias-gradient trick) leaves sum(y) and sum(y*y)
+    // of channel c in TMEM lane c, and the Y tile goes to global memory with one TMA store per 64 channels.
+    int ms;
+    CUtensorMap tmO;                // output tensor, box (64, TW, TH, TB), SWIZZLE_128B (ms only)
 };
 
 // persistent row-tile variant (igemm_rows.cu); same segments / epilogue as IgemmConvParams
