@@ -149,33 +149,43 @@ __global__ void __launch_bounds__(kThreads) attn_tc_fwd_kernel(const __grid_cons
     const uint32_t tmem = sm->tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            tma_prefetch_desc(&p.tmQKV);
+        // (whole warp converged; TMA / MMA / commit instructions under elect.sync: see elect_one_sync in ptx.cuh)
+        {
             const int nbox = t.ncols / 128;
-            mbar_expect_tx(&sm->bar_load, uint32_t(16384 * (1 + 2 * nbox)));
-            tma_load_2d(sQ, &p.tmQKV, &sm->bar_load, t.hp * 64, t.row0);
-            for (int i = 0; i < nbox; ++i) {
-                tma_load_2d(sK + i * 16384, &p.tmQKV, &sm->bar_load, C + t.hp * 64, t.col0 + i * 128);
-                tma_load_2d(sV + i * 16384, &p.tmQKV, &sm->bar_load, 2 * C + t.hp * 64, t.col0 + i * 128);
+            if (elect_one_sync()) {
+                tma_prefetch_desc(&p.tmQKV);
+                mbar_expect_tx(&sm->bar_load, uint32_t(16384 * (1 + 2 * nbox)));
+                tma_load_2d(sQ, &p.tmQKV, &sm->bar_load, t.hp * 64, t.row0);
+                for (int i = 0; i < nbox; ++i) {
+                    tma_load_2d(sK + i * 16384, &p.tmQKV, &sm->bar_load, C + t.hp * 64, t.col0 + i * 128);
+                    tma_load_2d(sV + i * 16384, &p.tmQKV, &sm->bar_load, 2 * C + t.hp * 64, t.col0 + i * 128);
+                }
             }
+            __syncwarp();
             mbar_wait(&sm->bar_load, 0);
             tc_fence_after();
             const uint32_t id_s = make_idesc_bf16(128, t.ncols, 0, 0);
             const uint32_t id_o = make_idesc_bf16(128, 64, 0, 1);
-            // descriptors = constant high word + start address in 16-byte units (the issue loop runs on one thread)
             const uint64_t dQ = make_smem_desc_sw128(smem_u32(sQ), 16, 1024), dK = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
             const uint64_t dP = make_smem_desc_sw128(smem_u32(sP), 16, 1024), dV = make_smem_desc_sw128(smem_u32(sV), 8192, 1024);
             for (int h = 0; h < 2; ++h) {
+                if (elect_one_sync()) {
 #pragma unroll
-                for (int k = 0; k < 2; ++k) umma_bf16(tmem, dQ + uint64_t(h * 4 + k * 2), dK + uint64_t(h * 4 + k * 2), id_s, k);
-                umma_commit(&sm->bar_s);
+                    for (int k = 0; k < 2; ++k)
+                        umma_bf16(tmem, dQ + uint64_t(h * 4 + k * 2), dK + uint64_t(h * 4 + k * 2), id_s, k);
+                    umma_commit(&sm->bar_s);
+                }
+                __syncwarp();
                 mbar_wait(&sm->bar_p, h);
                 tc_fence_after();
+                if (elect_one_sync()) {
 #pragma unroll 4
-                for (int j = 0; j < t.ncols / 16; ++j)
-                    umma_bf16(tmem + o_col, dP + uint64_t((j >> 2) * 1024 + (j & 3) * 2), dV + uint64_t(j * 128), id_o, j);
-                // (the row threads drain O_0 before they arrive on bar_p for head 1, so PV of head 1 may reuse it)
-                umma_commit(&sm->bar_o);
+                    for (int j = 0; j < t.ncols / 16; ++j)
+                        umma_bf16(tmem + o_col, dP + uint64_t((j >> 2) * 1024 + (j & 3) * 2), dV + uint64_t(j * 128), id_o, j);
+                    // (the row threads drain O_0 before they arrive on bar_p for head 1, so PV of head 1 may reuse it)
+                    umma_commit(&sm->bar_o);
+                }
+                __syncwarp();
             }
         }
     } else {
@@ -274,16 +284,19 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dq_kernel(const __grid_const
     // TMEM columns: S [0,128)  dP [128,256)  dQ_h [256 + 64h, +64)
 
     if (warp == 0) {
-        if (lane == 0) {
-            tma_prefetch_desc(&p.tmQKV);
-            tma_prefetch_desc(&p.tmDO);
-            mbar_expect_tx(&sm->bar_load, uint32_t(16384 * (2 + 2 * nchunk)));
-            tma_load_2d(sQ, &p.tmQKV, &sm->bar_load, t.hp * 64, t.row0);
-            tma_load_2d(sdO, &p.tmDO, &sm->bar_load, t.hp * 64, t.row0);
-            for (int i = 0; i < nchunk; ++i) {
-                tma_load_2d(sK + i * 16384, &p.tmQKV, &sm->bar_load, C + t.hp * 64, t.col0 + i * 128);
-                tma_load_2d(sV + i * 16384, &p.tmQKV, &sm->bar_load, 2 * C + t.hp * 64, t.col0 + i * 128);
+        {
+            if (elect_one_sync()) {
+                tma_prefetch_desc(&p.tmQKV);
+                tma_prefetch_desc(&p.tmDO);
+                mbar_expect_tx(&sm->bar_load, uint32_t(16384 * (2 + 2 * nchunk)));
+                tma_load_2d(sQ, &p.tmQKV, &sm->bar_load, t.hp * 64, t.row0);
+                tma_load_2d(sdO, &p.tmDO, &sm->bar_load, t.hp * 64, t.row0);
+                for (int i = 0; i < nchunk; ++i) {
+                    tma_load_2d(sK + i * 16384, &p.tmQKV, &sm->bar_load, C + t.hp * 64, t.col0 + i * 128);
+                    tma_load_2d(sV + i * 16384, &p.tmQKV, &sm->bar_load, 2 * C + t.hp * 64, t.col0 + i * 128);
+                }
             }
+            __syncwarp();
             mbar_wait(&sm->bar_load, 0);
             tc_fence_after();
             const uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);
@@ -294,20 +307,26 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dq_kernel(const __grid_const
             int it = 0;
             for (int h = 0; h < 2; ++h) {
                 for (int cc = 0; cc < nchunk; ++cc, ++it) {
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const uint64_t o = uint64_t(h * 4 + k * 2);
-                        umma_bf16(tmem, dQ + o, dK + o + uint64_t(cc * 1024), id_s, k);
-                        umma_bf16(tmem + 128, dG + o, dV + o + uint64_t(cc * 1024), id_s, k);
+                        for (int k = 0; k < 2; ++k) {
+                            const uint64_t o = uint64_t(h * 4 + k * 2);
+                            umma_bf16(tmem, dQ + o, dK + o + uint64_t(cc * 1024), id_s, k);
+                            umma_bf16(tmem + 128, dG + o, dV + o + uint64_t(cc * 1024), id_s, k);
+                        }
+                        umma_commit(&sm->bar_s);
                     }
-                    umma_commit(&sm->bar_s);
+                    __syncwarp();
                     mbar_wait(&sm->bar_p, it & 1);
                     tc_fence_after();
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        umma_bf16(tmem + 256 + h * 64, dS + uint64_t((j >> 2) * 1024 + (j & 3) * 2),
-                                  dKm + uint64_t(cc * 1024 + j * 128), id_o, (cc | j) != 0);
-                    umma_commit(&sm->bar_o);
+                        for (int j = 0; j < 8; ++j)
+                            umma_bf16(tmem + 256 + h * 64, dS + uint64_t((j >> 2) * 1024 + (j & 3) * 2),
+                                      dKm + uint64_t(cc * 1024 + j * 128), id_o, (cc | j) != 0);
+                        umma_commit(&sm->bar_o);
+                    }
+                    __syncwarp();
                 }
             }
         }
@@ -416,16 +435,19 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dkv_kernel(const __grid_cons
     // TMEM columns: S^T [0,128)  dP^T [128,256)  dK_h [256 + 64h, +64)  dV_h [384 + 64h, +64)
 
     if (warp == 0) {
-        if (lane == 0) {
-            tma_prefetch_desc(&p.tmQKV);
-            tma_prefetch_desc(&p.tmDO);
-            mbar_expect_tx(&sm->bar_load, uint32_t(16384 * (2 + 2 * nchunk)));
-            tma_load_2d(sK, &p.tmQKV, &sm->bar_load, C + t.hp * 64, t.row0);
-            tma_load_2d(sV, &p.tmQKV, &sm->bar_load, 2 * C + t.hp * 64, t.row0);
-            for (int i = 0; i < nchunk; ++i) {
-                tma_load_2d(sQ + i * 16384, &p.tmQKV, &sm->bar_load, t.hp * 64, t.col0 + i * 128);
-                tma_load_2d(sdO + i * 16384, &p.tmDO, &sm->bar_load, t.hp * 64, t.col0 + i * 128);
+        {
+            if (elect_one_sync()) {
+                tma_prefetch_desc(&p.tmQKV);
+                tma_prefetch_desc(&p.tmDO);
+                mbar_expect_tx(&sm->bar_load, uint32_t(16384 * (2 + 2 * nchunk)));
+                tma_load_2d(sK, &p.tmQKV, &sm->bar_load, C + t.hp * 64, t.row0);
+                tma_load_2d(sV, &p.tmQKV, &sm->bar_load, 2 * C + t.hp * 64, t.row0);
+                for (int i = 0; i < nchunk; ++i) {
+                    tma_load_2d(sQ + i * 16384, &p.tmQKV, &sm->bar_load, t.hp * 64, t.col0 + i * 128);
+                    tma_load_2d(sdO + i * 16384, &p.tmDO, &sm->bar_load, t.hp * 64, t.col0 + i * 128);
+                }
             }
+            __syncwarp();
             mbar_wait(&sm->bar_load, 0);
             tc_fence_after();
             const uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);
@@ -437,22 +459,28 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dkv_kernel(const __grid_cons
             int it = 0;
             for (int h = 0; h < 2; ++h) {
                 for (int cc = 0; cc < nchunk; ++cc, ++it) {
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const uint64_t o = uint64_t(h * 4 + k * 2);
-                        umma_bf16(tmem, dK + o, dQ + o + uint64_t(cc * 1024), id_s, k);
-                        umma_bf16(tmem + 128, dV + o, dG + o + uint64_t(cc * 1024), id_s, k);
+                        for (int k = 0; k < 2; ++k) {
+                            const uint64_t o = uint64_t(h * 4 + k * 2);
+                            umma_bf16(tmem, dK + o, dQ + o + uint64_t(cc * 1024), id_s, k);
+                            umma_bf16(tmem + 128, dV + o, dG + o + uint64_t(cc * 1024), id_s, k);
+                        }
+                        umma_commit(&sm->bar_s);
                     }
-                    umma_commit(&sm->bar_s);
+                    __syncwarp();
                     mbar_wait(&sm->bar_p, it & 1);
                     tc_fence_after();
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint64_t aoff = uint64_t((j >> 2) * 1024 + (j & 3) * 2);
-                        umma_bf16(tmem + 384 + h * 64, dPt + aoff, dGm + uint64_t(cc * 1024 + j * 128), id_o, (cc | j) != 0);
-                        umma_bf16(tmem + 256 + h * 64, dSt + aoff, dQm + uint64_t(cc * 1024 + j * 128), id_o, (cc | j) != 0);
+                        for (int j = 0; j < 8; ++j) {
+                            const uint64_t aoff = uint64_t((j >> 2) * 1024 + (j & 3) * 2);
+                            umma_bf16(tmem + 384 + h * 64, dPt + aoff, dGm + uint64_t(cc * 1024 + j * 128), id_o, (cc | j) != 0);
+                            umma_bf16(tmem + 256 + h * 64, dSt + aoff, dQm + uint64_t(cc * 1024 + j * 128), id_o, (cc | j) != 0);
+                        }
+                        umma_commit(&sm->bar_o);
                     }
-                    umma_commit(&sm->bar_o);
+                    __syncwarp();
                 }
             }
         }

@@ -97,6 +97,7 @@ __device__ __forceinline__ void conv_issue_loop(const IgemmConvParams& p, int is
 #ifdef UB_TRACE
     const int dbg = g_conv_dbg_mode;
 #endif
+    // The WHOLE warp runs this loop (converged); only the instruction block is under elect.sync -- see elect_one_sync.
     for (int it = issuer; it < nk; it += NACC) {
 #ifdef UB_TRACE
         if (dbg < 2)
@@ -110,10 +111,10 @@ __device__ __forceinline__ void conv_issue_loop(const IgemmConvParams& p, int is
         const uint64_t dB = make_smem_desc_sw128(sB, 16, 1024);
 #ifdef UB_TRACE
         if (dbg == 1) {
-            mbar_arrive(&empty_bar[stage]);
+            if (elect_one_sync()) mbar_arrive(&empty_bar[stage]);
         } else
 #endif
-        {
+        if (elect_one_sync()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 // advance 16 bf16 (32 B) along K inside the 128-byte swizzle row: +2 in the >>4 address field
@@ -121,15 +122,17 @@ __device__ __forceinline__ void conv_issue_loop(const IgemmConvParams& p, int is
             }
             umma_commit(&empty_bar[stage]);
         }
+        __syncwarp();
         stage += NACC;
         if (stage >= p.stages) stage -= p.stages, phase ^= 1;
     }
 #ifdef UB_TRACE
     if (dbg == 1) {
-        mbar_arrive(tmem_full_bar);
+        if (elect_one_sync()) mbar_arrive(tmem_full_bar);
     } else
 #endif
-    umma_commit(tmem_full_bar);
+    if (elect_one_sync()) umma_commit(tmem_full_bar);
+    __syncwarp();
     if (issuer == 0) UB_TR(7, (unsigned long long)clock64());
 }
 
@@ -229,10 +232,11 @@ __device__ __forceinline__ void igemm_conv_body(const IgemmConvParams& p) {
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
+        // (whole warp converged; the TMA instructions are issued under elect.sync -- see elect_one_sync)
 #ifdef UB_TRACE
-        if (lane == 0 && g_conv_dbg_mode < 2) {
+        if (g_conv_dbg_mode < 2) {
 #else
-        if (lane == 0) {
+        {
 #endif
             int stage = 0;
             uint32_t phase = 0;
@@ -245,9 +249,12 @@ __device__ __forceinline__ void igemm_conv_body(const IgemmConvParams& p) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* sA = smem + size_t(stage) * p.stage_bytes;
                         uint8_t* sB = sA + 16384;
-                        mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
-                        tma_load_4d(sA, &sg.tmA, &full_bar[stage], cb * 64, w0 + dx, h0 + dy, b0);
-                        tma_load_2d(sB, &sg.tmW, &full_bar[stage], cb * 64, tap * p.Cout + n0);
+                        if (elect_one_sync()) {
+                            mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
+                            tma_load_4d(sA, &sg.tmA, &full_bar[stage], cb * 64, w0 + dx, h0 + dy, b0);
+                            tma_load_2d(sB, &sg.tmW, &full_bar[stage], cb * 64, tap * p.Cout + n0);
+                        }
+                        __syncwarp();
                         if (++stage == p.stages) {
                             stage = 0;
                             phase ^= 1;
@@ -259,20 +266,14 @@ __device__ __forceinline__ void igemm_conv_body(const IgemmConvParams& p) {
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (stream 0)
-        if (lane == 0) conv_issue_loop<NACC>(p, 0, nk, smem, full_bar, empty_bar, tmem_full_bar, tmem_base);
+        conv_issue_loop<NACC>(p, 0, nk, smem, full_bar, empty_bar, tmem_full_bar, tmem_base);
     } else {
         // ------------------------------------------------------------ epilogue (warps 2..9)
         if constexpr (NACC == 2) {  // second MMA stream first; the warp reconverges before it touches the epilogue
-            if (warp == 9) {
-                if (lane == 0) conv_issue_loop<NACC>(p, 1, nk, smem, full_bar, empty_bar, tmem_full_bar, tmem_base);
-                __syncwarp();
-            }
+            if (warp == 9) conv_issue_loop<NACC>(p, 1, nk, smem, full_bar, empty_bar, tmem_full_bar, tmem_base);
         } else if constexpr (NACC > 2) {  // issuer i = 1 .. NACC-1 is lane 0 of warp 10 - i (the last epilogue warps)
-            if (warp > 10 - NACC) {
-                if (lane == 0)
-                    conv_issue_loop<NACC>(p, 10 - warp, nk, smem, full_bar, empty_bar, tmem_full_bar, tmem_base);
-                __syncwarp();
-            }
+            if (warp > 10 - NACC)
+                conv_issue_loop<NACC>(p, 10 - warp, nk, smem, full_bar, empty_bar, tmem_full_bar, tmem_base);
         }
         const int q = warp & 3;  // TMEM lane quadrant this warp may access
         const int half = (warp - 2) >> 2;  // the two warps of a quadrant split the columns
@@ -500,7 +501,8 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
     pdl_wait();  // everything above touched only kernel parameters, shared memory and TMEM
 
     if (warp == 0) {
-        if (lane == 0) {
+        // (whole warp converged, TMA instructions under elect.sync: see elect_one_sync in ptx.cuh)
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int kt = k_begin; kt < k_end; ++kt) {
@@ -512,17 +514,20 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* sA = smem + size_t(stage) * p.stage_bytes;
                 uint8_t* sB = sA + b_off;
-                mbar_expect_tx(&full_bar[stage], p.tx_bytes);
-                for (int a = 0; a < a_atoms; ++a)
-                    tma_load_4d(sA + a * atom, &p.tmDY, &full_bar[stage], o0 + a * 64, w0, h0, b0);
-                for (int ti = 0; ti < p.TC; ++ti) {
-                    const int tap = tap0 + ti;
-                    const int dy = p.ntaps == 9 ? tap / 3 - 1 : 0;
-                    const int dx = p.ntaps == 9 ? tap % 3 - 1 : 0;
-                    for (int nb = 0; nb < b_atoms; ++nb)
-                        tma_load_4d(sB + (ti * b_atoms + nb) * atom, &p.tmX, &full_bar[stage], c0 + nb * 64, w0 + dx,
-                                    h0 + dy, b0);
+                if (elect_one_sync()) {
+                    mbar_expect_tx(&full_bar[stage], p.tx_bytes);
+                    for (int a = 0; a < a_atoms; ++a)
+                        tma_load_4d(sA + a * atom, &p.tmDY, &full_bar[stage], o0 + a * 64, w0, h0, b0);
+                    for (int ti = 0; ti < p.TC; ++ti) {
+                        const int tap = tap0 + ti;
+                        const int dy = p.ntaps == 9 ? tap / 3 - 1 : 0;
+                        const int dx = p.ntaps == 9 ? tap % 3 - 1 : 0;
+                        for (int nb = 0; nb < b_atoms; ++nb)
+                            tma_load_4d(sB + (ti * b_atoms + nb) * atom, &p.tmX, &full_bar[stage], c0 + nb * 64, w0 + dx,
+                                        h0 + dy, b0);
+                    }
                 }
+                __syncwarp();
                 if (++stage == p.stages) {
                     stage = 0;
                     phase ^= 1;
@@ -530,11 +535,10 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // The issue loop runs on ONE thread: every instruction in it is on the critical path (the first version
-            // rebuilt two 64-bit descriptors per MMA, ~20 dependent instructions, and the tensor pipe sat idle 3/4 of
-            // the time -- ncu r01 wgrad).  Everything that does not change per K tile is hoisted: descriptors are a
-            // constant high word plus the 16-byte-granular start address, MMA groups are precomputed.
+        {
+            // Whole warp converged, MMAs / commits under elect.sync (see elect_one_sync in ptx.cuh).  Everything that does
+            // not change per K tile is hoisted: descriptors are a constant high word plus the 16-byte-granular start
+            // address, MMA groups are precomputed.
             const uint64_t dbase = make_smem_desc_sw128(0, atom, 1024);  // LBO = atom (64-channel atoms), SBO = 1024
             const int ksteps = p.KP / 16;
             const uint32_t idesc_b = make_idesc_bf16(p.MO, 16, 1, 1);
@@ -560,25 +564,30 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
                 // 16 pixels (K) per MMA = 16 rows of 128 B = 2048 B = 128 descriptor units
                 const uint64_t dA = dbase | uint64_t(((s0 + uint32_t(stage) * p.stage_bytes) >> 4) & 0x3FFF);
                 const uint32_t acc0 = kt != k_begin;
-                if (do_bias) {
+                if (elect_one_sync()) {
+                    if (do_bias) {
 #pragma unroll 4
-                    for (int k = 0; k < ksteps; ++k)
-                        umma_bf16(t_bias, dA + uint64_t(k * 128), d_ones + uint64_t(k * 128), idesc_b, acc0 | uint32_t(k));
-                }
+                        for (int k = 0; k < ksteps; ++k)
+                            umma_bf16(t_bias, dA + uint64_t(k * 128), d_ones + uint64_t(k * 128), idesc_b,
+                                      acc0 | uint32_t(k));
+                    }
 #pragma unroll 3
-                for (int g = 0; g < ng; ++g) {
+                    for (int g = 0; g < ng; ++g) {
 #pragma unroll 4
-                    for (int k = 0; k < ksteps; ++k)
-                        umma_bf16(tmem_base + g_col[g], dA + uint64_t(k * 128), dA + uint64_t(g_boff[g] + k * 128),
-                                  g_idesc[g], acc0 | uint32_t(k));
+                        for (int k = 0; k < ksteps; ++k)
+                            umma_bf16(tmem_base + g_col[g], dA + uint64_t(k * 128), dA + uint64_t(g_boff[g] + k * 128),
+                                      g_idesc[g], acc0 | uint32_t(k));
+                    }
+                    umma_commit(&empty_bar[stage]);
                 }
-                umma_commit(&empty_bar[stage]);
+                __syncwarp();
                 if (++stage == p.stages) {
                     stage = 0;
                     phase ^= 1;
                 }
             }
-            umma_commit(tmem_full_bar);
+            if (elect_one_sync()) umma_commit(tmem_full_bar);
+            __syncwarp();
         }
     } else {
         const int q = warp & 3;

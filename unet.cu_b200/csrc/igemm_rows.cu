@@ -90,7 +90,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
 
     if (warp == 0) {
         // ------------------------------------------------------------------ A producer: one box per (block, dx)
-        if (lane == 0) {
+        // (whole warp converged, instructions under elect.sync: see elect_one_sync in ptx.cuh)
+        {
             int st = 0;
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -101,9 +102,12 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
                     for (int cb = 0; cb < p.seg[s].cblocks; ++cb)
                         for (int dxi = 0; dxi < ndx; ++dxi) {
                             mbar_wait(&bars->a_empty[st], ph ^ 1);
-                            mbar_expect_tx(&bars->a_full[st], p.a_bytes);
-                            tma_load_4d(sA + size_t(st) * p.a_stage_bytes, &p.seg[s].tmA, &bars->a_full[st], cb * 64,
-                                        ndx == 3 ? dxi - 1 : 0, ndx == 3 ? h0 - 1 : h0, b);
+                            if (elect_one_sync()) {
+                                mbar_expect_tx(&bars->a_full[st], p.a_bytes);
+                                tma_load_4d(sA + size_t(st) * p.a_stage_bytes, &p.seg[s].tmA, &bars->a_full[st], cb * 64,
+                                            ndx == 3 ? dxi - 1 : 0, ndx == 3 ? h0 - 1 : h0, b);
+                            }
+                            __syncwarp();
                             if (++st == p.a_stages) st = 0, ph ^= 1;
                         }
                 }
@@ -111,7 +115,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ W producer: (block, dx, dy) order
-        if (lane == 0) {
+        {
             int st = 0;
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -123,9 +127,12 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
                             for (int dyi = 0; dyi < nd; ++dyi) {
                                 const int tap = dyi * 3 + dxi;  // (0 for a 1x1 segment)
                                 mbar_wait(&bars->w_empty[st], ph ^ 1);
-                                mbar_expect_tx(&bars->w_full[st], p.w_bytes);
-                                tma_load_2d(sW + size_t(st) * p.w_stage_bytes, &p.seg[s].tmW, &bars->w_full[st],
-                                            cb * 64, tap * p.Cout + n0);
+                                if (elect_one_sync()) {
+                                    mbar_expect_tx(&bars->w_full[st], p.w_bytes);
+                                    tma_load_2d(sW + size_t(st) * p.w_stage_bytes, &p.seg[s].tmW, &bars->w_full[st],
+                                                cb * 64, tap * p.Cout + n0);
+                                }
+                                __syncwarp();
                                 if (++st == p.w_stages) st = 0, ph ^= 1;
                             }
                 }
@@ -133,10 +140,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
         }
     } else if (warp == 2 || warp == 3) {
         // ------------------------------------------------------------------ MMA issuers: warp 2 -> M half 0, warp 3 -> 1
-        // One thread's tcgen05.mma stream runs at ~145 cycles per instruction whatever N is (measured with the phase
-        // trace of tools/igemm_test.cu, profiles/r01_mma_issue.txt); streams of different warps overlap, so the two
-        // halves of a tile are issued by two warps.
-        if (lane == 0) {
+        // (whole warp converged, MMAs / commits under elect.sync: see elect_one_sync in ptx.cuh)
+        {
             const int mhalf = warp - 2;
             const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
             const uint32_t row_bytes = uint32_t(p.W) * 128u;  // one image row of a box (multiple of 1024)
@@ -163,19 +168,23 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
                                 const uint64_t dB =
                                     make_smem_desc_sw128(smem_u32(sW + size_t(sw) * p.w_stage_bytes), 16, 1024);
                                 const uint64_t dA = make_smem_desc_sw128(a0 + uint32_t(mhalf) * 16384u, 16, 1024);
+                                if (elect_one_sync()) {
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    umma_bf16(d0 + uint32_t(mhalf * p.BN), dA + uint64_t(k * 2), dB + uint64_t(k * 2), idesc,
-                                              (!first || k != 0) ? 1u : 0u);
+                                    for (int k = 0; k < 4; ++k)
+                                        umma_bf16(d0 + uint32_t(mhalf * p.BN), dA + uint64_t(k * 2), dB + uint64_t(k * 2),
+                                                  idesc, (!first || k != 0) ? 1u : 0u);
+                                    umma_commit(&bars->w_empty[sw]);
+                                    if (dyi == nd - 1) umma_commit(&bars->a_empty[sa]);
+                                }
+                                __syncwarp();
                                 first = false;
-                                umma_commit(&bars->w_empty[sw]);
                                 if (++sw == p.w_stages) sw = 0, pw ^= 1;
                             }
-                            umma_commit(&bars->a_empty[sa]);
                             if (++sa == p.a_stages) sa = 0, pa ^= 1;
                         }
                 }
-                umma_commit(&bars->t_full[buf]);
+                if (elect_one_sync()) umma_commit(&bars->t_full[buf]);
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {

@@ -12,6 +12,27 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Warp-converged single-lane election, written exactly like CUTLASS's elect_one_sync so that ptxas recognises it.
+// Use as `if (elect_one_sync()) { tcgen05.mma ...; tcgen05.commit ...; }` from code the WHOLE warp executes: descriptors
+// computed in converged code live in uniform registers and the UTCHMMA / UTMALDG / UTCBAR are issued back to back.
+// The same instructions issued from a lane-divergent region (`if (lane == 0) { ... }`) are each wrapped by ptxas in a
+// waterfall loop (ELECT / R2UR.BROADCAST / BRA.U.ANY) that costs ~145 cycles per instruction -- what round 1 took for a
+// hardware issue limit (tools/mma_issue_bench.cu, profiles/r02_mma_issue_bench.txt).
+__device__ __forceinline__ uint32_t elect_one_sync() {
+    uint32_t pred = 0, laneid = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 %%rx;\n\t"
+        ".reg .pred %%px;\n\t"
+        "elect.sync %%rx|%%px, %2;\n\t"
+        "@%%px mov.s32 %1, 1;\n\t"
+        "mov.s32 %0, %%rx;\n\t"
+        "}\n"
+        : "+r"(laneid), "+r"(pred)
+        : "r"(0xFFFFFFFF));
+    return pred;
+}
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
     asm volatile(
