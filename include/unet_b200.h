@@ -38,6 +38,14 @@ const char* ub_last_error(void);
 const char* ub_version(void);
 /* stream used by the layer operators; `stream` is a cudaStream_t */
 int ub_set_stream(void* stream);
+/* Arithmetic of the layer operators' contractions (3x3 / 1x1 convolution, linear):
+ *   UB_PRECISION_BF16 (default): bf16 operands on the tcgen05 tensor cores, fp32 accumulation -- the fast path;
+ *   UB_PRECISION_FP32          : exact fp32 CUDA-core kernels of this library (slow; a validation mode: the
+ *                                reference's own self-tests, dev/resblock.cu:542-630, compare at 1e-5 / 1e-4 absolute).
+ * The environment variable UB_LAYER_PRECISION=fp32|bf16 sets the initial value.  Returns the previous mode. */
+#define UB_PRECISION_BF16 0
+#define UB_PRECISION_FP32 1
+int ub_set_layer_precision(int mode);
 /* number of kernels launched by this library since process start (bench.py's gpu_launches) */
 unsigned long long ub_launch_count(void);
 

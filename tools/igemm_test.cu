@@ -192,6 +192,7 @@ static bool test_conv(int B, int H, int W, int Cin, int Cout, int ntaps, int Cin
     }
 #ifdef UB_TRACE
     if (!halo && reps > 0) igemm_trace_dump(p.tiles_w * p.tiles_h * p.tiles_b * (p.Cout / p.BN), 1.965);
+    if (halo && reps > 0) igemm_rows_trace_dump(std::min(ph.num_tiles, 148), ph.num_tiles);
 #endif
     if (dstats) cudaFree(dstats);
     double flops = 2.0 * npix * Cout * (double(ntaps) * Cin + Cin2);

@@ -69,14 +69,17 @@ __global__ void __launch_bounds__(64) ingest(const __grid_constant__ CUtensorMap
         int st = 0;
         uint32_t ph = 0;
         // every CTA walks the tensor from its own offset (distinct rows per CTA per iteration, wrapping around)
-        long long row = (long long)blockIdx.x * p.boxes * p.rows;
+        // (32-bit, power-of-two wrap: a 64-bit modulo here cost ~220 cycles per box and WAS the measured "limit" in the
+        //  first version of this tool)
+        uint32_t row = blockIdx.x * p.boxes * p.rows;
+        const uint32_t mask = (uint32_t)p.total_rows - 1u;  // total_rows is a power of two, rows divides it
         for (int it = 0; it < p.iters; ++it) {
             mbar_wait(smem_u32(&empty[st]), ph ^ 1);
             if (elect_one_sync()) {
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[st])), "r"(stage_bytes)
                              : "memory");
                 for (int b = 0; b < p.boxes; ++b) {
-                    const int r = (int)((row + (long long)b * p.rows) % (p.total_rows - p.rows));
+                    const int r = (int)((row + (uint32_t)b * p.rows) & mask);
                     asm volatile(
                         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
                             smem_u32(smem + (size_t)st * stage_bytes + (size_t)b * box_bytes)),
@@ -85,7 +88,7 @@ __global__ void __launch_bounds__(64) ingest(const __grid_constant__ CUtensorMap
                 }
             }
             __syncwarp();
-            row += (long long)gridDim.x * p.boxes * p.rows;
+            row += gridDim.x * p.boxes * p.rows;
             if (++st == p.stages) st = 0, ph ^= 1;
         }
     } else {
@@ -124,9 +127,9 @@ int main() {
 
     struct Cfg { int stages, boxes, rows; };
     const Cfg cfgs[] = {{2, 1, 128}, {4, 1, 128}, {6, 1, 128}, {8, 1, 128}, {12, 1, 128}, {3, 3, 128}, {4, 3, 128},
-                        {4, 1, 256}, {6, 1, 256}, {3, 2, 256}, {8, 1, 64}, {16, 1, 64}, {4, 2, 192}};
+                        {4, 1, 256}, {6, 1, 256}, {3, 2, 256}, {8, 1, 64}, {16, 1, 64}, {2, 3, 256}, {6, 2, 128}, {4, 2, 128}};
     for (int ws = 0; ws < 2; ++ws) {
-        const size_t rows_total = ws == 0 ? ((size_t)48 << 20) / 128 : big_rows;  // 48 MiB (L2 resident) or 2 GiB (DRAM)
+        const size_t rows_total = ws == 0 ? ((size_t)32 << 20) / 128 : big_rows;  // 32 MiB (L2 resident) or 2 GiB (DRAM)
         for (int grid : {nsm, 64, 16}) {
             for (const Cfg& c : cfgs) {
                 IP p{c.stages, c.boxes, c.rows, 0, (int)rows_total};

@@ -189,6 +189,7 @@ size_t igemm_wgrad_partial_floats(int Cin, int Cout, int ntaps, int nsplit);
 #ifdef UB_TRACE
 void igemm_trace_dump(int nctas, double clock_ghz);  // phase timeline of the last igemm_conv_kernel launch
 void igemm_trace_set_mode(int m);                    // 0 normal, 1 TMA stream only, 2 MMA stream only
+void igemm_rows_trace_dump(int nctas, int ntiles_total);  // per-tile phase timeline of the last igemm_rows_kernel launch
 #endif
 
 }  // namespace ub

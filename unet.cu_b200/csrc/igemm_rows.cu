@@ -26,13 +26,56 @@
 
 #include <cstdio>
 #include <cstring>
+#ifdef UB_TRACE
+#include <algorithm>
+#include <vector>
+#endif
 
 namespace ub {
 
 static constexpr int kRowsThreads = 384;
 static constexpr int kRowsEpiThreads = 256;
 static constexpr int kMaxAStages = 4;
-static constexpr int kMaxWStages = 8;
+static constexpr int kMaxWStages = 16;
+
+// Phase timeline of igemm_rows_kernel (development only: -DUB_TRACE, build/igemm_trace shape ... halo=1).  Per CTA and
+// per tile of its schedule: SM clock (relative to CTA entry) at
+//   [0] A producer: first box issued  [1] last box issued  [2] W producer: last tile issued
+//   [3] MMA warp: accumulator buffer free (t_empty)  [4] first A box landed  [5] last MMA issued
+//   [6] epilogue: accumulator complete (t_full)  [7] epilogue done
+#ifdef UB_TRACE
+static constexpr int kRTiles = 6, kRSlots = 8, kRCtas = 160;
+__device__ unsigned long long g_rows_trace[kRCtas * kRTiles * kRSlots];
+__device__ unsigned long long g_rows_t0[kRCtas];
+#define UB_RTR(tile_i, slot)                                                                               \
+    do {                                                                                                   \
+        if ((threadIdx.x & 31) == 0 && int(blockIdx.x) < kRCtas && (tile_i) < kRTiles)                     \
+            g_rows_trace[(int(blockIdx.x) * kRTiles + (tile_i)) * kRSlots + (slot)] = clock64();            \
+    } while (0)
+void igemm_rows_trace_dump(int nctas, int ntiles_total) {
+    std::vector<unsigned long long> h(size_t(kRCtas) * kRTiles * kRSlots), t0(kRCtas);
+    cudaMemcpyFromSymbol(h.data(), g_rows_trace, h.size() * 8);
+    cudaMemcpyFromSymbol(t0.data(), g_rows_t0, t0.size() * 8);
+    nctas = std::min(nctas, kRCtas);
+    const char* names[kRSlots] = {"A first box issued", "A last box issued", "W last tile issued", "MMA: tmem buffer free",
+                                  "MMA: first A landed", "MMA: last MMA issued", "EPI: accumulator ready", "EPI: done"};
+    for (int t = 0; t < kRTiles; ++t) {
+        int n = 0;
+        double sum[kRSlots] = {0};
+        for (int c = 0; c < nctas; ++c) {
+            if (c + t * nctas >= ntiles_total) continue;
+            ++n;
+            for (int k = 0; k < kRSlots; ++k) sum[k] += double(h[(size_t(c) * kRTiles + t) * kRSlots + k] - t0[c]);
+        }
+        if (!n) break;
+        printf("  rows trace, tile #%d of the CTA (%d CTAs):", t, n);
+        for (int k = 0; k < kRSlots; ++k) printf("  %s %.0f", names[k], sum[k] / n);
+        printf("\n");
+    }
+}
+#else
+#define UB_RTR(tile_i, slot) do {} while (0)
+#endif
 
 struct RowsBars {
     uint64_t a_full[kMaxAStages], a_empty[kMaxAStages];
@@ -41,10 +84,12 @@ struct RowsBars {
     uint32_t tmem_slot;
     uint32_t pad_[3];
 };
-// smem tail behind the rings (floats): comb[2][BN] | gconst[2][4][BN] | red[8][BN][2] | tr[8][32*36]
+// smem tail behind the rings (floats): comb[2][BN] | gconst[2][4][BN] | red[8][BN][2]
+// (+ tr[8][32*36], the per-warp transpose scratch, only in the UB_EPI_SHUFFLE_REDUCE=0 experiment build: its 36 KiB are
+//  four more weight stages in the default build, which is what hides the ~1300-cycle TMA latency, r02b_rows_trace)
 // (16 epilogue warps -- a column split on top of quadrant x half -- measured 20 % slower: the 102-register cap of a
-// 640-thread CTA spills in the hooked chunk; two-pass 20-float transposes measured 2 % slower than this layout)
-static size_t rows_tail_floats(int BN) { return size_t(2 + 8 + 16) * BN + 8 * 32 * 36; }
+// 640-thread CTA spills in the hooked chunk)
+static size_t rows_tail_floats(int BN) { return size_t(2 + 8 + 16) * BN + (UB_EPI_SHUFFLE_REDUCE ? 0 : 8 * 32 * 36); }
 
 __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __grid_constant__ IgemmRowsParams p) {
     pdl_trigger();
@@ -60,6 +105,9 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_mb = p.B * p.tiles_per_img;  // pixel tiles; the N tile is the slow index of the schedule
+#ifdef UB_TRACE
+    if (threadIdx.x == 0 && int(blockIdx.x) < kRCtas) g_rows_t0[blockIdx.x] = clock64();
+#endif
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.nseg; ++s) {
@@ -94,7 +142,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
         {
             int st = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            int ti = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
                 const int mt = tile % tiles_mb;
                 const int b = mt / p.tiles_per_img, h0 = (mt % p.tiles_per_img) * p.TH;
                 for (int s = 0; s < p.nseg; ++s) {
@@ -102,6 +151,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
                     for (int cb = 0; cb < p.seg[s].cblocks; ++cb)
                         for (int dxi = 0; dxi < ndx; ++dxi) {
                             mbar_wait(&bars->a_empty[st], ph ^ 1);
+                            if (s == 0 && cb == 0 && dxi == 0) UB_RTR(ti, 0);
+                            UB_RTR(ti, 1);
                             if (elect_one_sync()) {
                                 mbar_expect_tx(&bars->a_full[st], p.a_bytes);
                                 tma_load_4d(sA + size_t(st) * p.a_stage_bytes, &p.seg[s].tmA, &bars->a_full[st], cb * 64,
@@ -118,7 +169,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
         {
             int st = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            int ti = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
                 const int n0 = (tile / tiles_mb) * p.BN;
                 for (int s = 0; s < p.nseg; ++s) {
                     const int nd = p.seg[s].ntaps == 9 ? 3 : 1;
@@ -127,6 +179,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
                             for (int dyi = 0; dyi < nd; ++dyi) {
                                 const int tap = dyi * 3 + dxi;  // (0 for a 1x1 segment)
                                 mbar_wait(&bars->w_empty[st], ph ^ 1);
+                                UB_RTR(ti, 2);
                                 if (elect_one_sync()) {
                                     mbar_expect_tx(&bars->w_full[st], p.w_bytes);
                                     tma_load_2d(sW + size_t(st) * p.w_stage_bytes, &p.seg[s].tmW, &bars->w_full[st],
@@ -151,6 +204,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
                 mbar_wait(&bars->t_empty[buf], ((it >> 1) & 1) ^ 1);
+                if (mhalf == 0) UB_RTR(it, 3);
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + uint32_t(buf * 2 * p.BN);
                 bool first = true;
@@ -159,6 +213,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
                     for (int cb = 0; cb < p.seg[s].cblocks; ++cb)
                         for (int dxi = 0; dxi < nd; ++dxi) {
                             mbar_wait(&bars->a_full[sa], pa);
+                            if (mhalf == 0 && first) UB_RTR(it, 4);
                             tc_fence_after();
                             const uint32_t a_base = smem_u32(sA + size_t(sa) * p.a_stage_bytes);
                             for (int dyi = 0; dyi < nd; ++dyi) {
@@ -183,6 +238,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
                             if (++sa == p.a_stages) sa = 0, pa ^= 1;
                         }
                 }
+                if (mhalf == 0) UB_RTR(it, 5);
                 if (elect_one_sync()) umma_commit(&bars->t_full[buf]);
                 __syncwarp();
             }
@@ -227,6 +283,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
             uint4 side[2];
             if (hook) epi_side_load(eo, valid, pix, n0, side);  // hidden behind the tile's main loop
             mbar_wait(&bars->t_full[buf], (it >> 1) & 1);
+            if (warp == 4) UB_RTR(it, 6);
             if (tile + int(gridDim.x) >= p.num_tiles) pdl_trigger_late();  // last tile of this CTA
             tc_fence_after();
             const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * 2 * p.BN + half * p.BN);
@@ -235,6 +292,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
             // all TMEM reads of this buffer are complete (tcgen05.wait::ld above): hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
+            if (warp == 4) UB_RTR(it, 7);
             if (lane == 0) mbar_arrive(&bars->t_empty[buf]);
             if (hook) {  // the 8 warps' column sums of this tile (one image) -> one vector RED per channel
                 named_bar_sync(2, kRowsEpiThreads);
@@ -337,8 +395,14 @@ int igemm_rows_plan(IgemmRowsParams* p, const ConvSegDesc* segs, int nseg, int B
     }
     if (as < 2 || ws < 2) return -3;
     if (ws > kMaxWStages) ws = kMaxWStages;
-    // spare room goes to a 4th A stage
-    if (as == 3 && size_t(4) * p->a_stage_bytes + size_t(ws) * p->w_stage_bytes <= budget) as = 4;
+    // The weight ring must cover the TMA round trip (~1300 cycles L2 hit + transfer, profiles/r02b_rows_trace.txt): with 4
+    // stages of 8 KiB the W producer paced the 64-channel layers at ~700 cycles per (dx, dy) step against 384 cycles of
+    // MMA work.  Spare room beyond 8 weight stages goes to a 4th A stage.
+    if (as == 3 && ws > 8 && size_t(4) * p->a_stage_bytes + size_t(8) * p->w_stage_bytes <= budget) {
+        as = 4;
+        ws = int((budget - size_t(4) * p->a_stage_bytes) / p->w_stage_bytes);
+        if (ws > kMaxWStages) ws = kMaxWStages;
+    }
     p->a_stages = as, p->w_stages = ws;
     for (int s = 0; s < nseg; ++s) {
         const ConvSegDesc& d = segs[s];

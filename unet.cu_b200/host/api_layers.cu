@@ -9,6 +9,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "../../include/unet_b200.h"
@@ -72,8 +73,19 @@ int pack_one(const float* w, bf16* wf, bf16* wd, int Cout, int Cin, int ntaps, c
     return UB_OK;
 }
 
-bool tensor_fprop_ok(int Cin, int Cout) { return Cin % 8 == 0 && Cout % 16 == 0; }
-bool tensor_wgrad_ok(int Cin, int Cout) { return Cin % 64 == 0 && Cout % 64 == 0; }
+// ub_set_layer_precision(): -1 = not yet read from the environment
+int g_precision = -1;
+bool fp32_mode() {
+    if (g_precision < 0) {
+        const char* e = getenv("UB_LAYER_PRECISION");
+        g_precision = (e && (e[0] == 'f' || e[0] == 'F')) ? UB_PRECISION_FP32 : UB_PRECISION_BF16;
+    }
+    return g_precision == UB_PRECISION_FP32;
+}
+bool shape_fprop_ok(int Cin, int Cout) { return Cin % 8 == 0 && Cout % 16 == 0; }
+bool shape_wgrad_ok(int Cin, int Cout) { return Cin % 64 == 0 && Cout % 64 == 0; }
+bool tensor_fprop_ok(int Cin, int Cout) { return !fp32_mode() && shape_fprop_ok(Cin, Cout); }
+bool tensor_wgrad_ok(int Cin, int Cout) { return !fp32_mode() && shape_wgrad_ok(Cin, Cout); }
 
 // generic convolution forward, KS = 1 or 3
 int conv_forward(const float* x, const float* weight, const float* bias, float* out, int B, int Cin, int Cout, int H,
@@ -177,6 +189,11 @@ int conv_backward(const float* dout, const float* x, const float* weight, float*
 }  // namespace
 
 extern "C" {
+int ub_set_layer_precision(int mode) {
+    const int prev = fp32_mode() ? UB_PRECISION_FP32 : UB_PRECISION_BF16;
+    g_precision = mode == UB_PRECISION_FP32 ? UB_PRECISION_FP32 : UB_PRECISION_BF16;
+    return prev;
+}
 
 int ub_conv2d_k3_forward3(const float* x, const float* weight, const float* bias, float* out, int B, int C_in,
                           int C_out, int H, int W) {
@@ -399,7 +416,7 @@ int ub_pack_conv_weight(const float* weight, void* wf, void* wd, int C_in, int C
 }
 int ub_conv2d_nhwc_forward(const void* x, const void* wf, const float* bias, void* out, int B, int H, int W, int C_in,
                            int C_out, int ksize) {
-    if (!tensor_fprop_ok(C_in, C_out)) {
+    if (!shape_fprop_ok(C_in, C_out)) {
         fail("conv2d_nhwc_forward needs C_in %% 8 == 0 and C_out %% 16 == 0");
         return UB_ERR_SHAPE;
     }
@@ -417,7 +434,7 @@ int ub_conv2d_nhwc_forward(const void* x, const void* wf, const float* bias, voi
 }
 int ub_conv2d_nhwc_dgrad(const void* dout, const void* wd, void* dx, int B, int H, int W, int C_in, int C_out,
                          int ksize) {
-    if (!tensor_fprop_ok(C_out, C_in)) {
+    if (!shape_fprop_ok(C_out, C_in)) {
         fail("conv2d_nhwc_dgrad needs C_out %% 8 == 0 and C_in %% 16 == 0");
         return UB_ERR_SHAPE;
     }
@@ -435,7 +452,7 @@ int ub_conv2d_nhwc_dgrad(const void* dout, const void* wd, void* dx, int B, int 
 }
 int ub_conv2d_nhwc_wgrad(const void* dout, const void* x, float* dweight, float* dbias, int B, int H, int W, int C_in,
                          int C_out, int ksize) {
-    if (!tensor_wgrad_ok(C_in, C_out)) {
+    if (!shape_wgrad_ok(C_in, C_out)) {
         fail("conv2d_nhwc_wgrad needs C_in %% 64 == 0 and C_out %% 64 == 0");
         return UB_ERR_SHAPE;
     }

@@ -380,7 +380,12 @@ struct Builder {
         float *chsum, *S;
     };
     // statistics buffer of a tensor whose producer (a conv epilogue) accumulates them
-    float* stats_buf(int C) { return zf32(size_t(B) * C * 2); }
+    // UB_GN_HOOKS=0: no GroupNorm work in the conv epilogues (statistics / gn-bwd pre-pass come from the GroupNorm kernels)
+    static bool gn_hooks() {
+        static const bool on = !(getenv("UB_GN_HOOKS") && atoi(getenv("UB_GN_HOOKS")) == 0);
+        return on;
+    }
+    float* stats_buf(int C) { return gn_hooks() ? zf32(size_t(B) * C * 2) : nullptr; }
     GN gn_fwd(View x, View y, int silu) {
         GN g;
         g.w = take(x.C), g.b = take(x.C);
@@ -399,10 +404,12 @@ struct Builder {
     // Fuse the first half of GroupNorm(+SiLU) backward into the epilogue of the dgrad conv that produces dL/dy:
     // that conv then writes dz = dL/d gn(x) and accumulates S (see epilogue.cuh); call gn_bwd(..., fused = true) after.
     void gn_hook(ConvEpilogue& ep, const GN& g, View x, int silu) {
+        if (!gn_hooks()) return;
         ep.gn_x = x.p, ep.gn_ldx = x.ld, ep.gn_chsum = g.chsum, ep.gn_gamma = P(g.w), ep.gn_beta = P(g.b);
         ep.gn_S = g.S, ep.gn_silu = silu, ep.gn_groups = c.gn_n_groups;
     }
     void gn_bwd(const GN& g, View x, View dy, int silu, View add_in, View dx, float* colsum_out, bool fused = false) {
+        fused = fused && gn_hooks();
         const int HW = x.H * x.W, Gn = c.gn_n_groups, Bn = B;
         float *gw = P(g.w), *gb = P(g.b), *cs = g.chsum, *S = g.S, *dgw = G(g.w), *dgb = G(g.b);
         const int mode = fused ? (silu ? 2 : 0) : silu;
