@@ -192,6 +192,18 @@ int ub_conv2d_nhwc_dgrad(const void* dout_bf16, const void* wd_bf16, void* dx_bf
 int ub_conv2d_nhwc_wgrad(const void* dout_bf16, const void* x_bf16, float* dweight, float* dbias, int B, int H, int W,
                          int C_in, int C_out, int ksize);
 
+/* GroupNorm (+ optional SiLU) in the native layout (what the trainer runs; replaces groupnorm_forward / groupnorm_backward
+ * fused with silu_forward / silu_backward, dev/groupnorm.cuh:3-13, dev/silu.cuh:3-13): x, y, dy, dx are NHWC bf16 [B*H*W][C].
+ * Single-pass "slab" kernels when the shape allows (C % 16 == 0; impl = 0), two-pass kernels otherwise / when impl = 1.
+ * chsum [B][C][2] fp32 = per-(image, channel) sum and sum of squares: written by forward, read by backward.
+ * backward: dy = dL/d act(gn(x)); dx = gn_bwd(dy) (+ add_in if non-NULL); dweight / dbias (C) are ACCUMULATED into, like
+ * the reference's groupnorm_backward (train_unet.cu:1926-1991); scratch [B][C][2] fp32 is used by impl 1 only. */
+int ub_groupnorm_nhwc_forward(const void* x_bf16, const float* weight, const float* bias, void* y_bf16, float* chsum,
+                              int B, int H, int W, int C, int n_groups, int silu, int impl);
+int ub_groupnorm_nhwc_backward(const void* x_bf16, const void* dy_bf16, const float* chsum, const float* weight,
+                               const float* bias, const void* add_in_bf16, void* dx_bf16, float* dweight, float* dbias,
+                               float* scratch, int B, int H, int W, int C, int n_groups, int silu, int impl);
+
 /* Attention core in the native layout (what the trainer runs; replaces attention_forward1 / attention_backward,
  * dev/attention.cuh:6-22, without their permutes and (B,NH,T,T) matrices): qkv is NHWC bf16 [B*T][3C], channel order
  * [Q | K | V], each [NH][32]; out [B*T][C] bf16; lse [B][NH][T] fp32 (log2-domain logsumexp, saved for backward).

@@ -42,9 +42,10 @@ __device__ __forceinline__ void pdl_trigger_late() {
 }
 // the usual kernel entry: let the dependent grid start early, then wait for our own prerequisite
 // (UB_PDL_ELT_EARLY: entry trigger only in the elementwise / normalisation kernels, whose CTAs hold no shared memory
-//  or TMEM that an early-resident dependent could be starved of)
+//  or TMEM that an early-resident dependent could be starved of.  Measured round 2, bench.py B = 32: 5.09 ms/step with,
+//  5.18 without -- the launch latency of every kernel that follows a GroupNorm / data-movement kernel was exposed.)
 #ifndef UB_PDL_ELT_EARLY
-#define UB_PDL_ELT_EARLY 0
+#define UB_PDL_ELT_EARLY 1
 #endif
 __device__ __forceinline__ void pdl_entry() {
 #if UB_PDL_ELT_EARLY

@@ -1019,6 +1019,7 @@ void nhwc_ops_init() {
     if (done) return;
     cudaFuncSetAttribute(smallc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(smallc_wgrad_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    gn_slab_init();
     done = true;
 }
 static void smallc_wgrad(const float* xs, const bf16* yb, int ldy, int B, int Cs, int Cb, int H, int W, int mode,

@@ -30,6 +30,20 @@ void gn_bwd_apply(const bf16* x, int ldx, const bf16* dy, int lddy, const float*
                   const float* gamma, const float* beta, int B, int HW, int C, int G, int silu, const bf16* add_in,
                   int ldadd, bf16* dx, int lddx, float* dgamma, float* dbeta, float* colsum_out, cudaStream_t st);
 
+// ---- single-pass GroupNorm (csrc/gn_slab.cu): statistics + normalisation (+SiLU) in ONE kernel, the slab (image, whole
+//      groups of channels) held in registers in between: 1R + 1W forward, 2R (+1R) + 1W backward.  Return -1 when the
+//      shape is not supported (channel count not a multiple of 16, slab too large): use the two-pass kernels above.
+bool gn_slab_supported(int B, int HW, int C, int G, bool backward);
+bool gn_slab_preferred(int B, int HW, int C, int G);  // supported AND measured faster than the two-pass kernels
+void gn_slab_init();  // opt-in shared memory attributes; called by nhwc_ops_init() (before graph capture)
+// y = act(gn(x)); chsum[B][C][2] receives the per-(image, channel) sum / sum of squares (overwritten, for the backward)
+int gn_slab_fwd(const bf16* x, int ldx, const float* gamma, const float* beta, int B, int HW, int C, int G, int silu,
+                bf16* y, int ldy, float* chsum, cudaStream_t st);
+// dx = gn_bwd(dy) [+ add_in]; dy = dL/d act(gn(x)) (silu: 0 identity, 1 SiLU); dgamma/dbeta += ; colsum_out[B][C] += sum_pix dx
+int gn_slab_bwd(const bf16* x, int ldx, const bf16* dy, int lddy, const float* chsum, const float* gamma,
+                const float* beta, int B, int HW, int C, int G, int silu, const bf16* add_in, int ldadd, bf16* dx,
+                int lddx, float* dgamma, float* dbeta, float* colsum_out, cudaStream_t st);
+
 // ---- data movement (replace avgpool/upsample/concat/add of train_unet.cu:187-627)
 void avgpool2_fwd(const bf16* x, int ldx, int B, int H, int W, int C, bf16* y, int ldy, cudaStream_t st);
 // dx (H x W) = dy (H/2 x W/2) / 4 [+ add_in]

@@ -414,6 +414,53 @@ int ub_pack_conv_weight(const float* weight, void* wf, void* wd, int C_in, int C
     if (pack_one(weight, (bf16*)wf, (bf16*)wd, C_out, C_in, ksize * ksize, ub_layer_stream())) return UB_ERR_CUDA;
     return finish(1);
 }
+int ub_groupnorm_nhwc_forward(const void* x, const float* weight, const float* bias, void* y, float* chsum, int B, int H,
+                              int W, int C, int n_groups, int silu, int impl) {
+    if (n_groups < 1 || C % n_groups || C % 8) {
+        fail("groupnorm_nhwc: needs C %% n_groups == 0 and C %% 8 == 0");
+        return UB_ERR_SHAPE;
+    }
+    cudaStream_t st = ub_layer_stream();
+    const int HW = H * W;
+    if (impl == 0 && gn_slab_supported(B, HW, C, n_groups, false)) {
+        if (gn_slab_fwd((const bf16*)x, C, weight, bias, B, HW, C, n_groups, silu, (bf16*)y, C, chsum, st)) {
+            fail("groupnorm_nhwc_forward: slab launch rejected (alignment)");
+            return UB_ERR_SHAPE;
+        }
+        return finish(1);
+    }
+    cudaMemsetAsync(chsum, 0, size_t(B) * C * 2 * sizeof(float), st);
+    gn_stats((const bf16*)x, C, B, HW, C, chsum, st);
+    gn_apply((const bf16*)x, C, chsum, weight, bias, B, HW, C, n_groups, silu, (bf16*)y, C, nullptr, st);
+    return finish(2);
+}
+int ub_groupnorm_nhwc_backward(const void* x, const void* dy, const float* chsum, const float* weight, const float* bias,
+                               const void* add_in, void* dx, float* dweight, float* dbias, float* scratch, int B, int H,
+                               int W, int C, int n_groups, int silu, int impl) {
+    if (n_groups < 1 || C % n_groups || C % 8) {
+        fail("groupnorm_nhwc: needs C %% n_groups == 0 and C %% 8 == 0");
+        return UB_ERR_SHAPE;
+    }
+    cudaStream_t st = ub_layer_stream();
+    const int HW = H * W;
+    if (impl == 0 && gn_slab_supported(B, HW, C, n_groups, true)) {
+        if (gn_slab_bwd((const bf16*)x, C, (const bf16*)dy, C, chsum, weight, bias, B, HW, C, n_groups, silu,
+                        (const bf16*)add_in, C, (bf16*)dx, C, dweight, dbias, nullptr, st)) {
+            fail("groupnorm_nhwc_backward: slab launch rejected (alignment)");
+            return UB_ERR_SHAPE;
+        }
+        return finish(1);
+    }
+    if (!scratch) {
+        fail("groupnorm_nhwc_backward: the two-pass path needs scratch [B][C][2]");
+        return UB_ERR_SHAPE;
+    }
+    cudaMemsetAsync(scratch, 0, size_t(B) * C * 2 * sizeof(float), st);
+    gn_bwd_stats((const bf16*)x, C, (const bf16*)dy, C, chsum, weight, bias, B, HW, C, n_groups, silu, scratch, st);
+    gn_bwd_apply((const bf16*)x, C, (const bf16*)dy, C, chsum, scratch, weight, bias, B, HW, C, n_groups, silu,
+                 (const bf16*)add_in, C, (bf16*)dx, C, dweight, dbias, nullptr, st);
+    return finish(2);
+}
 int ub_conv2d_nhwc_forward(const void* x, const void* wf, const float* bias, void* out, int B, int H, int W, int C_in,
                            int C_out, int ksize) {
     if (!shape_fprop_ok(C_in, C_out)) {

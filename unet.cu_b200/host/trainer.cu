@@ -105,6 +105,15 @@ struct UbTrainer {
     // they run on a side stream, concurrently with the dgrad -> GroupNorm -> dgrad critical path of backward (in the
     // captured graph this is a parallel branch).  Both kinds of kernel are latency-bound on their own.
     cudaStream_t side_stream = nullptr;
+    // Micro-batch pipelining: the main-stream ops that work image by image (conv fprop / dgrad, GroupNorm, attention,
+    // data movement) are emitted once per micro-batch of B / n_mb images -- batch-major views of the same buffers -- and
+    // micro-batch h > 0 runs on mb_streams[h - 1], a parallel branch of the captured graph.  The step is ~40 % batch-
+    // independent latency at B = 32 (5.17 ms at B = 32, 3.69 at 16, 2.96 at 8: profiles/r02_microbatch.txt); the idea
+    // was that two independent chains hide each other's latency.  They do not (5.30 ms with two chains): an experiment
+    // switch (UB_MICROBATCH), off by default.  Ops that need the whole batch (weight gradients on the side stream, loss,
+    // optimizer) join the chains first.
+    int n_mb = 1;
+    std::vector<cudaStream_t> mb_streams;
     std::vector<cudaEvent_t> side_events;
     size_t side_ev_next = 0;
     bool use_side = true;
@@ -153,6 +162,7 @@ struct UbTrainer {
         double bytes;   // ... or algorithmic bytes (memory-bound kernels)
         int side;       // 0 = main stream, 1 = weight-gradient branch (side stream), 2 = join marker
         std::string label;
+        int half = -1;  // >= 0: this op is micro-batch `half` of a per-image op (runs on that micro-batch's stream)
     };
     std::vector<OpInfo> fwd_info, bwd_info;
     int launches_fwd = 0, launches_bwd = 0, launches_misc = 0;
@@ -229,7 +239,32 @@ struct Builder {
     std::vector<Node> nodes;
     std::vector<View> skipgrad;  // per node: gradient arriving from the up path
 
-    explicit Builder(UbTrainer* t) : T(t), c(t->cfg), B(t->cfg.B) {}
+    // micro-batches (see UbTrainer::n_mb): nh chains of Bh images each
+    int nh = 1, Bh = 0;
+    int cur_half = -1;  // set while the ops of one micro-batch are being emitted (split())
+    explicit Builder(UbTrainer* t) : T(t), c(t->cfg), B(t->cfg.B) {
+        nh = t->n_mb > 0 && B % t->n_mb == 0 ? t->n_mb : 1;
+        Bh = B / nh;
+    }
+    // emit the same op for every micro-batch: fn(h) pushes the ops of micro-batch h (views offset with mb())
+    template <class Fn>
+    void split(Fn fn) {
+        std::string lbl = next_label;
+        for (int h = 0; h < nh; ++h) {
+            cur_half = nh > 1 ? h : -1;
+            next_label = lbl;
+            fn(h);
+        }
+        cur_half = -1;
+        next_label.clear();
+    }
+    // micro-batch h of a batch-major view / per-image fp32 table with `per_img` floats per image
+    View mb(View v, int h) const {
+        if (v.p) v.p += size_t(h) * Bh * v.H * v.W * v.ld;
+        if (v.cs) v.cs += size_t(h) * Bh * v.C * 2;
+        return v;
+    }
+    float* mbf(float* p, int h, size_t per_img) const { return p ? p + size_t(h) * Bh * per_img : nullptr; }
 
     size_t take(size_t n) {
         size_t o = poff;
@@ -255,7 +290,7 @@ struct Builder {
            int side = 0) {
         if (!real()) return;
         T->fwd_ops.push_back(std::move(op)), T->launches_fwd += launches;
-        T->fwd_info.push_back({kind, launches, flops, bytes, side, next_label}), next_label.clear();
+        T->fwd_info.push_back({kind, launches, flops, bytes, side, next_label, side == 0 ? cur_half : -1}), next_label.clear();
     }
     // forward: the time-embedding chain runs on the side stream until its first consumer (conv1 of the first ResBlock)
     bool fwd_side_pending = false;
@@ -267,7 +302,7 @@ struct Builder {
             int side = 0) {
         if (!real()) return;
         T->bwd_ops.push_back(std::move(op)), T->launches_bwd += launches;
-        T->bwd_info.push_back({kind, launches, flops, bytes, side, next_label}), next_label.clear();
+        T->bwd_info.push_back({kind, launches, flops, bytes, side, next_label, side == 0 ? cur_half : -1}), next_label.clear();
     }
     std::string next_label;  // optional description of the next op pushed (per-op profile dump)
     void label(const char* fmt, ...) {
@@ -312,32 +347,49 @@ struct Builder {
         double k = 0, bytes = act_bytes(Cout, H, W);
         for (auto& sg : segs) k += double(sg.ntaps) * sg.Cin, bytes += act_bytes(sg.Cin, H, W) + 2.0 * sg.ntaps * sg.Cin * Cout;
         const double flops = 2.0 * B * H * W * Cout * k;
-        UbTrainer::Op op;
-        // persistent row-tile kernel for the 16x16 .. 128x128 levels, one-CTA-per-128-pixels kernel otherwise
-        IgemmRowsParams pr;
-        if (!no_rows && igemm_rows_eligible(B, H, W, Cout) &&
-            igemm_rows_plan(&pr, segs.data(), int(segs.size()), B, H, W, Cout, ep, 148) == 0) {
-            op = [pr](cudaStream_t st) { igemm_rows_launch(pr, st); };
-            label("conv%s %s Cin=%d%s Cout=%d %dx%d rows BN=%d stages=%d/%d%s%s", segs[0].ntaps == 9 ? "3x3" : "1x1",
-                  fwd ? "fwd" : "dgrad", segs[0].Cin, segs.size() > 1 ? "+skip" : "", Cout, H, W, pr.BN, pr.a_stages,
-                  pr.w_stages, ep.stats ? " +stats" : "", ep.gn_x ? " +gnbwd" : "");
-        } else {
-            IgemmConvParams p;
-            int r = igemm_conv_plan(&p, segs.data(), int(segs.size()), B, H, W, Cout, ep);
-            if (r) {
-                set_err("igemm_conv_plan failed (%d) for %dx%d Cout=%d Cin0=%d", r, H, W, Cout, segs[0].Cin);
-                plan_errors++;
-                return;
+        // one launch per micro-batch: batch-major views of the same buffers (operands, output, residual, per-image
+        // embedding vector / GroupNorm statistics)
+        split([&](int h) {
+            std::vector<ConvSegDesc> sh = segs;
+            for (auto& sg : sh) sg.x += size_t(h) * Bh * H * W * sg.ldx;
+            ConvEpilogue eh = ep;
+            const size_t opix = size_t(h) * Bh * H * W;
+            eh.out = (bf16*)ep.out + opix * (ep.ldo ? ep.ldo : Cout);
+            if (ep.residual) eh.residual = ep.residual + opix * (ep.ldr ? ep.ldr : Cout);
+            eh.rowvec = mbf(const_cast<float*>(ep.rowvec), h, Cout);
+            eh.stats = mbf(ep.stats, h, size_t(Cout) * 2);
+            if (ep.gn_x) {
+                eh.gn_x = ep.gn_x + opix * ep.gn_ldx;
+                eh.gn_chsum = mbf(const_cast<float*>(ep.gn_chsum), h, size_t(Cout) * 2);
+                eh.gn_S = mbf(ep.gn_S, h, size_t(Cout) * 2);
             }
-            op = [p](cudaStream_t st) { igemm_conv_launch(p, st); };
-            label("conv%s %s Cin=%d%s Cout=%d %dx%d BN=%d stages=%d%s%s", segs[0].ntaps == 9 ? "3x3" : "1x1",
-                  fwd ? "fwd" : "dgrad", segs[0].Cin, segs.size() > 1 ? "+skip" : "", Cout, H, W, p.BN, p.stages,
-                  ep.stats ? " +stats" : "", ep.gn_x ? " +gnbwd" : "");
-        }
-        if (fwd)
-            F(op, 1, UB_KIND_CONV, flops, bytes);
-        else
-            Bk(op, 1, UB_KIND_CONV, flops, bytes);
+            UbTrainer::Op op;
+            // persistent row-tile kernel for the 16x16 .. 128x128 levels, one-CTA-per-128-pixels kernel otherwise
+            IgemmRowsParams pr;
+            if (!no_rows && igemm_rows_eligible(Bh, H, W, Cout) &&
+                igemm_rows_plan(&pr, sh.data(), int(sh.size()), Bh, H, W, Cout, eh, 148) == 0) {
+                op = [pr](cudaStream_t st) { igemm_rows_launch(pr, st); };
+                label("conv%s %s Cin=%d%s Cout=%d %dx%d rows BN=%d stages=%d/%d%s%s", segs[0].ntaps == 9 ? "3x3" : "1x1",
+                      fwd ? "fwd" : "dgrad", segs[0].Cin, segs.size() > 1 ? "+skip" : "", Cout, H, W, pr.BN, pr.a_stages,
+                      pr.w_stages, ep.stats ? " +stats" : "", ep.gn_x ? " +gnbwd" : "");
+            } else {
+                IgemmConvParams p;
+                int r = igemm_conv_plan(&p, sh.data(), int(sh.size()), Bh, H, W, Cout, eh);
+                if (r) {
+                    set_err("igemm_conv_plan failed (%d) for %dx%d Cout=%d Cin0=%d", r, H, W, Cout, segs[0].Cin);
+                    plan_errors++;
+                    return;
+                }
+                op = [p](cudaStream_t st) { igemm_conv_launch(p, st); };
+                label("conv%s %s Cin=%d%s Cout=%d %dx%d BN=%d stages=%d%s%s", segs[0].ntaps == 9 ? "3x3" : "1x1",
+                      fwd ? "fwd" : "dgrad", segs[0].Cin, segs.size() > 1 ? "+skip" : "", Cout, H, W, p.BN, p.stages,
+                      ep.stats ? " +stats" : "", ep.gn_x ? " +gnbwd" : "");
+            }
+            if (fwd)
+                F(op, 1, UB_KIND_CONV, flops / nh, bytes / nh);
+            else
+                Bk(op, 1, UB_KIND_CONV, flops / nh, bytes / nh);
+        });
     }
     // Weight (and bias) gradient of a conv / linear layer on the side stream.  Every CTA adds its tile into an fp32
     // accumulator with vector REDs; 3x3 layers accumulate in [tap][o][c] and are transposed into the reference
@@ -380,45 +432,92 @@ struct Builder {
         float *chsum, *S;
     };
     // statistics buffer of a tensor whose producer (a conv epilogue) accumulates them
-    // UB_GN_HOOKS=0: no GroupNorm work in the conv epilogues (statistics / gn-bwd pre-pass come from the GroupNorm kernels)
-    static bool gn_hooks() {
-        static const bool on = !(getenv("UB_GN_HOOKS") && atoi(getenv("UB_GN_HOOKS")) == 0);
-        return on;
+    // GroupNorm scheme (UB_GN_MODE), decided per tensor shape.  Measured round 2 (bench.py, B = 32, ms/step):
+    //   hooks 5.09 (default) | auto 5.23 | passes 5.47 | slab 6.05
+    //   hooks  statistics / gn-bwd pre-pass accumulated with atomics in the producing conv's epilogue + one apply pass
+    //          (costs ~0.5 ms per step inside the conv epilogues, profiles/r02d_ops_nohooks.txt, but every alternative
+    //          costs more on the GroupNorm side: the step is bound by kernel count x per-kernel latency, not bytes)
+    //   auto   single-pass slab kernels (csrc/gn_slab.cu: statistics + normalisation in one kernel, nothing in the conv
+    //          epilogues) wherever they beat the two-pass kernels stand-alone (gn_slab_preferred: below 64x64), hooks
+    //          elsewhere
+    //   slab   slab kernels wherever they are supported, `passes` elsewhere
+    //   passes separate statistics pass + apply pass, no hooks
+    static int gn_mode() {
+        static const int m = [] {
+            const char* e = getenv("UB_GN_MODE");
+            if (e && e[0] == 's') return 0;
+            if (e && e[0] == 'p') return 2;
+            if (e && e[0] == 'a') return 3;
+            return 1;
+        }();
+        return m;
     }
-    float* stats_buf(int C) { return gn_hooks() ? zf32(size_t(B) * C * 2) : nullptr; }
+    bool use_slab(int C, int H, int W) const {
+        const int m = gn_mode();
+        if (m == 0) return gn_slab_supported(Bh, H * W, C, c.gn_n_groups, false) && gn_slab_supported(Bh, H * W, C, c.gn_n_groups, true);
+        return m == 3 && gn_slab_preferred(Bh, H * W, C, c.gn_n_groups);
+    }
+    // does the conv that produces a (C, H, W) tensor accumulate its GroupNorm statistics / run the gn-bwd pre-pass?
+    bool use_hooks(int C, int H, int W) const {
+        const int m = gn_mode();
+        return m == 1 || (m == 3 && !use_slab(C, H, W));
+    }
+    float* stats_buf(int C, int H, int W) { return use_hooks(C, H, W) ? zf32(size_t(B) * C * 2) : nullptr; }
     GN gn_fwd(View x, View y, int silu) {
         GN g;
         g.w = take(x.C), g.b = take(x.C);
         const bool have = x.cs != nullptr;  // the producer's epilogue already accumulated the statistics
         g.chsum = have ? x.cs : zf32(size_t(B) * x.C * 2);
         g.S = zf32(size_t(B) * x.C * 2);
-        const int HW = x.H * x.W, Gn = c.gn_n_groups, Bn = B;
+        const int HW = x.H * x.W, Gn = c.gn_n_groups;
         float *gw = P(g.w), *gb = P(g.b), *cs = g.chsum;
-        label("gn_fwd C=%d %dx%d%s", x.C, x.H, x.W, have ? "" : " +stats pass");
-        F([=](cudaStream_t st) {
-            if (!have) gn_stats(x.p, x.ld, Bn, HW, x.C, cs, st);
-            gn_apply(x.p, x.ld, cs, gw, gb, Bn, HW, x.C, Gn, silu, y.p, y.ld, nullptr, st);
-        }, have ? 1 : 2, UB_KIND_NORM, 0, (have ? 2 : 3) * act_bytes(x.C, x.H, x.W));
+        const bool slab = !have && use_slab(x.C, x.H, x.W);
+        label("gn_fwd C=%d %dx%d%s", x.C, x.H, x.W, slab ? " slab" : (have ? "" : " +stats pass"));
+        split([&](int h) {
+            const View xh = mb(x, h), yh = mb(y, h);
+            float* csh = mbf(cs, h, size_t(x.C) * 2);
+            const int Bq = Bh;
+            if (slab)
+                F([=](cudaStream_t st) { gn_slab_fwd(xh.p, xh.ld, gw, gb, Bq, HW, xh.C, Gn, silu, yh.p, yh.ld, csh, st); }, 1,
+                  UB_KIND_NORM, 0, 2 * act_bytes(x.C, x.H, x.W) / nh);
+            else
+                F([=](cudaStream_t st) {
+                    if (!have) gn_stats(xh.p, xh.ld, Bq, HW, xh.C, csh, st);
+                    gn_apply(xh.p, xh.ld, csh, gw, gb, Bq, HW, xh.C, Gn, silu, yh.p, yh.ld, nullptr, st);
+                }, have ? 1 : 2, UB_KIND_NORM, 0, (have ? 2 : 3) * act_bytes(x.C, x.H, x.W) / nh);
+        });
         return g;
     }
     // Fuse the first half of GroupNorm(+SiLU) backward into the epilogue of the dgrad conv that produces dL/dy:
     // that conv then writes dz = dL/d gn(x) and accumulates S (see epilogue.cuh); call gn_bwd(..., fused = true) after.
     void gn_hook(ConvEpilogue& ep, const GN& g, View x, int silu) {
-        if (!gn_hooks()) return;
+        if (!use_hooks(x.C, x.H, x.W)) return;
         ep.gn_x = x.p, ep.gn_ldx = x.ld, ep.gn_chsum = g.chsum, ep.gn_gamma = P(g.w), ep.gn_beta = P(g.b);
         ep.gn_S = g.S, ep.gn_silu = silu, ep.gn_groups = c.gn_n_groups;
     }
     void gn_bwd(const GN& g, View x, View dy, int silu, View add_in, View dx, float* colsum_out, bool fused = false) {
-        fused = fused && gn_hooks();
-        const int HW = x.H * x.W, Gn = c.gn_n_groups, Bn = B;
+        fused = fused && use_hooks(x.C, x.H, x.W);
+        const int HW = x.H * x.W, Gn = c.gn_n_groups;
         float *gw = P(g.w), *gb = P(g.b), *cs = g.chsum, *S = g.S, *dgw = G(g.w), *dgb = G(g.b);
+        const bool slab = !fused && use_slab(x.C, x.H, x.W);
         const int mode = fused ? (silu ? 2 : 0) : silu;
-        label("gn_bwd C=%d %dx%d%s%s", x.C, x.H, x.W, fused ? "" : " +stats pass", add_in.p ? " +add" : "");
-        Bk([=](cudaStream_t st) {
-            if (!fused) gn_bwd_stats(x.p, x.ld, dy.p, dy.ld, cs, gw, gb, Bn, HW, x.C, Gn, silu, S, st);
-            gn_bwd_apply(x.p, x.ld, dy.p, dy.ld, cs, S, gw, gb, Bn, HW, x.C, Gn, mode, add_in.p, add_in.ld, dx.p,
-                         dx.ld, dgw, dgb, colsum_out, st);
-        }, fused ? 1 : 2, UB_KIND_NORM, 0, ((fused ? 3 : 5) + (add_in.p ? 1 : 0)) * act_bytes(x.C, x.H, x.W));
+        label("gn_bwd C=%d %dx%d%s%s", x.C, x.H, x.W, slab ? " slab" : (fused ? "" : " +stats pass"), add_in.p ? " +add" : "");
+        split([&](int h) {
+            const View xh = mb(x, h), dyh = mb(dy, h), ah = mb(add_in, h), dxh = mb(dx, h);
+            float *csh = mbf(cs, h, size_t(x.C) * 2), *Sh = mbf(S, h, size_t(x.C) * 2), *colh = mbf(colsum_out, h, x.C);
+            const int Bq = Bh;
+            if (slab)
+                Bk([=](cudaStream_t st) {
+                    gn_slab_bwd(xh.p, xh.ld, dyh.p, dyh.ld, csh, gw, gb, Bq, HW, xh.C, Gn, silu, ah.p, ah.ld, dxh.p, dxh.ld,
+                                dgw, dgb, colh, st);
+                }, 1, UB_KIND_NORM, 0, (3 + (add_in.p ? 1 : 0)) * act_bytes(x.C, x.H, x.W) / nh);
+            else
+                Bk([=](cudaStream_t st) {
+                    if (!fused) gn_bwd_stats(xh.p, xh.ld, dyh.p, dyh.ld, csh, gw, gb, Bq, HW, xh.C, Gn, silu, Sh, st);
+                    gn_bwd_apply(xh.p, xh.ld, dyh.p, dyh.ld, csh, Sh, gw, gb, Bq, HW, xh.C, Gn, mode, ah.p, ah.ld, dxh.p,
+                                 dxh.ld, dgw, dgb, colh, st);
+                }, fused ? 1 : 2, UB_KIND_NORM, 0, ((fused ? 3 : 5) + (add_in.p ? 1 : 0)) * act_bytes(x.C, x.H, x.W) / nh);
+        });
     }
 
     int res_index = 0;
@@ -462,7 +561,7 @@ struct Builder {
         const size_t w1 = take(size_t(Cout) * C * 9), b1 = take(Cout);
         const size_t wl = take(size_t(Cout) * Cemb), bl = take(Cout);
         View h1 = act(Cout, H, W);
-        h1.cs = stats_buf(Cout);
+        h1.cs = stats_buf(Cout, H, W);
         float* embproj = f32(size_t(B) * Cout);
         float* d_embproj = zf32(size_t(B) * Cout);
         Packed p1 = pack(w1, Cout, C, 9);
@@ -484,7 +583,7 @@ struct Builder {
             ps = pack(ws, Cout, C, 1);
         }
         View out = act(Cout, H, W);
-        out.cs = stats_buf(Cout);
+        out.cs = stats_buf(Cout, H, W);
         {
             ConvEpilogue ep;
             ep.bias = P(b2), ep.out = out.p, ep.ldo = out.ld, ep.stats = out.cs;
@@ -558,7 +657,7 @@ struct Builder {
         const size_t wp = take(size_t(C) * C), bp = take(C);
         Packed pq = pack(wq, 3 * C, C, 1), pp = pack(wp, C, C, 1);
         View qkv = act(3 * C, H, W), ao = act(C, H, W), out = act(C, H, W);
-        out.cs = stats_buf(C);
+        out.cs = stats_buf(C, H, W);
         float* lse = f32(size_t(B) * NH * Tn);
         float* dsum = f32(size_t(B) * NH * Tn);
         {
@@ -566,21 +665,25 @@ struct Builder {
             ep.bias = P(bq), ep.out = qkv.p, ep.ldo = qkv.ld;
             conv_op(true, {{g.p, C, g.ld, pq.wf, 1}}, H, W, 3 * C, ep);
         }
-        const int Bn = B;
         // tcgen05 attention core when the shape allows (T <= 256, even head count), SIMT fallback otherwise
         const bool tc = attn_tc_supported(Tn, NH, HSz);
-        AttnTcParams apf;
-        if (tc && real()) {
-            int r = attn_tc_plan(&apf, qkv.p, qkv.ld, B, Tn, NH, HSz, ao.p, ao.ld, lse, nullptr, 0, nullptr, 0, nullptr);
-            if (r) set_err("attn_tc_plan failed (%d)", r), plan_errors++;
-        }
         label("attn fwd T=%d C=%d", Tn, C);
-        F([=](cudaStream_t st) {
-            if (tc)
-                attn_tc_fwd(apf, st);
-            else
-                attn_fwd(qkv.p, qkv.ld, Bn, Tn, NH, HSz, ao.p, ao.ld, lse, st);
-        }, 1, UB_KIND_ATTN, 4.0 * B * NH * double(Tn) * Tn * HSz, act_bytes(4 * C, H, W));
+        split([&](int h) {
+            const View qh = mb(qkv, h), aoh = mb(ao, h);
+            float* lseh = mbf(lse, h, size_t(NH) * Tn);
+            const int Bq = Bh;
+            AttnTcParams apf;
+            if (tc && real()) {
+                int r = attn_tc_plan(&apf, qh.p, qh.ld, Bq, Tn, NH, HSz, aoh.p, aoh.ld, lseh, nullptr, 0, nullptr, 0, nullptr);
+                if (r) set_err("attn_tc_plan failed (%d)", r), plan_errors++;
+            }
+            F([=](cudaStream_t st) {
+                if (tc)
+                    attn_tc_fwd(apf, st);
+                else
+                    attn_fwd(qh.p, qh.ld, Bq, Tn, NH, HSz, aoh.p, aoh.ld, lseh, st);
+            }, 1, UB_KIND_ATTN, 4.0 * Bq * NH * double(Tn) * Tn * HSz, act_bytes(4 * C, H, W) / nh);
+        });
         {
             ConvEpilogue ep;
             ep.bias = P(bp), ep.out = out.p, ep.ldo = out.ld, ep.residual = x.p, ep.ldr = x.ld, ep.stats = out.cs;
@@ -597,20 +700,24 @@ struct Builder {
                 ep.out = dao.p, ep.ldo = dao.ld;
                 conv_op(false, {{dout.p, C, dout.ld, pp.wd, 1}}, H, W, C, ep);
             }
-            AttnTcParams apb;
-            if (tc && real()) {
-                int r = attn_tc_plan(&apb, qkv.p, qkv.ld, B, Tn, NH, HSz, ao.p, ao.ld, lse, dao.p, dao.ld, dqkv.p,
-                                     dqkv.ld, dsum);
-                if (r) set_err("attn_tc_plan (bwd) failed (%d)", r), plan_errors++;
-            }
             label("attn bwd T=%d C=%d", Tn, C);
-            Bk([=](cudaStream_t st) {
-                if (tc)
-                    attn_tc_bwd(apb, st);
-                else
-                    attn_bwd(qkv.p, qkv.ld, ao.p, ao.ld, dao.p, dao.ld, lse, Bn, Tn, NH, HSz, dqkv.p, dqkv.ld, dsum,
-                             st);
-            }, 2, UB_KIND_ATTN, 10.0 * B * NH * double(Tn) * Tn * HSz, act_bytes(8 * C, H, W));
+            split([&](int h) {
+                const View qh = mb(qkv, h), aoh = mb(ao, h), daoh = mb(dao, h), dqh = mb(dqkv, h);
+                float *lseh = mbf(lse, h, size_t(NH) * Tn), *dsh = mbf(dsum, h, size_t(NH) * Tn);
+                const int Bq = Bh;
+                AttnTcParams apb;
+                if (tc && real()) {
+                    int r = attn_tc_plan(&apb, qh.p, qh.ld, Bq, Tn, NH, HSz, aoh.p, aoh.ld, lseh, daoh.p, daoh.ld, dqh.p,
+                                         dqh.ld, dsh);
+                    if (r) set_err("attn_tc_plan (bwd) failed (%d)", r), plan_errors++;
+                }
+                Bk([=](cudaStream_t st) {
+                    if (tc)
+                        attn_tc_bwd(apb, st);
+                    else
+                        attn_bwd(qh.p, qh.ld, aoh.p, aoh.ld, daoh.p, daoh.ld, lseh, Bq, Tn, NH, HSz, dqh.p, dqh.ld, dsh, st);
+                }, 2, UB_KIND_ATTN, 10.0 * Bq * NH * double(Tn) * Tn * HSz, act_bytes(8 * C, H, W) / nh);
+            });
             wgrad_op(dqkv, g, C, 3 * C, 1, G(wq), gbq);
             {
                 ConvEpilogue ep;
@@ -686,7 +793,12 @@ int Builder::build() {
         float *w = P(wi), *b = P(bi), *gw = G(wi), *gb = G(bi);
         const int Cin = c.C_in;
         View hv = h;
-        F([=](cudaStream_t st) { conv_in_fwd(Tt->xt, w, b, Bn, Cin, hv.C, hv.H, hv.W, hv.p, hv.ld, st); });
+        split([&](int hh) {
+            const View hm = mb(hv, hh);
+            const size_t xoff = size_t(hh) * Bh * img;
+            const int Bq = Bh;
+            F([=](cudaStream_t st) { conv_in_fwd(Tt->xt + xoff, w, b, Bq, Cin, hm.C, hm.H, hm.W, hm.p, hm.ld, st); });
+        });
         nd.out = h, nd.pushed = true;
         nd.bwd = [=](View dout) -> View {
             Bk([=](cudaStream_t st) {
@@ -694,7 +806,12 @@ int Builder::build() {
                               Tt->small_scratch_floats, st);
             }, 1, UB_KIND_SMALL, 0, 0, 1);  // (one launch with the row kernel; two on its fallback path)
             if (Tt->cfg.compute_dinput)
-                Bk([=](cudaStream_t st) { conv_in_dgrad(dout.p, dout.ld, w, Bn, Cin, hv.C, hv.H, hv.W, Tt->dxt, st); }, 1);
+                split([&](int hh) {
+                    const View dm = mb(dout, hh);
+                    const size_t xoff = size_t(hh) * Bh * img;
+                    const int Bq = Bh;
+                    Bk([=](cudaStream_t st) { conv_in_dgrad(dm.p, dm.ld, w, Bq, Cin, hv.C, hv.H, hv.W, Tt->dxt + xoff, st); }, 1);
+                });
             return View{};
         };
         nodes.push_back(nd);
@@ -716,14 +833,22 @@ int Builder::build() {
             Node nd;
             nd.param_begin = poff;
             View x = h, y = act(h.C, h.H / 2, h.W / 2);
-            F([=](cudaStream_t st) { avgpool2_fwd(x.p, x.ld, Bn, x.H, x.W, x.C, y.p, y.ld, st); }, 1, UB_KIND_ELTWISE, 0,
-              1.25 * act_bytes(x.C, x.H, x.W));
+            split([&](int hh) {
+                const View xm = mb(x, hh), ym = mb(y, hh);
+                const int Bq = Bh;
+                F([=](cudaStream_t st) { avgpool2_fwd(xm.p, xm.ld, Bq, xm.H, xm.W, xm.C, ym.p, ym.ld, st); }, 1,
+                  UB_KIND_ELTWISE, 0, 1.25 * act_bytes(x.C, x.H, x.W) / nh);
+            });
             nd.out = y, nd.pushed = true;
             nd.bwd = [=](View dout) -> View {
                 View dx = act(x.C, x.H, x.W);
-                Bk([=](cudaStream_t st) {
-                    avgpool2_bwd(dout.p, dout.ld, Bn, x.H, x.W, x.C, nullptr, 0, dx.p, dx.ld, st);
-                }, 1, UB_KIND_ELTWISE, 0, 1.25 * act_bytes(x.C, x.H, x.W));
+                split([&](int hh) {
+                    const View dm = mb(dout, hh), dxm = mb(dx, hh);
+                    const int Bq = Bh;
+                    Bk([=](cudaStream_t st) {
+                        avgpool2_bwd(dm.p, dm.ld, Bq, x.H, x.W, x.C, nullptr, 0, dxm.p, dxm.ld, st);
+                    }, 1, UB_KIND_ELTWISE, 0, 1.25 * act_bytes(x.C, x.H, x.W) / nh);
+                });
                 return dx;
             };
             nodes.push_back(nd);
@@ -749,10 +874,14 @@ int Builder::build() {
             nd.param_begin = poff;
             const int C1 = h.C, C2 = sk.C, Hc = sk.H, Wc = sk.W, up = pending_up ? 1 : 0;
             View cat = act(C1 + C2, Hc, Wc), a = h;
-            if (a.cs && sk.cs) cat.cs = stats_buf(C1 + C2);  // GroupNorm statistics of the parts, side by side
-            F([=](cudaStream_t st) {
-                concat2(a.p, a.ld, C1, up, sk.p, sk.ld, C2, Bn, Hc, Wc, cat.p, cat.ld, a.cs, sk.cs, cat.cs, st);
-            }, 1, UB_KIND_ELTWISE, 0, 2 * act_bytes(C1 + C2, Hc, Wc));
+            if (a.cs && sk.cs) cat.cs = zf32(size_t(B) * (C1 + C2) * 2);  // GroupNorm statistics of the parts, side by side
+            split([&](int hh) {
+                const View am = mb(a, hh), sm = mb(sk, hh), cm = mb(cat, hh);
+                const int Bq = Bh;
+                F([=](cudaStream_t st) {
+                    concat2(am.p, am.ld, C1, up, sm.p, sm.ld, C2, Bq, Hc, Wc, cm.p, cm.ld, am.cs, sm.cs, cm.cs, st);
+                }, 1, UB_KIND_ELTWISE, 0, 2 * act_bytes(C1 + C2, Hc, Wc) / nh);
+            });
             nd.out = cat;
             std::vector<View>* sg = &skipgrad;
             nd.bwd = [=](View d) -> View {
@@ -761,8 +890,12 @@ int Builder::build() {
                 (*sg)[src] = skv;
                 if (up) {
                     View dlow = act(C1, Hc / 2, Wc / 2);
-                    Bk([=](cudaStream_t st) { upsample2_bwd(d.p, d.ld, Bn, Hc, Wc, C1, dlow.p, dlow.ld, st); }, 1,
-                       UB_KIND_ELTWISE, 0, 1.25 * act_bytes(C1, Hc, Wc));
+                    split([&](int hh) {
+                        const View dm = mb(d, hh), lm = mb(dlow, hh);
+                        const int Bq = Bh;
+                        Bk([=](cudaStream_t st) { upsample2_bwd(dm.p, dm.ld, Bq, Hc, Wc, C1, lm.p, lm.ld, st); }, 1,
+                           UB_KIND_ELTWISE, 0, 1.25 * act_bytes(C1, Hc, Wc) / nh);
+                    });
                     return dlow;
                 }
                 View mv = d;
@@ -796,7 +929,12 @@ int Builder::build() {
                 conv_out_wgrad(ao.p, ao.ld, Tt->dout, Bn, Cin, Co, Hh, Ww, gw, gb, Tt->small_scratch,
                                Tt->small_scratch_floats, st);
             }, 2, UB_KIND_SMALL, 0, 0, 1);  // (row kernel + bias sum; three on the fallback path)
-            Bk([=](cudaStream_t st) { conv_out_dgrad(Tt->dout, w, Bn, Cin, Co, Hh, Ww, dao.p, dao.ld, st); }, 1);
+            split([&](int hh) {
+                const View dm = mb(dao, hh);
+                const size_t ooff = size_t(hh) * Bh * Co * Hh * Ww;
+                const int Bq = Bh;
+                Bk([=](cudaStream_t st) { conv_out_dgrad(Tt->dout + ooff, w, Bq, Cin, Co, Hh, Ww, dm.p, dm.ld, st); }, 1);
+            });
             gn_bwd(g, hx, dao, 1, View{}, dh, nullptr);
             return dh;
         };
@@ -866,10 +1004,14 @@ int Builder::build() {
             View s = skipgrad[i];
             View sum = act(nd.out.C, nd.out.H, nd.out.W);
             View a = g;
-            const size_t npix = size_t(B) * nd.out.H * nd.out.W;
+            const size_t npix = size_t(Bh) * nd.out.H * nd.out.W;
             const int C = nd.out.C;
-            Bk([=](cudaStream_t st) { add2(a.p, a.ld, s.p, s.ld, npix, C, sum.p, sum.ld, st); }, 1, UB_KIND_ELTWISE, 0,
-               3 * act_bytes(C, nd.out.H, nd.out.W));
+            a.H = s.H = nd.out.H, a.W = s.W = nd.out.W;  // (channel-slice views keep the geometry of their buffer)
+            split([&](int hh) {
+                const View am = mb(a, hh), sm = mb(s, hh), um = mb(sum, hh);
+                Bk([=](cudaStream_t st) { add2(am.p, am.ld, sm.p, sm.ld, npix, C, um.p, um.ld, st); }, 1, UB_KIND_ELTWISE, 0,
+                   3 * act_bytes(C, nd.out.H, nd.out.W) / nh);
+            });
             g = sum;
         }
         if (i == 0) {  // only the 3-channel input conv is left: finalise the tcgen05 weight gradients before it
@@ -990,6 +1132,12 @@ extern "C" int ub_trainer_create(UbTrainer** out, const UbConfig* cfg, int devic
     UbTrainer* t = new UbTrainer();
     t->cfg = *cfg;
     t->device = device;
+    {   // micro-batch chains (UbTrainer::n_mb): off by default -- measured 5.18 ms/step with one chain, 5.30 with two, 5.74
+        // with four (profiles/r02_microbatch.txt): the latency that B-scaling exposes is per launch, and two chains double
+        // the launches.  UB_MICROBATCH=2 / 4 enables (B must be divisible).
+        const int want = getenv("UB_MICROBATCH") ? atoi(getenv("UB_MICROBATCH")) : 1;
+        t->n_mb = (want >= 2 && want <= 8 && cfg->B % want == 0) ? want : 1;
+    }
     // pass 1: count
     t->arena.counting = t->zarena.counting = true;
     {
@@ -1022,7 +1170,12 @@ extern "C" int ub_trainer_create(UbTrainer** out, const UbConfig* cfg, int devic
     cudaStreamCreateWithPriority(&t->stream, cudaStreamNonBlocking, use_prio ? prio_hi : 0);
     cudaStreamCreateWithPriority(&t->comm_stream, cudaStreamNonBlocking, use_prio ? prio_hi : 0);
     cudaStreamCreateWithPriority(&t->side_stream, cudaStreamNonBlocking, use_prio ? prio_lo : 0);
-    t->side_events.resize(512);
+    for (int i = 1; i < t->n_mb; ++i) {
+        cudaStream_t ms = nullptr;
+        cudaStreamCreateWithPriority(&ms, cudaStreamNonBlocking, use_prio ? prio_hi : 0);
+        t->mb_streams.push_back(ms);
+    }
+    t->side_events.resize(4096);
     for (auto& ev : t->side_events) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (const char* e = getenv("UB_NO_SIDE_STREAM")) t->use_side = atoi(e) == 0;
     cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming);
@@ -1090,6 +1243,7 @@ extern "C" void ub_trainer_destroy(UbTrainer* t) {
     if (t->stream) cudaStreamDestroy(t->stream);
     if (t->comm_stream) cudaStreamDestroy(t->comm_stream);
     if (t->side_stream) cudaStreamDestroy(t->side_stream);
+    for (auto ms : t->mb_streams) cudaStreamDestroy(ms);
     for (auto ev : t->side_events) cudaEventDestroy(ev);
     delete t;
 }
@@ -1113,14 +1267,38 @@ static void enqueue_step(UbTrainer* t, const StepOpts& o, cudaStream_t st) {
     if (debug_sync) cudaStreamIsCapturing(st, &cap);
     bool side_dirty = false;
     auto next_event = [&]() { return t->side_events[t->side_ev_next++ % t->side_events.size()]; };
+    // micro-batch chains: `forked` while the chains of micro-batches 1.. run beside the main stream
+    bool forked = false;
+    auto fork_mb = [&]() {
+        if (forked || t->mb_streams.empty()) return;
+        cudaEvent_t ev = next_event();
+        cudaEventRecord(ev, st);
+        for (cudaStream_t ms : t->mb_streams) cudaStreamWaitEvent(ms, ev, 0);
+        forked = true;
+    };
+    auto join_mb = [&]() {
+        if (!forked) return;
+        for (cudaStream_t ms : t->mb_streams) {
+            cudaEvent_t ev = next_event();
+            cudaEventRecord(ev, ms);
+            cudaStreamWaitEvent(st, ev, 0);
+        }
+        forked = false;
+    };
     auto run = [&](std::vector<UbTrainer::Op>& ops, std::vector<UbTrainer::OpInfo>& info, const char* what) {
         for (size_t i = 0; i < ops.size(); ++i) {
             static const bool skip_side = getenv("UB_DEBUG_SKIP_SIDE") != nullptr;  // timing experiments only
             if (info[i].side == 1 && skip_side) continue;
-            if (info[i].side == 1 && t->use_side) {  // fork: the branch sees everything enqueued on main so far
+            if (info[i].side == 1 && t->use_side) {  // fork: the branch sees everything enqueued on the main chains so far
                 cudaEvent_t ev = next_event();
                 cudaEventRecord(ev, st);
                 cudaStreamWaitEvent(t->side_stream, ev, 0);
+                if (forked)
+                    for (cudaStream_t ms : t->mb_streams) {
+                        cudaEvent_t e2 = next_event();
+                        cudaEventRecord(e2, ms);
+                        cudaStreamWaitEvent(t->side_stream, e2, 0);
+                    }
                 ops[i](t->side_stream);
                 side_dirty = true;
             } else if (info[i].side == 2) {
@@ -1128,13 +1306,22 @@ static void enqueue_step(UbTrainer* t, const StepOpts& o, cudaStream_t st) {
                     cudaEvent_t ev = next_event();
                     cudaEventRecord(ev, t->side_stream);
                     cudaStreamWaitEvent(st, ev, 0);
+                    if (forked)
+                        for (cudaStream_t ms : t->mb_streams) cudaStreamWaitEvent(ms, ev, 0);
                     side_dirty = false;
                 }
+            } else if (info[i].half > 0 && size_t(info[i].half) <= t->mb_streams.size()) {
+                fork_mb();
+                ops[i](t->mb_streams[info[i].half - 1]);
             } else {
+                if (info[i].half < 0 || info[i].side == 1) join_mb();  // whole-batch op: every chain must have arrived
+                else fork_mb();
                 ops[i](st);
             }
             if (debug_sync && cap == cudaStreamCaptureStatusNone) {
                 cudaError_t e = cudaStreamSynchronize(st);
+                for (cudaStream_t ms : t->mb_streams)
+                    if (e == cudaSuccess) e = cudaStreamSynchronize(ms);
                 if (e == cudaSuccess) e = cudaGetLastError();
                 if (e != cudaSuccess) {
                     fprintf(stderr, "[unet_b200] %s op %zu (kind %d): %s\n", what, i, info[i].kind,
@@ -1150,6 +1337,7 @@ static void enqueue_step(UbTrainer* t, const StepOpts& o, cudaStream_t st) {
     t->opt_done_lo = t->nparams;
     run(t->fwd_ops, t->fwd_info, "forward");
     run(t->bwd_ops, t->bwd_info, "backward");
+    join_mb();
     if (side_dirty) {  // (the tape ends with a join; this only guards against a tape that forgot it)
         cudaEvent_t ev = next_event();
         cudaEventRecord(ev, t->side_stream);
