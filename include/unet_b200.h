@@ -245,9 +245,13 @@ void ub_trainer_destroy(UbTrainer* t);
 
 /* checkpoint, train_unet.cu:4762-4911 / train_unet.py:768-795: int32[256] header {12345678, B, C_in, C_model, C_out,
  * H, W, max_period, has_adamw, has_rng} + fp32 params [+ m + v].  The rng flag is always written 0 (the reference's
- * blob is a raw curandState dump); header[10] additionally stores the AdamW step count (the reference forgets it). */
+ * blob is a raw curandState dump); header[10] additionally stores the AdamW step count (the reference forgets it),
+ * marked valid by header[11] = 0x55425354.  The reference's C writer leaves words 10..255 uninitialised
+ * (train_unet.cu:4764), so ub_trainer_load trusts header[10] only behind that marker and otherwise restarts the count
+ * at 0 -- what the reference's own resume does; ub_trainer_set_step supplies a count from elsewhere. */
 int ub_trainer_load(UbTrainer* t, const char* path);
 int ub_trainer_save(UbTrainer* t, const char* path, int with_adamw);
+int ub_trainer_set_step(UbTrainer* t, int step);
 /* read the {B, C_in, C_model, C_out, H, W, max_period} header of a checkpoint into cfg (other fields untouched) */
 int ub_read_checkpoint_header(const char* path, UbConfig* cfg);
 

@@ -27,6 +27,37 @@ def _per_tensor_rel(O, cfg, g, g_ref):
     return out
 
 
+# Stated per-tensor bound of the bf16 training path: every one of the gradient tensors within 5e-2 relative L2 of the
+# oracle's (fp32) gradient -- bf16 operands / activations carry 2^-9 relative rounding per element and a gradient tensor
+# accumulates it over 50-100 layers of backward; the global bounds (all gradients: rel-L2 2e-2, cosine 0.9995) are the
+# tighter ones.  Tensors whose oracle gradient is exactly zero (everything upstream of the zero-initialised conv2 / proj
+# weights, dev/unet.py zero_module) must be exactly zero here too.
+TOL_TENSOR_L2 = 5e-2
+
+
+def check_grads(O, cfg, g, g_ref, what=""):
+    """Global rel-L2 / cosine + per-tensor rel-L2 over every gradient tensor; prints the five worst tensors."""
+    assert not np.isnan(g).any()
+    cos = float(g @ g_ref / (np.linalg.norm(g) * np.linalg.norm(g_ref)))
+    glob = float(np.linalg.norm(g - g_ref) / np.linalg.norm(g_ref))
+    off, rows = 0, []
+    for name, shape in O.param_spec(cfg):
+        n = int(np.prod(shape))
+        a, b = g[off:off + n].astype(np.float64), g_ref[off:off + n].astype(np.float64)
+        nb = float(np.linalg.norm(b))
+        rel = float(np.linalg.norm(a - b)) / nb if nb > 0 else (0.0 if not a.any() else float("inf"))
+        rows.append((rel, name, n, nb))
+        off += n
+    rows.sort(reverse=True)
+    print(f"[grads {what}] global rel-L2 {glob:.3e} cosine {cos:.6f}; worst tensors (rel-L2, name, size, |ref|):")
+    for r in rows[:5]:
+        print(f"    {r[0]:.3e}  {r[1]}  n={r[2]}  |ref|={r[3]:.3e}")
+    assert cos > 0.9995, cos
+    assert glob <= 2e-2, glob
+    assert rows[0][0] <= TOL_TENSOR_L2, rows[:5]
+    return rows
+
+
 def test_forward_backward_matches_oracle_B4(ub, setup):
     """out, loss and all 326 gradient tensors (dev/unet_test.cu:2082-2107 checks the same set)."""
     O, cfg, flat = setup
@@ -38,14 +69,28 @@ def test_forward_backward_matches_oracle_B4(ub, setup):
     out, g = tr.get_output(), tr.get_grads()
     loss_ref, out_ref, g_ref = O.train_step_grads(cfg, flat, x0, t, noise)
     g_ref = g_ref.numpy()
-    assert not np.isnan(g).any()
     assert abs(loss - float(loss_ref)) <= 2e-3 * float(loss_ref)          # loss: 2e-3 relative
     assert np.abs(out - out_ref.numpy()).max() <= 3e-2 * np.abs(out_ref.numpy()).max()   # bf16 activations
-    cos = float(g @ g_ref / (np.linalg.norm(g) * np.linalg.norm(g_ref)))
-    assert cos > 0.9995, cos
-    assert np.linalg.norm(g - g_ref) <= 2e-2 * np.linalg.norm(g_ref)      # global rel-L2 of all gradients
+    check_grads(O, cfg, g, g_ref, "B=4")        # global rel-L2 2e-2, cosine 0.9995, every tensor rel-L2 5e-2
     worst = max(_per_tensor_rel(O, cfg, g, g_ref))
     assert worst[0] <= 0.15, worst                                        # every tensor: max-norm relative
+    tr.close()
+
+
+def test_forward_backward_matches_oracle_B32(ub, setup):
+    """BASELINE configs[2] as written: the default 64x64 U-Net at batch 32, one full forward + backward against the
+    oracle (a 5-6 s CPU step), loss / output / global and per-tensor gradient bounds."""
+    O, cfg, flat = setup
+    B = 32
+    x0, t, noise = O.synthetic_batch(cfg, B, seed=4321)
+    tr = ub.Trainer(B=B)
+    tr.set_params(flat.numpy())
+    loss = tr.forward_backward(x0.numpy(), t.numpy(), noise.numpy())
+    out, g = tr.get_output(), tr.get_grads()
+    loss_ref, out_ref, g_ref = O.train_step_grads(cfg, flat, x0, t, noise)
+    assert abs(loss - float(loss_ref)) <= 2e-3 * float(loss_ref)
+    assert np.abs(out - out_ref.numpy()).max() <= 3e-2 * np.abs(out_ref.numpy()).max()
+    check_grads(O, cfg, g, g_ref.numpy(), "B=32")
     tr.close()
 
 
@@ -151,6 +196,7 @@ def test_checkpoint_roundtrip_and_reference_layout(ub, setup, tmp_path):
     header, rest = O.read_model_bin(out_file)                 # generate.py:17-27 reads header + params
     n = tr.nparams
     assert list(header[:10]) == [12345678, 2, 3, 64, 3, 64, 64, 1000, 1, 0] and header[10] == 1
+    assert header[11] == 0x55425354                           # marks header[10] (AdamW step count) as valid
     assert rest.size == 3 * n and os.path.getsize(out_file) == 1024 + 12 * n
     np.testing.assert_array_equal(rest[:n], tr.get_params())
     tr2 = ub.Trainer(B=2)
@@ -160,6 +206,34 @@ def test_checkpoint_roundtrip_and_reference_layout(ub, setup, tmp_path):
     lb = tr2.train_step(b[0].numpy(), b[1].numpy(), b[2].numpy())
     assert abs(la - lb) < 1e-3
     assert np.abs(tr.get_params() - tr2.get_params()).max() <= 2.5e-4   # one step: 2*lr + rounding
+    tr.close(), tr2.close()
+
+
+def test_resume_from_reference_written_checkpoint_with_garbage_header(ub, setup, tmp_path):
+    """The reference's C writer fills words 0..9 of an uninitialised int[256] (train_unet.cu:4764): words 10.. are stack
+    garbage.  Loading such a checkpoint (with AdamW state) must not take the step count from it: a negative or huge count
+    makes the bias correction NaN / a no-op.  The count restarts at 0, like the reference's own resume."""
+    O, cfg, flat = setup
+    tr = ub.Trainer(B=2)
+    tr.set_params(flat.numpy())
+    x0, t, noise = O.synthetic_batch(cfg, 2)
+    tr.train_step(x0.numpy(), t.numpy(), noise.numpy())
+    good = str(tmp_path / "good.bin")
+    tr.save(good, with_adamw=True)
+    raw = np.fromfile(good, dtype=np.int32).copy()
+    rng = np.random.default_rng(3)
+    raw[10:256] = rng.integers(-2**31, 2**31 - 1, size=246, dtype=np.int64).astype(np.int32)
+    raw[10] = -123456789                                     # the dangerous case: 1 - beta2^t < 0 -> sqrt -> NaN
+    bad = str(tmp_path / "reference_written.bin")
+    raw.tofile(bad)
+    tr2 = ub.Trainer(B=2)
+    tr2.load(bad)
+    l = tr2.train_step(x0.numpy(), t.numpy(), noise.numpy())
+    p = tr2.get_params()
+    assert np.isfinite(l) and np.isfinite(p).all()
+    # step count 0 -> first-step bias correction: |update| = lr for every weight with a non-zero gradient
+    assert np.abs(p - tr.get_params()).max() <= 2.5e-4
+    assert ub.lib().ub_trainer_set_step(tr2._h, 7) == 0 and ub.lib().ub_trainer_set_step(tr2._h, -1) != 0
     tr.close(), tr2.close()
 
 
@@ -219,9 +293,7 @@ def test_config5_128px_five_levels_matches_oracle(ub, oracle):
     loss_ref, _, g_ref = O.train_step_grads(cfg, flat, x0, t, noise)
     g_ref = g_ref.numpy()
     assert abs(loss - float(loss_ref)) <= 2e-3 * float(loss_ref)
-    cos = float(g @ g_ref / (np.linalg.norm(g) * np.linalg.norm(g_ref)))
-    assert cos > 0.9995, cos
-    assert np.linalg.norm(g - g_ref) <= 2e-2 * np.linalg.norm(g_ref)
+    check_grads(O, cfg, g, g_ref, "config5 128px")
     tr.close()
 
 
@@ -314,9 +386,7 @@ def test_other_configs_match_oracle(ub, oracle, kw, okw, B):
     loss_ref, _, g_ref = O.train_step_grads(cfg, flat, x0, t, noise)
     g_ref = g_ref.numpy()
     assert abs(loss - float(loss_ref)) <= 2e-3 * float(loss_ref)
-    cos = float(g @ g_ref / (np.linalg.norm(g) * np.linalg.norm(g_ref)))
-    assert cos > 0.9995, cos
-    assert np.linalg.norm(g - g_ref) <= 2e-2 * np.linalg.norm(g_ref)
+    check_grads(O, cfg, g, g_ref, str(kw))
     l2 = tr.train_step(x0.numpy(), t.numpy(), noise.numpy(), lr=1e-4)   # the captured-graph path runs too
     assert np.isfinite(l2)
     tr.close()

@@ -41,5 +41,9 @@ if rank == 0:
     print(f"  max |p_dp - p_single| = {np.abs(p_dp - p_ref).max():.3e}  (3 AdamW steps moved weights by up to {moved:.3e}); "
           f"mean |diff| = {np.abs(p_dp - p_ref).mean():.3e}")
     print(f"  shard-0 losses {['%.5f' % l for l in losses]}  full-batch losses {['%.5f' % l for l in lref]}")
+    import json
+    print("DPCHECK " + json.dumps({"world": world, "identical": all(bool(torch.equal(allp[0], a)) for a in allp[1:]),
+                                   "max_diff": float(np.abs(p_dp - p_ref).max()), "moved": float(moved),
+                                   "mean_diff": float(np.abs(p_dp - p_ref).mean())}))
 dist.barrier()
 dist.destroy_process_group()

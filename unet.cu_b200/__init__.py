@@ -83,6 +83,10 @@ def _declare(L: C.CDLL) -> None:
     L.ub_trainer_train_step_device.argtypes = [vp, fp] + [C.c_float] * 5
     L.ub_trainer_sync.argtypes = [vp]
     L.ub_trainer_last_loss.argtypes = [vp, C.POINTER(C.c_float)]
+    L.ub_trainer_set_step.argtypes = [vp, i]
+    L.ub_set_layer_precision.argtypes = [i]
+    L.ub_groupnorm_nhwc_forward.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i]
+    L.ub_groupnorm_nhwc_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i]
     L.ub_trainer_stream.argtypes = [vp]
     L.ub_trainer_stream.restype = vp
     L.ub_trainer_launches_per_step.argtypes = [vp]

@@ -626,8 +626,11 @@ void pack_weights(const PackEntry* table_dev, int n_entries, int max_tiles, cuda
 // =====================================================================================================
 __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, size_t n4, size_t n, float lr, float b1, float b2, float eps,
-                             float wd, float gscale, const int* __restrict__ step_dev) {
+                             float wd, float gscale, const int* __restrict__ step_dev, const float* __restrict__ hp) {
     pdl_entry();
+    // hyper-parameters from device memory when given (the captured step graph: a learning-rate schedule must not force a
+    // re-capture), {lr, beta1, beta2, eps, weight_decay}
+    if (hp) lr = hp[0], b1 = hp[1], b2 = hp[2], eps = hp[3], wd = hp[4];
     const int t = *step_dev + 1;
     const float c1 = 1.f - powf(b1, float(t)), c2 = 1.f - powf(b2, float(t));
     const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -659,10 +662,10 @@ __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float
     }
 }
 void adamw_step(float* p, float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, float wd,
-                float grad_scale, const int* step_dev, cudaStream_t st) {
+                float grad_scale, const int* step_dev, cudaStream_t st, const float* hp_dev) {
     const size_t n4 = n / 4;
     launch_pdl(adamw_kernel, dim3(unsigned((n4 + 1 + 255) / 256)), dim3(256), 0, st, p, g, m, v, n4, n, lr, b1, b2, eps, wd, grad_scale,
-                                                                step_dev);
+                                                                step_dev, hp_dev);
 }
 // ---- DDPM sampling
 __global__ void sample_set_t_kernel(const int* __restrict__ t_dev, int B, float* __restrict__ tsteps) {

@@ -66,7 +66,7 @@ void pack_weights(const PackEntry* table_dev, int n_entries, int max_tiles, cuda
 // ---- AdamW (replaces adamw_kernel2 + unet_zero_grad, train_unet.cu:4706-4757): reads the step counter from
 //      device memory, applies grad_scale (1/world for data parallel), and zeroes the gradient.
 void adamw_step(float* p, float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, float wd,
-                float grad_scale, const int* step_dev, cudaStream_t st);
+                float grad_scale, const int* step_dev, cudaStream_t st, const float* hp_dev = nullptr);
 void increment_step(int* step_dev, cudaStream_t st);
 
 // ---- DDPM sampling step (generate.py:29-52).  t_dev holds the current t (2 <= t < T): fill t for the embedding,

@@ -136,7 +136,16 @@ struct UbTrainer {
     bool samp_graph_noise = false;
     float* samp_z = nullptr;  // injected noise of the current iteration (graph reads a fixed address)
     int* step_dev = nullptr;
-    float *h_x0 = nullptr, *h_noise = nullptr, *h_t = nullptr, *h_loss = nullptr;  // pinned staging
+    float* h_loss = nullptr;  // pinned
+    // Host batches are staged through the trainer's OWN page-locked double buffer: the caller's buffer (pageable or
+    // pinned, e.g. a data-loader slot that is refilled by a prefetch thread) may be reused as soon as the call returns,
+    // like cudaMemcpy from pageable memory -- the asynchronous copy that reads it may still be queued behind the previous
+    // step's graph.  A slot is rewritten only after the copies that last read it have completed (event per slot), so the
+    // host runs at most two steps ahead of the device.
+    float *hs_x0[2] = {nullptr, nullptr}, *hs_noise[2] = {nullptr, nullptr}, *hs_t[2] = {nullptr, nullptr};
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+    bool stage_used[2] = {false, false};
+    unsigned stage_next = 0;
     // wgrad workspace
     float* wg_partial = nullptr;
     size_t wg_cap = size_t(24) << 20;  // floats
@@ -185,6 +194,10 @@ struct UbTrainer {
     bool opt_in_tape = false;  // true while a step WITH an update is being enqueued
     bool opt_overlap_ok = true;
     float o_lr = 0, o_b1 = 0, o_b2 = 0, o_eps = 0, o_wd = 0;
+    // {lr, beta1, beta2, eps, weight_decay} in device memory: the captured graph's AdamW nodes read them from here, so a
+    // learning-rate schedule changes 20 bytes per step instead of forcing a re-capture of ~450 nodes
+    float* hp_dev = nullptr;
+    const float* hp_active = nullptr;  // = hp_dev while a graph is being captured / replayed, null for eager steps
     size_t opt_done_lo = 0;   // parameters >= this offset were updated by the tape
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::vector<cudaEvent_t> bucket_events;
@@ -749,6 +762,7 @@ int Builder::build() {
     T->samp_state = (int*)T->arena.alloc(256);
     T->samp_z = f32(size_t(B) * img);
     T->step_dev = (int*)T->arena.alloc(256);
+    T->hp_dev = f32(8);
     T->loss = zf32(64);
     T->sin_emb = f32(size_t(B) * Cm), T->h0 = f32(size_t(B) * Cemb), T->emb = f32(size_t(B) * Cemb);
     T->semb = f32(size_t(B) * Cemb);
@@ -992,7 +1006,7 @@ int Builder::build() {
             // optimizer of this bucket on the stream that owns its final gradients
             cudaStream_t os = dp ? Tt->comm_stream : st;
             adamw_step(Tt->params + lo, Tt->grads + lo, Tt->m + lo, Tt->v + lo, hi - lo, Tt->o_lr, Tt->o_b1, Tt->o_b2,
-                       Tt->o_eps, Tt->o_wd, 1.f / float(Tt->world), Tt->step_dev, os);
+                       Tt->o_eps, Tt->o_wd, 1.f / float(Tt->world), Tt->step_dev, os, Tt->hp_active);
             if (pk_count) pack_weights(Tt->pack_table + pk_first, pk_count, pk_tiles, os);
             Tt->opt_done_lo = lo;
         }, 0, UB_KIND_OPTIM, 0, 0, 1);
@@ -1212,9 +1226,12 @@ extern "C" int ub_trainer_create(UbTrainer** out, const UbConfig* cfg, int devic
         cudaMemcpy(t->sqrt_1mac, sb.data(), n * sizeof(float), cudaMemcpyHostToDevice);
     }
     const size_t img = size_t(cfg->B) * cfg->C_in * cfg->H * cfg->W;
-    cudaMallocHost(&t->h_x0, img * sizeof(float));
-    cudaMallocHost(&t->h_noise, img * sizeof(float));
-    cudaMallocHost(&t->h_t, cfg->B * sizeof(float));
+    for (int k = 0; k < 2; ++k) {
+        cudaMallocHost(&t->hs_x0[k], img * sizeof(float));
+        cudaMallocHost(&t->hs_noise[k], img * sizeof(float));
+        cudaMallocHost(&t->hs_t[k], cfg->B * sizeof(float));
+        cudaEventCreateWithFlags(&t->ev_stage[k], cudaEventDisableTiming);
+    }
     cudaMallocHost(&t->h_loss, 64);
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
@@ -1234,9 +1251,12 @@ extern "C" void ub_trainer_destroy(UbTrainer* t) {
     if (t->samp_graph) cudaGraphExecDestroy(t->samp_graph);
     if (t->comm && nccl().ok) nccl().CommDestroy(t->comm);
     if (t->params) cudaFree(t->params);
-    if (t->h_x0) cudaFreeHost(t->h_x0);
-    if (t->h_noise) cudaFreeHost(t->h_noise);
-    if (t->h_t) cudaFreeHost(t->h_t);
+    for (int k = 0; k < 2; ++k) {
+        if (t->hs_x0[k]) cudaFreeHost(t->hs_x0[k]);
+        if (t->hs_noise[k]) cudaFreeHost(t->hs_noise[k]);
+        if (t->hs_t[k]) cudaFreeHost(t->hs_t[k]);
+        if (t->ev_stage[k]) cudaEventDestroy(t->ev_stage[k]);
+    }
     if (t->h_loss) cudaFreeHost(t->h_loss);
     for (auto ev : t->bucket_events) cudaEventDestroy(ev);
     if (t->ev_join) cudaEventDestroy(t->ev_join);
@@ -1347,7 +1367,7 @@ static void enqueue_step(UbTrainer* t, const StepOpts& o, cudaStream_t st) {
         // the buckets the tape already updated are [opt_done_lo, nparams); the rest (the last bucket) is updated here
         const size_t n_left = t->opt_done_lo;
         adamw_step(t->params, t->grads, t->m, t->v, n_left, o.lr, o.b1, o.b2, o.eps, o.wd, 1.f / float(t->world),
-                   t->step_dev, st);
+                   t->step_dev, st, t->hp_active);
         int cnt = 0, tiles = 0;
         while (cnt < t->n_pack && t->pack_off[cnt] < n_left) {
             tiles = std::max(tiles, ((t->h_pack[cnt].Cout + 31) / 32) * ((t->h_pack[cnt].Cin + 31) / 32));
@@ -1367,10 +1387,20 @@ static int ensure_packed(UbTrainer* t) {
 static int stage_inputs(UbTrainer* t, const float* x0_host, const float* t_host, const float* noise_host) {
     const UbConfig& c = t->cfg;
     const size_t img = size_t(c.B) * c.C_in * c.H * c.W;
-    CUDA_TRY(cudaMemcpyAsync(t->x0, x0_host, img * sizeof(float), cudaMemcpyHostToDevice, t->stream));
-    if (t_host) CUDA_TRY(cudaMemcpyAsync(t->tsteps, t_host, c.B * sizeof(float), cudaMemcpyHostToDevice, t->stream));
-    if (noise_host)
-        CUDA_TRY(cudaMemcpyAsync(t->noise, noise_host, img * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+    const int k = int(t->stage_next++ & 1u);
+    if (t->stage_used[k]) CUDA_TRY(cudaEventSynchronize(t->ev_stage[k]));  // the copies that last read this slot are done
+    memcpy(t->hs_x0[k], x0_host, img * sizeof(float));
+    CUDA_TRY(cudaMemcpyAsync(t->x0, t->hs_x0[k], img * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+    if (t_host) {
+        memcpy(t->hs_t[k], t_host, c.B * sizeof(float));
+        CUDA_TRY(cudaMemcpyAsync(t->tsteps, t->hs_t[k], c.B * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+    }
+    if (noise_host) {
+        memcpy(t->hs_noise[k], noise_host, img * sizeof(float));
+        CUDA_TRY(cudaMemcpyAsync(t->noise, t->hs_noise[k], img * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+    }
+    CUDA_TRY(cudaEventRecord(t->ev_stage[k], t->stream));
+    t->stage_used[k] = true;
     return UB_OK;
 }
 
@@ -1419,13 +1449,19 @@ static int launch_step(UbTrainer* t, const StepOpts& o) {
         CUDA_TRY(cudaGetLastError());
         return UB_OK;
     }
-    const bool same = t->graph_valid && t->graph_gen_t == o.gen_t && t->graph_gen_noise == o.gen_noise &&
-                      t->g_lr == o.lr && t->g_b1 == o.b1 && t->g_b2 == o.b2 && t->g_eps == o.eps && t->g_wd == o.wd;
+    // (hyper-parameters are NOT part of the graph's identity: its AdamW nodes read them from hp_dev)
+    const bool same = t->graph_valid && t->graph_gen_t == o.gen_t && t->graph_gen_noise == o.gen_noise;
+    {
+        const float hp[5] = {o.lr, o.b1, o.b2, o.eps, o.wd};  // pageable source: staged by the driver before the call returns
+        CUDA_TRY(cudaMemcpyAsync(t->hp_dev, hp, sizeof hp, cudaMemcpyHostToDevice, t->stream));
+    }
+    t->hp_active = t->hp_dev;
     if (!same) {
         if (t->graph_exec) cudaGraphExecDestroy(t->graph_exec), t->graph_exec = nullptr;
         cudaGraph_t graph = nullptr;
         CUDA_TRY(cudaStreamBeginCapture(t->stream, cudaStreamCaptureModeThreadLocal));
         enqueue_step(t, o, t->stream);
+        t->hp_active = nullptr;
         cudaError_t e = cudaStreamEndCapture(t->stream, &graph);
         if (e != cudaSuccess || !graph) {
             set_err("graph capture failed: %s", cudaGetErrorString(e));
@@ -1440,6 +1476,7 @@ static int launch_step(UbTrainer* t, const StepOpts& o) {
         t->graph_valid = true, t->graph_gen_t = o.gen_t, t->graph_gen_noise = o.gen_noise;
         t->g_lr = o.lr, t->g_b1 = o.b1, t->g_b2 = o.b2, t->g_eps = o.eps, t->g_wd = o.wd;
     }
+    t->hp_active = nullptr;
     CUDA_TRY(cudaGraphLaunch(t->graph_exec, t->stream));
     ub_count_launches((unsigned long long)ub_trainer_launches_per_step(t));
     return UB_OK;
@@ -1486,6 +1523,20 @@ extern "C" int ub_trainer_profile(UbTrainer* t, int reps, UbProfile* out) {
     for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
     cudaStream_t st = t->stream;
     t->comm_off = true;  // a profile is rank-local: the peers are not replaying with us
+    // The timed replays run REAL optimizer steps (their time is part of the profile): snapshot parameters, AdamW moments
+    // and the step counter and restore them afterwards, so that profiling in the middle of a training run changes nothing.
+    float* snap = nullptr;
+    int snap_step = 0;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (cudaMalloc(&snap, 3 * t->nparams * sizeof(float)) == cudaSuccess) {
+        cudaMemcpy(snap, t->params, t->nparams * sizeof(float), cudaMemcpyDeviceToDevice);
+        cudaMemcpy(snap + t->nparams, t->m, t->nparams * sizeof(float), cudaMemcpyDeviceToDevice);
+        cudaMemcpy(snap + 2 * t->nparams, t->v, t->nparams * sizeof(float), cudaMemcpyDeviceToDevice);
+        cudaMemcpy(&snap_step, t->step_dev, sizeof(int), cudaMemcpyDeviceToHost);
+    } else {
+        cudaGetLastError();
+        snap = nullptr;
+    }
     for (int rep = 0; rep < reps; ++rep) {
         size_t k = 0;
         // the host needs ~3 us per launch + event, many kernels run for less: park the stream for a few ms so that the
@@ -1520,6 +1571,16 @@ extern "C" int ub_trainer_profile(UbTrainer* t, int reps, UbProfile* out) {
         }
         cudaEventElapsedTime(&ms, ev[j], ev[j + 1]);
         out->ms[UB_KIND_OPTIM] += ms;
+    }
+    if (snap) {
+        cudaMemcpy(t->params, snap, t->nparams * sizeof(float), cudaMemcpyDeviceToDevice);
+        cudaMemcpy(t->m, snap + t->nparams, t->nparams * sizeof(float), cudaMemcpyDeviceToDevice);
+        cudaMemcpy(t->v, snap + 2 * t->nparams, t->nparams * sizeof(float), cudaMemcpyDeviceToDevice);
+        cudaMemcpy(t->step_dev, &snap_step, sizeof(int), cudaMemcpyHostToDevice);
+        cudaMemset(t->grads, 0, t->nparams * sizeof(float));
+        run_pack(t, st);
+        cudaStreamSynchronize(st);
+        cudaFree(snap);
     }
     t->comm_off = false;
     for (auto& e : ev) cudaEventDestroy(e);
@@ -1681,6 +1742,7 @@ extern "C" int ub_trainer_get_dinput(UbTrainer* t, float* host, size_t n) {
 }
 
 static const int kModelMagic = 12345678;  // train_unet.py:781
+static const int kStepMagic = 0x55425354;  // "UBST": header[10] holds the AdamW step count of a checkpoint written here
 
 extern "C" int ub_read_checkpoint_header(const char* path, UbConfig* cfg) {
     FILE* f = fopen(path, "rb");
@@ -1733,7 +1795,12 @@ extern "C" int ub_trainer_load(UbTrainer* t, const char* path) {
     if (!r && header[8] == 1) {  // AdamW moments (train_unet.cu:4874-4886)
         r = read_arena(t->m);
         if (!r) r = read_arena(t->v);
-        const int step = header[10];
+        // The reference writer (save_unet_states, train_unet.cu:4764) fills header words 0..9 of an UNINITIALISED
+        // int[256]: words 10.. of a reference-written checkpoint are stack garbage.  The AdamW step count is therefore
+        // trusted only behind this library's own marker word; otherwise the count restarts at 0, which is what the
+        // reference's own resume does (its loop index restarts, train_unet.cu:5019-5037).  ub_trainer_set_step overrides.
+        int step = 0;
+        if (header[11] == kStepMagic && header[10] >= 0 && header[10] <= 1000000000) step = header[10];
         cudaMemcpy(t->step_dev, &step, sizeof(int), cudaMemcpyHostToDevice);
         t->host_step = step;
     }
@@ -1744,6 +1811,18 @@ extern "C" int ub_trainer_load(UbTrainer* t, const char* path) {
     }
     ensure_packed(t);
     CUDA_TRY(cudaStreamSynchronize(t->stream));
+    return UB_OK;
+}
+
+extern "C" int ub_trainer_set_step(UbTrainer* t, int step) {
+    if (step < 0) {
+        set_err("ub_trainer_set_step: negative step");
+        return UB_ERR_STATE;
+    }
+    CUDA_TRY(cudaSetDevice(t->device));
+    CUDA_TRY(cudaStreamSynchronize(t->stream));
+    CUDA_TRY(cudaMemcpy(t->step_dev, &step, sizeof(int), cudaMemcpyHostToDevice));
+    t->host_step = step;
     return UB_OK;
 }
 
@@ -1762,7 +1841,7 @@ extern "C" int ub_trainer_save(UbTrainer* t, const char* path, int with_adamw) {
     header[5] = c.H, header[6] = c.W, header[7] = c.max_period, header[8] = with_adamw ? 1 : 0, header[9] = 0;
     int step = 0;
     cudaMemcpy(&step, t->step_dev, sizeof(int), cudaMemcpyDeviceToHost);
-    header[10] = step;
+    header[10] = step, header[11] = kStepMagic;
     std::vector<float> buf(t->nparams);
     bool ok = fwrite(header, sizeof(int), 256, f) == 256;
     auto write_arena = [&](const float* dev) {
@@ -1813,6 +1892,9 @@ extern "C" int ub_trainer_attach_dp(UbTrainer* t, int rank, int world, const voi
         return UB_ERR_NCCL;
     }
     t->rank = rank, t->world = world;
+    // device-side timestep / noise draws are keyed by (seed, step): give every rank its own stream, otherwise ranks created
+    // with the same seed draw identical t and correlated noise for different images
+    t->cfg.seed ^= (unsigned long long)rank * 0x9E3779B97F4A7C15ULL;
     t->graph_valid = false;  // the step must be re-captured with the all-reduce nodes
     return UB_OK;
 }
