@@ -113,19 +113,36 @@ def cpu_step_timer(B: int, steps: int, warmup: int):
     return sum(times) / len(times), cores, torch.get_num_threads()
 
 
+def cpu_sample_batch(budget_s: float, n_steps: int) -> int:
+    """Largest batch in {32, 16, 8, 4} whose n_steps CPU steps fit the time budget (probe: one batch-4 step)."""
+    sec4, _, _ = cpu_step_timer(4, 1, 0)
+    for B in (32, 16, 8):
+        if sec4 * (B / 4.0) * n_steps <= budget_s:   # the CPU path scales ~linearly with the batch
+            return B
+    return 4
+
+
 def run_reference(args):
+    """The reference's own CPU implementation of the path (its PyTorch ground truth, restated in oracle/unet_oracle.py and
+    pinned against it) on all host cores, on this arm's config: default 64x64 U-Net, full train step, batch 32 per step
+    unless that would not finish within a few minutes on this box (then a smaller, stated, sample of the batch)."""
     rank, _, world = dist_env()
     if rank != 0:
         return
-    B = 4  # bounded sample of the batch-32 workload (configs[0] size): ~1-3 s of CPU work per step
-    sec, cores, threads = cpu_step_timer(B, args.steps, min(args.warmup, 2))
+    n = args.steps + args.warmup
+    B = cpu_sample_batch(240.0, n)
+    sec, cores, threads = cpu_step_timer(B, args.steps, args.warmup)
     val = B / sec
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 2), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "train_unet default 64x64 unconditional U-Net (20494211 params), full train step",
-                   "batch_per_step": B, "note": "CPU arm: each step is a batch-4 sample of the batch-32 workload"},
+        "config": {"workload": "train_unet default 64x64 unconditional U-Net (20494211 params, channel_mult 1-2-3-4, "
+                               "attention at 16x16 and 8x8), full train step (q-sample, fwd, MSE, bwd, AdamW)",
+                   "batch_per_gpu": 32, "global_batch": 32, "parallelism": "cpu",
+                   "batch_per_step": B,
+                   "note": ("CPU arm: full batch-32 steps" if B == 32 else
+                            f"CPU arm: each step is a batch-{B} sample of the batch-32 workload (bounded run time)")},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{args.steps} full train steps (fwd+bwd+AdamW) at batch {B}, torch CPU fp32, "
                                    f"{threads} threads of {cores} cores"},
@@ -233,18 +250,30 @@ def run_cuda(args):
         pk = peaks()
         conv = prof["conv_igemm"]
         conv_tf = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
+        traffic, traffic_note = conv_traffic()
         roofline = {
             "bound": "tensor", "kernel": "igemm_conv_kernel + igemm_conv2_kernel + igemm_rows_kernel (3x3/1x1 conv fprop+dgrad, qkv/proj GEMMs; tcgen05)",
             "achieved": conv_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-            "frac": conv_tf / pk["tf_sustained"], "traffic": conv_traffic(),
-            "traffic_note": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
-                            "profiles/r01_tc_traffic.json; writes are absorbed by the L2 within the kernel); "
-                            "algorithmic bytes per launch = bytes_per_launch",
+            "frac": conv_tf / pk["tf_sustained"], "traffic": traffic, "traffic_note": traffic_note,
             "bytes_per_launch": conv["bytes"] / max(conv["launches"], 1),
             "peak_source": pk["source"] + ", sustained bf16",
             "flops_per_launch": conv["flops"] / max(conv["launches"], 1),
             "avg_launch_ms": conv["ms"] / max(conv["launches"], 1), "launches_per_step": conv["launches"],
             "share_of_step": conv["ms"] / prof["total_ms"],
+        }
+        # the other two kernel classes that carry most of the step: weight gradients (tensor) and GroupNorm (HBM)
+        wg, gn = prof["wgrad_igemm"], prof["groupnorm"]
+        wg_tf = wg["flops"] / (wg["ms"] * 1e-3) / 1e12 if wg["ms"] > 0 else 0.0
+        gn_gbs = gn["bytes"] / (gn["ms"] * 1e-3) / 1e9 if gn["ms"] > 0 else 0.0
+        roofline_more = {
+            "wgrad": {"bound": "tensor", "kernel": "igemm_wgrad_kernel (tcgen05, split-K, vector-RED accumulation)",
+                      "achieved": wg_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": wg_tf / pk["tf_sustained"],
+                      "launches_per_step": wg["launches"], "avg_launch_ms": wg["ms"] / max(wg["launches"], 1)},
+            "groupnorm": {"bound": "hbm", "kernel": "gn_apply / gn_bwd_apply_dz / gn_stats (+ gn_slab_*)",
+                          "achieved": gn_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gn_gbs / pk["hbm_gbs"],
+                          "launches_per_step": gn["launches"], "avg_launch_ms": gn["ms"] / max(gn["launches"], 1),
+                          "note": "algorithmic bytes / event time; most launches are latency-bound tensors of <= 4 MB "
+                                  "(ncu per-kernel DRAM throughput: profiles/r02_ncu_hbm_kernels.txt)"},
         }
         classes = {}
         for k in ub.UB_KINDS:
@@ -268,15 +297,18 @@ def run_cuda(args):
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 3 * 64 * 64 * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": float(e2e_ms.item())},
-            "roofline": roofline, "kernel_classes": classes, "profile_total_ms": prof["total_ms"],
+            "roofline": roofline, "roofline_more": roofline_more, "kernel_classes": classes,
+            "profile_total_ms": prof["total_ms"],
             "model_tflops": value * FLOP_PER_IMG_FWD_BWD / 1e12 / world,
             "loss_after": loss_now,
         }
         if world == 1 and not args.no_cpu_baseline:
-            sec, cores, threads = cpu_step_timer(4, 5, 1)
-            line["cpu_baseline"] = {"value": 4 / sec, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"5 full train steps at batch 4 (a batch-4 sample of the batch-32 "
-                                              f"workload), torch CPU fp32 oracle, {threads} threads"}
+            Bc = cpu_sample_batch(25.0, 4)
+            sec, cores, threads = cpu_step_timer(Bc, 3, 1)
+            line["cpu_baseline"] = {"value": Bc / sec, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"3 full train steps at batch {Bc}"
+                                              + ("" if Bc == 32 else f" (a batch-{Bc} sample of the batch-32 workload)")
+                                              + f", torch CPU fp32 oracle, {threads} threads of {cores} cores"}
             ref = reference_cuda_baseline(args)
             if ref:
                 line["reference_cuda"] = ref
@@ -339,19 +371,37 @@ def conv_microbench(ub, pk):
     return out
 
 
+def kernel_source_hash():
+    """sha1 over the tcgen05 conv kernel sources: profiles/*_tc_traffic.json is only valid for the kernels it was
+    captured from."""
+    import hashlib
+    h = hashlib.sha1()
+    for f in ("igemm.cu", "igemm_rows.cu", "epilogue.cuh", "ptx.cuh", "igemm.cuh"):
+        with open(os.path.join(ROOT, "unet.cu_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:12]
+
+
 def conv_traffic():
-    """DRAM bytes per launch of the conv kernel (read + write) from the committed ncu capture of one training step
-    (profiles/r01_tc_traffic.json, produced by tools/measure_all.sh + tools/traffic_summary.py); None if absent."""
-    p = os.path.join(ROOT, "profiles", "r01_tc_traffic.json")
+    """DRAM bytes per launch of the conv kernels (read + write) from the committed ncu capture of one training step
+    (profiles/r02_tc_traffic.json, produced by tools/measure_all.sh + tools/traffic_summary.py, stamped with the hash of
+    the kernel sources it was taken from).  (None, why) when absent or stale."""
+    p = os.path.join(ROOT, "profiles", "r02_tc_traffic.json")
     try:
         with open(p) as f:
             d = json.load(f)
+        stamp = d.get("_kernel_source_hash")
+        if stamp != kernel_source_hash():
+            return None, f"profiles/r02_tc_traffic.json was captured from kernel sources {stamp}, current {kernel_source_hash()}: stale"
         ks = [v for k, v in d.items() if k in ("igemm_conv_kernel", "igemm_conv2_kernel", "igemm_rows_kernel")]
         n = sum(v["launches"] for v in ks)
         byts = sum(v["launches"] * (v["dram_read_bytes_per_launch"] + v["dram_write_bytes_per_launch"]) for v in ks)
-        return byts / n if n else None
-    except Exception:
-        return None
+        return (byts / n if n else None), ("DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                           "training step, profiles/r02_tc_traffic.json, kernel sources " + stamp +
+                                           "; writes are absorbed by the L2 within the kernel); algorithmic bytes per "
+                                           "launch = bytes_per_launch")
+    except Exception as e:
+        return None, f"no ncu traffic capture ({type(e).__name__})"
 
 
 def reference_cuda_baseline(args):
@@ -376,8 +426,8 @@ def reference_cuda_baseline(args):
                                   "log.txt"], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
             t0 = time.time()
             pts = []
-            while time.time() - t0 < 90:   # its first log line appears after 100 iterations
-                time.sleep(1.0)
+            while time.time() - t0 < 170:   # a log line every 100 iterations: wait for two of them
+                time.sleep(0.5)
                 if os.path.exists(log):
                     pts = []
                     for ln in open(log).read().splitlines():
@@ -385,17 +435,24 @@ def reference_cuda_baseline(args):
                             it = int(ln.split("/")[0].split()[1])
                             sec = float(ln.split("cur time")[1].split()[0])
                             pts.append((it, sec))
-                    if pts or p.poll() is not None:
+                    if len(pts) >= 2 or p.poll() is not None:
                         break
             p.kill()
             p.wait()
+            what = ("reference train_unet.cu (fp32 SIMT + cuBLAS), unmodified, nvcc -O3 --use_fast_math -arch=sm_100, same "
+                    "GPU, from its own 'cur time' log (CUDA-event time since its loop started, train_unet.cu:5014-5043)")
+            if len(pts) >= 2:   # steady state: the delta between two consecutive log lines (no cold start, no lazy mallocs)
+                (i0, s0), (i1, s1) = pts[-2], pts[-1]
+                ms = (s1 - s0) / (i1 - i0) * 1e3
+                cold = s0 / i0 * 1e3
+                return {"ms_per_step": ms, "value": 32 / (ms * 1e-3), "unit": UNIT, "batch": 32, "what": what,
+                        "iters_measured": [i0, i1], "ms_per_step_first_interval_incl_cold_start": cold}
             if pts:
-                it, sec = pts[-1]   # 'cur time' is CUDA-event time since the loop started (train_unet.cu:5014-5043)
+                it, sec = pts[-1]
                 ms = sec / it * 1e3
                 return {"ms_per_step": ms, "value": 32 / (ms * 1e-3), "unit": UNIT, "batch": 32,
-                        "what": "reference train_unet.cu (fp32 SIMT + cuBLAS), unmodified, nvcc -O3 --use_fast_math "
-                                "-arch=sm_100, same GPU, its own 'cur time' log", "iters_measured": it}
-            return {"error": "no log line within 90 s"}
+                        "what": what + "; cumulative over the first interval (includes cold start)", "iters_measured": it}
+            return {"error": "no log line within 170 s"}
     except Exception as e:  # the comparison line is best effort
         return {"error": str(e)[:200]}
     return None

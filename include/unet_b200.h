@@ -234,6 +234,9 @@ typedef struct {
     unsigned long long seed;
     int use_cuda_graph;  /* capture the whole step in one CUDA graph */
     int compute_dinput;  /* also compute dL/d(x_t) (the reference's unet_backward does, dev/unet_test.cu:2103); 0 */
+    int random_flip;     /* on-GPU augmentation: every image of a batch is mirrored left-right with probability 1/2 before
+                            q-sample (the PyTorch loader's random_flip, train_unet.py:508-536: arr[:, ::-1]; the reference's
+                            C loader has none).  Decisions are Philox draws keyed by (seed, step, image); 0 */
 } UbConfig;
 
 void ub_default_config(UbConfig* cfg);
@@ -260,6 +263,8 @@ int ub_trainer_set_params(UbTrainer* t, const float* host, size_t n);
 int ub_trainer_get_params(UbTrainer* t, float* host, size_t n);
 int ub_trainer_get_grads(UbTrainer* t, float* host, size_t n);
 int ub_trainer_get_output(UbTrainer* t, float* host, size_t n); /* last forward's eps prediction (B,C_out,H,W) */
+/* the flip decisions (0 / 1 per image) the last step took, when cfg.random_flip is set */
+int ub_trainer_get_flips(UbTrainer* t, int* host, size_t n);
 int ub_trainer_get_dinput(UbTrainer* t, float* host, size_t n); /* dL/d(x_t) (B,C_in,H,W); needs cfg.compute_dinput */
 
 /* One forward + backward (unet_forward + unet_backward, train_unet.cu:4335-4701) on a HOST batch x0 (B,C_in,H,W).

@@ -376,6 +376,16 @@ def ddpm_sample(cfg: UNetConfig, P: Dict[str, torch.Tensor], x: torch.Tensor, t_
     return x
 
 
+def random_flip(x0: torch.Tensor, flips) -> torch.Tensor:
+    """train_unet.py:531-532 (ImageDataset.__getitem__): `arr = arr[:, ::-1]` on the HWC image = mirror the width axis
+    of every image whose coin came up; `flips` holds the coins (the reference draws them with np.random.rand() < 0.5)."""
+    out = x0.clone()
+    for b, f in enumerate(flips):
+        if int(f):
+            out[b] = torch.flip(x0[b], dims=[-1])
+    return out
+
+
 def mse_loss(out: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     """train_unet.cu:2981-3030: mean over all elements."""
     return ((out - target) ** 2).mean()

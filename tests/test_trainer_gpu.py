@@ -185,6 +185,35 @@ def test_device_noise_statistics(ub, setup):
     tr.close()
 
 
+def test_random_flip_matches_oracle(ub, setup):
+    """On-GPU augmentation (cfg.random_flip; the PyTorch loader's random_flip, train_unet.py:508-536): the step must
+    equal the oracle's step on the batch mirrored by the same coins, the coins are fair and change from step to step."""
+    O, cfg, flat = setup
+    B = 8
+    x0, t, noise = O.synthetic_batch(cfg, B, seed=77)
+    tr = ub.Trainer(B=B, random_flip=1)
+    tr.set_params(flat.numpy())
+    seen = []
+    for step in range(3):
+        loss = tr.forward_backward(x0.numpy(), t.numpy(), noise.numpy())
+        flips = tr.get_flips()
+        assert set(np.unique(flips)) <= {0, 1}
+        seen.append(flips.copy())
+        loss_ref, out_ref, _ = O.train_step_grads(cfg, flat, O.random_flip(x0, flips), t, noise)
+        assert abs(loss - float(loss_ref)) <= 2e-3 * float(loss_ref), (step, flips)
+        assert np.abs(tr.get_output() - out_ref.numpy()).max() <= 3e-2 * np.abs(out_ref.numpy()).max()
+        tr.update(lr=0.0)   # advances the step counter that keys the draws; lr 0 keeps the parameters
+    allf = np.concatenate(seen)
+    assert 0 < allf.sum() < allf.size                      # both outcomes occur in 24 fair coins (p = 1 - 2^-23)
+    assert any((seen[0] != s).any() for s in seen[1:])     # not the same coins every step
+    tr.close()
+    # without the flag nothing is flipped and the call says so
+    tr = ub.Trainer(B=2)
+    with pytest.raises(ub.UbError):
+        tr.get_flips()
+    tr.close()
+
+
 def test_checkpoint_roundtrip_and_reference_layout(ub, setup, tmp_path):
     O, cfg, flat = setup
     tr = ub.Trainer(B=2)

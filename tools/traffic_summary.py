@@ -23,6 +23,11 @@ out = {n: {"launches": c, "avg_us": round(t / c, 2), "dram_read_bytes_per_launch
 out["_how"] = ("ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none over the "
                "tcgen05 launches of one eager B=32 training step (tools/measure_all.sh); DRAM writes land in the 126 MB L2 "
                "and are written back after the kernel, so the write counter reads ~0")
+# stamp: bench.py reports this capture only while the kernel sources are the ones it was taken from
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+out["_kernel_source_hash"] = bench.kernel_source_hash()
 json.dump(out, open(sys.argv[2], 'w'), indent=1)
 for n, v in out.items():
     print(n, v)

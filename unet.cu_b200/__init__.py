@@ -29,7 +29,7 @@ class UbConfig(C.Structure):
                 ("W", C.c_int), ("max_period", C.c_int), ("n_levels", C.c_int), ("channel_mult", C.c_int * 8),
                 ("n_res_blocks", C.c_int), ("att_start_level", C.c_int), ("head_size", C.c_int),
                 ("gn_n_groups", C.c_int), ("n_timesteps", C.c_int), ("seed", C.c_ulonglong),
-                ("use_cuda_graph", C.c_int), ("compute_dinput", C.c_int)]
+                ("use_cuda_graph", C.c_int), ("compute_dinput", C.c_int), ("random_flip", C.c_int)]
 
 
 UB_KINDS = ("conv_igemm", "wgrad_igemm", "groupnorm", "attention", "eltwise", "small", "optimizer")
@@ -84,6 +84,7 @@ def _declare(L: C.CDLL) -> None:
     L.ub_trainer_sync.argtypes = [vp]
     L.ub_trainer_last_loss.argtypes = [vp, C.POINTER(C.c_float)]
     L.ub_trainer_set_step.argtypes = [vp, i]
+    L.ub_trainer_get_flips.argtypes = [vp, vp, C.c_size_t]
     L.ub_set_layer_precision.argtypes = [i]
     L.ub_groupnorm_nhwc_forward.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i]
     L.ub_groupnorm_nhwc_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i]
@@ -174,6 +175,12 @@ class Trainer:
     def get_dinput(self):
         c = self.cfg
         return self._get(lib().ub_trainer_get_dinput, c.B * c.C_in * c.H * c.W).reshape(c.B, c.C_in, c.H, c.W)
+
+    def get_flips(self) -> np.ndarray:
+        """0 / 1 per image: the random horizontal flips of the last step (cfg.random_flip, train_unet.py:531-532)."""
+        out = np.empty(self.cfg.B, dtype=np.int32)
+        check(lib().ub_trainer_get_flips(self._h, out.ctypes.data_as(C.c_void_p), out.size), "get_flips")
+        return out
 
     def get_output(self):
         c = self.cfg

@@ -833,6 +833,15 @@ int igemm_conv_plan(IgemmConvParams* p, const ConvSegDesc* segs, int nseg, int B
     if (stages < 3) stages = int((227u * 1024u - tail) / p->stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) return -3;
+    if (p->nacc == 2) {
+        // One CTA per SM: the main loop of these sub-chip grids is paced by L2->SMEM latency x bytes in flight
+        // (profiles/r02_tma_ingest_bench.txt: 64 KiB in flight = 52 B/clk/SM, 128 KiB = 104), so the ring may use more
+        // than the two-CTA budget.  UB_CONV2_SMEM_KB bounds it (a wgrad CTA of the side stream wants 96 KiB beside it).
+        static const int kb = getenv("UB_CONV2_SMEM_KB") ? atoi(getenv("UB_CONV2_SMEM_KB")) : 128;
+        int s2 = int((uint32_t(kb) * 1024u - tail) / p->stage_bytes);
+        if (s2 > kMaxStages) s2 = kMaxStages;
+        if (s2 > stages) stages = s2;
+    }
     if (p->nacc == 2 && (stages & 1)) {
         // Two issuers need an EVEN ring: with an odd one the owner of a stage alternates, an issuer skips every other
         // phase of a full barrier, and a parity wait that comes one whole phase early passes immediately (this was a

@@ -546,7 +546,7 @@ __global__ void diffusion_prepare_kernel(const float* __restrict__ x0, const flo
                                          const float* __restrict__ sqrt_1mac, size_t total4, size_t per_image,
                                          uint64_t seed, const int* __restrict__ step_dev, int gen_noise,
                                          const float* __restrict__ t, float* __restrict__ noise,
-                                         float* __restrict__ x_t) {
+                                         float* __restrict__ x_t, int W, int* __restrict__ flips) {
     pdl_entry();
     const size_t i4 = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i4 >= total4) return;
@@ -567,17 +567,32 @@ __global__ void diffusion_prepare_kernel(const float* __restrict__ x0, const flo
     const int b = int(i / per_image);  // per_image % 4 == 0, so the 4 elements share one image
     const int ti = int(t[b]);
     const float a = sqrt_ac[ti], s = sqrt_1mac[ti];
-    const float4 x = *reinterpret_cast<const float4*>(x0 + i);
+    float4 x;
+    if (flips) {  // random horizontal flip (train_unet.py:531-532), one Philox coin per (step, image); W % 4 == 0
+        const uint4 r = philox4x32_10(make_uint4(uint32_t(b), 0u, 0x9u, uint32_t(*step_dev)),
+                                      make_uint2(uint32_t(seed), uint32_t(seed >> 32)));
+        const int flip = int(r.x >> 31);
+        if (i == size_t(b) * per_image) flips[b] = flip;
+        if (flip) {
+            const size_t row = i - i % size_t(W), w = i % size_t(W);
+            const float4 m = *reinterpret_cast<const float4*>(x0 + row + (size_t(W) - 4 - w));
+            x = make_float4(m.w, m.z, m.y, m.x);
+        } else {
+            x = *reinterpret_cast<const float4*>(x0 + i);
+        }
+    } else {
+        x = *reinterpret_cast<const float4*>(x0 + i);
+    }
     *reinterpret_cast<float4*>(x_t + i) = make_float4(a * x.x + s * e.x, a * x.y + s * e.y, a * x.z + s * e.z,
                                                       a * x.w + s * e.w);
 }
 void diffusion_prepare(const float* x0, const float* sqrt_ac, const float* sqrt_1mac, int B, size_t per_image,
                        int n_timesteps, uint64_t seed, const int* step_dev, int gen_t, int gen_noise, float* t,
-                       float* noise, float* x_t, cudaStream_t st) {
+                       float* noise, float* x_t, cudaStream_t st, int W, int* flips) {
     if (gen_t) launch_pdl(diffusion_t_kernel, dim3((B + 127) / 128), dim3(128), 0, st, B, n_timesteps, seed, step_dev, t);
     const size_t total4 = size_t(B) * per_image / 4;
     launch_pdl(diffusion_prepare_kernel, dim3(unsigned((total4 + 255) / 256)), dim3(256), 0, st, x0, sqrt_ac, sqrt_1mac, total4, per_image,
-                                                                             seed, step_dev, gen_noise, t, noise, x_t);
+                                                                             seed, step_dev, gen_noise, t, noise, x_t, W, flips);
 }
 
 // =====================================================================================================

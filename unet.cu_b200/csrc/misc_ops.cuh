@@ -51,7 +51,7 @@ void timestep_embedding(const float* t, int B, int dim, int max_period, float* o
 //      t / noise buffers are used as they are (parity runs inject the oracle's draws).
 void diffusion_prepare(const float* x0, const float* sqrt_ac, const float* sqrt_1mac, int B, size_t per_image,
                        int n_timesteps, uint64_t seed, const int* step_dev, int gen_t, int gen_noise, float* t,
-                       float* noise, float* x_t, cudaStream_t st);
+                       float* noise, float* x_t, cudaStream_t st, int W = 0, int* flips = nullptr);
 
 // ---- weight packing: fp32 master (Cout, Cin, ntaps) -> bf16 fprop pack [tap][Cout][Cin] and (optional) dgrad pack
 //      [ntaps-1-tap][Cin][Cout]

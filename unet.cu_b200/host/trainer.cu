@@ -130,6 +130,7 @@ struct UbTrainer {
     // io buffers
     float *x0 = nullptr, *xt = nullptr, *noise = nullptr, *tsteps = nullptr, *out = nullptr, *dout = nullptr;
     float* dxt = nullptr;  // dL/d(x_t), only with cfg.compute_dinput
+    int* flips = nullptr;  // per-image flip decisions of the last step, only with cfg.random_flip
     float *loss = nullptr, *sqrt_ac = nullptr, *sqrt_1mac = nullptr, *betas = nullptr;
     int* samp_state = nullptr;  // {t, iteration} of the sampling loop
     cudaGraphExec_t samp_graph = nullptr;
@@ -475,6 +476,14 @@ struct Builder {
         const int m = gn_mode();
         return m == 1 || (m == 3 && !use_slab(C, H, W));
     }
+    // The gn-bwd pre-pass hook (x read + silu' + two column sums in the dgrad epilogue) makes the 64x64 dgrad convs
+    // epilogue-bound (39 us against 24 us unhooked): above UB_GN_BWD_HOOK_MAX_HW pixels per image the backward uses the
+    // separate statistics pass instead (the forward statistics hook stays).
+    static int bwd_hook_max_hw() {
+        static const int v = getenv("UB_GN_BWD_HOOK_MAX_HW") ? atoi(getenv("UB_GN_BWD_HOOK_MAX_HW")) : (1 << 30);
+        return v;
+    }
+    bool use_bwd_hook(int C, int H, int W) const { return use_hooks(C, H, W) && H * W <= bwd_hook_max_hw(); }
     float* stats_buf(int C, int H, int W) { return use_hooks(C, H, W) ? zf32(size_t(B) * C * 2) : nullptr; }
     GN gn_fwd(View x, View y, int silu) {
         GN g;
@@ -504,12 +513,12 @@ struct Builder {
     // Fuse the first half of GroupNorm(+SiLU) backward into the epilogue of the dgrad conv that produces dL/dy:
     // that conv then writes dz = dL/d gn(x) and accumulates S (see epilogue.cuh); call gn_bwd(..., fused = true) after.
     void gn_hook(ConvEpilogue& ep, const GN& g, View x, int silu) {
-        if (!use_hooks(x.C, x.H, x.W)) return;
+        if (!use_bwd_hook(x.C, x.H, x.W)) return;
         ep.gn_x = x.p, ep.gn_ldx = x.ld, ep.gn_chsum = g.chsum, ep.gn_gamma = P(g.w), ep.gn_beta = P(g.b);
         ep.gn_S = g.S, ep.gn_silu = silu, ep.gn_groups = c.gn_n_groups;
     }
     void gn_bwd(const GN& g, View x, View dy, int silu, View add_in, View dx, float* colsum_out, bool fused = false) {
-        fused = fused && use_hooks(x.C, x.H, x.W);
+        fused = fused && use_bwd_hook(x.C, x.H, x.W);
         const int HW = x.H * x.W, Gn = c.gn_n_groups;
         float *gw = P(g.w), *gb = P(g.b), *cs = g.chsum, *S = g.S, *dgw = G(g.w), *dgb = G(g.b);
         const bool slab = !fused && use_slab(x.C, x.H, x.W);
@@ -757,6 +766,7 @@ int Builder::build() {
     T->x0 = f32(size_t(B) * img), T->xt = f32(size_t(B) * img), T->noise = f32(size_t(B) * img);
     T->tsteps = f32(B);
     T->dxt = c.compute_dinput ? f32(size_t(B) * img) : nullptr;
+    T->flips = c.random_flip ? (int*)T->arena.alloc(size_t(B) * sizeof(int) + 256) : nullptr;
     T->out = f32(size_t(B) * c.C_out * H0 * W0), T->dout = f32(size_t(B) * c.C_out * H0 * W0);
     T->sqrt_ac = f32(c.n_timesteps), T->sqrt_1mac = f32(c.n_timesteps), T->betas = f32(c.n_timesteps);
     T->samp_state = (int*)T->arena.alloc(256);
@@ -1091,6 +1101,10 @@ static int validate_config(const UbConfig& c) {
         set_err("H, W must be divisible by 2^(n_levels-1)");
         return UB_ERR_SHAPE;
     }
+    if (c.random_flip && c.W % 4) {
+        set_err("random_flip needs W %% 4 == 0");
+        return UB_ERR_SHAPE;
+    }
     if ((size_t(c.C_in) * c.H * c.W) % 4) {
         set_err("C_in*H*W must be a multiple of 4");
         return UB_ERR_SHAPE;
@@ -1281,7 +1295,7 @@ static void enqueue_step(UbTrainer* t, const StepOpts& o, cudaStream_t st) {
     const UbConfig& c = t->cfg;
     cudaMemsetAsync(t->zero_base, 0, t->zero_bytes, st);
     diffusion_prepare(t->x0, t->sqrt_ac, t->sqrt_1mac, c.B, size_t(c.C_in) * c.H * c.W, c.n_timesteps, c.seed,
-                      t->step_dev, o.gen_t ? 1 : 0, o.gen_noise ? 1 : 0, t->tsteps, t->noise, t->xt, st);
+                      t->step_dev, o.gen_t ? 1 : 0, o.gen_noise ? 1 : 0, t->tsteps, t->noise, t->xt, st, c.W, t->flips);
     static const bool debug_sync = getenv("UB_DEBUG_SYNC") != nullptr;  // eager runs only: find the faulting op
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (debug_sync) cudaStreamIsCapturing(st, &cap);
@@ -1545,7 +1559,7 @@ extern "C" int ub_trainer_profile(UbTrainer* t, int reps, UbProfile* out) {
         cudaEventRecord(ev[k++], st);
         cudaMemsetAsync(t->zero_base, 0, t->zero_bytes, st);
         diffusion_prepare(t->x0, t->sqrt_ac, t->sqrt_1mac, c.B, size_t(c.C_in) * c.H * c.W, c.n_timesteps, c.seed,
-                          t->step_dev, 1, 1, t->tsteps, t->noise, t->xt, st);
+                          t->step_dev, 1, 1, t->tsteps, t->noise, t->xt, st, c.W, t->flips);
         cudaEventRecord(ev[k++], st);
         for (auto& op : t->fwd_ops) op(st), cudaEventRecord(ev[k++], st);
         for (auto& op : t->bwd_ops) op(st), cudaEventRecord(ev[k++], st);
@@ -1739,6 +1753,21 @@ extern "C" int ub_trainer_get_dinput(UbTrainer* t, float* host, size_t n) {
     }
     const UbConfig& c = t->cfg;
     return copy_out(t, t->dxt, host, n, size_t(c.B) * c.C_in * c.H * c.W);
+}
+
+extern "C" int ub_trainer_get_flips(UbTrainer* t, int* host, size_t n) {
+    if (!t->flips) {
+        set_err("flip decisions exist only when the trainer was created with cfg.random_flip = 1");
+        return UB_ERR_STATE;
+    }
+    if (n != size_t(t->cfg.B)) {
+        set_err("ub_trainer_get_flips: expected %d entries", t->cfg.B);
+        return UB_ERR_SHAPE;
+    }
+    CUDA_TRY(cudaSetDevice(t->device));
+    CUDA_TRY(cudaStreamSynchronize(t->stream));
+    CUDA_TRY(cudaMemcpy(host, t->flips, n * sizeof(int), cudaMemcpyDeviceToHost));
+    return UB_OK;
 }
 
 static const int kModelMagic = 12345678;  // train_unet.py:781
