@@ -34,8 +34,18 @@ __device__ __forceinline__ uint32_t elect_one_sync() {
         : "r"(0xFFFFFFFF));
     return pred;
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// poll = 1: mbarrier.test_wait in a spin loop (never suspends the thread) instead of try_wait (may suspend for a
+// system-dependent time before it re-checks)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int poll = 0) {
     uint32_t ok = 0;
+    if (poll) {
+        while (!ok)
+            asm volatile("{\n.reg .pred P;\nmbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\nselp.b32 %0, 1, 0, P;\n}\n"
+                         : "=r"(ok)
+                         : "r"(bar), "r"(parity)
+                         : "memory");
+        return;
+    }
     while (!ok)
         asm volatile("{\n.reg .pred P;\nmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\nselp.b32 %0, 1, 0, P;\n}\n"
                      : "=r"(ok)
@@ -47,6 +57,7 @@ struct IP {
     int stages, boxes, rows;  // stage = boxes x (rows x 128 B)
     int iters;                // stages pulled per CTA
     int total_rows;           // rows of the global tensor (working set = total_rows x 128 B)
+    int poll;                 // 1 = test_wait spin loops
 };
 
 __global__ void __launch_bounds__(64) ingest(const __grid_constant__ CUtensorMap tm, const IP p, unsigned long long* out) {
@@ -74,7 +85,7 @@ __global__ void __launch_bounds__(64) ingest(const __grid_constant__ CUtensorMap
         uint32_t row = blockIdx.x * p.boxes * p.rows;
         const uint32_t mask = (uint32_t)p.total_rows - 1u;  // total_rows is a power of two, rows divides it
         for (int it = 0; it < p.iters; ++it) {
-            mbar_wait(smem_u32(&empty[st]), ph ^ 1);
+            mbar_wait(smem_u32(&empty[st]), ph ^ 1, p.poll);
             if (elect_one_sync()) {
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[st])), "r"(stage_bytes)
                              : "memory");
@@ -95,7 +106,7 @@ __global__ void __launch_bounds__(64) ingest(const __grid_constant__ CUtensorMap
         int st = 0;
         uint32_t ph = 0;
         for (int it = 0; it < p.iters; ++it) {
-            mbar_wait(smem_u32(&full[st]), ph);
+            mbar_wait(smem_u32(&full[st]), ph, p.poll);
             if (elect_one_sync()) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[st])) : "memory");
             __syncwarp();
             if (++st == p.stages) st = 0, ph ^= 1;
@@ -128,11 +139,14 @@ int main() {
     struct Cfg { int stages, boxes, rows; };
     const Cfg cfgs[] = {{2, 1, 128}, {4, 1, 128}, {6, 1, 128}, {8, 1, 128}, {12, 1, 128}, {3, 3, 128}, {4, 3, 128},
                         {4, 1, 256}, {6, 1, 256}, {3, 2, 256}, {8, 1, 64}, {16, 1, 64}, {2, 3, 256}, {6, 2, 128}, {4, 2, 128}};
-    for (int ws = 0; ws < 2; ++ws) {
+    const int poll = getenv("POLL") ? atoi(getenv("POLL")) : 0;
+    const int only_l2 = getenv("ONLY_L2") ? 1 : 0;
+    printf("# wait = %s\n", poll ? "mbarrier.test_wait spin" : "mbarrier.try_wait");
+    for (int ws = 0; ws < (only_l2 ? 1 : 2); ++ws) {
         const size_t rows_total = ws == 0 ? ((size_t)32 << 20) / 128 : big_rows;  // 32 MiB (L2 resident) or 2 GiB (DRAM)
         for (int grid : {nsm, 64, 16}) {
             for (const Cfg& c : cfgs) {
-                IP p{c.stages, c.boxes, c.rows, 0, (int)rows_total};
+                IP p{c.stages, c.boxes, c.rows, 0, (int)rows_total, poll};
                 const size_t stage_bytes = (size_t)c.boxes * c.rows * 128;
                 if (c.stages * stage_bytes > 200 * 1024) continue;
                 p.iters = (int)std::max<size_t>(64, ((size_t)8 << 20) / stage_bytes);  // ~8 MiB per CTA

@@ -498,8 +498,21 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dkv_kernel(const __grid_cons
             const int gq = t.col0 + col;
             float L = 0.f, D = 0.f;
             if (gq < p.B * p.T) {
-                const size_t idx = (size_t(gq / p.T) * p.NH + t.hp * 2 + h) * p.T + gq % p.T;
-                L = p.lse[idx], D = p.dsum[idx];
+                const int head = t.hp * 2 + h;
+                const size_t idx = (size_t(gq / p.T) * p.NH + head) * p.T + gq % p.T;
+                L = p.lse[idx];
+                // D = rowsum(dO o O) of the query, recomputed here (32 products) instead of read from the dq kernel's
+                // dsum: the two backward kernels then have no dependency and run concurrently (attn_tc_bwd)
+                const uint4* gp = reinterpret_cast<const uint4*>(p.dout + size_t(gq) * p.lddo + head * HS);
+                const uint4* op = reinterpret_cast<const uint4*>(p.out + size_t(gq) * p.ldo + head * HS);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float a[8], o[8];
+                    unpack8(gp[j], a);
+                    unpack8(op[j], o);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) D = fmaf(a[e], o[e], D);
+                }
             }
             sL[h * 256 + col] = L, sD[h * 256 + col] = D;
         }
@@ -632,14 +645,27 @@ int attn_tc_fwd(const AttnTcParams& p, cudaStream_t st) {
     return int(cudaGetLastError());
 }
 
-int attn_tc_bwd(const AttnTcParams& p, cudaStream_t st) {
+// dq and dkv are independent (each recomputes S and D): with an auxiliary stream and two events the dkv kernel runs
+// beside the dq kernel (fork after everything enqueued on st so far, join before st continues); works eagerly and
+// under stream capture (the fork / join become graph edges).  aux == nullptr: both on st, one after the other.
+int attn_tc_bwd(const AttnTcParams& p, cudaStream_t st, cudaStream_t aux, cudaEvent_t ev_fork, cudaEvent_t ev_join) {
     attn_tc_init();
+    cudaStream_t s2 = st;
+    if (aux && ev_fork && ev_join) {
+        cudaEventRecord(ev_fork, st);
+        cudaStreamWaitEvent(aux, ev_fork, 0);
+        s2 = aux;
+    }
     if (p.T >= 128) {
+        launch_pdl(attn_tc_dkv_kernel<false>, dim3(attn_grid(p)), dim3(kThreads), smem_dkv(attn_ncols(p)), s2, p);
         launch_pdl(attn_tc_dq_kernel<false>, dim3(attn_grid(p)), dim3(kThreads), smem_dq(attn_ncols(p)), st, p);
-        launch_pdl(attn_tc_dkv_kernel<false>, dim3(attn_grid(p)), dim3(kThreads), smem_dkv(attn_ncols(p)), st, p);
     } else {
+        launch_pdl(attn_tc_dkv_kernel<true>, dim3(attn_grid(p)), dim3(kThreads), smem_dkv(attn_ncols(p)), s2, p);
         launch_pdl(attn_tc_dq_kernel<true>, dim3(attn_grid(p)), dim3(kThreads), smem_dq(attn_ncols(p)), st, p);
-        launch_pdl(attn_tc_dkv_kernel<true>, dim3(attn_grid(p)), dim3(kThreads), smem_dkv(attn_ncols(p)), st, p);
+    }
+    if (s2 != st) {
+        cudaEventRecord(ev_join, s2);
+        cudaStreamWaitEvent(st, ev_join, 0);
     }
     return int(cudaGetLastError());
 }

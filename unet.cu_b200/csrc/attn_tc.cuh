@@ -20,7 +20,7 @@ struct AttnTcParams {
     int lddo;
     __nv_bfloat16* dqkv;  // [B*T][ldd], sections [dQ | dK | dV]
     int ldd;
-    float* dsum;          // [B][NH][T] rowsum(dO o O), written by the dq kernel, read by the dkv kernel
+    float* dsum;          // [B][NH][T] rowsum(dO o O), written by the dq kernel (the dkv kernel recomputes it)
 };
 
 bool attn_tc_supported(int T, int NH, int HS);
@@ -29,6 +29,7 @@ void attn_tc_init();
 int attn_tc_plan(AttnTcParams* p, const __nv_bfloat16* qkv, int ld, int B, int T, int NH, int HS, __nv_bfloat16* out,
                  int ldo, float* lse, const __nv_bfloat16* dout, int lddo, __nv_bfloat16* dqkv, int ldd, float* dsum);
 int attn_tc_fwd(const AttnTcParams& p, cudaStream_t st);
-int attn_tc_bwd(const AttnTcParams& p, cudaStream_t st);
+int attn_tc_bwd(const AttnTcParams& p, cudaStream_t st, cudaStream_t aux = nullptr, cudaEvent_t ev_fork = nullptr,
+                cudaEvent_t ev_join = nullptr);
 
 }  // namespace ub

@@ -13,6 +13,8 @@
 #include <cstring>
 #include <algorithm>
 #include <functional>
+#include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -105,6 +107,11 @@ struct UbTrainer {
     // they run on a side stream, concurrently with the dgrad -> GroupNorm -> dgrad critical path of backward (in the
     // captured graph this is a parallel branch).  Both kinds of kernel are latency-bound on their own.
     cudaStream_t side_stream = nullptr;
+    // Auxiliary main-priority stream for a short fork inside ONE main-stream op (fork and join within the op): the
+    // attention backward's dkv kernel beside its dq kernel (attn_tc_bwd).
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_aux_fork = nullptr, ev_aux_join = nullptr;
+    bool attn_concurrent = true;
     // Micro-batch pipelining: the main-stream ops that work image by image (conv fprop / dgrad, GroupNorm, attention,
     // data movement) are emitted once per micro-batch of B / n_mb images -- batch-major views of the same buffers -- and
     // micro-batch h > 0 runs on mb_streams[h - 1], a parallel branch of the captured graph.  The step is ~40 % batch-
@@ -387,14 +394,17 @@ struct Builder {
                       fwd ? "fwd" : "dgrad", segs[0].Cin, segs.size() > 1 ? "+skip" : "", Cout, H, W, pr.BN, pr.a_stages,
                       pr.w_stages, ep.stats ? " +stats" : "", ep.gn_x ? " +gnbwd" : "");
             } else {
-                IgemmConvParams p;
+                // (shared: a GroupNorm that consumes the output may still extend the plan, see gn_finish)
+                auto pp = std::make_shared<IgemmConvParams>();
+                IgemmConvParams& p = *pp;
                 int r = igemm_conv_plan(&p, sh.data(), int(sh.size()), Bh, H, W, Cout, eh);
                 if (r) {
                     set_err("igemm_conv_plan failed (%d) for %dx%d Cout=%d Cin0=%d", r, H, W, Cout, segs[0].Cin);
                     plan_errors++;
                     return;
                 }
-                op = [p](cudaStream_t st) { igemm_conv_launch(p, st); };
+                if (nh == 1 && p.gnf_cluster && (ep.stats || ep.gn_x)) gn_finish[ep.out] = pp;
+                op = [pp](cudaStream_t st) { igemm_conv_launch(*pp, st); };
                 label("conv%s %s Cin=%d%s Cout=%d %dx%d BN=%d stages=%d%s%s", segs[0].ntaps == 9 ? "3x3" : "1x1",
                       fwd ? "fwd" : "dgrad", segs[0].Cin, segs.size() > 1 ? "+skip" : "", Cout, H, W, p.BN, p.stages,
                       ep.stats ? " +stats" : "", ep.gn_x ? " +gnbwd" : "");
@@ -445,6 +455,11 @@ struct Builder {
         size_t w, b;
         float *chsum, *S;
     };
+    // GroupNorm finish (IgemmConvParams::gnf): convs of the low-resolution levels whose epilogue can complete the
+    // GroupNorm that consumes their output (forward) / whose gn-bwd hook they carry (backward), keyed by output tensor.
+    // gn_fwd / gn_bwd extend the plan and emit no kernel of their own when the output's producer is registered here.
+    std::map<const void*, std::shared_ptr<IgemmConvParams>> gn_finish;
+    int gn_finished_fwd = 0, gn_finished_bwd = 0;
     // statistics buffer of a tensor whose producer (a conv epilogue) accumulates them
     // GroupNorm scheme (UB_GN_MODE), decided per tensor shape.  Measured round 2 (bench.py, B = 32, ms/step):
     //   hooks 5.09 (default) | auto 5.23 | passes 5.47 | slab 6.05
@@ -494,6 +509,18 @@ struct Builder {
         const int HW = x.H * x.W, Gn = c.gn_n_groups;
         float *gw = P(g.w), *gb = P(g.b), *cs = g.chsum;
         const bool slab = !have && use_slab(x.C, x.H, x.W);
+        if (have && real()) {
+            auto it = gn_finish.find(x.p);
+            if (it != gn_finish.end()) {
+                auto pp = it->second;
+                gn_finish.erase(it);
+                if (x.ld == pp->ldo && x.C == pp->Cout && pp->stats == cs &&
+                    igemm_conv_gn_finish_fwd(pp.get(), gw, gb, Gn, silu, y.p, y.ld)) {
+                    gn_finished_fwd++;
+                    return g;  // the producing conv's epilogue writes y
+                }
+            }
+        }
         label("gn_fwd C=%d %dx%d%s", x.C, x.H, x.W, slab ? " slab" : (have ? "" : " +stats pass"));
         split([&](int h) {
             const View xh = mb(x, h), yh = mb(y, h);
@@ -523,6 +550,18 @@ struct Builder {
         float *gw = P(g.w), *gb = P(g.b), *cs = g.chsum, *S = g.S, *dgw = G(g.w), *dgb = G(g.b);
         const bool slab = !fused && use_slab(x.C, x.H, x.W);
         const int mode = fused ? (silu ? 2 : 0) : silu;
+        if (fused && real()) {
+            auto it = gn_finish.find(dy.p);
+            if (it != gn_finish.end()) {
+                auto pp = it->second;
+                gn_finish.erase(it);
+                if (dy.ld == pp->ldo && x.C == pp->Cout && pp->gn_S == S &&
+                    igemm_conv_gn_finish_bwd(pp.get(), add_in.p, add_in.ld, dx.p, dx.ld, dgw, dgb, colsum_out)) {
+                    gn_finished_bwd++;
+                    return;  // the dgrad conv's epilogue writes dx, dgamma, dbeta and the column sums
+                }
+            }
+        }
         label("gn_bwd C=%d %dx%d%s%s", x.C, x.H, x.W, slab ? " slab" : (fused ? "" : " +stats pass"), add_in.p ? " +add" : "");
         split([&](int h) {
             const View xh = mb(x, h), dyh = mb(dy, h), ah = mb(add_in, h), dxh = mb(dx, h);
@@ -558,6 +597,14 @@ struct Builder {
     // Time-MLP backward (needs the complete d_embact, i.e. every embedding projection's backward).  Emitted on the
     // weight-gradient branch as soon as the first ResBlock has produced its embedding gradient, so that it runs under
     // the last dgrad convs instead of after them (it used to be 80 us of the step's serial tail).
+    // Step tail (UB_TAIL_AUX=0 restores the single-branch order): the time-MLP backward (six small dependent kernels)
+    // forks off the weight-gradient branch into a branch of its own, and the 3-channel input conv's weight gradient --
+    // the last gradient of the step -- runs on the main stream, which has nothing left to do: the three chains
+    // (last wgrad -> finalize -> bucket optimizer | time MLP | input-conv wgrad) overlap instead of queueing.
+    static bool tail_aux() {
+        static const bool on = !(getenv("UB_TAIL_AUX") && atoi(getenv("UB_TAIL_AUX")) == 0);
+        return on;
+    }
     bool time_mlp_bwd_done = false;
     void time_mlp_bwd() {
         if (time_mlp_bwd_done) return;
@@ -569,7 +616,7 @@ struct Builder {
             small_linear_bwd(Tt->temb_table + 1, 1, Bn, Cemb, Cemb, st);
             dsilu_mul(Tt->d_h0act, Tt->h0, Tt->dh0, size_t(Bn) * Cemb, st);
             small_linear_bwd(Tt->temb_table, 1, Bn, Cemb, Cm, st);
-        }, 6, UB_KIND_SMALL, 0, 0, 1);
+        }, 6, UB_KIND_SMALL, 0, 0, tail_aux() ? 3 : 1);  // 3: a branch of its own, forked from the weight-gradient branch
     }
 
     // ResBlock (dev/resblock.py:107-160, train_unet.cu:2213-2384)
@@ -723,6 +770,7 @@ struct Builder {
                 conv_op(false, {{dout.p, C, dout.ld, pp.wd, 1}}, H, W, C, ep);
             }
             label("attn bwd T=%d C=%d", Tn, C);
+            UbTrainer* Tt = T;
             split([&](int h) {
                 const View qh = mb(qkv, h), aoh = mb(ao, h), daoh = mb(dao, h), dqh = mb(dqkv, h);
                 float *lseh = mbf(lse, h, size_t(NH) * Tn), *dsh = mbf(dsum, h, size_t(NH) * Tn);
@@ -735,7 +783,7 @@ struct Builder {
                 }
                 Bk([=](cudaStream_t st) {
                     if (tc)
-                        attn_tc_bwd(apb, st);
+                        attn_tc_bwd(apb, st, Tt->attn_concurrent ? Tt->aux_stream : nullptr, Tt->ev_aux_fork, Tt->ev_aux_join);
                     else
                         attn_bwd(qh.p, qh.ld, aoh.p, aoh.ld, daoh.p, daoh.ld, lseh, Bq, Tn, NH, HSz, dqh.p, dqh.ld, dsh, st);
                 }, 2, UB_KIND_ATTN, 10.0 * Bq * NH * double(Tn) * Tn * HSz, act_bytes(8 * C, H, W) / nh);
@@ -828,7 +876,7 @@ int Builder::build() {
             Bk([=](cudaStream_t st) {
                 conv_in_wgrad(Tt->xt, dout.p, dout.ld, Bn, Cin, hv.C, hv.H, hv.W, gw, gb, Tt->small_scratch,
                               Tt->small_scratch_floats, st);
-            }, 1, UB_KIND_SMALL, 0, 0, 1);  // (one launch with the row kernel; two on its fallback path)
+            }, 1, UB_KIND_SMALL, 0, 0, tail_aux() ? 0 : 1);  // (one launch with the row kernel; two on its fallback path)
             if (Tt->cfg.compute_dinput)
                 split([&](int hh) {
                     const View dm = mb(dout, hh);
@@ -1067,6 +1115,9 @@ int Builder::build() {
         cudaEventRecord(Tt->ev_join, Tt->comm_stream);
         cudaStreamWaitEvent(st, Tt->ev_join, 0);
     }, 0);
+    if (real() && getenv("UB_DEBUG_GNF"))
+        fprintf(stderr, "[unet_b200] GroupNorm finished inside conv epilogues: %d forward, %d backward\n",
+                gn_finished_fwd, gn_finished_bwd);
     return plan_errors ? UB_ERR_SHAPE : UB_OK;
 }
 
@@ -1198,6 +1249,10 @@ extern "C" int ub_trainer_create(UbTrainer** out, const UbConfig* cfg, int devic
     cudaStreamCreateWithPriority(&t->stream, cudaStreamNonBlocking, use_prio ? prio_hi : 0);
     cudaStreamCreateWithPriority(&t->comm_stream, cudaStreamNonBlocking, use_prio ? prio_hi : 0);
     cudaStreamCreateWithPriority(&t->side_stream, cudaStreamNonBlocking, use_prio ? prio_lo : 0);
+    cudaStreamCreateWithPriority(&t->aux_stream, cudaStreamNonBlocking, use_prio ? prio_hi : 0);
+    cudaEventCreateWithFlags(&t->ev_aux_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&t->ev_aux_join, cudaEventDisableTiming);
+    t->attn_concurrent = !(getenv("UB_ATTN_SERIAL") && atoi(getenv("UB_ATTN_SERIAL")) != 0) && t->n_mb == 1;
     for (int i = 1; i < t->n_mb; ++i) {
         cudaStream_t ms = nullptr;
         cudaStreamCreateWithPriority(&ms, cudaStreamNonBlocking, use_prio ? prio_hi : 0);
@@ -1277,6 +1332,9 @@ extern "C" void ub_trainer_destroy(UbTrainer* t) {
     if (t->stream) cudaStreamDestroy(t->stream);
     if (t->comm_stream) cudaStreamDestroy(t->comm_stream);
     if (t->side_stream) cudaStreamDestroy(t->side_stream);
+    if (t->aux_stream) cudaStreamDestroy(t->aux_stream);
+    if (t->ev_aux_fork) cudaEventDestroy(t->ev_aux_fork);
+    if (t->ev_aux_join) cudaEventDestroy(t->ev_aux_join);
     for (auto ms : t->mb_streams) cudaStreamDestroy(ms);
     for (auto ev : t->side_events) cudaEventDestroy(ev);
     delete t;
@@ -1299,7 +1357,7 @@ static void enqueue_step(UbTrainer* t, const StepOpts& o, cudaStream_t st) {
     static const bool debug_sync = getenv("UB_DEBUG_SYNC") != nullptr;  // eager runs only: find the faulting op
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (debug_sync) cudaStreamIsCapturing(st, &cap);
-    bool side_dirty = false;
+    bool side_dirty = false, aux_dirty = false;
     auto next_event = [&]() { return t->side_events[t->side_ev_next++ % t->side_events.size()]; };
     // micro-batch chains: `forked` while the chains of micro-batches 1.. run beside the main stream
     bool forked = false;
@@ -1335,7 +1393,19 @@ static void enqueue_step(UbTrainer* t, const StepOpts& o, cudaStream_t st) {
                     }
                 ops[i](t->side_stream);
                 side_dirty = true;
+            } else if (info[i].side == 3 && t->use_side) {  // a branch off the weight-gradient branch (time-MLP backward)
+                cudaEvent_t ev = next_event();
+                cudaEventRecord(ev, side_dirty ? t->side_stream : st);
+                cudaStreamWaitEvent(t->aux_stream, ev, 0);
+                ops[i](t->aux_stream);
+                aux_dirty = true;
             } else if (info[i].side == 2) {
+                if (aux_dirty) {
+                    cudaEvent_t ev = next_event();
+                    cudaEventRecord(ev, t->aux_stream);
+                    cudaStreamWaitEvent(st, ev, 0);
+                    aux_dirty = false;
+                }
                 if (side_dirty) {
                     cudaEvent_t ev = next_event();
                     cudaEventRecord(ev, t->side_stream);
@@ -1348,7 +1418,7 @@ static void enqueue_step(UbTrainer* t, const StepOpts& o, cudaStream_t st) {
                 fork_mb();
                 ops[i](t->mb_streams[info[i].half - 1]);
             } else {
-                if (info[i].half < 0 || info[i].side == 1) join_mb();  // whole-batch op: every chain must have arrived
+                if (info[i].half < 0 || info[i].side == 1 || info[i].side == 3) join_mb();  // whole-batch op: every chain must have arrived
                 else fork_mb();
                 ops[i](st);
             }
@@ -1372,6 +1442,11 @@ static void enqueue_step(UbTrainer* t, const StepOpts& o, cudaStream_t st) {
     run(t->fwd_ops, t->fwd_info, "forward");
     run(t->bwd_ops, t->bwd_info, "backward");
     join_mb();
+    if (aux_dirty) {
+        cudaEvent_t ev = next_event();
+        cudaEventRecord(ev, t->aux_stream);
+        cudaStreamWaitEvent(st, ev, 0);
+    }
     if (side_dirty) {  // (the tape ends with a join; this only guards against a tape that forgot it)
         cudaEvent_t ev = next_event();
         cudaEventRecord(ev, t->side_stream);
@@ -1526,10 +1601,22 @@ extern "C" int ub_trainer_train_step_device(UbTrainer* t, const float* x0_dev, f
 }
 
 // Eager replay of one step with a CUDA event pair around every tape op (device time per kernel class).
+// Every op is enqueued R times back to back between its two events and the interval is divided by R (R =
+// UB_PROFILE_REPLAY, default 4; 1 = one launch per event pair as in round 1).  With a single launch per pair the
+// interval is dominated by the event records and the un-pipelined launch for the ~300 kernels of a step that run for
+// less than 10 us (a 256->256 conv at 8x8: 16.7 us between events, 9.6 us in the kernel's own phase trace); replicas
+// follow each other through programmatic dependent launch exactly as the different kernels of the captured step do,
+// so interval / R is the per-launch device time inside a pipelined stream.  Accumulating ops (statistics / weight-
+// gradient REDs) simply accumulate R times: the profile's results are discarded (state is restored below).
 extern "C" int ub_trainer_profile(UbTrainer* t, int reps, UbProfile* out) {
     CUDA_TRY(cudaSetDevice(t->device));
     memset(out, 0, sizeof(*out));
     if (reps < 1) reps = 1;
+    static const int R = [] {
+        const int v = getenv("UB_PROFILE_REPLAY") ? atoi(getenv("UB_PROFILE_REPLAY")) : 4;
+        return v < 1 ? 1 : (v > 16 ? 16 : v);
+    }();
+    const float invR = 1.f / float(R);
     const UbConfig& c = t->cfg;
     const size_t nops = t->fwd_ops.size() + t->bwd_ops.size() + 2;
     std::vector<cudaEvent_t> ev(nops + 1);
@@ -1555,14 +1642,20 @@ extern "C" int ub_trainer_profile(UbTrainer* t, int reps, UbProfile* out) {
         size_t k = 0;
         // the host needs ~3 us per launch + event, many kernels run for less: park the stream for a few ms so that the
         // whole tape is queued before the first op starts and the event intervals are pure device time
-        stream_delay(6000, st);
+        stream_delay(unsigned(3000 + 3000 * R), st);
         cudaEventRecord(ev[k++], st);
         cudaMemsetAsync(t->zero_base, 0, t->zero_bytes, st);
         diffusion_prepare(t->x0, t->sqrt_ac, t->sqrt_1mac, c.B, size_t(c.C_in) * c.H * c.W, c.n_timesteps, c.seed,
                           t->step_dev, 1, 1, t->tsteps, t->noise, t->xt, st, c.W, t->flips);
         cudaEventRecord(ev[k++], st);
-        for (auto& op : t->fwd_ops) op(st), cudaEventRecord(ev[k++], st);
-        for (auto& op : t->bwd_ops) op(st), cudaEventRecord(ev[k++], st);
+        for (auto& op : t->fwd_ops) {
+            for (int r = 0; r < R; ++r) op(st);
+            cudaEventRecord(ev[k++], st);
+        }
+        for (auto& op : t->bwd_ops) {
+            for (int r = 0; r < R; ++r) op(st);
+            cudaEventRecord(ev[k++], st);
+        }
         adamw_step(t->params, t->grads, t->m, t->v, t->nparams, t->g_lr > 0 ? t->g_lr : 1e-4f, 0.9f, 0.999f, 1e-8f, 0.f,
                    1.f / float(t->world), t->step_dev, st);
         run_pack(t, st);
@@ -1575,11 +1668,13 @@ extern "C" int ub_trainer_profile(UbTrainer* t, int reps, UbProfile* out) {
         out->ms[UB_KIND_OPTIM] += ms;
         for (size_t i = 0; i < t->fwd_ops.size(); ++i, ++j) {
             cudaEventElapsedTime(&ms, ev[j], ev[j + 1]);
+            ms *= invR;
             out->ms[t->fwd_info[i].kind] += ms;
             op_us[i] = ms * 1e3f;
         }
         for (size_t i = 0; i < t->bwd_ops.size(); ++i, ++j) {
             cudaEventElapsedTime(&ms, ev[j], ev[j + 1]);
+            ms *= invR;
             out->ms[t->bwd_info[i].kind] += ms;
             op_us[t->fwd_ops.size() + i] = ms * 1e3f;
         }
