@@ -22,9 +22,21 @@ import unet_oracle as O  # noqa: E402
 ub = ge.load_package()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 out = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "timeline.tsv")
+# under torchrun: data parallel over NCCL, rank 0 reports (the all-reduce kernels show up as ncclDevKernel_*)
+rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+local_rank = int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local_rank)
 cfg = O.UNetConfig()
-tr = ub.Trainer(B=B)
+tr = ub.Trainer(B=B, device=local_rank, seed=1234 + rank)
 tr.set_params(O.flatten_params(cfg, O.init_params(cfg, seed=0)).numpy())
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    idt = torch.zeros(ub.UB_NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(ub.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    tr.attach_dp(rank, world, bytes(idt.cpu().numpy().tobytes()))
 x = (torch.rand(B, 3, 64, 64) * 2 - 1).cuda()
 for _ in range(5):
     tr.train_step_device(x.data_ptr())
@@ -40,6 +52,9 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
 import json  # noqa: E402
 import tempfile  # noqa: E402
 
+if rank != 0:
+    tr.close()
+    sys.exit(0)
 tmp = os.path.join(tempfile.mkdtemp(), "trace.json")
 prof.export_chrome_trace(tmp)
 evs = []
@@ -91,6 +106,11 @@ for (s0, d0, n0), (s1, d1, n1) in zip(lst, lst[1:]):
 print(f"main stream idle between kernels: {sum(g for g, *_ in gaps):.1f} us in {len(gaps)} gaps (overlap counts as 0); largest:")
 for g, at, a, b in sorted(gaps, reverse=True)[:12]:
     print(f"  {g:7.1f} us at {at:8.1f}  after {a}  before {b}")
+nc = [(s_, d_, n_) for st_, lst_ in by_stream.items() for s_, d_, n_ in lst_ if "nccl" in n_.lower()]
+if nc:
+    print(f"NCCL kernels: {len(nc)}, busy {sum(d for _, d, _ in nc):.1f} us; start / duration / end (us from step start):")
+    for s_, d_, n_ in sorted(nc):
+        print(f"  {s_:8.1f} {d_:7.1f} {s_ + d_:8.1f}  {n_[:60]}")
 ov = sum(max(0.0, (s0 + d0) - s1) for (s0, d0, _), (s1, _, _) in zip(lst, lst[1:]))
 print(f"main stream kernel-to-kernel overlap (programmatic dependent launch): {ov:.1f} us")
 tr.close()

@@ -103,6 +103,10 @@ struct UbTrainer {
     UbConfig cfg;
     int device = 0;
     cudaStream_t stream = nullptr, comm_stream = nullptr;
+    // data parallel: AdamW + weight re-pack of an all-reduced bucket run here, behind the bucket's all-reduce, so that
+    // the communication stream is free for the next bucket's all-reduce (the last ones are the step's serial tail)
+    cudaStream_t opt_stream = nullptr;
+    bool opt_stream_dirty = false;
     // Weight gradients (wgrad GEMMs, bias column sums, embedding-projection backward) feed nothing but the optimizer:
     // they run on a side stream, concurrently with the dgrad -> GroupNorm -> dgrad critical path of backward (in the
     // captured graph this is a parallel branch).  Both kinds of kernel are latency-bound on their own.
@@ -207,7 +211,7 @@ struct UbTrainer {
     float* hp_dev = nullptr;
     const float* hp_active = nullptr;  // = hp_dev while a graph is being captured / replayed, null for eager steps
     size_t opt_done_lo = 0;   // parameters >= this offset were updated by the tape
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
     std::vector<cudaEvent_t> bucket_events;
     std::vector<size_t> bucket_bounds;  // param offsets, descending
     // emb bookkeeping
@@ -1027,6 +1031,9 @@ int Builder::build() {
         // A last cut right above the input conv: the bucket that must wait for the very end of backward (and whose
         // AdamW + weight re-pack are the serial tail of the step) then holds only the time MLP and the 3-channel conv.
         static const bool tail_cut = !(getenv("UB_TAIL_CUT") && atoi(getenv("UB_TAIL_CUT")) == 0);
+        // (Measured round 2: further cuts at the level boundaries of the down path, so that only the first level's
+        //  small bucket waits for the end of backward, cost more in extra optimizer / re-pack launches on the tail
+        //  than the shorter last all-reduce won: 5.08 vs 5.02 ms on one GPU, 5.13 vs 5.11 on two.)
         if (tail_cut && nodes.size() > 1 && nodes[1].param_begin > time_mlp_end &&
             (cuts.empty() || nodes[1].param_begin < cuts.back()))
             cuts.push_back(nodes[1].param_begin);
@@ -1054,15 +1061,22 @@ int Builder::build() {
         Bk([=](cudaStream_t st) {
             const bool dp = Tt->world > 1 && !Tt->comm_off;
             if (dp) {
-                cudaEvent_t ev = Tt->bucket_events[k % Tt->bucket_events.size()];
+                cudaEvent_t ev = Tt->bucket_events[k % 16];
                 cudaEventRecord(ev, st);
                 cudaStreamWaitEvent(Tt->comm_stream, ev, 0);
                 nccl().AllReduce(Tt->grads + lo, Tt->grads + lo, hi - lo, kNcclFloat, kNcclSum, Tt->comm,
                                  Tt->comm_stream);
             }
             if (!Tt->opt_in_tape || last) return;  // the last bucket is updated at the end of the step
-            // optimizer of this bucket on the stream that owns its final gradients
-            cudaStream_t os = dp ? Tt->comm_stream : st;
+            // optimizer of this bucket behind its final gradients: the producing branch, or (data parallel) a stream
+            // of its own that waits for the bucket's all-reduce
+            cudaStream_t os = st;
+            if (dp) {
+                cudaEvent_t ev2 = Tt->bucket_events[16 + k % 16];
+                cudaEventRecord(ev2, Tt->comm_stream);
+                cudaStreamWaitEvent(Tt->opt_stream, ev2, 0);
+                os = Tt->opt_stream, Tt->opt_stream_dirty = true;
+            }
             adamw_step(Tt->params + lo, Tt->grads + lo, Tt->m + lo, Tt->v + lo, hi - lo, Tt->o_lr, Tt->o_b1, Tt->o_b2,
                        Tt->o_eps, Tt->o_wd, 1.f / float(Tt->world), Tt->step_dev, os, Tt->hp_active);
             if (pk_count) pack_weights(Tt->pack_table + pk_first, pk_count, pk_tiles, os);
@@ -1114,6 +1128,11 @@ int Builder::build() {
         if (Tt->world <= 1 || Tt->comm_off) return;
         cudaEventRecord(Tt->ev_join, Tt->comm_stream);
         cudaStreamWaitEvent(st, Tt->ev_join, 0);
+        if (Tt->opt_stream_dirty) {
+            cudaEventRecord(Tt->ev_join2, Tt->opt_stream);
+            cudaStreamWaitEvent(st, Tt->ev_join2, 0);
+            Tt->opt_stream_dirty = false;
+        }
     }, 0);
     if (real() && getenv("UB_DEBUG_GNF"))
         fprintf(stderr, "[unet_b200] GroupNorm finished inside conv epilogues: %d forward, %d backward\n",
@@ -1262,7 +1281,9 @@ extern "C" int ub_trainer_create(UbTrainer** out, const UbConfig* cfg, int devic
     for (auto& ev : t->side_events) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (const char* e = getenv("UB_NO_SIDE_STREAM")) t->use_side = atoi(e) == 0;
     cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming);
-    t->bucket_events.resize(16);
+    cudaEventCreateWithFlags(&t->ev_join2, cudaEventDisableTiming);
+    cudaStreamCreateWithPriority(&t->opt_stream, cudaStreamNonBlocking, use_prio ? prio_lo : 0);
+    t->bucket_events.resize(32);  // [0, 16): branch -> communication stream, [16, 32): communication -> optimizer stream
     for (auto& ev : t->bucket_events) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     // pass 2: build
     {
@@ -1329,6 +1350,8 @@ extern "C" void ub_trainer_destroy(UbTrainer* t) {
     if (t->h_loss) cudaFreeHost(t->h_loss);
     for (auto ev : t->bucket_events) cudaEventDestroy(ev);
     if (t->ev_join) cudaEventDestroy(t->ev_join);
+    if (t->ev_join2) cudaEventDestroy(t->ev_join2);
+    if (t->opt_stream) cudaStreamDestroy(t->opt_stream);
     if (t->stream) cudaStreamDestroy(t->stream);
     if (t->comm_stream) cudaStreamDestroy(t->comm_stream);
     if (t->side_stream) cudaStreamDestroy(t->side_stream);
