@@ -1,12 +1,17 @@
 """Summarise an ncu --metrics gpu__time_duration.sum --csv launch list: per kernel and (optionally) per grid.
-python tools/launch_summary.py gpurun_out/launches.csv [kernel-substring ...]"""
-import collections, csv, sys
+python tools/launch_summary.py gpurun_out/launches.csv [kernel-substring ...]
+python tools/launch_summary.py gpurun_out/launches.csv --count REGEX     -> number of launches whose kernel name matches"""
+import collections, csv, re, sys
 rows = list(csv.reader(open(sys.argv[1])))
 for i, r in enumerate(rows):
     if 'Kernel Name' in r:
         hdr, start = r, i + 1
         break
 ki, vi, ui, gi = hdr.index('Kernel Name'), hdr.index('Metric Value'), hdr.index('Metric Unit'), hdr.index('Grid Size')
+if len(sys.argv) > 3 and sys.argv[2] == '--count':
+    pat = re.compile(sys.argv[3])
+    print(sum(1 for r in rows[start:] if len(r) > vi and pat.search(r[ki])))
+    sys.exit(0)
 agg, per_grid, tot = collections.defaultdict(lambda: [0, 0.0]), collections.defaultdict(lambda: [0, 0.0]), 0.0
 for r in rows[start:]:
     if len(r) <= vi:

@@ -58,9 +58,10 @@ struct IP {
     int iters;                // stages pulled per CTA
     int total_rows;           // rows of the global tensor (working set = total_rows x 128 B)
     int poll;                 // 1 = test_wait spin loops
+    int nprod;                // producer warps: warp w issues the stages it = w (mod nprod) -- is one thread's issue rate the limit?
 };
 
-__global__ void __launch_bounds__(64) ingest(const __grid_constant__ CUtensorMap tm, const IP p, unsigned long long* out) {
+__global__ void __launch_bounds__(160) ingest(const __grid_constant__ CUtensorMap tm, const IP p, unsigned long long* out) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int box_bytes = p.rows * 128, stage_bytes = p.boxes * box_bytes;
@@ -76,7 +77,41 @@ __global__ void __launch_bounds__(64) ingest(const __grid_constant__ CUtensorMap
     }
     __syncthreads();
     const unsigned long long t0 = clock64();
-    if (warp == 0) {
+    if (warp >= 1 && warp <= p.nprod && p.nprod > 1) {
+        // several producers: producer w takes iterations w-1, w-1+nprod, ... (warp 0 is the consumer in this mode)
+        const int w = warp - 1;
+        const uint32_t mask = (uint32_t)p.total_rows - 1u;
+        for (int it = w; it < p.iters; it += p.nprod) {
+            const int st = it % p.stages;
+            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+            mbar_wait(smem_u32(&empty[st]), ph ^ 1, p.poll);
+            if (elect_one_sync()) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[st])), "r"(stage_bytes)
+                             : "memory");
+                const uint32_t row = (blockIdx.x + (uint32_t)it * gridDim.x) * p.boxes * p.rows;
+                for (int b = 0; b < p.boxes; ++b) {
+                    const int r = (int)((row + (uint32_t)b * p.rows) & mask);
+                    asm volatile(
+                        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                            smem_u32(smem + (size_t)st * stage_bytes + (size_t)b * box_bytes)),
+                        "l"(&tm), "r"(smem_u32(&full[st])), "r"(0), "r"(r)
+                        : "memory");
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == 0 && p.nprod > 1) {
+        int st = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < p.iters; ++it) {
+            mbar_wait(smem_u32(&full[st]), ph, p.poll);
+            if (elect_one_sync()) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[st])) : "memory");
+            __syncwarp();
+            if (++st == p.stages) st = 0, ph ^= 1;
+        }
+        if (threadIdx.x == 0) out[blockIdx.x] = clock64() - t0;
+    } else if (p.nprod > 1) {
+    } else if (warp == 0) {
         int st = 0;
         uint32_t ph = 0;
         // every CTA walks the tensor from its own offset (distinct rows per CTA per iteration, wrapping around)
@@ -102,7 +137,7 @@ __global__ void __launch_bounds__(64) ingest(const __grid_constant__ CUtensorMap
             row += gridDim.x * p.boxes * p.rows;
             if (++st == p.stages) st = 0, ph ^= 1;
         }
-    } else {
+    } else if (warp == 1) {
         int st = 0;
         uint32_t ph = 0;
         for (int it = 0; it < p.iters; ++it) {
@@ -141,12 +176,13 @@ int main() {
                         {4, 1, 256}, {6, 1, 256}, {3, 2, 256}, {8, 1, 64}, {16, 1, 64}, {2, 3, 256}, {6, 2, 128}, {4, 2, 128}};
     const int poll = getenv("POLL") ? atoi(getenv("POLL")) : 0;
     const int only_l2 = getenv("ONLY_L2") ? 1 : 0;
-    printf("# wait = %s\n", poll ? "mbarrier.test_wait spin" : "mbarrier.try_wait");
+    const int nprod = getenv("NPROD") ? atoi(getenv("NPROD")) : 1;
+    printf("# wait = %s, producer warps = %d\n", poll ? "mbarrier.test_wait spin" : "mbarrier.try_wait", nprod);
     for (int ws = 0; ws < (only_l2 ? 1 : 2); ++ws) {
         const size_t rows_total = ws == 0 ? ((size_t)32 << 20) / 128 : big_rows;  // 32 MiB (L2 resident) or 2 GiB (DRAM)
         for (int grid : {nsm, 64, 16}) {
             for (const Cfg& c : cfgs) {
-                IP p{c.stages, c.boxes, c.rows, 0, (int)rows_total, poll};
+                IP p{c.stages, c.boxes, c.rows, 0, (int)rows_total, poll, nprod};
                 const size_t stage_bytes = (size_t)c.boxes * c.rows * 128;
                 if (c.stages * stage_bytes > 200 * 1024) continue;
                 p.iters = (int)std::max<size_t>(64, ((size_t)8 << 20) / stage_bytes);  // ~8 MiB per CTA
@@ -162,7 +198,7 @@ int main() {
                     return 1;
                 }
                 const size_t smem = c.stages * stage_bytes + 1024 + 512;
-                for (int rep = 0; rep < 3; ++rep) ingest<<<grid, 64, smem>>>(tm, p, d_out);
+                for (int rep = 0; rep < 3; ++rep) ingest<<<grid, 160, smem>>>(tm, p, d_out);
                 CK(cudaDeviceSynchronize());
                 std::vector<unsigned long long> h(grid);
                 CK(cudaMemcpy(h.data(), d_out, grid * 8, cudaMemcpyDeviceToHost));

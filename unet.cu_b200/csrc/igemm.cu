@@ -137,6 +137,41 @@ __device__ __forceinline__ void conv_issue_loop(const IgemmConvParams& p, int is
     if (issuer == 0) UB_TR(7, (unsigned long long)clock64());
 }
 
+// TMA producer `prod` of NPROD: K blocks it = prod (mod NPROD) into stage it % stages (NPROD > 1: the ring is a
+// multiple of NPROD, so a stage always belongs to the same producer).  One thread's TMA issue rate is part of what
+// paces a one-CTA-per-SM pipeline: tools/tma_ingest_bench.cu NPROD=2 moves 68 B/clk/SM through one-box stages against
+// 50 with a single producer warp (123 against 92 with two boxes per stage, profiles/r02_tma_producers.txt).
+template <int NPROD>
+__device__ __forceinline__ void conv_produce_loop(const IgemmConvParams& p, int prod, int /*nk*/, uint8_t* smem,
+                                                  uint64_t* full_bar, uint64_t* empty_bar, int w0, int h0, int b0,
+                                                  int n0) {
+    // (nested loops over segment / tap / channel block with the K blocks of the other producers skipped: a flat loop
+    //  that derives (segment, tap, block) per iteration cost 130 cycles more per K block in the phase trace)
+    int stage = prod, it = 0;
+    uint32_t phase = 0;
+    for (int s = 0; s < p.nseg; ++s) {
+        const IgemmSeg& sg = p.seg[s];
+        for (int tap = 0; tap < sg.ntaps; ++tap) {
+            const int dy = sg.ntaps == 9 ? tap / 3 - 1 : 0;
+            const int dx = sg.ntaps == 9 ? tap % 3 - 1 : 0;
+            for (int cb = 0; cb < sg.cblocks; ++cb, ++it) {
+                if (NPROD > 1 && (it % NPROD) != prod) continue;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sA = smem + size_t(stage) * p.stage_bytes;
+                uint8_t* sB = sA + 16384;
+                if (elect_one_sync()) {
+                    mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
+                    tma_load_4d(sA, &sg.tmA, &full_bar[stage], cb * 64, w0 + dx, h0 + dy, b0);
+                    tma_load_2d(sB, &sg.tmW, &full_bar[stage], cb * 64, tap * p.Cout + n0);
+                }
+                __syncwarp();
+                stage += NPROD;
+                if (stage >= p.stages) stage -= p.stages, phase ^= 1;
+            }
+        }
+    }
+}
+
 // NACC = number of MMA issue streams (and accumulators).  One thread's tcgen05.mma stream runs at ~145 cycles per
 // M=128 instruction whatever N is, and streams of different warps / CTAs overlap (profiles/r01_mma_issue.txt).  Grids
 // that fill the chip run NACC = 1 with two CTAs per SM (two streams per SM already).  Grids of <= one CTA per SM (the
@@ -247,30 +282,11 @@ __device__ __forceinline__ void igemm_conv_body(const IgemmConvParams& p) {
 #else
         {
 #endif
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int s = 0; s < p.nseg; ++s) {
-                const IgemmSeg& sg = p.seg[s];
-                for (int tap = 0; tap < sg.ntaps; ++tap) {
-                    const int dy = sg.ntaps == 9 ? tap / 3 - 1 : 0;
-                    const int dx = sg.ntaps == 9 ? tap % 3 - 1 : 0;
-                    for (int cb = 0; cb < sg.cblocks; ++cb) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                        uint8_t* sA = smem + size_t(stage) * p.stage_bytes;
-                        uint8_t* sB = sA + 16384;
-                        if (elect_one_sync()) {
-                            mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
-                            tma_load_4d(sA, &sg.tmA, &full_bar[stage], cb * 64, w0 + dx, h0 + dy, b0);
-                            tma_load_2d(sB, &sg.tmW, &full_bar[stage], cb * 64, tap * p.Cout + n0);
-                        }
-                        __syncwarp();
-                        if (++stage == p.stages) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
-                    }
-                }
-            }
+            // two-stream kernels (one CTA per SM): a second producer (warp 8, see below) takes the odd K blocks
+            if (NACC == 2 && p.nprod == 2)
+                conv_produce_loop<2>(p, 0, nk, smem, full_bar, empty_bar, w0, h0, b0, n0);
+            else
+                conv_produce_loop<1>(p, 0, nk, smem, full_bar, empty_bar, w0, h0, b0, n0);
             UB_TR(5, (unsigned long long)clock64());
         }
     } else if (warp == 1) {
@@ -280,6 +296,13 @@ __device__ __forceinline__ void igemm_conv_body(const IgemmConvParams& p) {
         // ------------------------------------------------------------ epilogue (warps 2..9)
         if constexpr (NACC == 2) {  // second MMA stream first; the warp reconverges before it touches the epilogue
             if (warp == 9) conv_issue_loop<NACC>(p, 1, nk, smem, full_bar, empty_bar, tmem_full_bar, tmem_base);
+            // ... and the second TMA producer (odd K blocks) on another epilogue warp that idles during the main loop
+            if (warp == 8 && p.nprod == 2) {
+#ifdef UB_TRACE
+                if (g_conv_dbg_mode < 2)
+#endif
+                conv_produce_loop<2>(p, 1, nk, smem, full_bar, empty_bar, w0, h0, b0, n0);
+            }
         }
         const int q = warp & 3;  // TMEM lane quadrant this warp may access
         const int half = (warp - 2) >> 2;  // the two warps of a quadrant split the columns
@@ -849,6 +872,10 @@ int igemm_conv_plan(IgemmConvParams* p, const ConvSegDesc* segs, int nseg, int B
         for (int s = 0; s < nseg; ++s) nkb += segs[s].ntaps * ceil_div_i(segs[s].Cin, 64);
         if (want >= 2 && pix_tiles * (Cout / BN) <= 148 && BN % 32 == 0 && BN <= 128 && nkb >= 4) p->nacc = 2;
     }
+    {
+        static const int want_np = getenv("UB_CONV2_NPROD") ? atoi(getenv("UB_CONV2_NPROD")) : 2;
+        p->nprod = (p->nacc == 2 && want_np >= 2) ? 2 : 1;  // (the two-stream ring is even: see below)
+    }
     p->tmem_cols = next_pow2(p->nacc * BN < 32 ? 32 : p->nacc * BN);
     p->a_bytes = uint32_t(64 * p->TW * p->TH * p->TB * 2);
     p->b_bytes = uint32_t(64 * BN * 2);
@@ -880,12 +907,14 @@ int igemm_conv_plan(IgemmConvParams* p, const ConvSegDesc* segs, int nseg, int B
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) return -3;
     if (p->nacc == 2) {
-        // One CTA per SM: the ring may use more than the two-CTA budget (UB_CONV2_SMEM_KB; a wgrad CTA of the side
-        // stream wants 96 KiB beside it).  Measured round 2: 128 / 160 / 200 KiB all give 5.09-5.10 ms per step, and
-        // stages of TWO K blocks sharing one barrier pair (both issuers on every stage) were slower -- 890 cycles per
-        // pair of K blocks in the phase trace against 2 x 322 -- although the TMA microbenchmark moves more bytes per
-        // cycle with more boxes per stage (profiles/r02_tma_ingest_bench.txt): removed again.
-        static const int kb = getenv("UB_CONV2_SMEM_KB") ? atoi(getenv("UB_CONV2_SMEM_KB")) : 128;
+        // One CTA per SM: the ring may use more than the two-CTA budget (UB_CONV2_SMEM_KB; at 128 KiB a wgrad CTA of
+        // the side stream still fits beside it).  Measured round 2 (ms per step): with ONE producer warp 128 / 160 /
+        // 200 KiB all gave 5.09-5.10; with the second producer warp 5.02 / 4.99 / 4.975 -- default 200.  Stages of
+        // TWO K blocks sharing one barrier pair (both issuers on every stage) were slower -- 890 cycles per pair of K
+        // blocks in the phase trace against 2 x 322 -- and were removed again.  What bounds the main loop of these
+        // layers is the TMA stream itself: the phase trace with the MMAs switched off (UB_TRACE_MODE=1) takes as long
+        // as the full kernel (~77 B/clk/SM for the 4-D halo boxes), the MMA stream alone 35 % less.
+        static const int kb = getenv("UB_CONV2_SMEM_KB") ? atoi(getenv("UB_CONV2_SMEM_KB")) : 200;
         int s2 = int((uint32_t(kb) * 1024u - tail) / p->stage_bytes);
         if (s2 > kMaxStages) s2 = kMaxStages;
         if (s2 > stages) stages = s2;

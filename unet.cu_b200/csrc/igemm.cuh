@@ -39,6 +39,7 @@ struct IgemmConvParams {
     int stages;
     int tmem_cols;   // power of two >= max(32, nacc * BN)
     int nacc;        // MMA issue streams = accumulators (1, or 2 for grids of at most one CTA per SM)
+    int nprod;       // TMA producer warps (2 with nacc == 2: even / odd K blocks)
     int ncomb;       // rows of the staged per-channel addend (TB when a per-image vector is fused, else 1)
     uint32_t a_bytes, b_bytes;  // TMA transaction bytes per stage
     uint32_t stage_bytes;       // smem bytes per stage (A tile 16 KiB + B tile, 1024-aligned)
