@@ -1,7 +1,10 @@
-o=gpurun_out
-for m in 0 1 2; do for kb in 128 200; do
-echo "== mode $m kb $kb"; UB_TRACE_MODE=$m UB_CONV2_SMEM_KB=$kb timeout 60 unet.cu_b200/build/igemm_trace shape 32 8 8 256 256 0 20 2>&1 | grep -E "first stage|last MMA|last TMA|accumulator|conv B32"
-done; done > $o/s19_trace.txt 2>&1
-echo "== nacc1"; UB_CONV_NACC=1 timeout 60 unet.cu_b200/build/igemm_trace shape 32 8 8 256 256 0 20 2>&1 | grep -E "first stage|last MMA|last TMA|conv B32" >> $o/s19_trace.txt
-echo "== BN128"; UB_CONV_FORCE_BN=128 timeout 60 unet.cu_b200/build/igemm_trace shape 32 8 8 256 256 0 20 2>&1 | grep -E "first stage|last MMA|last TMA|conv B32" >> $o/s19_trace.txt
-echo "== BN32"; UB_CONV_FORCE_BN=32 timeout 60 unet.cu_b200/build/igemm_trace shape 32 8 8 256 256 0 20 2>&1 | grep -E "first stage|last MMA|last TMA|conv B32" >> $o/s19_trace.txt
+o=gpurun_out; mkdir -p $o
+b() { tag=$1; shift; env "$@" timeout 200 python bench.py --steps 30 --warmup 10 --no-cpu-baseline --no-reference-cuda > $o/$tag.json 2> $o/$tag.err; python -c "
+import json
+try:
+    d=json.loads(open('$o/$tag.json').read().strip().splitlines()[-1]); print('$tag', round(d['ms_per_step'],4), round(d['roofline']['frac'],4), round(d['profile_total_ms'],3), {k:(round(v['ms'],3), v.get('tflops')) for k,v in d['kernel_classes'].items()})
+except Exception as e: print('$tag', 'ERR', e)
+"; tail -3 $o/$tag.err; }
+b s21_base A=1
+b s21_gnb3 UB_LIB_VARIANT=gnb3
+b s21_gnb4 UB_LIB_VARIANT=gnb4

@@ -100,6 +100,7 @@ struct IgemmRowsParams {
     int num_tiles;      // B * tiles_per_img * (Cout / BN)
     int BN;             // <= 128
     int a_stages, w_stages;
+    int w_resident;     // the weight ring holds the layer's whole weight set (ntaps tiles), loaded once per CTA
     int grid;
     uint32_t a_bytes, a_stage_bytes, w_bytes, w_stage_bytes;
     const float* bias;

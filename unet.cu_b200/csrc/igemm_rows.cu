@@ -25,6 +25,7 @@
 #include "ptx.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #ifdef UB_TRACE
 #include <algorithm>
@@ -171,6 +172,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
             uint32_t ph = 0;
             int ti = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
+                if (p.w_resident && ti > 0) break;  // resident weights: the ring was filled for the first tile, for good
                 const int n0 = (tile / tiles_mb) * p.BN;
                 for (int s = 0; s < p.nseg; ++s) {
                     const int nd = p.seg[s].ntaps == 9 ? 3 : 1;
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
                             tc_fence_after();
                             const uint32_t a_base = smem_u32(sA + size_t(sa) * p.a_stage_bytes);
                             for (int dyi = 0; dyi < nd; ++dyi) {
-                                mbar_wait(&bars->w_full[sw], pw);
+                                if (!p.w_resident || it == 0) mbar_wait(&bars->w_full[sw], pw);
                                 tc_fence_after();
                                 const uint32_t a0 = a_base + uint32_t(dyi) * row_bytes;  // box starts at row h0 - 1
                                 const uint64_t dB =
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
                                     for (int k = 0; k < 4; ++k)
                                         umma_bf16(d0 + uint32_t(mhalf * p.BN), dA + uint64_t(k * 2), dB + uint64_t(k * 2),
                                                   idesc, (!first || k != 0) ? 1u : 0u);
-                                    umma_commit(&bars->w_empty[sw]);
+                                    if (!p.w_resident) umma_commit(&bars->w_empty[sw]);
                                     if (dyi == nd - 1) umma_commit(&bars->a_empty[sa]);
                                 }
                                 __syncwarp();
@@ -402,6 +404,21 @@ int igemm_rows_plan(IgemmRowsParams* p, const ConvSegDesc* segs, int nseg, int B
         as = 4;
         ws = int((budget - size_t(4) * p->a_stage_bytes) / p->w_stage_bytes);
         if (ws > kMaxWStages) ws = kMaxWStages;
+    }
+    // Resident weights: a layer whose whole weight set is one ring's worth -- a single segment of <= 64 input channels and
+    // one N tile (the 64 -> 64 convs of the 64x64 level) -- loads its ntaps tiles ONCE per CTA; the ring has exactly ntaps
+    // stages, the MMA issuers wait for them during their first tile only and never release them.  The 72 KiB of weight
+    // traffic per 256-pixel tile (a third of the tile's bytes, nine barrier round trips) disappear.  UB_ROWS_WRES=0: off.
+    p->w_resident = 0;
+    {
+        static const bool want = !(getenv("UB_ROWS_WRES") && atoi(getenv("UB_ROWS_WRES")) == 0);
+        if (want && nseg == 1 && segs[0].Cin <= 64 && Cout == BN && ws >= segs[0].ntaps) {
+            p->w_resident = 1;
+            ws = segs[0].ntaps;
+            // the room the shorter ring frees goes to the activation ring
+            const int as2 = int((budget - size_t(ws) * p->w_stage_bytes) / p->a_stage_bytes);
+            if (as2 > as) as = as2 > kMaxAStages ? kMaxAStages : as2;
+        }
     }
     p->a_stages = as, p->w_stages = ws;
     for (int s = 0; s < nseg; ++s) {

@@ -4,7 +4,7 @@
 namespace ub {
 namespace f32 {
 
-static constexpr int kSMs = 148;
+static constexpr int kSMs = 148;  // B200 (the library is built for sm_100a only); used for grid-size heuristics, never for correctness
 
 static inline unsigned grid_for(size_t n, int threads, int waves = 8) {
     size_t b = (n + threads - 1) / threads;

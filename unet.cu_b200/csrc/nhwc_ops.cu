@@ -2,13 +2,17 @@
 // Every kernel moves 16-byte vectors (8 bf16 channels) per thread, is coalesced along the channel axis and
 // sizes its grid to a few waves of the 148 SMs.
 #include "nhwc_ops.cuh"
+#ifndef UB_GN_BWD_MINBLOCKS
+#define UB_GN_BWD_MINBLOCKS 2  // resident blocks per SM the dz-in GroupNorm backward kernel is compiled for (register cap);
+                               // measured round 2 (ms per step): 2 -> 4.89, 3 (85 registers, 60 B spilled) -> 5.03, 4 -> 5.17
+#endif
 #include "launch.cuh"
 
 #include <cstdio>
 
 namespace ub {
 
-static constexpr int kSMs = 148;
+static constexpr int kSMs = 148;  // B200 (the library is built for sm_100a only); used for grid-size heuristics, never for correctness
 
 __device__ __forceinline__ void ld8(const bf16* p, float (&f)[8]) {
     const uint4 v = *reinterpret_cast<const uint4*>(p);
@@ -71,20 +75,39 @@ __device__ __forceinline__ float column_total(const float* scratch, int C, int r
 struct RowMap {
     int C8, rows, threads, nchunks, ppb;
 };
-static RowMap make_rowmap(int B, int HW, int C) {
+// blocks_per_sm = how many blocks of the kernel fit on an SM (rowmap_occupancy): the grid is sized to ONE wave.  With a
+// fixed "3 blocks per SM" the 121-register backward kernel (two resident blocks per SM) ran its 448 blocks in two
+// waves, the second a third full (ncu, round 2: 18.8 us for the 64x64 tensors at 28 % of the HBM peak, 22 % warps active).
+static RowMap make_rowmap(int B, int HW, int C, int blocks_per_sm = 3) {
     RowMap m;
     m.C8 = C / 8;
     m.rows = 256 / m.C8;
     if (m.rows < 1) m.rows = 1;
     if (m.rows > HW) m.rows = HW;
     m.threads = m.C8 * m.rows;
+    static const bool one_wave = !(getenv("UB_GN_ONE_WAVE") && atoi(getenv("UB_GN_ONE_WAVE")) == 0);
     int want = (3 * kSMs + B - 1) / B;  // chunks per image: ~3 blocks per SM, each with a long pixel loop
+    if (one_wave) {
+        want = (blocks_per_sm * kSMs) / B;  // all blocks resident at once
+        if (want < 1) want = 1;
+    }
     int maxc = (HW + m.rows - 1) / m.rows;
     m.nchunks = want < maxc ? want : maxc;
     if (m.nchunks < 1) m.nchunks = 1;
     m.ppb = (HW + m.nchunks - 1) / m.nchunks;
     m.nchunks = (HW + m.ppb - 1) / m.ppb;
     return m;
+}
+
+// resident blocks per SM of `kernel` at (threads, dynamic smem); cached per call site (static local in the caller)
+template <typename K>
+static int rowmap_occupancy(K kernel, int threads, size_t smem) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        n = 1;
+    }
+    return n > 8 ? 8 : n;
 }
 
 // ------------------------------------------------------------------------------------------------ GN stats
@@ -126,6 +149,7 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, int ldx, int HW, int
 
 void gn_stats(const bf16* x, int ldx, int B, int HW, int C, float* chsum, cudaStream_t st) {
     RowMap m = make_rowmap(B, HW, C);
+    m = make_rowmap(B, HW, C, rowmap_occupancy(gn_stats_kernel, m.threads, 2 * size_t(m.rows) * C * sizeof(float)));
     launch_pdl(gn_stats_kernel, dim3(dim3(m.nchunks, B)), dim3(m.threads), 2 * size_t(m.rows) * C * sizeof(float), st, x, ldx, HW, C, m.C8, m.rows, m.ppb,
                                                                                    chsum);
 }
@@ -204,6 +228,7 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int ldx, const float
 void gn_apply(const bf16* x, int ldx, const float* chsum, const float* gamma, const float* beta, int B, int HW, int C,
               int G, int silu, bf16* y, int ldy, float* meanrstd, cudaStream_t st) {
     RowMap m = make_rowmap(B, HW, C);
+    m = make_rowmap(B, HW, C, rowmap_occupancy(gn_apply_kernel, m.threads, 2 * C * sizeof(float)));
     launch_pdl(gn_apply_kernel, dim3(dim3(m.nchunks, B)), dim3(m.threads), 2 * C * sizeof(float), st, 
         x, ldx, chsum, gamma, beta, HW, C, G, silu, m.C8, m.rows, m.ppb, y, ldy, meanrstd);
 }
@@ -271,6 +296,7 @@ __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ x, int ldx, const b
 void gn_bwd_stats(const bf16* x, int ldx, const bf16* dy, int lddy, const float* chsum, const float* gamma,
                   const float* beta, int B, int HW, int C, int G, int silu, float* S, cudaStream_t st) {
     RowMap m = make_rowmap(B, HW, C);
+    m = make_rowmap(B, HW, C, rowmap_occupancy(gn_bwd_stats_kernel, m.threads, (4 + 2 * size_t(m.rows)) * C * sizeof(float)));
     launch_pdl(gn_bwd_stats_kernel, dim3(dim3(m.nchunks, B)), dim3(m.threads), (4 + 2 * size_t(m.rows)) * C * sizeof(float), st, 
         x, ldx, dy, lddy, chsum, gamma, beta, HW, C, G, silu, m.C8, m.rows, m.ppb, S);
 }
@@ -360,7 +386,7 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ x, int ldx, const b
 // The same pass when dy already holds dz = dL/d gn(x) (modes 0 and 2): no activation derivative, and
 //   dx = a*dz - c1 - xhat*c2 = A*dz - Bc*x + Cc   with  A = gamma*rstd,  Bc = c2*rstd,  Cc = mean*rstd*c2 - c1
 // -- three constants per channel and two FMAs per element, 4 x (x, dz) loads in flight per thread.
-__global__ void gn_bwd_apply_dz_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ dz, int lddz,
+__global__ void __launch_bounds__(256, UB_GN_BWD_MINBLOCKS) gn_bwd_apply_dz_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ dz, int lddz,
                                        const float* __restrict__ chsum, const float* __restrict__ S,
                                        const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C,
                                        int G, int C8, int rows, int ppb, const bf16* __restrict__ add_in, int ldadd,
@@ -437,6 +463,10 @@ void gn_bwd_apply(const bf16* x, int ldx, const bf16* dy, int lddy, const float*
                   const float* gamma, const float* beta, int B, int HW, int C, int G, int silu, const bf16* add_in,
                   int ldadd, bf16* dx, int lddx, float* dgamma, float* dbeta, float* colsum_out, cudaStream_t st) {
     RowMap m = make_rowmap(B, HW, C);
+    if (silu != 1)
+        m = make_rowmap(B, HW, C, rowmap_occupancy(gn_bwd_apply_dz_kernel, m.threads, (3 + size_t(m.rows)) * C * sizeof(float)));
+    else
+        m = make_rowmap(B, HW, C, rowmap_occupancy(gn_bwd_apply_kernel, m.threads, (6 + size_t(m.rows)) * C * sizeof(float)));
     if (silu != 1) {  // dy is dz already
         launch_pdl(gn_bwd_apply_dz_kernel, dim3(dim3(m.nchunks, B)), dim3(m.threads),
                    (3 + size_t(m.rows)) * C * sizeof(float), st, x, ldx, dy, lddy, chsum, S, gamma, beta, HW, C, G, m.C8,

@@ -158,9 +158,7 @@ struct UbTrainer {
     cudaEvent_t ev_stage[2] = {nullptr, nullptr};
     bool stage_used[2] = {false, false};
     unsigned stage_next = 0;
-    // wgrad workspace
-    float* wg_partial = nullptr;
-    size_t wg_cap = size_t(24) << 20;  // floats
+    // scratch of the 3-channel weight-gradient fallback kernels (the tcgen05 wgrads accumulate with REDs, no workspace)
     float* small_scratch = nullptr;
     size_t small_scratch_floats = size_t(1) << 20;
     // tables (device)
@@ -830,7 +828,6 @@ int Builder::build() {
     T->semb = f32(size_t(B) * Cemb);
     T->d_embact = zf32(size_t(B) * Cemb), T->demb = f32(size_t(B) * Cemb);
     T->d_h0act = zf32(size_t(B) * Cemb), T->dh0 = f32(size_t(B) * Cemb);
-    T->wg_partial = f32(T->wg_cap);
     T->small_scratch = f32(T->small_scratch_floats);
     T->emb_table = (SmallLinear*)T->arena.alloc(kMaxEmbEntries * sizeof(SmallLinear));
     T->temb_table = (SmallLinear*)T->arena.alloc(2 * sizeof(SmallLinear));
