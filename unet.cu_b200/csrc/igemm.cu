@@ -731,24 +731,31 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     }
 }
 
-// dw[o][c][tap] = acc[tap][o][c]; acc = 0.  grid (ceil(max_elems / 32), n_entries), block 288 = 32 (o,c) pairs x 9 taps:
-// reads are 9 coalesced 128-byte rows, the write is one contiguous 1152-byte run.
+// dw[o][c][tap] = acc[tap][o][c]; acc = 0.  grid (ceil(max_elems / 256), n_entries), block 288 = 32 (o,c) pairs x 9 taps,
+// eight 32-element chunks per block: reads are 9 coalesced 128-byte rows per chunk, the write one contiguous 1152-byte
+// run.  (One chunk per block -- 26 880 blocks of 1.1 KB for a bucket -- cost 16 us per launch in ncu, mostly block
+// scheduling; skipping the kernel altogether bought 0.04 ms of the step, profiles/r02_skip_experiments.txt.)
 __global__ void __launch_bounds__(288) wgrad_finalize_kernel(const WgradFinalizeEntry* __restrict__ table) {
     pdl_entry();
     const WgradFinalizeEntry e = table[blockIdx.y];
     const size_t n = size_t(e.Cout) * e.Cin;
-    const size_t e0 = size_t(blockIdx.x) * 32;
-    if (e0 >= n) return;
-    __shared__ float t[9][33];
+    __shared__ float t[2][9][33];
     const int el = threadIdx.x & 31, tap = threadIdx.x >> 5;  // 9 warps: warp = tap
-    if (e0 + el < n) {
-        float* src = e.acc + size_t(tap) * n + e0 + el;
-        t[tap][el] = *src;
-        *src = 0.f;
+    const int i = threadIdx.x;                                 // output run: (element i / 9, tap i % 9)
+    const int oe = i / 9, ot = i - oe * 9;
+#pragma unroll 1
+    for (int k = 0; k < 8; ++k) {
+        const size_t e0 = (size_t(blockIdx.x) * 8 + k) * 32;
+        if (e0 >= n) break;  // (uniform over the block)
+        float(*tk)[33] = t[k & 1];
+        if (e0 + el < n) {
+            float* src = e.acc + size_t(tap) * n + e0 + el;
+            tk[tap][el] = *src;
+            *src = 0.f;
+        }
+        __syncthreads();  // (double-buffered tile: one barrier per chunk)
+        if (e0 + oe < n) e.dw[e0 * 9 + i] = tk[ot][oe];
     }
-    __syncthreads();
-    const int i = threadIdx.x;  // output run: (element i / 9, tap i % 9)
-    if (e0 + i / 9 < n) e.dw[e0 * 9 + i] = t[i % 9][i / 9];
 }
 
 // =====================================================================================================
@@ -1135,7 +1142,9 @@ int igemm_wgrad_plan_acc(IgemmWgradParams* p, const __nv_bfloat16* dy, int ldy, 
 
 int igemm_wgrad_finalize(const WgradFinalizeEntry* table_dev, int n_entries, size_t max_elems, cudaStream_t st) {
     if (n_entries < 1) return 0;
-    return int(launch_pdl(wgrad_finalize_kernel, dim3(unsigned((max_elems + 31) / 32), unsigned(n_entries)), dim3(288),
+    static const bool skip = getenv("UB_DEBUG_SKIP_FINALIZE") != nullptr;  // timing experiments only (wrong gradients)
+    if (skip) return 0;
+    return int(launch_pdl(wgrad_finalize_kernel, dim3(unsigned((max_elems + 255) / 256), unsigned(n_entries)), dim3(288),
                           0, st, table_dev));
 }
 

@@ -1,5 +1,6 @@
 // See misc_ops.cuh.
 #include "misc_ops.cuh"
+#include <cstdlib>
 #include "launch.cuh"
 
 #include <cstdio>
@@ -598,42 +599,83 @@ void diffusion_prepare(const float* x0, const float* sqrt_ac, const float* sqrt_
 // =====================================================================================================
 // weight packing: 32x32 (o, c) tiles through smem so both packed layouts are written coalesced
 // =====================================================================================================
-__global__ void pack_weights_kernel(const PackEntry* __restrict__ table) {
+// One 32 (o) x 32 (c) tile of all taps per block.  An o row of the tile is ONE contiguous run of 32 * ntaps floats in
+// the (Cout, Cin, taps) master layout: it is read as float4 into raw[oo][cc * ntaps + tap] (row pitch 32 * ntaps + 1
+// floats, so that walking oo at fixed (cc, tap) -- the dgrad pack -- and walking cc at fixed (oo, tap) -- stride ntaps,
+// odd -- are both bank-conflict free); every thread then writes bf16 PAIRS (4-byte stores, 128 B per warp and row pair).
+// (The first version read scalars with a divide per element and wrote 2-byte stores: 31 us per bucket in ncu at 3-6 %
+// of the HBM peak; skipping the re-pack bought 0.09 ms of the step, profiles/r02_skip_experiments.txt.)
+__global__ void __launch_bounds__(256) pack_weights_kernel(const PackEntry* __restrict__ table) {
     pdl_entry();
     const PackEntry e = table[blockIdx.y];
     const int tiles_c = (e.Cin + 31) / 32, tiles_o = (e.Cout + 31) / 32;
     if (int(blockIdx.x) >= tiles_c * tiles_o) return;
     const int o0 = (blockIdx.x / tiles_c) * 32, c0 = (blockIdx.x % tiles_c) * 32;
-    __shared__ float tile[9][32][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 256 threads: ty in 0..7
     const int nt = e.ntaps;
-    // load: rows o, the (c, tap) run is contiguous in memory: nt*32 floats per o row
+    const int run = 32 * nt, pitch = run + 1;
+    extern __shared__ float raw[];  // [32][pitch]
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 256 threads: ty in 0..7
+    const bool full = o0 + 32 <= e.Cout && c0 + 32 <= e.Cin && ((size_t(c0) * nt) % 4) == 0 && ((size_t(e.Cin) * nt) % 4) == 0 &&
+                      (reinterpret_cast<uintptr_t>(e.w) & 15) == 0;
     for (int oo = ty; oo < 32; oo += 8) {
         const int o = o0 + oo;
-        for (int i = tx; i < 32 * nt; i += 32) {
-            const int cc = i / nt, tap = i % nt;
-            float v = 0.f;
-            if (o < e.Cout && c0 + cc < e.Cin) v = e.w[(size_t(o) * e.Cin + c0 + cc) * nt + tap];
-            tile[tap][oo][cc] = v;
+        float* dst = raw + oo * pitch;
+        if (full) {
+            const float4* src = reinterpret_cast<const float4*>(e.w + (size_t(o) * e.Cin + c0) * nt);
+            for (int i = tx; i < run / 4; i += 32) {
+                const float4 v = src[i];
+                dst[4 * i] = v.x, dst[4 * i + 1] = v.y, dst[4 * i + 2] = v.z, dst[4 * i + 3] = v.w;
+            }
+        } else {
+            for (int i = tx; i < run; i += 32) {
+                const int cc = i / nt;
+                dst[i] = (o < e.Cout && c0 + cc < e.Cin) ? e.w[(size_t(o) * e.Cin + c0) * nt + i] : 0.f;
+            }
         }
     }
     __syncthreads();
-    for (int tap = 0; tap < nt; ++tap) {
-        if (e.wf) {
-            for (int oo = ty; oo < 32; oo += 8)
-                if (o0 + oo < e.Cout && c0 + tx < e.Cin)
-                    e.wf[(size_t(tap) * e.Cout + o0 + oo) * e.Cin + c0 + tx] = __float2bfloat16(tile[tap][oo][tx]);
+    // 16 lanes per 32-element output row (two elements each); a warp writes two rows per step
+    const int half = tx >> 4, l2 = (tx & 15) * 2;
+    if (e.wf && (e.Cin % 2) == 0) {  // fprop pack [tap][o][c]: rows (tap, oo), pairs along c
+        for (int r = ty * 2 + half; r < 32 * nt; r += 16) {
+            const int tap = r / 32, oo = r - tap * 32;
+            if (o0 + oo < e.Cout && c0 + l2 < e.Cin) {
+                const float* sp = raw + oo * pitch + l2 * nt + tap;
+                const __nv_bfloat162 v = __floats2bfloat162_rn(sp[0], c0 + l2 + 1 < e.Cin ? sp[nt] : 0.f);
+                *reinterpret_cast<__nv_bfloat162*>(e.wf + (size_t(tap) * e.Cout + o0 + oo) * e.Cin + c0 + l2) = v;
+            }
         }
-        if (e.wd) {
-            for (int cc = ty; cc < 32; cc += 8)
-                if (c0 + cc < e.Cin && o0 + tx < e.Cout)
-                    e.wd[(size_t(nt - 1 - tap) * e.Cin + c0 + cc) * e.Cout + o0 + tx] =
-                        __float2bfloat16(tile[tap][tx][cc]);
+    } else if (e.wf) {
+        for (int r = ty; r < 32 * nt; r += 8) {
+            const int tap = r / 32, oo = r - tap * 32;
+            if (o0 + oo < e.Cout && c0 + tx < e.Cin)
+                e.wf[(size_t(tap) * e.Cout + o0 + oo) * e.Cin + c0 + tx] = __float2bfloat16(raw[oo * pitch + tx * nt + tap]);
+        }
+    }
+    if (e.wd && (e.Cout % 2) == 0) {  // dgrad pack [ntaps-1-tap][c][o]: rows (tap, cc), pairs along o
+        for (int r = ty * 2 + half; r < 32 * nt; r += 16) {
+            const int tap = r / 32, cc = r - tap * 32;
+            if (c0 + cc < e.Cin && o0 + l2 < e.Cout) {
+                const float* sp = raw + l2 * pitch + cc * nt + tap;
+                const __nv_bfloat162 v = __floats2bfloat162_rn(sp[0], o0 + l2 + 1 < e.Cout ? sp[pitch] : 0.f);
+                *reinterpret_cast<__nv_bfloat162*>(e.wd + (size_t(nt - 1 - tap) * e.Cin + c0 + cc) * e.Cout + o0 + l2) = v;
+            }
+        }
+    } else if (e.wd) {
+        for (int r = ty; r < 32 * nt; r += 8) {
+            const int tap = r / 32, cc = r - tap * 32;
+            if (c0 + cc < e.Cin && o0 + tx < e.Cout)
+                e.wd[(size_t(nt - 1 - tap) * e.Cin + c0 + cc) * e.Cout + o0 + tx] =
+                    __float2bfloat16(raw[tx * pitch + cc * nt + tap]);
         }
     }
 }
 void pack_weights(const PackEntry* table_dev, int n_entries, int max_tiles, cudaStream_t st) {
-    launch_pdl(pack_weights_kernel, dim3(dim3(max_tiles, n_entries)), dim3(256), 0, st, table_dev);
+    static const bool skip = getenv("UB_DEBUG_SKIP_PACK") != nullptr;  // timing experiments only (stale bf16 weights)
+    if (skip) return;
+    // (9 taps: 32 x 289 floats = 36 992 B of dynamic shared memory, below the 48 KiB that needs no opt-in)
+    launch_pdl(pack_weights_kernel, dim3(dim3(max_tiles, n_entries)), dim3(256), size_t(32) * (32 * 9 + 1) * sizeof(float), st,
+               table_dev);
 }
 
 // =====================================================================================================
