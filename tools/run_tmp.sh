@@ -1,12 +1,13 @@
 o=gpurun_out; mkdir -p $o
-timeout 900 python -m pytest tests/test_trainer_gpu.py -m gpu -q -x > $o/s24_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $o/s24_pytest.log
-b() { tag=$1; shift; env "$@" timeout 200 python bench.py --steps 30 --warmup 10 --no-cpu-baseline --no-reference-cuda > $o/$tag.json 2> $o/$tag.err; python -c "
+run() { tag=$1; np=$2; shift 2; env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $np --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 500)) bench.py --gpus $np --steps 40 --warmup 10 > $o/$tag.json 2> $o/$tag.err; python -c "
 import json
 try:
-    d=json.loads(open('$o/$tag.json').read().strip().splitlines()[-1]); print('$tag', round(d['ms_per_step'],4), round(d['roofline']['frac'],4), round(d['profile_total_ms'],3), {k:(round(v['ms'],3), v.get('tflops')) for k,v in d['kernel_classes'].items()})
+    d=json.loads(open('$o/$tag.json').read().strip().splitlines()[-1]); print('$tag', 'gpus', d['n_gpus'], 'ms', round(d['ms_per_step'],4), 'img/s', round(d['value'],1))
 except Exception as e: print('$tag', 'ERR', e)
-"; tail -3 $o/$tag.err; }
-b s24_new A=1
-b s24_wg128 UB_WGRAD_SMEM_KB=128
-b s24_wg64 UB_WGRAD_SMEM_KB=64
-timeout 120 python tools/timeline.py 32 $o/s24_timeline.tsv > $o/s24_timeline.txt 2>&1
+"; grep -iE "error|fail" $o/$tag.err | head -2 | cut -c1-200; }
+run n_cta8_tail1 8 NCCL_MAX_CTAS=8 UB_TAIL_NODE=1
+run n_cta8_tail2 8 NCCL_MAX_CTAS=8 UB_TAIL_NODE=2
+run n_cta8_tail2_ll128 8 NCCL_MAX_CTAS=8 UB_TAIL_NODE=2 NCCL_PROTO=LL128
+run n_cta8_tail2_nvls 8 NCCL_MAX_CTAS=8 UB_TAIL_NODE=2 NCCL_ALGO=NVLS
+run n_cta8_tail2_tree 8 NCCL_MAX_CTAS=8 UB_TAIL_NODE=2 NCCL_ALGO=Tree
+run n_cta16_tail2 8 NCCL_MAX_CTAS=16 UB_TAIL_NODE=2

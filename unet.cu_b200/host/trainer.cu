@@ -1031,8 +1031,16 @@ int Builder::build() {
         // (Measured round 2: further cuts at the level boundaries of the down path, so that only the first level's
         //  small bucket waits for the end of backward, cost more in extra optimizer / re-pack launches on the tail
         //  than the shorter last all-reduce won: 5.08 vs 5.02 ms on one GPU, 5.13 vs 5.11 on two.)
-        if (tail_cut && nodes.size() > 1 && nodes[1].param_begin > time_mlp_end &&
-            (cuts.empty() || nodes[1].param_begin < cuts.back()))
+        // UB_TAIL_NODE = n: the last bucket ends above node n (1 (default) = only the time MLP and the input conv; 2 = the
+        // first ResBlock too, so that the last full-size all-reduce is complete one ResBlock earlier).  Measured round 2:
+        // 2 costs the single GPU 0.08 ms (a longer serial optimizer tail) and changes nothing on 8 GPUs (5.015 vs 5.006).
+        static const int tail_node = getenv("UB_TAIL_NODE") ? atoi(getenv("UB_TAIL_NODE")) : 1;
+        const size_t tn = size_t(tail_node < 1 ? 1 : tail_node);
+        if (tail_cut && nodes.size() > tn && nodes[tn].param_begin > time_mlp_end && (nodes[tn].param_begin % 4) == 0 &&
+            (cuts.empty() || nodes[tn].param_begin < cuts.back()))
+            cuts.push_back(nodes[tn].param_begin);
+        else if (tail_cut && nodes.size() > 1 && nodes[1].param_begin > time_mlp_end &&
+                 (cuts.empty() || nodes[1].param_begin < cuts.back()))
             cuts.push_back(nodes[1].param_begin);
     }
     size_t flushed_hi = T->nparams;
@@ -1493,9 +1501,25 @@ static int ensure_packed(UbTrainer* t) {
     return UB_OK;
 }
 
-static int stage_inputs(UbTrainer* t, const float* x0_host, const float* t_host, const float* noise_host) {
+// `sync_call`: the caller blocks until the step has finished (it asked for the loss), so a page-locked source buffer
+// cannot be overwritten while the copy is in flight: it is DMA'd directly, without the pass through the staging slot
+// (1.5 MB of host memcpy per step at B = 32, ~0.1 ms of the end-to-end step).
+static bool is_pinned_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+static int stage_inputs(UbTrainer* t, const float* x0_host, const float* t_host, const float* noise_host,
+                        bool sync_call = false) {
     const UbConfig& c = t->cfg;
     const size_t img = size_t(c.B) * c.C_in * c.H * c.W;
+    if (sync_call && !t_host && !noise_host && is_pinned_host(x0_host)) {
+        CUDA_TRY(cudaMemcpyAsync(t->x0, x0_host, img * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+        return UB_OK;
+    }
     const int k = int(t->stage_next++ & 1u);
     if (t->stage_used[k]) CUDA_TRY(cudaEventSynchronize(t->ev_stage[k]));  // the copies that last read this slot are done
     memcpy(t->hs_x0[k], x0_host, img * sizeof(float));
@@ -1595,7 +1619,7 @@ extern "C" int ub_trainer_train_step(UbTrainer* t, const float* x0_host, const f
                                      float lr, float beta1, float beta2, float eps, float weight_decay,
                                      float* loss_out) {
     CUDA_TRY(cudaSetDevice(t->device));
-    int r = stage_inputs(t, x0_host, t_host, noise_host);
+    int r = stage_inputs(t, x0_host, t_host, noise_host, loss_out != nullptr);
     if (r) return r;
     StepOpts o{t_host == nullptr, noise_host == nullptr, true, lr, beta1, beta2, eps, weight_decay};
     r = launch_step(t, o);
@@ -2028,6 +2052,10 @@ extern "C" int ub_trainer_attach_dp(UbTrainer* t, int rank, int world, const voi
     if (n_buckets != t->n_buckets && n_buckets > 0)
         fprintf(stderr, "[unet_b200] note: bucket count is fixed at build time (%d)\n", t->n_buckets);
     CUDA_TRY(cudaSetDevice(t->device));
+    // The all-reduces run beside backward: every NCCL CTA takes an SM slot from the conv / wgrad kernels.  Measured on
+    // 8 x B200 (ms per step, B = 32 per GPU): NCCL default 5.089, NCCL_MAX_CTAS = 16: 5.021, 8: 5.004, 4: 5.159
+    // (profiles/r02_scaling.txt).  Only a default: an NCCL_MAX_CTAS already in the environment wins.
+    setenv("NCCL_MAX_CTAS", "8", /*overwrite=*/0);
     ncclUniqueId id;
     memcpy(&id, nccl_id, sizeof id);
     int r = nccl().CommInitRank(&t->comm, world, id, rank);
