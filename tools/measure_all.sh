@@ -9,7 +9,7 @@
 tag=${1:-final}
 o=gpurun_out
 mkdir -p $o
-timeout 900 python -m pytest tests -m gpu -q > $o/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 $o/${tag}_pytest_gpu.log
+timeout 900 python -m pytest tests -m gpu -q -rs > $o/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 $o/${tag}_pytest_gpu.log
 timeout 900 python bench.py > $o/${tag}_bench.json 2> $o/${tag}_bench.err; echo "bench rc=$?"
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $o/${tag}_bench_reference_arm.json 2> $o/${tag}_bench_reference_arm.err; echo "reference arm rc=$?"
 timeout 120 python tools/profile_step.py 3 > $o/${tag}_plain.log 2>&1 || { echo "plain run failed"; cat $o/${tag}_plain.log; exit 1; }
