@@ -237,6 +237,12 @@ typedef struct {
     int random_flip;     /* on-GPU augmentation: every image of a batch is mirrored left-right with probability 1/2 before
                             q-sample (the PyTorch loader's random_flip, train_unet.py:508-536: arr[:, ::-1]; the reference's
                             C loader has none).  Decisions are Philox draws keyed by (seed, step, image); 0 */
+    int num_classes;     /* > 0: class-conditional model (dev/unet.py:142,174-175,301-303 `num_classes`): a label-embedding
+                            table (num_classes, 4*C_model) follows the time MLP in the parameter order and
+                            emb = time_embed(t) + label_emb[y]; labels come from ub_trainer_set_labels; 0 */
+    float ema_rate;      /* > 0: keep an exponential moving average of the parameters, ema = rate*ema + (1-rate)*p
+                            after every AdamW update, fused into the AdamW kernel (guided-diffusion's update_ema;
+                            the option the reference carries as `ema_rate`, train_unet.py:708); 0 */
 } UbConfig;
 
 void ub_default_config(UbConfig* cfg);
@@ -262,6 +268,13 @@ int ub_read_checkpoint_header(const char* path, UbConfig* cfg);
 int ub_trainer_set_params(UbTrainer* t, const float* host, size_t n);
 int ub_trainer_get_params(UbTrainer* t, float* host, size_t n);
 int ub_trainer_get_grads(UbTrainer* t, float* host, size_t n);
+/* moving average of the parameters (cfg.ema_rate > 0): starts as a copy of the parameters (set_params / load) */
+int ub_trainer_get_ema(UbTrainer* t, float* host, size_t n);
+int ub_trainer_set_ema(UbTrainer* t, const float* host, size_t n);
+int ub_trainer_save_ema(UbTrainer* t, const char* path); /* parameters-only .bin of the averaged weights */
+/* class labels y (B ints in [0, num_classes)) of the batch(es) that follow (cfg.num_classes > 0, dev/unet.py:301-303);
+ * used by forward_backward / train_step / predict / sample until set again */
+int ub_trainer_set_labels(UbTrainer* t, const int* labels_host, size_t n);
 int ub_trainer_get_output(UbTrainer* t, float* host, size_t n); /* last forward's eps prediction (B,C_out,H,W) */
 /* the flip decisions (0 / 1 per image) the last step took, when cfg.random_flip is set */
 int ub_trainer_get_flips(UbTrainer* t, int* host, size_t n);

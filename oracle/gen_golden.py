@@ -112,6 +112,37 @@ def main():
     print("golden fixtures written to", out_dir, "losses", losses)
 
 
+def gen_class_cond(out_dir):
+    """Class-conditional model (dev/unet.py num_classes=10), zero-initialised tensors perturbed (oracle.perturb_zero_params
+    recipe applied to the reference model's own parameters), B = 2, labels (3, 7): loss, output slice, gradient slice,
+    per-tensor gradient norms and the full label-embedding gradient.   python oracle/gen_golden.py class_cond"""
+    from unet import UNetModel
+    import train_unet as ref_train
+    torch.manual_seed(0)
+    model = UNetModel(3, 64, 3, 2, (4, 8), num_head_channels=32, num_classes=10)
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for _, p in model.named_parameters():
+            if not p.detach().any():
+                p.add_(0.02 * torch.randn(p.shape, generator=g))
+    shapes = [tuple(p.shape) for _, p in model.named_parameters()]
+    diffusion = ref_train.GaussianDiffusion(ref_train.get_named_beta_schedule("linear", 1000))
+    B = 2
+    x0, t, noise = synthetic(B)
+    y = torch.tensor([3, 7])
+    out = model(diffusion.q_sample(x0, t.view(B).long(), noise), t, y)
+    loss = ((out - noise) ** 2).mean()
+    loss.backward()
+    gflat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    np.savez_compressed(
+        os.path.join(out_dir, "class_cond_B2.npz"), labels=y.numpy(), loss=np.array([float(loss)]),
+        out_slice=out.detach().reshape(-1)[::37].numpy(), grad_slice=gflat[::4099].numpy(),
+        grad_norms=np.array([float(gflat[o:o + n].double().norm()) for o, n in offsets(shapes)]),
+        label_emb_grad=model.label_emb.weight.grad.numpy(),
+        param_slice=torch.cat([p.detach().reshape(-1) for p in model.parameters()])[::4099].numpy())
+    print("class_cond_B2.npz written, loss", float(loss))
+
+
 def offsets(shapes):
     o = 0
     for s in shapes:
@@ -127,4 +158,9 @@ def pad4(v):
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "class_cond":   # (added later: leaves the other fixtures untouched)
+        torch.set_num_threads(os.cpu_count())
+        gen_class_cond(os.path.join(ROOT, "tests", "golden"))
+    else:
+        main()
+        gen_class_cond(os.path.join(ROOT, "tests", "golden"))

@@ -40,6 +40,7 @@ class UNetConfig:
     max_period: int = 1000             # header[7], dev/unet.py:327
     H: int = 64
     W: int = 64
+    num_classes: int = 0               # > 0: class-conditional, label_emb = nn.Embedding(num_classes, 4*mc) (dev/unet.py:174-175)
 
     @property
     def emb_channels(self) -> int:
@@ -90,6 +91,9 @@ def build_layers(cfg: UNetConfig) -> List[Layer]:
                    name="time_embed.0"))
     L.append(Layer('linear', cemb, cemb, params=[("time_embed.2.weight", (cemb, cemb)),
                                                    ("time_embed.2.bias", (cemb,))], name="time_embed.2"))
+    if cfg.num_classes:   # dev/unet.py:174-175: constructed (and hence ordered) right after time_embed
+        L.append(Layer('embed', cfg.num_classes, cemb, params=[("label_emb.weight", (cfg.num_classes, cemb))],
+                       name="label_emb"))
     ch = cfg.channel_mult[0] * mc
     L.append(Layer('conv3', cfg.in_channels, ch, params=[("input_blocks.0.0.weight", (ch, cfg.in_channels, 3, 3)),
                                                           ("input_blocks.0.0.bias", (ch,))], skip_push=True,
@@ -159,6 +163,10 @@ def init_params(cfg: UNetConfig, seed: int = 0, dtype=torch.float32) -> Dict[str
     while i < len(spec):
         name, shape = spec[i]
         base = name.rsplit('.', 1)[0]
+        if name == 'label_emb.weight':                         # nn.Embedding: N(0, 1), no bias
+            out[name] = torch.nn.Embedding(shape[0], shape[1]).weight.detach().to(dtype).clone()
+            i += 1
+            continue
         if len(shape) == 1 and name.endswith('.weight'):      # GroupNorm affine: ones / zeros
             out[name] = torch.ones(shape, dtype=dtype)
             out[spec[i + 1][0]] = torch.zeros(spec[i + 1][1], dtype=dtype)
@@ -306,14 +314,20 @@ def attention_block(x, P, prefix: str, head_size=32, groups=32):
     return x + F.conv1d(a, P[prefix + '.proj.weight'], P[prefix + '.proj.bias']).reshape(B, C, H, W)
 
 
-def unet_forward(cfg: UNetConfig, P: Dict[str, torch.Tensor], x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
-    """dev/unet.py:293-319, train_unet.cu:4335-4416."""
+def unet_forward(cfg: UNetConfig, P: Dict[str, torch.Tensor], x: torch.Tensor, t: torch.Tensor,
+                 y: torch.Tensor | None = None) -> torch.Tensor:
+    """dev/unet.py:283-319, train_unet.cu:4335-4416.  `y` (B,) int64 class labels iff cfg.num_classes (dev/unet.py:291-303)."""
+    assert (y is not None) == bool(cfg.num_classes), "must specify y if and only if the model is class-conditional"
     emb = timestep_embedding(t, cfg.model_channels, cfg.max_period).to(x.dtype)
     emb = F.linear(emb, P['time_embed.0.weight'], P['time_embed.0.bias'])
     emb = F.linear(silu(emb), P['time_embed.2.weight'], P['time_embed.2.bias'])
+    if cfg.num_classes:
+        emb = emb + P['label_emb.weight'][y.long()]
     hs: List[torch.Tensor] = []
     h = x
-    for l in build_layers(cfg)[2:]:
+    for l in build_layers(cfg):
+        if l.kind in ('linear', 'embed'):
+            continue
         if l.kind == 'conv3':
             h = conv3x3(h, P[l.name + '.weight'], P[l.name + '.bias'])
         elif l.kind == 'res':
@@ -410,12 +424,35 @@ def synthetic_batch(cfg: UNetConfig, B: int, seed: int = 1234):
     return x0, t, noise
 
 
-def train_step_grads(cfg: UNetConfig, flat: torch.Tensor, x0, t, noise):
+def ema_update(ema: torch.Tensor, p: torch.Tensor, rate: float) -> torch.Tensor:
+    """Exponential moving average of the parameters after an optimizer step: guided-diffusion's `update_ema`
+    (targ.mul_(rate).add_(src, alpha=1 - rate)), the algorithm behind the `ema_rate` option the reference carries
+    (train_unet.py:708) but never applies."""
+    return ema * rate + p * (1 - rate)
+
+
+def perturb_zero_params(cfg: UNetConfig, flat: torch.Tensor, seed: int = 5, std: float = 0.02) -> torch.Tensor:
+    """Test helper: N(0, std^2) noise on every tensor that is all-zero at initialisation (the zero_module conv2 / proj
+    weights, dev/unet.py:21-27, and all biases PyTorch zero-fills), drawn tensor by tensor in parameter order.  With
+    conv2 at zero nothing upstream of it -- the whole embedding path in particular -- receives a gradient, so tests of
+    that path start from these weights."""
+    g = torch.Generator().manual_seed(seed)
+    flat = flat.clone()
+    off = 0
+    for _, shape in param_spec(cfg):
+        n = int(np.prod(shape))
+        if not flat[off:off + n].any():
+            flat[off:off + n] += std * torch.randn(shape, generator=g).reshape(-1)
+        off += n
+    return flat
+
+
+def train_step_grads(cfg: UNetConfig, flat: torch.Tensor, x0, t, noise, y=None):
     """One forward + backward of the training step (train_unet.cu:5019-5036): returns loss, out, grads(flat)."""
     flat = flat.detach().clone().requires_grad_(True)
     P = unflatten_params(cfg, flat)
     x_t = q_sample(x0.to(flat.dtype), t, noise.to(flat.dtype))
-    out = unet_forward(cfg, P, x_t, t.to(flat.dtype))
+    out = unet_forward(cfg, P, x_t, t.to(flat.dtype), y)
     loss = mse_loss(out, noise.to(flat.dtype))
     loss.backward()
     return loss.detach(), out.detach(), flat.grad.detach()

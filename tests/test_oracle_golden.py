@@ -89,3 +89,29 @@ def test_model_bin_layout_matches_reference_writer(oracle, golden_dir, tmp_path)
     np.testing.assert_array_equal(header, g["header"])
     assert payload.size == int(g["n_floats"][0])
     np.testing.assert_array_equal(payload[::4099], g["payload_slice"])
+
+
+def test_class_conditional_step_matches_reference(oracle, golden_dir):
+    """num_classes = 10 (dev/unet.py:174-175, 301-303) from perturbed weights: the fixture came from the reference's own
+    UNetModel(num_classes=10); loss, output, gradients incl. the complete label-embedding gradient."""
+    O = oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = np.load(os.path.join(golden_dir, "class_cond_B2.npz"))
+    cfg = O.UNetConfig(num_classes=10)
+    assert O.param_spec(cfg)[4] == ("label_emb.weight", (10, 256))
+    assert O.num_params(cfg) == 20494211 + 2560
+    flat = O.perturb_zero_params(cfg, _flat(O, cfg, O.init_params(cfg, seed=0)))
+    np.testing.assert_array_equal(flat[::4099].numpy(), g["param_slice"])
+    x0, t, noise = O.synthetic_batch(cfg, 2)
+    loss, out, grads = O.train_step_grads(cfg, flat, x0, t, noise, torch.from_numpy(g["labels"]))
+    assert abs(float(loss) - float(g["loss"][0])) < 1e-6
+    np.testing.assert_allclose(out.reshape(-1)[::37].numpy(), g["out_slice"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(grads[::4099].numpy(), g["grad_slice"], rtol=1e-3, atol=1e-6)
+    P = O.unflatten_params(cfg, grads)
+    np.testing.assert_allclose(P["label_emb.weight"].numpy(), g["label_emb_grad"], rtol=1e-3, atol=1e-7)
+    off, norms = 0, []
+    for _, s in O.param_spec(cfg):
+        n = int(np.prod(s))
+        norms.append(float(grads[off:off + n].double().norm()))
+        off += n
+    np.testing.assert_allclose(np.array(norms), g["grad_norms"], rtol=1e-3)

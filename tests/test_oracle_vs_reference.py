@@ -86,3 +86,40 @@ def test_sampler_matches_generate_py(oracle, ref_unet):
             x_ref = gen.sample_next_step(x_ref, torch.tensor([[t]]), model, 1000, beta_t, acp).float()
     x_or = O.ddpm_sample(cfg, P, x, 700, 698, noises)
     assert float((x_or - x_ref).abs().max()) < 1e-4
+
+
+def test_class_conditional_matches_reference(oracle, ref_unet):
+    """num_classes (dev/unet.py:142,174-175,301-303): parameter order / init bit-identical, forward and every gradient
+    (the label-embedding rows included) against the reference's own UNetModel.  The zero-initialised conv2 / proj
+    weights are perturbed first -- with them at zero nothing upstream of a ResBlock's second conv receives a gradient,
+    the embedding path included."""
+    O = oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.UNetConfig(num_classes=10)
+    torch.manual_seed(0)
+    model = ref_unet.UNetModel(3, 64, 3, 2, (4, 8), num_head_channels=32, num_classes=10)
+    names = [(n, tuple(p.shape)) for n, p in model.named_parameters()]
+    assert names == O.param_spec(cfg)
+    assert names[4] == ("label_emb.weight", (10, 256))
+    P = O.init_params(cfg, seed=0)
+    for n, p in model.named_parameters():
+        assert torch.equal(P[n], p.detach()), n
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if not p.detach().any():
+                p.add_(0.02 * torch.randn(p.shape, generator=g))
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    B = 2
+    x0, t, noise = O.synthetic_batch(cfg, B)
+    y = torch.tensor([3, 7])
+    loss, out, gr = O.train_step_grads(cfg, flat, x0, t, noise, y)
+    out_ref = model(O.q_sample(x0, t, noise), t, y)
+    loss_ref = ((out_ref - noise) ** 2).mean()
+    loss_ref.backward()
+    g_ref = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    assert abs(float(loss) - float(loss_ref)) < 1e-6
+    assert float((out - out_ref.detach()).abs().max()) < 1e-5
+    assert float((gr - g_ref).abs().max()) < 1e-6 + 1e-4 * float(g_ref.abs().max())
+    ge = model.label_emb.weight.grad
+    assert float(ge[3].abs().max()) > 0 and float(ge[7].abs().max()) > 0 and float(ge[0].abs().max()) == 0

@@ -422,3 +422,86 @@ def test_other_configs_match_oracle(ub, oracle, kw, okw, B):
     l2 = tr.train_step(x0.numpy(), t.numpy(), noise.numpy(), lr=1e-4)   # the captured-graph path runs too
     assert np.isfinite(l2)
     tr.close()
+
+
+def test_class_conditional_matches_oracle(ub, oracle, golden_dir):
+    """class-conditional embedding (dev/unet.py:174-175, 301-303).  Weights = the initialisation
+    with the zero-initialised tensors perturbed (otherwise the embedding path receives no gradient); loss, output and
+    every gradient against the oracle, the label-embedding gradient also against the fixture the reference's own
+    UNetModel(num_classes=10) produced; rows of unused classes stay exactly zero; predict() takes the labels too."""
+    O = oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.UNetConfig(num_classes=10)
+    flat = O.perturb_zero_params(cfg, O.flatten_params(cfg, O.init_params(cfg, seed=0)))
+    gold = np.load(os.path.join(golden_dir, "class_cond_B2.npz"))
+    B = 2
+    x0, t, noise = O.synthetic_batch(cfg, B)
+    y = gold["labels"]
+    tr = ub.Trainer(B=B, num_classes=10)
+    assert tr.nparams == flat.numel() == 20494211 + 10 * 256
+    tr.set_params(flat.numpy())
+    tr.set_labels(y)
+    loss = tr.forward_backward(x0.numpy(), t.numpy(), noise.numpy())
+    out, g = tr.get_output(), tr.get_grads()
+    loss_ref, out_ref, g_ref = O.train_step_grads(cfg, flat, x0, t, noise, torch.from_numpy(y))
+    assert abs(loss - float(loss_ref)) <= 2e-3 * float(loss_ref)
+    assert abs(loss - float(gold["loss"][0])) <= 2e-3 * float(gold["loss"][0])
+    assert np.abs(out - out_ref.numpy()).max() <= 3e-2 * np.abs(out_ref.numpy()).max()
+    rows = {name: rel for rel, name, _, _ in check_grads(O, cfg, g, g_ref.numpy(), "class-conditional")}
+    assert rows["label_emb.weight"] <= 2e-2, rows["label_emb.weight"]
+    off = sum(int(np.prod(s)) for _, s in O.param_spec(cfg)[:4])
+    ge = g[off:off + 2560].reshape(10, 256)
+    ref = gold["label_emb_grad"]
+    assert np.linalg.norm(ge - ref) <= 2e-2 * np.linalg.norm(ref)
+    unused = [k for k in range(10) if k not in set(y.tolist())]
+    assert np.abs(ge[unused]).max() == 0.0
+    # other labels -> another output; the same labels through predict() -> the oracle's forward
+    xt = O.q_sample(x0, t, noise)
+    with torch.no_grad():
+        P = O.unflatten_params(cfg, flat)
+        o_same = O.unet_forward(cfg, P, xt, t, torch.from_numpy(y)).numpy()
+        o_other = O.unet_forward(cfg, P, xt, t, torch.tensor([1, 2])).numpy()
+    assert np.abs(tr.predict(xt.numpy(), t.numpy()) - o_same).max() <= 3e-2 * np.abs(o_same).max()
+    tr.set_labels([1, 2])
+    assert np.abs(tr.predict(xt.numpy(), t.numpy()) - o_other).max() <= 3e-2 * np.abs(o_other).max()
+    # the captured-graph training step reads the label buffer too
+    l2 = tr.train_step(x0.numpy(), t.numpy(), noise.numpy(), lr=1e-4)
+    assert np.isfinite(l2)
+    with pytest.raises(ub.UbError):
+        tr.set_labels([1, 10])
+    tr.close()
+    plain = ub.Trainer(B=B)
+    with pytest.raises(ub.UbError):
+        plain.set_labels([0, 1])
+    plain.close()
+
+
+@pytest.mark.parametrize("graph", [0, 1])
+def test_ema_matches_oracle(ub, setup, tmp_path, graph):
+    """EMA of the parameters fused into the AdamW kernel (guided-diffusion update_ema,
+    train_unet.py:708): after every step ema == rate * ema + (1 - rate) * params, fp32-exact on the parameters the CUDA
+    path itself produced; saved as a parameters-only checkpoint of the reference layout."""
+    O, cfg, flat = setup
+    B, rate = 2, 0.9
+    x0, t, noise = O.synthetic_batch(cfg, B)
+    tr = ub.Trainer(B=B, ema_rate=rate, use_cuda_graph=graph)
+    tr.set_params(flat.numpy())
+    np.testing.assert_array_equal(tr.get_ema(), flat.numpy())      # starts as a copy of the parameters
+    ema = flat.clone()
+    for _ in range(3):
+        tr.train_step(x0.numpy(), t.numpy(), noise.numpy(), lr=1e-3)
+        ema = O.ema_update(ema, torch.from_numpy(tr.get_params()), rate)
+        np.testing.assert_allclose(tr.get_ema(), ema.numpy(), rtol=0, atol=1e-6)
+    assert np.abs(tr.get_ema() - tr.get_params()).max() > 1e-4
+    path = str(tmp_path / "ema.bin")
+    tr.save_ema(path)
+    hdr, payload = O.read_model_bin(path)[:2]
+    assert int(hdr[0]) == O.MODEL_MAGIC and int(hdr[8]) == 0
+    np.testing.assert_array_equal(np.asarray(payload[:flat.numel()]), tr.get_ema())
+    tr.set_ema(flat.numpy())
+    np.testing.assert_array_equal(tr.get_ema(), flat.numpy())
+    tr.close()
+    plain = ub.Trainer(B=B)
+    with pytest.raises(ub.UbError):
+        plain.get_ema()
+    plain.close()

@@ -29,7 +29,8 @@ class UbConfig(C.Structure):
                 ("W", C.c_int), ("max_period", C.c_int), ("n_levels", C.c_int), ("channel_mult", C.c_int * 8),
                 ("n_res_blocks", C.c_int), ("att_start_level", C.c_int), ("head_size", C.c_int),
                 ("gn_n_groups", C.c_int), ("n_timesteps", C.c_int), ("seed", C.c_ulonglong),
-                ("use_cuda_graph", C.c_int), ("compute_dinput", C.c_int), ("random_flip", C.c_int)]
+                ("use_cuda_graph", C.c_int), ("compute_dinput", C.c_int), ("random_flip", C.c_int),
+                ("num_classes", C.c_int), ("ema_rate", C.c_float)]
 
 
 UB_KINDS = ("conv_igemm", "wgrad_igemm", "groupnorm", "attention", "eltwise", "small", "optimizer")
@@ -75,7 +76,9 @@ def _declare(L: C.CDLL) -> None:
     L.ub_trainer_load.argtypes = [vp, C.c_char_p]
     L.ub_trainer_save.argtypes = [vp, C.c_char_p, i]
     L.ub_read_checkpoint_header.argtypes = [C.c_char_p, C.POINTER(UbConfig)]
-    for n in ("set_params", "get_params", "get_grads", "get_output", "get_dinput"):
+    L.ub_trainer_save_ema.argtypes = [vp, C.c_char_p]
+    L.ub_trainer_set_labels.argtypes = [vp, vp, C.c_size_t]
+    for n in ("set_params", "get_params", "get_grads", "get_output", "get_dinput", "get_ema", "set_ema"):
         getattr(L, "ub_trainer_" + n).argtypes = [vp, fp, C.c_size_t]
     L.ub_trainer_forward_backward.argtypes = [vp, fp, fp, fp, C.POINTER(C.c_float)]
     L.ub_trainer_update.argtypes = [vp] + [C.c_float] * 5
@@ -171,6 +174,22 @@ class Trainer:
 
     def get_grads(self):
         return self._get(lib().ub_trainer_get_grads, self.nparams)
+
+    def get_ema(self):
+        """Moving average of the parameters (cfg.ema_rate > 0; guided-diffusion update_ema, train_unet.py:708)."""
+        return self._get(lib().ub_trainer_get_ema, self.nparams)
+
+    def set_ema(self, flat: np.ndarray):
+        flat = np.ascontiguousarray(flat, dtype=np.float32)
+        check(lib().ub_trainer_set_ema(self._h, _ptr(flat), flat.size), "set_ema")
+
+    def save_ema(self, path: str):
+        check(lib().ub_trainer_save_ema(self._h, path.encode()), "ub_trainer_save_ema")
+
+    def set_labels(self, y):
+        """Class labels of the batches that follow (cfg.num_classes > 0; `y` of UNetModel.forward, dev/unet.py:301-303)."""
+        y = np.ascontiguousarray(y, dtype=np.int32).reshape(-1)
+        check(lib().ub_trainer_set_labels(self._h, y.ctypes.data_as(C.c_void_p), y.size), "set_labels")
 
     def get_dinput(self):
         c = self.cfg

@@ -42,7 +42,59 @@ __global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, int C, int
         if (p < HW && c < C) y[(size_t(b) * HW + p) * C + c] = __float2bfloat16(tile[tx][i]);
     }
 }
+// The same conversion for HW % 4 == 0, C % 2 == 0 (every tensor-core shape): a block moves a 64-channel x 64-pixel tile.
+// Read side: every thread has four 16-byte loads in flight (two channels x 4 pixels, twice), 16 lanes cover 256
+// contiguous bytes of a channel row.  The pair (c, c+1) is rounded to bf16 and parked as one 32-bit word in a
+// [pixel][channel-pair] tile with an odd pitch (33 words: 2-way conflicts on the stores, none on the reads).  Write side:
+// a warp owns a pixel and stores its 64 channels as one 128-byte row -- the row the TMA boxes of the conv kernels read.
+// (The 32 x 32 kernel above moved 4 KiB per block with one 4-byte load per thread in flight and wrote 64-byte half rows:
+// 1.8 TB/s on a 100 MB tensor; this one is sized for the HBM roofline of 6 B per element.)
+__global__ void __launch_bounds__(256) nchw_to_nhwc_bf16_tile64_kernel(const float* __restrict__ x, int C, int HW,
+                                                                       __nv_bfloat16* __restrict__ y) {
+    __shared__ uint32_t tile[64][33];  // [pixel][channel pair]
+    const int b = blockIdx.z, p0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+    float4 v[2][2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int idx = threadIdx.x + 256 * k;  // 32 channel pairs x 16 pixel quads
+        const int cp = idx >> 4, q = idx & 15;
+        const int c = c0 + 2 * cp, p = p0 + 4 * q;
+        const bool ok = c < C && p < HW;        // (C even, HW % 4 == 0: a pair / quad is inside or outside as a whole)
+        const float* src = x + (size_t(b) * C + c) * HW + p;
+        v[k][0] = ok ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[k][1] = ok ? __ldg(reinterpret_cast<const float4*>(src + HW)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int idx = threadIdx.x + 256 * k;
+        const int cp = idx >> 4, q = idx & 15;
+        const float a[4] = {v[k][0].x, v[k][0].y, v[k][0].z, v[k][0].w};
+        const float d[4] = {v[k][1].x, v[k][1].y, v[k][1].z, v[k][1].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(a[j], d[j]);
+            tile[4 * q + j][cp] = *reinterpret_cast<const uint32_t*>(&h2);
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (c0 + 2 * lane < C) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int pl = warp + 8 * i;
+            if (p0 + pl < HW)
+                *reinterpret_cast<uint32_t*>(y + (size_t(b) * HW + p0 + pl) * C + c0 + 2 * lane) = tile[pl][lane];
+        }
+    }
+}
 void nchw_to_nhwc_bf16(const float* x, int B, int C, int HW, __nv_bfloat16* y, cudaStream_t st) {
+    static const bool old = getenv("UB_NCHW_CONVERT_OLD") != nullptr;  // (measurement switch)
+    if (!old && HW % 4 == 0 && C % 2 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(y) & 3) == 0) {
+        dim3 grid((HW + 63) / 64, (C + 63) / 64, B);
+        nchw_to_nhwc_bf16_tile64_kernel<<<grid, 256, 0, st>>>(x, C, HW, y);
+        return;
+    }
     dim3 grid((HW + 31) / 32, (C + 31) / 32, B);
     nchw_to_nhwc_bf16_kernel<<<grid, dim3(32, 8), 0, st>>>(x, C, HW, y);
 }

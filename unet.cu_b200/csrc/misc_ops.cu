@@ -471,7 +471,8 @@ __global__ void __launch_bounds__(512) time_mlp_fwd_kernel(const float* __restri
                                                            const float* __restrict__ w1, const float* __restrict__ b1,
                                                            float* __restrict__ sin_emb, float* __restrict__ h0,
                                                            float* __restrict__ emb, float* __restrict__ semb, int Cm,
-                                                           int Cemb) {
+                                                           int Cemb, const float* __restrict__ label_w,
+                                                           const int* __restrict__ labels) {
     pdl_entry();
     extern __shared__ float sm[];
     float* s_in = sm;        // [Cm]
@@ -501,7 +502,9 @@ __global__ void __launch_bounds__(512) time_mlp_fwd_kernel(const float* __restri
         float s[4];
         dot4_rows(s_h, w1 + size_t(o) * Cemb, Cemb, lane, s);
         if (lane < 4) {
-            const float v = s[lane] + b1[o + lane];
+            float v = s[lane] + b1[o + lane];
+            // class-conditional model: emb = time_embed(t) + label_emb[y]  (dev/unet.py:301-303)
+            if (label_w) v += label_w[size_t(labels[b]) * Cemb + o + lane];
             emb[size_t(b) * Cemb + o + lane] = v;
             semb[size_t(b) * Cemb + o + lane] = silu_f(v);
         }
@@ -509,9 +512,23 @@ __global__ void __launch_bounds__(512) time_mlp_fwd_kernel(const float* __restri
 }
 void time_mlp_fwd(const float* t, int B, int Cm, int Cemb, int max_period, const float* w0, const float* b0,
                   const float* w1, const float* b1, float* sin_emb, float* h0, float* emb, float* semb,
-                  cudaStream_t st) {
+                  cudaStream_t st, const float* label_w, const int* labels) {
     launch_pdl(time_mlp_fwd_kernel, dim3(B, kTimeMlpSplit), dim3(512), size_t(Cm + Cemb) * sizeof(float), st, t, Cm / 2,
-               logf(float(max_period)), w0, b0, w1, b1, sin_emb, h0, emb, semb, Cm, Cemb);
+               logf(float(max_period)), w0, b0, w1, b1, sin_emb, h0, emb, semb, Cm, Cemb, label_w, labels);
+}
+
+// d label_emb[y[b]][:] += demb[b][:]  (the backward of the embedding lookup: rows of equal labels add up, hence atomics;
+// the gradient arena is zero at the start of a step)
+__global__ void label_emb_bwd_kernel(const float* __restrict__ demb, const int* __restrict__ labels, int B, int Cemb,
+                                     float* __restrict__ dw) {
+    pdl_entry();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * Cemb) return;
+    const int b = i / Cemb, j = i - b * Cemb;
+    atomicAdd(dw + size_t(labels[b]) * Cemb + j, demb[i]);
+}
+void label_emb_bwd(const float* demb, const int* labels, int B, int Cemb, float* dw, cudaStream_t st) {
+    launch_pdl(label_emb_bwd_kernel, dim3((B * Cemb + 255) / 256), dim3(256), 0, st, demb, labels, B, Cemb, dw);
 }
 
 void timestep_embedding(const float* t, int B, int dim, int max_period, float* out, cudaStream_t st) {
@@ -685,7 +702,8 @@ void pack_weights(const PackEntry* table_dev, int n_entries, int max_tiles, cuda
 // =====================================================================================================
 __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, size_t n4, size_t n, float lr, float b1, float b2, float eps,
-                             float wd, float gscale, const int* __restrict__ step_dev, const float* __restrict__ hp) {
+                             float wd, float gscale, const int* __restrict__ step_dev, const float* __restrict__ hp,
+                             float* __restrict__ ema, float ema_rate) {
     pdl_entry();
     // hyper-parameters from device memory when given (the captured step graph: a learning-rate schedule must not force a
     // re-capture), {lr, beta1, beta2, eps, weight_decay}
@@ -710,6 +728,12 @@ __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float
         reinterpret_cast<float4*>(m)[i] = make_float4(mp[0], mp[1], mp[2], mp[3]);
         reinterpret_cast<float4*>(v)[i] = make_float4(vp[0], vp[1], vp[2], vp[3]);
         reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ema) {  // exponential moving average of the updated parameters: ema = rate * ema + (1 - rate) * p
+            const float4 ev = reinterpret_cast<float4*>(ema)[i];
+            reinterpret_cast<float4*>(ema)[i] =
+                make_float4(ema_rate * ev.x + (1.f - ema_rate) * pp[0], ema_rate * ev.y + (1.f - ema_rate) * pp[1],
+                            ema_rate * ev.z + (1.f - ema_rate) * pp[2], ema_rate * ev.w + (1.f - ema_rate) * pp[3]);
+        }
     } else if (i == n4) {  // tail (n % 4 elements)
         for (size_t k = n4 * 4; k < n; ++k) {
             const float gr = g[k] * gscale;
@@ -717,14 +741,16 @@ __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float
             v[k] = b2 * v[k] + (1.f - b2) * gr * gr;
             p[k] -= lr * ((m[k] / c1) / (sqrtf(v[k] / c2) + eps) + wd * p[k]);
             g[k] = 0.f;
+            if (ema) ema[k] = ema_rate * ema[k] + (1.f - ema_rate) * p[k];
         }
     }
 }
 void adamw_step(float* p, float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, float wd,
-                float grad_scale, const int* step_dev, cudaStream_t st, const float* hp_dev) {
+                float grad_scale, const int* step_dev, cudaStream_t st, const float* hp_dev, float* ema,
+                float ema_rate) {
     const size_t n4 = n / 4;
     launch_pdl(adamw_kernel, dim3(unsigned((n4 + 1 + 255) / 256)), dim3(256), 0, st, p, g, m, v, n4, n, lr, b1, b2, eps, wd, grad_scale,
-                                                                step_dev, hp_dev);
+                                                                step_dev, hp_dev, ema, ema_rate);
 }
 // ---- DDPM sampling
 __global__ void sample_set_t_kernel(const int* __restrict__ t_dev, int B, float* __restrict__ tsteps) {

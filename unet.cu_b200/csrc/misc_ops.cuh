@@ -42,7 +42,9 @@ void dsilu_mul(const float* dact, const float* pre, float* g, size_t n, cudaStre
 // timestep embedding (replaces get_timestep_embeddings, train_unet.cu:3258-3313): out[b][j]=cos(t f_j), [half+j]=sin
 void time_mlp_fwd(const float* t, int B, int Cm, int Cemb, int max_period, const float* w0, const float* b0,
                   const float* w1, const float* b1, float* sin_emb, float* h0, float* emb, float* semb,
-                  cudaStream_t st);
+                  cudaStream_t st, const float* label_w = nullptr, const int* labels = nullptr);
+// class-conditional model (dev/unet.py:174-175, 301-303): gradient of the label-embedding rows, dw[y[b]] += demb[b]
+void label_emb_bwd(const float* demb, const int* labels, int B, int Cemb, float* dw, cudaStream_t st);
 void timestep_embedding(const float* t, int B, int dim, int max_period, float* out, cudaStream_t st);
 
 // ---- diffusion: t ~ U{0..T-1}, eps ~ N(0,1) (Philox4x32-10, counter = element index, key = (seed, step)),
@@ -66,7 +68,8 @@ void pack_weights(const PackEntry* table_dev, int n_entries, int max_tiles, cuda
 // ---- AdamW (replaces adamw_kernel2 + unet_zero_grad, train_unet.cu:4706-4757): reads the step counter from
 //      device memory, applies grad_scale (1/world for data parallel), and zeroes the gradient.
 void adamw_step(float* p, float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, float wd,
-                float grad_scale, const int* step_dev, cudaStream_t st, const float* hp_dev = nullptr);
+                float grad_scale, const int* step_dev, cudaStream_t st, const float* hp_dev = nullptr,
+                float* ema = nullptr, float ema_rate = 0.f);  // ema: optional moving average of the parameters
 void increment_step(int* step_dev, cudaStream_t st);
 
 // ---- DDPM sampling step (generate.py:29-52).  t_dev holds the current t (2 <= t < T): fill t for the embedding,

@@ -131,6 +131,12 @@ struct UbTrainer {
     // flat fp32 arenas in reference order
     size_t nparams = 0;
     float *params = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr;
+    // cfg.ema_rate > 0: exponential moving average of the parameters, updated by the AdamW kernel (guided-diffusion's
+    // update_ema; train_unet.py:708 carries the option, the reference trainer ignores it); starts as a copy of params
+    float* ema = nullptr;
+    // cfg.num_classes > 0: class labels of the current batch (ub_trainer_set_labels) and the label-embedding table
+    int* labels = nullptr;
+    size_t label_w_off = 0;
     std::vector<ParamRef> tensors;  // every parameter tensor in order
     // everything else lives in one bump arena
     DeviceArena arena;
@@ -613,12 +619,14 @@ struct Builder {
         time_mlp_bwd_done = true;
         UbTrainer* Tt = T;
         const int Bn = B, Cm = c.C_model, Cemb = 4 * c.C_model;
+        const bool cls = c.num_classes > 0;
         Bk([=](cudaStream_t st) {
             dsilu_mul(Tt->d_embact, Tt->emb, Tt->demb, size_t(Bn) * Cemb, st);
+            if (cls) label_emb_bwd(Tt->demb, Tt->labels, Bn, Cemb, Tt->grads + Tt->label_w_off, st);
             small_linear_bwd(Tt->temb_table + 1, 1, Bn, Cemb, Cemb, st);
             dsilu_mul(Tt->d_h0act, Tt->h0, Tt->dh0, size_t(Bn) * Cemb, st);
             small_linear_bwd(Tt->temb_table, 1, Bn, Cemb, Cm, st);
-        }, 6, UB_KIND_SMALL, 0, 0, tail_aux() ? 3 : 1);  // 3: a branch of its own, forked from the weight-gradient branch
+        }, cls ? 7 : 6, UB_KIND_SMALL, 0, 0, tail_aux() ? 3 : 1);  // 3: a branch of its own, forked from the weight-gradient branch
     }
 
     // ResBlock (dev/resblock.py:107-160, train_unet.cu:2213-2384)
@@ -815,6 +823,7 @@ int Builder::build() {
     // io + small fp32 state
     T->x0 = f32(size_t(B) * img), T->xt = f32(size_t(B) * img), T->noise = f32(size_t(B) * img);
     T->tsteps = f32(B);
+    T->labels = c.num_classes > 0 ? (int*)T->arena.alloc(size_t(B) * sizeof(int) + 256) : nullptr;
     T->dxt = c.compute_dinput ? f32(size_t(B) * img) : nullptr;
     T->flips = c.random_flip ? (int*)T->arena.alloc(size_t(B) * sizeof(int) + 256) : nullptr;
     T->out = f32(size_t(B) * c.C_out * H0 * W0), T->dout = f32(size_t(B) * c.C_out * H0 * W0);
@@ -844,12 +853,18 @@ int Builder::build() {
         e1.dout = T->demb, e1.dw = G(tw1), e1.db = G(tb1), e1.dinp = T->d_h0act;
         T->h_temb = {e0, e1};
     }
+    // class-conditional model: label_emb.weight (num_classes, 4*C_model) follows the time MLP in named_parameters()
+    // order (dev/unet.py:174-175); emb = time_embed(t) + label_emb[y] (dev/unet.py:301-303)
+    const size_t lw = c.num_classes > 0 ? take(size_t(c.num_classes) * Cemb) : 0;
+    if (real()) T->label_w_off = lw;
     {
         const int mp = c.max_period;
+        const bool cls = c.num_classes > 0;
         F([=](cudaStream_t st) {
             const SmallLinear &e0 = Tt->h_temb[0], &e1 = Tt->h_temb[1];
             time_mlp_fwd(Tt->tsteps, Bn, Cm, Cemb, mp, e0.w, e0.b, e1.w, e1.b, Tt->sin_emb, Tt->h0, Tt->emb, Tt->semb,
-                         st);  // (semb = silu(emb) is the shared input of all embedding projections)
+                         st, cls ? Tt->params + Tt->label_w_off : nullptr,
+                         Tt->labels);  // (semb = silu(emb) is the shared input of all embedding projections)
             small_linear_fwd(Tt->emb_table, int(Tt->h_emb.size()), Bn, Tt->emb_max_oc, st, true);  // (Cout % 16 == 0)
         }, 2, UB_KIND_SMALL, 0, 0, 1);  // beside the input conv and the first GroupNorm
         fwd_side_pending = true;
@@ -1083,7 +1098,8 @@ int Builder::build() {
                 os = Tt->opt_stream, Tt->opt_stream_dirty = true;
             }
             adamw_step(Tt->params + lo, Tt->grads + lo, Tt->m + lo, Tt->v + lo, hi - lo, Tt->o_lr, Tt->o_b1, Tt->o_b2,
-                       Tt->o_eps, Tt->o_wd, 1.f / float(Tt->world), Tt->step_dev, os, Tt->hp_active);
+                       Tt->o_eps, Tt->o_wd, 1.f / float(Tt->world), Tt->step_dev, os, Tt->hp_active,
+                       Tt->ema ? Tt->ema + lo : nullptr, Tt->cfg.ema_rate);
             if (pk_count) pack_weights(Tt->pack_table + pk_first, pk_count, pk_tiles, os);
             Tt->opt_done_lo = lo;
         }, 0, UB_KIND_OPTIM, 0, 0, 1);
@@ -1176,6 +1192,10 @@ static int validate_config(const UbConfig& c) {
         set_err("H, W must be divisible by 2^(n_levels-1)");
         return UB_ERR_SHAPE;
     }
+    if (c.num_classes < 0 || !(c.ema_rate >= 0.f && c.ema_rate < 1.f)) {
+        set_err("bad config: num_classes must be >= 0 and ema_rate in [0, 1)");
+        return UB_ERR_SHAPE;
+    }
     if (c.random_flip && c.W % 4) {
         set_err("random_flip needs W %% 4 == 0");
         return UB_ERR_SHAPE;
@@ -1265,6 +1285,15 @@ extern "C" int ub_trainer_create(UbTrainer** out, const UbConfig* cfg, int devic
     t->zarena.base = blob + 4 * pbytes + arena_bytes, t->zarena.cap = zero_bytes, t->zarena.off = 0,
     t->zarena.counting = false;
     t->zero_base = t->zarena.base, t->zero_bytes = zero_bytes;
+    if (cfg->ema_rate > 0.f) {
+        if (cudaMalloc(&t->ema, pbytes) != cudaSuccess) {
+            set_err("cudaMalloc of the moving-average arena (%zu MiB) failed", pbytes >> 20);
+            t->ema = nullptr;
+            ub_trainer_destroy(t);
+            return UB_ERR_CUDA;
+        }
+        cudaMemset(t->ema, 0, pbytes);
+    }
     // the main stream carries the critical path (forward, dgrad chain): highest priority; the weight-gradient branch
     // and the collectives fill the gaps (stream priorities become kernel-node priorities in the captured graph)
     int prio_lo = 0, prio_hi = 0;
@@ -1346,6 +1375,7 @@ extern "C" void ub_trainer_destroy(UbTrainer* t) {
     if (t->samp_graph) cudaGraphExecDestroy(t->samp_graph);
     if (t->comm && nccl().ok) nccl().CommDestroy(t->comm);
     if (t->params) cudaFree(t->params);
+    if (t->ema) cudaFree(t->ema);
     for (int k = 0; k < 2; ++k) {
         if (t->hs_x0[k]) cudaFreeHost(t->hs_x0[k]);
         if (t->hs_noise[k]) cudaFreeHost(t->hs_noise[k]);
@@ -1484,7 +1514,7 @@ static void enqueue_step(UbTrainer* t, const StepOpts& o, cudaStream_t st) {
         // the buckets the tape already updated are [opt_done_lo, nparams); the rest (the last bucket) is updated here
         const size_t n_left = t->opt_done_lo;
         adamw_step(t->params, t->grads, t->m, t->v, n_left, o.lr, o.b1, o.b2, o.eps, o.wd, 1.f / float(t->world),
-                   t->step_dev, st, t->hp_active);
+                   t->step_dev, st, t->hp_active, t->ema, t->cfg.ema_rate);
         int cnt = 0, tiles = 0;
         while (cnt < t->n_pack && t->pack_off[cnt] < n_left) {
             tiles = std::max(tiles, ((t->h_pack[cnt].Cout + 31) / 32) * ((t->h_pack[cnt].Cin + 31) / 32));
@@ -1566,7 +1596,7 @@ extern "C" int ub_trainer_update(UbTrainer* t, float lr, float beta1, float beta
         return UB_ERR_STATE;
     }
     adamw_step(t->params, t->grads, t->m, t->v, t->nparams, lr, beta1, beta2, eps, weight_decay,
-               1.f / float(t->world), t->step_dev, t->stream);
+               1.f / float(t->world), t->step_dev, t->stream, nullptr, t->ema, t->cfg.ema_rate);
     run_pack(t, t->stream);
     increment_step(t->step_dev, t->stream);
     t->have_grads = false;
@@ -1701,7 +1731,7 @@ extern "C" int ub_trainer_profile(UbTrainer* t, int reps, UbProfile* out) {
             cudaEventRecord(ev[k++], st);
         }
         adamw_step(t->params, t->grads, t->m, t->v, t->nparams, t->g_lr > 0 ? t->g_lr : 1e-4f, 0.9f, 0.999f, 1e-8f, 0.f,
-                   1.f / float(t->world), t->step_dev, st);
+                   1.f / float(t->world), t->step_dev, st);  // (no moving-average update: it is not snapshotted)
         run_pack(t, st);
         increment_step(t->step_dev, st);
         cudaEventRecord(ev[k++], st);
@@ -1871,12 +1901,54 @@ extern "C" int ub_trainer_set_params(UbTrainer* t, const float* host, size_t n) 
     CUDA_TRY(cudaSetDevice(t->device));
     CUDA_TRY(cudaStreamSynchronize(t->stream));
     CUDA_TRY(cudaMemcpy(t->params, host, n * sizeof(float), cudaMemcpyHostToDevice));
+    if (t->ema) CUDA_TRY(cudaMemcpy(t->ema, t->params, n * sizeof(float), cudaMemcpyDeviceToDevice));
     ensure_packed(t);
     CUDA_TRY(cudaStreamSynchronize(t->stream));
     return UB_OK;
 }
 extern "C" int ub_trainer_get_params(UbTrainer* t, float* host, size_t n) {
     return copy_out(t, t->params, host, n, t->nparams);
+}
+extern "C" int ub_trainer_get_ema(UbTrainer* t, float* host, size_t n) {
+    if (!t->ema) {
+        set_err("no moving average: the trainer was created with cfg.ema_rate = 0");
+        return UB_ERR_STATE;
+    }
+    return copy_out(t, t->ema, host, n, t->nparams);
+}
+extern "C" int ub_trainer_set_ema(UbTrainer* t, const float* host, size_t n) {
+    if (!t->ema) {
+        set_err("no moving average: the trainer was created with cfg.ema_rate = 0");
+        return UB_ERR_STATE;
+    }
+    if (n != t->nparams) {
+        set_err("size mismatch: got %zu expected %zu", n, t->nparams);
+        return UB_ERR_SHAPE;
+    }
+    CUDA_TRY(cudaSetDevice(t->device));
+    CUDA_TRY(cudaStreamSynchronize(t->stream));
+    CUDA_TRY(cudaMemcpy(t->ema, host, n * sizeof(float), cudaMemcpyHostToDevice));
+    return UB_OK;
+}
+extern "C" int ub_trainer_set_labels(UbTrainer* t, const int* labels_host, size_t n) {
+    if (!t->labels) {
+        set_err("not a class-conditional model: the trainer was created with cfg.num_classes = 0");
+        return UB_ERR_STATE;
+    }
+    if (n != size_t(t->cfg.B)) {
+        set_err("size mismatch: got %zu labels, batch is %d", n, t->cfg.B);
+        return UB_ERR_SHAPE;
+    }
+    for (size_t i = 0; i < n; ++i)
+        if (labels_host[i] < 0 || labels_host[i] >= t->cfg.num_classes) {
+            set_err("label %d of image %zu outside [0, %d)", labels_host[i], i, t->cfg.num_classes);
+            return UB_ERR_SHAPE;
+        }
+    CUDA_TRY(cudaSetDevice(t->device));
+    // the captured step reads the labels from this fixed buffer: wait for the steps in flight, then overwrite it
+    CUDA_TRY(cudaStreamSynchronize(t->stream));
+    CUDA_TRY(cudaMemcpy(t->labels, labels_host, n * sizeof(int), cudaMemcpyHostToDevice));
+    return UB_OK;
 }
 extern "C" int ub_trainer_get_grads(UbTrainer* t, float* host, size_t n) {
     return copy_out(t, t->grads, host, n, t->nparams);
@@ -1977,6 +2049,8 @@ extern "C" int ub_trainer_load(UbTrainer* t, const char* path) {
         set_err("%s: truncated checkpoint", path);
         return r;
     }
+    // the moving average restarts from the loaded weights (ub_trainer_set_ema restores a saved one)
+    if (t->ema) CUDA_TRY(cudaMemcpy(t->ema, t->params, t->nparams * sizeof(float), cudaMemcpyDeviceToDevice));
     ensure_packed(t);
     CUDA_TRY(cudaStreamSynchronize(t->stream));
     return UB_OK;
@@ -1994,7 +2068,7 @@ extern "C" int ub_trainer_set_step(UbTrainer* t, int step) {
     return UB_OK;
 }
 
-extern "C" int ub_trainer_save(UbTrainer* t, const char* path, int with_adamw) {
+static int save_checkpoint(UbTrainer* t, const char* path, const float* weights, int with_adamw) {
     CUDA_TRY(cudaSetDevice(t->device));
     CUDA_TRY(cudaStreamSynchronize(t->stream));
     FILE* f = fopen(path, "wb");
@@ -2016,7 +2090,7 @@ extern "C" int ub_trainer_save(UbTrainer* t, const char* path, int with_adamw) {
         ok = ok && cudaMemcpy(buf.data(), dev, t->nparams * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess;
         ok = ok && fwrite(buf.data(), sizeof(float), t->nparams, f) == t->nparams;
     };
-    write_arena(t->params);
+    write_arena(weights);
     if (with_adamw) write_arena(t->m), write_arena(t->v);
     fclose(f);
     if (!ok) {
@@ -2024,6 +2098,18 @@ extern "C" int ub_trainer_save(UbTrainer* t, const char* path, int with_adamw) {
         return UB_ERR_IO;
     }
     return UB_OK;
+}
+extern "C" int ub_trainer_save(UbTrainer* t, const char* path, int with_adamw) {
+    return save_checkpoint(t, path, t->params, with_adamw);
+}
+// The moving-average weights as a parameters-only checkpoint of the same layout: what generate.py (or
+// ub_trainer_load + ub_trainer_sample) samples from in guided-diffusion practice.
+extern "C" int ub_trainer_save_ema(UbTrainer* t, const char* path) {
+    if (!t->ema) {
+        set_err("no moving average: the trainer was created with cfg.ema_rate = 0");
+        return UB_ERR_STATE;
+    }
+    return save_checkpoint(t, path, t->ema, 0);
 }
 
 // ======================================================================================================
