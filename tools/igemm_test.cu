@@ -456,6 +456,11 @@ int main(int argc, char** argv) {
         test_conv(B, H, W, Cin, Cout, 9, 0, OUT_NHWC_BF16, true, true, false, 2000, atoi(argv[8]), atoi(argv[7]) != 0);
         return g_fail ? 1 : 0;
     }
+    if (argc > 9 && !strcmp(argv[1], "conv")) {  // conv B H W Cin Cout ntaps rows reps  (single timed case, no hooks / addends)
+        test_conv(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), 0,
+                  OUT_NHWC_BF16, false, false, false, 2000, atoi(argv[9]), atoi(argv[8]) != 0);
+        return g_fail ? 1 : 0;
+    }
     if (argc > 7 && !strcmp(argv[1], "wgrad")) {  // wgrad B H W Cin Cout reps
         test_wgrad(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), 9, 200, atoi(argv[7]));
         return g_fail ? 1 : 0;

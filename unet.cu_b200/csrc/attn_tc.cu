@@ -145,6 +145,8 @@ __global__ void __launch_bounds__(kThreads) attn_tc_fwd_kernel(const __grid_cons
     const int C = p.NH * HS;
     const uint32_t tm_cols = t.ncols > 128 ? 512 : 256;
     const uint32_t o_col = t.ncols;  // O accumulator behind the scores
+    // head split (AttnTcParams::hsplit): gridDim.z == 2 and the CTA works on ONE head of its pair
+    const int h_lo = gridDim.z == 2 ? int(blockIdx.z) : 0, h_hi = gridDim.z == 2 ? int(blockIdx.z) + 1 : 2;
     prologue(sm, tm_cols, warp, lane);
     const uint32_t tmem = sm->tmem_slot;
 
@@ -168,7 +170,7 @@ __global__ void __launch_bounds__(kThreads) attn_tc_fwd_kernel(const __grid_cons
             const uint32_t id_o = make_idesc_bf16(128, 64, 0, 1);
             const uint64_t dQ = make_smem_desc_sw128(smem_u32(sQ), 16, 1024), dK = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
             const uint64_t dP = make_smem_desc_sw128(smem_u32(sP), 16, 1024), dV = make_smem_desc_sw128(smem_u32(sV), 8192, 1024);
-            for (int h = 0; h < 2; ++h) {
+            for (int h = h_lo; h < h_hi; ++h) {
                 if (elect_one_sync()) {
 #pragma unroll
                     for (int k = 0; k < 2; ++k)
@@ -176,13 +178,14 @@ __global__ void __launch_bounds__(kThreads) attn_tc_fwd_kernel(const __grid_cons
                     umma_commit(&sm->bar_s);
                 }
                 __syncwarp();
-                mbar_wait(&sm->bar_p, h);
+                mbar_wait(&sm->bar_p, h - h_lo);
                 tc_fence_after();
                 if (elect_one_sync()) {
 #pragma unroll 4
                     for (int j = 0; j < t.ncols / 16; ++j)
                         umma_bf16(tmem + o_col, dP + uint64_t((j >> 2) * 1024 + (j & 3) * 2), dV + uint64_t(j * 128), id_o, j);
-                    // (the row threads drain O_0 before they arrive on bar_p for head 1, so PV of head 1 may reuse it)
+                    // (the row threads drain O of the first head before they arrive on bar_p for the second, so its PV may
+                    //  reuse the columns)
                     umma_commit(&sm->bar_o);
                 }
                 __syncwarp();
@@ -195,8 +198,8 @@ __global__ void __launch_bounds__(kThreads) attn_tc_fwd_kernel(const __grid_cons
         const bool rvalid = gr < p.B * p.T;
         const uint32_t trow = tmem + (uint32_t(q * 32) << 16);
         const float c = rsqrtf(float(HS)) * kLog2e;
-        for (int h = 0; h < 2; ++h) {
-            mbar_wait(&sm->bar_s, h);
+        for (int h = h_lo; h < h_hi; ++h) {
+            mbar_wait(&sm->bar_s, h - h_lo);
             tc_fence_after();
             float m = -1e30f;
             for (int c0 = 32 * half; c0 < t.ncols; c0 += 64) {
@@ -231,8 +234,8 @@ __global__ void __launch_bounds__(kThreads) attn_tc_fwd_kernel(const __grid_cons
             fence_async_smem();
             tc_fence_before();
             mbar_arrive(&sm->bar_p);
-            mbar_wait(&sm->bar_o, h);
-            if (h == 1) pdl_trigger_late();  // all MMAs of this CTA are complete
+            mbar_wait(&sm->bar_o, h - h_lo);
+            if (h == h_hi - 1) pdl_trigger_late();  // all MMAs of this CTA are complete
             tc_fence_after();
             l += sl[(h * 2 + (half ^ 1)) * 128 + r];  // (ordered by the bar_p arrive / bar_o wait pair)
             uint32_t o[16];
@@ -278,6 +281,7 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dq_kernel(const __grid_const
     Smem* sm = reinterpret_cast<Smem*>(sdS + 32768);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int C = p.NH * HS;
+    const int h_lo = gridDim.z == 2 ? int(blockIdx.z) : 0, h_hi = gridDim.z == 2 ? int(blockIdx.z) + 1 : 2;  // head split
     prologue(sm, 512, warp, lane);
     const uint32_t tmem = sm->tmem_slot;
     const int nchunk = t.ncols / 128;
@@ -305,7 +309,7 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dq_kernel(const __grid_const
             const uint64_t dK = make_smem_desc_sw128(smem_u32(sK), 16, 1024), dV = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
             const uint64_t dS = make_smem_desc_sw128(smem_u32(sdS), 16, 1024), dKm = make_smem_desc_sw128(smem_u32(sK), 8192, 1024);
             int it = 0;
-            for (int h = 0; h < 2; ++h) {
+            for (int h = h_lo; h < h_hi; ++h) {
                 for (int cc = 0; cc < nchunk; ++cc, ++it) {
                     if (elect_one_sync()) {
 #pragma unroll
@@ -344,6 +348,7 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dq_kernel(const __grid_const
         if (rvalid) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
+                if (h < h_lo || h >= h_hi) continue;
                 const int head = t.hp * 2 + h;
                 const uint4* gp = reinterpret_cast<const uint4*>(p.dout + size_t(gr) * p.lddo + head * HS);
                 const uint4* op = reinterpret_cast<const uint4*>(p.out + size_t(gr) * p.ldo + head * HS);
@@ -362,7 +367,7 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dq_kernel(const __grid_const
             }
         }
         int it = 0;
-        for (int h = 0; h < 2; ++h) {
+        for (int h = h_lo; h < h_hi; ++h) {
             for (int cc = 0; cc < nchunk; ++cc, ++it) {
                 mbar_wait(&sm->bar_s, it & 1);
                 tc_fence_after();
@@ -387,7 +392,7 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dq_kernel(const __grid_const
             }
             // dQ of this head is complete when the last chunk's MMAs are
             mbar_wait(&sm->bar_o, (it - 1) & 1);
-            if (h == 1) pdl_trigger_late();  // all MMAs of this CTA are complete
+            if (h == h_hi - 1) pdl_trigger_late();  // all MMAs of this CTA are complete
             tc_fence_after();
             uint32_t o[16];
             tmem_ld16(trow + 256 + h * 64 + h * 32 + half * 16, o);
@@ -429,6 +434,7 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dkv_kernel(const __grid_cons
     Smem* sm = reinterpret_cast<Smem*>(sD + 2 * 256);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int C = p.NH * HS;
+    const int h_lo = gridDim.z == 2 ? int(blockIdx.z) : 0, h_hi = gridDim.z == 2 ? int(blockIdx.z) + 1 : 2;  // head split
     prologue(sm, 512, warp, lane);
     const uint32_t tmem = sm->tmem_slot;
     const int nchunk = t.ncols / 128;
@@ -457,7 +463,7 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dkv_kernel(const __grid_cons
             const uint64_t dPt = make_smem_desc_sw128(smem_u32(sPt), 16, 1024), dSt = make_smem_desc_sw128(smem_u32(sdSt), 16, 1024);
             const uint64_t dQm = make_smem_desc_sw128(smem_u32(sQ), 8192, 1024), dGm = make_smem_desc_sw128(smem_u32(sdO), 8192, 1024);
             int it = 0;
-            for (int h = 0; h < 2; ++h) {
+            for (int h = h_lo; h < h_hi; ++h) {
                 for (int cc = 0; cc < nchunk; ++cc, ++it) {
                     if (elect_one_sync()) {
 #pragma unroll
@@ -518,7 +524,7 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dkv_kernel(const __grid_cons
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         int it = 0;
-        for (int h = 0; h < 2; ++h) {
+        for (int h = h_lo; h < h_hi; ++h) {
             for (int cc = 0; cc < nchunk; ++cc, ++it) {
                 mbar_wait(&sm->bar_s, it & 1);
                 tc_fence_after();
@@ -547,7 +553,7 @@ __global__ void __launch_bounds__(kThreads) attn_tc_dkv_kernel(const __grid_cons
                 mbar_arrive(&sm->bar_p);
             }
             mbar_wait(&sm->bar_o, (it - 1) & 1);
-            if (h == 1) pdl_trigger_late();  // all MMAs of this CTA are complete
+            if (h == h_hi - 1) pdl_trigger_late();  // all MMAs of this CTA are complete
             tc_fence_after();
             uint32_t dk[16], dv[16];
             tmem_ld16(trow + 256 + h * 64 + h * 32 + half * 16, dk);
@@ -633,15 +639,25 @@ int attn_tc_plan(AttnTcParams* p, const __nv_bfloat16* qkv, int ld, int B, int T
     return r;
 }
 
-static dim3 attn_grid(const AttnTcParams& p) { return dim3((p.B * p.T + 127) / 128, p.NH / 2); }
+// Head split (UB_ATTN_HSPLIT bit mask: 1 forward, 2 dq, 4 dkv; default 1): a CTA owns 128 rows x a PAIR of heads (one
+// 64-channel box) and works through the two heads one after the other; with the split the pair is shared by two CTAs
+// (grid z) that each load the box and take one head.  T = 256: 192 one-per-SM CTAs are two waves on 148 SMs, 384 half
+// CTAs are three half-waves; T = 64: 64 CTAs become 128.
+static int attn_hsplit() {
+    static const int v = getenv("UB_ATTN_HSPLIT") ? atoi(getenv("UB_ATTN_HSPLIT")) : 1;
+    return v;
+}
+static dim3 attn_grid(const AttnTcParams& p, int bit) {
+    return dim3((p.B * p.T + 127) / 128, p.NH / 2, (attn_hsplit() & bit) ? 2 : 1);
+}
 static int attn_ncols(const AttnTcParams& p) { return p.T >= 128 ? p.T : 128; }
 
 int attn_tc_fwd(const AttnTcParams& p, cudaStream_t st) {
     attn_tc_init();
     if (p.T >= 128)
-        launch_pdl(attn_tc_fwd_kernel<false>, dim3(attn_grid(p)), dim3(kThreads), smem_fwd(attn_ncols(p)), st, p);
+        launch_pdl(attn_tc_fwd_kernel<false>, dim3(attn_grid(p, 1)), dim3(kThreads), smem_fwd(attn_ncols(p)), st, p);
     else
-        launch_pdl(attn_tc_fwd_kernel<true>, dim3(attn_grid(p)), dim3(kThreads), smem_fwd(attn_ncols(p)), st, p);
+        launch_pdl(attn_tc_fwd_kernel<true>, dim3(attn_grid(p, 1)), dim3(kThreads), smem_fwd(attn_ncols(p)), st, p);
     return int(cudaGetLastError());
 }
 
@@ -657,11 +673,11 @@ int attn_tc_bwd(const AttnTcParams& p, cudaStream_t st, cudaStream_t aux, cudaEv
         s2 = aux;
     }
     if (p.T >= 128) {
-        launch_pdl(attn_tc_dkv_kernel<false>, dim3(attn_grid(p)), dim3(kThreads), smem_dkv(attn_ncols(p)), s2, p);
-        launch_pdl(attn_tc_dq_kernel<false>, dim3(attn_grid(p)), dim3(kThreads), smem_dq(attn_ncols(p)), st, p);
+        launch_pdl(attn_tc_dkv_kernel<false>, dim3(attn_grid(p, 4)), dim3(kThreads), smem_dkv(attn_ncols(p)), s2, p);
+        launch_pdl(attn_tc_dq_kernel<false>, dim3(attn_grid(p, 2)), dim3(kThreads), smem_dq(attn_ncols(p)), st, p);
     } else {
-        launch_pdl(attn_tc_dkv_kernel<true>, dim3(attn_grid(p)), dim3(kThreads), smem_dkv(attn_ncols(p)), s2, p);
-        launch_pdl(attn_tc_dq_kernel<true>, dim3(attn_grid(p)), dim3(kThreads), smem_dq(attn_ncols(p)), st, p);
+        launch_pdl(attn_tc_dkv_kernel<true>, dim3(attn_grid(p, 4)), dim3(kThreads), smem_dkv(attn_ncols(p)), s2, p);
+        launch_pdl(attn_tc_dq_kernel<true>, dim3(attn_grid(p, 2)), dim3(kThreads), smem_dq(attn_ncols(p)), st, p);
     }
     if (s2 != st) {
         cudaEventRecord(ev_join, s2);

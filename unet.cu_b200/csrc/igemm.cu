@@ -347,12 +347,17 @@ __device__ __forceinline__ void igemm_conv_body(const IgemmConvParams& p) {
             if (p.ms) {
                 done_ms = true;
                 // ---- statistics on the tensor core (see IgemmConvParams::ms).  The pipeline stages are dead.
+                // ms == 2: no statistics, only the staged tile + TMA store (plain convs: the per-thread 16-byte stores
+                // of a pixel-per-thread epilogue hit 32 different lines per instruction -- 8.6 B/clk/SM measured on the
+                // 1x1 skip-conv dgrads of the 64x64 level, whose epilogue is all they do)
+                const bool stat = p.ms == 1;
                 uint64_t* stat_bar = tmem_full_bar + 2;
                 const int atoms = p.BN / 64;
                 const uint32_t ys = smem_u32(smem), y2s = ys + uint32_t(atoms) * 16384u;
                 const uint32_t ones_s = ys + 2u * uint32_t(atoms) * 16384u;
-                for (int i = et; i < 1024; i += kEpiThreads)  // 128 pixel rows x 128 B of bf16 1.0
-                    sts_v4_b32(ones_s + 16u * i, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+                if (stat)
+                    for (int i = et; i < 1024; i += kEpiThreads)  // 128 pixel rows x 128 B of bf16 1.0
+                        sts_v4_b32(ones_s + 16u * i, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
                 const float* cmb = comb + (p.ncomb > 1 ? min(lb, p.ncomb - 1) : 0) * p.BN;
                 const uint32_t rowoff = uint32_t(row >> 3) * 1024u + uint32_t(row & 7) * 128u;
                 for (int c0 = 16 * half; c0 < p.BN; c0 += 32) {
@@ -390,8 +395,10 @@ __device__ __forceinline__ void igemm_conv_body(const IgemmConvParams& p) {
                     const uint32_t ch = uint32_t((c0 & 63) >> 3), sw = uint32_t(row & 7);
                     sts_v4_b32(ys + abase + ((ch ^ sw) << 4), py[0], py[1], py[2], py[3]);
                     sts_v4_b32(ys + abase + (((ch + 1) ^ sw) << 4), py[4], py[5], py[6], py[7]);
-                    sts_v4_b32(y2s + abase + ((ch ^ sw) << 4), pq[0], pq[1], pq[2], pq[3]);
-                    sts_v4_b32(y2s + abase + (((ch + 1) ^ sw) << 4), pq[4], pq[5], pq[6], pq[7]);
+                    if (stat) {
+                        sts_v4_b32(y2s + abase + ((ch ^ sw) << 4), pq[0], pq[1], pq[2], pq[3]);
+                        sts_v4_b32(y2s + abase + (((ch + 1) ^ sw) << 4), pq[4], pq[5], pq[6], pq[7]);
+                    }
                 }
                 fence_proxy_async_smem();
                 tc_fence_before();
@@ -401,6 +408,7 @@ __device__ __forceinline__ void igemm_conv_body(const IgemmConvParams& p) {
                     tc_fence_after();
                     for (int a = 0; a < atoms; ++a) tma_store_4d(smem + size_t(a) * 16384, &p.tmO, n0 + a * 64, w0, h0, b0);
                     bulk_commit_group();
+                  if (stat) {
                     const uint32_t idesc = make_idesc_bf16(uint32_t(p.BN), 16, 1, 1);
                     const uint64_t dbase = make_smem_desc_sw128(0, 16384, 1024);  // LBO = 64-channel atom, SBO = 8 rows
                     const uint64_t dY = dbase | uint64_t((ys >> 4) & 0x3FFF), dY2 = dbase | uint64_t((y2s >> 4) & 0x3FFF);
@@ -413,7 +421,9 @@ __device__ __forceinline__ void igemm_conv_body(const IgemmConvParams& p) {
                             umma_bf16(t_stat + uint32_t(img * 32 + 16), dY2 + ko, dO + ko, idesc, k != 0);
                         }
                     umma_commit(stat_bar);
+                  }
                 }
+                if (stat) {
                 mbar_wait(stat_bar, 0);
                 tc_fence_after();
                 if (half == 0) {
@@ -433,6 +443,7 @@ __device__ __forceinline__ void igemm_conv_body(const IgemmConvParams& p) {
                         }
                     }
                 }
+                }  // stat
                 if (threadIdx.x == 64) bulk_wait_group0();  // the Y tile has left shared memory
             }
         }
@@ -851,7 +862,8 @@ int igemm_conv_plan(IgemmConvParams* p, const ConvSegDesc* segs, int nseg, int B
     for (int cand = 256; cand >= 16; cand -= 16)
         if (Cout % cand == 0 && (!gn_hook || cand % 32 == 0)) {
             if (!BN) BN = cand;
-            if (cand < 64) break;
+            static const int min_bn = getenv("UB_CONV_MIN_BN") ? atoi(getenv("UB_CONV_MIN_BN")) : 64;
+            if (cand < min_bn) break;
             BN = cand;
             if (pix_tiles * (Cout / cand) >= 128) break;
         }
@@ -994,6 +1006,15 @@ int igemm_conv_plan(IgemmConvParams* p, const ConvSegDesc* segs, int nseg, int B
             p->ms = 1;
             p->tmem_cols = next_pow2(p->nacc * BN + 64);
         }
+        // ms == 2, store-only: a conv without any hook whose output is an NHWC bf16 tensor leaves through the same staged
+        // tile + TMA store (any whole-tile shape, N tiles of 64 .. 256 channels); UB_EPI_TMA_STORE=0 keeps the
+        // per-thread stores
+        static const bool want_st = !(getenv("UB_EPI_TMA_STORE") && atoi(getenv("UB_EPI_TMA_STORE")) == 0);
+        if (want_ms && want_st && !p->ms && !gn_hook && !p->gnf_cluster && p->out_mode == OUT_NHWC_BF16 && BN % 64 == 0 &&
+            p->nacc <= 2 && full_tiles && size_t(BN / 64) * 16384 <= size_t(p->stages) * p->stage_bytes &&
+            make_act_map(&p->tmO, reinterpret_cast<const __nv_bfloat16*>(ep.out), Cout, p->ldo, W, H, B, p->TW, p->TH,
+                         p->TB) == 0)
+            p->ms = 2;
     }
     if (size_t(p->ncomb + 4 * p->ngimg + p->nred + ngnf) * BN * sizeof(float) > 24576) return -9;  // smem tail budget
     if (size_t(p->stages) * p->stage_bytes + 1024 + kBarrierBytes +

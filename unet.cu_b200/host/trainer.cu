@@ -372,7 +372,12 @@ struct Builder {
         // UB_ROWS=0 / 2 forces never / always.
         static const int rows_mode = getenv("UB_ROWS") ? atoi(getenv("UB_ROWS")) : 1;
         const bool rows_pref = (W >= 64 && (Cout <= 64 || Cout >= 192)) || (W >= 32 && Cout >= 192 && segs[0].ntaps == 9);
-        const bool no_rows = rows_mode == 0 || (rows_mode == 1 && !rows_pref);
+        // A one-tap conv without a hook (the 1x1 skip-conv dgrads) is all epilogue.  Measured (profiles/r02_plain_1x1.txt):
+        // the row-tile kernel stays ahead of the basic kernel there even with the latter's staged tile + TMA store
+        // (64 -> 192 at 64x64: 30.6 vs 39.7 us), so the rule above stands; UB_PLAIN_1X1_BASIC=1 routes them to the basic kernel.
+        static const bool plain_basic = getenv("UB_PLAIN_1X1_BASIC") && atoi(getenv("UB_PLAIN_1X1_BASIC")) != 0;
+        const bool plain_1x1 = segs.size() == 1 && segs[0].ntaps == 1 && !ep.stats && !ep.gn_x && plain_basic;
+        const bool no_rows = rows_mode == 0 || (rows_mode == 1 && (!rows_pref || plain_1x1));
         double k = 0, bytes = act_bytes(Cout, H, W);
         for (auto& sg : segs) k += double(sg.ntaps) * sg.Cin, bytes += act_bytes(sg.Cin, H, W) + 2.0 * sg.ntaps * sg.Cin * Cout;
         const double flops = 2.0 * B * H * W * Cout * k;
@@ -413,9 +418,9 @@ struct Builder {
                 }
                 if (nh == 1 && p.gnf_cluster && (ep.stats || ep.gn_x)) gn_finish[ep.out] = pp;
                 op = [pp](cudaStream_t st) { igemm_conv_launch(*pp, st); };
-                label("conv%s %s Cin=%d%s Cout=%d %dx%d BN=%d stages=%d%s%s", segs[0].ntaps == 9 ? "3x3" : "1x1",
+                label("conv%s %s Cin=%d%s Cout=%d %dx%d BN=%d stages=%d%s%s%s", segs[0].ntaps == 9 ? "3x3" : "1x1",
                       fwd ? "fwd" : "dgrad", segs[0].Cin, segs.size() > 1 ? "+skip" : "", Cout, H, W, p.BN, p.stages,
-                      ep.stats ? " +stats" : "", ep.gn_x ? " +gnbwd" : "");
+                      ep.stats ? " +stats" : "", ep.gn_x ? " +gnbwd" : "", p.ms == 2 ? " +tmast" : p.ms ? " +ms" : "");
             }
             if (fwd)
                 F(op, 1, UB_KIND_CONV, flops / nh, bytes / nh);
