@@ -409,6 +409,11 @@ def reference_cuda_baseline(args):
     oracle/Makefile) timed for a bounded ~20 s on the same GPU: parsed from its own log lines
     (train_unet.cu:5045-5051: 'step N/... | cur time X s')."""
     exe = os.path.join(ROOT, "oracle", "_ref", "train_unet")
+    # (train_unet_log10 = the same source with the log cadence literal 100 -> 10, oracle/Makefile: two log lines after
+    #  30 iterations instead of 200)
+    every = 100
+    if os.path.exists(exe + "_log10"):
+        exe, every = exe + "_log10", 10
     if not os.path.exists(exe) or args.no_reference_cuda:
         return None
     try:
@@ -426,7 +431,7 @@ def reference_cuda_baseline(args):
                                   "log.txt"], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
             t0 = time.time()
             pts = []
-            while time.time() - t0 < 170:   # a log line every 100 iterations: wait for two of them
+            while time.time() - t0 < (75 if every == 10 else 170):   # a log line every `every` iterations: wait for three
                 time.sleep(0.5)
                 if os.path.exists(log):
                     pts = []
@@ -435,18 +440,23 @@ def reference_cuda_baseline(args):
                             it = int(ln.split("/")[0].split()[1])
                             sec = float(ln.split("cur time")[1].split()[0])
                             pts.append((it, sec))
-                    if len(pts) >= 2 or p.poll() is not None:
+                    if len(pts) >= (3 if every == 10 else 2) or p.poll() is not None:
                         break
             p.kill()
             p.wait()
             what = ("reference train_unet.cu (fp32 SIMT + cuBLAS), unmodified, nvcc -O3 --use_fast_math -arch=sm_100, same "
                     "GPU, from its own 'cur time' log (CUDA-event time since its loop started, train_unet.cu:5014-5043)")
-            if len(pts) >= 2:   # steady state: the delta between two consecutive log lines (no cold start, no lazy mallocs)
-                (i0, s0), (i1, s1) = pts[-2], pts[-1]
-                ms = (s1 - s0) / (i1 - i0) * 1e3
-                cold = s0 / i0 * 1e3
-                return {"ms_per_step": ms, "value": 32 / (ms * 1e-3), "unit": UNIT, "batch": 32, "what": what,
-                        "iters_measured": [i0, i1], "ms_per_step_first_interval_incl_cold_start": cold}
+            if len(pts) >= 2:   # steady state: deltas between consecutive log lines (no cold start, no lazy mallocs)
+                iv = [(b[1] - a[1]) / (b[0] - a[0]) * 1e3 for a, b in zip(pts[:-1], pts[1:])]
+                ms = sorted(iv)[len(iv) // 2]
+                cold = pts[0][1] / pts[0][0] * 1e3
+                # (the reference's step time wanders from one interval to the next on a B200 box -- 220 .. 850 ms within
+                #  one run, profiles/r02_reference_cuda.txt: per-call cudaMalloc / cudaFree, 46 device synchronisations
+                #  per backward and a 1 GiB memset per step are host-side costs; every interval is reported)
+                return {"ms_per_step": ms, "value": 32 / (ms * 1e-3), "unit": UNIT, "batch": 32,
+                        "what": what + "; median of the intervals between its log lines", "iters_measured":
+                        [pts[0][0], pts[-1][0]], "intervals_ms_per_step": [round(v, 1) for v in iv],
+                        "ms_per_step_first_interval_incl_cold_start": cold}
             if pts:
                 it, sec = pts[-1]
                 ms = sec / it * 1e3
