@@ -273,7 +273,7 @@ def run_cuda(args):
                           "achieved": gn_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gn_gbs / pk["hbm_gbs"],
                           "launches_per_step": gn["launches"], "avg_launch_ms": gn["ms"] / max(gn["launches"], 1),
                           "note": "algorithmic bytes / event time; most launches are latency-bound tensors of <= 4 MB "
-                                  "(ncu per-kernel DRAM throughput: profiles/r02_ncu_hbm_kernels.txt)"},
+                                  "(ncu per-kernel DRAM throughput: profiles/r02_final_hbm_kernels.txt)"},
         }
         classes = {}
         for k in ub.UB_KINDS:
@@ -440,7 +440,7 @@ def reference_cuda_baseline(args):
                             it = int(ln.split("/")[0].split()[1])
                             sec = float(ln.split("cur time")[1].split()[0])
                             pts.append((it, sec))
-                    if len(pts) >= (3 if every == 10 else 2) or p.poll() is not None:
+                    if len(pts) >= (6 if every == 10 else 2) or p.poll() is not None:
                         break
             p.kill()
             p.wait()
@@ -448,7 +448,8 @@ def reference_cuda_baseline(args):
                     "GPU, from its own 'cur time' log (CUDA-event time since its loop started, train_unet.cu:5014-5043)")
             if len(pts) >= 2:   # steady state: deltas between consecutive log lines (no cold start, no lazy mallocs)
                 iv = [(b[1] - a[1]) / (b[0] - a[0]) * 1e3 for a, b in zip(pts[:-1], pts[1:])]
-                ms = sorted(iv)[len(iv) // 2]
+                sv = sorted(iv)
+                ms = sv[len(sv) // 2] if len(sv) % 2 else 0.5 * (sv[len(sv) // 2 - 1] + sv[len(sv) // 2])
                 cold = pts[0][1] / pts[0][0] * 1e3
                 # (the reference's step time wanders from one interval to the next on a B200 box -- 220 .. 850 ms within
                 #  one run, profiles/r02_reference_cuda.txt: per-call cudaMalloc / cudaFree, 46 device synchronisations
@@ -456,6 +457,7 @@ def reference_cuda_baseline(args):
                 return {"ms_per_step": ms, "value": 32 / (ms * 1e-3), "unit": UNIT, "batch": 32,
                         "what": what + "; median of the intervals between its log lines", "iters_measured":
                         [pts[0][0], pts[-1][0]], "intervals_ms_per_step": [round(v, 1) for v in iv],
+                        "ms_per_step_best_interval": round(min(iv), 1),
                         "ms_per_step_first_interval_incl_cold_start": cold}
             if pts:
                 it, sec = pts[-1]

@@ -243,6 +243,10 @@ typedef struct {
     float ema_rate;      /* > 0: keep an exponential moving average of the parameters, ema = rate*ema + (1-rate)*p
                             after every AdamW update, fused into the AdamW kernel (guided-diffusion's update_ema;
                             the option the reference carries as `ema_rate`, train_unet.py:708); 0 */
+    int resblock_updown; /* 1: the Downsample / Upsample layers become ResBlock(down=True) / ResBlock(up=True)
+                            (dev/unet.py:147,205-222,271-284 `resblock_updown`, dev/resblock.py:78-86,125-128: average
+                            pool / nearest upsample of both the main and the skip path inside the block); each adds the
+                            10 parameter tensors of a ResBlock at the place of the parameter-free layer; 0 */
 } UbConfig;
 
 void ub_default_config(UbConfig* cfg);

@@ -143,6 +143,35 @@ def gen_class_cond(out_dir):
     print("class_cond_B2.npz written, loss", float(loss))
 
 
+def gen_updown(out_dir):
+    """resblock_updown=True (dev/unet.py:147,205-222,271-284), zero-initialised tensors perturbed as in gen_class_cond,
+    B = 2: loss, output slice, gradient slice, per-tensor gradient norms.   python oracle/gen_golden.py updown"""
+    from unet import UNetModel
+    import train_unet as ref_train
+    torch.manual_seed(0)
+    model = UNetModel(3, 64, 3, 2, (4, 8), num_head_channels=32, resblock_updown=True)
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for _, p in model.named_parameters():
+            if not p.detach().any():
+                p.add_(0.02 * torch.randn(p.shape, generator=g))
+    shapes = [tuple(p.shape) for _, p in model.named_parameters()]
+    diffusion = ref_train.GaussianDiffusion(ref_train.get_named_beta_schedule("linear", 1000))
+    B = 2
+    x0, t, noise = synthetic(B)
+    out = model(diffusion.q_sample(x0, t.view(B).long(), noise), t)
+    loss = ((out - noise) ** 2).mean()
+    loss.backward()
+    gflat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    np.savez_compressed(
+        os.path.join(out_dir, "updown_B2.npz"), names=np.array([n for n, _ in model.named_parameters()]),
+        loss=np.array([float(loss.detach())]), out_slice=out.detach().reshape(-1)[::37].numpy(),
+        grad_slice=gflat[::4099].numpy(),
+        grad_norms=np.array([float(gflat[o:o + n].double().norm()) for o, n in offsets(shapes)]),
+        param_slice=torch.cat([p.detach().reshape(-1) for p in model.parameters()])[::4099].numpy())
+    print("updown_B2.npz written, loss", float(loss.detach()), "params", int(gflat.numel()))
+
+
 def offsets(shapes):
     o = 0
     for s in shapes:
@@ -158,9 +187,10 @@ def pad4(v):
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "class_cond":   # (added later: leaves the other fixtures untouched)
+    if len(sys.argv) > 1 and sys.argv[1] in ("class_cond", "updown"):   # (added later: leave the other fixtures untouched)
         torch.set_num_threads(os.cpu_count())
-        gen_class_cond(os.path.join(ROOT, "tests", "golden"))
+        (gen_class_cond if sys.argv[1] == "class_cond" else gen_updown)(os.path.join(ROOT, "tests", "golden"))
     else:
         main()
         gen_class_cond(os.path.join(ROOT, "tests", "golden"))
+        gen_updown(os.path.join(ROOT, "tests", "golden"))

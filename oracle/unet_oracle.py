@@ -41,6 +41,7 @@ class UNetConfig:
     H: int = 64
     W: int = 64
     num_classes: int = 0               # > 0: class-conditional, label_emb = nn.Embedding(num_classes, 4*mc) (dev/unet.py:174-175)
+    resblock_updown: bool = False      # ResBlock(down=True / up=True) instead of Downsample / Upsample (dev/unet.py:147,205-222,271-284)
 
     @property
     def emb_channels(self) -> int:
@@ -114,7 +115,11 @@ def build_layers(cfg: UNetConfig) -> List[Layer]:
             chans.append(ch)
             ib += 1
         if level != nlev - 1:
-            L.append(Layer('down', ch, ch, level, skip_push=True, name=f"input_blocks.{ib}.0"))
+            if cfg.resblock_updown:
+                L.append(Layer('res_down', ch, ch, level, res_params(f"input_blocks.{ib}.0", ch, ch, cemb), skip_push=True,
+                               name=f"input_blocks.{ib}.0"))
+            else:
+                L.append(Layer('down', ch, ch, level, skip_push=True, name=f"input_blocks.{ib}.0"))
             chans.append(ch)
             ib += 1
     L.append(Layer('res', ch, ch, nlev - 1, res_params("middle_block.0", ch, ch, cemb), name="middle_block.0"))
@@ -136,7 +141,11 @@ def build_layers(cfg: UNetConfig) -> List[Layer]:
                                name=f"output_blocks.{ob}.1"))
                 sub = 2
             if level and i == cfg.num_res_blocks:
-                L.append(Layer('up', ch, ch, level, name=f"output_blocks.{ob}.{sub}"))
+                if cfg.resblock_updown:
+                    L.append(Layer('res_up', ch, ch, level, res_params(f"output_blocks.{ob}.{sub}", ch, ch, cemb),
+                                   name=f"output_blocks.{ob}.{sub}"))
+                else:
+                    L.append(Layer('up', ch, ch, level, name=f"output_blocks.{ob}.{sub}"))
             ob += 1
     L.append(Layer('gn', ch, ch, 0, [("out.0.weight", (ch,)), ("out.0.bias", (ch,))], name="out.0"))
     L.append(Layer('conv3', ch, cfg.out_channels, 0, [("out.2.weight", (cfg.out_channels, ch, 3, 3)),
@@ -278,10 +287,15 @@ def upsample2(x):
     return x.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
 
 
-def resblock(x, emb, P: Dict[str, torch.Tensor], prefix: str, groups=32):
-    """dev/resblock.py:107-160, train_unet.cu:2213-2287 (up = down = 0 in the U-Net, train_unet.cu:4278)."""
-    h = conv3x3(silu(groupnorm(x, P[prefix + '.gn1.weight'], P[prefix + '.gn1.bias'], groups)),
-                P[prefix + '.cv3_1.weight'], P[prefix + '.cv3_1.bias'])
+def resblock(x, emb, P: Dict[str, torch.Tensor], prefix: str, groups=32, updown: str | None = None):
+    """dev/resblock.py:107-160, train_unet.cu:2213-2287 (up = down = 0 in the default U-Net, train_unet.cu:4278).
+    updown = 'down' / 'up' (dev/resblock.py:78-86, 125-128): h_upd / x_upd resample the main path between SiLU and conv1
+    and the skip path -- average pool 2x2 (Downsample, dev/resblock.py:34-43) or nearest x2 (Upsample, :25-32)."""
+    h = silu(groupnorm(x, P[prefix + '.gn1.weight'], P[prefix + '.gn1.bias'], groups))
+    if updown:
+        rs = avgpool2 if updown == 'down' else upsample2
+        h, x = rs(h), rs(x)
+    h = conv3x3(h, P[prefix + '.cv3_1.weight'], P[prefix + '.cv3_1.bias'])
     e = F.linear(silu(emb), P[prefix + '.l_emb.weight'], P[prefix + '.l_emb.bias'])
     h = h + e[:, :, None, None]
     h = conv3x3(silu(groupnorm(h, P[prefix + '.gn2.weight'], P[prefix + '.gn2.bias'], groups)),
@@ -332,6 +346,8 @@ def unet_forward(cfg: UNetConfig, P: Dict[str, torch.Tensor], x: torch.Tensor, t
             h = conv3x3(h, P[l.name + '.weight'], P[l.name + '.bias'])
         elif l.kind == 'res':
             h = resblock(h, emb, P, l.name, cfg.gn_groups)
+        elif l.kind in ('res_down', 'res_up'):
+            h = resblock(h, emb, P, l.name, cfg.gn_groups, updown=l.kind[4:])
         elif l.kind == 'attn':
             h = attention_block(h, P, l.name, cfg.head_size, cfg.gn_groups)
         elif l.kind == 'down':

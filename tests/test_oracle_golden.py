@@ -115,3 +115,26 @@ def test_class_conditional_step_matches_reference(oracle, golden_dir):
         norms.append(float(grads[off:off + n].double().norm()))
         off += n
     np.testing.assert_allclose(np.array(norms), g["grad_norms"], rtol=1e-3)
+
+
+def test_resblock_updown_step_matches_reference(oracle, golden_dir):
+    """resblock_updown=True (dev/unet.py:147,205-222,271-284): the fixture came from the reference's own
+    UNetModel(resblock_updown=True) with the zero-initialised tensors perturbed."""
+    O = oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = np.load(os.path.join(golden_dir, "updown_B2.npz"))
+    cfg = O.UNetConfig(resblock_updown=True)
+    assert [n for n, _ in O.param_spec(cfg)] == [str(n) for n in g["names"]]
+    flat = O.perturb_zero_params(cfg, _flat(O, cfg, O.init_params(cfg, seed=0)))
+    np.testing.assert_array_equal(flat[::4099].numpy(), g["param_slice"])
+    x0, t, noise = O.synthetic_batch(cfg, 2)
+    loss, out, grads = O.train_step_grads(cfg, flat, x0, t, noise)
+    assert abs(float(loss) - float(g["loss"][0])) < 1e-6
+    np.testing.assert_allclose(out.reshape(-1)[::37].numpy(), g["out_slice"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(grads[::4099].numpy(), g["grad_slice"], rtol=1e-3, atol=1e-6)
+    off, norms = 0, []
+    for _, s in O.param_spec(cfg):
+        n = int(np.prod(s))
+        norms.append(float(grads[off:off + n].double().norm()))
+        off += n
+    np.testing.assert_allclose(np.array(norms), g["grad_norms"], rtol=1e-3)

@@ -123,3 +123,35 @@ def test_class_conditional_matches_reference(oracle, ref_unet):
     assert float((gr - g_ref).abs().max()) < 1e-6 + 1e-4 * float(g_ref.abs().max())
     ge = model.label_emb.weight.grad
     assert float(ge[3].abs().max()) > 0 and float(ge[7].abs().max()) > 0 and float(ge[0].abs().max()) == 0
+
+
+def test_resblock_updown_matches_reference(oracle, ref_unet):
+    """resblock_updown=True (dev/unet.py:147,205-222,271-284): parameter order / init bit-identical, forward output and
+    every gradient against the reference's own UNetModel (zero-initialised tensors perturbed, see
+    perturb_zero_params)."""
+    O = oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.UNetConfig(resblock_updown=True)
+    torch.manual_seed(0)
+    model = ref_unet.UNetModel(3, 64, 3, 2, (4, 8), num_head_channels=32, resblock_updown=True)
+    names = [(n, tuple(p.shape)) for n, p in model.named_parameters()]
+    assert names == O.param_spec(cfg)
+    P = O.init_params(cfg, seed=0)
+    for n, p in model.named_parameters():
+        assert torch.equal(P[n], p.detach()), n
+    flat = O.perturb_zero_params(cfg, O.flatten_params(cfg, P))
+    with torch.no_grad():
+        off = 0
+        for p in model.parameters():
+            p.copy_(flat[off:off + p.numel()].reshape(p.shape))
+            off += p.numel()
+    B = 2
+    x0, t, noise = O.synthetic_batch(cfg, B)
+    loss, out, gr = O.train_step_grads(cfg, flat, x0, t, noise)
+    out_ref = model(O.q_sample(x0, t, noise), t)
+    loss_ref = ((out_ref - noise) ** 2).mean()
+    loss_ref.backward()
+    g_ref = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    assert abs(float(loss) - float(loss_ref.detach())) < 1e-6
+    assert float((out - out_ref.detach()).abs().max()) < 1e-5
+    assert float((gr - g_ref).abs().max()) < 1e-6 + 1e-4 * float(g_ref.abs().max())

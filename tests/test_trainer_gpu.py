@@ -505,3 +505,41 @@ def test_ema_matches_oracle(ub, setup, tmp_path, graph):
     with pytest.raises(ub.UbError):
         plain.get_ema()
     plain.close()
+
+
+@pytest.mark.parametrize("kw,okw,B", [
+    (dict(resblock_updown=1), dict(resblock_updown=True), 2),
+    (dict(resblock_updown=1, H=32, W=32, channel_mult=(1, 2, 2), att_start_level=1, n_res_blocks=1),
+     dict(resblock_updown=True, H=32, W=32, channel_mult=(1, 2, 2), attn_start_level=1, num_res_blocks=1), 3),
+])
+def test_resblock_updown_matches_oracle(ub, oracle, golden_dir, kw, okw, B):
+    """ResBlock(down=True) / ResBlock(up=True) in place of Downsample / Upsample
+    (dev/unet.py:147,205-222,271-284; dev/resblock.py:78-86,125-128).  Perturbed weights (every path carries a gradient);
+    loss, output, all gradients against the oracle (pinned to the reference's UNetModel(resblock_updown=True) live and by
+    fixture); the default-shape case also against the fixture's loss and per-tensor gradient norms."""
+    O = oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.UNetConfig(**okw)
+    flat = O.perturb_zero_params(cfg, O.flatten_params(cfg, O.init_params(cfg, seed=0)))
+    x0, t, noise = O.synthetic_batch(cfg, B)
+    tr = ub.Trainer(B=B, **kw)
+    assert tr.nparams == flat.numel()
+    tr.set_params(flat.numpy())
+    loss = tr.forward_backward(x0.numpy(), t.numpy(), noise.numpy())
+    out, g = tr.get_output(), tr.get_grads()
+    loss_ref, out_ref, g_ref = O.train_step_grads(cfg, flat, x0, t, noise)
+    assert abs(loss - float(loss_ref)) <= 2e-3 * float(loss_ref)
+    assert np.abs(out - out_ref.numpy()).max() <= 3e-2 * np.abs(out_ref.numpy()).max()
+    check_grads(O, cfg, g, g_ref.numpy(), "resblock_updown " + str(kw))
+    if len(kw) == 1:
+        gold = np.load(os.path.join(golden_dir, "updown_B2.npz"))
+        assert abs(loss - float(gold["loss"][0])) <= 2e-3 * float(gold["loss"][0])
+        off, norms = 0, []
+        for _, s in O.param_spec(cfg):
+            n = int(np.prod(s))
+            norms.append(float(np.linalg.norm(g[off:off + n].astype(np.float64))))
+            off += n
+        np.testing.assert_allclose(np.array(norms), gold["grad_norms"], rtol=0.1)
+    l2 = tr.train_step(x0.numpy(), t.numpy(), noise.numpy(), lr=1e-4)   # the captured-graph path runs too
+    assert np.isfinite(l2)
+    tr.close()

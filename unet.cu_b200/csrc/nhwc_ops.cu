@@ -609,6 +609,27 @@ void upsample2_bwd(const bf16* dy, int lddy, int B, int H, int W, int C, bf16* d
     launch_pdl(upsample2_bwd_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), 0, st, dy, lddy, H, W, C / 8, total, dx, lddx);
 }
 
+// y (2H x 2W) = nearest-neighbour x2 upsample of x (H x W)  (dev/resblock.py:25-32, F.interpolate(scale_factor=2, "nearest"));
+// one thread per output pixel and 8-channel chunk.  Only the up/down ResBlocks use it (cfg.resblock_updown): the plain
+// Upsample layer is fused into the concat that consumes it.
+__global__ void upsample2_fwd_kernel(const bf16* __restrict__ x, int ldx, int H, int W, int C8, size_t total,
+                                     bf16* __restrict__ y, int ldy) {
+    pdl_entry();
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int j = int(i % C8);
+    const size_t p = i / C8;  // output pixel
+    const int Wo = 2 * W, Ho = 2 * H;
+    const int wo = int(p % Wo), ho = int((p / Wo) % Ho);
+    const size_t b = p / (size_t(Wo) * Ho);
+    const uint4 v = *reinterpret_cast<const uint4*>(x + ((b * H + ho / 2) * W + wo / 2) * ldx + j * 8);
+    *reinterpret_cast<uint4*>(y + p * ldy + j * 8) = v;
+}
+void upsample2_fwd(const bf16* x, int ldx, int B, int H, int W, int C, bf16* y, int ldy, cudaStream_t st) {
+    const size_t total = size_t(B) * (2 * H) * (2 * W) * (C / 8);
+    launch_pdl(upsample2_fwd_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), 0, st, x, ldx, H, W, C / 8, total, y, ldy);
+}
+
 __global__ void add2_kernel(const bf16* __restrict__ a, int lda, const bf16* __restrict__ b, int ldb, int C8,
                             size_t total, bf16* __restrict__ out, int ldo) {
     pdl_entry();

@@ -54,6 +54,8 @@ void avgpool2_bwd(const bf16* dy, int lddy, int B, int H, int W, int C, const bf
 // the concatenation.
 void concat2(const bf16* a, int lda, int C1, int up, const bf16* b, int ldb, int C2, int B, int H, int W, bf16* out,
              int ldo, const float* cs_a, const float* cs_b, float* cs_out, cudaStream_t st);
+// y (2H x 2W) = nearest x2 upsample of x (H x W); (H, W) is the INPUT resolution
+void upsample2_fwd(const bf16* x, int ldx, int B, int H, int W, int C, bf16* y, int ldy, cudaStream_t st);
 // dx (H/2 x W/2) = sum of the 4 children of dy (H x W)
 void upsample2_bwd(const bf16* dy, int lddy, int B, int H, int W, int C, bf16* dx, int lddx, cudaStream_t st);
 void add2(const bf16* a, int lda, const bf16* b, int ldb, size_t npix, int C, bf16* out, int ldo, cudaStream_t st);

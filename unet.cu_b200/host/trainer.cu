@@ -634,14 +634,53 @@ struct Builder {
         }, cls ? 7 : 6, UB_KIND_SMALL, 0, 0, tail_aux() ? 3 : 1);  // 3: a branch of its own, forked from the weight-gradient branch
     }
 
-    // ResBlock (dev/resblock.py:107-160, train_unet.cu:2213-2384)
-    View resblock(View x, int Cout) {
+    // 2x resampling of a tensor inside an up/down ResBlock (h_upd / x_upd, dev/resblock.py:78-86,125-128): ud = 1 average
+    // pool, ud = 2 nearest upsample
+    void resample_fwd(View x, View y, int ud) {
+        split([&](int hh) {
+            const View xm = mb(x, hh), ym = mb(y, hh);
+            const int Bq = Bh;
+            F([=](cudaStream_t st) {
+                if (ud == 1)
+                    avgpool2_fwd(xm.p, xm.ld, Bq, xm.H, xm.W, xm.C, ym.p, ym.ld, st);
+                else
+                    upsample2_fwd(xm.p, xm.ld, Bq, xm.H, xm.W, xm.C, ym.p, ym.ld, st);
+            }, 1, UB_KIND_ELTWISE, 0, 1.25 * act_bytes(x.C, std::max(x.H, y.H), std::max(x.W, y.W)) / nh);
+        });
+    }
+    // gradient of resample_fwd: dx (resolution of x) from dy (resolution of y)
+    void resample_bwd(View dy, View dx, int ud) {
+        split([&](int hh) {
+            const View dm = mb(dy, hh), dxm = mb(dx, hh);
+            const int Bq = Bh;
+            Bk([=](cudaStream_t st) {
+                if (ud == 1)
+                    avgpool2_bwd(dm.p, dm.ld, Bq, dxm.H, dxm.W, dxm.C, nullptr, 0, dxm.p, dxm.ld, st);
+                else
+                    upsample2_bwd(dm.p, dm.ld, Bq, dm.H, dm.W, dm.C, dxm.p, dxm.ld, st);
+            }, 1, UB_KIND_ELTWISE, 0, 1.25 * act_bytes(dx.C, std::max(dx.H, dy.H), std::max(dx.W, dy.W)) / nh);
+        });
+    }
+
+    // ResBlock (dev/resblock.py:107-160, train_unet.cu:2213-2384).  ud != 0 (cfg.resblock_updown, dev/unet.py:205-222,
+    // 271-284): the block resamples -- 1 = down (average pool), 2 = up (nearest) -- both its main path, between SiLU and
+    // conv1, and its skip path (h_upd / x_upd, dev/resblock.py:125-128); x is at the input resolution, everything from
+    // conv1 on at the output resolution, and Cout == C.
+    View resblock(View x, int Cout, int ud = 0) {
         Node nd;
         nd.param_begin = poff;
-        const int C = x.C, H = x.H, W = x.W, Cemb = 4 * c.C_model;
+        const int C = x.C, Hin = x.H, Win = x.W, Cemb = 4 * c.C_model;
+        const int H = ud == 1 ? Hin / 2 : (ud == 2 ? 2 * Hin : Hin), W = ud == 1 ? Win / 2 : (ud == 2 ? 2 * Win : Win);
         const int blk = res_index++;
-        View a1 = act(C, H, W);
+        View a1 = act(C, Hin, Win);
         GN g1 = gn_fwd(x, a1, 1);
+        const View xin = x;  // at the input resolution
+        if (ud) {
+            View a1r = act(C, H, W), xr = act(C, H, W);
+            resample_fwd(a1, a1r, ud);
+            resample_fwd(x, xr, ud);
+            a1 = a1r, x = xr;  // what conv1 and the (identity) skip connection see
+        }
         const size_t w1 = take(size_t(Cout) * C * 9), b1 = take(Cout);
         const size_t wl = take(size_t(Cout) * Cemb), bl = take(Cout);
         View h1 = act(Cout, H, W);
@@ -712,6 +751,18 @@ struct Builder {
                 time_mlp_bwd();
             }
             wgrad_op(dh1, a1, C, Cout, 9, G(w1));
+            if (ud) {
+                // conv1 ran on the resampled tensor: its dgrad is plain (no gn-bwd hook -- GroupNorm 1 lives at the input
+                // resolution), both gradients go back through the resampling, GroupNorm 1 + SiLU backward run unfused
+                ConvEpilogue ep;
+                ep.out = da1.p, ep.ldo = da1.ld;
+                conv_op(false, {{dh1.p, Cout, dh1.ld, p1.wd, 9}}, H, W, C, ep);
+                View da1in = act(C, Hin, Win), dskip = act(C, Hin, Win), dxin = act(C, Hin, Win);
+                resample_bwd(da1, da1in, ud);
+                resample_bwd(dout, dskip, ud);  // identity skip connection behind x_upd (Cout == C)
+                gn_bwd(g1, xin, da1in, 1, dskip, dxin, nullptr, false);
+                return dxin;
+            }
             {
                 ConvEpilogue ep;
                 ep.out = da1.p, ep.ldo = da1.ld;
@@ -922,7 +973,12 @@ int Builder::build() {
             skip_stack.push_back(int(nodes.size()) - 1);
             skip_views.push_back(h);
         }
-        if (level != nlev - 1) {  // Downsample (dev/resblock.py:34-43)
+        if (level != nlev - 1 && c.resblock_updown) {  // ResBlock(down=True) instead of Downsample (dev/unet.py:205-222)
+            h = resblock(h, h.C, 1);
+            nodes.back().pushed = true;
+            skip_stack.push_back(int(nodes.size()) - 1);
+            skip_views.push_back(h);
+        } else if (level != nlev - 1) {  // Downsample (dev/resblock.py:34-43)
             Node nd;
             nd.param_begin = poff;
             View x = h, y = act(h.C, h.H / 2, h.W / 2);
@@ -999,7 +1055,12 @@ int Builder::build() {
             pending_up = false;
             h = resblock(cat, cout);
             if (level >= c.att_start_level) h = attnblock(h);
-            if (level && i == c.n_res_blocks) pending_up = true;
+            if (level && i == c.n_res_blocks) {
+                if (c.resblock_updown)
+                    h = resblock(h, h.C, 2);  // ResBlock(up=True) instead of Upsample (dev/unet.py:271-284)
+                else
+                    pending_up = true;
+            }
         }
     }
     // ---- output head: GN + SiLU + conv3x3 (-> C_out) + MSE (dev/unet.py:286-290, train_unet.cu:4408-4418)
@@ -1195,6 +1256,10 @@ static int validate_config(const UbConfig& c) {
     }
     if ((c.H >> (c.n_levels - 1)) < 1 || c.H % (1 << (c.n_levels - 1)) || c.W % (1 << (c.n_levels - 1))) {
         set_err("H, W must be divisible by 2^(n_levels-1)");
+        return UB_ERR_SHAPE;
+    }
+    if (c.resblock_updown != 0 && c.resblock_updown != 1) {
+        set_err("bad config: resblock_updown must be 0 or 1");
         return UB_ERR_SHAPE;
     }
     if (c.num_classes < 0 || !(c.ema_rate >= 0.f && c.ema_rate < 1.f)) {
