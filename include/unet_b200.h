@@ -247,6 +247,9 @@ typedef struct {
                             (dev/unet.py:147,205-222,271-284 `resblock_updown`, dev/resblock.py:78-86,125-128: average
                             pool / nearest upsample of both the main and the skip path inside the block); each adds the
                             10 parameter tensors of a ResBlock at the place of the parameter-free layer; 0 */
+    int use_scale_shift_norm; /* 1: FiLM-like conditioning (dev/unet.py:146 `use_scale_shift_norm`, dev/resblock.py:211,
+                            243-247): every ResBlock's embedding projection has 2*Cout outputs [scale | shift] and the second
+                            GroupNorm computes gn(h) * (1 + scale) + shift instead of gn(h + emb); 0 */
 } UbConfig;
 
 void ub_default_config(UbConfig* cfg);

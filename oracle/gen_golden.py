@@ -143,6 +143,35 @@ def gen_class_cond(out_dir):
     print("class_cond_B2.npz written, loss", float(loss))
 
 
+_RBO_NAMES = {"in_layers.0": "gn1", "in_layers.2": "cv3_1", "emb_layers.1": "l_emb", "out_layers.0": "gn2",
+              "out_layers.2": "cv3_2", "skip_connection": "skip_connection"}
+
+
+def gen_scale_shift(out_dir):
+    """use_scale_shift_norm on the reference's copy of the original ResBlock (ResBlockO, dev/resblock.py:165-247 -- the
+    explicit ResBlock's own scale-shift branch refers to an attribute it does not define): two blocks, 64 -> 32 plain and
+    64 -> 64 with down=True; inputs, outputs and the gradients of x, emb and every parameter for a fixed dL/dy.
+    python oracle/gen_golden.py scale_shift"""
+    from resblock import ResBlockO
+    out = {}
+    for tag, kw, cout in (("a", {}, 32), ("d", {"down": True}, 64)):
+        torch.manual_seed(3)
+        rb = ResBlockO(64, 256, out_channels=cout, use_scale_shift_norm=True, **kw)
+        x = torch.randn(2, 64, 8, 8, requires_grad=True)
+        emb = torch.randn(2, 256, requires_grad=True)
+        y = rb(x, emb)
+        dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(4))
+        y.backward(dy)
+        out.update({f"{tag}_x": x.detach().numpy(), f"{tag}_emb": emb.detach().numpy(), f"{tag}_y": y.detach().numpy(),
+                    f"{tag}_dy": dy.numpy(), f"{tag}_dx": x.grad.numpy(), f"{tag}_demb": emb.grad.numpy()})
+        for k, v in rb.named_parameters():
+            mod, leaf = k.rsplit(".", 1)
+            out[f"{tag}.{_RBO_NAMES[mod]}.{leaf}"] = v.detach().numpy()
+            out[f"{tag}.grad.{_RBO_NAMES[mod]}.{leaf}"] = v.grad.numpy()
+    np.savez_compressed(os.path.join(out_dir, "resblock_scale_shift.npz"), **out)
+    print("resblock_scale_shift.npz written")
+
+
 def gen_updown(out_dir):
     """resblock_updown=True (dev/unet.py:147,205-222,271-284), zero-initialised tensors perturbed as in gen_class_cond,
     B = 2: loss, output slice, gradient slice, per-tensor gradient norms.   python oracle/gen_golden.py updown"""
@@ -187,10 +216,11 @@ def pad4(v):
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] in ("class_cond", "updown"):   # (added later: leave the other fixtures untouched)
+    later = {"class_cond": gen_class_cond, "updown": gen_updown, "scale_shift": gen_scale_shift}
+    if len(sys.argv) > 1 and sys.argv[1] in later:   # (added later: leave the other fixtures untouched)
         torch.set_num_threads(os.cpu_count())
-        (gen_class_cond if sys.argv[1] == "class_cond" else gen_updown)(os.path.join(ROOT, "tests", "golden"))
+        later[sys.argv[1]](os.path.join(ROOT, "tests", "golden"))
     else:
         main()
-        gen_class_cond(os.path.join(ROOT, "tests", "golden"))
-        gen_updown(os.path.join(ROOT, "tests", "golden"))
+        for fn in later.values():
+            fn(os.path.join(ROOT, "tests", "golden"))

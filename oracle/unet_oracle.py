@@ -42,6 +42,7 @@ class UNetConfig:
     W: int = 64
     num_classes: int = 0               # > 0: class-conditional, label_emb = nn.Embedding(num_classes, 4*mc) (dev/unet.py:174-175)
     resblock_updown: bool = False      # ResBlock(down=True / up=True) instead of Downsample / Upsample (dev/unet.py:147,205-222,271-284)
+    use_scale_shift_norm: bool = False # FiLM-like conditioning in every ResBlock (dev/unet.py:146, dev/resblock.py:211,243-247)
 
     @property
     def emb_channels(self) -> int:
@@ -65,11 +66,13 @@ class Layer:
     name: str = ""
 
 
-def res_params(prefix: str, cin: int, cout: int, cemb: int):
-    """ResBlock parameter order (dev/resblock.cuh:8-21, dev/resblock.py:70-105)."""
+def res_params(prefix: str, cin: int, cout: int, cemb: int, scale_shift: bool = False):
+    """ResBlock parameter order (dev/resblock.cuh:8-21, dev/resblock.py:70-105); with use_scale_shift_norm the embedding
+    projection has 2 * cout outputs (dev/resblock.py:91-94)."""
+    oce = 2 * cout if scale_shift else cout
     p = [(f"{prefix}.gn1.weight", (cin,)), (f"{prefix}.gn1.bias", (cin,)),
          (f"{prefix}.cv3_1.weight", (cout, cin, 3, 3)), (f"{prefix}.cv3_1.bias", (cout,)),
-         (f"{prefix}.l_emb.weight", (cout, cemb)), (f"{prefix}.l_emb.bias", (cout,)),
+         (f"{prefix}.l_emb.weight", (oce, cemb)), (f"{prefix}.l_emb.bias", (oce,)),
          (f"{prefix}.gn2.weight", (cout,)), (f"{prefix}.gn2.bias", (cout,)),
          (f"{prefix}.cv3_2.weight", (cout, cout, 3, 3)), (f"{prefix}.cv3_2.bias", (cout,))]
     if cin != cout:
@@ -106,7 +109,7 @@ def build_layers(cfg: UNetConfig) -> List[Layer]:
         for _ in range(cfg.num_res_blocks):
             cout = mult * mc
             has_attn = level >= cfg.attn_start_level
-            L.append(Layer('res', ch, cout, level, res_params(f"input_blocks.{ib}.0", ch, cout, cemb),
+            L.append(Layer('res', ch, cout, level, res_params(f"input_blocks.{ib}.0", ch, cout, cemb, cfg.use_scale_shift_norm),
                            skip_push=not has_attn, name=f"input_blocks.{ib}.0"))
             ch = cout
             if has_attn:
@@ -116,15 +119,15 @@ def build_layers(cfg: UNetConfig) -> List[Layer]:
             ib += 1
         if level != nlev - 1:
             if cfg.resblock_updown:
-                L.append(Layer('res_down', ch, ch, level, res_params(f"input_blocks.{ib}.0", ch, ch, cemb), skip_push=True,
+                L.append(Layer('res_down', ch, ch, level, res_params(f"input_blocks.{ib}.0", ch, ch, cemb, cfg.use_scale_shift_norm), skip_push=True,
                                name=f"input_blocks.{ib}.0"))
             else:
                 L.append(Layer('down', ch, ch, level, skip_push=True, name=f"input_blocks.{ib}.0"))
             chans.append(ch)
             ib += 1
-    L.append(Layer('res', ch, ch, nlev - 1, res_params("middle_block.0", ch, ch, cemb), name="middle_block.0"))
+    L.append(Layer('res', ch, ch, nlev - 1, res_params("middle_block.0", ch, ch, cemb, cfg.use_scale_shift_norm), name="middle_block.0"))
     L.append(Layer('attn', ch, ch, nlev - 1, attn_params("middle_block.1", ch), name="middle_block.1"))
-    L.append(Layer('res', ch, ch, nlev - 1, res_params("middle_block.2", ch, ch, cemb), name="middle_block.2"))
+    L.append(Layer('res', ch, ch, nlev - 1, res_params("middle_block.2", ch, ch, cemb, cfg.use_scale_shift_norm), name="middle_block.2"))
     ob = 0
     for level in reversed(range(nlev)):
         mult = cfg.channel_mult[level]
@@ -132,7 +135,7 @@ def build_layers(cfg: UNetConfig) -> List[Layer]:
             ich = chans.pop()
             cout = mult * mc
             L.append(Layer('concat', ch, ch + ich, level, name=f"output_blocks.{ob}.cat"))
-            L.append(Layer('res', ch + ich, cout, level, res_params(f"output_blocks.{ob}.0", ch + ich, cout, cemb),
+            L.append(Layer('res', ch + ich, cout, level, res_params(f"output_blocks.{ob}.0", ch + ich, cout, cemb, cfg.use_scale_shift_norm),
                            name=f"output_blocks.{ob}.0"))
             ch = cout
             sub = 1
@@ -142,7 +145,7 @@ def build_layers(cfg: UNetConfig) -> List[Layer]:
                 sub = 2
             if level and i == cfg.num_res_blocks:
                 if cfg.resblock_updown:
-                    L.append(Layer('res_up', ch, ch, level, res_params(f"output_blocks.{ob}.{sub}", ch, ch, cemb),
+                    L.append(Layer('res_up', ch, ch, level, res_params(f"output_blocks.{ob}.{sub}", ch, ch, cemb, cfg.use_scale_shift_norm),
                                    name=f"output_blocks.{ob}.{sub}"))
                 else:
                     L.append(Layer('up', ch, ch, level, name=f"output_blocks.{ob}.{sub}"))
@@ -297,9 +300,12 @@ def resblock(x, emb, P: Dict[str, torch.Tensor], prefix: str, groups=32, updown:
         h, x = rs(h), rs(x)
     h = conv3x3(h, P[prefix + '.cv3_1.weight'], P[prefix + '.cv3_1.bias'])
     e = F.linear(silu(emb), P[prefix + '.l_emb.weight'], P[prefix + '.l_emb.bias'])
-    h = h + e[:, :, None, None]
-    h = conv3x3(silu(groupnorm(h, P[prefix + '.gn2.weight'], P[prefix + '.gn2.bias'], groups)),
-                P[prefix + '.cv3_2.weight'], P[prefix + '.cv3_2.bias'])
+    if e.shape[1] == 2 * h.shape[1]:   # use_scale_shift_norm (dev/resblock.py:243-247): gn(h) * (1 + scale) + shift
+        scale, shift = torch.chunk(e[:, :, None, None], 2, dim=1)
+        h = groupnorm(h, P[prefix + '.gn2.weight'], P[prefix + '.gn2.bias'], groups) * (1 + scale) + shift
+    else:
+        h = groupnorm(h + e[:, :, None, None], P[prefix + '.gn2.weight'], P[prefix + '.gn2.bias'], groups)
+    h = conv3x3(silu(h), P[prefix + '.cv3_2.weight'], P[prefix + '.cv3_2.bias'])
     if (prefix + '.skip_connection.weight') in P:
         x = conv1x1(x, P[prefix + '.skip_connection.weight'], P[prefix + '.skip_connection.bias'])
     return x + h

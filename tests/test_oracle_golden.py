@@ -138,3 +138,26 @@ def test_resblock_updown_step_matches_reference(oracle, golden_dir):
         norms.append(float(grads[off:off + n].double().norm()))
         off += n
     np.testing.assert_allclose(np.array(norms), g["grad_norms"], rtol=1e-3)
+
+
+def test_scale_shift_resblock_matches_reference_original(oracle, golden_dir):
+    """use_scale_shift_norm (dev/resblock.py:211,243-247): the fixture came from the reference's copy of the original
+    ResBlock (ResBlockO) -- output and the gradients of x, emb and every parameter, plain and with down=True."""
+    O = oracle
+    g = np.load(os.path.join(golden_dir, "resblock_scale_shift.npz"))
+    for tag, updown in (("a", None), ("d", "down")):
+        P = {k: torch.from_numpy(g[k]).requires_grad_(True) for k in g.files
+             if k.startswith(tag + ".") and not k.startswith(tag + ".grad.")}
+        assert P[tag + ".l_emb.weight"].shape[0] == 2 * P[tag + ".cv3_1.weight"].shape[0]
+        x = torch.from_numpy(g[tag + "_x"]).requires_grad_(True)
+        emb = torch.from_numpy(g[tag + "_emb"]).requires_grad_(True)
+        y = O.resblock(x, emb, P, tag, updown=updown)
+        np.testing.assert_allclose(y.detach().numpy(), g[tag + "_y"], rtol=1e-4, atol=1e-5)
+        y.backward(torch.from_numpy(g[tag + "_dy"]))
+        np.testing.assert_allclose(x.grad.numpy(), g[tag + "_dx"], rtol=1e-3, atol=1e-5)
+        np.testing.assert_allclose(emb.grad.numpy(), g[tag + "_demb"], rtol=1e-3, atol=1e-5)
+        for k, v in P.items():
+            ref = g[tag + ".grad." + k[len(tag) + 1:]]
+            # (a bias in front of a GroupNorm has a gradient that is a difference of nearly equal sums: fp32 noise of
+            #  ~5e-6 absolute around values of 1e-6)
+            np.testing.assert_allclose(v.grad.numpy(), ref, rtol=1e-3, atol=2e-5 + 1e-4 * float(np.abs(ref).max()))

@@ -1,4 +1,6 @@
 o=gpurun_out; mkdir -p $o
-timeout 100 python tools/run_reference_cuda.py 40 > $o/e1_ref_plain.txt 2>&1; tail -12 $o/e1_ref_plain.txt
-timeout 200 python tools/run_reference_cuda.py 150 $o/e1_ref_launches.csv 5000 4000 > $o/e1_ref_ncu.txt 2>&1; tail -5 $o/e1_ref_ncu.txt
-python tools/launch_summary.py $o/e1_ref_launches.csv > $o/e1_ref_launch_summary.txt 2>&1; head -40 $o/e1_ref_launch_summary.txt
+timeout 250 python -m pytest tests/test_dp_gpu.py -q -x > $o/g1_pytest_dp.log 2>&1; echo "dp pytest rc=$?"; tail -3 $o/g1_pytest_dp.log
+timeout 250 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29617 bench.py --gpus 2 --steps 40 --warmup 10 --no-cpu-baseline --no-reference-cuda > $o/g1_bench_2gpu.json 2> $o/g1_bench_2gpu.err; echo "bench rc=$?"
+python -c "
+import json
+d=json.loads(open('$o/g1_bench_2gpu.json').read().strip().splitlines()[-1]); print('2gpu ms', round(d['ms_per_step'],4), 'img/s', round(d['value'],1), 'e2e', round(d['e2e']['value'],1))"

@@ -30,7 +30,8 @@ class UbConfig(C.Structure):
                 ("n_res_blocks", C.c_int), ("att_start_level", C.c_int), ("head_size", C.c_int),
                 ("gn_n_groups", C.c_int), ("n_timesteps", C.c_int), ("seed", C.c_ulonglong),
                 ("use_cuda_graph", C.c_int), ("compute_dinput", C.c_int), ("random_flip", C.c_int),
-                ("num_classes", C.c_int), ("ema_rate", C.c_float), ("resblock_updown", C.c_int)]
+                ("num_classes", C.c_int), ("ema_rate", C.c_float), ("resblock_updown", C.c_int),
+                ("use_scale_shift_norm", C.c_int)]
 
 
 UB_KINDS = ("conv_igemm", "wgrad_igemm", "groupnorm", "attention", "eltwise", "small", "optimizer")

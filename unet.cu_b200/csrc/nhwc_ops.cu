@@ -173,20 +173,32 @@ __device__ __forceinline__ void gn_channel_consts(const float* __restrict__ chsu
     bb = beta[c] - mean * a;
 }
 
+// use_scale_shift_norm (dev/resblock.py:243-247, ResBlockO): v = gn(x) * (1 + scale) + shift with a per-(image, channel)
+// scale / shift from the embedding projection, ss_b = this image's [scale (C) | shift (C)] row.  It is a GroupNorm with a
+// per-image affine: gamma_e = gamma * (1 + scale), beta_e = beta * (1 + scale) + shift.
+__device__ __forceinline__ void gn_scale_shift(const float* __restrict__ ss_b, int C, int c, float& a, float& bb) {
+    if (!ss_b) return;
+    const float sc = 1.f + ss_b[c];
+    a *= sc;
+    bb = bb * sc + ss_b[C + c];
+}
+
 // ------------------------------------------------------------------------------------------------ GN apply
 __global__ void gn_apply_kernel(const bf16* __restrict__ x, int ldx, const float* __restrict__ chsum,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C, int G,
                                 int silu, int C8, int rows, int ppb, bf16* __restrict__ y, int ldy,
-                                float* __restrict__ meanrstd) {
+                                float* __restrict__ meanrstd, const float* __restrict__ ss) {
     pdl_entry();
     extern __shared__ float sm[];  // sa[C], sb[C]
     float* sa = sm;
     float* sb = sm + C;
     const int b = blockIdx.y;
     const int cpg = C / G;
+    const float* ss_b = ss ? ss + size_t(b) * 2 * C : nullptr;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float r, mr, a, bb;
         gn_channel_consts(chsum + size_t(b) * C * 2, gamma, beta, C, cpg, HW, c, r, mr, a, bb);
+        gn_scale_shift(ss_b, C, c, a, bb);
         sa[c] = a, sb[c] = bb;
         if (meanrstd && blockIdx.x == 0 && (c % cpg) == 0) {
             meanrstd[(size_t(b) * G + c / cpg) * 2] = mr / r;
@@ -226,26 +238,28 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int ldx, const float
 }
 
 void gn_apply(const bf16* x, int ldx, const float* chsum, const float* gamma, const float* beta, int B, int HW, int C,
-              int G, int silu, bf16* y, int ldy, float* meanrstd, cudaStream_t st) {
+              int G, int silu, bf16* y, int ldy, float* meanrstd, cudaStream_t st, const float* ss) {
     RowMap m = make_rowmap(B, HW, C);
     m = make_rowmap(B, HW, C, rowmap_occupancy(gn_apply_kernel, m.threads, 2 * C * sizeof(float)));
     launch_pdl(gn_apply_kernel, dim3(dim3(m.nchunks, B)), dim3(m.threads), 2 * C * sizeof(float), st, 
-        x, ldx, chsum, gamma, beta, HW, C, G, silu, m.C8, m.rows, m.ppb, y, ldy, meanrstd);
+        x, ldx, chsum, gamma, beta, HW, C, G, silu, m.C8, m.rows, m.ppb, y, ldy, meanrstd, ss);
 }
 
 // ------------------------------------------------------------------------------------------------ GN backward
 __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ dy, int lddy,
                                     const float* __restrict__ chsum, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, int HW, int C, int G, int silu, int C8, int rows,
-                                    int ppb, float* __restrict__ S) {
+                                    int ppb, float* __restrict__ S, const float* __restrict__ ss) {
     pdl_entry();
     extern __shared__ float sm[];  // sa, sb, sr, smr : 4*C ; then scratch [2][rows][C]
     float *sa = sm, *sb = sm + C, *sr = sm + 2 * C, *smr = sm + 3 * C, *scr = sm + 4 * C;
     const int b = blockIdx.y;
     const int cpg = C / G;
+    const float* ss_b = ss ? ss + size_t(b) * 2 * C : nullptr;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float r, mr, a, bb;
         gn_channel_consts(chsum + size_t(b) * C * 2, gamma, beta, C, cpg, HW, c, r, mr, a, bb);
+        gn_scale_shift(ss_b, C, c, a, bb);
         sa[c] = a, sb[c] = bb, sr[c] = r, smr[c] = mr;
     }
     __syncthreads();
@@ -294,11 +308,11 @@ __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ x, int ldx, const b
 }
 
 void gn_bwd_stats(const bf16* x, int ldx, const bf16* dy, int lddy, const float* chsum, const float* gamma,
-                  const float* beta, int B, int HW, int C, int G, int silu, float* S, cudaStream_t st) {
+                  const float* beta, int B, int HW, int C, int G, int silu, float* S, cudaStream_t st, const float* ss) {
     RowMap m = make_rowmap(B, HW, C);
     m = make_rowmap(B, HW, C, rowmap_occupancy(gn_bwd_stats_kernel, m.threads, (4 + 2 * size_t(m.rows)) * C * sizeof(float)));
     launch_pdl(gn_bwd_stats_kernel, dim3(dim3(m.nchunks, B)), dim3(m.threads), (4 + 2 * size_t(m.rows)) * C * sizeof(float), st, 
-        x, ldx, dy, lddy, chsum, gamma, beta, HW, C, G, silu, m.C8, m.rows, m.ppb, S);
+        x, ldx, dy, lddy, chsum, gamma, beta, HW, C, G, silu, m.C8, m.rows, m.ppb, S, ss);
 }
 
 __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ dy, int lddy,
@@ -306,30 +320,41 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ x, int ldx, const b
                                     const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C,
                                     int G, int silu, int C8, int rows, int ppb, const bf16* __restrict__ add_in,
                                     int ldadd, bf16* __restrict__ dx, int lddx, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta, float* __restrict__ colsum_out) {
+                                    float* __restrict__ dbeta, float* __restrict__ colsum_out,
+                                    const float* __restrict__ ss, float* __restrict__ dss) {
     pdl_entry();
     // silu == 2: `dy` already holds dz = dL/d(gn(x)) (the producing dgrad conv applied silu' in its epilogue)
+    // ss / dss (scale-shift norm, see gn_scale_shift): the affine is per image; dss[b] = [dscale (C) | dshift (C)] with
+    // dscale = sum_pix dz * (gamma * xhat + beta) = gamma * S1 + beta * S0 and dshift = S0 (overwritten)
     extern __shared__ float sm[];  // sa, sb, sr, smr, sm1, sm2 : 6*C ; then scratch [rows][C]
     float *sa = sm, *sb = sm + C, *sr = sm + 2 * C, *smr = sm + 3 * C, *sm1 = sm + 4 * C, *sm2 = sm + 5 * C,
           *scr = sm + 6 * C;
     const int b = blockIdx.y;
     const int cpg = C / G;
     const float* Sb = S + size_t(b) * C * 2;
+    const float* ss_b = ss ? ss + size_t(b) * 2 * C : nullptr;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float r, mr, a, bb;
         gn_channel_consts(chsum + size_t(b) * C * 2, gamma, beta, C, cpg, HW, c, r, mr, a, bb);
+        gn_scale_shift(ss_b, C, c, a, bb);
         const int g0 = (c / cpg) * cpg;
         float m1 = 0.f, m2 = 0.f;
         for (int k = 0; k < cpg; ++k) {
-            m1 += gamma[g0 + k] * Sb[(g0 + k) * 2];
-            m2 += gamma[g0 + k] * Sb[(g0 + k) * 2 + 1];
+            const float ge = ss_b ? gamma[g0 + k] * (1.f + ss_b[g0 + k]) : gamma[g0 + k];
+            m1 += ge * Sb[(g0 + k) * 2];
+            m2 += ge * Sb[(g0 + k) * 2 + 1];
         }
         const float n = float(cpg) * float(HW);
-        sa[c] = a, sb[c] = bb, sr[c] = r, smr[c] = mr;  // a == gamma * rstd
+        sa[c] = a, sb[c] = bb, sr[c] = r, smr[c] = mr;  // a == gamma_e * rstd
         sm1[c] = r * m1 / n, sm2[c] = r * m2 / n;
         if (blockIdx.x == 0) {
-            atomicAdd(&dgamma[c], Sb[c * 2 + 1]);
-            atomicAdd(&dbeta[c], Sb[c * 2]);
+            const float sc = ss_b ? 1.f + ss_b[c] : 1.f;
+            atomicAdd(&dgamma[c], sc * Sb[c * 2 + 1]);
+            atomicAdd(&dbeta[c], sc * Sb[c * 2]);
+            if (dss) {
+                dss[size_t(b) * 2 * C + c] = gamma[c] * Sb[c * 2 + 1] + beta[c] * Sb[c * 2];
+                dss[size_t(b) * 2 * C + C + c] = Sb[c * 2];
+            }
         }
     }
     __syncthreads();
@@ -461,8 +486,13 @@ __global__ void __launch_bounds__(256, UB_GN_BWD_MINBLOCKS) gn_bwd_apply_dz_kern
 
 void gn_bwd_apply(const bf16* x, int ldx, const bf16* dy, int lddy, const float* chsum, const float* S,
                   const float* gamma, const float* beta, int B, int HW, int C, int G, int silu, const bf16* add_in,
-                  int ldadd, bf16* dx, int lddx, float* dgamma, float* dbeta, float* colsum_out, cudaStream_t st) {
+                  int ldadd, bf16* dx, int lddx, float* dgamma, float* dbeta, float* colsum_out, cudaStream_t st,
+                  const float* ss, float* dss) {
     RowMap m = make_rowmap(B, HW, C);
+    if (ss && silu != 1) {  // (the scale-shift affine exists only in the unfused kernel; the trainer never asks for this)
+        fprintf(stderr, "[unet_b200] gn_bwd_apply: scale-shift norm needs the unfused pass (silu == 1)\n");
+        return;
+    }
     if (silu != 1)
         m = make_rowmap(B, HW, C, rowmap_occupancy(gn_bwd_apply_dz_kernel, m.threads, (3 + size_t(m.rows)) * C * sizeof(float)));
     else
@@ -475,7 +505,7 @@ void gn_bwd_apply(const bf16* x, int ldx, const bf16* dy, int lddy, const float*
     }
     launch_pdl(gn_bwd_apply_kernel, dim3(dim3(m.nchunks, B)), dim3(m.threads), (6 + size_t(m.rows)) * C * sizeof(float), st, 
         x, ldx, dy, lddy, chsum, S, gamma, beta, HW, C, G, silu, m.C8, m.rows, m.ppb, add_in, ldadd, dx, lddx, dgamma,
-        dbeta, colsum_out);
+        dbeta, colsum_out, ss, dss);
 }
 
 // ------------------------------------------------------------------------------------------------ pooling etc.

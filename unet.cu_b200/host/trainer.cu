@@ -513,7 +513,8 @@ struct Builder {
     }
     bool use_bwd_hook(int C, int H, int W) const { return use_hooks(C, H, W) && H * W <= bwd_hook_max_hw(); }
     float* stats_buf(int C, int H, int W) { return use_hooks(C, H, W) ? zf32(size_t(B) * C * 2) : nullptr; }
-    GN gn_fwd(View x, View y, int silu) {
+    // ss (use_scale_shift_norm): per-image [scale | shift] rows applied after the normalisation (gn_scale_shift)
+    GN gn_fwd(View x, View y, int silu, const float* ss = nullptr) {
         GN g;
         g.w = take(x.C), g.b = take(x.C);
         const bool have = x.cs != nullptr;  // the producer's epilogue already accumulated the statistics
@@ -521,8 +522,8 @@ struct Builder {
         g.S = zf32(size_t(B) * x.C * 2);
         const int HW = x.H * x.W, Gn = c.gn_n_groups;
         float *gw = P(g.w), *gb = P(g.b), *cs = g.chsum;
-        const bool slab = !have && use_slab(x.C, x.H, x.W);
-        if (have && real()) {
+        const bool slab = !have && !ss && use_slab(x.C, x.H, x.W);
+        if (have && real() && !ss) {
             auto it = gn_finish.find(x.p);
             if (it != gn_finish.end()) {
                 auto pp = it->second;
@@ -545,7 +546,8 @@ struct Builder {
             else
                 F([=](cudaStream_t st) {
                     if (!have) gn_stats(xh.p, xh.ld, Bq, HW, xh.C, csh, st);
-                    gn_apply(xh.p, xh.ld, csh, gw, gb, Bq, HW, xh.C, Gn, silu, yh.p, yh.ld, nullptr, st);
+                    gn_apply(xh.p, xh.ld, csh, gw, gb, Bq, HW, xh.C, Gn, silu, yh.p, yh.ld, nullptr, st,
+                             mbf(const_cast<float*>(ss), h, size_t(2) * xh.C));
                 }, have ? 1 : 2, UB_KIND_NORM, 0, (have ? 2 : 3) * act_bytes(x.C, x.H, x.W) / nh);
         });
         return g;
@@ -557,11 +559,12 @@ struct Builder {
         ep.gn_x = x.p, ep.gn_ldx = x.ld, ep.gn_chsum = g.chsum, ep.gn_gamma = P(g.w), ep.gn_beta = P(g.b);
         ep.gn_S = g.S, ep.gn_silu = silu, ep.gn_groups = c.gn_n_groups;
     }
-    void gn_bwd(const GN& g, View x, View dy, int silu, View add_in, View dx, float* colsum_out, bool fused = false) {
-        fused = fused && use_bwd_hook(x.C, x.H, x.W);
+    void gn_bwd(const GN& g, View x, View dy, int silu, View add_in, View dx, float* colsum_out, bool fused = false,
+                const float* ss = nullptr, float* dss = nullptr) {
+        fused = fused && use_bwd_hook(x.C, x.H, x.W) && !ss;
         const int HW = x.H * x.W, Gn = c.gn_n_groups;
         float *gw = P(g.w), *gb = P(g.b), *cs = g.chsum, *S = g.S, *dgw = G(g.w), *dgb = G(g.b);
-        const bool slab = !fused && use_slab(x.C, x.H, x.W);
+        const bool slab = !fused && !ss && use_slab(x.C, x.H, x.W);
         const int mode = fused ? (silu ? 2 : 0) : silu;
         if (fused && real()) {
             auto it = gn_finish.find(dy.p);
@@ -587,9 +590,11 @@ struct Builder {
                 }, 1, UB_KIND_NORM, 0, (3 + (add_in.p ? 1 : 0)) * act_bytes(x.C, x.H, x.W) / nh);
             else
                 Bk([=](cudaStream_t st) {
-                    if (!fused) gn_bwd_stats(xh.p, xh.ld, dyh.p, dyh.ld, csh, gw, gb, Bq, HW, xh.C, Gn, silu, Sh, st);
+                    const float* ssh = mbf(const_cast<float*>(ss), h, size_t(2) * xh.C);
+                    float* dssh = mbf(dss, h, size_t(2) * xh.C);
+                    if (!fused) gn_bwd_stats(xh.p, xh.ld, dyh.p, dyh.ld, csh, gw, gb, Bq, HW, xh.C, Gn, silu, Sh, st, ssh);
                     gn_bwd_apply(xh.p, xh.ld, dyh.p, dyh.ld, csh, Sh, gw, gb, Bq, HW, xh.C, Gn, mode, ah.p, ah.ld, dxh.p,
-                                 dxh.ld, dgw, dgb, colh, st);
+                                 dxh.ld, dgw, dgb, colh, st, ssh, dssh);
                 }, fused ? 1 : 2, UB_KIND_NORM, 0, ((fused ? 3 : 5) + (add_in.p ? 1 : 0)) * act_bytes(x.C, x.H, x.W) / nh);
         });
     }
@@ -681,21 +686,27 @@ struct Builder {
             resample_fwd(x, xr, ud);
             a1 = a1r, x = xr;  // what conv1 and the (identity) skip connection see
         }
+        // use_scale_shift_norm (cfg.use_scale_shift_norm; dev/resblock.py:211,243-247 ResBlockO): the embedding projection
+        // has 2 * Cout outputs [scale | shift], nothing is added to conv1's output and GroupNorm 2 becomes
+        // gn(h) * (1 + scale) + shift -- a per-image affine inside the GroupNorm kernels (gn_scale_shift); its backward
+        // runs unfused (plain dgrad of conv2, statistics pass, apply pass that also writes dscale / dshift)
+        const bool ssn = c.use_scale_shift_norm != 0;
+        const int OCe = ssn ? 2 * Cout : Cout;
         const size_t w1 = take(size_t(Cout) * C * 9), b1 = take(Cout);
-        const size_t wl = take(size_t(Cout) * Cemb), bl = take(Cout);
+        const size_t wl = take(size_t(OCe) * Cemb), bl = take(OCe);
         View h1 = act(Cout, H, W);
         h1.cs = stats_buf(Cout, H, W);
-        float* embproj = f32(size_t(B) * Cout);
-        float* d_embproj = zf32(size_t(B) * Cout);
+        float* embproj = f32(size_t(B) * OCe);
+        float* d_embproj = zf32(size_t(B) * OCe);
         Packed p1 = pack(w1, Cout, C, 9);
         {
             ConvEpilogue ep;
-            ep.bias = P(b1), ep.rowvec = embproj, ep.out = h1.p, ep.ldo = h1.ld, ep.stats = h1.cs;
+            ep.bias = P(b1), ep.rowvec = ssn ? nullptr : embproj, ep.out = h1.p, ep.ldo = h1.ld, ep.stats = h1.cs;
             join_side_fwd();  // embproj comes from the time-embedding chain
             conv_op(true, {{a1.p, C, a1.ld, p1.wf, 9}}, H, W, Cout, ep);
         }
         View a2 = act(Cout, H, W);
-        GN g2 = gn_fwd(h1, a2, 1);
+        GN g2 = gn_fwd(h1, a2, 1, ssn ? embproj : nullptr);
         const size_t w2 = take(size_t(Cout) * Cout * 9), b2 = take(Cout);
         Packed p2 = pack(w2, Cout, Cout, 9);
         const bool proj = C != Cout;
@@ -721,10 +732,11 @@ struct Builder {
         }
         if (real()) {
             SmallLinear e{};
-            e.w = P(wl), e.b = P(bl), e.inp = T->semb, e.out = embproj, e.C = Cemb, e.OC = Cout, e.silu_in = 0;
-            e.dout = d_embproj, e.dw = G(wl), e.db = G(bl), e.db2 = G(b1), e.dinp = T->d_embact;
+            e.w = P(wl), e.b = P(bl), e.inp = T->semb, e.out = embproj, e.C = Cemb, e.OC = OCe, e.silu_in = 0;
+            // (without scale-shift, conv1's bias gradient equals the embedding projection's: h1 = conv1 + b1 + emb)
+            e.dout = d_embproj, e.dw = G(wl), e.db = G(bl), e.db2 = ssn ? nullptr : G(b1), e.dinp = T->d_embact;
             T->h_emb.push_back(e);
-            if (Cout > T->emb_max_oc) T->emb_max_oc = Cout;
+            if (OCe > T->emb_max_oc) T->emb_max_oc = OCe;
         }
         nd.out = out;
         nd.bwd = [=](View dout) -> View {
@@ -740,17 +752,21 @@ struct Builder {
             {
                 ConvEpilogue ep;
                 ep.out = da2.p, ep.ldo = da2.ld;
-                gn_hook(ep, g2, h1, 1);  // da2 receives dz = dL/d gn2(h1)
+                if (!ssn) gn_hook(ep, g2, h1, 1);  // da2 receives dz = dL/d gn2(h1)
                 conv_op(false, {{dout.p, Cout, dout.ld, p2.wd, 9}}, H, W, Cout, ep);
             }
             // GN2 + SiLU backward; per-image column sums of dh1 feed the embedding-projection backward
-            gn_bwd(g2, h1, da2, 1, View{}, dh1, d_embproj, true);
+            // (scale-shift: the apply pass writes [dscale | dshift] there instead)
+            if (ssn)
+                gn_bwd(g2, h1, da2, 1, View{}, dh1, nullptr, false, embproj, d_embproj);
+            else
+                gn_bwd(g2, h1, da2, 1, View{}, dh1, d_embproj, true);
             emb_lo = blk < emb_lo ? blk : emb_lo, emb_hi = blk + 1 > emb_hi ? blk + 1 : emb_hi;  // batched, see emb_flush
             if (blk == 0) {  // the last embedding gradient of the step: finish the embedding path on the branch now
                 emb_flush();
                 time_mlp_bwd();
             }
-            wgrad_op(dh1, a1, C, Cout, 9, G(w1));
+            wgrad_op(dh1, a1, C, Cout, 9, G(w1), ssn ? G(b1) : nullptr);  // (+ conv1's bias gradient when it is its own)
             if (ud) {
                 // conv1 ran on the resampled tensor: its dgrad is plain (no gn-bwd hook -- GroupNorm 1 lives at the input
                 // resolution), both gradients go back through the resampling, GroupNorm 1 + SiLU backward run unfused
@@ -1258,8 +1274,8 @@ static int validate_config(const UbConfig& c) {
         set_err("H, W must be divisible by 2^(n_levels-1)");
         return UB_ERR_SHAPE;
     }
-    if (c.resblock_updown != 0 && c.resblock_updown != 1) {
-        set_err("bad config: resblock_updown must be 0 or 1");
+    if ((c.resblock_updown != 0 && c.resblock_updown != 1) || (c.use_scale_shift_norm != 0 && c.use_scale_shift_norm != 1)) {
+        set_err("bad config: resblock_updown / use_scale_shift_norm must be 0 or 1");
         return UB_ERR_SHAPE;
     }
     if (c.num_classes < 0 || !(c.ema_rate >= 0.f && c.ema_rate < 1.f)) {
