@@ -250,6 +250,10 @@ typedef struct {
     int use_scale_shift_norm; /* 1: FiLM-like conditioning (dev/unet.py:146 `use_scale_shift_norm`, dev/resblock.py:211,
                             243-247): every ResBlock's embedding projection has 2*Cout outputs [scale | shift] and the second
                             GroupNorm computes gn(h) * (1 + scale) + shift instead of gn(h + emb); 0 */
+    float dropout;       /* > 0: dropout with this probability between SiLU and the second conv of every ResBlock
+                            (guided-diffusion's out_layers; the reference carries the option commented out,
+                            dev/resblock.py:51,61, dev/unet.py:116,140) in training steps; predict / sample run without.
+                            Masks are Philox draws keyed by (seed, step, block, element), never stored; 0 */
 } UbConfig;
 
 void ub_default_config(UbConfig* cfg);
@@ -282,6 +286,9 @@ int ub_trainer_save_ema(UbTrainer* t, const char* path); /* parameters-only .bin
 /* class labels y (B ints in [0, num_classes)) of the batch(es) that follow (cfg.num_classes > 0, dev/unet.py:301-303);
  * used by forward_backward / train_step / predict / sample until set again */
 int ub_trainer_set_labels(UbTrainer* t, const int* labels_host, size_t n);
+/* the dropout mask (0 / 1 bytes, B x H x W x C in NHWC order) the LAST training step applied in ResBlock `block`
+ * (forward order), regenerated from its Philox key -- for parity checks (cfg.dropout > 0) */
+int ub_trainer_get_dropout_mask(UbTrainer* t, int block, unsigned char* host, size_t n);
 int ub_trainer_get_output(UbTrainer* t, float* host, size_t n); /* last forward's eps prediction (B,C_out,H,W) */
 /* the flip decisions (0 / 1 per image) the last step took, when cfg.random_flip is set */
 int ub_trainer_get_flips(UbTrainer* t, int* host, size_t n);

@@ -10,6 +10,11 @@ modules (/root/reference/dev/unet.py, dev/resblock.py, train_unet.py) when the r
 tests/golden/ that oracle/gen_golden.py produced from the reference itself.
 
 Each function cites the reference lines it follows (paths under /root/reference).
+
+One restated feature has no reference implementation to pin against and says so: dropout (UNetConfig.dropout) is
+commented out in the reference (dev/resblock.py:51,61, dev/unet.py:116,140) -- PARITY UNPINNED for it; the restatement is
+nn.Dropout's training-mode arithmetic with a given keep-mask.  Everything else is pinned (class labels, resblock_updown:
+the reference's UNetModel; use_scale_shift_norm: the reference's ResBlockO).
 """
 from __future__ import annotations
 
@@ -43,6 +48,8 @@ class UNetConfig:
     num_classes: int = 0               # > 0: class-conditional, label_emb = nn.Embedding(num_classes, 4*mc) (dev/unet.py:174-175)
     resblock_updown: bool = False      # ResBlock(down=True / up=True) instead of Downsample / Upsample (dev/unet.py:147,205-222,271-284)
     use_scale_shift_norm: bool = False # FiLM-like conditioning in every ResBlock (dev/unet.py:146, dev/resblock.py:211,243-247)
+    dropout: float = 0.0               # Dropout(p) between SiLU and conv2 of every ResBlock (commented out in the reference:
+                                       # dev/resblock.py:51,61; guided-diffusion's out_layers = GroupNorm, SiLU, Dropout, conv)
 
     @property
     def emb_channels(self) -> int:
@@ -290,7 +297,8 @@ def upsample2(x):
     return x.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
 
 
-def resblock(x, emb, P: Dict[str, torch.Tensor], prefix: str, groups=32, updown: str | None = None):
+def resblock(x, emb, P: Dict[str, torch.Tensor], prefix: str, groups=32, updown: str | None = None,
+             drop_mask: torch.Tensor | None = None, drop_p: float = 0.0):
     """dev/resblock.py:107-160, train_unet.cu:2213-2287 (up = down = 0 in the default U-Net, train_unet.cu:4278).
     updown = 'down' / 'up' (dev/resblock.py:78-86, 125-128): h_upd / x_upd resample the main path between SiLU and conv1
     and the skip path -- average pool 2x2 (Downsample, dev/resblock.py:34-43) or nearest x2 (Upsample, :25-32)."""
@@ -305,7 +313,10 @@ def resblock(x, emb, P: Dict[str, torch.Tensor], prefix: str, groups=32, updown:
         h = groupnorm(h, P[prefix + '.gn2.weight'], P[prefix + '.gn2.bias'], groups) * (1 + scale) + shift
     else:
         h = groupnorm(h + e[:, :, None, None], P[prefix + '.gn2.weight'], P[prefix + '.gn2.bias'], groups)
-    h = conv3x3(silu(h), P[prefix + '.cv3_2.weight'], P[prefix + '.cv3_2.bias'])
+    h = silu(h)
+    if drop_mask is not None:   # nn.Dropout(p) in training mode with a GIVEN keep-mask: kept values are scaled by 1 / (1 - p)
+        h = h * drop_mask.to(h.dtype) / (1.0 - drop_p)
+    h = conv3x3(h, P[prefix + '.cv3_2.weight'], P[prefix + '.cv3_2.bias'])
     if (prefix + '.skip_connection.weight') in P:
         x = conv1x1(x, P[prefix + '.skip_connection.weight'], P[prefix + '.skip_connection.bias'])
     return x + h
@@ -335,7 +346,7 @@ def attention_block(x, P, prefix: str, head_size=32, groups=32):
 
 
 def unet_forward(cfg: UNetConfig, P: Dict[str, torch.Tensor], x: torch.Tensor, t: torch.Tensor,
-                 y: torch.Tensor | None = None) -> torch.Tensor:
+                 y: torch.Tensor | None = None, drop_masks=None) -> torch.Tensor:
     """dev/unet.py:283-319, train_unet.cu:4335-4416.  `y` (B,) int64 class labels iff cfg.num_classes (dev/unet.py:291-303)."""
     assert (y is not None) == bool(cfg.num_classes), "must specify y if and only if the model is class-conditional"
     emb = timestep_embedding(t, cfg.model_channels, cfg.max_period).to(x.dtype)
@@ -345,15 +356,18 @@ def unet_forward(cfg: UNetConfig, P: Dict[str, torch.Tensor], x: torch.Tensor, t
         emb = emb + P['label_emb.weight'][y.long()]
     hs: List[torch.Tensor] = []
     h = x
+    # drop_masks: one keep-mask (B, C, H, W) per ResBlock in forward order (training with cfg.dropout; None = inference)
+    dm = iter(drop_masks) if drop_masks is not None else None
     for l in build_layers(cfg):
         if l.kind in ('linear', 'embed'):
             continue
         if l.kind == 'conv3':
             h = conv3x3(h, P[l.name + '.weight'], P[l.name + '.bias'])
         elif l.kind == 'res':
-            h = resblock(h, emb, P, l.name, cfg.gn_groups)
+            h = resblock(h, emb, P, l.name, cfg.gn_groups, drop_mask=next(dm) if dm else None, drop_p=cfg.dropout)
         elif l.kind in ('res_down', 'res_up'):
-            h = resblock(h, emb, P, l.name, cfg.gn_groups, updown=l.kind[4:])
+            h = resblock(h, emb, P, l.name, cfg.gn_groups, updown=l.kind[4:], drop_mask=next(dm) if dm else None,
+                         drop_p=cfg.dropout)
         elif l.kind == 'attn':
             h = attention_block(h, P, l.name, cfg.head_size, cfg.gn_groups)
         elif l.kind == 'down':
@@ -469,12 +483,12 @@ def perturb_zero_params(cfg: UNetConfig, flat: torch.Tensor, seed: int = 5, std:
     return flat
 
 
-def train_step_grads(cfg: UNetConfig, flat: torch.Tensor, x0, t, noise, y=None):
+def train_step_grads(cfg: UNetConfig, flat: torch.Tensor, x0, t, noise, y=None, drop_masks=None):
     """One forward + backward of the training step (train_unet.cu:5019-5036): returns loss, out, grads(flat)."""
     flat = flat.detach().clone().requires_grad_(True)
     P = unflatten_params(cfg, flat)
     x_t = q_sample(x0.to(flat.dtype), t, noise.to(flat.dtype))
-    out = unet_forward(cfg, P, x_t, t.to(flat.dtype), y)
+    out = unet_forward(cfg, P, x_t, t.to(flat.dtype), y, drop_masks)
     loss = mse_loss(out, noise.to(flat.dtype))
     loss.backward()
     return loss.detach(), out.detach(), flat.grad.detach()

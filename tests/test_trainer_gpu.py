@@ -580,3 +580,68 @@ def test_scale_shift_norm_matches_oracle(ub, oracle, kw, okw, B):
     l2 = tr.train_step(x0.numpy(), t.numpy(), noise.numpy(), lr=1e-4)   # the captured-graph path runs too
     assert np.isfinite(l2)
     tr.close()
+
+
+def _resblock_shapes(O, cfg):
+    """(C, H, W) of every ResBlock's second-GroupNorm tensor, forward order (= the dropout masks' shapes)."""
+    out = []
+    for l in O.build_layers(cfg):
+        if l.kind.startswith("res"):
+            lev = l.level + (1 if l.kind == "res_down" else (-1 if l.kind == "res_up" else 0))
+            out.append((l.cout, cfg.H >> lev, cfg.W >> lev))
+    return out
+
+
+@pytest.mark.parametrize("kw,okw,B", [
+    (dict(dropout=0.1), dict(dropout=0.1), 2),
+    (dict(dropout=0.25, use_scale_shift_norm=1, resblock_updown=1, H=32, W=32, channel_mult=(1, 2, 2), att_start_level=1,
+          n_res_blocks=1),
+     dict(dropout=0.25, use_scale_shift_norm=True, resblock_updown=True, H=32, W=32, channel_mult=(1, 2, 2),
+          attn_start_level=1, num_res_blocks=1), 3),
+])
+def test_dropout_matches_oracle_with_the_device_masks(ub, oracle, kw, okw, B):
+    """dropout between SiLU and conv2 of every ResBlock (guided-diffusion's out_layers; the
+    reference carries the option commented out, dev/resblock.py:51,61 -- PARITY UNPINNED against the reference for this
+    one feature: the oracle restates nn.Dropout's training-mode arithmetic, keep / (1 - p), with the masks the device
+    drew).  The masks are Philox draws that are never stored; they are regenerated for the check, must keep ~(1 - p) of the
+    elements, must differ between blocks and steps, and predict() must run without dropout."""
+    O = oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.UNetConfig(**okw)
+    p = cfg.dropout
+    flat = O.perturb_zero_params(cfg, O.flatten_params(cfg, O.init_params(cfg, seed=0)))
+    x0, t, noise = O.synthetic_batch(cfg, B)
+    tr = ub.Trainer(B=B, **kw)
+    tr.set_params(flat.numpy())
+    loss = tr.forward_backward(x0.numpy(), t.numpy(), noise.numpy())
+    out, g = tr.get_output(), tr.get_grads()
+    shapes = _resblock_shapes(O, cfg)
+    masks = [tr.get_dropout_mask(i, *s) for i, s in enumerate(shapes)]
+    total = sum(m.size for m in masks)
+    kept = sum(int(m.sum()) for m in masks)
+    assert abs(kept / total - (1 - p)) < 5e-3, kept / total
+    assert all(set(np.unique(m)) <= {0, 1} for m in masks)
+    same_shape = [(a, b) for i, a in enumerate(masks) for b in masks[i + 1:] if a.shape == b.shape]
+    assert same_shape and all((a != b).mean() > 0.5 * p for a, b in same_shape)      # blocks draw different masks
+    loss_ref, out_ref, g_ref = O.train_step_grads(cfg, flat, x0, t, noise,
+                                                  drop_masks=[torch.from_numpy(m) for m in masks])
+    assert abs(loss - float(loss_ref)) <= 2e-3 * float(loss_ref)
+    assert np.abs(out - out_ref.numpy()).max() <= 3e-2 * np.abs(out_ref.numpy()).max()
+    check_grads(O, cfg, g, g_ref.numpy(), "dropout " + str(kw))
+    # without the masks the oracle is measurably elsewhere (the check above is not vacuous)
+    _, _, g_nodrop = O.train_step_grads(cfg, flat, x0, t, noise)
+    gap = float(np.linalg.norm(g_ref.numpy() - g_nodrop.numpy()) / np.linalg.norm(g_ref.numpy()))
+    print(f"[dropout] oracle gradient with vs without the masks: rel-L2 {gap:.3f}")
+    assert gap > 3 * 2e-2, gap     # several times the global gradient bound of check_grads
+    # inference: no dropout
+    xt = O.q_sample(x0, t, noise)
+    with torch.no_grad():
+        o_inf = O.unet_forward(cfg, O.unflatten_params(cfg, flat), xt, t).numpy()
+    assert np.abs(tr.predict(xt.numpy(), t.numpy()) - o_inf).max() <= 3e-2 * np.abs(o_inf).max()
+    # next step (captured graph path): other masks
+    tr.update(lr=1e-4)
+    l2 = tr.train_step(x0.numpy(), t.numpy(), noise.numpy(), lr=1e-4)
+    assert np.isfinite(l2)
+    m2 = tr.get_dropout_mask(0, *shapes[0])
+    assert (m2 != masks[0]).mean() > 0.5 * p
+    tr.close()

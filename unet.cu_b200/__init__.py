@@ -31,7 +31,7 @@ class UbConfig(C.Structure):
                 ("gn_n_groups", C.c_int), ("n_timesteps", C.c_int), ("seed", C.c_ulonglong),
                 ("use_cuda_graph", C.c_int), ("compute_dinput", C.c_int), ("random_flip", C.c_int),
                 ("num_classes", C.c_int), ("ema_rate", C.c_float), ("resblock_updown", C.c_int),
-                ("use_scale_shift_norm", C.c_int)]
+                ("use_scale_shift_norm", C.c_int), ("dropout", C.c_float)]
 
 
 UB_KINDS = ("conv_igemm", "wgrad_igemm", "groupnorm", "attention", "eltwise", "small", "optimizer")
@@ -79,6 +79,7 @@ def _declare(L: C.CDLL) -> None:
     L.ub_read_checkpoint_header.argtypes = [C.c_char_p, C.POINTER(UbConfig)]
     L.ub_trainer_save_ema.argtypes = [vp, C.c_char_p]
     L.ub_trainer_set_labels.argtypes = [vp, vp, C.c_size_t]
+    L.ub_trainer_get_dropout_mask.argtypes = [vp, i, vp, C.c_size_t]
     for n in ("set_params", "get_params", "get_grads", "get_output", "get_dinput", "get_ema", "set_ema"):
         getattr(L, "ub_trainer_" + n).argtypes = [vp, fp, C.c_size_t]
     L.ub_trainer_forward_backward.argtypes = [vp, fp, fp, fp, C.POINTER(C.c_float)]
@@ -191,6 +192,12 @@ class Trainer:
         """Class labels of the batches that follow (cfg.num_classes > 0; `y` of UNetModel.forward, dev/unet.py:301-303)."""
         y = np.ascontiguousarray(y, dtype=np.int32).reshape(-1)
         check(lib().ub_trainer_set_labels(self._h, y.ctypes.data_as(C.c_void_p), y.size), "set_labels")
+
+    def get_dropout_mask(self, block: int, C_: int, H: int, W: int) -> np.ndarray:
+        """Keep-mask (B, C, H, W) of 0 / 1 the last training step applied in ResBlock `block` (cfg.dropout > 0)."""
+        out = np.empty((self.cfg.B, H, W, C_), dtype=np.uint8)
+        check(lib().ub_trainer_get_dropout_mask(self._h, block, out.ctypes.data_as(C.c_void_p), out.size), "dropout mask")
+        return np.ascontiguousarray(out.transpose(0, 3, 1, 2))
 
     def get_dinput(self):
         c = self.cfg

@@ -173,6 +173,53 @@ __device__ __forceinline__ void gn_channel_consts(const float* __restrict__ chsu
     bb = beta[c] - mean * a;
 }
 
+// ---- dropout mask (DropArgs, nhwc_ops.cuh): Philox4x32-10, the same round function as the diffusion draws (misc_ops.cu)
+__device__ __forceinline__ uint4 drop_philox(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+// multipliers (0 or 1 / (1 - p)) of the 8 consecutive elements starting at linear NHWC index e0 (a multiple of 8)
+__device__ __forceinline__ void drop_mult8(const DropArgs& d, float p, unsigned step, size_t e0, float (&m)[8]) {
+    const uint32_t thresh = uint32_t(fminf(p * 4294967296.f, 4294967040.f));
+    const float keep = 1.f / (1.f - p);
+    const uint2 key = make_uint2(d.ctl[2], d.ctl[3] ^ step);
+    const uint64_t c0 = e0 >> 2;
+    const uint4 r0 = drop_philox(make_uint4(uint32_t(c0), uint32_t(c0 >> 32), 0xD0u, d.layer), key);
+    const uint4 r1 = drop_philox(make_uint4(uint32_t(c0 + 1), uint32_t((c0 + 1) >> 32), 0xD0u, d.layer), key);
+    const uint32_t u[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = u[i] < thresh ? 0.f : keep;
+}
+__global__ void dropout_set_ctl_kernel(unsigned* ctl, float p, unsigned long long seed, const int* __restrict__ step_dev) {
+    pdl_entry();
+    if (threadIdx.x == 0)
+        ctl[0] = __float_as_uint(p), ctl[1] = unsigned(*step_dev), ctl[2] = unsigned(seed), ctl[3] = unsigned(seed >> 32);
+}
+void dropout_set_ctl(unsigned* ctl, float p, unsigned long long seed, const int* step_dev, cudaStream_t st) {
+    launch_pdl(dropout_set_ctl_kernel, dim3(1), dim3(32), 0, st, ctl, p, seed, step_dev);
+}
+__global__ void dropout_mask_kernel(DropArgs d, float p, size_t n8, unsigned char* __restrict__ out) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    float m[8];
+    drop_mult8(d, p, d.ctl[1], i * 8, m);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out[i * 8 + k] = m[k] != 0.f;
+}
+void dropout_mask(const unsigned* ctl, float p, unsigned layer, size_t n, unsigned char* out, cudaStream_t st) {
+    DropArgs d;
+    d.ctl = ctl, d.layer = layer;
+    dropout_mask_kernel<<<unsigned((n / 8 + 255) / 256), 256, 0, st>>>(d, p, n / 8, out);
+}
+
 // use_scale_shift_norm (dev/resblock.py:243-247, ResBlockO): v = gn(x) * (1 + scale) + shift with a per-(image, channel)
 // scale / shift from the embedding projection, ss_b = this image's [scale (C) | shift (C)] row.  It is a GroupNorm with a
 // per-image affine: gamma_e = gamma * (1 + scale), beta_e = beta * (1 + scale) + shift.
@@ -187,9 +234,11 @@ __device__ __forceinline__ void gn_scale_shift(const float* __restrict__ ss_b, i
 __global__ void gn_apply_kernel(const bf16* __restrict__ x, int ldx, const float* __restrict__ chsum,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C, int G,
                                 int silu, int C8, int rows, int ppb, bf16* __restrict__ y, int ldy,
-                                float* __restrict__ meanrstd, const float* __restrict__ ss) {
+                                float* __restrict__ meanrstd, const float* __restrict__ ss, DropArgs drop) {
     pdl_entry();
     extern __shared__ float sm[];  // sa[C], sb[C]
+    const float drop_p = drop.ctl ? __uint_as_float(drop.ctl[0]) : 0.f;
+    const unsigned drop_step = drop.ctl ? drop.ctl[1] : 0u;
     float* sa = sm;
     float* sb = sm + C;
     const int b = blockIdx.y;
@@ -232,25 +281,33 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int ldx, const float
                 const float z = f[i] * a[i] + bb[i];
                 f[i] = silu ? silu_f(z) : z;
             }
+            if (drop_p > 0.f) {  // y = dropout(act(gn(x)))
+                float dm[8];
+                drop_mult8(drop, drop_p, drop_step, (size_t(b) * HW + pp) * C + j * 8, dm);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] *= dm[i];
+            }
             st8(yb + size_t(pp) * ldy, f);
         }
     }
 }
 
 void gn_apply(const bf16* x, int ldx, const float* chsum, const float* gamma, const float* beta, int B, int HW, int C,
-              int G, int silu, bf16* y, int ldy, float* meanrstd, cudaStream_t st, const float* ss) {
+              int G, int silu, bf16* y, int ldy, float* meanrstd, cudaStream_t st, const float* ss, DropArgs drop) {
     RowMap m = make_rowmap(B, HW, C);
     m = make_rowmap(B, HW, C, rowmap_occupancy(gn_apply_kernel, m.threads, 2 * C * sizeof(float)));
     launch_pdl(gn_apply_kernel, dim3(dim3(m.nchunks, B)), dim3(m.threads), 2 * C * sizeof(float), st, 
-        x, ldx, chsum, gamma, beta, HW, C, G, silu, m.C8, m.rows, m.ppb, y, ldy, meanrstd, ss);
+        x, ldx, chsum, gamma, beta, HW, C, G, silu, m.C8, m.rows, m.ppb, y, ldy, meanrstd, ss, drop);
 }
 
 // ------------------------------------------------------------------------------------------------ GN backward
 __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ dy, int lddy,
                                     const float* __restrict__ chsum, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, int HW, int C, int G, int silu, int C8, int rows,
-                                    int ppb, float* __restrict__ S, const float* __restrict__ ss) {
+                                    int ppb, float* __restrict__ S, const float* __restrict__ ss, DropArgs drop) {
     pdl_entry();
+    const float drop_p = drop.ctl ? __uint_as_float(drop.ctl[0]) : 0.f;
+    const unsigned drop_step = drop.ctl ? drop.ctl[1] : 0u;
     extern __shared__ float sm[];  // sa, sb, sr, smr : 4*C ; then scratch [2][rows][C]
     float *sa = sm, *sb = sm + C, *sr = sm + 2 * C, *smr = sm + 3 * C, *scr = sm + 4 * C;
     const int b = blockIdx.y;
@@ -288,6 +345,12 @@ __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ x, int ldx, const b
             float f[8], d[8];
             unpack8(vx[u], f);
             unpack8(vd[u], d);  // zero-filled when out of range: contributes nothing
+            if (drop_p > 0.f && p + u * rows < p1) {  // dy is the gradient of the dropped-out activation
+                float dm[8];
+                drop_mult8(drop, drop_p, drop_step, (size_t(b) * HW + p + u * rows) * C + j * 8, dm);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) d[i] *= dm[i];
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 float dz = d[i];
@@ -308,11 +371,12 @@ __global__ void gn_bwd_stats_kernel(const bf16* __restrict__ x, int ldx, const b
 }
 
 void gn_bwd_stats(const bf16* x, int ldx, const bf16* dy, int lddy, const float* chsum, const float* gamma,
-                  const float* beta, int B, int HW, int C, int G, int silu, float* S, cudaStream_t st, const float* ss) {
+                  const float* beta, int B, int HW, int C, int G, int silu, float* S, cudaStream_t st, const float* ss,
+                  DropArgs drop) {
     RowMap m = make_rowmap(B, HW, C);
     m = make_rowmap(B, HW, C, rowmap_occupancy(gn_bwd_stats_kernel, m.threads, (4 + 2 * size_t(m.rows)) * C * sizeof(float)));
     launch_pdl(gn_bwd_stats_kernel, dim3(dim3(m.nchunks, B)), dim3(m.threads), (4 + 2 * size_t(m.rows)) * C * sizeof(float), st, 
-        x, ldx, dy, lddy, chsum, gamma, beta, HW, C, G, silu, m.C8, m.rows, m.ppb, S, ss);
+        x, ldx, dy, lddy, chsum, gamma, beta, HW, C, G, silu, m.C8, m.rows, m.ppb, S, ss, drop);
 }
 
 __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ dy, int lddy,
@@ -321,8 +385,10 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ x, int ldx, const b
                                     int G, int silu, int C8, int rows, int ppb, const bf16* __restrict__ add_in,
                                     int ldadd, bf16* __restrict__ dx, int lddx, float* __restrict__ dgamma,
                                     float* __restrict__ dbeta, float* __restrict__ colsum_out,
-                                    const float* __restrict__ ss, float* __restrict__ dss) {
+                                    const float* __restrict__ ss, float* __restrict__ dss, DropArgs drop) {
     pdl_entry();
+    const float drop_p = drop.ctl ? __uint_as_float(drop.ctl[0]) : 0.f;
+    const unsigned drop_step = drop.ctl ? drop.ctl[1] : 0u;
     // silu == 2: `dy` already holds dz = dL/d(gn(x)) (the producing dgrad conv applied silu' in its epilogue)
     // ss / dss (scale-shift norm, see gn_scale_shift): the affine is per image; dss[b] = [dscale (C) | dshift (C)] with
     // dscale = sum_pix dz * (gamma * xhat + beta) = gamma * S1 + beta * S0 and dshift = S0 (overwritten)
@@ -388,6 +454,12 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ x, int ldx, const b
             unpack8(vx[u], f);
             unpack8(vd[u], d);
             unpack8(va[u], o);
+            if (drop_p > 0.f) {
+                float dm[8];
+                drop_mult8(drop, drop_p, drop_step, (img + pp) * C + j * 8, dm);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) d[i] *= dm[i];
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 float dz = d[i];
@@ -487,9 +559,9 @@ __global__ void __launch_bounds__(256, UB_GN_BWD_MINBLOCKS) gn_bwd_apply_dz_kern
 void gn_bwd_apply(const bf16* x, int ldx, const bf16* dy, int lddy, const float* chsum, const float* S,
                   const float* gamma, const float* beta, int B, int HW, int C, int G, int silu, const bf16* add_in,
                   int ldadd, bf16* dx, int lddx, float* dgamma, float* dbeta, float* colsum_out, cudaStream_t st,
-                  const float* ss, float* dss) {
+                  const float* ss, float* dss, DropArgs drop) {
     RowMap m = make_rowmap(B, HW, C);
-    if (ss && silu != 1) {  // (the scale-shift affine exists only in the unfused kernel; the trainer never asks for this)
+    if ((ss || drop.ctl) && silu != 1) {  // (the scale-shift affine exists only in the unfused kernel; the trainer never asks for this)
         fprintf(stderr, "[unet_b200] gn_bwd_apply: scale-shift norm needs the unfused pass (silu == 1)\n");
         return;
     }
@@ -505,7 +577,7 @@ void gn_bwd_apply(const bf16* x, int ldx, const bf16* dy, int lddy, const float*
     }
     launch_pdl(gn_bwd_apply_kernel, dim3(dim3(m.nchunks, B)), dim3(m.threads), (6 + size_t(m.rows)) * C * sizeof(float), st, 
         x, ldx, dy, lddy, chsum, S, gamma, beta, HW, C, G, silu, m.C8, m.rows, m.ppb, add_in, ldadd, dx, lddx, dgamma,
-        dbeta, colsum_out, ss, dss);
+        dbeta, colsum_out, ss, dss, drop);
 }
 
 // ------------------------------------------------------------------------------------------------ pooling etc.

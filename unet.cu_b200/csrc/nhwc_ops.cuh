@@ -13,27 +13,41 @@ typedef __nv_bfloat16 bf16;
 // one-time kernel attribute setup (opt-in shared memory); call before graph capture
 void nhwc_ops_init();
 
+// ---- dropout behind a GroupNorm + SiLU (guided-diffusion's ResBlock out_layers: GroupNorm, SiLU, Dropout(p), conv; the
+//      reference carries the option but has it commented out, dev/resblock.py:51,61, dev/unet.py:116,140).  The mask is
+//      never stored: forward and backward regenerate it from Philox4x32-10 with counter = element index / 4 (NHWC order),
+//      stream word = layer and key = (seed, step).  ctl (device) = {p as float bits, step, seed lo, seed hi}: written at
+//      the start of every step (p = 0 for inference), so one captured graph serves all steps.  ctl == nullptr: no dropout.
+struct DropArgs {
+    const unsigned* ctl = nullptr;
+    unsigned layer = 0;
+};
+void dropout_set_ctl(unsigned* ctl, float p, unsigned long long seed, const int* step_dev, cudaStream_t st);
+// mask (0 / 1 bytes, NHWC element order) of `layer` for the (seed, step) recorded in ctl, with the drop probability p given here
+void dropout_mask(const unsigned* ctl, float p, unsigned layer, size_t n, unsigned char* out, cudaStream_t st);
+
 // ---- GroupNorm (+ optional SiLU), replaces groupnorm_forward/backward + silu_forward/backward
 //      (/root/reference/train_unet.cu:1768-1991, :305-351).
 // chsum: [B][C][2] fp32 per-(image, channel) sum and sum of squares (must be zero on entry to gn_stats).
 void gn_stats(const bf16* x, int ldx, int B, int HW, int C, float* chsum, cudaStream_t st);
 // y = act(gn(x)); also writes meanrstd[B][G][2] if non-null.
 void gn_apply(const bf16* x, int ldx, const float* chsum, const float* gamma, const float* beta, int B, int HW, int C,
-              int G, int silu, bf16* y, int ldy, float* meanrstd, cudaStream_t st, const float* ss = nullptr);
+              int G, int silu, bf16* y, int ldy, float* meanrstd, cudaStream_t st, const float* ss = nullptr,
+              DropArgs drop = DropArgs());
 // ss (optional, use_scale_shift_norm, dev/resblock.py:243-247): [B][2C] fp32, per image [scale (C) | shift (C)];
 // the normalised value becomes gn(x) * (1 + scale) + shift before the activation.  gn_bwd_stats / gn_bwd_apply take the
 // same pointer; gn_bwd_apply (unfused, silu == 1) additionally writes dss [B][2C] = [dscale | dshift].
 // Backward pass 1: S[B][C][2] = per-(image,channel) sums of dz and dz*xhat (must be zero on entry).
 void gn_bwd_stats(const bf16* x, int ldx, const bf16* dy, int lddy, const float* chsum, const float* gamma,
                   const float* beta, int B, int HW, int C, int G, int silu, float* S, cudaStream_t st,
-                  const float* ss = nullptr);
+                  const float* ss = nullptr, DropArgs drop = DropArgs());
 // Backward pass 2: dx = gn_bwd(dy) [+ add_in]; dgamma/dbeta += (atomic); colsum_out[B][C] += sum_pix dx (optional).
 // silu: 0 = no activation, 1 = SiLU follows the norm (dy is dL/d silu(gn(x))), 2 = SiLU follows the norm and dy is
 // already dL/d gn(x) (the dgrad conv that produced it applied silu' in its epilogue, see epilogue.cuh).
 void gn_bwd_apply(const bf16* x, int ldx, const bf16* dy, int lddy, const float* chsum, const float* S,
                   const float* gamma, const float* beta, int B, int HW, int C, int G, int silu, const bf16* add_in,
                   int ldadd, bf16* dx, int lddx, float* dgamma, float* dbeta, float* colsum_out, cudaStream_t st,
-                  const float* ss = nullptr, float* dss = nullptr);
+                  const float* ss = nullptr, float* dss = nullptr, DropArgs drop = DropArgs());
 
 // ---- single-pass GroupNorm (csrc/gn_slab.cu): statistics + normalisation (+SiLU) in ONE kernel, the slab (image, whole
 //      groups of channels) held in registers in between: 1R + 1W forward, 2R (+1R) + 1W backward.  Return -1 when the

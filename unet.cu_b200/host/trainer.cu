@@ -137,6 +137,13 @@ struct UbTrainer {
     // cfg.num_classes > 0: class labels of the current batch (ub_trainer_set_labels) and the label-embedding table
     int* labels = nullptr;
     size_t label_w_off = 0;
+    // cfg.dropout > 0: {p bits, step, seed} read by the GroupNorm kernels that regenerate the masks (DropArgs), and the
+    // (C, H, W) of every ResBlock's dropped-out tensor (ub_trainer_get_dropout_mask)
+    unsigned* drop_ctl = nullptr;
+    struct DropInfo {
+        int C, H, W;
+    };
+    std::vector<DropInfo> drop_layers;
     std::vector<ParamRef> tensors;  // every parameter tensor in order
     // everything else lives in one bump arena
     DeviceArena arena;
@@ -514,7 +521,7 @@ struct Builder {
     bool use_bwd_hook(int C, int H, int W) const { return use_hooks(C, H, W) && H * W <= bwd_hook_max_hw(); }
     float* stats_buf(int C, int H, int W) { return use_hooks(C, H, W) ? zf32(size_t(B) * C * 2) : nullptr; }
     // ss (use_scale_shift_norm): per-image [scale | shift] rows applied after the normalisation (gn_scale_shift)
-    GN gn_fwd(View x, View y, int silu, const float* ss = nullptr) {
+    GN gn_fwd(View x, View y, int silu, const float* ss = nullptr, DropArgs drop = DropArgs()) {
         GN g;
         g.w = take(x.C), g.b = take(x.C);
         const bool have = x.cs != nullptr;  // the producer's epilogue already accumulated the statistics
@@ -522,8 +529,8 @@ struct Builder {
         g.S = zf32(size_t(B) * x.C * 2);
         const int HW = x.H * x.W, Gn = c.gn_n_groups;
         float *gw = P(g.w), *gb = P(g.b), *cs = g.chsum;
-        const bool slab = !have && !ss && use_slab(x.C, x.H, x.W);
-        if (have && real() && !ss) {
+        const bool slab = !have && !ss && !drop.ctl && use_slab(x.C, x.H, x.W);
+        if (have && real() && !ss && !drop.ctl) {
             auto it = gn_finish.find(x.p);
             if (it != gn_finish.end()) {
                 auto pp = it->second;
@@ -547,7 +554,7 @@ struct Builder {
                 F([=](cudaStream_t st) {
                     if (!have) gn_stats(xh.p, xh.ld, Bq, HW, xh.C, csh, st);
                     gn_apply(xh.p, xh.ld, csh, gw, gb, Bq, HW, xh.C, Gn, silu, yh.p, yh.ld, nullptr, st,
-                             mbf(const_cast<float*>(ss), h, size_t(2) * xh.C));
+                             mbf(const_cast<float*>(ss), h, size_t(2) * xh.C), drop);
                 }, have ? 1 : 2, UB_KIND_NORM, 0, (have ? 2 : 3) * act_bytes(x.C, x.H, x.W) / nh);
         });
         return g;
@@ -560,11 +567,11 @@ struct Builder {
         ep.gn_S = g.S, ep.gn_silu = silu, ep.gn_groups = c.gn_n_groups;
     }
     void gn_bwd(const GN& g, View x, View dy, int silu, View add_in, View dx, float* colsum_out, bool fused = false,
-                const float* ss = nullptr, float* dss = nullptr) {
-        fused = fused && use_bwd_hook(x.C, x.H, x.W) && !ss;
+                const float* ss = nullptr, float* dss = nullptr, DropArgs drop = DropArgs()) {
+        fused = fused && use_bwd_hook(x.C, x.H, x.W) && !ss && !drop.ctl;
         const int HW = x.H * x.W, Gn = c.gn_n_groups;
         float *gw = P(g.w), *gb = P(g.b), *cs = g.chsum, *S = g.S, *dgw = G(g.w), *dgb = G(g.b);
-        const bool slab = !fused && !ss && use_slab(x.C, x.H, x.W);
+        const bool slab = !fused && !ss && !drop.ctl && use_slab(x.C, x.H, x.W);
         const int mode = fused ? (silu ? 2 : 0) : silu;
         if (fused && real()) {
             auto it = gn_finish.find(dy.p);
@@ -592,9 +599,9 @@ struct Builder {
                 Bk([=](cudaStream_t st) {
                     const float* ssh = mbf(const_cast<float*>(ss), h, size_t(2) * xh.C);
                     float* dssh = mbf(dss, h, size_t(2) * xh.C);
-                    if (!fused) gn_bwd_stats(xh.p, xh.ld, dyh.p, dyh.ld, csh, gw, gb, Bq, HW, xh.C, Gn, silu, Sh, st, ssh);
+                    if (!fused) gn_bwd_stats(xh.p, xh.ld, dyh.p, dyh.ld, csh, gw, gb, Bq, HW, xh.C, Gn, silu, Sh, st, ssh, drop);
                     gn_bwd_apply(xh.p, xh.ld, dyh.p, dyh.ld, csh, Sh, gw, gb, Bq, HW, xh.C, Gn, mode, ah.p, ah.ld, dxh.p,
-                                 dxh.ld, dgw, dgb, colh, st, ssh, dssh);
+                                 dxh.ld, dgw, dgb, colh, st, ssh, dssh, drop);
                 }, fused ? 1 : 2, UB_KIND_NORM, 0, ((fused ? 3 : 5) + (add_in.p ? 1 : 0)) * act_bytes(x.C, x.H, x.W) / nh);
         });
     }
@@ -692,6 +699,14 @@ struct Builder {
         // runs unfused (plain dgrad of conv2, statistics pass, apply pass that also writes dscale / dshift)
         const bool ssn = c.use_scale_shift_norm != 0;
         const int OCe = ssn ? 2 * Cout : Cout;
+        // dropout (cfg.dropout; guided-diffusion out_layers = GroupNorm, SiLU, Dropout, conv): the mask multiplies
+        // silu(gn2(h)) inside the GroupNorm apply kernel and is regenerated by the unfused GroupNorm backward (DropArgs)
+        DropArgs drp;
+        if (c.dropout > 0.f) {
+            drp.ctl = T->drop_ctl, drp.layer = unsigned(blk);
+            if (real()) T->drop_layers.push_back({Cout, H, W});
+        }
+        const bool unfused2 = ssn || c.dropout > 0.f;  // GroupNorm 2 backward without the dgrad hook
         const size_t w1 = take(size_t(Cout) * C * 9), b1 = take(Cout);
         const size_t wl = take(size_t(OCe) * Cemb), bl = take(OCe);
         View h1 = act(Cout, H, W);
@@ -706,7 +721,7 @@ struct Builder {
             conv_op(true, {{a1.p, C, a1.ld, p1.wf, 9}}, H, W, Cout, ep);
         }
         View a2 = act(Cout, H, W);
-        GN g2 = gn_fwd(h1, a2, 1, ssn ? embproj : nullptr);
+        GN g2 = gn_fwd(h1, a2, 1, ssn ? embproj : nullptr, drp);
         const size_t w2 = take(size_t(Cout) * Cout * 9), b2 = take(Cout);
         Packed p2 = pack(w2, Cout, Cout, 9);
         const bool proj = C != Cout;
@@ -752,15 +767,15 @@ struct Builder {
             {
                 ConvEpilogue ep;
                 ep.out = da2.p, ep.ldo = da2.ld;
-                if (!ssn) gn_hook(ep, g2, h1, 1);  // da2 receives dz = dL/d gn2(h1)
+                if (!unfused2) gn_hook(ep, g2, h1, 1);  // da2 receives dz = dL/d gn2(h1)
                 conv_op(false, {{dout.p, Cout, dout.ld, p2.wd, 9}}, H, W, Cout, ep);
             }
             // GN2 + SiLU backward; per-image column sums of dh1 feed the embedding-projection backward
             // (scale-shift: the apply pass writes [dscale | dshift] there instead)
             if (ssn)
-                gn_bwd(g2, h1, da2, 1, View{}, dh1, nullptr, false, embproj, d_embproj);
+                gn_bwd(g2, h1, da2, 1, View{}, dh1, nullptr, false, embproj, d_embproj, drp);
             else
-                gn_bwd(g2, h1, da2, 1, View{}, dh1, d_embproj, true);
+                gn_bwd(g2, h1, da2, 1, View{}, dh1, d_embproj, !unfused2, nullptr, nullptr, drp);
             emb_lo = blk < emb_lo ? blk : emb_lo, emb_hi = blk + 1 > emb_hi ? blk + 1 : emb_hi;  // batched, see emb_flush
             if (blk == 0) {  // the last embedding gradient of the step: finish the embedding path on the branch now
                 emb_flush();
@@ -896,6 +911,7 @@ int Builder::build() {
     T->x0 = f32(size_t(B) * img), T->xt = f32(size_t(B) * img), T->noise = f32(size_t(B) * img);
     T->tsteps = f32(B);
     T->labels = c.num_classes > 0 ? (int*)T->arena.alloc(size_t(B) * sizeof(int) + 256) : nullptr;
+    T->drop_ctl = c.dropout > 0.f ? (unsigned*)T->arena.alloc(256) : nullptr;
     T->dxt = c.compute_dinput ? f32(size_t(B) * img) : nullptr;
     T->flips = c.random_flip ? (int*)T->arena.alloc(size_t(B) * sizeof(int) + 256) : nullptr;
     T->out = f32(size_t(B) * c.C_out * H0 * W0), T->dout = f32(size_t(B) * c.C_out * H0 * W0);
@@ -1278,8 +1294,8 @@ static int validate_config(const UbConfig& c) {
         set_err("bad config: resblock_updown / use_scale_shift_norm must be 0 or 1");
         return UB_ERR_SHAPE;
     }
-    if (c.num_classes < 0 || !(c.ema_rate >= 0.f && c.ema_rate < 1.f)) {
-        set_err("bad config: num_classes must be >= 0 and ema_rate in [0, 1)");
+    if (c.num_classes < 0 || !(c.ema_rate >= 0.f && c.ema_rate < 1.f) || !(c.dropout >= 0.f && c.dropout < 1.f)) {
+        set_err("bad config: num_classes must be >= 0, ema_rate and dropout in [0, 1)");
         return UB_ERR_SHAPE;
     }
     if (c.random_flip && c.W % 4) {
@@ -1498,6 +1514,7 @@ static void enqueue_step(UbTrainer* t, const StepOpts& o, cudaStream_t st) {
     cudaMemsetAsync(t->zero_base, 0, t->zero_bytes, st);
     diffusion_prepare(t->x0, t->sqrt_ac, t->sqrt_1mac, c.B, size_t(c.C_in) * c.H * c.W, c.n_timesteps, c.seed,
                       t->step_dev, o.gen_t ? 1 : 0, o.gen_noise ? 1 : 0, t->tsteps, t->noise, t->xt, st, c.W, t->flips);
+    if (t->drop_ctl) dropout_set_ctl(t->drop_ctl, c.dropout, c.seed, t->step_dev, st);  // training: masks of this step
     static const bool debug_sync = getenv("UB_DEBUG_SYNC") != nullptr;  // eager runs only: find the faulting op
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (debug_sync) cudaStreamIsCapturing(st, &cap);
@@ -1807,6 +1824,7 @@ extern "C" int ub_trainer_profile(UbTrainer* t, int reps, UbProfile* out) {
         cudaMemsetAsync(t->zero_base, 0, t->zero_bytes, st);
         diffusion_prepare(t->x0, t->sqrt_ac, t->sqrt_1mac, c.B, size_t(c.C_in) * c.H * c.W, c.n_timesteps, c.seed,
                           t->step_dev, 1, 1, t->tsteps, t->noise, t->xt, st, c.W, t->flips);
+        if (t->drop_ctl) dropout_set_ctl(t->drop_ctl, c.dropout, c.seed, t->step_dev, st);
         cudaEventRecord(ev[k++], st);
         for (auto& op : t->fwd_ops) {
             for (int r = 0; r < R; ++r) op(st);
@@ -1900,6 +1918,7 @@ extern "C" int ub_trainer_predict(UbTrainer* t, const float* xt_host, const floa
     CUDA_TRY(cudaMemcpyAsync(t->tsteps, t_host, c.B * sizeof(float), cudaMemcpyHostToDevice, t->stream));
     CUDA_TRY(cudaMemsetAsync(t->zero_base, 0, t->zero_bytes, t->stream));
     CUDA_TRY(cudaMemsetAsync(t->noise, 0, img * sizeof(float), t->stream));
+    if (t->drop_ctl) dropout_set_ctl(t->drop_ctl, 0.f, c.seed, t->step_dev, t->stream);  // inference: no dropout
     for (auto& op : t->fwd_ops) op(t->stream);
     CUDA_TRY(cudaMemcpyAsync(out_host, t->out, oimg * sizeof(float), cudaMemcpyDeviceToHost, t->stream));
     CUDA_TRY(cudaStreamSynchronize(t->stream));
@@ -1938,6 +1957,7 @@ extern "C" int ub_trainer_sample(UbTrainer* t, const float* x_init_host, int t_s
         CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         cudaMemsetAsync(t->zero_base, 0, t->zero_bytes, st);
         sample_set_t(t->samp_state, c.B, t->tsteps, st);
+        if (t->drop_ctl) dropout_set_ctl(t->drop_ctl, 0.f, c.seed, t->step_dev, st);  // inference: no dropout
         for (auto& op : t->fwd_ops) op(st);
         ddpm_step(t->xt, t->out, t->betas, t->sqrt_ac, t->sqrt_1mac, inject ? t->samp_z : nullptr, img, seed,
                   t->samp_state, t->samp_state + 1, st);
@@ -2001,6 +2021,36 @@ extern "C" int ub_trainer_get_ema(UbTrainer* t, float* host, size_t n) {
         return UB_ERR_STATE;
     }
     return copy_out(t, t->ema, host, n, t->nparams);
+}
+extern "C" int ub_trainer_get_dropout_mask(UbTrainer* t, int block, unsigned char* host, size_t n) {
+    if (!t->drop_ctl) {
+        set_err("no dropout: the trainer was created with cfg.dropout = 0");
+        return UB_ERR_STATE;
+    }
+    if (block < 0 || size_t(block) >= t->drop_layers.size()) {
+        set_err("dropout mask: block %d outside [0, %zu)", block, t->drop_layers.size());
+        return UB_ERR_SHAPE;
+    }
+    const auto& d = t->drop_layers[size_t(block)];
+    const size_t want = size_t(t->cfg.B) * d.C * d.H * d.W;
+    if (n != want) {
+        set_err("dropout mask of block %d has %zu elements (B x %d x %d x %d, NHWC order), got %zu", block, want, d.H, d.W,
+                d.C, n);
+        return UB_ERR_SHAPE;
+    }
+    CUDA_TRY(cudaSetDevice(t->device));
+    unsigned char* dev = nullptr;
+    CUDA_TRY(cudaMalloc(&dev, want));
+    CUDA_TRY(cudaStreamSynchronize(t->stream));
+    dropout_mask(t->drop_ctl, t->cfg.dropout, unsigned(block), want, dev, t->stream);
+    cudaError_t e = cudaMemcpyAsync(host, dev, want, cudaMemcpyDeviceToHost, t->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(t->stream);
+    cudaFree(dev);
+    if (e != cudaSuccess) {
+        set_err("dropout mask readback failed: %s", cudaGetErrorString(e));
+        return UB_ERR_CUDA;
+    }
+    return UB_OK;
 }
 extern "C" int ub_trainer_set_ema(UbTrainer* t, const float* host, size_t n) {
     if (!t->ema) {
