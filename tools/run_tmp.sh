@@ -1,6 +1,15 @@
 o=gpurun_out; mkdir -p $o
-timeout 250 python -m pytest tests/test_dp_gpu.py -q -x > $o/g1_pytest_dp.log 2>&1; echo "dp pytest rc=$?"; tail -3 $o/g1_pytest_dp.log
-timeout 250 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29617 bench.py --gpus 2 --steps 40 --warmup 10 --no-cpu-baseline --no-reference-cuda > $o/g1_bench_2gpu.json 2> $o/g1_bench_2gpu.err; echo "bench rc=$?"
-python -c "
+UB_MICROBATCH=2 UB_MICROBATCH_LOWRES=256 timeout 200 python -m pytest tests/test_trainer_gpu.py -q -x -k "B4 or B32 or eager_and_graph or ten_step" > $o/k1_pytest.log 2>&1; echo "pytest lowres rc=$?"; tail -2 $o/k1_pytest.log
+run() { tag=$1; shift; env "$@" timeout 200 python bench.py --steps 40 --warmup 10 --no-cpu-baseline --no-reference-cuda > $o/$tag.json 2> $o/$tag.err; python -c "
 import json
-d=json.loads(open('$o/g1_bench_2gpu.json').read().strip().splitlines()[-1]); print('2gpu ms', round(d['ms_per_step'],4), 'img/s', round(d['value'],1), 'e2e', round(d['e2e']['value'],1))"
+try:
+    d=json.loads(open('$o/$tag.json').read().strip().splitlines()[-1]); print('$tag', 'ms', round(d['ms_per_step'],4), 'launches', d['gpu_launches'])
+except Exception as e: print('$tag', 'ERR', e)
+"; }
+run k1_base UB_X=1
+run k1_low256 UB_MICROBATCH=2 UB_MICROBATCH_LOWRES=256
+run k1_low64 UB_MICROBATCH=2 UB_MICROBATCH_LOWRES=64
+run k1_low256_fwd UB_MICROBATCH_FWD=2 UB_MICROBATCH_LOWRES=256
+run k1_low64_fwd UB_MICROBATCH_FWD=2 UB_MICROBATCH_LOWRES=64
+run k1_low1024 UB_MICROBATCH=2 UB_MICROBATCH_LOWRES=1024
+run k1_base2 UB_X=1

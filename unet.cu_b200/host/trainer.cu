@@ -124,6 +124,8 @@ struct UbTrainer {
     // switch (UB_MICROBATCH), off by default.  Ops that need the whole batch (weight gradients on the side stream, loss,
     // optimizer) join the chains first.
     int n_mb = 1;
+    bool mb_fwd_only = false;  // UB_MICROBATCH_FWD: the chains exist in the forward pass only
+    int mb_max_hw = 0;         // UB_MICROBATCH_LOWRES: > 0 = chains only at levels of at most this many pixels per image
     std::vector<cudaStream_t> mb_streams;
     std::vector<cudaEvent_t> side_events;
     size_t side_ev_next = 0;
@@ -274,6 +276,15 @@ struct Builder {
     };
     std::vector<Node> nodes;
     std::vector<View> skipgrad;  // per node: gradient arriving from the up path
+    // UB_MICROBATCH_LOWRES = hw: micro-batch chains only at levels of at most hw pixels per image (the 8x8 / 16x16 levels
+    // run on less than half of the SMs and are bound by per-kernel latency); node_nh[i] = chains of node i
+    std::vector<int> node_nh;
+    void level_mb(int H, int W) {
+        if (T->mb_max_hw <= 0) return;
+        nh = (H * W <= T->mb_max_hw && T->n_mb > 1 && B % T->n_mb == 0) ? T->n_mb : 1;
+        Bh = B / nh;
+    }
+    void sync_nh() { node_nh.resize(nodes.size(), nh); }
 
     // micro-batches (see UbTrainer::n_mb): nh chains of Bh images each
     int nh = 1, Bh = 0;
@@ -281,6 +292,7 @@ struct Builder {
     explicit Builder(UbTrainer* t) : T(t), c(t->cfg), B(t->cfg.B) {
         nh = t->n_mb > 0 && B % t->n_mb == 0 ? t->n_mb : 1;
         Bh = B / nh;
+        level_mb(t->cfg.H, t->cfg.W);  // (UB_MICROBATCH_LOWRES: the full-resolution head of the step runs as one chain)
     }
     // emit the same op for every micro-batch: fn(h) pushes the ops of micro-batch h (views offset with mb())
     template <class Fn>
@@ -996,8 +1008,11 @@ int Builder::build() {
     std::vector<View> skip_views = {h};
 
     const int nlev = c.n_levels;
+    level_mb(H0, W0);
+    sync_nh();
     for (int level = 0; level < nlev; ++level) {
         const int cout = c.channel_mult[level] * Cm;
+        level_mb(H0 >> level, W0 >> level);
         for (int i = 0; i < c.n_res_blocks; ++i) {
             h = resblock(h, cout);
             if (level >= c.att_start_level) h = attnblock(h);
@@ -1038,6 +1053,7 @@ int Builder::build() {
             skip_views.push_back(h);
         }
     }
+    sync_nh();
     // ---- middle (dev/unet.py:224-243)
     h = resblock(h, h.C);
     h = attnblock(h);
@@ -1046,6 +1062,8 @@ int Builder::build() {
     bool pending_up = false;
     for (int level = nlev - 1; level >= 0; --level) {
         const int cout = c.channel_mult[level] * Cm;
+        sync_nh();
+        level_mb(H0 >> level, W0 >> level);
         for (int i = 0; i <= c.n_res_blocks; ++i) {
             const int src = skip_stack.back();
             View sk = skip_views.back();
@@ -1095,6 +1113,7 @@ int Builder::build() {
             }
         }
     }
+    sync_nh();
     // ---- output head: GN + SiLU + conv3x3 (-> C_out) + MSE (dev/unet.py:286-290, train_unet.cu:4408-4418)
     {
         Node nd;
@@ -1133,6 +1152,11 @@ int Builder::build() {
     // ---- backward: walk the nodes in reverse.  Gradient buckets (data parallel): parameters live in forward
     //      order, so once node i's backward has been emitted every parameter at offset >= node[i].param_begin is
     //      final (the time MLP at the head of the arena finishes last).
+    // UB_MICROBATCH_FWD=n: micro-batch chains in the FORWARD pass only -- there the device runs one kernel at a time and
+    // the 8x8 / 16x16 levels fill less than half of it, while backward already shares the device with the weight-gradient
+    // branch.  Backward ops are emitted once for the whole batch (the activations are batch-major views either way).
+    sync_nh();
+    if (T->mb_fwd_only) nh = 1, Bh = B;
     skipgrad.assign(nodes.size(), View{});
     std::vector<size_t> cuts;  // descending offsets at which a bucket is flushed
     {
@@ -1205,6 +1229,7 @@ int Builder::build() {
     View g{};
     for (int i = int(nodes.size()) - 1; i >= 0; --i) {
         Node& nd = nodes[i];
+        if (T->mb_max_hw > 0 && !T->mb_fwd_only) nh = node_nh[size_t(i)], Bh = B / nh;  // the chains of this node's level
         if (nd.pushed) {  // gradient of a tensor that also fed a skip connection: sum both contributions
             View s = skipgrad[i];
             View sum = act(nd.out.C, nd.out.H, nd.out.W);
@@ -1360,8 +1385,12 @@ extern "C" int ub_trainer_create(UbTrainer** out, const UbConfig* cfg, int devic
     {   // micro-batch chains (UbTrainer::n_mb): off by default -- measured 5.18 ms/step with one chain, 5.30 with two, 5.74
         // with four (profiles/r02_microbatch.txt): the latency that B-scaling exposes is per launch, and two chains double
         // the launches.  UB_MICROBATCH=2 / 4 enables (B must be divisible).
-        const int want = getenv("UB_MICROBATCH") ? atoi(getenv("UB_MICROBATCH")) : 1;
+        int want = getenv("UB_MICROBATCH") ? atoi(getenv("UB_MICROBATCH")) : 1;
+        if (getenv("UB_MICROBATCH_FWD") && atoi(getenv("UB_MICROBATCH_FWD")) >= 2)
+            want = atoi(getenv("UB_MICROBATCH_FWD")), t->mb_fwd_only = true;
         t->n_mb = (want >= 2 && want <= 8 && cfg->B % want == 0) ? want : 1;
+        if (t->n_mb == 1) t->mb_fwd_only = false;
+        t->mb_max_hw = (t->n_mb > 1 && getenv("UB_MICROBATCH_LOWRES")) ? atoi(getenv("UB_MICROBATCH_LOWRES")) : 0;
     }
     // pass 1: count
     t->arena.counting = t->zarena.counting = true;
@@ -1407,7 +1436,7 @@ extern "C" int ub_trainer_create(UbTrainer** out, const UbConfig* cfg, int devic
     cudaStreamCreateWithPriority(&t->aux_stream, cudaStreamNonBlocking, use_prio ? prio_hi : 0);
     cudaEventCreateWithFlags(&t->ev_aux_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&t->ev_aux_join, cudaEventDisableTiming);
-    t->attn_concurrent = !(getenv("UB_ATTN_SERIAL") && atoi(getenv("UB_ATTN_SERIAL")) != 0) && t->n_mb == 1;
+    t->attn_concurrent = !(getenv("UB_ATTN_SERIAL") && atoi(getenv("UB_ATTN_SERIAL")) != 0) && (t->n_mb == 1 || t->mb_fwd_only);
     for (int i = 1; i < t->n_mb; ++i) {
         cudaStream_t ms = nullptr;
         cudaStreamCreateWithPriority(&ms, cudaStreamNonBlocking, use_prio ? prio_hi : 0);
