@@ -296,6 +296,71 @@ static bool test_wgrad(int B, int H, int W, int Cin, int Cout, int ntaps, int ns
            B, H, W, Cin, Cout, ntaps, p.MO, p.NC, p.TC, p.nsplit, p.stages, ncheck, bad, max_err, max_ref, ms, ms_red,
            ms > 0 ? flops / ms * 1e-9 : 0.0, bad ? "FAIL" : "ok");
     if (bad) g_fail++;
+    // accumulate mode (the trainer's): every CTA adds its tile into acc[tap][o][c] -- TMA reduce-add boxes (default) and
+    // per-lane REDs (tma_red = 0) -- compared with the two-pass result above, element by element
+    for (int mode = 1; mode >= 0; --mode) {
+        float *dacc, *dbias;
+        CK(cudaMalloc(&dacc, hdw.size() * 4));
+        CK(cudaMalloc(&dbias, size_t(Cout) * 4));
+        CK(cudaMemset(dacc, 0, hdw.size() * 4));
+        CK(cudaMemset(dbias, 0, size_t(Cout) * 4));
+        IgemmWgradParams pa;
+        r = igemm_wgrad_plan_acc(&pa, ddy, Cout, dx_, Cin, B, H, W, Cin, Cout, ntaps, dacc, dbias, nullptr, 148);
+        if (r) {
+            printf("wgrad acc plan failed %d\n", r);
+            g_fail++;
+            return false;
+        }
+        if (!mode) pa.tma_red = 0;
+        r = igemm_wgrad_launch(pa, 0);
+        e = cudaDeviceSynchronize();
+        if (r || e != cudaSuccess) {
+            printf("wgrad acc launch failed r=%d e=%s\n", r, cudaGetErrorString(e));
+            exit(3);
+        }
+        std::vector<float> hacc(hdw.size()), hb(Cout);
+        CK(cudaMemcpy(hacc.data(), dacc, hacc.size() * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(hb.data(), dbias, hb.size() * 4, cudaMemcpyDeviceToHost));
+        int bad2 = 0;
+        double me = 0;
+        for (int tap = 0; tap < ntaps; ++tap)
+            for (int o = 0; o < Cout; ++o)
+                for (int c = 0; c < Cin; ++c) {
+                    const double a = hacc[(size_t(tap) * Cout + o) * Cin + c], b = hdw[(size_t(o) * Cin + c) * ntaps + tap];
+                    const double err = fabs(a - b);
+                    if (err > me) me = err;
+                    if (!(err <= 1e-4 * (1.0 + fabs(b)) + 2e-5 * sqrt(double(npix)))) {
+                        if (bad2 < 5) printf("   acc mismatch tap=%d o=%d c=%d got=%f two-pass=%f\n", tap, o, c, a, b);
+                        bad2++;
+                    }
+                }
+        int badb = 0;
+        for (int o = 0; o < Cout; ++o) {  // bias gradient = column sums of dY
+            double sref = 0;
+            for (size_t px = 0; px < npix; ++px) sref += dy[px * Cout + o];
+            if (!(fabs(hb[o] - sref) <= 1e-3 * (1.0 + fabs(sref)) + 1e-4 * sqrt(double(npix)))) {
+                if (badb < 3) printf("   bias mismatch o=%d got=%f ref=%f\n", o, hb[o], sref);
+                badb++;
+            }
+        }
+        float msa = 0;
+        if (reps > 0) {
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0), cudaEventCreate(&e1);
+            for (int i = 0; i < 3; ++i) igemm_wgrad_launch(pa, 0);
+            cudaEventRecord(e0);
+            for (int i = 0; i < reps; ++i) igemm_wgrad_launch(pa, 0);
+            cudaEventRecord(e1);
+            CK(cudaEventSynchronize(e1));
+            cudaEventElapsedTime(&msa, e0, e1);
+            msa /= reps;
+        }
+        printf("   acc mode %-14s max |acc - two-pass| %.3g bad %d bias bad %d | %.4f ms %.1f TFLOP/s  %s\n",
+               mode ? "TMA reduce-add" : "per-lane RED", me, bad2, badb, msa, msa > 0 ? flops / msa * 1e-9 : 0.0,
+               (bad2 || badb) ? "FAIL" : "ok");
+        if (bad2 || badb) g_fail++;
+        cudaFree(dacc), cudaFree(dbias);
+    }
     cudaFree(dx_), cudaFree(ddy), cudaFree(dpart), cudaFree(ddw);
     return bad == 0;
 }

@@ -548,6 +548,7 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmDY);
         tma_prefetch_desc(&p.tmX);
+        if (p.tma_red) tma_prefetch_desc(&p.tmAcc);
         for (int i = 0; i < p.stages; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
@@ -669,7 +670,50 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
         mbar_wait(tmem_full_bar, 0);
         pdl_trigger_late();  // main loop complete: the next kernel's prologue may overlap this epilogue
         tc_fence_after();
-        if (k_end > k_begin) {
+        if (k_end > k_begin && p.tma_red) {
+            // Accumulate mode through the TMA: thread = accumulator row, so a per-lane RED (or store) instruction touches
+            // 32 different lines and the LSU takes one pass per lane -- 12 288 passes for a 128 x 384 tile, ~6 us, the
+            // largest phase of the low-resolution launches.  Instead every warp stages 32 columns of its MO/4 rows in
+            // the idle operand ring (fp32 rows of 128 B, 16-byte chunks XOR-swizzled with the row: conflict-free
+            // STS.128 and the layout a SWIZZLE_128B box expects) and one elected lane issues a reduce-add box per
+            // (tap, 32 columns); the L2 adds whole lines.  Warps are independent: each owns a slice of the ring and
+            // re-uses a buffer only after its bulk group has read it.
+            const int rpw = p.MO >> 2;  // accumulator rows of this warp: TMEM lanes 32q .. 32q + rpw - 1
+            const uint32_t bufbytes = uint32_t(rpw) * 128u;
+            const int nsub = p.NC >> 5, ntile = p.TC * nsub;
+            int nbuf = int((uint32_t(p.stages) * p.stage_bytes / 4u) / bufbytes);
+            if (nbuf > ntile) nbuf = ntile;
+            const uint32_t wbase = smem_u32(smem) + uint32_t(q) * uint32_t(nbuf) * bufbytes;
+            const uint32_t rowoff = uint32_t(lane) * 128u, sw = uint32_t(lane & 7);
+            int slot = 0;
+            for (int it = 0; it < ntile; ++it) {
+                const int ti = it / nsub, s = it - ti * nsub;
+                if (it != 0 && slot == 0) {  // wrapped around this warp's buffers
+                    if (elect_one_sync()) bulk_wait_group_read0();
+                    __syncwarp();
+                }
+                uint32_t v[32];
+                tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(ti * p.NC + s * 32), v);
+                tmem_ld_wait();
+                const uint32_t buf = wbase + uint32_t(slot) * bufbytes;
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        sts_v4_b32(buf + rowoff + ((uint32_t(j) ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2],
+                                   v[4 * j + 3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (elect_one_sync()) {
+                    tma_reduce_add_2d(buf, &p.tmAcc, c0 + s * 32, (tap0 + ti) * p.Cout + o0 + q * rpw);
+                    bulk_commit_group();
+                }
+                __syncwarp();
+                if (++slot == nbuf) slot = 0;
+            }
+            if (elect_one_sync()) bulk_wait_group0();  // (the same lane committed every group: elect.sync is deterministic)
+            __syncwarp();
+        } else if (k_end > k_begin) {
             for (int ti = 0; ti < p.TC; ++ti) {
                 const int tap = tap0 + ti;
                 float* dst = p.acc ? p.acc + (size_t(tap) * p.Cout + (o0 + row)) * p.Cin + c0
@@ -696,14 +740,14 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
                     }
                 }
             }
-            if (do_bias) {  // every column of the ones-accumulator holds sum_pixels dY[pix][o]
-                uint32_t v[16];
-                tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(p.TC * p.NC), v);
-                tmem_ld_wait();
-                if (valid) {
-                    atomicAdd(p.dbias + o0 + row, __uint_as_float(v[0]));
-                    if (p.dbias2) atomicAdd(p.dbias2 + o0 + row, __uint_as_float(v[0]));
-                }
+        }
+        if (k_end > k_begin && do_bias) {  // every column of the ones-accumulator holds sum_pixels dY[pix][o]
+            uint32_t v[16];
+            tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(p.TC * p.NC), v);
+            tmem_ld_wait();
+            if (valid) {
+                atomicAdd(p.dbias + o0 + row, __uint_as_float(v[0]));
+                if (p.dbias2) atomicAdd(p.dbias2 + o0 + row, __uint_as_float(v[0]));
             }
         }
     }
@@ -1128,7 +1172,8 @@ static int wgrad_plan_common(IgemmWgradParams* p, const __nv_bfloat16* dy, int l
     // One CTA per SM (a CTA owns the SM's smem and TMEM), and never more CTAs than SMs: a grid of 150 CTAs on 148
     // SMs runs as two waves and doubles the kernel time (ncu r01: 64->64@64x64 took 57 us as (1,3,50)).
     int nsplit = sm_count / base_ctas;
-    if (nsplit > ktiles * KP / 256) nsplit = ktiles * KP / 256;  // at least 256 pixels of K per CTA
+    static const int min_kpix = getenv("UB_WGRAD_MIN_KPIX") ? atoi(getenv("UB_WGRAD_MIN_KPIX")) : 256;
+    if (nsplit > ktiles * KP / min_kpix) nsplit = ktiles * KP / min_kpix;  // at least 256 pixels of K per CTA
     if (nsplit < 1) nsplit = 1;
     if (!acc_mode) {
         while (nsplit > 1 && igemm_wgrad_partial_floats(Cin, Cout, ntaps, nsplit) > partial_cap_floats) --nsplit;
@@ -1158,6 +1203,26 @@ int igemm_wgrad_plan_acc(IgemmWgradParams* p, const __nv_bfloat16* dy, int ldy, 
     if (r) return r;
     if (!acc || (reinterpret_cast<uintptr_t>(acc) & 15)) return -16;
     p->acc = acc, p->dbias = dbias, p->dbias2 = dbias2;
+    // TMA reduce-add epilogue (see the kernel): fp32 map over acc[ntaps * Cout][Cin], box = 32 columns (128 B, the
+    // swizzle span) x the MO/4 accumulator rows of one epilogue warp.  UB_WGRAD_TMA_RED=0: per-lane red.global.add.
+    static const bool tma_red = !(getenv("UB_WGRAD_TMA_RED") && atoi(getenv("UB_WGRAD_TMA_RED")) == 0);
+    if (tma_red) {
+        EncodeTiledFn fn = get_encode_fn();
+        if (!fn) return -10;
+        cuuint64_t dims[2] = {cuuint64_t(Cin), cuuint64_t(ntaps) * cuuint64_t(Cout)};
+        cuuint64_t strides[1] = {cuuint64_t(Cin) * 4};
+        cuuint32_t box[2] = {32, cuuint32_t(p->MO / 4)};
+        cuuint32_t es[2] = {1, 1};
+        CUresult cr = fn(&p->tmAcc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, acc, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) {
+            fprintf(stderr, "[unet_b200] cuTensorMapEncodeTiled(wgrad acc Cin=%d rows=%d) -> %d\n", Cin, ntaps * Cout,
+                    int(cr));
+            return -17;
+        }
+        p->tma_red = 1;
+    }
     return 0;
 }
 

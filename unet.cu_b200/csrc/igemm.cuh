@@ -140,6 +140,11 @@ struct IgemmWgradParams {
     // partial buffer, no per-layer reduce launch; wgrad_finalize turns [tap][o][c] into the reference [o][c][tap]
     // layout for a whole gradient bucket at once (for 1x1 / linear layers acc IS the final gradient).
     float* acc;
+    // accumulate mode, tma_red != 0: the epilogue stages its accumulator rows in the (idle) operand ring and adds them
+    // with TMA reduce-add boxes of 32 columns x MO/4 rows (one epilogue warp's rows) instead of per-lane REDs, whose
+    // thread-per-row addresses cost one LSU pass per lane.  tmAcc: fp32, dims (Cin, ntaps*Cout), 128B swizzle.
+    CUtensorMap tmAcc;
+    int tma_red;
     // fused bias gradient: the CTAs of the centre tap / first Cin tile also contract dY with a tile of ones
     // (one extra N=16 MMA per K step), and add column 0 of that accumulator into dbias (and dbias2) atomically.
     float* dbias;

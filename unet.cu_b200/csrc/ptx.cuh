@@ -128,8 +128,17 @@ __device__ __forceinline__ void tma_store_4d(const void* smem, const CUtensorMap
         ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// TMA reduce-add of a shared-memory box into global memory (element type and box from the tensor map): the additions
+// are performed by the L2 as whole lines -- the bulk counterpart of red.global.add, without a per-lane request stream
+__device__ __forceinline__ void tma_reduce_add_2d(uint32_t smem_addr, const CUtensorMap* m, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_addr), "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// only the shared-memory reads of the committed groups are complete (the source buffers may be rewritten)
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // generic-proxy writes to shared memory -> visible to the async proxy (TMA store, tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
