@@ -298,7 +298,7 @@ static bool test_wgrad(int B, int H, int W, int Cin, int Cout, int ntaps, int ns
     if (bad) g_fail++;
     // accumulate mode (the trainer's): every CTA adds its tile into acc[tap][o][c] -- TMA reduce-add boxes (default) and
     // per-lane REDs (tma_red = 0) -- compared with the two-pass result above, element by element
-    for (int mode = 1; mode >= 0; --mode) {
+    for (int mode = 2; mode >= 0; --mode) {  // 2 = default, 1 = one TMA producer warp, 0 = also per-lane REDs
         float *dacc, *dbias;
         CK(cudaMalloc(&dacc, hdw.size() * 4));
         CK(cudaMalloc(&dbias, size_t(Cout) * 4));
@@ -311,6 +311,7 @@ static bool test_wgrad(int B, int H, int W, int Cin, int Cout, int ntaps, int ns
             g_fail++;
             return false;
         }
+        if (mode < 2) pa.nprod = 1;
         if (!mode) pa.tma_red = 0;
         r = igemm_wgrad_launch(pa, 0);
         e = cudaDeviceSynchronize();
@@ -355,8 +356,8 @@ static bool test_wgrad(int B, int H, int W, int Cin, int Cout, int ntaps, int ns
             cudaEventElapsedTime(&msa, e0, e1);
             msa /= reps;
         }
-        printf("   acc mode %-14s max |acc - two-pass| %.3g bad %d bias bad %d | %.4f ms %.1f TFLOP/s  %s\n",
-               mode ? "TMA reduce-add" : "per-lane RED", me, bad2, badb, msa, msa > 0 ? flops / msa * 1e-9 : 0.0,
+        printf("   acc mode %-16s max |acc - two-pass| %.3g bad %d bias bad %d | %.4f ms %.1f TFLOP/s  %s\n",
+               mode == 2 ? (pa.nprod == 2 ? "TMA red, 2 prod" : "TMA red, 1 prod*") : mode ? "TMA red, 1 prod" : "lane RED, 1 prod", me, bad2, badb, msa, msa > 0 ? flops / msa * 1e-9 : 0.0,
                (bad2 || badb) ? "FAIL" : "ok");
         if (bad2 || badb) g_fail++;
         cudaFree(dacc), cudaFree(dbias);

@@ -566,12 +566,19 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();  // everything above touched only kernel parameters, shared memory and TMEM
 
-    if (warp == 0) {
-        // (whole warp converged, TMA instructions under elect.sync: see elect_one_sync in ptx.cuh)
+    if (warp == 0 || (warp == 2 && p.nprod == 2)) {
+        // TMA producer(s) (whole warp converged, TMA instructions under elect.sync: see elect_one_sync in ptx.cuh).
+        // With nprod == 2 (opt-in) the first epilogue warp -- idle until the accumulator is complete -- issues the odd
+        // K tiles: two producers lift single-box stages from ~52 to ~68 B/clk per SM (tools/tma_ingest_bench.cu), but
+        // these stages hold 3-8 boxes and one producer already reaches ~72, so it measured no gain here.
+        // Stage and phase follow from the tile index, so the producers share no state; the ring is EVEN in that case
+        // (plan), so a stage always belongs to the same producer and it waits for consecutive phases of its barriers.
         {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int kt = k_begin; kt < k_end; ++kt) {
+            const int step = p.nprod == 2 ? 2 : 1;
+            for (int kt = k_begin + (warp == 0 ? 0 : 1); kt < k_end; kt += step) {
+                const int kl = kt - k_begin;
+                const int stage = kl % p.stages;
+                const uint32_t phase = uint32_t(kl / p.stages) & 1u;
                 int t = kt;
                 const int w0 = (t % p.tiles_w) * p.TW;
                 t /= p.tiles_w;
@@ -594,13 +601,10 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
                     }
                 }
                 __syncwarp();
-                if (++stage == p.stages) {
-                    stage = 0;
-                    phase ^= 1;
-                }
             }
         }
-    } else if (warp == 1) {
+    }
+    if (warp == 1) {
         {
             // Whole warp converged, MMAs / commits under elect.sync (see elect_one_sync in ptx.cuh).  Everything that does
             // not change per K tile is hoisted: descriptors are a constant high word plus the 16-byte-granular start
@@ -655,7 +659,7 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
             if (elect_one_sync()) umma_commit(tmem_full_bar);
             __syncwarp();
         }
-    } else {
+    } else if (warp >= 2) {
         const int q = warp & 3;
         // M=128: accumulator row m lives in TMEM lane m.  M=64: row m lives in lane (m%16) + 32*(m/16).
         int row;
@@ -1166,6 +1170,12 @@ static int wgrad_plan_common(IgemmWgradParams* p, const __nv_bfloat16* dy, int l
     if (stages < 2) stages = 2;
     if (stages > kMaxStages) stages = kMaxStages;
     if (size_t(stages) * p->stage_bytes > 220u * 1024u) return -3;
+    // two TMA producer warps (see the kernel) need an even ring: a stage must always belong to the same producer.
+    // Measured (profiles/r02n_wgrad_tma_red.txt): no gain -- the stages are multi-box, so one producer already reaches
+    // the chip-wide L2 -> shared-memory rate -- hence opt-in (UB_WGRAD_NPROD=2).
+    static const int nprod_env = getenv("UB_WGRAD_NPROD") ? atoi(getenv("UB_WGRAD_NPROD")) : 1;
+    if (nprod_env == 2 && stages > 2 && (stages & 1)) --stages;
+    p->nprod = (nprod_env == 2 && (stages & 1) == 0) ? 2 : 1;
     p->stages = stages;
     const int ktiles = p->tiles_w * p->tiles_h * p->tiles_b;
     const int base_ctas = (Cout / p->MO) * (Cin / p->NC) * (ntaps / p->TC);

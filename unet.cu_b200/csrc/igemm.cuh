@@ -133,6 +133,7 @@ struct IgemmWgradParams {
     int nsplit;  // split of the pixel (K) dimension across CTAs
     int KP;      // pixels per K tile (= per stage): 64 or 128; an operand atom is KP rows of 128 B
     int stages;
+    int nprod;   // TMA producer warps: 2 = the first epilogue warp loads the odd K tiles (even ring only)
     int tmem_cols;
     uint32_t stage_bytes, tx_bytes;
     float* partial;  // [nsplit][ntaps][Cout][Cin] fp32 (two-pass mode: igemm_wgrad_reduce sums the splits)
