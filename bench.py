@@ -252,7 +252,7 @@ def run_cuda(args):
         conv_tf = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
         traffic, traffic_note = conv_traffic()
         roofline = {
-            "bound": "tensor", "kernel": "igemm_conv_kernel + igemm_conv2_kernel + igemm_rows_kernel (3x3/1x1 conv fprop+dgrad, qkv/proj GEMMs; tcgen05)",
+            "bound": "tensor", "kernel": "igemm_conv[_ms]_kernel + igemm_conv2[_ms]_kernel + igemm_rows_kernel (3x3/1x1 conv fprop+dgrad, qkv/proj GEMMs; tcgen05)",
             "achieved": conv_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
             "frac": conv_tf / pk["tf_sustained"], "traffic": traffic, "traffic_note": traffic_note,
             "bytes_per_launch": conv["bytes"] / max(conv["launches"], 1),
@@ -266,7 +266,7 @@ def run_cuda(args):
         wg_tf = wg["flops"] / (wg["ms"] * 1e-3) / 1e12 if wg["ms"] > 0 else 0.0
         gn_gbs = gn["bytes"] / (gn["ms"] * 1e-3) / 1e9 if gn["ms"] > 0 else 0.0
         roofline_more = {
-            "wgrad": {"bound": "tensor", "kernel": "igemm_wgrad_kernel (tcgen05, split-K, vector-RED accumulation)",
+            "wgrad": {"bound": "tensor", "kernel": "igemm_wgrad_kernel (tcgen05, split-K, TMA reduce-add accumulation)",
                       "achieved": wg_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": wg_tf / pk["tf_sustained"],
                       "launches_per_step": wg["launches"], "avg_launch_ms": wg["ms"] / max(wg["launches"], 1)},
             "groupnorm": {"bound": "hbm", "kernel": "gn_apply / gn_bwd_apply_dz / gn_stats (+ gn_slab_*)",
@@ -393,7 +393,8 @@ def conv_traffic():
         stamp = d.get("_kernel_source_hash")
         if stamp != kernel_source_hash():
             return None, f"profiles/r02_tc_traffic.json was captured from kernel sources {stamp}, current {kernel_source_hash()}: stale"
-        ks = [v for k, v in d.items() if k in ("igemm_conv_kernel", "igemm_conv2_kernel", "igemm_rows_kernel")]
+        ks = [v for k, v in d.items() if k in ("igemm_conv_kernel", "igemm_conv2_kernel", "igemm_rows_kernel",
+                                               "igemm_conv_ms_kernel", "igemm_conv2_ms_kernel")]
         n = sum(v["launches"] for v in ks)
         byts = sum(v["launches"] * (v["dram_read_bytes_per_launch"] + v["dram_write_bytes_per_launch"]) for v in ks)
         return (byts / n if n else None), ("DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum of one "

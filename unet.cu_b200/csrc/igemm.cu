@@ -444,7 +444,9 @@ __device__ __forceinline__ void igemm_conv_body(const IgemmConvParams& p) {
                     }
                 }
                 }  // stat
-                if (threadIdx.x == 64) bulk_wait_group0();  // the Y tile has left shared memory
+                // the Y tile has left shared memory (waiting for the reads only -- wait_group.read -- measured the same:
+                // profiles/r02n_wgrad_tma_red.txt)
+                if (threadIdx.x == 64) bulk_wait_group0();
             }
         }
         bool done_gnf = false;
