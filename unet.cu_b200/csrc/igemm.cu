@@ -6,7 +6,8 @@
 //   conv     : warps 2-9 epilogue (two per TMEM lane quadrant) - tcgen05.ld accumulators out of TMEM, fuse bias / emb /
 //              residual / GroupNorm hooks, store; in igemm_conv2/4_kernel lane 0 of the last epilogue warp(s) first
 //              issues the extra MMA streams
-//   wgrad    : warps 2-5 epilogue - vector REDs of the accumulators into the fp32 weight-gradient buffers
+//   wgrad    : warps 2-5 epilogue - TMA reduce-add boxes (staged in the idle operand ring) into the fp32 weight-gradient
+//              buffers (two-pass mode of the layer API: plain stores of split-K partials)
 // smem stages are handed over with mbarriers (full: TMA complete_tx, empty: tcgen05.commit).
 //
 // Reference behaviour being replaced (not its structure): /root/reference/dev/conv2d_k3.cu:679-740 (forward3),

@@ -137,7 +137,7 @@ struct IgemmWgradParams {
     int tmem_cols;
     uint32_t stage_bytes, tx_bytes;
     float* partial;  // [nsplit][ntaps][Cout][Cin] fp32 (two-pass mode: igemm_wgrad_reduce sums the splits)
-    // accumulate mode (trainer): every CTA adds its tile into acc[ntaps][Cout][Cin] with red.global.add.v4.f32 -- no
+    // accumulate mode (trainer): every CTA adds its tile into acc[ntaps][Cout][Cin] (TMA reduce-add, see tmAcc) -- no
     // partial buffer, no per-layer reduce launch; wgrad_finalize turns [tap][o][c] into the reference [o][c][tap]
     // layout for a whole gradient bucket at once (for 1x1 / linear layers acc IS the final gradient).
     float* acc;

@@ -448,7 +448,7 @@ struct Builder {
         });
     }
     // Weight (and bias) gradient of a conv / linear layer on the side stream.  Every CTA adds its tile into an fp32
-    // accumulator with vector REDs; 3x3 layers accumulate in [tap][o][c] and are transposed into the reference
+    // accumulator with TMA reduce-add boxes; 3x3 layers accumulate in [tap][o][c] and are transposed into the reference
     // (Cout, Cin, 3, 3) layout by one finalize launch per gradient bucket (fin_flush), 1x1 layers accumulate straight
     // into the gradient arena.  db (and db2) = sum over pixels of dy, from an extra ones-column MMA in the same kernel.
     int fin_done = 0;
