@@ -56,6 +56,18 @@ __device__ __forceinline__ void pdl_entry() {
     pdl_wait();
 }
 
+// SMs of the current device (148 on a B200), queried once: grid-size heuristics only, never correctness
+inline int sm_count() {
+    static const int n = [] {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0)
+            v = 148;
+        return v;
+    }();
+    return n;
+}
+
 inline bool pdl_enabled() {
     static const bool on = !(getenv("UB_NO_PDL") && atoi(getenv("UB_NO_PDL")) != 0);
     return on;

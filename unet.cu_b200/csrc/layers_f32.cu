@@ -1,14 +1,13 @@
 // See layers_f32.cuh.
 #include "layers_f32.cuh"
+#include "launch.cuh"
 
 namespace ub {
 namespace f32 {
 
-static constexpr int kSMs = 148;  // B200 (the library is built for sm_100a only); used for grid-size heuristics, never for correctness
-
 static inline unsigned grid_for(size_t n, int threads, int waves = 8) {
     size_t b = (n + threads - 1) / threads;
-    const size_t cap = size_t(kSMs) * waves;
+    const size_t cap = size_t(sm_count()) * waves;  // (launch.cuh: 148 on a B200)
     return unsigned(b < cap ? (b ? b : 1) : cap);
 }
 

@@ -15,6 +15,7 @@
 #include "../../include/unet_b200.h"
 #include "../csrc/attn_tc.cuh"
 #include "../csrc/igemm.cuh"
+#include "../csrc/launch.cuh"
 #include "../csrc/layers_f32.cuh"
 #include "../csrc/misc_ops.cuh"
 #include "../csrc/nhwc_ops.cuh"
@@ -167,7 +168,7 @@ int conv_backward(const float* dout, const float* x, const float* weight, float*
             if (!xb || !partial) return UB_ERR_CUDA;
             f32::nchw_to_nhwc_bf16(x, B, Cin, H * W, xb, st);
             IgemmWgradParams p;
-            int r = igemm_wgrad_plan(&p, dyb, Cout, xb, Cin, B, H, W, Cin, Cout, ntaps, partial, cap, 148);
+            int r = igemm_wgrad_plan(&p, dyb, Cout, xb, Cin, B, H, W, Cin, Cout, ntaps, partial, cap, sm_count());
             if (r) {
                 fail("conv backward: wgrad plan failed (%d)", r);
                 return UB_ERR_SHAPE;
@@ -282,7 +283,7 @@ int ub_matmul_backward1(float* dinp, float* dweight, float* dbias, const float* 
         launches += 2;
     }
     IgemmWgradParams p;
-    int r = igemm_wgrad_plan(&p, dyb, OC, xb, C, 1, 1, N, C, OC, 1, partial, cap, 148);
+    int r = igemm_wgrad_plan(&p, dyb, OC, xb, C, 1, 1, N, C, OC, 1, partial, cap, sm_count());
     if (r) {
         fail("matmul_backward1: wgrad plan failed (%d)", r);
         return UB_ERR_SHAPE;
@@ -510,7 +511,7 @@ int ub_conv2d_nhwc_wgrad(const void* dout, const void* x, float* dweight, float*
     if (!partial) return UB_ERR_CUDA;
     IgemmWgradParams p;
     int r = igemm_wgrad_plan(&p, (const bf16*)dout, C_out, (const bf16*)x, C_in, B, H, W, C_in, C_out, ksize * ksize,
-                             partial, cap, 148);
+                             partial, cap, sm_count());
     if (r) {
         fail("conv2d_nhwc_wgrad: plan failed (%d)", r);
         return UB_ERR_SHAPE;

@@ -21,6 +21,7 @@
 #include "../../include/unet_b200.h"
 #include "../csrc/attn_tc.cuh"
 #include "../csrc/igemm.cuh"
+#include "../csrc/launch.cuh"
 #include "../csrc/misc_ops.cuh"
 #include "../csrc/nhwc_ops.cuh"
 #include "host_common.h"
@@ -420,7 +421,7 @@ struct Builder {
             // persistent row-tile kernel for the 16x16 .. 128x128 levels, one-CTA-per-128-pixels kernel otherwise
             IgemmRowsParams pr;
             if (!no_rows && igemm_rows_eligible(Bh, H, W, Cout) &&
-                igemm_rows_plan(&pr, sh.data(), int(sh.size()), Bh, H, W, Cout, eh, 148) == 0) {
+                igemm_rows_plan(&pr, sh.data(), int(sh.size()), Bh, H, W, Cout, eh, sm_count()) == 0) {
                 op = [pr](cudaStream_t st) { igemm_rows_launch(pr, st); };
                 label("conv%s %s Cin=%d%s Cout=%d %dx%d rows BN=%d stages=%d/%d%s%s", segs[0].ntaps == 9 ? "3x3" : "1x1",
                       fwd ? "fwd" : "dgrad", segs[0].Cin, segs.size() > 1 ? "+skip" : "", Cout, H, W, pr.BN, pr.a_stages,
@@ -455,7 +456,7 @@ struct Builder {
     void wgrad_op(View dy, View x, int Cin, int Cout, int ntaps, float* dw, float* db = nullptr, float* db2 = nullptr) {
         float* acc = ntaps == 9 ? f32(size_t(9) * Cout * Cin) : dw;
         if (!real()) return;
-        static const int wg_sms = getenv("UB_WGRAD_SMS") ? atoi(getenv("UB_WGRAD_SMS")) : 148;
+        static const int wg_sms = getenv("UB_WGRAD_SMS") ? atoi(getenv("UB_WGRAD_SMS")) : sm_count();
         IgemmWgradParams p;
         int r = igemm_wgrad_plan_acc(&p, dy.p, dy.ld, x.p, x.ld, B, x.H, x.W, Cin, Cout, ntaps, acc, db, db2, wg_sms);
         if (r) {
