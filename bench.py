@@ -227,6 +227,10 @@ def run_cuda(args):
     loss_c = ctypes.c_float()
 
     def e2e_step(i):
+        # every step: announce the next pinned batch (its H2D copy then runs on the trainer's copy stream under this
+        # step's kernels), H2D of this step's batch (already on its way when it was announced), 4-byte loss readback
+        if not args.no_prefetch:
+            tr.set_next_batch(host_batches[(i + 1) % n_host].data_ptr())
         tr.train_step_ptr(host_batches[i % n_host].data_ptr(), loss_ref=ctypes.byref(loss_c), **hp)
 
     for i in range(3):
@@ -234,7 +238,7 @@ def run_cuda(args):
     t_e2e = []
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(3, 3 + args.steps):
         e2e_step(i)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
@@ -480,6 +484,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-cuda", action="store_true")
+    ap.add_argument("--no-prefetch", action="store_true",
+                    help="end-to-end leg without ub_trainer_set_next_batch (synchronous H2D before every step)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -292,6 +292,7 @@ int ub_trainer_get_dropout_mask(UbTrainer* t, int block, unsigned char* host, si
 int ub_trainer_get_output(UbTrainer* t, float* host, size_t n); /* last forward's eps prediction (B,C_out,H,W) */
 /* the flip decisions (0 / 1 per image) the last step took, when cfg.random_flip is set */
 int ub_trainer_get_flips(UbTrainer* t, int* host, size_t n);
+int ub_trainer_get_batch(UbTrainer* t, float* host, size_t n);  /* the x0 batch the last step consumed (B,C_in,H,W) */
 int ub_trainer_get_dinput(UbTrainer* t, float* host, size_t n); /* dL/d(x_t) (B,C_in,H,W); needs cfg.compute_dinput */
 
 /* One forward + backward (unet_forward + unet_backward, train_unet.cu:4335-4701) on a HOST batch x0 (B,C_in,H,W).
@@ -307,6 +308,13 @@ int ub_trainer_update(UbTrainer* t, float lr, float beta1, float beta2, float ep
  * NULL (then no device->host copy / sync happens; use ub_trainer_sync + ub_trainer_last_loss). */
 int ub_trainer_train_step(UbTrainer* t, const float* x0_host, const float* t_host, const float* noise_host, float lr,
                           float beta1, float beta2, float eps, float weight_decay, float* loss_out);
+/* Announce the batch the NEXT ub_trainer_train_step will be called with (a page-locked host buffer; NULL cancels).
+ * The train_step that follows this call enqueues the announced batch's H2D copy on a copy stream as soon as its own
+ * step is launched, so the transfer runs under that step's kernels (the reference copies synchronously before every
+ * step, train_unet.cu:5021-5024); the next train_step, called with the same pointer, then starts from the device
+ * copy.  The announced buffer must stay unchanged until that next call returns.  A pageable pointer, or a next call
+ * with another pointer, silently falls back to the ordinary path. */
+int ub_trainer_set_next_batch(UbTrainer* t, const float* next_x0_host);
 /* Same step with the batch already resident on the device (bench.py's device-resident `value`). */
 int ub_trainer_train_step_device(UbTrainer* t, const float* x0_dev, float lr, float beta1, float beta2, float eps,
                                  float weight_decay);

@@ -374,6 +374,50 @@ def test_train_from_dataloader(ub, setup, tmp_path):
     tr.close(), dl.close()
 
 
+def test_next_batch_prefetch(ub, setup):
+    """ub_trainer_set_next_batch: the announced batch's H2D copy runs on the copy stream under the current step; the next
+    train_step called with that pointer must consume exactly that batch (bit-for-bit on the device), a step called with
+    another pointer must fall back to the ordinary copy, and the losses must be those of the synchronous path."""
+    import ctypes as C
+    O, cfg, flat = setup
+    B = 2
+    g = torch.Generator().manual_seed(5)
+    params = (flat + 0.02 * torch.randn(flat.shape, generator=g)).numpy()  # (zero-initialised layers made non-zero)
+    batches = [((torch.rand(B, 3, 64, 64, generator=g) * 2 - 1) * s).pin_memory() for s in (0.1, 1.0, 0.5, 0.8, 0.3)]
+
+    def run(announce):
+        tr = ub.Trainer(B=B)
+        tr.set_params(params)
+        loss, losses = C.c_float(), []
+        for i in range(len(batches)):
+            if announce is not None:
+                tr.set_next_batch(batches[announce[i]].data_ptr())
+            tr.train_step_ptr(batches[i].data_ptr(), loss_ref=C.byref(loss))
+            np.testing.assert_array_equal(tr.get_batch(), batches[i].numpy())
+            losses.append(loss.value)
+        tr.close()
+        return np.array(losses)
+
+    plain = run(None)
+    hit = run([1, 2, 3, 4, 0])    # step i announces batch i + 1: every step from the second on starts from the prefetch
+    miss = run([2, 3, 4, 0, 1])   # always announces a batch the next step does not use: ordinary path, prefetch dropped
+    mixed = run([1, 0, 3, 1, 2])  # hit, miss, hit, miss
+    assert not np.isnan(plain).any()
+    # (fp32 atomics: two runs of the same steps differ by summation order, bounded as in test_eager_and_graph_steps_agree)
+    for other in (hit, miss, mixed):
+        assert np.abs(other - plain).max() < 2e-3, (plain, other)
+    # an un-pinned announcement is ignored
+    tr = ub.Trainer(B=B)
+    tr.set_params(params)
+    pageable = batches[1].clone()
+    tr.set_next_batch(pageable.data_ptr())
+    loss = C.c_float()
+    tr.train_step_ptr(batches[0].data_ptr(), loss_ref=C.byref(loss))
+    tr.train_step_ptr(pageable.data_ptr(), loss_ref=C.byref(loss))
+    np.testing.assert_array_equal(tr.get_batch(), pageable.numpy())
+    tr.close()
+
+
 def test_dinput_matches_oracle(ub, setup):
     """dL/d(x_t), the last tensor dev/unet_test.cu:2082-2107 compares (unet_backward writes it into its dinp buffer)."""
     O, cfg, flat = setup

@@ -80,12 +80,13 @@ def _declare(L: C.CDLL) -> None:
     L.ub_trainer_save_ema.argtypes = [vp, C.c_char_p]
     L.ub_trainer_set_labels.argtypes = [vp, vp, C.c_size_t]
     L.ub_trainer_get_dropout_mask.argtypes = [vp, i, vp, C.c_size_t]
-    for n in ("set_params", "get_params", "get_grads", "get_output", "get_dinput", "get_ema", "set_ema"):
+    for n in ("set_params", "get_params", "get_grads", "get_output", "get_batch", "get_dinput", "get_ema", "set_ema"):
         getattr(L, "ub_trainer_" + n).argtypes = [vp, fp, C.c_size_t]
     L.ub_trainer_forward_backward.argtypes = [vp, fp, fp, fp, C.POINTER(C.c_float)]
     L.ub_trainer_update.argtypes = [vp] + [C.c_float] * 5
     L.ub_trainer_train_step.argtypes = [vp, fp, fp, fp] + [C.c_float] * 5 + [C.POINTER(C.c_float)]
     L.ub_trainer_train_step_device.argtypes = [vp, fp] + [C.c_float] * 5
+    L.ub_trainer_set_next_batch.argtypes = [vp, vp]
     L.ub_trainer_sync.argtypes = [vp]
     L.ub_trainer_last_loss.argtypes = [vp, C.POINTER(C.c_float)]
     L.ub_trainer_set_step.argtypes = [vp, i]
@@ -209,6 +210,11 @@ class Trainer:
         check(lib().ub_trainer_get_flips(self._h, out.ctypes.data_as(C.c_void_p), out.size), "get_flips")
         return out
 
+    def get_batch(self):
+        """The x0 batch the last step consumed, as it sits on the device (B, C_in, H, W)."""
+        c = self.cfg
+        return self._get(lib().ub_trainer_get_batch, c.B * c.C_in * c.H * c.W).reshape(c.B, c.C_in, c.H, c.W)
+
     def get_output(self):
         c = self.cfg
         return self._get(lib().ub_trainer_get_output, c.B * c.C_out * c.H * c.W).reshape(c.B, c.C_out, c.H, c.W)
@@ -247,6 +253,10 @@ class Trainer:
         """Same as train_step with a raw (e.g. pinned) host pointer; device-side timestep/noise draws."""
         check(lib().ub_trainer_train_step(self._h, C.c_void_p(x0_host_ptr), None, None, lr, beta1, beta2, eps,
                                           weight_decay, loss_ref), "train_step")
+
+    def set_next_batch(self, next_x0_host_ptr: int):
+        """Announce the (pinned) host batch of the NEXT train_step: its H2D copy overlaps the step that follows this call."""
+        check(lib().ub_trainer_set_next_batch(self._h, C.c_void_p(next_x0_host_ptr)), "set_next_batch")
 
     def train_step_device(self, x0_dev_ptr: int, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0):
         check(lib().ub_trainer_train_step_device(self._h, C.c_void_p(x0_dev_ptr), lr, beta1, beta2, eps,

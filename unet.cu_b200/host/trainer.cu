@@ -174,6 +174,17 @@ struct UbTrainer {
     cudaEvent_t ev_stage[2] = {nullptr, nullptr};
     bool stage_used[2] = {false, false};
     unsigned stage_next = 0;
+    // Next-batch prefetch (ub_trainer_set_next_batch): the H2D copy of the batch the NEXT train_step will be called with
+    // runs on a copy stream under the current step's kernels; that step then starts with a 1.5 MB device copy instead of
+    // a PCIe transfer.  One device buffer: a new prefetch waits (event) for the copy that consumed the previous one.
+    const float* next_hint = nullptr;  // announced by the caller, picked up by the train_step that follows
+    const float* pref_src = nullptr;   // host pointer whose batch x0_pref holds once ev_pref has completed
+    float* x0_pref = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_pref = nullptr, ev_pref_free = nullptr;
+    bool pref_free_pending = false;
+    float hp_last[5] = {0, 0, 0, 0, 0};  // what hp_dev holds (uploaded again only when a value changes)
+    bool hp_uploaded = false;
     // scratch of the 3-channel weight-gradient fallback kernels (the tcgen05 wgrads accumulate with REDs, no workspace)
     float* small_scratch = nullptr;
     size_t small_scratch_floats = size_t(1) << 20;
@@ -1515,6 +1526,10 @@ extern "C" void ub_trainer_destroy(UbTrainer* t) {
         if (t->ev_stage[k]) cudaEventDestroy(t->ev_stage[k]);
     }
     if (t->h_loss) cudaFreeHost(t->h_loss);
+    if (t->x0_pref) cudaFree(t->x0_pref);
+    if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
+    if (t->ev_pref) cudaEventDestroy(t->ev_pref);
+    if (t->ev_pref_free) cudaEventDestroy(t->ev_pref_free);
     for (auto ev : t->bucket_events) cudaEventDestroy(ev);
     if (t->ev_join) cudaEventDestroy(t->ev_join);
     if (t->ev_join2) cudaEventDestroy(t->ev_join2);
@@ -1679,6 +1694,17 @@ static int stage_inputs(UbTrainer* t, const float* x0_host, const float* t_host,
                         bool sync_call = false) {
     const UbConfig& c = t->cfg;
     const size_t img = size_t(c.B) * c.C_in * c.H * c.W;
+    if (t->pref_src) {  // a prefetched batch is waiting on the device
+        const bool hit = t->pref_src == x0_host && !t_host && !noise_host;
+        t->pref_src = nullptr;  // (a miss drops it: the caller went another way)
+        if (hit) {
+            CUDA_TRY(cudaStreamWaitEvent(t->stream, t->ev_pref, 0));
+            CUDA_TRY(cudaMemcpyAsync(t->x0, t->x0_pref, img * sizeof(float), cudaMemcpyDeviceToDevice, t->stream));
+            CUDA_TRY(cudaEventRecord(t->ev_pref_free, t->stream));
+            t->pref_free_pending = true;
+            return UB_OK;
+        }
+    }
     if (sync_call && !t_host && !noise_host && is_pinned_host(x0_host)) {
         CUDA_TRY(cudaMemcpyAsync(t->x0, x0_host, img * sizeof(float), cudaMemcpyHostToDevice, t->stream));
         return UB_OK;
@@ -1697,6 +1723,34 @@ static int stage_inputs(UbTrainer* t, const float* x0_host, const float* t_host,
     }
     CUDA_TRY(cudaEventRecord(t->ev_stage[k], t->stream));
     t->stage_used[k] = true;
+    return UB_OK;
+}
+
+// Enqueue the H2D copy of the announced next batch on the copy stream (page-locked sources only: a pageable source
+// would make the copy synchronous with the host).  Called right after the current step has been launched.
+static int start_prefetch(UbTrainer* t) {
+    const float* src = t->next_hint;
+    t->next_hint = nullptr;
+    if (!src || !is_pinned_host(src)) return UB_OK;
+    const UbConfig& c = t->cfg;
+    const size_t img = size_t(c.B) * c.C_in * c.H * c.W;
+    if (!t->x0_pref) {
+        CUDA_TRY(cudaMalloc(&t->x0_pref, img * sizeof(float)));
+        CUDA_TRY(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&t->ev_pref, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&t->ev_pref_free, cudaEventDisableTiming));
+    }
+    if (t->pref_free_pending) CUDA_TRY(cudaStreamWaitEvent(t->copy_stream, t->ev_pref_free, 0));
+    t->pref_free_pending = false;
+    CUDA_TRY(cudaMemcpyAsync(t->x0_pref, src, img * sizeof(float), cudaMemcpyHostToDevice, t->copy_stream));
+    CUDA_TRY(cudaEventRecord(t->ev_pref, t->copy_stream));
+    t->pref_src = src;
+    return UB_OK;
+}
+
+extern "C" int ub_trainer_set_next_batch(UbTrainer* t, const float* next_x0_host) {
+    if (!t) return UB_ERR_STATE;
+    t->next_hint = next_x0_host;
     return UB_OK;
 }
 
@@ -1749,7 +1803,11 @@ static int launch_step(UbTrainer* t, const StepOpts& o) {
     const bool same = t->graph_valid && t->graph_gen_t == o.gen_t && t->graph_gen_noise == o.gen_noise;
     {
         const float hp[5] = {o.lr, o.b1, o.b2, o.eps, o.wd};  // pageable source: staged by the driver before the call returns
-        CUDA_TRY(cudaMemcpyAsync(t->hp_dev, hp, sizeof hp, cudaMemcpyHostToDevice, t->stream));
+        if (!same || !t->hp_uploaded || memcmp(hp, t->hp_last, sizeof hp) != 0) {
+            CUDA_TRY(cudaMemcpyAsync(t->hp_dev, hp, sizeof hp, cudaMemcpyHostToDevice, t->stream));
+            memcpy(t->hp_last, hp, sizeof hp);
+            t->hp_uploaded = true;
+        }
     }
     t->hp_active = t->hp_dev;
     if (!same) {
@@ -1789,6 +1847,7 @@ extern "C" int ub_trainer_train_step(UbTrainer* t, const float* x0_host, const f
     if (r) return r;
     t->host_step++;
     t->have_grads = false;
+    if (t->next_hint && (r = start_prefetch(t)) != UB_OK) return r;
     if (loss_out) return fetch_loss(t, loss_out);
     return UB_OK;
 }
@@ -2122,6 +2181,10 @@ extern "C" int ub_trainer_get_grads(UbTrainer* t, float* host, size_t n) {
 extern "C" int ub_trainer_get_output(UbTrainer* t, float* host, size_t n) {
     const UbConfig& c = t->cfg;
     return copy_out(t, t->out, host, n, size_t(c.B) * c.C_out * c.H * c.W);
+}
+extern "C" int ub_trainer_get_batch(UbTrainer* t, float* host, size_t n) {
+    const UbConfig& c = t->cfg;
+    return copy_out(t, t->x0, host, n, size_t(c.B) * c.C_in * c.H * c.W);
 }
 extern "C" int ub_trainer_get_dinput(UbTrainer* t, float* host, size_t n) {
     if (!t->dxt) {
