@@ -12,7 +12,7 @@ o=gpurun_out
 mkdir -p $o
 timeout 900 python -m pytest tests -m gpu -q -rs > $o/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 $o/${tag}_pytest_gpu.log
 timeout 900 python bench.py > $o/${tag}_bench.json 2> $o/${tag}_bench.err; echo "bench rc=$?"
-[ -z "$SHORT" ] && timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $o/${tag}_bench_reference_arm.json 2> $o/${tag}_bench_reference_arm.err; echo "reference arm rc=$?"
+if [ -z "$SHORT" ]; then timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $o/${tag}_bench_reference_arm.json 2> $o/${tag}_bench_reference_arm.err; echo "reference arm rc=$?"; fi
 timeout 120 python tools/profile_step.py 3 > $o/${tag}_plain.log 2>&1 || { echo "plain run failed"; cat $o/${tag}_plain.log; exit 1; }
 n=$(grep -o "launches/step [0-9]*" $o/${tag}_plain.log | awk '{print $2}'); echo "launches per eager step: $n"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s $((2 * n)) -c $n --csv \
