@@ -535,6 +535,8 @@ int main(int argc, char** argv) {
     CK(cudaGetDeviceProperties(&prop, 0));
     printf("device: %s, %d SMs, cc %d.%d\n", prop.name, prop.multiProcessorCount, prop.major, prop.minor);
 
+    const bool wgrad_only = argc > 1 && !strcmp(argv[1], "wgradonly");  // only the weight-gradient cases (timed)
+    if (wgrad_only) goto wgrad_tests;
     printf("== descriptor probe ==\n");
     run_probe();
 
@@ -585,23 +587,35 @@ int main(int argc, char** argv) {
         test_conv(32, 64, 64, 256, 256, 9, 0, OUT_NHWC_BF16, true, false, false, 20000, reps, true);
         test_conv(32, 64, 64, 512, 512, 9, 0, OUT_NHWC_BF16, true, false, false, 5000, 5, true);
     }
-    printf("== wgrad ==\n");
-    test_wgrad(2, 8, 8, 64, 64, 9, 1 << 20, 0);
-    test_wgrad(2, 16, 16, 128, 128, 9, 20000, 0);
-    test_wgrad(3, 8, 8, 64, 128, 1, 1 << 20, 0);
-    test_wgrad(2, 12, 20, 64, 64, 9, 1 << 20, 0);
-    test_wgrad(4, 16, 16, 192, 64, 9, 20000, 0);
-    if (!quick) {
-        int reps = 20;
-        test_wgrad(32, 64, 64, 64, 64, 9, 400, reps);
-        test_wgrad(32, 64, 64, 192, 64, 9, 400, reps);
-        test_wgrad(32, 32, 32, 128, 128, 9, 400, reps);
-        test_wgrad(32, 16, 16, 192, 192, 9, 1000, reps);
-        test_wgrad(32, 8, 8, 256, 256, 9, 2000, reps);
-        test_wgrad(32, 8, 8, 512, 256, 9, 2000, reps);
-        test_wgrad(32, 32, 32, 320, 128, 1, 2000, reps);
-        test_wgrad(32, 64, 64, 256, 256, 9, 200, reps);
+wgrad_tests:
+    // column mode (default for 3x3: one halo box per filter column) and row mode (UB_WGRAD_COLMODE=0: three boxes per
+    // filter row); the plan reads the variable on every call
+    for (int colmode = 1; colmode >= 0; --colmode) {
+        setenv("UB_WGRAD_COLMODE", colmode ? "1" : "0", 1);
+        printf("== wgrad, %s mode ==\n", colmode ? "column" : "row");
+        test_wgrad(2, 8, 8, 64, 64, 9, 1 << 20, 0);
+        test_wgrad(5, 8, 8, 64, 64, 9, 1 << 20, 0);     // two images per K tile, the last tile half outside the batch
+        test_wgrad(6, 8, 8, 128, 128, 9, 1 << 20, 0);
+        test_wgrad(2, 16, 16, 128, 128, 9, 20000, 0);
+        test_wgrad(3, 8, 8, 64, 128, 1, 1 << 20, 0);
+        test_wgrad(2, 12, 20, 64, 64, 9, 1 << 20, 0);
+        test_wgrad(3, 20, 12, 64, 64, 9, 1 << 20, 0);
+        test_wgrad(4, 16, 16, 192, 64, 9, 20000, 0);
+        test_wgrad(2, 32, 32, 64, 128, 9, 20000, 0);
+        if (!quick) {
+            int reps = 20;
+            test_wgrad(32, 64, 64, 64, 64, 9, 400, reps);
+            test_wgrad(32, 64, 64, 192, 64, 9, 400, reps);
+            test_wgrad(32, 64, 64, 64, 128, 9, 400, reps);
+            test_wgrad(32, 32, 32, 128, 128, 9, 400, reps);
+            test_wgrad(32, 16, 16, 192, 192, 9, 1000, reps);
+            test_wgrad(32, 8, 8, 256, 256, 9, 2000, reps);
+            test_wgrad(32, 8, 8, 512, 256, 9, 2000, reps);
+            test_wgrad(32, 32, 32, 320, 128, 1, 2000, reps);
+            test_wgrad(32, 64, 64, 256, 256, 9, 200, reps);
+        }
     }
+    unsetenv("UB_WGRAD_COLMODE");
     printf("== %s (%d failing groups) ==\n", g_fail ? "FAILED" : "ALL OK", g_fail);
     return g_fail ? 1 : 0;
 }

@@ -539,9 +539,13 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
     const int k_end = int((long long)ktiles * (split + 1) / p.nsplit);
     const int a_atoms = p.MO / 64, b_atoms = p.NC / 64;
     const uint32_t b_off = uint32_t(a_atoms) * atom;  // B region offset inside a stage
+    // Column mode (3x3 layers, see IgemmWgradParams::colmode): blockIdx.y is the filter COLUMN dx + 1 and the CTA's
+    // three taps are dy = -1, 0, +1 of that column, all read from ONE halo box of TH + 2 image rows per 64-channel atom.
+    const bool colmode = p.colmode != 0;
     // fused bias gradient: only the CTAs that own the centre tap (or the single tap) of the first Cin tile
+    // (row mode: filter row 1 holds taps 3..5; column mode: filter column 1 holds taps 1, 4, 7 -- blockIdx.y == 1 both)
     const int bias_ti = (p.ntaps == 9 ? 4 : 0) - tap0;
-    const bool do_bias = p.ones_off != 0 && c0 == 0 && bias_ti >= 0 && bias_ti < p.TC;
+    const bool do_bias = p.ones_off != 0 && c0 == 0 && (colmode ? blockIdx.y == 1 : (bias_ti >= 0 && bias_ti < p.TC));
     if (do_bias) {  // KP pixel rows x 128 B of bf16 1.0 (any swizzle of a constant tile is the same tile)
         uint4* ones = reinterpret_cast<uint4*>(smem + p.ones_off);
         for (int i = threadIdx.x; i < p.KP * 8; i += blockDim.x) ones[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
@@ -594,6 +598,11 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
                     mbar_expect_tx(&full_bar[stage], p.tx_bytes);
                     for (int a = 0; a < a_atoms; ++a)
                         tma_load_4d(sA + a * atom, &p.tmDY, &full_bar[stage], o0 + a * 64, w0, h0, b0);
+                    if (colmode) {  // one (TH + 2)-row halo box per 64-channel atom, shifted by this CTA's dx
+                        for (int nb = 0; nb < b_atoms; ++nb)
+                            tma_load_4d(sB + nb * p.hatom, &p.tmX, &full_bar[stage], c0 + nb * 64,
+                                        w0 + int(blockIdx.y) - 1, h0 - 1, b0);
+                    } else
                     for (int ti = 0; ti < p.TC; ++ti) {
                         const int tap = tap0 + ti;
                         const int dy = p.ntaps == 9 ? tap / 3 - 1 : 0;
@@ -627,6 +636,12 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
                 g_boff[ng] = (b_off + uint32_t(ti * b_atoms) * atom) >> 4;
                 g_idesc[ng] = make_idesc_bf16(p.MO, nt * p.NC, 1, 1);
             }
+            // column mode: per 64-channel atom ONE N = 192 MMA per K step -- its three 64-channel N atoms are the three dy
+            // windows of the halo box, TW pixels (one image row of the tile) apart: LBO = TW * 128 B, a multiple of the
+            // 1 KiB swizzle atom, so every window starts aligned.  Accumulator columns: [atom][dy][64 channels].
+            const uint64_t dbase_c = make_smem_desc_sw128(0, uint32_t(p.TW) * 128u, 1024);
+            const uint32_t idesc_c = make_idesc_bf16(p.MO, 192, 1, 1);
+            const uint32_t hatom16 = p.hatom >> 4, img_skip16 = uint32_t(p.TW) * 16u;  // (2 halo rows per image, in 16 B)
             const uint32_t s0 = smem_u32(smem);
             const uint32_t t_bias = tmem_base + uint32_t(p.TC * p.NC);
             int stage = 0;
@@ -644,12 +659,27 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
                             umma_bf16(t_bias, dA + uint64_t(k * 128), d_ones + uint64_t(k * 128), idesc_b,
                                       acc0 | uint32_t(k));
                     }
+                    if (colmode) {
+                        const uint64_t dB =
+                            dbase_c | uint64_t(((s0 + uint32_t(stage) * p.stage_bytes + b_off) >> 4) & 0x3FFF);
+                        for (int nb = 0; nb < b_atoms; ++nb) {
+#pragma unroll 4
+                            for (int k = 0; k < ksteps; ++k) {
+                                // K step k = pixels [16 k, 16 k + 16) of the dY tile; in the halo box every image before
+                                // it adds two rows
+                                const uint32_t xo = uint32_t(k * 128) + (uint32_t(k * 16) >> p.lg_img) * img_skip16;
+                                umma_bf16(tmem_base + uint32_t(nb * 192), dA + uint64_t(k * 128),
+                                          dB + uint64_t(uint32_t(nb) * hatom16 + xo), idesc_c, acc0 | uint32_t(k));
+                            }
+                        }
+                    } else {
 #pragma unroll 3
                     for (int g = 0; g < ng; ++g) {
 #pragma unroll 4
                         for (int k = 0; k < ksteps; ++k)
                             umma_bf16(tmem_base + g_col[g], dA + uint64_t(k * 128), dA + uint64_t(g_boff[g] + k * 128),
                                       g_idesc[g], acc0 | uint32_t(k));
+                    }
                     }
                     umma_commit(&empty_bar[stage]);
                 }
@@ -699,8 +729,10 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
                     if (elect_one_sync()) bulk_wait_group_read0();
                     __syncwarp();
                 }
+                // accumulator column of (tap ti, channel s * 32): [ti][NC] in row mode, [atom][ti][64] in column mode
+                const int tcol = colmode ? ((s >> 1) * 3 + ti) * 64 + (s & 1) * 32 : ti * p.NC + s * 32;
                 uint32_t v[32];
-                tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(ti * p.NC + s * 32), v);
+                tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(tcol), v);
                 tmem_ld_wait();
                 const uint32_t buf = wbase + uint32_t(slot) * bufbytes;
                 if (valid) {
@@ -712,7 +744,8 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (elect_one_sync()) {
-                    tma_reduce_add_2d(buf, &p.tmAcc, c0 + s * 32, (tap0 + ti) * p.Cout + o0 + q * rpw);
+                    const int tap = colmode ? 3 * ti + int(blockIdx.y) : tap0 + ti;
+                    tma_reduce_add_2d(buf, &p.tmAcc, c0 + s * 32, tap * p.Cout + o0 + q * rpw);
                     bulk_commit_group();
                 }
                 __syncwarp();
@@ -722,12 +755,13 @@ __global__ void __launch_bounds__(kWgradThreads) igemm_wgrad_kernel(const __grid
             __syncwarp();
         } else if (k_end > k_begin) {
             for (int ti = 0; ti < p.TC; ++ti) {
-                const int tap = tap0 + ti;
+                const int tap = colmode ? 3 * ti + int(blockIdx.y) : tap0 + ti;
                 float* dst = p.acc ? p.acc + (size_t(tap) * p.Cout + (o0 + row)) * p.Cin + c0
                                    : p.partial + ((size_t(split) * p.ntaps + tap) * p.Cout + (o0 + row)) * p.Cin + c0;
                 for (int cc = 0; cc < p.NC; cc += 16) {
+                    const int tcol = colmode ? ((cc >> 6) * 3 + ti) * 64 + (cc & 63) : ti * p.NC + cc;
                     uint32_t v[16];
-                    tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(ti * p.NC + cc), v);
+                    tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(tcol), v);
                     tmem_ld_wait();
                     if (valid) {
                         if (p.acc) {
@@ -1148,25 +1182,39 @@ static int wgrad_plan_common(IgemmWgradParams* p, const __nv_bfloat16* dy, int l
     // producer thread was the pacing resource at KP = 64); 64 is kept for operands whose tiles would not fit.
     static const int kp_env = getenv("UB_WGRAD_KP") ? atoi(getenv("UB_WGRAD_KP")) : 128;
     int KP = (kp_env == 64 || size_t(B) * H * W < 256) ? 64 : 128;
-    {   // two stages of the chosen tile must fit beside the epilogue's needs
-        const int mo = (Cout % 128 == 0) ? 128 : 64, nc = (Cin % 128 == 0) ? 128 : 64, tc = ntaps == 9 ? 3 : 1;
-        if (size_t(2) * (mo / 64 + tc * (nc / 64)) * 128 * 128 > size_t(160) * 1024) KP = 64;
-    }
-    p->KP = KP;
-    p->TW = next_pow2(W) < KP ? next_pow2(W) : KP;
-    p->TH = next_pow2(H) < KP / p->TW ? next_pow2(H) : KP / p->TW;
-    p->TB = KP / (p->TW * p->TH);
-    p->tiles_w = ceil_div_i(W, p->TW);
-    p->tiles_h = ceil_div_i(H, p->TH);
-    p->tiles_b = ceil_div_i(B, p->TB);
     p->MO = (Cout % 128 == 0) ? 128 : 64;
     p->TC = ntaps == 9 ? 3 : 1;
     // TMEM: TC * NC columns <= 512
     p->NC = (Cin % 128 == 0) ? 128 : 64;
+    const int a_atoms = p->MO / 64, b_atoms = p->NC / 64;
+    // Column mode (3x3 layers; UB_WGRAD_COLMODE=0 = row mode): a CTA owns a filter COLUMN and takes its three dy taps from
+    // one halo box of TH + 2 image rows per 64-channel atom instead of three boxes of TH rows -- the main loop runs at
+    // the chip-wide L2 -> shared-memory rate, so bytes are time: the activation operand shrinks to
+    // (KP + 2 TW TB) / (3 KP) = 0.67 of its size at 64x64, 0.5 at 32x32, 0.42 at 16x16 and 8x8.
+    // (halo windows must start on the 8-pixel swizzle atom: image rows of the tile >= 8 pixels, i.e. W > 4)
+    p->colmode = (ntaps == 9 && next_pow2(W) >= 8 && !(getenv("UB_WGRAD_COLMODE") && atoi(getenv("UB_WGRAD_COLMODE")) == 0)) ? 1 : 0;
+    for (;;) {
+        p->KP = KP;
+        p->TW = next_pow2(W) < KP ? next_pow2(W) : KP;
+        p->TH = next_pow2(H) < KP / p->TW ? next_pow2(H) : KP / p->TW;
+        p->TB = KP / (p->TW * p->TH);
+        p->hatom = uint32_t((p->TH + 2) * p->TW * p->TB) * 128u;  // one halo box (a multiple of 1 KiB: TW % 8 == 0)
+        p->stage_bytes = p->colmode ? uint32_t(a_atoms) * uint32_t(KP) * 128u + uint32_t(b_atoms) * p->hatom
+                                    : uint32_t(a_atoms + p->TC * b_atoms) * uint32_t(KP) * 128u;
+        // two stages of the chosen tile must fit beside the epilogue's needs
+        if (KP == 128 && size_t(2) * p->stage_bytes > size_t(160) * 1024) {
+            KP = 64;
+            continue;
+        }
+        break;
+    }
+    p->lg_img = 0;
+    while ((1 << p->lg_img) < p->TW * p->TH) ++p->lg_img;
+    p->tiles_w = ceil_div_i(W, p->TW);
+    p->tiles_h = ceil_div_i(H, p->TH);
+    p->tiles_b = ceil_div_i(B, p->TB);
     p->tmem_cols = next_pow2(p->TC * p->NC + (bias ? 16 : 0) < 32 ? 32 : p->TC * p->NC + (bias ? 16 : 0));
     if (p->tmem_cols > 512) return -3;
-    const int a_atoms = p->MO / 64, b_atoms = p->NC / 64;
-    p->stage_bytes = uint32_t(a_atoms + p->TC * b_atoms) * uint32_t(KP) * 128u;
     p->tx_bytes = p->stage_bytes;
     static const unsigned smem_kb = getenv("UB_WGRAD_SMEM_KB") ? unsigned(atoi(getenv("UB_WGRAD_SMEM_KB"))) : 96u;
     int stages = int((smem_kb * 1024u) / p->stage_bytes);
@@ -1197,7 +1245,7 @@ static int wgrad_plan_common(IgemmWgradParams* p, const __nv_bfloat16* dy, int l
     if (bias) p->ones_off = uint32_t(p->stages) * p->stage_bytes;
     int r = make_act_map(&p->tmDY, dy, Cout, ldy, W, H, B, p->TW, p->TH, p->TB);
     if (r) return r;
-    r = make_act_map(&p->tmX, x, Cin, ldx, W, H, B, p->TW, p->TH, p->TB);
+    r = make_act_map(&p->tmX, x, Cin, ldx, W, H, B, p->TW, p->colmode ? p->TH + 2 : p->TH, p->TB);
     return r;
 }
 

@@ -134,6 +134,11 @@ struct IgemmWgradParams {
     int KP;      // pixels per K tile (= per stage): 64 or 128; an operand atom is KP rows of 128 B
     int stages;
     int nprod;   // TMA producer warps: 2 = the first epilogue warp loads the odd K tiles (even ring only)
+    // column mode (3x3): blockIdx.y = filter column; the three dy taps come from one halo box (64, TW, TH + 2, TB) per
+    // 64-channel atom of X (tmX then has that box), hatom bytes each; accumulator columns [atom][dy][64]
+    int colmode;
+    uint32_t hatom;
+    int lg_img;  // log2(TW * TH): pixels of one image inside a K tile
     int tmem_cols;
     uint32_t stage_bytes, tx_bytes;
     float* partial;  // [nsplit][ntaps][Cout][Cin] fp32 (two-pass mode: igemm_wgrad_reduce sums the splits)
