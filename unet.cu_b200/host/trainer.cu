@@ -185,7 +185,7 @@ struct UbTrainer {
     bool pref_free_pending = false;
     float hp_last[5] = {0, 0, 0, 0, 0};  // what hp_dev holds (uploaded again only when a value changes)
     bool hp_uploaded = false;
-    // scratch of the 3-channel weight-gradient fallback kernels (the tcgen05 wgrads accumulate with REDs, no workspace)
+    // scratch of the 3-channel weight-gradient fallback kernels (the tcgen05 wgrads accumulate with TMA reduce-adds, no workspace)
     float* small_scratch = nullptr;
     size_t small_scratch_floats = size_t(1) << 20;
     // tables (device)
