@@ -338,13 +338,15 @@ int ub_trainer_sample(UbTrainer* t, const float* x_init_host, int t_start, int t
 
 /* ---- dataset reader: prepare_data.py:20-38 format (int32[256] header {20240620, N, C, H, W} + float32 images),
  * semantics of DataLoader / dataloader_next_batch (train_unet.cu:3035-3099): sequential batches of B images,
- * wrapping to the start when fewer than B images remain.  Batches are prefetched by a background thread into two
- * page-locked buffers, so the returned pointer can be handed to ub_trainer_train_step directly (async H2D).
+ * wrapping to the start when fewer than B images remain.  Batches are prefetched by a background thread into three
+ * page-locked buffers, so the returned pointer can be handed to ub_trainer_train_step directly (async H2D), and the
+ * batch of one call stays intact through the NEXT call: the caller can hold the current batch and the following one
+ * (ub_trainer_set_next_batch) at the same time.
  * Data parallel: rank r of `world` reads global batches r, r + world, ... (each global step consumes world batches). */
 typedef struct UbDataLoader UbDataLoader;
 int ub_dataloader_open(UbDataLoader** out, const char* path, int B, int rank, int world);
 int ub_dataloader_info(UbDataLoader* d, int* n_imgs, int* C, int* H, int* W, long long* batches_per_epoch);
-const float* ub_dataloader_next(UbDataLoader* d);  /* valid until the next call; NULL on I/O error */
+const float* ub_dataloader_next(UbDataLoader* d);  /* valid until the call after the next one; NULL on I/O error */
 void ub_dataloader_reset(UbDataLoader* d);
 void ub_dataloader_close(UbDataLoader* d);
 

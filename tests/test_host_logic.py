@@ -78,6 +78,20 @@ def test_dataloader_batches_wrap_and_rank_striding(ub, oracle, tmp_path):
         np.testing.assert_array_equal(dl.next(), imgs[(k % 2) * 4:(k % 2) * 4 + 4])
     dl.reset()
     np.testing.assert_array_equal(dl.next(), imgs[0:4])
+    # three buffers: the batch of one call stays intact through the next call (current + announced next batch, the
+    # pattern ub_trainer_set_next_batch needs), and is recycled by the call after that
+    import ctypes as C
+    n = 4 * 3 * 8 * 8
+    view = lambda p: np.frombuffer((C.c_float * n).from_address(p), dtype=np.float32).reshape(4, 3, 8, 8)
+    p1 = dl.next_ptr()                                                 # batch 1
+    keep1 = view(p1).copy()
+    p2 = dl.next_ptr()                                                 # batch 0 (wrapped), another buffer
+    assert p2 != p1
+    np.testing.assert_array_equal(view(p1), keep1)
+    np.testing.assert_array_equal(view(p2), imgs[0:4])
+    p3 = dl.next_ptr()
+    assert p3 not in (p1, p2)
+    np.testing.assert_array_equal(view(p2), imgs[0:4])
     dl.close()
     imgs = rng.uniform(-1, 1, (24, 1, 4, 4)).astype(np.float32)        # 6 batches of 4, two ranks
     oracle.write_data_bin(path, imgs)

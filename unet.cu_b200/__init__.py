@@ -317,7 +317,7 @@ class DataLoader:
         self.B, self.n_imgs, self.shape, self.batches_per_epoch = B, n.value, (c.value, h.value, w.value), nb.value
 
     def next_ptr(self) -> int:
-        """Address of the (page-locked) buffer holding the next batch; valid until the following call."""
+        """Address of the (page-locked) buffer holding the next batch; valid until the call after the following one."""
         p = lib().ub_dataloader_next(self._h)
         if not p:
             raise UbError("ub_dataloader_next failed: " + lib().ub_last_error().decode())

@@ -2,8 +2,10 @@
 // {20240620, N, C, H, W} followed by N*C*H*W float32 in [-1, 1]) with the batching semantics of the reference's
 // DataLoader (train_unet.cu:3035-3099): sequential batches of B images, wrap to the start when fewer than B remain.
 // Unlike the reference (a blocking fread into one pinned buffer inside the training loop, train_unet.cu:5021-5023) the
-// next batch is read by a background thread into the second of two page-locked buffers while the GPU trains on the
-// first.  Data parallel: rank r reads global batches r, r + world, r + 2 world, ...
+// next batch is read by a background thread into another of THREE page-locked buffers while the GPU trains on the
+// current one.  Three, not two: the batch returned by a call stays intact until the call AFTER the next one, so the
+// caller can hold the current batch and the next one at the same time -- what ub_trainer_set_next_batch needs (the next
+// batch's H2D copy runs under the current step).  Data parallel: rank r reads global batches r, r + world, r + 2 world, ...
 #include <cuda_runtime.h>
 
 #include <condition_variable>
@@ -23,7 +25,8 @@ struct UbDataLoader {
     size_t img_floats = 0;
     long long batches_per_epoch = 0;  // floor(N / B), as the reference's num_batches
     long long next_global = 0;        // index of the next global batch this rank will read (before wrapping)
-    float* buf[2] = {nullptr, nullptr};
+    static constexpr int kSlots = 3;
+    float* buf[kSlots] = {nullptr, nullptr, nullptr};
     bool pinned = false;
     int cur = 0;  // buffer handed to the caller last
     // prefetch thread
@@ -99,16 +102,20 @@ extern "C" int ub_dataloader_open(UbDataLoader** out, const char* path, int B, i
     const size_t bytes = size_t(B) * d->img_floats * sizeof(float);
     // page-locked when a CUDA device is there (async H2D), plain aligned memory otherwise (CPU-only tests)
     int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0 && cudaMallocHost(&d->buf[0], bytes) == cudaSuccess &&
-        cudaMallocHost(&d->buf[1], bytes) == cudaSuccess) {
+    if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
         d->pinned = true;
-    } else {
-        cudaGetLastError();
-        if (d->buf[0]) cudaFreeHost(d->buf[0]), d->buf[0] = nullptr;
-        d->buf[0] = static_cast<float*>(aligned_alloc(4096, (bytes + 4095) & ~size_t(4095)));
-        d->buf[1] = static_cast<float*>(aligned_alloc(4096, (bytes + 4095) & ~size_t(4095)));
+        for (int k = 0; k < UbDataLoader::kSlots; ++k)
+            if (cudaMallocHost(&d->buf[k], bytes) != cudaSuccess) d->pinned = false, d->buf[k] = nullptr;
+        if (!d->pinned)
+            for (int k = 0; k < UbDataLoader::kSlots; ++k)
+                if (d->buf[k]) cudaFreeHost(d->buf[k]), d->buf[k] = nullptr;
     }
-    if (!d->buf[0] || !d->buf[1]) {
+    if (!d->pinned) {
+        cudaGetLastError();
+        for (int k = 0; k < UbDataLoader::kSlots; ++k)
+            d->buf[k] = static_cast<float*>(aligned_alloc(4096, (bytes + 4095) & ~size_t(4095)));
+    }
+    if (!d->buf[0] || !d->buf[1] || !d->buf[2]) {
         ub_dataloader_close(d);
         ub_host_set_error("dataloader: out of host memory");
         return UB_ERR_IO;
@@ -117,7 +124,7 @@ extern "C" int ub_dataloader_open(UbDataLoader** out, const char* path, int B, i
     d->worker = std::thread(worker_main, d);
     {
         std::lock_guard<std::mutex> lk(d->mu);
-        d->cur = 1;  // so that the first batch lands in buffer 0
+        d->cur = UbDataLoader::kSlots - 1;  // so that the first batch lands in buffer 0
         request(d, 0, d->next_global);
     }
     *out = d;
@@ -142,7 +149,8 @@ extern "C" const float* ub_dataloader_next(UbDataLoader* d) {
     }
     d->cur = d->fill;
     d->next_global += d->world;
-    request(d, d->cur ^ 1, d->next_global);  // prefetch the following batch into the other buffer
+    // prefetch the following batch into the buffer handed out two calls ago (the previous one stays intact)
+    request(d, (d->cur + 1) % UbDataLoader::kSlots, d->next_global);
     return d->buf[d->cur];
 }
 
@@ -150,7 +158,7 @@ extern "C" void ub_dataloader_reset(UbDataLoader* d) {
     std::unique_lock<std::mutex> lk(d->mu);
     d->cv.wait(lk, [&] { return d->ready; });  // let the in-flight read finish
     d->next_global = d->rank;
-    request(d, d->cur ^ 1, d->next_global);
+    request(d, (d->cur + 1) % UbDataLoader::kSlots, d->next_global);
 }
 
 extern "C" void ub_dataloader_close(UbDataLoader* d) {
